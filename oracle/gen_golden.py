@@ -1,0 +1,255 @@
+"""TEST INFRASTRUCTURE ONLY.  Generates ``tests/golden/*.npz`` by running the reference's
+own, unmodified model files (imported from /root/reference through ``oracle/freerec_shim``)
+on small seeded inputs, and recording the tensors that cross the hot-path boundary:
+
+    U (query rows), W (item table view), bias, labels  ->  scores / loss / dU / dW / dbias
+    gather indices + upstream grad                     ->  embedding-table gradient
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python oracle/gen_golden.py
+
+The reference code is *instrumented from outside* (forward hooks / wrapper around
+``encode``), never edited.
+"""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+from oracle import freerec_shim as shim  # noqa: E402
+
+OUT = ROOT / "tests" / "golden"
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _seqs(g, B, S, N, pads=1, min_len=1):
+    """Left-padded item sequences with ids offset by NUM_PADS (lpad_, SASRec/main.py:150-154)."""
+    lens = torch.randint(min_len, S + 1, (B,), generator=g)
+    seq = torch.zeros(B, S, dtype=torch.long)
+    for b in range(B):
+        L = int(lens[b])
+        seq[b, S - L:] = torch.randint(0, N, (L,), generator=g) + pads
+    return seq
+
+
+def _capture_encode(model):
+    """Wrap model.encode so its outputs are cached with retain_grad (no source edits)."""
+    cache = {}
+    orig = model.encode
+
+    def wrapped(*a, **k):
+        out = orig(*a, **k)
+        outs = out if isinstance(out, tuple) else (out,)
+        for o in outs:
+            if o.requires_grad and not o.is_leaf:
+                o.retain_grad()
+        cache["out"] = outs
+        return out
+
+    model.encode = wrapped
+    return cache
+
+
+def gen_sasrec():
+    N, d, B, S = 300, 64, 16, 12
+    torch.manual_seed(2026)
+    ref = shim.load_reference("SASRec", loss="CE", embedding_dim=d, maxlen=S, dropout_rate=0.0)
+    ds = shim.RecDataSet(n_users=B, n_items=N)
+    model = ref.SASRec(ds)
+    g = torch.Generator().manual_seed(11)
+    ISeq = _seqs(g, B, S, N)
+    IPos = torch.randint(0, N, (B, S), generator=g)
+    IPos[ISeq == 0] = 0
+    data = {model.ISeq: ISeq, model.IPos: IPos}
+
+    cache = _capture_encode(model)
+    model.train()
+    loss = model(data)["rec_loss"]
+    userEmbds, itemEmbds = cache["out"]
+    loss.backward()
+    indices = ISeq != 0
+    U = userEmbds[indices]
+    dU = userEmbds.grad[indices]
+    dTable = model.Item.embeddings.weight.grad
+    labels = IPos[indices]
+
+    model.eval()
+    with torch.no_grad():
+        scores = model(data, ranking="full")
+        uE, iE = model.encode(data)
+    np.savez_compressed(
+        OUT / "sasrec_ce.npz",
+        ISeq=_np(ISeq), IPos=_np(IPos), U=_np(U), W=_np(itemEmbds), labels=_np(labels),
+        loss=_np(loss), dU=_np(dU), dTable_total=_np(dTable),
+        table=_np(model.Item.embeddings.weight),
+        U_eval=_np(uE[:, -1, :]), scores_full=_np(scores),
+    )
+    print("sasrec_ce: loss", loss.item(), "M", U.shape[0])
+
+
+def gen_gru4rec():
+    N, d, B, S = 257, 64, 24, 10
+    torch.manual_seed(2027)
+    ref = shim.load_reference("GRU4Rec", loss="CE", embedding_dim=d, maxlen=S)
+    ds = shim.RecDataSet(n_users=B, n_items=N)
+    model = ref.GRU4Rec(ds)
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    g = torch.Generator().manual_seed(12)
+    ISeq = _seqs(g, B, S, N)
+    IPos = torch.randint(0, N, (B, 1), generator=g)
+    INeg = torch.randint(0, N, (B, 1), generator=g)
+    data = {model.ISeq: ISeq, model.IPos: IPos, model.INeg: INeg}
+    cache = _capture_encode(model)
+    model.train()
+    loss = model(data)["rec_loss"]
+    loss.backward()
+    userEmbds, itemEmbds = cache["out"]
+    model.eval()
+    with torch.no_grad():
+        scores = model(data, ranking="full")
+        uE, _ = model.encode(data)
+    np.savez_compressed(
+        OUT / "gru4rec_ce.npz",
+        U=_np(userEmbds), W=_np(itemEmbds), labels=_np(IPos.flatten()), loss=_np(loss),
+        dU=_np(userEmbds.grad), U_eval=_np(uE), scores_full=_np(scores),
+    )
+    print("gru4rec_ce: loss", loss.item())
+
+
+def gen_bert4rec():
+    N, d, B, S = 203, 64, 12, 16
+    torch.manual_seed(2028)
+    ref = shim.load_reference(
+        "BERT4Rec", embedding_dim=d, maxlen=S, dropout_rate=0.0, num_heads=2, num_blocks=1
+    )
+    ds = shim.RecDataSet(n_users=B, n_items=N)
+    model = ref.BERT4Rec(ds)
+    with torch.no_grad():  # non-zero bias so the bias path is really exercised
+        model.fc.bias.normal_(0.0, 0.1)
+        model.fc.weight.mul_(20.0)
+    g = torch.Generator().manual_seed(13)
+    ISeq = _seqs(g, B, S, N, pads=2, min_len=4)
+    data = {model.ISeq: ISeq.clone()}
+    cache = _capture_encode(model)
+    captured = {}
+    orig_mask = model.random_mask
+
+    def mask_wrapped(*a, **k):
+        out = orig_mask(*a, **k)
+        captured["masked_seqs"], captured["labels"], captured["masks"] = out
+        return out
+
+    model.random_mask = mask_wrapped
+    model.train()
+    loss = model(data)["rec_loss"]
+    loss.backward()
+    (userEmbds,) = cache["out"]
+    masks = captured["masks"]
+    np.savez_compressed(
+        OUT / "bert4rec_ce.npz",
+        U=_np(userEmbds[masks]), W=_np(model.fc.weight), bias=_np(model.fc.bias),
+        labels=_np(captured["labels"]), loss=_np(loss), dU=_np(userEmbds.grad[masks]),
+        dW=_np(model.fc.weight.grad), dbias=_np(model.fc.bias.grad),
+    )
+    model.eval()
+    with torch.no_grad():
+        data = {model.ISeq: ISeq.clone()}
+        scores = model(data, ranking="full")
+        uE = model.encode(data)[:, -1, :]
+    np.savez_compressed(
+        OUT / "bert4rec_full.npz",
+        U=_np(uE), W=_np(model.fc.weight), bias=_np(model.fc.bias), scores_full=_np(scores),
+        num_pads=np.int64(2),
+    )
+    print("bert4rec_ce: loss", loss.item(), "M", int(masks.sum()))
+
+
+def gen_mf_lightgcn():
+    U_, N, d, B = 96, 411, 64, 32
+    for name, cls in (("MF-BPR", "MF"), ("LightGCN", "LightGCN")):
+        torch.manual_seed(2029)
+        ref = shim.load_reference(name, embedding_dim=d)
+        ds = shim.RecDataSet(n_users=U_, n_items=N)
+        model = getattr(ref, cls)(ds)
+        with torch.no_grad():
+            model.User.embeddings.weight.normal_(0, 0.3)
+            model.Item.embeddings.weight.normal_(0, 0.3)
+        model.eval()
+        g = torch.Generator().manual_seed(14)
+        users = torch.randperm(U_, generator=g)[:B].unsqueeze(1)
+        with torch.no_grad():
+            model.reset_ranking_buffers()
+            scores = model({model.User: users}, ranking="full")
+        np.savez_compressed(
+            OUT / f"{cls.lower()}_full.npz",
+            users=_np(users), user_table=_np(model.ranking_buffer[model.User]),
+            item_table=_np(model.ranking_buffer[model.Item]), scores_full=_np(scores),
+        )
+        print(f"{cls}_full: scores", tuple(scores.shape))
+
+
+def gen_hstu():
+    N, d, B, S = 222, 64, 8, 12
+    torch.manual_seed(2030)
+    ref = shim.load_reference("HSTU", embedding_dim=d, maxlen=S)
+    ds = shim.RecDataSet(n_users=B, n_items=N)
+    model = ref.HSTU(ds)
+    model.eval()
+    g = torch.Generator().manual_seed(15)
+    ISeq = _seqs(g, B, S, N, min_len=S)
+    Time = torch.sort(torch.randint(0, 10_000_000, (B, S), generator=g), dim=1).values
+    data = {model.ISeq: ISeq, model.Time: Time}
+    with torch.no_grad():
+        scores = model(data, ranking="full")
+        uE, iE = model.encode(data)
+    np.savez_compressed(
+        OUT / "hstu_full.npz", U=_np(uE[:, -1, :]), W=_np(iE), scores_full=_np(scores),
+        table=_np(model.Item.embeddings.weight),
+    )
+    print("hstu_full: scores", tuple(scores.shape))
+
+
+def gen_gather_backward():
+    """nn.Embedding(padding_idx=0) forward/backward exactly as the reference instantiates it
+    (SASRec/main.py:70-77,183) with duplicate and pad ids."""
+    torch.manual_seed(2031)
+    N, d = 97, 32
+    emb = torch.nn.Embedding(N + 1, d, padding_idx=0)
+    g = torch.Generator().manual_seed(16)
+    idx = torch.randint(0, 12, (9, 7), generator=g)  # few distinct ids => many duplicates
+    idx[0, :3] = 0
+    out = emb(idx)
+    go = torch.randn(out.shape, generator=g)
+    out.backward(go)
+    np.savez_compressed(
+        OUT / "embedding_bwd.npz", table=_np(emb.weight), idx=_np(idx), out=_np(out),
+        grad_out=_np(go), grad_table=_np(emb.weight.grad),
+    )
+    print("embedding_bwd ok")
+
+
+def main():
+    OUT.mkdir(parents=True, exist_ok=True)
+    torch.set_num_threads(1)  # deterministic summation order for the committed vectors
+    gen_sasrec()
+    gen_gru4rec()
+    gen_bert4rec()
+    gen_mf_lightgcn()
+    gen_hstu()
+    gen_gather_backward()
+
+
+if __name__ == "__main__":
+    main()

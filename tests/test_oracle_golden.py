@@ -1,0 +1,130 @@
+"""Pins the CPU oracle (oracle/reference_path.py) against golden vectors produced by the
+reference's own unmodified model files (oracle/gen_golden.py -> tests/golden/*.npz)."""
+import numpy as np
+import torch
+
+from oracle import reference_path as orc
+
+T = torch.from_numpy
+
+
+def close(a, b, rtol=1e-5, atol=None):
+    a, b = torch.as_tensor(a).float(), torch.as_tensor(b).float()
+    if atol is None:
+        atol = rtol * float(b.abs().max().clamp_min(1e-30))
+    torch.testing.assert_close(a, b, rtol=rtol, atol=atol)
+
+
+def test_sasrec_ce_loss_and_grads(golden):
+    g = golden("sasrec_ce")
+    loss, dU, dW, _ = orc.ce_fwd_bwd(T(g["U"]), T(g["W"]), T(g["labels"]))
+    close(loss, g["loss"])
+    close(dU, g["dU"])
+    # table grad = CE dW (rows 1..N) + gather backward of the encoder path; the CE part alone
+    # must reproduce the rows no sequence position touches
+    touched = np.unique(g["ISeq"])
+    untouched = np.setdiff1d(np.arange(g["table"].shape[0]), touched)
+    close(dW[untouched - 1], g["dTable_total"][untouched])
+    assert np.all(g["dTable_total"][0] == 0.0)  # padding_idx row (SASRec/main.py:75)
+
+
+def test_sasrec_full_scores(golden):
+    g = golden("sasrec_ce")
+    close(orc.score_dense(T(g["U_eval"]), T(g["W"])), g["scores_full"])
+
+
+def test_gru4rec(golden):
+    g = golden("gru4rec_ce")
+    loss, dU, _, _ = orc.ce_fwd_bwd(T(g["U"]), T(g["W"]), T(g["labels"]))
+    close(loss, g["loss"])
+    close(dU, g["dU"])
+    close(orc.score_dense(T(g["U_eval"]), T(g["W"])), g["scores_full"])
+
+
+def test_bert4rec_bias_path(golden):
+    g = golden("bert4rec_ce")
+    loss, dU, dW, db = orc.ce_fwd_bwd(T(g["U"]), T(g["W"]), T(g["labels"]), bias=T(g["bias"]))
+    close(loss, g["loss"])
+    close(dU, g["dU"])
+    close(dW, g["dW"])
+    close(db, g["dbias"])
+    f = golden("bert4rec_full")
+    s = orc.score_dense(T(f["U"]), T(f["W"]), bias=T(f["bias"]))[:, int(f["num_pads"]):]
+    close(s, f["scores_full"])
+
+
+def test_mf_lightgcn_full(golden):
+    for name in ("mf_full", "lightgcn_full"):
+        g = golden(name)
+        U = T(g["user_table"])[T(g["users"]).squeeze(1)]
+        close(orc.score_dense(U, T(g["item_table"])), g["scores_full"])
+
+
+def test_hstu_cosine(golden):
+    g = golden("hstu_full")
+    close(orc.score_dense(T(g["U"]), T(g["W"])), g["scores_full"])
+    W = torch.nn.functional.normalize(T(g["table"])[1:], dim=-1)
+    close(W, g["W"])
+
+
+def test_embedding_forward_backward(golden):
+    g = golden("embedding_bwd")
+    close(orc.gather_rows(T(g["table"]), T(g["idx"])), g["out"], rtol=0, atol=0)
+    close(orc.scatter_add_rows(T(g["grad_out"]), T(g["idx"]), g["table"].shape[0], 0), g["grad_table"])
+
+
+def test_rowstats_merge_equals_unsharded(golden):
+    g = golden("sasrec_ce")
+    U, W, lab = T(g["U"]), T(g["W"]), T(g["labels"])
+    m, l, ll = orc.ce_rowstats(U, W, lab)
+    bounds = [0, 77, 150, 151, W.shape[0]]
+    parts = []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        S = orc.score_dense(U, W[a:b])
+        pm = S.max(1).values
+        pl = torch.exp(S - pm[:, None]).sum(1)
+        inside = (lab >= a) & (lab < b)
+        pll = torch.where(inside, S.gather(1, (lab - a).clamp(0, b - a - 1)[:, None]).squeeze(1), torch.zeros(len(lab)))
+        parts.append((pm, pl, pll))
+    lse, ll2 = orc.merge_rowstats(parts)
+    close(lse, m + torch.log(l), rtol=1e-6)
+    close(ll2, ll, rtol=0, atol=0)
+    close((lse - ll2).mean(), g["loss"])
+
+
+def test_metrics_hand_cases():
+    # 1 row, 6 items; target item 3 is ranked 2nd after masking item 0
+    scores = torch.tensor([[9.0, 1.0, 5.0, 4.0, 0.5, 0.1]])
+    crow, col = orc.lists_to_csr([[0]])
+    tcrow, tcol = orc.lists_to_csr([[3]])
+    r = orc.evaluate_batch(scores, crow, col, tcrow, tcol, ["HITRATE@1", "HITRATE@2", "NDCG@2", "NDCG@5", "MRR@5", "RECALL@2", "PRECISION@2"])
+    assert r["HITRATE@1"] == 0.0 and r["HITRATE@2"] == 1.0
+    assert abs(r["NDCG@2"] - 1 / np.log2(3)) < 1e-7 and abs(r["NDCG@5"] - 1 / np.log2(3)) < 1e-7
+    assert abs(r["MRR@5"] - 0.5) < 1e-7 and r["RECALL@2"] == 1.0 and r["PRECISION@2"] == 0.5
+    # a seen target can never be hit (mask precedes ranking, UniSRec/main.py:413)
+    crow, col = orc.lists_to_csr([[0, 3]])
+    r = orc.evaluate_batch(scores, crow, col, tcrow, tcol, ["HITRATE@5"])
+    assert r["HITRATE@5"] == 0.0
+
+
+def test_topk_tie_policy_and_topk_metrics_agree():
+    g = torch.Generator().manual_seed(3)
+    scores = torch.randint(0, 6, (17, 40), generator=g).float()  # many ties
+    seen = [sorted(set(torch.randint(0, 40, (5,), generator=g).tolist())) for _ in range(17)]
+    tgt = [[int(torch.randint(0, 40, (1,), generator=g))] for _ in range(17)]
+    crow, col = orc.lists_to_csr(seen)
+    tcrow, tcol = orc.lists_to_csr(tgt)
+    mons = ["HITRATE@1", "HITRATE@5", "HITRATE@10", "NDCG@5", "NDCG@10", "MRR@10", "RECALL@10"]
+    dense = orc.evaluate_batch(scores, crow, col, tcrow, tcol, mons)
+    vals, ids = orc.topk_sorted(orc.mask_seen(scores, crow, col), 10)
+    assert torch.all(vals[:, :-1] >= vals[:, 1:])
+    same = vals[:, :-1] == vals[:, 1:]
+    assert torch.all(ids[:, :-1][same] < ids[:, 1:][same])
+    assert orc.metrics_from_topk(ids, tcrow, tcol, 40, mons) == dense
+    # sharded top-k merge == global
+    parts = []
+    for a, b in ((0, 13), (13, 14), (14, 40)):
+        v, i = orc.topk_sorted(orc.mask_seen(scores, crow, col)[:, a:b], min(10, b - a))
+        parts.append((v, i + a))
+    mv, mi = orc.merge_topk(parts, 10)
+    assert torch.equal(mi, ids) and torch.equal(mv, vals)
