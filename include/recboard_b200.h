@@ -1,0 +1,111 @@
+/* recboard_b200 -- C ABI of the B200-native full-catalog scoring path.
+ *
+ * The reference (MTandHJ/RecBoard) has no FFI layer: its hot path is a handful of PyTorch
+ * lines repeated in every model file.  Each entry point below names the reference lines it
+ * replaces (paths relative to the reference root); INTEGRATION.md shows the Python binding a
+ * RecBoard maintainer adds (ctypes, recboard_b200/_lib.py).
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers owned by the caller (PyTorch); kernels never allocate,
+ *     free or retain them.  All work is enqueued on `stream`; no host synchronisation inside.
+ *   - Return value: 0 = ok, <0 = argument error (RB_E_*), >0 = cudaError_t.  Nothing throws or
+ *     exits; rb_last_error() returns a thread-local message for the last failure.
+ *   - dtype: storage type of U / W / table.  mode: arithmetic of the contraction.
+ *   - Matrices are row-major and contiguous: U (M,d), W (N,d) ("TN" GEMM, both K-major).
+ *   - d must be a multiple of 8; bf16 mode supports d <= 256 (CE backward: d <= 128),
+ *     fp32x3 mode supports d <= 64.  Base pointers must be 16-byte aligned.
+ *   - There is no CPU fallback: without a CUDA device every compute entry returns an error.
+ */
+#ifndef RECBOARD_B200_H
+#define RECBOARD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* rb_stream_t; /* == cudaStream_t */
+
+enum { RB_DTYPE_F32 = 0, RB_DTYPE_BF16 = 1 };
+enum { RB_MODE_BF16 = 0,   /* bf16 operands, fp32 accumulate (tcgen05 kind::f16)               */
+       RB_MODE_FP32X3 = 1  /* fp32 operands split hi/lo, 3 TF32 MMAs (error ~1e-6, "fp32 parity") */ };
+enum { RB_OP_SCATTER_ADD = 0, RB_OP_SCORE_DENSE = 1, RB_OP_CE_FWD = 2, RB_OP_CE_BWD = 3,
+       RB_OP_TOPK_EVAL = 4 };
+enum { RB_E_ARG = -1, RB_E_ALIGN = -2, RB_E_UNSUPPORTED = -3, RB_E_WORKSPACE = -4, RB_E_NODEVICE = -5 };
+
+#define RB_MASKED_SCORE (-1e23f) /* UniSRec/main.py:413 */
+
+/* out[i,:] = table[idx[i],:]                      replaces `self.Item.embeddings(seqs)`
+ * (SASRec/main.py:183, BERT4Rec/main.py:168, GRU4Rec/main.py:138, HSTU/main.py:171) and the
+ * row gathers `itemEmbds[...]`, `userEmbds[users]` (MF-BPR/main.py:84-86,102; LightGCN/main.py:91-93,118). */
+int rb_gather_rows(const void* table, const int64_t* idx, void* out, int64_t n_idx, int64_t n_rows,
+                   int d, int dtype, rb_stream_t stream);
+
+/* grad_table[idx[i],:] += grad_out[i,:], row `padding_idx` untouched (pass -1 for none).
+ * Deterministic (stable radix sort by row + in-order segment sums).  Replaces the autograd of the
+ * gather above = ATen embedding_dense_backward, triggered by `loss.backward()` (SASRec/main.py:249). */
+int rb_scatter_add_rows(const void* grad_out, const int64_t* idx, float* grad_table, int64_t n_idx,
+                        int64_t n_rows, int d, int dtype, int64_t padding_idx, void* ws,
+                        size_t ws_bytes, rb_stream_t stream);
+
+/* S = scale * U W^T + bias  (M,N) fp32.          replaces `torch.einsum("BD,ND->BN", ...)`
+ * (SASRec/main.py:228; MF-BPR/main.py:104; LightGCN/main.py:120; HSTU/main.py:209) and
+ * `self.fc(userEmbds)` (BERT4Rec/main.py:189).  Compatibility path: it materialises (M,N). */
+int rb_score_dense(const void* U, const void* W, const float* bias, float scale, float* S,
+                   int64_t M, int64_t N, int d, int dtype, int mode, void* ws, size_t ws_bytes,
+                   rb_stream_t stream);
+
+/* Per-row softmax statistics of S = scale*U W^T + bias over this shard's N items, without
+ * materialising S:  row_max[i] = max_j S_ij, row_sumexp[i] = sum_j exp(S_ij - row_max[i]),
+ * label_logit[i] = S_i,(labels[i]-label_base) if that column lies in [0,N) else 0.
+ * loss = mean(row_max + log(row_sumexp) - label_logit) replaces
+ * `einsum("MD,ND->MN")` + `self.criterion(logits, labels)` (SASRec/main.py:217-219,
+ * GRU4Rec/main.py:175-178, BERT4Rec/main.py:181-182).  Row-sharded tables: merge
+ * (max, sumexp, label_logit) across ranks. */
+int rb_ce_fwd(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
+              int64_t label_base, int64_t M, int64_t N, int d, int dtype, int mode, float* row_max,
+              float* row_sumexp, float* label_logit, void* ws, size_t ws_bytes, rb_stream_t stream);
+
+/* Gradients of grad_scale * sum_i (lse_i - S_i,label_i) given the GLOBAL lse (natural log):
+ *   dU (M,d)  = grad_scale * scale * (softmax - onehot) W      (this shard's partial; nullable)
+ *   dW (N,d)  = grad_scale * scale * (softmax - onehot)^T U    (nullable)
+ *   dbias (N) = grad_scale * column sums of (softmax - onehot) (nullable)
+ * Recomputes S tile by tile; P lives only in SMEM/TMEM.  Replaces the autograd of
+ * SASRec/main.py:217-219 run by `loss.backward()` (:249): nll_loss_backward,
+ * _log_softmax_backward_data and the two cuBLAS GEMMs. */
+int rb_ce_bwd(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
+              int64_t label_base, const float* lse, float grad_scale, int64_t M, int64_t N, int d,
+              int dtype, int mode, float* dU, float* dW, float* dbias, void* ws, size_t ws_bytes,
+              rb_stream_t stream);
+
+/* Masked full-catalog top-K: for every query row the K best (score desc, id asc) items among this
+ * shard's N items, skipping ids in the row's seen list (CSR over GLOBAL ids, sorted ascending per
+ * row; pass NULL/NULL to keep seen items).  top_ids are global (id_base + local); missing entries
+ * (fewer than K unmasked items) are (RB_MASKED_SCORE, -1).  Replaces, without a dense (B,N):
+ * `recommend_from_full` + `scores[seen] = -1e23` + one `torch.topk` per metric@k
+ * (UniSRec/main.py:408-435).  K <= 224. */
+int rb_topk_eval(const void* U, const void* W, const float* bias, float scale,
+                 const int64_t* seen_crow, const int64_t* seen_col, int64_t seen_nnz, int64_t id_base,
+                 int64_t B, int64_t N, int d, int dtype, int mode, int K, float* top_vals,
+                 int32_t* top_ids, void* ws, size_t ws_bytes, rb_stream_t stream);
+
+/* Merge R sorted per-shard lists (vals,ids)[R][B][K] into the global top-K (rb_topk_eval order). */
+int rb_topk_merge(const float* vals, const int32_t* ids, int R, int64_t B, int K, float* out_vals,
+                  int32_t* out_ids, rb_stream_t stream);
+
+/* Upper bound of the workspace an op needs (bytes). nnz = seen-list entries for RB_OP_TOPK_EVAL,
+ * number of indices for RB_OP_SCATTER_ADD, else ignored. */
+size_t rb_workspace_bytes(int op, int64_t M, int64_t N, int d, int K, int mode, int64_t nnz);
+
+/* Number of kernel launches issued by this library since load (bench.py's `gpu_launches`). */
+int64_t rb_launch_count(void);
+
+const char* rb_last_error(void);
+const char* rb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECBOARD_B200_H */

@@ -1,0 +1,147 @@
+"""Drop-in mixins behind the reference's ``RecSysArch`` / ``SeqRecArch`` / ``GenRecArch`` method
+contract (``fit(data) -> {"rec_loss": ...}``, ``recommend_from_full(data) -> Tensor[B,N]``,
+``reset_ranking_buffers()``; CONTRIBUTING.md:13-16, SASRec/main.py:143-236).
+
+A reference model keeps its ``__init__``, ``encode`` and data pipes; the mixin (listed *before* the
+freerec arch class in the bases) replaces only the hot-path lines:
+
+    class SASRecB200(SASRecFused, SASRec): pass          # SASRec from /root/reference/SASRec/main.py
+
+    fit                 lines SASRec/main.py:217-219  -> ops.fused_ce        (no (M,N) logits)
+    recommend_from_full lines SASRec/main.py:223-228  -> ops.score_dense     (strict-compat dense path)
+    recommend_topk      (new) UniSRec/main.py:408-413 -> ops.topk_eval       (mask + top-K fused)
+
+Every mixin states how the reference picks the query rows (U), the item table view (W), the labels
+and the optional bias / temperature; nothing else differs between the six models.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+
+class FusedFullCatalogMixin:
+    """Common machinery.  Subclasses implement ``_train_operands`` and ``_eval_operands``."""
+
+    #: "bf16" | "fp32" | None (None: follow the operand dtype; fp32 tensors -> 3xTF32 "fp32 parity")
+    fused_precision: Optional[str] = None
+
+    # -- hooks -------------------------------------------------------------------------
+    def _train_operands(self, data) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, Optional[torch.Tensor], float]:
+        """-> (U (M,d), W (N,d), labels (M,), bias (N,)|None, scale)"""
+        raise NotImplementedError
+
+    def _eval_operands(self, data) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor], float, int]:
+        """-> (U (B,d), W (N',d), bias|None, scale, n_skip) where the first ``n_skip`` rows of W are
+        non-item rows (BERT4Rec's pad/mask columns, BERT4Rec/main.py:189)."""
+        raise NotImplementedError
+
+    # -- RecSysArch contract ------------------------------------------------------------
+    def fit(self, data: Dict) -> Dict[str, torch.Tensor]:
+        U, W, labels, bias, scale = self._train_operands(data)
+        return {"rec_loss": ops.fused_ce(U, W, labels, bias=bias, scale=scale, precision=self.fused_precision)}
+
+    def recommend_from_full(self, data: Dict) -> torch.Tensor:
+        U, W, bias, scale, n_skip = self._eval_operands(data)
+        S = ops.score_dense(U, W, bias=bias, scale=scale, precision=self.fused_precision)
+        return S[:, n_skip:] if n_skip else S
+
+    @torch.no_grad()
+    def recommend_topk(self, data: Dict, K: int, seen_crow: Optional[torch.Tensor] = None,
+                       seen_col: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Sorted top-K (vals, item ids) per row with the row's seen items skipped -- the fused
+        stand-in for ``scores = model(data, ranking="full"); scores[seen] = -1e23; topk``
+        (UniSRec/main.py:408-413).  ``seen`` is the CSR of ``data[ISeen]`` over 0-based item ids."""
+        U, W, bias, scale, n_skip = self._eval_operands(data)
+        if n_skip:
+            W = W[n_skip:]
+            bias = bias[n_skip:].contiguous() if bias is not None else None
+        return ops.topk_eval(U, W, K, seen_crow, seen_col, bias=bias, scale=scale, precision=self.fused_precision)
+
+
+class SASRecFused(FusedFullCatalogMixin):
+    """SASRec ``--loss CE``: queries = every non-pad position, labels = IPos there
+    (SASRec/main.py:197-200,217-219); eval query = last position (:226-228)."""
+
+    def _train_operands(self, data):
+        userEmbds, itemEmbds = self.encode(data)
+        indices = data[self.ISeq] != self.PADDING_VALUE
+        return userEmbds[indices], itemEmbds, data[self.IPos][indices], None, 1.0
+
+    def _eval_operands(self, data):
+        userEmbds, itemEmbds = self.encode(data)
+        return userEmbds[:, -1, :], itemEmbds, None, 1.0, 0
+
+
+class GRU4RecFused(FusedFullCatalogMixin):
+    """GRU4Rec ``--loss CE``: one query per sequence (last valid step, GRU4Rec/main.py:143-150),
+    labels = IPos.flatten() (:174-178)."""
+
+    def _train_operands(self, data):
+        userEmbds, itemEmbds = self.encode(data)
+        return userEmbds, itemEmbds, data[self.IPos].flatten(), None, 1.0
+
+    def _eval_operands(self, data):
+        userEmbds, itemEmbds = self.encode(data)
+        return userEmbds, itemEmbds, None, 1.0, 0
+
+
+class BERT4RecFused(FusedFullCatalogMixin):
+    """BERT4Rec: ``nn.Linear(D, N+2)`` head with bias, CE over all N+2 columns at the masked
+    positions (BERT4Rec/main.py:174-184).  The reference runs the (B,S,N+2) GEMM *before* masking
+    (:181); here the masked rows are selected first and only they are scored."""
+
+    def _train_operands(self, data):
+        masked_seqs, labels, masks = self.random_mask(seqs=data[self.ISeq], p=self.mask_ratio)
+        data[self.ISeq] = masked_seqs
+        userEmbds = self.encode(data)
+        return userEmbds[masks], self.fc.weight, labels, self.fc.bias, 1.0
+
+    def _eval_operands(self, data):
+        userEmbds = self.encode(data)
+        return userEmbds[:, -1, :], self.fc.weight, self.fc.bias, 1.0, self.NUM_PADS
+
+
+class HSTUFused(FusedFullCatalogMixin):
+    """HSTU full ranking: cosine scores, both sides already L2-normalised by ``encode``
+    (HSTU/main.py:180-184,204-209).  Its ``fit`` is sampled softmax (not full-catalog) and is left
+    to the reference implementation."""
+
+    def fit(self, data):  # keep the reference's sampled-softmax fit
+        return super(FusedFullCatalogMixin, self).fit(data)
+
+    def _eval_operands(self, data):
+        userEmbds, itemEmbds = self.encode(data)
+        return userEmbds[:, -1, :], itemEmbds, None, 1.0, 0
+
+
+class GenRecFused(FusedFullCatalogMixin):
+    """MF-BPR / LightGCN family: eval queries are rows of ``ranking_buffer[User]`` picked by
+    ``data[User]`` (B,1) (MF-BPR/main.py:95-104, LightGCN/main.py:110-120).  ``fit`` (BPR on sampled
+    pairs) is not a full-catalog contraction and stays with the reference."""
+
+    def fit(self, data):
+        return super(FusedFullCatalogMixin, self).fit(data)
+
+    def reset_ranking_buffers(self):
+        super().reset_ranking_buffers()
+        # build the operand copies the fused eval wants once per sweep, not once per batch
+        self._fused_user = self.ranking_buffer[self.User].contiguous()
+        self._fused_item = self.ranking_buffer[self.Item].contiguous()
+        if self.fused_precision == "bf16":
+            self._fused_item = self._fused_item.to(torch.bfloat16)
+
+    def _eval_operands(self, data):
+        users = data[self.User]
+        U = ops.gather_rows_raw(self._fused_user, users.reshape(-1).contiguous())  # "BKD" with K == 1
+        return U, self._fused_item, None, 1.0, 0
+
+
+def normalized_table(weight: torch.Tensor, num_pads: int = 1) -> torch.Tensor:
+    """``F.normalize(weight[NUM_PADS:], dim=-1)`` (HSTU/main.py:182-184) -- helper for callers that
+    cache the normalised table across an evaluation sweep instead of recomputing it per batch."""
+    return F.normalize(weight[num_pads:], dim=-1)

@@ -1,0 +1,509 @@
+// C ABI of recboard_b200 (see include/recboard_b200.h for the contract and the reference lines
+// each entry point replaces).  Host-side planning + kernel launches only; no allocation.
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/recboard_b200.h"
+#include "simt.cuh"
+#include "sweep.cuh"
+
+using namespace rb;
+
+// ------------------------------------------------------------------------------- errors
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return static_cast<int>(e);
+}
+#define RB_CUDA(x)                                   \
+  do {                                               \
+    cudaError_t e_ = (x);                            \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #x); \
+  } while (0)
+#define RB_LAUNCH_CHECK(name)                                 \
+  do {                                                        \
+    ++g_launches;                                             \
+    cudaError_t e_ = cudaGetLastError();                      \
+    if (e_ != cudaSuccess) return cuda_fail(e_, name);        \
+  } while (0)
+
+extern "C" const char* rb_last_error(void) { return g_err.c_str(); }
+extern "C" const char* rb_version(void) { return "recboard_b200 0.1 (sm_100a)"; }
+extern "C" int64_t rb_launch_count(void) { return g_launches.load(); }
+
+// ----------------------------------------------------------------------------- device
+struct DevInfo { int ok = 0; int sms = 0; int cc = 0; };
+static int get_dev(DevInfo& d) {
+  static thread_local DevInfo cache[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(RB_E_NODEVICE, "no CUDA device: %s (there is no CPU fallback)", cudaGetErrorString(e)); }
+  if (dev < 0 || dev >= 64) return fail(RB_E_NODEVICE, "device ordinal %d out of range", dev);
+  if (!cache[dev].ok) {
+    cudaDeviceProp p;
+    RB_CUDA(cudaGetDeviceProperties(&p, dev));
+    cache[dev].sms = p.multiProcessorCount;
+    cache[dev].cc = p.major * 10 + p.minor;
+    cache[dev].ok = 1;
+  }
+  d = cache[dev];
+  if (d.cc != 100) return fail(RB_E_NODEVICE, "recboard_b200 kernels are sm_100a only; device is sm_%d", d.cc);
+  return 0;
+}
+
+// -------------------------------------------------------------------------- TMA maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// Row-major (rows, cols) matrix -> 2-D map with a (box_rows x 128-byte) box, 128-byte swizzle.
+static int make_tmap(CUtensorMap* m, const void* base, bool bf16, long long rows, long long cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(RB_E_NODEVICE, "cuTensorMapEncodeTiled not available from the driver");
+  const int es = bf16 ? 2 : 4;
+  if (reinterpret_cast<uintptr_t>(base) & 15) return fail(RB_E_ALIGN, "operand base %p is not 16-byte aligned", base);
+  if ((cols * es) % 16) return fail(RB_E_ALIGN, "row pitch %lld bytes is not a multiple of 16", cols * es);
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(cols * es)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / es), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(RB_E_ARG, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld box_rows=%d)", (int)r, rows, cols, box_rows);
+  return 0;
+}
+
+// --------------------------------------------------------------------------- planning
+constexpr int BN = 128;  // streamed tile rows
+
+struct Plan { int n_stat_tiles, n_strm_tiles, n_splits, grid; };
+
+// Work item = (stationary tile, split of the streamed range).  Pick the smallest split count that
+// fills the SMs in whole waves (>= 97 %), keeping at least `min_tiles` streamed tiles per item.
+static Plan make_plan(long long n_stat, long long n_strm, int sms, int max_splits_cap, int min_tiles = 8) {
+  Plan p;
+  p.n_stat_tiles = static_cast<int>((n_stat + 127) / 128);
+  p.n_strm_tiles = static_cast<int>((n_strm + BN - 1) / BN);
+  int max_s = std::max(1, std::min(p.n_strm_tiles / min_tiles, max_splits_cap));
+  max_s = std::min(max_s, 8 * sms);
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= max_s; ++s) {
+    const long long items = 1ll * p.n_stat_tiles * s;
+    const long long waves = (items + sms - 1) / sms;
+    const double eff = static_cast<double>(items) / static_cast<double>(waves * sms);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+    if (best_eff >= 0.97) break;
+  }
+  p.n_splits = best;
+  p.grid = static_cast<int>(std::min<long long>(1ll * p.n_stat_tiles * p.n_splits, sms));
+  return p;
+}
+
+struct Bump {
+  char* base; size_t cap; size_t off = 0;
+  Bump(void* b, size_t c) : base(static_cast<char*>(b)), cap(c) {}
+  template <typename T> T* take(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += n * sizeof(T);
+    return p;
+  }
+  bool ok() const { return off <= cap; }
+};
+
+static int kc_for(int d, int mode) {
+  const int per = (mode == RB_MODE_BF16) ? 64 : 32;
+  return (d + per - 1) / per;
+}
+static int check_common(const void* U, const void* W, long long M, long long N, int d, int dtype, int mode) {
+  if (!U || !W) return fail(RB_E_ARG, "null operand");
+  if (M <= 0 || N <= 0 || d <= 0) return fail(RB_E_ARG, "bad shape M=%lld N=%lld d=%d", M, N, d);
+  if (M >= (1ll << 31) - 256 || N >= (1ll << 31) - 256) return fail(RB_E_ARG, "M/N must be < 2^31");
+  if (d % 8) return fail(RB_E_ARG, "d=%d must be a multiple of 8", d);
+  if (mode == RB_MODE_BF16) {
+    if (dtype != RB_DTYPE_BF16) return fail(RB_E_UNSUPPORTED, "bf16 mode needs bf16 operands (cast on the host side)");
+    if (d > 256) return fail(RB_E_UNSUPPORTED, "bf16 mode supports d <= 256 (got %d)", d);
+  } else if (mode == RB_MODE_FP32X3) {
+    if (dtype != RB_DTYPE_F32) return fail(RB_E_UNSUPPORTED, "fp32x3 mode needs fp32 operands");
+    if (d > 64) return fail(RB_E_UNSUPPORTED, "fp32x3 mode supports d <= 64 (got %d)", d);
+  } else {
+    return fail(RB_E_ARG, "unknown mode %d", mode);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------- sweep dispatch
+template <class C>
+static int launch_sweep_t(const CUtensorMap& ts, const CUtensorMap& ty, const SweepArgs& a, int grid, cudaStream_t st) {
+  RB_CUDA(cudaFuncSetAttribute(sweep_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  sweep_kernel<C><<<grid, 192, C::SMEM_BYTES, st>>>(ts, ty, a);
+  RB_LAUNCH_CHECK("sweep_kernel");
+  return 0;
+}
+
+// NS chosen so that SMEM stays under 227 KB
+template <int EPI, bool ROWS, int CAPE>
+static int launch_sweep(int mode, int kc, const CUtensorMap& ts, const CUtensorMap& ty, const SweepArgs& a, int grid,
+                        cudaStream_t st) {
+  if (mode == RB_MODE_BF16) {
+    if constexpr (EPI == EPI_GRAD) {
+      if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 1, BN, 4, ROWS, CAPE>>(ts, ty, a, grid, st);
+      if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 2, BN, 3, ROWS, CAPE>>(ts, ty, a, grid, st);
+      return fail(RB_E_UNSUPPORTED, "CE backward supports d <= 128 in bf16 mode");
+    } else {
+      if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 1, BN, 6, ROWS, CAPE>>(ts, ty, a, grid, st);
+      if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 2, BN, 4, ROWS, CAPE>>(ts, ty, a, grid, st);
+      if (kc <= 4) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 4, BN, 2, ROWS, CAPE>>(ts, ty, a, grid, st);
+    }
+  } else {
+    if constexpr (EPI != EPI_GRAD) {
+      if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 1, BN, 4, ROWS, CAPE>>(ts, ty, a, grid, st);
+      if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 2, BN, 2, ROWS, CAPE>>(ts, ty, a, grid, st);
+    } else {
+      return fail(RB_E_UNSUPPORTED, "CE backward is bf16-mode only in this build");
+    }
+  }
+  return fail(RB_E_UNSUPPORTED, "unsupported feature width for mode %d (kc=%d)", mode, kc);
+}
+
+// Operand staging: bf16 operands are used in place; fp32x3 operands are split into [hi|lo] in ws.
+struct Operand { const void* ptr; long long cols; bool bf16; };
+static int stage_operand(const void* X, long long rows, int d, int mode, Bump& ws, Operand& o, cudaStream_t st) {
+  if (mode == RB_MODE_BF16) { o = {X, d, true}; return 0; }
+  const int dpad = kc_for(d, mode) * 32;
+  float* hl = ws.take<float>(static_cast<size_t>(rows) * 2 * dpad);
+  if (!ws.ok()) return fail(RB_E_WORKSPACE, "workspace too small (need > %zu bytes)", ws.off);
+  const long long total = rows * dpad;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+  split_hi_lo_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(X), hl, rows, d, dpad);
+  RB_LAUNCH_CHECK("split_hi_lo_kernel");
+  o = {hl, 2ll * dpad, false};
+  return 0;
+}
+static size_t staged_bytes(long long rows, int d, int mode) {
+  if (mode == RB_MODE_BF16) return 0;
+  return static_cast<size_t>(rows) * 2 * kc_for(d, mode) * 32 * 4 + 256;
+}
+
+// ============================================================================ gather
+extern "C" int rb_gather_rows(const void* table, const int64_t* idx, void* out, int64_t n_idx, int64_t n_rows,
+                              int d, int dtype, rb_stream_t stream) {
+  DevInfo dv; if (int r = get_dev(dv)) return r;
+  if (!table || !idx || !out) return fail(RB_E_ARG, "null pointer");
+  if (n_idx < 0 || n_rows <= 0 || d <= 0) return fail(RB_E_ARG, "bad shape");
+  const int es = dtype == RB_DTYPE_BF16 ? 2 : 4;
+  const long long row_bytes = 1ll * d * es;
+  if (row_bytes % 16) return fail(RB_E_ALIGN, "row of %lld bytes is not a multiple of 16", row_bytes);
+  if ((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(out)) & 15) return fail(RB_E_ALIGN, "table/out must be 16-byte aligned");
+  if (n_idx == 0) return 0;
+  const int vpr = static_cast<int>(row_bytes / 16);
+  const long long total = n_idx * vpr;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 1ll * dv.sms * 8));
+  gather_rows_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(table), idx, static_cast<uint4*>(out), n_idx, n_rows, vpr);
+  RB_LAUNCH_CHECK("gather_rows_kernel");
+  return 0;
+}
+
+// ======================================================================= scatter-add
+static size_t scatter_ws_bytes(long long n_idx) {
+  const long long chunks = (n_idx + RS_CHUNK - 1) / RS_CHUNK;
+  return static_cast<size_t>(n_idx) * 4 * 4 + static_cast<size_t>(chunks) * 256 * 4 + 5 * 256;
+}
+extern "C" int rb_scatter_add_rows(const void* grad_out, const int64_t* idx, float* grad_table, int64_t n_idx,
+                                   int64_t n_rows, int d, int dtype, int64_t padding_idx, void* ws, size_t ws_bytes,
+                                   rb_stream_t stream) {
+  DevInfo dv; if (int r = get_dev(dv)) return r;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!grad_out || !idx || !grad_table) return fail(RB_E_ARG, "null pointer");
+  if (n_idx < 0 || n_rows <= 0 || d <= 0 || d % 4) return fail(RB_E_ARG, "bad shape (d must be a multiple of 4)");
+  if (n_idx >= (1ll << 31) || n_rows >= (1ll << 32) - 1) return fail(RB_E_ARG, "n_idx/n_rows too large");
+  if (n_idx == 0) return 0;
+  if (!ws || ws_bytes < scatter_ws_bytes(n_idx)) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", scatter_ws_bytes(n_idx));
+  Bump b(ws, ws_bytes);
+  const int n = static_cast<int>(n_idx);
+  const int chunks = (n + RS_CHUNK - 1) / RS_CHUNK;
+  uint32_t* k0 = b.take<uint32_t>(n); uint32_t* v0 = b.take<uint32_t>(n);
+  uint32_t* k1 = b.take<uint32_t>(n); uint32_t* v1 = b.take<uint32_t>(n);
+  uint32_t* hist = b.take<uint32_t>(static_cast<size_t>(chunks) * 256);
+  rs_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(idx, k0, v0, n, n_rows);
+  RB_LAUNCH_CHECK("rs_init_kernel");
+  int bits = 1;
+  while ((1ull << bits) <= static_cast<unsigned long long>(n_rows)) ++bits;  // keys in [0, n_rows]
+  for (int shift = 0; shift < bits; shift += 8) {
+    rs_hist_kernel<<<chunks, 256, 0, st>>>(k0, n, shift, hist, chunks);
+    RB_LAUNCH_CHECK("rs_hist_kernel");
+    rs_scan_kernel<<<1, 1024, 0, st>>>(hist, chunks * 256);
+    RB_LAUNCH_CHECK("rs_scan_kernel");
+    rs_scatter_kernel<<<chunks, 32, 0, st>>>(k0, v0, k1, v1, n, shift, hist, chunks);
+    RB_LAUNCH_CHECK("rs_scatter_kernel");
+    std::swap(k0, k1); std::swap(v0, v1);
+  }
+  const long long threads = 32ll * n;
+  const int grid = static_cast<int>((threads + 255) / 256);
+  if (dtype == RB_DTYPE_BF16)
+    scatter_segments_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(k0, v0, static_cast<const __nv_bfloat16*>(grad_out), grad_table, n, d, n_rows, padding_idx);
+  else
+    scatter_segments_kernel<float><<<grid, 256, 0, st>>>(k0, v0, static_cast<const float*>(grad_out), grad_table, n, d, n_rows, padding_idx);
+  RB_LAUNCH_CHECK("scatter_segments_kernel");
+  return 0;
+}
+
+// ======================================================================= score dense
+extern "C" int rb_score_dense(const void* U, const void* W, const float* bias, float scale, float* S, int64_t M,
+                              int64_t N, int d, int dtype, int mode, void* ws, size_t ws_bytes, rb_stream_t stream) {
+  DevInfo dv; if (int r = get_dev(dv)) return r;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (int r = check_common(U, W, M, N, d, dtype, mode)) return r;
+  if (!S) return fail(RB_E_ARG, "null output");
+  Bump b(ws, ws_bytes);
+  Operand ou, ow;
+  if (int r = stage_operand(U, M, d, mode, b, ou, st)) return r;
+  if (int r = stage_operand(W, N, d, mode, b, ow, st)) return r;
+  Plan p = make_plan(M, N, dv.sms, 1 << 20);
+  CUtensorMap ts, ty;
+  if (int r = make_tmap(&ts, ou.ptr, ou.bf16, M, ou.cols, 128)) return r;
+  if (int r = make_tmap(&ty, ow.ptr, ow.bf16, N, ow.cols, BN)) return r;
+  SweepArgs a{};
+  a.n_stat = (int)M; a.n_strm = (int)N; a.n_stat_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
+  a.n_splits = p.n_splits; a.d = d; a.scale = scale; a.bias = bias; a.out = S; a.ld_out = N;
+  return launch_sweep<EPI_DENSE, true, 8>(mode, kc_for(d, mode), ts, ty, a, p.grid, st);
+}
+
+// ============================================================================ CE fwd
+extern "C" int rb_ce_fwd(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
+                         int64_t label_base, int64_t M, int64_t N, int d, int dtype, int mode, float* row_max,
+                         float* row_sumexp, float* label_logit, void* ws, size_t ws_bytes, rb_stream_t stream) {
+  DevInfo dv; if (int r = get_dev(dv)) return r;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (int r = check_common(U, W, M, N, d, dtype, mode)) return r;
+  if (!labels || !row_max || !row_sumexp || !label_logit) return fail(RB_E_ARG, "null pointer");
+  if (!ws) return fail(RB_E_WORKSPACE, "workspace required");
+  Bump b(ws, ws_bytes);
+  Operand ou, ow;
+  if (int r = stage_operand(U, M, d, mode, b, ou, st)) return r;
+  if (int r = stage_operand(W, N, d, mode, b, ow, st)) return r;
+  Plan p = make_plan(M, N, dv.sms, 1 << 20);
+  const long long m_pad = 1ll * p.n_stat_tiles * 128;
+  int* lab32 = b.take<int>(m_pad);
+  float* pm2 = b.take<float>(m_pad * p.n_splits);
+  float* pl = b.take<float>(m_pad * p.n_splits);
+  float* pll = b.take<float>(m_pad * p.n_splits);
+  if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
+  labels_local_kernel<<<(int)((m_pad + 255) / 256), 256, 0, st>>>(labels, label_base, N, lab32, (int)M, (int)m_pad);
+  RB_LAUNCH_CHECK("labels_local_kernel");
+  CUtensorMap ts, ty;
+  if (int r = make_tmap(&ts, ou.ptr, ou.bf16, M, ou.cols, 128)) return r;
+  if (int r = make_tmap(&ty, ow.ptr, ow.bf16, N, ow.cols, BN)) return r;
+  SweepArgs a{};
+  a.n_stat = (int)M; a.n_strm = (int)N; a.n_stat_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
+  a.n_splits = p.n_splits; a.d = d; a.scale = scale; a.bias = bias; a.labels = lab32;
+  a.part_m2 = pm2; a.part_l = pl; a.part_ll = pll;
+  if (int r = launch_sweep<EPI_LSE, true, 8>(mode, kc_for(d, mode), ts, ty, a, p.grid, st)) return r;
+  lse_merge_kernel<<<(int)((M + 255) / 256), 256, 0, st>>>(pm2, pl, pll, p.n_splits, m_pad, (int)M, row_max, row_sumexp, label_logit);
+  RB_LAUNCH_CHECK("lse_merge_kernel");
+  return 0;
+}
+
+// ============================================================================ CE bwd
+extern "C" int rb_ce_bwd(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
+                         int64_t label_base, const float* lse, float grad_scale, int64_t M, int64_t N, int d,
+                         int dtype, int mode, float* dU, float* dW, float* dbias, void* ws, size_t ws_bytes,
+                         rb_stream_t stream) {
+  DevInfo dv; if (int r = get_dev(dv)) return r;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (int r = check_common(U, W, M, N, d, dtype, mode)) return r;
+  if (mode != RB_MODE_BF16) return fail(RB_E_UNSUPPORTED, "CE backward is bf16-mode only in this build");
+  if (d > 128) return fail(RB_E_UNSUPPORTED, "CE backward supports d <= 128");
+  if (!labels || !lse) return fail(RB_E_ARG, "null pointer");
+  if (!ws) return fail(RB_E_WORKSPACE, "workspace required");
+  if (dbias && !dW) return fail(RB_E_ARG, "dbias is produced by the dW pass: pass dW too");
+  Bump b(ws, ws_bytes);
+  const long long m_pad = ((M + 255) / 256) * 256 + 256;
+  int* lab32 = b.take<int>(m_pad);
+  float* lse2 = b.take<float>(m_pad);
+  if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small");
+  labels_local_kernel<<<(int)((m_pad + 255) / 256), 256, 0, st>>>(labels, label_base, N, lab32, (int)M, (int)m_pad);
+  RB_LAUNCH_CHECK("labels_local_kernel");
+  lse2_kernel<<<(int)((m_pad + 255) / 256), 256, 0, st>>>(lse, lse2, (int)M, (int)m_pad);
+  RB_LAUNCH_CHECK("lse2_kernel");
+  const int kc = kc_for(d, mode);
+  const float gs = grad_scale * scale;
+
+  if (dU) {  // rows stationary: dU_i = sum_j (P_ij - 1[j = label_i]) w_j
+    Plan p = make_plan(M, N, dv.sms, 1 << 20);
+    float* part = (p.n_splits > 1) ? b.take<float>(static_cast<size_t>(p.n_splits) * M * d) : dU;
+    if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
+    CUtensorMap ts, ty;
+    if (int r = make_tmap(&ts, U, true, M, d, 128)) return r;
+    if (int r = make_tmap(&ty, W, true, N, d, BN)) return r;
+    SweepArgs a{};
+    a.n_stat = (int)M; a.n_strm = (int)N; a.n_stat_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
+    a.n_splits = p.n_splits; a.d = d; a.scale = scale; a.bias = bias; a.labels = lab32; a.lse2 = lse2;
+    a.gscale = gs; a.acc_out = part;
+    if (int r = launch_sweep<EPI_GRAD, true, 8>(mode, kc, ts, ty, a, p.grid, st)) return r;
+    if (p.n_splits > 1) {
+      const long long n = M * d;
+      partial_sum_kernel<<<(int)std::min<long long>((n + 255) / 256, dv.sms * 8), 256, 0, st>>>(part, p.n_splits, n, dU);
+      RB_LAUNCH_CHECK("partial_sum_kernel");
+    }
+  }
+  if (dW) {  // items stationary: dW_j = sum_i (P_ij - 1[j = label_i]) u_i
+    Plan p = make_plan(N, M, dv.sms, 64);
+    float* part = (p.n_splits > 1) ? b.take<float>(static_cast<size_t>(p.n_splits) * N * d) : dW;
+    float* rs_part = nullptr;
+    if (dbias) rs_part = (p.n_splits > 1) ? b.take<float>(static_cast<size_t>(p.n_splits) * N) : dbias;
+    if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
+    CUtensorMap ts, ty;
+    if (int r = make_tmap(&ts, W, true, N, d, 128)) return r;
+    if (int r = make_tmap(&ty, U, true, M, d, BN)) return r;
+    SweepArgs a{};
+    a.n_stat = (int)N; a.n_strm = (int)M; a.n_stat_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
+    a.n_splits = p.n_splits; a.d = d; a.scale = scale; a.bias = bias; a.labels = lab32; a.lse2 = lse2;
+    a.gscale = gs; a.acc_out = part; a.rowsum_out = rs_part;
+    if (int r = launch_sweep<EPI_GRAD, false, 8>(mode, kc, ts, ty, a, p.grid, st)) return r;
+    if (p.n_splits > 1) {
+      const long long n = N * d;
+      partial_sum_kernel<<<(int)std::min<long long>((n + 255) / 256, dv.sms * 8), 256, 0, st>>>(part, p.n_splits, n, dW);
+      RB_LAUNCH_CHECK("partial_sum_kernel");
+      if (dbias) {
+        partial_sum_kernel<<<(int)std::min<long long>((N + 255) / 256, dv.sms * 8), 256, 0, st>>>(rs_part, p.n_splits, N, dbias);
+        RB_LAUNCH_CHECK("partial_sum_kernel");
+      }
+    }
+  }
+  return 0;
+}
+
+// ========================================================================= top-K eval
+static int launch_topk_merge(const float* vals, const int* ids, const int* cnt, int n_lists, long long list_stride,
+                             int cap, long long rows, int K, int id_add, float* ov, int* oi, cudaStream_t st) {
+  const long long threads = rows * 32;
+  const int grid = static_cast<int>((threads + 127) / 128);
+  if (K <= 128)
+    topk_merge_kernel<4><<<grid, 128, 0, st>>>(vals, ids, cnt, n_lists, list_stride, cap, rows, K, id_add, ov, oi);
+  else
+    topk_merge_kernel<8><<<grid, 128, 0, st>>>(vals, ids, cnt, n_lists, list_stride, cap, rows, K, id_add, ov, oi);
+  RB_LAUNCH_CHECK("topk_merge_kernel");
+  return 0;
+}
+
+extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, float scale, const int64_t* seen_crow,
+                            const int64_t* seen_col, int64_t seen_nnz, int64_t id_base, int64_t B, int64_t N, int d,
+                            int dtype, int mode, int K, float* top_vals, int32_t* top_ids, void* ws, size_t ws_bytes,
+                            rb_stream_t stream) {
+  DevInfo dv; if (int r = get_dev(dv)) return r;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (int r = check_common(U, W, B, N, d, dtype, mode)) return r;
+  if (!top_vals || !top_ids) return fail(RB_E_ARG, "null output");
+  if (K < 1 || K > 224) return fail(RB_E_UNSUPPORTED, "K=%d outside [1,224]", K);
+  if (!(scale > 0.f)) return fail(RB_E_UNSUPPORTED, "top-K needs scale > 0");
+  if ((seen_crow == nullptr) != (seen_col == nullptr)) return fail(RB_E_ARG, "seen_crow/seen_col must both be given");
+  if (!ws) return fail(RB_E_WORKSPACE, "workspace required");
+  Bump b(ws, ws_bytes);
+  Operand ou, ow;
+  if (int r = stage_operand(U, B, d, mode, b, ou, st)) return r;
+  if (int r = stage_operand(W, N, d, mode, b, ow, st)) return r;
+  Plan p = make_plan(B, N, dv.sms, 1 << 20);
+  const long long b_pad = 1ll * p.n_stat_tiles * 128;
+  const int cape = (K <= 96) ? 4 : 8;
+  const int cap = 32 * cape;
+  int* crow32 = nullptr; int* col32 = nullptr;
+  long long nnz = 0;
+  if (seen_crow) {
+    if (seen_nnz < 0) return fail(RB_E_ARG, "seen_nnz < 0");
+    nnz = seen_nnz;
+    crow32 = b.take<int>(B + 1);
+    col32 = b.take<int>(std::max<long long>(nnz, 1));
+  }
+  float* cval = b.take<float>(static_cast<size_t>(p.n_splits) * b_pad * cap);
+  int* cid = b.take<int>(static_cast<size_t>(p.n_splits) * b_pad * cap);
+  int* ccnt = b.take<int>(static_cast<size_t>(p.n_splits) * b_pad);
+  if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
+  if (seen_crow) {
+    const long long n = std::max<long long>(B + 1, nnz);
+    csr_local_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(seen_crow, seen_col, id_base, crow32, col32, B, nnz);
+    RB_LAUNCH_CHECK("csr_local_kernel");
+  }
+  CUtensorMap ts, ty;
+  if (int r = make_tmap(&ts, ou.ptr, ou.bf16, B, ou.cols, 128)) return r;
+  if (int r = make_tmap(&ty, ow.ptr, ow.bf16, N, ow.cols, BN)) return r;
+  SweepArgs a{};
+  a.n_stat = (int)B; a.n_strm = (int)N; a.n_stat_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
+  a.n_splits = p.n_splits; a.d = d; a.scale = scale; a.bias = bias; a.K = K; a.id_base = 0;
+  a.seen_crow = crow32; a.seen_col = col32; a.cand_val = cval; a.cand_id = cid; a.cand_cnt = ccnt;
+  int r;
+  if (cape == 4) r = launch_sweep<EPI_TOPK, true, 4>(mode, kc_for(d, mode), ts, ty, a, p.grid, st);
+  else r = launch_sweep<EPI_TOPK, true, 8>(mode, kc_for(d, mode), ts, ty, a, p.grid, st);
+  if (r) return r;
+  return launch_topk_merge(cval, cid, ccnt, p.n_splits, b_pad, cap, B, K, (int)id_base, top_vals, top_ids, st);
+}
+
+extern "C" int rb_topk_merge(const float* vals, const int32_t* ids, int R, int64_t B, int K, float* out_vals,
+                             int32_t* out_ids, rb_stream_t stream) {
+  DevInfo dv; if (int r = get_dev(dv)) return r;
+  if (!vals || !ids || !out_vals || !out_ids) return fail(RB_E_ARG, "null pointer");
+  if (R < 1 || B < 1 || K < 1 || K > 256) return fail(RB_E_ARG, "bad shape R=%d B=%lld K=%d", R, (long long)B, K);
+  return launch_topk_merge(vals, ids, nullptr, R, B, K, B, K, 0, out_vals, out_ids, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ========================================================================== workspace
+extern "C" size_t rb_workspace_bytes(int op, int64_t M, int64_t N, int d, int K, int mode, int64_t nnz) {
+  int sms = 148;  // B200; refined from the current device when there is one
+  { DevInfo dv; if (get_dev(dv) == 0 && dv.sms > 0) sms = dv.sms; }
+  size_t need = 4096;
+  switch (op) {
+    case RB_OP_SCATTER_ADD: return scatter_ws_bytes(nnz) + 4096;
+    case RB_OP_SCORE_DENSE: return need + staged_bytes(M, d, mode) + staged_bytes(N, d, mode);
+    case RB_OP_CE_FWD: {
+      Plan p = make_plan(M, N, sms, 1 << 20);
+      const size_t m_pad = static_cast<size_t>(p.n_stat_tiles) * 128;
+      return need + staged_bytes(M, d, mode) + staged_bytes(N, d, mode) + m_pad * 4 + 3 * m_pad * p.n_splits * 4 + 2048;
+    }
+    case RB_OP_CE_BWD: {
+      const size_t m_pad = ((M + 255) / 256) * 256 + 256;
+      size_t n = need + 2 * m_pad * 4 + 1024;
+      // split counts depend on the SM count of the device; bound them by the 8*sms cap of make_plan
+      Plan pu = make_plan(M, N, sms, 1 << 20);
+      Plan pw = make_plan(N, M, sms, 64);
+      n += (pu.n_splits > 1 ? static_cast<size_t>(pu.n_splits) * M * d * 4 : 0) + 512;
+      n += (pw.n_splits > 1 ? static_cast<size_t>(pw.n_splits) * N * (d + 1) * 4 : 0) + 512;
+      return n;
+    }
+    case RB_OP_TOPK_EVAL: {
+      Plan p = make_plan(M, N, sms, 1 << 20);
+      const size_t b_pad = static_cast<size_t>(p.n_stat_tiles) * 128;
+      const int cap = (K <= 96) ? 128 : 256;
+      return need + staged_bytes(M, d, mode) + staged_bytes(N, d, mode) + (M + 1 + std::max<int64_t>(nnz, 1)) * 4 +
+             static_cast<size_t>(p.n_splits) * b_pad * (cap * 8 + 4) + 2048;
+    }
+    default: return 0;
+  }
+}

@@ -1,0 +1,111 @@
+"""HR@k / NDCG@k / RECALL@k / PRECISION@k / MRR@k from a sorted top-K id list.
+
+The reference computes these inside ``Coach.monitor(scores, targets, ...)`` from dense (B,N) score
+and multi-hot target matrices, one ``torch.topk`` per ``metric@k`` (UniSRec/main.py:428-435; the
+metric functions are freerec's).  The fused path gets the sorted (B,Kmax) id list from
+``ops.topk_eval`` once and derives every metric@k from it.
+
+Reduction contract: per batch a float32 mean, then a bsz-weighted running mean
+(``monitor(..., n=bsz, reduction="mean")``).  ``hits_from_topk`` runs on the device; the tiny (B,K)
+hit matrix is reduced with the same float32 torch ops the CPU oracle uses, so metric values are
+bit-identical whenever the ranked ids agree.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence
+
+import torch
+
+
+def hits_from_topk(top_ids: torch.Tensor, target_crow: torch.Tensor, target_col: torch.Tensor,
+                   n_items: int) -> torch.Tensor:
+    """(B,K) float32 hit matrix: 1 where the ranked id is one of the row's targets.
+
+    ``target_crow/col`` is the CSR of ``data[IUnseen]`` (``Item.to_csr``, UniSRec/main.py:414);
+    LOU evaluation has exactly one target per row."""
+    B, K = top_ids.shape
+    ids = top_ids.long()
+    rows = torch.arange(B, device=ids.device).unsqueeze(1)
+    keys = rows * n_items + ids.clamp_min(0)
+    trow = torch.repeat_interleave(torch.arange(B, device=ids.device), target_crow[1:] - target_crow[:-1])
+    tkeys = trow * n_items + target_col  # sorted: rows ascending, cols ascending inside a row
+    pos = torch.searchsorted(tkeys, keys.reshape(-1)).clamp_max(max(tkeys.numel() - 1, 0))
+    hit = (tkeys[pos] == keys.reshape(-1)).reshape(B, K) if tkeys.numel() else torch.zeros(B, K, dtype=torch.bool, device=ids.device)
+    return (hit & (top_ids >= 0)).float()
+
+
+def _dcg_weights(k: int) -> torch.Tensor:
+    return 1.0 / torch.log2(torch.arange(k, dtype=torch.float32) + 2.0)
+
+
+def metric_rows(hits: torch.Tensor, n_targets: torch.Tensor, name: str, k: int) -> torch.Tensor:
+    """Per-row metric values (float32, on ``hits.device``)."""
+    h = hits[:, :k]
+    if name == "HITRATE":
+        return (h.sum(-1) > 0).float()
+    if name == "RECALL":
+        return h.sum(-1) / n_targets.clamp_min(1.0)
+    if name == "PRECISION":
+        return h.sum(-1) / k
+    if name == "NDCG":
+        w = _dcg_weights(k).to(h.device)
+        dcg = (h * w).sum(-1)
+        n_rel = n_targets.clamp(max=k).long()
+        idcg = torch.cumsum(w, 0)[(n_rel - 1).clamp_min(0)]
+        return torch.where(n_rel > 0, dcg / idcg, torch.zeros_like(dcg))
+    if name == "MRR":
+        first = torch.where(h.sum(-1) > 0, h.argmax(-1), torch.full_like(h[:, 0], -1, dtype=torch.long))
+        return torch.where(first >= 0, 1.0 / (first.float() + 1.0), torch.zeros(len(h), device=h.device))
+    raise KeyError(f"unknown metric {name!r}")
+
+
+def batch_metrics(top_ids: torch.Tensor, target_crow: torch.Tensor, target_col: torch.Tensor, n_items: int,
+                  monitors: Sequence[str], exact: bool = True) -> Dict[str, float]:
+    """Batch means for every ``METRIC@k`` in ``monitors`` (names as in ``cfg.monitors``,
+    e.g. SASRec/configs/Amazon2014Beauty_550_LOU.yaml:21).
+
+    exact=True reduces the (B,K) hit matrix with CPU float32 torch ops (bit-identical to the
+    oracle); exact=False reduces on the device (one scalar read per metric)."""
+    hits = hits_from_topk(top_ids, target_crow, target_col, n_items)
+    n_t = (target_crow[1:] - target_crow[:-1]).float()
+    if exact:
+        hits, n_t = hits.cpu(), n_t.cpu()
+    out = {}
+    for mon in monitors:
+        name, k = mon.split("@")
+        k = int(k)
+        if k > hits.shape[1]:
+            raise ValueError(f"{mon}: k exceeds the ranked list length {hits.shape[1]}")
+        out[mon.upper()] = metric_rows(hits, n_t, name.upper(), k).mean().item()
+    return out
+
+
+class AverageMeter:
+    """bsz-weighted running mean (``monitor(..., n=bsz, reduction="mean")``)."""
+
+    def __init__(self):
+        self.sum, self.n = 0.0, 0
+
+    def update(self, batch_mean: float, n: int):
+        self.sum += float(batch_mean) * n
+        self.n += n
+
+    @property
+    def avg(self) -> float:
+        return self.sum / max(self.n, 1)
+
+
+def kmax_of(monitors: Sequence[str]) -> int:
+    return max(int(m.split("@")[1]) for m in monitors if "@" in m)
+
+
+def lists_to_csr(rows, device: Optional[torch.device] = None):
+    """Ragged id lists -> (crow, col) int64 with ids sorted-unique per row (``Field.to_csr``)."""
+    crow, col = [0], []
+    for r in rows:
+        r = sorted(set(int(x) for x in (r.tolist() if isinstance(r, torch.Tensor) else r)))
+        col.extend(r)
+        crow.append(len(col))
+    crow = torch.tensor(crow, dtype=torch.int64, device=device)
+    col = torch.tensor(col, dtype=torch.int64, device=device)
+    return crow, col

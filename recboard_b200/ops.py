@@ -1,0 +1,253 @@
+"""Host-side operators of the full-catalog scoring path (thin wrappers over the C ABI).
+
+Each function names the reference lines it stands in for (paths relative to the reference
+root).  All tensors must be CUDA tensors: there is no CPU fallback.
+
+Precision: ``precision="bf16"`` runs the contraction on bf16 operands with fp32 accumulation
+(configs 3-5); ``precision="fp32"`` runs the error-compensated 3xTF32 tensor-core mode whose
+scores agree with an fp32 SGEMM to ~1e-6 (configs 1-2).  Default: taken from the operand dtype.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+def _mode_for(U: torch.Tensor, precision: Optional[str]) -> str:
+    if precision is None:
+        precision = "bf16" if U.dtype == torch.bfloat16 else "fp32"
+    if precision not in ("bf16", "fp32"):
+        raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+    return precision
+
+
+def _prep(U, W, precision):
+    """Cast operands to the storage type the chosen arithmetic mode needs."""
+    precision = _mode_for(U, precision)
+    if precision == "bf16":
+        return U.to(torch.bfloat16).contiguous(), W.to(torch.bfloat16).contiguous(), L.MODE_BF16
+    return U.float().contiguous(), W.float().contiguous(), L.MODE_FP32X3
+
+
+def _ws(dev, op, M, N, d, K=0, mode=L.MODE_BF16, nnz=0):
+    n = L.workspace_bytes(op, M, N, d, K, mode, nnz)
+    return L.Workspace.get(dev, n), n
+
+
+# --------------------------------------------------------------------------------------
+# item-embedding gather + deterministic scatter-add backward
+# --------------------------------------------------------------------------------------
+def gather_rows_raw(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    dev = L.require_cuda(table, idx)
+    if idx.dtype != torch.int64:
+        raise TypeError("idx must be int64")
+    n_rows, d = table.shape
+    out = torch.empty(*idx.shape, d, dtype=table.dtype, device=dev)
+    L.check(
+        L.lib().rb_gather_rows(L.ptr(table), L.ptr(idx), L.ptr(out), idx.numel(), n_rows, d,
+                               L.dtype_code(table), L.stream_ptr(dev)),
+        "rb_gather_rows",
+    )
+    return out
+
+
+def scatter_add_rows_(grad_table: torch.Tensor, grad_out: torch.Tensor, idx: torch.Tensor,
+                      padding_idx: int = -1) -> torch.Tensor:
+    """grad_table[idx[i]] += grad_out[i] (fp32 accumulate, fixed summation order)."""
+    dev = L.require_cuda(grad_table, grad_out, idx)
+    if grad_table.dtype != torch.float32:
+        raise TypeError("grad_table must be float32")
+    n_rows, d = grad_table.shape
+    n_idx = idx.numel()
+    ws, n = _ws(dev, L.OP_SCATTER_ADD, 0, 0, d, nnz=n_idx)
+    L.check(
+        L.lib().rb_scatter_add_rows(L.ptr(grad_out), L.ptr(idx), L.ptr(grad_table), n_idx, n_rows, d,
+                                    L.dtype_code(grad_out), padding_idx, L.ptr(ws), n, L.stream_ptr(dev)),
+        "rb_scatter_add_rows",
+    )
+    return grad_table
+
+
+class _GatherRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, table, idx, padding_idx):
+        ctx.save_for_backward(idx)
+        ctx.shape, ctx.dtype, ctx.padding_idx = table.shape, table.dtype, padding_idx
+        return gather_rows_raw(table.contiguous(), idx.contiguous())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        g = torch.zeros(ctx.shape, dtype=torch.float32, device=grad_out.device)
+        go = grad_out.contiguous()
+        if go.dtype not in (torch.float32, torch.bfloat16):
+            go = go.float()
+        scatter_add_rows_(g, go.view(-1, ctx.shape[1]), idx.contiguous().view(-1), ctx.padding_idx)
+        return g.to(ctx.dtype), None, None
+
+
+def gather_rows(table: torch.Tensor, idx: torch.Tensor, padding_idx: int = -1) -> torch.Tensor:
+    """``self.Item.embeddings(seqs)`` (SASRec/main.py:183) with the ``nn.Embedding(padding_idx=)``
+    backward contract: dense table gradient, ``padding_idx`` row left at zero."""
+    return _GatherRows.apply(table, idx, padding_idx)
+
+
+# --------------------------------------------------------------------------------------
+# dense scores (compatibility path of recommend_from_full)
+# --------------------------------------------------------------------------------------
+def score_dense(U: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, scale: float = 1.0,
+                precision: Optional[str] = None) -> torch.Tensor:
+    """``torch.einsum("BD,ND->BN", U, W)`` (SASRec/main.py:228) -> fp32 (B,N); no autograd."""
+    dev = L.require_cuda(U, W, bias)
+    Uc, Wc, mode = _prep(U.detach(), W.detach(), precision)
+    M, d = Uc.shape
+    N = Wc.shape[0]
+    b = None if bias is None else bias.detach().float().contiguous()
+    S = torch.empty(M, N, dtype=torch.float32, device=dev)
+    ws, n = _ws(dev, L.OP_SCORE_DENSE, M, N, d, mode=mode)
+    L.check(
+        L.lib().rb_score_dense(L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(S), M, N, d,
+                               L.dtype_code(Uc), mode, L.ptr(ws), n, L.stream_ptr(dev)),
+        "rb_score_dense",
+    )
+    return S
+
+
+# --------------------------------------------------------------------------------------
+# fused full-catalog cross-entropy
+# --------------------------------------------------------------------------------------
+def ce_rowstats(U, W, labels, bias=None, scale: float = 1.0, label_base: int = 0,
+                precision: Optional[str] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(row_max, row_sumexp, label_logit) of scale*U W^T + bias over this shard; (M,N) never exists."""
+    dev = L.require_cuda(U, W, labels, bias)
+    Uc, Wc, mode = _prep(U.detach(), W.detach(), precision)
+    M, d = Uc.shape
+    N = Wc.shape[0]
+    if labels.dtype != torch.int64 or labels.numel() != M:
+        raise TypeError("labels must be int64 of shape (M,)")
+    b = None if bias is None else bias.detach().float().contiguous()
+    out = torch.empty(3, M, dtype=torch.float32, device=dev)
+    ws, n = _ws(dev, L.OP_CE_FWD, M, N, d, mode=mode)
+    L.check(
+        L.lib().rb_ce_fwd(L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(labels.contiguous()), label_base,
+                          M, N, d, L.dtype_code(Uc), mode, L.ptr(out[0]), L.ptr(out[1]), L.ptr(out[2]),
+                          L.ptr(ws), n, L.stream_ptr(dev)),
+        "rb_ce_fwd",
+    )
+    return out[0], out[1], out[2]
+
+
+def ce_backward(U, W, labels, lse, grad_scale: float, bias=None, scale: float = 1.0, label_base: int = 0,
+                need_dU: bool = True, need_dW: bool = True, need_dbias: bool = False,
+                precision: Optional[str] = None):
+    """Gradients of ``grad_scale * sum_i (lse_i - S_i,label_i)`` -> (dU, dW, dbias) fp32."""
+    dev = L.require_cuda(U, W, labels, lse, bias)
+    Uc, Wc, mode = _prep(U.detach(), W.detach(), precision)
+    M, d = Uc.shape
+    N = Wc.shape[0]
+    b = None if bias is None else bias.detach().float().contiguous()
+    dU = torch.empty(M, d, dtype=torch.float32, device=dev) if need_dU else None
+    dW = torch.empty(N, d, dtype=torch.float32, device=dev) if (need_dW or need_dbias) else None
+    db = torch.empty(N, dtype=torch.float32, device=dev) if need_dbias else None
+    ws, n = _ws(dev, L.OP_CE_BWD, M, N, d, mode=mode)
+    L.check(
+        L.lib().rb_ce_bwd(L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(labels.contiguous()), label_base,
+                          L.ptr(lse.float().contiguous()), float(grad_scale), M, N, d, L.dtype_code(Uc), mode,
+                          L.ptr(dU), L.ptr(dW), L.ptr(db), L.ptr(ws), n, L.stream_ptr(dev)),
+        "rb_ce_bwd",
+    )
+    return dU, (dW if need_dW else None), db
+
+
+class _FusedCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, U, W, labels, bias, scale, precision, reduction):
+        m, l, ll = ce_rowstats(U, W, labels, bias, scale, 0, precision)
+        lse = m + torch.log(l)
+        row_loss = lse - ll
+        ctx.save_for_backward(U, W, labels, bias if bias is not None else torch.empty(0, device=U.device), lse)
+        ctx.has_bias = bias is not None
+        ctx.scale, ctx.precision, ctx.reduction = scale, precision, reduction
+        if reduction == "mean":
+            return row_loss.mean()
+        if reduction == "sum":
+            return row_loss.sum()
+        raise ValueError(f"reduction {reduction!r} not supported by the fused path")
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        U, W, labels, bias, lse = ctx.saved_tensors
+        bias = bias if ctx.has_bias else None
+        M = U.shape[0]
+        # one host read of the upstream scalar (the reference reads loss.item() every step anyway,
+        # SASRec/main.py:252)
+        g = float(grad_out) / (M if ctx.reduction == "mean" else 1)
+        need = ctx.needs_input_grad
+        dU, dW, db = ce_backward(U, W, labels, lse, g, bias, ctx.scale, 0, need[0], need[1],
+                                 ctx.has_bias and need[3], ctx.precision)
+        return (
+            dU.to(U.dtype) if dU is not None else None,
+            dW.to(W.dtype) if dW is not None else None,
+            None,
+            db.to(bias.dtype) if db is not None else None,
+            None, None, None,
+        )
+
+
+def fused_ce(U: torch.Tensor, W: torch.Tensor, labels: torch.Tensor, bias: Optional[torch.Tensor] = None,
+             scale: float = 1.0, precision: Optional[str] = None, reduction: str = "mean") -> torch.Tensor:
+    """Drop-in for ``self.criterion(torch.einsum("MD,ND->MN", U, W), labels)`` with
+    ``criterion = CrossEntropy4Logits(reduction="mean")`` (SASRec/main.py:126,217-219): same value,
+    same gradients, no (M,N) logit matrix in forward or backward."""
+    return _FusedCE.apply(U, W, labels, bias, float(scale), precision, reduction)
+
+
+# --------------------------------------------------------------------------------------
+# masked full-catalog top-K
+# --------------------------------------------------------------------------------------
+def topk_eval(U: torch.Tensor, W: torch.Tensor, K: int, seen_crow: Optional[torch.Tensor] = None,
+              seen_col: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, scale: float = 1.0,
+              id_base: int = 0, precision: Optional[str] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Top-K (score desc, id asc) of ``scale*U W^T + bias`` with the row's seen ids skipped, i.e. the
+    outcome of ``scores[seen] = -1e23; torch.topk(scores, K)`` (UniSRec/main.py:408-413 + the metric
+    functions) without the dense (B,N).  ``seen_col`` must be sorted ascending inside each row.
+    Returns (vals fp32 (B,K), ids int32 (B,K)); missing entries are (-1e23, -1)."""
+    dev = L.require_cuda(U, W, seen_crow, seen_col, bias)
+    Uc, Wc, mode = _prep(U.detach(), W.detach(), precision)
+    B, d = Uc.shape
+    N = Wc.shape[0]
+    b = None if bias is None else bias.detach().float().contiguous()
+    nnz = 0
+    if seen_crow is not None:
+        if seen_crow.dtype != torch.int64 or seen_col.dtype != torch.int64:
+            raise TypeError("seen CSR must be int64")
+        if seen_crow.numel() != B + 1:
+            raise ValueError("seen_crow must have B+1 entries")
+        nnz = seen_col.numel()
+    vals = torch.empty(B, K, dtype=torch.float32, device=dev)
+    ids = torch.empty(B, K, dtype=torch.int32, device=dev)
+    ws, n = _ws(dev, L.OP_TOPK_EVAL, B, N, d, K=K, mode=mode, nnz=nnz)
+    L.check(
+        L.lib().rb_topk_eval(L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(seen_crow), L.ptr(seen_col), nnz,
+                             id_base, B, N, d, L.dtype_code(Uc), mode, K, L.ptr(vals), L.ptr(ids), L.ptr(ws), n,
+                             L.stream_ptr(dev)),
+        "rb_topk_eval",
+    )
+    return vals, ids
+
+
+def topk_merge(vals: torch.Tensor, ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge per-shard sorted lists (R,B,K) into the global (B,K) list."""
+    dev = L.require_cuda(vals, ids)
+    R, B, K = vals.shape
+    ov = torch.empty(B, K, dtype=torch.float32, device=dev)
+    oi = torch.empty(B, K, dtype=torch.int32, device=dev)
+    L.check(
+        L.lib().rb_topk_merge(L.ptr(vals.float().contiguous()), L.ptr(ids.int().contiguous()), R, B, K,
+                              L.ptr(ov), L.ptr(oi), L.stream_ptr(dev)),
+        "rb_topk_merge",
+    )
+    return ov, oi

@@ -1,0 +1,240 @@
+"""Bring-up probe for the GPU box: runs one named case per process (a trap in one case must not
+take the others down).  `python tests/gpu_probe.py all` spawns every case under `timeout`.
+Not a pytest module; the parity tests proper are tests/test_gpu_*.py."""
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+
+def rel_err(a, b):
+    import torch
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def inputs(M, N, d, dtype, seed=0, scale=1.0):
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    U = (torch.randn(M, d, generator=g, device="cuda") * scale).to(dtype)
+    W = (torch.randn(N, d, generator=g, device="cuda") * scale).to(dtype)
+    return U, W
+
+
+def case_gather():
+    import torch
+    from recboard_b200 import ops
+    for dtype in (torch.float32, torch.bfloat16):
+        for d in (64, 128, 8):
+            table = torch.randn(1001, d, device="cuda").to(dtype)
+            idx = torch.randint(0, 1001, (37, 50), device="cuda")
+            out = ops.gather_rows_raw(table, idx)
+            assert torch.equal(out, table[idx]), (dtype, d)
+            go = torch.randn(37 * 50, d, device="cuda").to(dtype)
+            idx2 = torch.randint(0, 40, (37 * 50,), device="cuda")
+            g = torch.zeros(1001, d, device="cuda")
+            ops.scatter_add_rows_(g, go, idx2, padding_idx=0)
+            ref = torch.zeros(1001, d, device="cuda", dtype=torch.float64)
+            keep = idx2 != 0
+            ref.index_add_(0, idx2[keep], go[keep].double())
+            e = rel_err(g, ref)
+            g2 = torch.zeros(1001, d, device="cuda")
+            ops.scatter_add_rows_(g2, go, idx2, padding_idx=0)
+            print(f"gather/scatter {dtype} d={d}: scatter rel err {e:.2e} deterministic={torch.equal(g, g2)}")
+            assert e < 1e-5
+
+
+def _dense(shapes, dtype, precision, tol):
+    import torch
+    from recboard_b200 import ops
+    for (M, N, d) in shapes:
+        U, W = inputs(M, N, d, dtype, scale=d ** -0.25)
+        t0 = time.time()
+        S = ops.score_dense(U, W, precision=precision)
+        torch.cuda.synchronize()
+        ref = U.double() @ W.double().T
+        e = rel_err(S, ref)
+        print(f"dense {precision} M={M} N={N} d={d}: rel err {e:.3e} ({time.time() - t0:.2f}s)", flush=True)
+        if e > tol:
+            bad = ((S.double() - ref).abs() > tol * ref.abs().max()).nonzero()
+            print("  first bad entries:", bad[:8].tolist(), "n_bad", len(bad))
+            print("  got", S[:2, :6].tolist(), "\n  ref", ref[:2, :6].tolist())
+        assert e <= tol
+
+
+def case_dense_bf16_small():
+    import torch
+    _dense([(128, 128, 64), (128, 256, 128), (300, 1000, 64), (77, 130, 32)], torch.bfloat16, "bf16", 2e-6)
+
+
+def case_dense_bf16_big():
+    import torch
+    _dense([(4096, 20000, 128), (1000, 3001, 256), (130, 50000, 64)], torch.bfloat16, "bf16", 2e-6)
+
+
+def case_dense_fp32():
+    import torch
+    _dense([(128, 128, 64), (300, 1000, 64), (77, 130, 32), (512, 12101, 64)], torch.float32, "fp32", 1e-5)
+
+
+def _lse(shapes, dtype, precision, tol):
+    import torch
+    from recboard_b200 import ops
+    for (M, N, d, use_bias, scale) in shapes:
+        U, W = inputs(M, N, d, dtype, scale=d ** -0.25 * 1.5)
+        labels = torch.randint(0, N, (M,), device="cuda")
+        bias = torch.randn(N, device="cuda") if use_bias else None
+        m, l, ll = ops.ce_rowstats(U, W, labels, bias, scale, precision=precision)
+        S = (U.double() @ W.double().T) * scale
+        if bias is not None:
+            S = S + bias.double()
+        lse_ref = torch.logsumexp(S, dim=1)
+        ll_ref = S.gather(1, labels[:, None]).squeeze(1)
+        lse = m.double() + torch.log(l.double())
+        e1 = float((lse - lse_ref).abs().max())
+        e2 = float((ll.double() - ll_ref).abs().max() / ll_ref.abs().max())
+        print(f"lse {precision} M={M} N={N} d={d} bias={use_bias} scale={scale}: |dlse| {e1:.3e} label rel {e2:.3e}", flush=True)
+        assert e1 < tol and e2 < tol
+
+
+def case_lse_bf16():
+    import torch
+    _lse([(128, 128, 64, False, 1.0), (300, 1000, 64, True, 1.0), (4096, 100003, 128, False, 1.0),
+          (257, 5000, 256, True, 0.5), (50, 70, 32, False, 2.0)], torch.bfloat16, "bf16", 2e-4)
+
+
+def case_lse_fp32():
+    import torch
+    _lse([(128, 128, 64, False, 1.0), (300, 1000, 64, True, 1.0), (3013, 12101, 64, False, 1.0)],
+         torch.float32, "fp32", 2e-5)
+
+
+def _grad(shapes, which):
+    import torch
+    from recboard_b200 import ops
+    for (M, N, d, use_bias, scale) in shapes:
+        U, W = inputs(M, N, d, torch.bfloat16, scale=d ** -0.25 * 1.5)
+        labels = torch.randint(0, N, (M,), device="cuda")
+        bias = torch.randn(N, device="cuda") if use_bias else None
+        Ud = U.double().requires_grad_(True)
+        Wd = W.double().requires_grad_(True)
+        bd = bias.double().requires_grad_(True) if use_bias else None
+        S = (Ud @ Wd.T) * scale
+        if bd is not None:
+            S = S + bd
+        lse_ref = torch.logsumexp(S, dim=1)
+        loss = torch.nn.functional.cross_entropy(S, labels)
+        loss.backward()
+        dU, dW, db = ops.ce_backward(U, W, labels, lse_ref.float().detach(), 1.0 / M, bias, scale,
+                                     need_dU=which in ("dU", "both"), need_dW=which in ("dW", "both"),
+                                     need_dbias=use_bias and which in ("dW", "both"))
+        torch.cuda.synchronize()
+        msg = f"grad[{which}] M={M} N={N} d={d} bias={use_bias} scale={scale}:"
+        ok = True
+        if dU is not None:
+            e = rel_err(dU, Ud.grad); msg += f" dU {e:.3e}"; ok &= e < 4e-3
+        if dW is not None:
+            e = rel_err(dW, Wd.grad); msg += f" dW {e:.3e}"; ok &= e < 4e-3
+        if db is not None:
+            e = rel_err(db, bd.grad); msg += f" db {e:.3e}"; ok &= e < 4e-3
+        print(msg, flush=True)
+        if not ok and dU is not None:
+            print("  dU got", dU[:2, :4].tolist(), "ref", Ud.grad[:2, :4].tolist())
+        if not ok and dW is not None:
+            print("  dW got", dW[:2, :4].tolist(), "ref", Wd.grad[:2, :4].tolist())
+        assert ok
+
+
+SH_GRAD = [(128, 128, 64, False, 1.0), (128, 128, 128, False, 1.0), (300, 1000, 64, True, 1.0),
+           (1000, 3001, 128, False, 0.5), (4096, 50000, 128, False, 1.0)]
+
+
+def case_grad_dU():
+    _grad(SH_GRAD, "dU")
+
+
+def case_grad_dW():
+    _grad(SH_GRAD, "dW")
+
+
+def _topk(shapes, dtype, precision):
+    import torch
+    from recboard_b200 import ops
+    for (B, N, d, K, n_seen) in shapes:
+        U, W = inputs(B, N, d, dtype, scale=d ** -0.25, seed=5)
+        crow = col = None
+        if n_seen > 0:
+            cols = torch.rand(B, N, device="cuda").argsort(dim=1)[:, :n_seen].sort(dim=1).values
+            lens = torch.randint(0, n_seen + 1, (B,), device="cuda")
+            keep = torch.arange(n_seen, device="cuda")[None, :] < lens[:, None]
+            col = cols[keep].contiguous()
+            crow = torch.zeros(B + 1, dtype=torch.int64, device="cuda")
+            crow[1:] = lens.cumsum(0)
+        vals, ids = ops.topk_eval(U, W, K, crow, col, precision=precision)
+        torch.cuda.synchronize()
+        S = (U.double() @ W.double().T).float()
+        if n_seen > 0:
+            rows = torch.repeat_interleave(torch.arange(B, device="cuda"), crow[1:] - crow[:-1])
+            S[rows, col] = -1e23
+        rv, ri = torch.sort(S, dim=1, descending=True, stable=True)
+        rv, ri = rv[:, :K], ri[:, :K]
+        same = (ids.long() == ri)
+        # allow swaps only where reference scores are within tolerance of each other
+        gap_ok = (vals - rv).abs() <= 1e-5 * rv.abs().clamp_min(1e-3) + (2e-6 if precision == "bf16" else 1e-5)
+        print(f"topk {precision} B={B} N={N} d={d} K={K} seen={n_seen}: id match {float(same.float().mean()):.6f} "
+              f"val ok {float(gap_ok.float().mean()):.6f}", flush=True)
+        if not bool(gap_ok.all()):
+            bad = (~gap_ok).nonzero()[:5]
+            for r, c in bad.tolist():
+                print("   row", r, "pos", c, "got", float(vals[r, c]), int(ids[r, c]), "ref", float(rv[r, c]), int(ri[r, c]))
+        assert bool(gap_ok.all())
+        assert float(same.float().mean()) > 0.999
+
+
+def case_topk_bf16():
+    import torch
+    _topk([(128, 1000, 64, 20, 0), (300, 5000, 64, 20, 40), (512, 38048, 64, 20, 60), (4096, 100000, 128, 100, 30),
+           (100, 300, 128, 100, 250), (64, 50000, 256, 100, 0)], torch.bfloat16, "bf16")
+
+
+def case_topk_fp32():
+    import torch
+    _topk([(128, 1000, 64, 20, 0), (512, 12101, 64, 50, 40), (1000, 38048, 64, 20, 60)], torch.float32, "fp32")
+
+
+def case_fused_ce_autograd():
+    import torch
+    from recboard_b200 import ops
+    M, N, d = 700, 9000, 128
+    U, W = inputs(M, N, d, torch.bfloat16, scale=d ** -0.25 * 1.5)
+    labels = torch.randint(0, N, (M,), device="cuda")
+    U1 = U.clone().requires_grad_(True)
+    W1 = W.clone().requires_grad_(True)
+    loss = ops.fused_ce(U1, W1, labels)
+    loss.backward()
+    Ud = U.double().requires_grad_(True)
+    Wd = W.double().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(Ud @ Wd.T, labels)
+    ref.backward()
+    print(f"fused_ce: loss {float(loss):.6f} ref {float(ref):.6f} dU {rel_err(U1.grad.float(), Ud.grad):.3e} dW {rel_err(W1.grad.float(), Wd.grad):.3e}")
+    assert abs(float(loss) - float(ref)) < 2e-3 * abs(float(ref))
+
+
+CASES = {k[5:]: v for k, v in globals().items() if k.startswith("case_")}
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which == "all":
+        names = sys.argv[2:] or list(CASES)
+        rc = 0
+        for n in names:
+            print(f"===== {n}", flush=True)
+            r = subprocess.run(["timeout", "240", sys.executable, __file__, n])
+            print(f"===== {n} -> exit {r.returncode}", flush=True)
+            rc |= r.returncode != 0
+        sys.exit(rc)
+    CASES[which]()
+    print("OK", which)
