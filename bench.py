@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- the full-catalog scoring hot path on N B200s of one node.
+
+A "step" is one pass of the hot path over one batch of synthetic input (BASELINE.json configs[2],
+the configuration the metric's target is quoted on: 1M-item catalog per GPU, d=128, 4096 query
+rows, bf16 operands / fp32 accumulate):
+
+    item gather (4096x50 ids) -> fused full-catalog CE forward (row stats) -> CE backward (dU, dW)
+    -> gather's scatter-add backward -> masked top-K evaluation of 4096 rows (K=50).
+
+metric = full-catalog scored user-item pairs / s = (train rows + eval rows) x catalog size / time.
+With N GPUs the item table is row-sharded (1M rows per GPU => weak scaling; queries replicated);
+the exchange steps are one all-gather (CE stats), one all-reduce (dU) and one all-gather (top-K).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+`--impl reference` times the reference's own CPU implementation of the path (the oracle port of
+the reference lines; freerec is not installable here) on the host cores, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_ITEMS_PER_GPU = 1_000_000
+ROWS = 4096
+D = 128
+SEQ = 50
+TOPK = 50
+METRIC = "full-catalog scored user-item pairs/sec (CE train + top-K eval)"
+UNIT = "pairs/s"
+
+
+# ------------------------------------------------------------------------------ CPU arm
+def cpu_sample(rows: int, n_items: int, d: int, reps: int, seed: int = 2026):
+    """The reference lines (oracle port) on the host cores: CE fwd+bwd of `rows` queries and a
+    masked top-K/metrics batch of `rows` queries against `n_items` items, fp32."""
+    import torch
+    from oracle import reference_path as orc
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    orc.TOPK_IMPL = "torch"  # time what the reference runs: one torch.topk per metric@k
+    g = torch.Generator().manual_seed(seed)
+    U = torch.randn(rows, d, generator=g) / d ** 0.25
+    W = torch.randn(n_items, d, generator=g) / d ** 0.25
+    labels = torch.randint(0, n_items, (rows,), generator=g)
+    seen = [torch.randint(0, n_items, (25,), generator=g).tolist() for _ in range(rows)]
+    crow, col = orc.lists_to_csr(seen)
+    tcrow, tcol = orc.lists_to_csr([[int(x)] for x in labels])
+    mons = ["HITRATE@1", "HITRATE@5", "HITRATE@10", "HITRATE@20", "HITRATE@50", "NDCG@5", "NDCG@10", "NDCG@20", "NDCG@50"]
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        orc.ce_fwd_bwd(U, W, labels)
+        orc.evaluate_batch(orc.score_dense(U, W), crow, col, tcrow, tcol, mons)
+        times.append(time.perf_counter() - t0)
+    return times, 2 * rows * n_items
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    rows, n_items = 512, 100_000
+    for _ in range(args.warmup):
+        cpu_sample(rows, n_items, D, 1)
+    times, pairs = cpu_sample(rows, n_items, D, args.steps)
+    total = sum(times)
+    value = pairs * args.steps / total
+    cores = os.cpu_count() or 1
+    sample = f"{rows} train rows + {rows} eval rows x {n_items} items, d={D}, fp32, per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[2]: SASRec full-softmax CE train + top-50 eval, 1M-item catalog/GPU, d=128, 4096 rows",
+                   "note": "reference arm = oracle port of the reference's PyTorch lines on the host CPU, bounded sample"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, f"/tmp/rb_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1])); power.append(float(p[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[3:7]):
+                if v == "Active":
+                    reasons.add(n)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm), "power_w_max": max(power)}
+        return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from recboard_b200 import _lib as L
+    from recboard_b200 import metrics as MX
+    from recboard_b200 import ops, sharded, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: recboard_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L.lib()
+
+    n_total = N_ITEMS_PER_GPU * world
+    row_start, row_end = sharded.shard_bounds(n_total, world, rank)
+    n_shard = row_end - row_start
+
+    # ---- parameters (resident): this rank's shard of the item table, bf16 + its fp32 gradient
+    gw = torch.Generator(device=dev).manual_seed(1000 + rank)
+    W = synth.embeddings(n_shard, D, gw, dev, torch.bfloat16, gain=1.5).requires_grad_(True)
+    # ---- one batch of inputs (identical on every rank: queries are replicated)
+    g = torch.Generator(device=dev).manual_seed(2026 + 3)
+    U_train = synth.embeddings(ROWS, D, g, dev, torch.bfloat16, gain=1.5)
+    labels = synth.zipf_ids(ROWS, n_total, g, dev)
+    seqs = synth.sequences(ROWS, SEQ, n_shard, g, dev)               # ids into the local shard (+1 pad row)
+    table = torch.cat([torch.zeros(1, D, dtype=torch.bfloat16, device=dev), W.detach()])  # (n_shard+1, d), row 0 = pad
+    gather_grad = synth.embeddings(ROWS * SEQ, D, g, dev, torch.bfloat16, gain=0.01)
+    table_grad = torch.zeros(n_shard + 1, D, dtype=torch.float32, device=dev)
+    U_eval = synth.embeddings(ROWS, D, g, dev, torch.bfloat16, gain=1.5)
+    seen_crow, seen_col = synth.seen_csr(ROWS, n_total, g, dev)
+    tgt = synth.targets(ROWS, n_total, g, dev, (seen_crow, seen_col))
+    tgt_crow = torch.arange(ROWS + 1, device=dev, dtype=torch.int64)
+    monitors = ["HITRATE@1", "HITRATE@5", "HITRATE@10", "HITRATE@20", "HITRATE@50", "NDCG@5", "NDCG@10", "NDCG@20", "NDCG@50"]
+
+    def hot_path(U_tr, lab, sq, U_ev, s_crow, s_col):
+        """One pass of the path through the public API (recboard_b200.ops / .sharded)."""
+        emb = ops.gather_rows_raw(table, sq)                                      # a2
+        Uq = U_tr.detach().requires_grad_(True)
+        W.grad = None
+        if world > 1:
+            loss = sharded.sharded_fused_ce(Uq, W, lab, row_start)                # a5+a6 (+ all-gather)
+        else:
+            loss = ops.fused_ce(Uq, W, lab)
+        loss.backward()                                                           # a7 (+ all-reduce of dU)
+        ops.scatter_add_rows_(table_grad, gather_grad, sq.view(-1), padding_idx=0)  # a3
+        if world > 1:
+            vals, ids = sharded.sharded_topk(U_ev, W.detach(), TOPK, row_start, s_crow, s_col)  # a8-a10
+        else:
+            vals, ids = ops.topk_eval(U_ev, W.detach(), TOPK, s_crow, s_col)
+        return loss, ids, emb
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for _ in range(max(args.warmup, 3)):
+        hot_path(U_train, labels, seqs, U_eval, seen_crow, seen_col)
+    barrier()
+
+    # ---- device-resident timing of exactly K steps (inputs > L2: the 256 MB table shard is streamed
+    #      from HBM several times per step, so no L2 flush is needed between iterations)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss, ids, _ = hot_path(U_train, labels, seqs, U_eval, seen_crow, seen_col)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = L.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    pairs_per_step = 2 * ROWS * n_total
+    value = pairs_per_step * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end: host buffers in, host results out, every step
+    pin = lambda x: x.cpu().pin_memory()
+    hU, hl, hs, hUe, hc, hcol = pin(U_train), pin(labels), pin(seqs), pin(U_eval), pin(seen_crow), pin(seen_col)
+    h2d = sum(x.numel() * x.element_size() for x in (hU, hl, hs, hUe, hc, hcol))
+    d2h = 4 + ROWS * TOPK * 4
+
+    def e2e_step():
+        dU_, dl, dsq, dUe, dc, dcol = (x.to(dev, non_blocking=True) for x in (hU, hl, hs, hUe, hc, hcol))
+        loss, ids, _ = hot_path(dU_, dl, dsq, dUe, dc, dcol)
+        loss_host = loss.item()
+        res = MX.batch_metrics(ids, tgt_crow, tgt, n_total, monitors, exact=True)   # reads the (B,K) hit matrix back
+        return loss_host, res
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loss_host, res = e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = pairs_per_step * args.steps / float(t)
+
+    # ---- per-kernel timing of the path's sweeps (CUDA events on the launching stream)
+    def time_op(fn, reps=5):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    breakdown = None
+    roofline = None
+    if rank == 0:
+        Wd = W.detach()
+        with torch.no_grad():
+            m_, l_, ll_ = ops.ce_rowstats(U_train, Wd, labels, label_base=row_start)
+            lse = m_ + torch.log(l_)
+            t_fwd = time_op(lambda: ops.ce_rowstats(U_train, Wd, labels, label_base=row_start))
+            t_dU = time_op(lambda: ops.ce_backward(U_train, Wd, labels, lse, 1.0 / ROWS, label_base=row_start, need_dU=True, need_dW=False))
+            t_dW = time_op(lambda: ops.ce_backward(U_train, Wd, labels, lse, 1.0 / ROWS, label_base=row_start, need_dU=False, need_dW=True))
+            t_topk = time_op(lambda: ops.topk_eval(U_eval, Wd, TOPK, seen_crow, seen_col, id_base=row_start))
+            t_gather = time_op(lambda: ops.gather_rows_raw(table, seqs))
+            t_scatter = time_op(lambda: ops.scatter_add_rows_(table_grad, gather_grad, seqs.view(-1), padding_idx=0))
+        flop_tile = 2.0 * ROWS * n_shard * D
+        breakdown = {
+            "ce_fwd_ms": t_fwd, "ce_bwd_dU_ms": t_dU, "ce_bwd_dW_ms": t_dW, "topk_ms": t_topk, "gather_ms": t_gather,
+            "scatter_add_ms": t_scatter,
+            "ce_train_algorithmic_tflops": 3 * flop_tile / ((t_fwd + t_dU + t_dW) * 1e-3) / 1e12,
+            "ce_train_executed_tflops": 5 * flop_tile / ((t_fwd + t_dU + t_dW) * 1e-3) / 1e12,
+            "topk_tflops": flop_tile / (t_topk * 1e-3) / 1e12,
+            "gather_gbs": (ROWS * SEQ * (8 + 2 * D * 2)) / (t_gather * 1e-3) / 1e9,
+        }
+        peaks = {}
+        try:
+            peaks = json.load(open(ROOT / "MEASURED_PEAKS.json"))
+        except Exception:
+            pass
+        peak = peaks.get("bf16_tflops", 1590.0)
+        # dominant kernel: sweep_kernel<EPI_GRAD> (items stationary => dW).  Algorithmic work of that
+        # launch = the dW GEMM, 2*M*N*d flop (6d flop per pair per train step, 2d of them here);
+        # it also executes the score recompute (another 2*M*N*d) which is not counted.
+        dom_ms, dom_name = max((t_dW, "sweep_kernel<GRAD,items-stationary> (dW)"), (t_dU, "sweep_kernel<GRAD,rows-stationary> (dU)"))
+        ach = flop_tile / (dom_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "traffic": None, "kernel": dom_name, "executed_tflops": 2 * ach,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.59 PFLOP/s"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1:
+        rows_s, n_s = 512, 100_000
+        cpu_sample(rows_s, n_s, D, 1)
+        times, pairs = cpu_sample(rows_s, n_s, D, 3)
+        cpu_baseline = {"value": pairs / statistics.median(times), "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                        "sample": f"{rows_s} train + {rows_s} eval rows x {n_s} items, d={D}, fp32 (oracle port of the reference lines), median of 3"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "configs[2]: SASRec bf16 full-softmax CE train + masked top-50 eval, 1M-item catalog per GPU (row-sharded), d=128, 4096 query rows, gather 4096x50",
+                       "rows": ROWS, "n_items_total": n_total, "d": D, "topk": TOPK, "parallelism": f"row-sharded table x{world}",
+                       "l2": "inputs larger than L2 (256 MB table shard streamed per sweep); no flush"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "loss": loss_host, "metrics": res},
+            "gpu_launches": launches,
+            "roofline": roofline, "breakdown": breakdown, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29511", __file__, "--gpus", str(args.gpus),
+               "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        return subprocess.call(cmd)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

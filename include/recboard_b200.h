@@ -68,17 +68,19 @@ int rb_ce_fwd(const void* U, const void* W, const float* bias, float scale, cons
               int64_t label_base, int64_t M, int64_t N, int d, int dtype, int mode, float* row_max,
               float* row_sumexp, float* label_logit, void* ws, size_t ws_bytes, rb_stream_t stream);
 
-/* Gradients of grad_scale * sum_i (lse_i - S_i,label_i) given the GLOBAL lse (natural log):
- *   dU (M,d)  = grad_scale * scale * (softmax - onehot) W      (this shard's partial; nullable)
- *   dW (N,d)  = grad_scale * scale * (softmax - onehot)^T U    (nullable)
- *   dbias (N) = grad_scale * column sums of (softmax - onehot) (nullable)
+/* Gradients of g * sum_i (lse_i - S_i,label_i) given the GLOBAL lse (natural log), where
+ * g = grad_scale * (grad_scale_dev ? *grad_scale_dev : 1)  (a device scalar lets autograd's
+ * grad_output flow in without a host read):
+ *   dU (M,d)  = g * scale * (softmax - onehot) W      (this shard's partial; nullable)
+ *   dW (N,d)  = g * scale * (softmax - onehot)^T U    (nullable)
+ *   dbias (N) = g * column sums of (softmax - onehot) (nullable)
  * Recomputes S tile by tile; P lives only in SMEM/TMEM.  Replaces the autograd of
  * SASRec/main.py:217-219 run by `loss.backward()` (:249): nll_loss_backward,
  * _log_softmax_backward_data and the two cuBLAS GEMMs. */
 int rb_ce_bwd(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
-              int64_t label_base, const float* lse, float grad_scale, int64_t M, int64_t N, int d,
-              int dtype, int mode, float* dU, float* dW, float* dbias, void* ws, size_t ws_bytes,
-              rb_stream_t stream);
+              int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
+              int64_t M, int64_t N, int d, int dtype, int mode, float* dU, float* dW, float* dbias,
+              void* ws, size_t ws_bytes, rb_stream_t stream);
 
 /* Masked full-catalog top-K: for every query row the K best (score desc, id asc) items among this
  * shard's N items, skipping ids in the row's seen list (CSR over GLOBAL ids, sorted ascending per

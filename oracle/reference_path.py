@@ -137,24 +137,36 @@ def _dcg_weights(k: int) -> torch.Tensor:
     return 1.0 / torch.log2(torch.arange(k, dtype=torch.float32) + 2.0)
 
 
+#: "stable": (score desc, id asc) -- the documented tie policy, used by every parity test.
+#: "torch":  plain ``torch.topk`` exactly as the reference's metric functions call it (tie order
+#:           unspecified) -- used only when TIMING the reference path on the CPU (bench.py).
+TOPK_IMPL = "stable"
+
+
+def _topk_idx(scores, k):
+    if TOPK_IMPL == "torch":
+        return torch.topk(scores, k, dim=1).indices
+    return topk_sorted(scores, k)[1]
+
+
 def hitrate(scores, targets, k):
-    _, idx = topk_sorted(scores, k)
+    idx = _topk_idx(scores, k)
     return (targets.gather(1, idx).sum(-1) > 0).float()
 
 
 def recall(scores, targets, k):
-    _, idx = topk_sorted(scores, k)
+    idx = _topk_idx(scores, k)
     hits = targets.gather(1, idx).sum(-1)
     return hits / targets.sum(-1).clamp_min(1.0)
 
 
 def precision(scores, targets, k):
-    _, idx = topk_sorted(scores, k)
+    idx = _topk_idx(scores, k)
     return targets.gather(1, idx).sum(-1) / k
 
 
 def ndcg(scores, targets, k):
-    _, idx = topk_sorted(scores, k)
+    idx = _topk_idx(scores, k)
     h = targets.gather(1, idx)
     w = _dcg_weights(k)
     dcg = (h * w).sum(-1)
@@ -165,7 +177,7 @@ def ndcg(scores, targets, k):
 
 def mrr(scores, targets, k=None):
     k = scores.shape[1] if k is None else k
-    _, idx = topk_sorted(scores, k)
+    idx = _topk_idx(scores, k)
     h = targets.gather(1, idx)
     first = torch.where(h.sum(-1) > 0, h.argmax(-1), torch.full_like(h[:, 0], -1, dtype=torch.long))
     return torch.where(first >= 0, 1.0 / (first.float() + 1.0), torch.zeros(len(h)))

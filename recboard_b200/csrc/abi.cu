@@ -334,9 +334,9 @@ extern "C" int rb_ce_fwd(const void* U, const void* W, const float* bias, float 
 
 // ============================================================================ CE bwd
 extern "C" int rb_ce_bwd(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
-                         int64_t label_base, const float* lse, float grad_scale, int64_t M, int64_t N, int d,
-                         int dtype, int mode, float* dU, float* dW, float* dbias, void* ws, size_t ws_bytes,
-                         rb_stream_t stream) {
+                         int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
+                         int64_t M, int64_t N, int d, int dtype, int mode, float* dU, float* dW, float* dbias,
+                         void* ws, size_t ws_bytes, rb_stream_t stream) {
   DevInfo dv; if (int r = get_dev(dv)) return r;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (int r = check_common(U, W, M, N, d, dtype, mode)) return r;
@@ -367,7 +367,7 @@ extern "C" int rb_ce_bwd(const void* U, const void* W, const float* bias, float 
     SweepArgs a{};
     a.n_stat = (int)M; a.n_strm = (int)N; a.n_stat_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
     a.n_splits = p.n_splits; a.d = d; a.scale = scale; a.bias = bias; a.labels = lab32; a.lse2 = lse2;
-    a.gscale = gs; a.acc_out = part;
+    a.gscale = gs; a.gscale_dev = grad_scale_dev; a.acc_out = part;
     if (int r = launch_sweep<EPI_GRAD, true, 8>(mode, kc, ts, ty, a, p.grid, st)) return r;
     if (p.n_splits > 1) {
       const long long n = M * d;
@@ -387,7 +387,7 @@ extern "C" int rb_ce_bwd(const void* U, const void* W, const float* bias, float 
     SweepArgs a{};
     a.n_stat = (int)N; a.n_strm = (int)M; a.n_stat_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
     a.n_splits = p.n_splits; a.d = d; a.scale = scale; a.bias = bias; a.labels = lab32; a.lse2 = lse2;
-    a.gscale = gs; a.acc_out = part; a.rowsum_out = rs_part;
+    a.gscale = gs; a.gscale_dev = grad_scale_dev; a.acc_out = part; a.rowsum_out = rs_part;
     if (int r = launch_sweep<EPI_GRAD, false, 8>(mode, kc, ts, ty, a, p.grid, st)) return r;
     if (p.n_splits > 1) {
       const long long n = N * d;

@@ -43,6 +43,7 @@ struct SweepArgs {
   // EPI_GRAD
   const float* lse2;  // per query row lse*log2(e), padded with +inf to a tile multiple
   float gscale;       // upstream grad / M
+  const float* gscale_dev;  // optional device scalar multiplied into gscale (autograd's grad_output)
   float* acc_out;     // [n_splits][n_stat][d]
   float* rowsum_out;  // [n_splits][n_stat]  sum_j P (items stationary: dbias), nullable
   // EPI_TOPK (rows stationary)
@@ -551,6 +552,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
       } else if (C::EPI == EPI_GRAD) {
         mbar_wait(&bar->acc_full, k & 1);
         tc_fence_after();
+        const float gsc = a.gscale * (a.gscale_dev != nullptr ? __ldg(a.gscale_dev) : 1.f);
         float* o = a.acc_out + (static_cast<long long>(split) * a.n_stat + srow) * a.d;
 #pragma unroll 1
         for (int ch = 0; ch < C::DPAD / 32; ++ch) {
@@ -563,10 +565,10 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
               const int col = ch * 32 + c4 * 4;
               if (col < a.d) {  // d % 4 == 0 (checked on host)
                 float4 v;
-                v.x = __uint_as_float(raw[c4 * 4 + 0]) * a.gscale;
-                v.y = __uint_as_float(raw[c4 * 4 + 1]) * a.gscale;
-                v.z = __uint_as_float(raw[c4 * 4 + 2]) * a.gscale;
-                v.w = __uint_as_float(raw[c4 * 4 + 3]) * a.gscale;
+                v.x = __uint_as_float(raw[c4 * 4 + 0]) * gsc;
+                v.y = __uint_as_float(raw[c4 * 4 + 1]) * gsc;
+                v.z = __uint_as_float(raw[c4 * 4 + 2]) * gsc;
+                v.w = __uint_as_float(raw[c4 * 4 + 3]) * gsc;
                 *reinterpret_cast<float4*>(o + col) = v;
               }
             }
@@ -575,7 +577,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
         tc_fence_before();
         mbar_arrive(&bar->acc_empty);
         if (!C::STAT_ROWS && a.rowsum_out != nullptr && srow_ok)
-          a.rowsum_out[static_cast<long long>(split) * a.n_stat + srow] = rowsum * a.gscale;
+          a.rowsum_out[static_cast<long long>(split) * a.n_stat + srow] = rowsum * gsc;
       }
     }  // items
   }

@@ -142,9 +142,12 @@ def ce_rowstats(U, W, labels, bias=None, scale: float = 1.0, label_base: int = 0
 
 def ce_backward(U, W, labels, lse, grad_scale: float, bias=None, scale: float = 1.0, label_base: int = 0,
                 need_dU: bool = True, need_dW: bool = True, need_dbias: bool = False,
-                precision: Optional[str] = None):
-    """Gradients of ``grad_scale * sum_i (lse_i - S_i,label_i)`` -> (dU, dW, dbias) fp32."""
-    dev = L.require_cuda(U, W, labels, lse, bias)
+                precision: Optional[str] = None, grad_scale_dev: Optional[torch.Tensor] = None):
+    """Gradients of ``g * sum_i (lse_i - S_i,label_i)`` -> (dU, dW, dbias) fp32, with
+    ``g = grad_scale * grad_scale_dev`` (the latter an optional fp32 device scalar)."""
+    dev = L.require_cuda(U, W, labels, lse, bias, grad_scale_dev)
+    if grad_scale_dev is not None and (grad_scale_dev.dtype != torch.float32 or grad_scale_dev.numel() != 1):
+        raise TypeError("grad_scale_dev must be a float32 scalar tensor")
     Uc, Wc, mode = _prep(U.detach(), W.detach(), precision)
     M, d = Uc.shape
     N = Wc.shape[0]
@@ -155,7 +158,8 @@ def ce_backward(U, W, labels, lse, grad_scale: float, bias=None, scale: float = 
     ws, n = _ws(dev, L.OP_CE_BWD, M, N, d, mode=mode)
     L.check(
         L.lib().rb_ce_bwd(L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(labels.contiguous()), label_base,
-                          L.ptr(lse.float().contiguous()), float(grad_scale), M, N, d, L.dtype_code(Uc), mode,
+                          L.ptr(lse.float().contiguous()), float(grad_scale), L.ptr(grad_scale_dev), M, N, d,
+                          L.dtype_code(Uc), mode,
                           L.ptr(dU), L.ptr(dW), L.ptr(db), L.ptr(ws), n, L.stream_ptr(dev)),
         "rb_ce_bwd",
     )
@@ -182,12 +186,12 @@ class _FusedCE(torch.autograd.Function):
         U, W, labels, bias, lse = ctx.saved_tensors
         bias = bias if ctx.has_bias else None
         M = U.shape[0]
-        # one host read of the upstream scalar (the reference reads loss.item() every step anyway,
-        # SASRec/main.py:252)
-        g = float(grad_out) / (M if ctx.reduction == "mean" else 1)
+        g = 1.0 / (M if ctx.reduction == "mean" else 1)
         need = ctx.needs_input_grad
+        # the upstream scalar stays on the device: no host synchronisation in backward
         dU, dW, db = ce_backward(U, W, labels, lse, g, bias, ctx.scale, 0, need[0], need[1],
-                                 ctx.has_bias and need[3], ctx.precision)
+                                 ctx.has_bias and need[3], ctx.precision,
+                                 grad_scale_dev=grad_out.detach().float().reshape(1).contiguous())
         return (
             dU.to(U.dtype) if dU is not None else None,
             dW.to(W.dtype) if dW is not None else None,

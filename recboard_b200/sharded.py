@@ -1,0 +1,104 @@
+"""Row-sharded item table across the GPUs of one box: rank r owns a contiguous block of
+item rows (with its gradient and optimizer state); query rows are replicated.
+
+The reference has no counterpart -- its only multi-GPU mode is DDP, which all-reduces the whole
+dense (N,d) table gradient every step (``ddp_backend: nccl``, E4SRec/README.md:23).  Here the
+exchange steps are tiny and explicit:
+
+  CE forward   one all-gather of the per-rank (row_max, row_sumexp, label_logit)  [3*M floats/rank]
+  CE backward  one all-reduce (SUM) of the partial dU (M,d); the dW shard is purely local
+  top-K eval   one all-gather of the per-rank sorted (vals, ids) (B,K) + a K-way merge kernel
+
+The collectives and the elementwise merge math below are device-agnostic torch (they are exercised
+on CPU with gloo, world_size 2, in tests/test_sharded_gloo.py); the per-shard partials come from
+the CUDA kernels through ``recboard_b200.ops`` -- there is no CPU compute path in the product.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_items: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row block of rank ``rank``: [start, end)."""
+    base, rem = divmod(n_items, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def merge_rowstats(stats: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """stats (R,3,M) = per-rank (max, sumexp, label_logit) -> (global lse (M,), label_logit (M,))."""
+    m, l, ll = stats[:, 0], stats[:, 1], stats[:, 2]
+    mg = m.max(dim=0).values
+    lg = (l * torch.exp(m - mg)).sum(dim=0)
+    return mg + torch.log(lg), ll.sum(dim=0)
+
+
+def allgather_rowstats(m: torch.Tensor, l: torch.Tensor, ll: torch.Tensor, group=None) -> torch.Tensor:
+    local = torch.stack([m, l, ll]).contiguous()
+    world = dist.get_world_size(group)
+    out = torch.empty(world * local.shape[0], *local.shape[1:], dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local, group=group)  # concatenates along dim 0 (gloo and nccl)
+    return out.view(world, *local.shape)
+
+
+def allgather_topk(vals: torch.Tensor, ids: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(B,K) float32 vals + int32 ids per rank -> (R,B,K) each, with ONE collective."""
+    packed = torch.stack([vals.contiguous().view(torch.int32), ids.contiguous()]).contiguous()
+    world = dist.get_world_size(group)
+    out = torch.empty(world * packed.shape[0], *packed.shape[1:], dtype=torch.int32, device=packed.device)
+    dist.all_gather_into_tensor(out, packed, group=group)
+    out = out.view(world, *packed.shape)
+    return out[:, 0].contiguous().view(torch.float32), out[:, 1].contiguous()
+
+
+class _ShardedCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, U, W_shard, labels, bias_shard, scale, row_start, group, precision):
+        from . import ops
+        m, l, ll = ops.ce_rowstats(U, W_shard, labels, bias_shard, scale, label_base=row_start, precision=precision)
+        lse, llg = merge_rowstats(allgather_rowstats(m, l, ll, group))
+        ctx.save_for_backward(U, W_shard, labels, bias_shard if bias_shard is not None else torch.empty(0, device=U.device), lse)
+        ctx.has_bias = bias_shard is not None
+        ctx.scale, ctx.row_start, ctx.group, ctx.precision = scale, row_start, group, precision
+        return (lse - llg).mean()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from . import ops
+        U, W_shard, labels, bias, lse = ctx.saved_tensors
+        bias = bias if ctx.has_bias else None
+        need = ctx.needs_input_grad
+        dU, dW, db = ops.ce_backward(U, W_shard, labels, lse, 1.0 / U.shape[0], bias, ctx.scale, ctx.row_start,
+                                     need[0], need[1], ctx.has_bias and need[3], ctx.precision,
+                                     grad_scale_dev=grad_out.detach().float().reshape(1).contiguous())
+        if dU is not None:
+            dist.all_reduce(dU, op=dist.ReduceOp.SUM, group=ctx.group)
+        return (dU.to(U.dtype) if dU is not None else None, dW.to(W_shard.dtype) if dW is not None else None, None,
+                db.to(bias.dtype) if db is not None else None, None, None, None, None)
+
+
+def sharded_fused_ce(U: torch.Tensor, W_shard: torch.Tensor, labels: torch.Tensor, row_start: int,
+                     bias_shard: Optional[torch.Tensor] = None, scale: float = 1.0, group=None,
+                     precision: Optional[str] = None) -> torch.Tensor:
+    """Full-catalog CE where this rank scores only rows [row_start, row_start+len(W_shard)) of the
+    table.  ``labels`` are GLOBAL item ids; every rank returns the same loss; ``W_shard.grad`` is the
+    local gradient shard (never all-reduced), ``U.grad`` is the full gradient."""
+    return _ShardedCE.apply(U, W_shard, labels, bias_shard, float(scale), int(row_start), group, precision)
+
+
+@torch.no_grad()
+def sharded_topk(U: torch.Tensor, W_shard: torch.Tensor, K: int, row_start: int,
+                 seen_crow: Optional[torch.Tensor] = None, seen_col: Optional[torch.Tensor] = None,
+                 bias_shard: Optional[torch.Tensor] = None, scale: float = 1.0, group=None,
+                 precision: Optional[str] = None,
+                 merge_fn: Optional[Callable] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Global masked top-K over a row-sharded table: local top-K with global ids, one all-gather,
+    K-way merge.  The seen CSR (global ids) is replicated; each rank applies the part in its range."""
+    from . import ops
+    vals, ids = ops.topk_eval(U, W_shard, K, seen_crow, seen_col, bias=bias_shard, scale=scale,
+                              id_base=row_start, precision=precision)
+    av, ai = allgather_topk(vals, ids, group)
+    return (merge_fn or ops.topk_merge)(av, ai)

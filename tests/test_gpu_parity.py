@@ -1,0 +1,323 @@
+"""Parity tests proper: the CUDA path (through the C ABI) vs the CPU oracle on the same seeded
+inputs and against the golden vectors produced by the reference's own model files.
+
+Tolerances (BASELINE.json north_star): fp32 mode 1e-5 relative; bf16 mode 2e-3 relative (the bf16
+inputs are shared with the oracle, so forward values agree far tighter; gradients carry one bf16
+rounding of the softmax tile).  Top-K ids must be identical wherever neighbouring reference scores
+are further apart than the fp32 tolerance.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_path as orc
+from recboard_b200 import metrics as MX
+
+pytestmark = pytest.mark.gpu
+
+FP32_RTOL = 1e-5
+BF16_RTOL = 2e-3
+T = torch.from_numpy
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a B200")
+    from recboard_b200 import ops as _ops
+    return _ops
+
+
+def dev(x):
+    return None if x is None else x.cuda()
+
+
+def assert_rel(got, ref, rtol, what=""):
+    got, ref = got.detach().float().cpu(), torch.as_tensor(ref).float()
+    scale = float(ref.abs().max().clamp_min(1e-30))
+    err = float((got - ref).abs().max()) / scale
+    assert err <= rtol, f"{what}: max err / max|ref| = {err:.3e} > {rtol:.1e}"
+
+
+def bf16_round(x):
+    return x.bfloat16().float()
+
+
+# ------------------------------------------------------------------------------- golden vectors
+def test_golden_sasrec_ce_fp32_forward(ops, golden):
+    g = golden("sasrec_ce")
+    U, W, lab = T(g["U"]), T(g["W"]), T(g["labels"])
+    m, l, ll = ops.ce_rowstats(dev(U), dev(W), dev(lab), precision="fp32")
+    loss = (m + torch.log(l) - ll).mean()
+    assert abs(float(loss) - float(g["loss"])) <= FP32_RTOL * abs(float(g["loss"]))
+    assert_rel(ops.score_dense(dev(T(g["U_eval"])), dev(W), precision="fp32"), g["scores_full"], FP32_RTOL, "scores")
+
+
+def test_golden_sasrec_ce_bf16_loss_and_grads(ops, golden):
+    g = golden("sasrec_ce")
+    U, W, lab = bf16_round(T(g["U"])), bf16_round(T(g["W"])), T(g["labels"])
+    ref_loss, ref_dU, ref_dW, _ = orc.ce_fwd_bwd(U, W, lab)
+    Ud, Wd = dev(U).bfloat16().requires_grad_(True), dev(W).bfloat16().requires_grad_(True)
+    loss = ops.fused_ce(Ud, Wd, dev(lab))
+    loss.backward()
+    assert abs(float(loss) - float(ref_loss)) <= 1e-5 * abs(float(ref_loss))
+    assert_rel(Ud.grad, ref_dU, 2 * BF16_RTOL, "dU")
+    assert_rel(Wd.grad, ref_dW, 2 * BF16_RTOL, "dW")
+    # and against the reference's own numbers (fp32 inputs): within the bf16 tolerance
+    assert abs(float(loss) - float(g["loss"])) <= BF16_RTOL * abs(float(g["loss"]))
+
+
+def test_golden_bert4rec_bias_head(ops, golden):
+    g = golden("bert4rec_ce")
+    U, W, b, lab = T(g["U"]), T(g["W"]), T(g["bias"]), T(g["labels"])
+    m, l, ll = ops.ce_rowstats(dev(U), dev(W), dev(lab), bias=dev(b), precision="fp32")
+    loss = (m + torch.log(l) - ll).mean()
+    assert abs(float(loss) - float(g["loss"])) <= FP32_RTOL * abs(float(g["loss"]))
+    Ub, Wb = bf16_round(U), bf16_round(W)
+    _, rdU, rdW, rdb = orc.ce_fwd_bwd(Ub, Wb, lab, bias=b)
+    lse = torch.logsumexp(orc.score_dense(Ub, Wb, b), dim=1)
+    dU, dW, db = ops.ce_backward(dev(Ub).bfloat16(), dev(Wb).bfloat16(), dev(lab), dev(lse), 1.0 / len(lab), bias=dev(b),
+                                 need_dbias=True)
+    assert_rel(dU, rdU, 2 * BF16_RTOL, "dU")
+    assert_rel(dW, rdW, 2 * BF16_RTOL, "dW")
+    assert_rel(db, rdb, 2 * BF16_RTOL, "dbias")
+    f = golden("bert4rec_full")
+    S = ops.score_dense(dev(T(f["U"])), dev(T(f["W"])), bias=dev(T(f["bias"])), precision="fp32")[:, int(f["num_pads"]):]
+    assert_rel(S, f["scores_full"], FP32_RTOL, "bert4rec scores")
+
+
+@pytest.mark.parametrize("name", ["mf_full", "lightgcn_full"])
+def test_golden_genrec_full_ranking(ops, golden, name):
+    g = golden(name)
+    users = T(g["users"]).squeeze(1)
+    U = ops.gather_rows_raw(dev(T(g["user_table"])), dev(users))
+    assert torch.equal(U.cpu(), T(g["user_table"])[users])
+    assert_rel(ops.score_dense(U, dev(T(g["item_table"])), precision="fp32"), g["scores_full"], FP32_RTOL, name)
+
+
+def test_golden_hstu_and_gru4rec_scores(ops, golden):
+    for name in ("hstu_full", "gru4rec_ce"):
+        g = golden(name)
+        Uk = "U" if name == "hstu_full" else "U_eval"
+        assert_rel(ops.score_dense(dev(T(g[Uk])), dev(T(g["W"])), precision="fp32"), g["scores_full"], FP32_RTOL, name)
+
+
+def test_golden_embedding_forward_backward(ops, golden):
+    g = golden("embedding_bwd")
+    table, idx, go = T(g["table"]), T(g["idx"]), T(g["grad_out"])
+    t = dev(table).requires_grad_(True)
+    out = ops.gather_rows(t, dev(idx), padding_idx=0)
+    assert torch.equal(out.detach().cpu(), T(g["out"]))
+    out.backward(dev(go))
+    assert_rel(t.grad, g["grad_table"], 1e-6, "embedding backward")
+    assert torch.all(t.grad[0] == 0)  # padding_idx row (SASRec/main.py:75)
+
+
+# ----------------------------------------------------------------------- seeded oracle parity
+SHAPES = [  # (M, N, d) incl. partial tiles, M=1, tiny N, label in last partial tile
+    (1, 130, 64), (77, 129, 32), (300, 1000, 64), (513, 4099, 128), (256, 2048, 256), (129, 257, 8),
+]
+
+
+@pytest.mark.parametrize("M,N,d", SHAPES)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_scores_and_rowstats(ops, M, N, d, precision):
+    if precision == "fp32" and d > 64:
+        pytest.skip("fp32x3 mode supports d <= 64")
+    g = torch.Generator().manual_seed(M * 7 + N)
+    U = torch.randn(M, d, generator=g) / d ** 0.25
+    W = torch.randn(N, d, generator=g) / d ** 0.25
+    if precision == "bf16":
+        U, W = bf16_round(U), bf16_round(W)
+    lab = torch.randint(0, N, (M,), generator=g)
+    lab[-1] = N - 1  # label in the last (partial) tile
+    bias = torch.randn(N, generator=g) * 0.3
+    rtol = FP32_RTOL if precision == "fp32" else 1e-5
+    cast = (lambda x: dev(x).bfloat16()) if precision == "bf16" else dev
+    for b, scale in ((None, 1.0), (bias, 0.7)):
+        S = ops.score_dense(cast(U), cast(W), bias=dev(b), scale=scale, precision=precision)
+        assert_rel(S, orc.score_dense(U, W, b, scale), rtol, "scores")
+        m, l, ll = ops.ce_rowstats(cast(U), cast(W), dev(lab), bias=dev(b), scale=scale, precision=precision)
+        rm, rl, rll = orc.ce_rowstats(U, W, lab, b, scale)
+        lse, rlse = (m + torch.log(l)).cpu(), rm + torch.log(rl)
+        assert float((lse - rlse).abs().max()) <= rtol * float(rlse.abs().max()) + 1e-6
+        assert_rel(ll, rll, rtol, "label logit")
+
+
+@pytest.mark.parametrize("M,N,d", [(1, 130, 64), (300, 1000, 64), (513, 4099, 128), (3013, 12101, 64)])
+def test_ce_gradients_bf16(ops, M, N, d):
+    g = torch.Generator().manual_seed(M + N + d)
+    U = bf16_round(torch.randn(M, d, generator=g) * 1.5 / d ** 0.25)
+    W = bf16_round(torch.randn(N, d, generator=g) * 1.5 / d ** 0.25)
+    lab = torch.randint(0, N, (M,), generator=g)
+    lab[: max(1, M // 8)] = 3  # hot label row: many queries share one item
+    ref_loss, rdU, rdW, _ = orc.ce_fwd_bwd(U, W, lab, scale=0.9, grad_out=2.0)
+    Ud, Wd = dev(U).bfloat16().requires_grad_(True), dev(W).bfloat16().requires_grad_(True)
+    loss = ops.fused_ce(Ud, Wd, dev(lab), scale=0.9)
+    (loss * 2.0).backward()
+    assert abs(float(loss) - float(ref_loss)) <= 1e-5 * abs(float(ref_loss))
+    assert_rel(Ud.grad, rdU, 2 * BF16_RTOL, "dU")
+    assert_rel(Wd.grad, rdW, 2 * BF16_RTOL, "dW")
+
+
+def _seen_lists(g, B, N, max_len):
+    return [torch.randperm(N, generator=g)[: int(torch.randint(0, max_len + 1, (1,), generator=g))].tolist() for _ in range(B)]
+
+
+def _check_topk(vals, ids, ref_scores_masked, K, tol):
+    """ids identical wherever the reference gaps exceed `tol`; values within tol everywhere."""
+    rv, ri = orc.topk_sorted(ref_scores_masked, K)
+    vals, ids = vals.cpu(), ids.cpu().long()
+    valid = rv > orc.MASK_VALUE / 2  # entries past the unmasked catalog: the build reports (-1e23, -1)
+    assert torch.all(ids[~valid] == -1) and torch.all(vals[~valid] == orc.MASK_VALUE)
+    scale = float(rv[valid].abs().max()) if valid.any() else 1.0
+    assert float((vals - rv)[valid].abs().max() if valid.any() else 0.0) <= tol * scale
+    # a rank is "decided" when both neighbours (in the full reference ranking) are > tol away
+    full_sorted = torch.sort(ref_scores_masked, dim=1, descending=True, stable=True).values
+    nxt = full_sorted[:, 1 : K + 1] if full_sorted.shape[1] > K else torch.cat([full_sorted[:, 1:], full_sorted[:, -1:] - 1], 1)
+    kk = rv.shape[1]
+    gap_next = (rv - nxt[:, :kk]).abs() > 4 * tol * scale
+    gap_prev = torch.ones_like(gap_next)
+    gap_prev[:, 1:] = (rv[:, :-1] - rv[:, 1:]).abs() > 4 * tol * scale
+    decided = gap_next & gap_prev & valid
+    assert torch.equal(ids[decided], ri[decided])
+    return float((ids == ri)[valid].float().mean()) if valid.any() else 1.0
+
+
+@pytest.mark.parametrize("B,N,d,K,max_seen", [
+    (1, 200, 64, 20, 10), (130, 1000, 64, 50, 40), (300, 5000, 128, 100, 64), (64, 300, 32, 100, 290),
+    (257, 12101, 64, 50, 30),
+])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_masked_topk_and_metrics(ops, B, N, d, K, max_seen, precision):
+    if precision == "fp32" and d > 64:
+        pytest.skip("fp32x3 mode supports d <= 64")
+    g = torch.Generator().manual_seed(B + N)
+    U = torch.randn(B, d, generator=g) / d ** 0.25
+    W = torch.randn(N, d, generator=g) / d ** 0.25
+    if precision == "bf16":
+        U, W = bf16_round(U), bf16_round(W)
+    seen = _seen_lists(g, B, N, max_seen)
+    seen[0] = []  # empty seen list
+    crow, col = orc.lists_to_csr(seen)
+    tgt = torch.randint(0, N, (B,), generator=g)
+    if seen[-1]:
+        tgt[-1] = seen[-1][0]  # target inside the seen list: guaranteed miss
+    tcrow, tcol = orc.lists_to_csr([[int(x)] for x in tgt])
+    cast = (lambda x: dev(x).bfloat16()) if precision == "bf16" else dev
+    vals, ids = ops.topk_eval(cast(U), cast(W), K, dev(crow), dev(col), precision=precision)
+    masked = orc.mask_seen(orc.score_dense(U, W), crow, col)
+    tol = FP32_RTOL if precision == "fp32" else 2e-6
+    match = _check_topk(vals, ids, masked, K, tol)
+    assert match > 0.99
+    mons = [f"{m}@{k}" for m in ("HITRATE", "NDCG") for k in (1, 5, 10, 20) if k <= K]
+    ref = orc.evaluate_batch(orc.score_dense(U, W), crow, col, tcrow, tcol, mons)
+    got = MX.batch_metrics(ids, dev(tcrow), dev(tcol), N, mons, exact=True)
+    _, ri = orc.topk_sorted(masked, K)
+    if torch.equal(ids.cpu().long()[:, :20], ri[:, :20]):
+        assert got == ref  # bit-identical metrics whenever the ranked ids agree
+    else:
+        assert all(abs(got[k] - ref[k]) <= 2.0 / B for k in ref)
+
+
+def test_topk_without_seen_and_ties(ops):
+    # duplicated item rows => exact score ties: lowest id must win, like the oracle's stable sort
+    g = torch.Generator().manual_seed(9)
+    U = bf16_round(torch.randn(40, 64, generator=g))
+    Wb = bf16_round(torch.randn(100, 64, generator=g))
+    W = torch.cat([Wb, Wb, Wb])  # ids i, i+100, i+200 tie
+    vals, ids = ops.topk_eval(dev(U).bfloat16(), dev(W).bfloat16(), 30)
+    rv, ri = orc.topk_sorted(orc.score_dense(U, W), 30)
+    assert torch.equal(ids.cpu().long(), ri)
+    assert_rel(vals, rv, 2e-6, "tie vals")
+
+
+def test_scatter_add_hot_rows_deterministic(ops):
+    g = torch.Generator().manual_seed(3)
+    n_rows, d, n = 5000, 128, 40000
+    idx = (torch.rand(n, generator=g) ** 6 * n_rows).long()  # heavy duplicates (popularity skew)
+    idx[:100] = 0
+    go = torch.randn(n, d, generator=g)
+    ref = orc.scatter_add_rows(go, idx, n_rows, padding_idx=0)
+    outs = []
+    for _ in range(2):
+        t = torch.zeros(n_rows, d, device="cuda")
+        ops.scatter_add_rows_(t, dev(go), dev(idx), padding_idx=0)
+        outs.append(t)
+    assert torch.equal(outs[0], outs[1])
+    assert_rel(outs[0], ref, 1e-5, "scatter-add")
+    tb = torch.zeros(n_rows, d, device="cuda")
+    ops.scatter_add_rows_(tb, dev(go).bfloat16(), dev(idx), padding_idx=0)
+    assert_rel(tb, orc.scatter_add_rows(bf16_round(go), idx, n_rows, 0), 1e-5, "scatter-add bf16")
+
+
+def test_sharded_partials_merge_like_multi_gpu(ops):
+    """Single-GPU simulation of R row shards: sharded stats/top-K/dW == unsharded."""
+    from recboard_b200 import sharded
+    g = torch.Generator().manual_seed(21)
+    M, N, d, K, R = 200, 3001, 64, 20, 3
+    U = bf16_round(torch.randn(M, d, generator=g) / d ** 0.25)
+    W = bf16_round(torch.randn(N, d, generator=g) / d ** 0.25)
+    lab = torch.randint(0, N, (M,), generator=g)
+    Ud, Wd, labd = dev(U).bfloat16(), dev(W).bfloat16(), dev(lab)
+    stats, tops = [], []
+    for r in range(R):
+        a, b = sharded.shard_bounds(N, R, r)
+        stats.append(torch.stack(ops.ce_rowstats(Ud, Wd[a:b].contiguous(), labd, label_base=a)))
+        tops.append(ops.topk_eval(Ud, Wd[a:b].contiguous(), K, id_base=a))
+    lse, ll = sharded.merge_rowstats(torch.stack(stats))
+    rm, rl, rll = orc.ce_rowstats(U, W, lab)
+    assert float((lse.cpu() - (rm + torch.log(rl))).abs().max()) < 1e-5
+    assert_rel(ll, rll, 1e-5, "label logit")
+    mv, mi = ops.topk_merge(torch.stack([t[0] for t in tops]), torch.stack([t[1] for t in tops]))
+    gv, gi = ops.topk_eval(Ud, Wd, K)
+    assert torch.equal(mi, gi) and torch.equal(mv, gv)
+    # gradient shards: dW of shard == rows of the unsharded dW; partial dU sum == dU
+    _, rdU, rdW, _ = orc.ce_fwd_bwd(U, W, lab)
+    dU_sum = torch.zeros(M, d, device="cuda")
+    for r in range(R):
+        a, b = sharded.shard_bounds(N, R, r)
+        dU, dW, _ = ops.ce_backward(Ud, Wd[a:b].contiguous(), labd, lse, 1.0 / M, label_base=a)
+        dU_sum += dU
+        assert_rel(dW, rdW[a:b], 2 * BF16_RTOL * float(rdW.abs().max() / rdW[a:b].abs().max()), f"dW shard {r}")
+    assert_rel(dU_sum, rdU, 2 * BF16_RTOL, "dU")
+
+
+def test_full_size_properties(ops):
+    """BASELINE configs[2] size (M=4096, N=1M, d=128, bf16): size-independent properties."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, N, d, K = 4096, 1_000_000, 128, 50
+    U = (torch.randn(M, d, generator=g, device="cuda") * 1.5 / d ** 0.25).bfloat16()
+    W = (torch.randn(N, d, generator=g, device="cuda") * 1.5 / d ** 0.25).bfloat16()
+    lab = torch.randint(0, N, (M,), generator=g, device="cuda")
+    m, l, ll = ops.ce_rowstats(U, W, lab)
+    lse = m + torch.log(l)
+    # (1) label logit == direct dot product; (2) lse >= max and lse <= max + log N
+    direct = (U.float() * W[lab].float()).sum(-1)
+    assert_rel(ll, direct.cpu(), 1e-5, "label logit")
+    assert torch.all(lse >= m) and torch.all(lse <= m + np.log(N) + 1e-3)
+    # (3) rows of softmax - onehot sum to zero  =>  sum_j dW_j . 1 relation: sum over items of dW == sum_i (sum_j G_ij) u_i = 0
+    dU, dW, _ = ops.ce_backward(U, W, lab, lse, 1.0 / M)
+    col_sum = dW.double().sum(0)
+    ref_scale = float(dW.double().abs().sum(0).max())
+    assert float(col_sum.abs().max()) <= 5e-3 * ref_scale
+    # (4) split-invariance: stats of two half catalogs merge to the full stats
+    from recboard_b200 import sharded
+    h = N // 2
+    s0 = torch.stack(ops.ce_rowstats(U, W[:h], lab, label_base=0))
+    s1 = torch.stack(ops.ce_rowstats(U, W[h:], lab, label_base=h))
+    lse2, ll2 = sharded.merge_rowstats(torch.stack([s0, s1]))
+    assert float((lse2 - lse).abs().max()) < 1e-4 and torch.equal(ll2, ll)
+    # (5) top-K is sorted, unique, unmasked, and each value is the true score of its id
+    crow = torch.arange(0, (M + 1) * 4, 4, device="cuda")
+    col = torch.sort(torch.randint(0, N, (M, 4), generator=g, device="cuda"), dim=1).values.reshape(-1)
+    vals, ids = ops.topk_eval(U, W, K, crow, col)
+    assert torch.all(vals[:, :-1] >= vals[:, 1:])
+    true = (U.float().unsqueeze(1) * W[ids.long()].float()).sum(-1)
+    assert_rel(vals, true.cpu(), 1e-5, "top-K values")
+    assert not torch.any(ids.unsqueeze(-1) == col.view(M, 1, 4))
+    # (6) a dense spot check of 8 rows against torch
+    S = U[:8].float() @ W.float().T
+    S[torch.arange(8, device="cuda").repeat_interleave(4), col[:32]] = -1e23
+    rv, ri = torch.sort(S, dim=1, descending=True, stable=True)
+    assert torch.equal(ri[:, :K], ids[:8].long()) or float((rv[:, :K] - vals[:8]).abs().max()) < 1e-5

@@ -1,0 +1,79 @@
+"""Host logic: metric reduction from a top-K list == the oracle's dense evaluation; synthetic
+generators; shard bounds."""
+import torch
+
+from oracle import reference_path as orc
+from recboard_b200 import metrics as MX
+from recboard_b200 import sharded, synth
+
+MONS = ["HITRATE@1", "HITRATE@5", "HITRATE@10", "NDCG@5", "NDCG@10", "RECALL@10", "PRECISION@5", "MRR@10"]
+
+
+def _case(seed, B=33, N=257, multi=False):
+    g = torch.Generator().manual_seed(seed)
+    scores = torch.randn(B, N, generator=g)
+    seen = [torch.randint(0, N, (9,), generator=g).tolist() for _ in range(B)]
+    tg = [torch.randint(0, N, (3 if multi else 1,), generator=g).tolist() for _ in range(B)]
+    return scores, orc.lists_to_csr(seen), orc.lists_to_csr(tg)
+
+
+def test_metrics_from_topk_bit_identical_to_dense_oracle():
+    for seed, multi in ((0, False), (1, False), (2, True)):
+        scores, (crow, col), (tcrow, tcol) = _case(seed, multi=multi)
+        dense = orc.evaluate_batch(scores, crow, col, tcrow, tcol, MONS)
+        _, ids = orc.topk_sorted(orc.mask_seen(scores, crow, col), 10)
+        got = MX.batch_metrics(ids.int(), tcrow, tcol, scores.shape[1], MONS, exact=True)
+        assert got == dense  # bit-identical floats
+
+
+def test_missing_entries_never_hit():
+    ids = torch.tensor([[3, -1, -1]], dtype=torch.int32)
+    tcrow, tcol = MX.lists_to_csr([[0]])
+    assert MX.batch_metrics(ids, tcrow, tcol, 5, ["HITRATE@3"])["HITRATE@3"] == 0.0
+
+
+def test_average_meter_weighting():
+    m, o = MX.AverageMeter(), orc.AverageMeter()
+    for v, n in ((0.25, 512), (0.5, 100)):
+        m.update(v, n); o.update(v, n)
+    assert m.avg == o.avg == (0.25 * 512 + 0.5 * 100) / 612
+
+
+def test_shard_bounds_cover_catalog():
+    for n, w in ((10, 3), (1_000_000, 8), (7, 8)):
+        spans = [sharded.shard_bounds(n, w, r) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_merge_rowstats_matches_oracle():
+    g = torch.Generator().manual_seed(5)
+    U, W = torch.randn(20, 16, generator=g), torch.randn(90, 16, generator=g)
+    lab = torch.randint(0, 90, (20,), generator=g)
+    parts = []
+    for a, b in ((0, 31), (31, 90)):
+        S = orc.score_dense(U, W[a:b])
+        m = S.max(1).values
+        inside = (lab >= a) & (lab < b)
+        ll = torch.where(inside, S.gather(1, (lab - a).clamp(0, b - a - 1)[:, None]).squeeze(1), torch.zeros(20))
+        parts.append(torch.stack([m, torch.exp(S - m[:, None]).sum(1), ll]))
+    lse, ll = sharded.merge_rowstats(torch.stack(parts))
+    m, l, ll_ref = orc.ce_rowstats(U, W, lab)
+    torch.testing.assert_close(lse, m + torch.log(l), rtol=1e-6, atol=1e-6)
+    assert torch.equal(ll, ll_ref)
+
+
+def test_synth_shapes_and_invariants():
+    g = torch.Generator().manual_seed(0)
+    dev = torch.device("cpu")
+    ids = synth.zipf_ids(5000, 1000, g, dev)
+    assert ids.min() >= 0 and ids.max() < 1000
+    crow, col = synth.seen_csr(64, 1000, g, dev)
+    assert crow[0] == 0 and crow[-1] == col.numel()
+    for r in range(64):
+        seg = col[crow[r]:crow[r + 1]]
+        assert torch.all(seg[1:] > seg[:-1])  # sorted unique per row
+    t = synth.targets(64, 1000, g, dev, (crow, col), frac_in_seen=1.0)
+    assert all(int(t[r]) in col[crow[r]:crow[r + 1]].tolist() for r in range(64))
+    s = synth.sequences(16, 50, 1000, g, dev)
+    assert s.shape == (16, 50) and (s[:, -1] > 0).all() and s.max() <= 1000
