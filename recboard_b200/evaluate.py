@@ -1,0 +1,99 @@
+"""Fused evaluation sweep: the override point of ``freerec.launcher.Coach.evaluate`` whose in-tree
+statement is UniSRec/main.py:400-447.
+
+Reference, per batch:   scores = model(data, ranking="full")            dense (B,N)         :408
+                        seen = Item.to_csr(data[ISeen]).to_dense().bool(); scores[seen] = -1e23  :410-413
+                        targets = Item.to_csr(data[IUnseen]).to_dense()  dense (B,N)         :414
+                        monitor(scores, targets, n=bsz, ...)  -> one torch.topk per metric@k :428-435
+
+Fused, per batch:       ids = model.recommend_topk(data, Kmax, seen CSR)  one kernel sweep, (B,Kmax)
+                        metric@k for every k from that one sorted list (recboard_b200.metrics)
+                        monitor(precomputed batch means, n=bsz) through identity metrics
+                        (the pattern of TIGER/train_rqvae.py:224-230)
+
+``FusedEvalCoach`` is a mixin for a freerec ``Coach`` subclass; ``evaluate_sweep`` is the same loop
+without freerec (used by bench.py and the tests).
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, Optional, Sequence, Tuple
+
+import torch
+
+from . import metrics as MX
+
+
+def _to_csr(field_value, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``data[ISeen]`` / ``data[IUnseen]`` arrive as ragged lists or (B,k) tensors of 0-based item ids."""
+    if isinstance(field_value, tuple) and len(field_value) == 2 and all(isinstance(x, torch.Tensor) for x in field_value):
+        crow, col = field_value
+        return crow.to(device), col.to(device)
+    if isinstance(field_value, torch.Tensor) and field_value.dim() == 2:
+        B, k = field_value.shape
+        vals, _ = torch.sort(field_value.to(device), dim=1)
+        if k > 1:  # unique per row
+            keep = torch.ones_like(vals, dtype=torch.bool)
+            keep[:, 1:] = vals[:, 1:] != vals[:, :-1]
+            crow = torch.zeros(B + 1, dtype=torch.int64, device=device)
+            crow[1:] = keep.sum(1).cumsum(0)
+            return crow, vals[keep].contiguous()
+        return torch.arange(B + 1, device=device, dtype=torch.int64), vals.reshape(-1).contiguous()
+    return MX.lists_to_csr(field_value, device)
+
+
+@torch.no_grad()
+def evaluate_sweep(model, batches: Iterable[Dict], monitors: Sequence[str], n_items: int, remove_seen: bool = True,
+                   seen_key=None, unseen_key=None, size_key=None, exact: bool = True) -> Dict[str, float]:
+    """bsz-weighted means of every ``METRIC@k`` over an evaluation sweep (UniSRec/main.py:400-435).
+    ``model`` provides ``reset_ranking_buffers()`` and ``recommend_topk(data, K, seen_crow, seen_col)``."""
+    seen_key = seen_key if seen_key is not None else model.ISeen
+    unseen_key = unseen_key if unseen_key is not None else model.IUnseen
+    kmax = MX.kmax_of(monitors)
+    meters = {m.upper(): MX.AverageMeter() for m in monitors}
+    model.reset_ranking_buffers()                                                   # :401
+    for data in batches:
+        device = next(model.parameters()).device
+        seen_crow = seen_col = None
+        if remove_seen:                                                             # :409
+            seen_crow, seen_col = _to_csr(data[seen_key], device)
+        tcrow, tcol = _to_csr(data[unseen_key], device)                             # :414
+        bsz = int(data[size_key]) if size_key is not None and size_key in data else tcrow.numel() - 1   # :403
+        _, ids = model.recommend_topk(data, kmax, seen_crow, seen_col)              # :408-413 fused
+        for name, v in MX.batch_metrics(ids, tcrow, tcol, n_items, monitors, exact=exact).items():
+            meters[name].update(v, bsz)                                             # :428-435
+    return {k: m.avg for k, m in meters.items()}
+
+
+class FusedEvalCoach:
+    """Mixin for a ``freerec.launcher.Coach`` subclass (listed before ``Coach`` in the bases).
+
+    ``set_other`` registers identity metrics named like the configured monitors so that the
+    precomputed batch means flow through ``self.monitor`` unchanged (bsz weighting, best-epoch
+    tracking, logging stay freerec's)."""
+
+    def set_other(self):
+        for monitor in self.cfg.monitors:
+            if "@" not in monitor:
+                continue
+            metric, k = monitor.split("@")
+            self.register_metric(f"{metric.upper()}@{k}", func=lambda x: x, fmt=".4f", best_caster=max)
+
+    @torch.no_grad()
+    def evaluate(self, epoch: int, step: int = -1, mode: str = "valid"):
+        model = self.get_res_sys_arch()
+        model.reset_ranking_buffers()                                               # UniSRec/main.py:401
+        monitors = [m for m in self.cfg.monitors if "@" in m]
+        kmax = MX.kmax_of(monitors)
+        n_items = model.Item.count
+        for data in self.dataloader:
+            bsz = data[self.Size]                                                   # :403
+            data = self.dict_to_device(data)                                        # :405
+            if self.cfg.ranking != "full":
+                raise NotImplementedError("the fused evaluate covers ranking='full' (UniSRec/main.py:407-414)")
+            seen_crow = seen_col = None
+            if self.remove_seen:                                                    # :409
+                seen_crow, seen_col = _to_csr(data[self.ISeen], self.device)
+            tcrow, tcol = _to_csr(data[self.IUnseen], self.device)                  # :414
+            _, ids = model.recommend_topk(data, kmax, seen_crow, seen_col)
+            for name, v in MX.batch_metrics(ids, tcrow, tcol, n_items, monitors).items():
+                self.monitor(v, n=bsz, reduction="mean", mode=mode, pool=[name])    # :428-435

@@ -231,6 +231,8 @@ def topk_eval(U: torch.Tensor, W: torch.Tensor, K: int, seen_crow: Optional[torc
         if seen_crow.numel() != B + 1:
             raise ValueError("seen_crow must have B+1 entries")
         nnz = seen_col.numel()
+        if nnz == 0:  # nothing to mask: same as no seen lists
+            seen_crow = seen_col = None
     vals = torch.empty(B, K, dtype=torch.float32, device=dev)
     ids = torch.empty(B, K, dtype=torch.int32, device=dev)
     ws, n = _ws(dev, L.OP_TOPK_EVAL, B, N, d, K=K, mode=mode, nnz=nnz)
