@@ -87,7 +87,7 @@ int rb_ce_bwd(const void* U, const void* W, const float* bias, float scale, cons
  * row; pass NULL/NULL to keep seen items).  top_ids are global (id_base + local); missing entries
  * (fewer than K unmasked items) are (RB_MASKED_SCORE, -1).  Replaces, without a dense (B,N):
  * `recommend_from_full` + `scores[seen] = -1e23` + one `torch.topk` per metric@k
- * (UniSRec/main.py:408-435).  K <= 224. */
+ * (UniSRec/main.py:408-435).  K <= 256. */
 int rb_topk_eval(const void* U, const void* W, const float* bias, float scale,
                  const int64_t* seen_crow, const int64_t* seen_col, int64_t seen_nnz, int64_t id_base,
                  int64_t B, int64_t N, int d, int dtype, int mode, int K, float* top_vals,

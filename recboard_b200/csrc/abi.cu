@@ -8,8 +8,8 @@
 #include <string>
 
 #include "../../include/recboard_b200.h"
-#include "simt.cuh"
 #include "sweep.cuh"
+#include "simt.cuh"
 
 using namespace rb;
 
@@ -163,29 +163,29 @@ static int check_common(const void* U, const void* W, long long M, long long N, 
 template <class C>
 static int launch_sweep_t(const CUtensorMap& ts, const CUtensorMap& ty, const SweepArgs& a, int grid, cudaStream_t st) {
   RB_CUDA(cudaFuncSetAttribute(sweep_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-  sweep_kernel<C><<<grid, 192, C::SMEM_BYTES, st>>>(ts, ty, a);
+  sweep_kernel<C><<<grid, SWEEP_THREADS, C::SMEM_BYTES, st>>>(ts, ty, a);
   RB_LAUNCH_CHECK("sweep_kernel");
   return 0;
 }
 
 // NS chosen so that SMEM stays under 227 KB
-template <int EPI, bool ROWS, int CAPE>
+template <int EPI, bool ROWS>
 static int launch_sweep(int mode, int kc, const CUtensorMap& ts, const CUtensorMap& ty, const SweepArgs& a, int grid,
                         cudaStream_t st) {
   if (mode == RB_MODE_BF16) {
     if constexpr (EPI == EPI_GRAD) {
-      if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 1, BN, 4, ROWS, CAPE>>(ts, ty, a, grid, st);
-      if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 2, BN, 3, ROWS, CAPE>>(ts, ty, a, grid, st);
+      if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 1, BN, 4, ROWS>>(ts, ty, a, grid, st);
+      if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 2, BN, 3, ROWS>>(ts, ty, a, grid, st);
       return fail(RB_E_UNSUPPORTED, "CE backward supports d <= 128 in bf16 mode");
     } else {
-      if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 1, BN, 6, ROWS, CAPE>>(ts, ty, a, grid, st);
-      if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 2, BN, 4, ROWS, CAPE>>(ts, ty, a, grid, st);
-      if (kc <= 4) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 4, BN, 2, ROWS, CAPE>>(ts, ty, a, grid, st);
+      if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 1, BN, 6, ROWS>>(ts, ty, a, grid, st);
+      if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 2, BN, 4, ROWS>>(ts, ty, a, grid, st);
+      if (kc <= 4) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 4, BN, 2, ROWS>>(ts, ty, a, grid, st);
     }
   } else {
     if constexpr (EPI != EPI_GRAD) {
-      if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 1, BN, 4, ROWS, CAPE>>(ts, ty, a, grid, st);
-      if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 2, BN, 2, ROWS, CAPE>>(ts, ty, a, grid, st);
+      if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 1, BN, 4, ROWS>>(ts, ty, a, grid, st);
+      if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 2, BN, 2, ROWS>>(ts, ty, a, grid, st);
     } else {
       return fail(RB_E_UNSUPPORTED, "CE backward is bf16-mode only in this build");
     }
@@ -294,7 +294,7 @@ extern "C" int rb_score_dense(const void* U, const void* W, const float* bias, f
   SweepArgs a{};
   a.n_stat = (int)M; a.n_strm = (int)N; a.n_stat_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
   a.n_splits = p.n_splits; a.d = d; a.scale = scale; a.bias = bias; a.out = S; a.ld_out = N;
-  return launch_sweep<EPI_DENSE, true, 8>(mode, kc_for(d, mode), ts, ty, a, p.grid, st);
+  return launch_sweep<EPI_DENSE, true>(mode, kc_for(d, mode), ts, ty, a, p.grid, st);
 }
 
 // ============================================================================ CE fwd
@@ -326,7 +326,7 @@ extern "C" int rb_ce_fwd(const void* U, const void* W, const float* bias, float 
   a.n_stat = (int)M; a.n_strm = (int)N; a.n_stat_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
   a.n_splits = p.n_splits; a.d = d; a.scale = scale; a.bias = bias; a.labels = lab32;
   a.part_m2 = pm2; a.part_l = pl; a.part_ll = pll;
-  if (int r = launch_sweep<EPI_LSE, true, 8>(mode, kc_for(d, mode), ts, ty, a, p.grid, st)) return r;
+  if (int r = launch_sweep<EPI_LSE, true>(mode, kc_for(d, mode), ts, ty, a, p.grid, st)) return r;
   lse_merge_kernel<<<(int)((M + 255) / 256), 256, 0, st>>>(pm2, pl, pll, p.n_splits, m_pad, (int)M, row_max, row_sumexp, label_logit);
   RB_LAUNCH_CHECK("lse_merge_kernel");
   return 0;
@@ -368,7 +368,7 @@ extern "C" int rb_ce_bwd(const void* U, const void* W, const float* bias, float 
     a.n_stat = (int)M; a.n_strm = (int)N; a.n_stat_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
     a.n_splits = p.n_splits; a.d = d; a.scale = scale; a.bias = bias; a.labels = lab32; a.lse2 = lse2;
     a.gscale = gs; a.gscale_dev = grad_scale_dev; a.acc_out = part;
-    if (int r = launch_sweep<EPI_GRAD, true, 8>(mode, kc, ts, ty, a, p.grid, st)) return r;
+    if (int r = launch_sweep<EPI_GRAD, true>(mode, kc, ts, ty, a, p.grid, st)) return r;
     if (p.n_splits > 1) {
       const long long n = M * d;
       partial_sum_kernel<<<(int)std::min<long long>((n + 255) / 256, dv.sms * 8), 256, 0, st>>>(part, p.n_splits, n, dU);
@@ -388,7 +388,7 @@ extern "C" int rb_ce_bwd(const void* U, const void* W, const float* bias, float 
     a.n_stat = (int)N; a.n_strm = (int)M; a.n_stat_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
     a.n_splits = p.n_splits; a.d = d; a.scale = scale; a.bias = bias; a.labels = lab32; a.lse2 = lse2;
     a.gscale = gs; a.gscale_dev = grad_scale_dev; a.acc_out = part; a.rowsum_out = rs_part;
-    if (int r = launch_sweep<EPI_GRAD, false, 8>(mode, kc, ts, ty, a, p.grid, st)) return r;
+    if (int r = launch_sweep<EPI_GRAD, false>(mode, kc, ts, ty, a, p.grid, st)) return r;
     if (p.n_splits > 1) {
       const long long n = N * d;
       partial_sum_kernel<<<(int)std::min<long long>((n + 255) / 256, dv.sms * 8), 256, 0, st>>>(part, p.n_splits, n, dW);
@@ -403,17 +403,9 @@ extern "C" int rb_ce_bwd(const void* U, const void* W, const float* bias, float 
 }
 
 // ========================================================================= top-K eval
-static int launch_topk_merge(const float* vals, const int* ids, const int* cnt, int n_lists, long long list_stride,
-                             int cap, long long rows, int K, int id_add, float* ov, int* oi, cudaStream_t st) {
-  const long long threads = rows * 32;
-  const int grid = static_cast<int>((threads + 127) / 128);
-  if (K <= 128)
-    topk_merge_kernel<4><<<grid, 128, 0, st>>>(vals, ids, cnt, n_lists, list_stride, cap, rows, K, id_add, ov, oi);
-  else
-    topk_merge_kernel<8><<<grid, 128, 0, st>>>(vals, ids, cnt, n_lists, list_stride, cap, rows, K, id_add, ov, oi);
-  RB_LAUNCH_CHECK("topk_merge_kernel");
-  return 0;
-}
+// Three launches: (1) sweep with the tile-max epilogue, (2) per-row selection of the <= 2K-1 tiles that can
+// hold a top-K member, (3) exact re-scoring of those tiles + masked top-K.
+static int topk_selcap(int K) { return ((2 * K + 31) / 32) * 32; }
 
 extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, float scale, const int64_t* seen_crow,
                             const int64_t* seen_col, int64_t seen_nnz, int64_t id_base, int64_t B, int64_t N, int d,
@@ -423,7 +415,7 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (int r = check_common(U, W, B, N, d, dtype, mode)) return r;
   if (!top_vals || !top_ids) return fail(RB_E_ARG, "null output");
-  if (K < 1 || K > 224) return fail(RB_E_UNSUPPORTED, "K=%d outside [1,224]", K);
+  if (K < 1 || K > 256) return fail(RB_E_UNSUPPORTED, "K=%d outside [1,256]", K);
   if (!(scale > 0.f)) return fail(RB_E_UNSUPPORTED, "top-K needs scale > 0");
   if ((seen_crow == nullptr) != (seen_col == nullptr)) return fail(RB_E_ARG, "seen_crow/seen_col must both be given");
   if (!ws) return fail(RB_E_WORKSPACE, "workspace required");
@@ -432,9 +424,7 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
   if (int r = stage_operand(U, B, d, mode, b, ou, st)) return r;
   if (int r = stage_operand(W, N, d, mode, b, ow, st)) return r;
   Plan p = make_plan(B, N, dv.sms, 1 << 20);
-  const long long b_pad = 1ll * p.n_stat_tiles * 128;
-  const int cape = (K <= 96) ? 4 : 8;
-  const int cap = 32 * cape;
+  const int selcap = topk_selcap(K);
   int* crow32 = nullptr; int* col32 = nullptr;
   long long nnz = 0;
   if (seen_crow) {
@@ -443,9 +433,9 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
     crow32 = b.take<int>(B + 1);
     col32 = b.take<int>(std::max<long long>(nnz, 1));
   }
-  float* cval = b.take<float>(static_cast<size_t>(p.n_splits) * b_pad * cap);
-  int* cid = b.take<int>(static_cast<size_t>(p.n_splits) * b_pad * cap);
-  int* ccnt = b.take<int>(static_cast<size_t>(p.n_splits) * b_pad);
+  float* tmax = b.take<float>(static_cast<size_t>(B) * p.n_strm_tiles);
+  int* sel = b.take<int>(static_cast<size_t>(B) * selcap);
+  int* selcnt = b.take<int>(B);
   if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
   if (seen_crow) {
     const long long n = std::max<long long>(B + 1, nnz);
@@ -457,21 +447,39 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
   if (int r = make_tmap(&ty, ow.ptr, ow.bf16, N, ow.cols, BN)) return r;
   SweepArgs a{};
   a.n_stat = (int)B; a.n_strm = (int)N; a.n_stat_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
-  a.n_splits = p.n_splits; a.d = d; a.scale = scale; a.bias = bias; a.K = K; a.id_base = 0;
-  a.seen_crow = crow32; a.seen_col = col32; a.cand_val = cval; a.cand_id = cid; a.cand_cnt = ccnt;
-  int r;
-  if (cape == 4) r = launch_sweep<EPI_TOPK, true, 4>(mode, kc_for(d, mode), ts, ty, a, p.grid, st);
-  else r = launch_sweep<EPI_TOPK, true, 8>(mode, kc_for(d, mode), ts, ty, a, p.grid, st);
-  if (r) return r;
-  return launch_topk_merge(cval, cid, ccnt, p.n_splits, b_pad, cap, B, K, (int)id_base, top_vals, top_ids, st);
+  a.n_splits = p.n_splits; a.d = d; a.scale = scale; a.bias = bias;
+  a.seen_crow = crow32; a.seen_col = col32; a.tile_max = tmax;
+  if (int r = launch_sweep<EPI_TOPK, true>(mode, kc_for(d, mode), ts, ty, a, p.grid, st)) return r;
+  const int grid_w = static_cast<int>((B * 32 + 127) / 128);
+  if (K <= 128) tilemax_select_kernel<4><<<grid_w, 128, 0, st>>>(tmax, p.n_strm_tiles, B, K, selcap, sel, selcnt);
+  else tilemax_select_kernel<8><<<grid_w, 128, 0, st>>>(tmax, p.n_strm_tiles, B, K, selcap, sel, selcnt);
+  RB_LAUNCH_CHECK("tilemax_select_kernel");
+  const int grid_r = static_cast<int>((B + 3) / 4);
+  const int id_add = static_cast<int>(id_base);
+  if (dtype == RB_DTYPE_BF16) {
+    const __nv_bfloat16* Ub = static_cast<const __nv_bfloat16*>(U); const __nv_bfloat16* Wb = static_cast<const __nv_bfloat16*>(W);
+    if (K <= 128) topk_refine_kernel<__nv_bfloat16, 4><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, crow32, col32, sel, selcnt, selcap, K, id_add, top_vals, top_ids);
+    else topk_refine_kernel<__nv_bfloat16, 8><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, crow32, col32, sel, selcnt, selcap, K, id_add, top_vals, top_ids);
+  } else {
+    const float* Uf = static_cast<const float*>(U); const float* Wf = static_cast<const float*>(W);
+    if (K <= 128) topk_refine_kernel<float, 4><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, crow32, col32, sel, selcnt, selcap, K, id_add, top_vals, top_ids);
+    else topk_refine_kernel<float, 8><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, crow32, col32, sel, selcnt, selcap, K, id_add, top_vals, top_ids);
+  }
+  RB_LAUNCH_CHECK("topk_refine_kernel");
+  return 0;
 }
 
 extern "C" int rb_topk_merge(const float* vals, const int32_t* ids, int R, int64_t B, int K, float* out_vals,
                              int32_t* out_ids, rb_stream_t stream) {
   DevInfo dv; if (int r = get_dev(dv)) return r;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (!vals || !ids || !out_vals || !out_ids) return fail(RB_E_ARG, "null pointer");
   if (R < 1 || B < 1 || K < 1 || K > 256) return fail(RB_E_ARG, "bad shape R=%d B=%lld K=%d", R, (long long)B, K);
-  return launch_topk_merge(vals, ids, nullptr, R, B, K, B, K, 0, out_vals, out_ids, reinterpret_cast<cudaStream_t>(stream));
+  const int grid = static_cast<int>((B * 32 + 127) / 128);
+  if (K <= 128) topk_merge_kernel<4><<<grid, 128, 0, st>>>(vals, ids, R, B, K, out_vals, out_ids);
+  else topk_merge_kernel<8><<<grid, 128, 0, st>>>(vals, ids, R, B, K, out_vals, out_ids);
+  RB_LAUNCH_CHECK("topk_merge_kernel");
+  return 0;
 }
 
 // ========================================================================== workspace
@@ -499,10 +507,8 @@ extern "C" size_t rb_workspace_bytes(int op, int64_t M, int64_t N, int d, int K,
     }
     case RB_OP_TOPK_EVAL: {
       Plan p = make_plan(M, N, sms, 1 << 20);
-      const size_t b_pad = static_cast<size_t>(p.n_stat_tiles) * 128;
-      const int cap = (K <= 96) ? 128 : 256;
       return need + staged_bytes(M, d, mode) + staged_bytes(N, d, mode) + (M + 1 + std::max<int64_t>(nnz, 1)) * 4 +
-             static_cast<size_t>(p.n_splits) * b_pad * (cap * 8 + 4) + 2048;
+             static_cast<size_t>(M) * (static_cast<size_t>(p.n_strm_tiles) + topk_selcap(K) + 1) * 4 + 2048;
     }
     default: return 0;
   }

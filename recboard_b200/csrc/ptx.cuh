@@ -185,18 +185,49 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 // Instruction descriptor for kind::f16 / kind::tf32 with fp32 accumulation.
 //   [4,6) D fmt (1 = f32)  [7,10) A fmt  [10,13) B fmt (0 f16, 1 bf16, 2 tf32)
 //   [15] A major (0 = K)   [16] B major (0 = K, 1 = MN)   [17,23) N >> 3   [24,29) M >> 4
-__host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t M, uint32_t N,
-                                                  uint32_t a_mn_major, uint32_t b_mn_major) {
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | (a_mn_major << 15) | (b_mn_major << 16) |
+__host__ __device__ constexpr uint32_t make_idesc2(uint32_t a_fmt, uint32_t b_fmt, uint32_t M, uint32_t N,
+                                                   uint32_t a_mn_major, uint32_t b_mn_major) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | (a_mn_major << 15) | (b_mn_major << 16) |
          ((N >> 3) << 17) | ((M >> 4) << 24);
 }
-constexpr uint32_t FMT_BF16 = 1, FMT_TF32 = 2;
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t M, uint32_t N,
+                                                  uint32_t a_mn_major, uint32_t b_mn_major) {
+  return make_idesc2(fmt, fmt, M, N, a_mn_major, b_mn_major);
+}
+constexpr uint32_t FMT_F16 = 0, FMT_BF16 = 1, FMT_TF32 = 2;
 
 // ------------------------------------------------------------------- math
+// order-preserving map float -> uint32 (and back)
+__device__ __forceinline__ uint32_t f32_orderable(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float f32_from_orderable(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// {2^x0 (low half), 2^x1 (high half)} as packed f16: one MUFU op for two exponentials.
+// x = -inf (or below the f16 range) gives exactly 0.
+__device__ __forceinline__ uint32_t ex2_f16x2(float x0, float x1) {
+  uint32_t h;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+  asm("ex2.approx.f16x2 %0, %0;" : "+r"(h));
+  return h;
+}
+__device__ __forceinline__ uint32_t hsub2_u32(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ float2 h2_to_f2(uint32_t h) {
+  float lo, hi;
+  asm("{\n\t.reg .b16 l, u;\n\tmov.b32 {l, u}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, u;\n\t}\n"
+      : "=f"(lo), "=f"(hi) : "r"(h));
+  return make_float2(lo, hi);
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;

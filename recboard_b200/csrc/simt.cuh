@@ -218,33 +218,28 @@ __global__ void partial_sum_kernel(const float* __restrict__ part, int n_splits,
   }
 }
 
-// ------------------------------------------------------------------------- top-K merge
-__device__ __forceinline__ uint32_t f32_orderable(float f) {
-  const uint32_t u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float f32_from_orderable(uint32_t o) {
-  return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
-}
+// ------------------------------------------------------------------------- top-K machinery
 // key order: score desc, then id asc
 __device__ __forceinline__ unsigned long long topk_key(float v, int id) {
   return (static_cast<unsigned long long>(f32_orderable(v)) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(id));
 }
 
-template <int E>
-__device__ __forceinline__ void warp_bitonic_stage64(unsigned long long (&v)[E], int k, int j) {
+// Warp-wide bitonic network over 32*E values held E per lane (blocked: element index = lane*E + e).
+// One compare-exchange stage (k = block size, j = partner distance); "up" blocks sort descending.
+template <typename T, int E>
+__device__ __forceinline__ void warp_bitonic_stage(T (&v)[E], int k, int j) {
   const uint32_t lane = lane_id();
   if (j >= E) {
     const int lj = j / E;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const int i = lane * E + e;
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, v[e], lj);
+      const T other = __shfl_xor_sync(0xffffffffu, v[e], lj);
       const bool up = ((i & k) == 0);
       const bool lower = ((i & j) == 0);
       const bool take_max = (up == lower);
-      const unsigned long long mx = v[e] > other ? v[e] : other;
-      const unsigned long long mn = v[e] > other ? other : v[e];
+      const T mx = v[e] > other ? v[e] : other;
+      const T mn = v[e] > other ? other : v[e];
       v[e] = take_max ? mx : mn;
     }
   } else {
@@ -253,35 +248,216 @@ __device__ __forceinline__ void warp_bitonic_stage64(unsigned long long (&v)[E],
       if ((e & j) == 0) {
         const int i = lane * E + e;
         const bool up = ((i & k) == 0);
-        const unsigned long long a = v[e], b = v[e + j];
-        const unsigned long long hi = a > b ? a : b, lo = a > b ? b : a;
+        const T a = v[e], b = v[e + j];
+        const T hi = a > b ? a : b, lo = a > b ? b : a;
         v[e] = up ? hi : lo;
         v[e + j] = up ? lo : hi;
       }
     }
   }
 }
-template <int E>
-__device__ __forceinline__ void warp_bitonic_sort64_desc(unsigned long long (&v)[E]) {
+template <typename T, int E>
+__device__ __forceinline__ void warp_bitonic_sort_desc(T (&v)[E]) {
 #pragma unroll
   for (int k = 2; k <= 32 * E; k <<= 1)
 #pragma unroll
-    for (int j = k >> 1; j >= 1; j >>= 1) warp_bitonic_stage64<E>(v, k, j);
+    for (int j = k >> 1; j >= 1; j >>= 1) warp_bitonic_stage<T, E>(v, k, j);
 }
 // v is bitonic (as produced by max(best[i], new[n-1-i])): finish with the last merge network, descending
-template <int E>
-__device__ __forceinline__ void warp_bitonic_merge64_desc(unsigned long long (&v)[E]) {
+template <typename T, int E>
+__device__ __forceinline__ void warp_bitonic_merge_desc(T (&v)[E]) {
 #pragma unroll
-  for (int j = 16 * E; j >= 1; j >>= 1) warp_bitonic_stage64<E>(v, 64 * E /* bit never set => all "up" */, j);
+  for (int j = 16 * E; j >= 1; j >>= 1) warp_bitonic_stage<T, E>(v, 64 * E /* bit never set => all "up" */, j);
+}
+// best <- the 32*E largest of (best U cur); both sorted descending on entry (cur is consumed)
+template <typename T, int E>
+__device__ __forceinline__ void warp_topk_absorb(T (&best)[E], T (&cur)[E]) {
+  const uint32_t lane = lane_id();
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const T rev = __shfl_sync(0xffffffffu, cur[E - 1 - e], 31 - lane);
+    best[e] = best[e] > rev ? best[e] : rev;
+  }
+  warp_bitonic_merge_desc<T, E>(best);
+}
+// element `idx` (0-based rank) of a blocked warp array
+template <typename T, int E>
+__device__ __forceinline__ T warp_blocked_get(const T (&v)[E], int idx) {
+  T out = v[0];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const T c = __shfl_sync(0xffffffffu, v[e], idx / E);
+    if (e == idx % E) out = c;
+  }
+  return out;
 }
 
-// One warp per query row: merge `n_lists` candidate lists of up to `cap` entries each
-// (list l of row i at base + (l*list_stride + i)*cap, length cnt[l*list_stride+i] or `cap` when cnt==nullptr)
-// into the K best, sorted (score desc, id asc). E*32 >= K.
+// ---- top-K pass 2a: per row, the K-th largest tile maximum tau and the list of tiles that can hold
+// a top-K member: every tile with max > tau (at most K-1 of them) plus the first K tiles with
+// max == tau (lowest ids first: the tie rule), in ascending tile order.  One warp per row.
 template <int E>
-__global__ void topk_merge_kernel(const float* __restrict__ vals, const int* __restrict__ ids, const int* __restrict__ cnt,
-                                  int n_lists, long long list_stride, int cap, long long n_rows, int K, int id_add,
-                                  float* __restrict__ out_vals, int* __restrict__ out_ids) {
+__global__ void tilemax_select_kernel(const float* __restrict__ T, int n_tiles, long long n_rows, int K, int selcap,
+                                      int* __restrict__ sel, int* __restrict__ selcnt) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n_rows) return;
+  const float* t = T + row * n_tiles;
+  float best[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) best[e] = -INFINITY;
+  float tau = -INFINITY;
+  for (int base = 0; base < n_tiles; base += 32 * E) {
+    float cur[E];
+    bool any = false;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = base + e * 32 + lane;
+      cur[e] = (i < n_tiles) ? __ldg(t + i) : -INFINITY;
+      any |= cur[e] > tau;
+    }
+    if (!__any_sync(0xffffffffu, any)) continue;
+    warp_bitonic_sort_desc<float, E>(cur);
+    warp_topk_absorb<float, E>(best, cur);
+    tau = warp_blocked_get<float, E>(best, K - 1);
+  }
+  int cnt = 0, eq_taken = 0;
+  const uint32_t lt = (1u << lane) - 1u;
+  for (int base = 0; base < n_tiles; base += 32) {
+    const int i = base + lane;
+    const float v = (i < n_tiles) ? __ldg(t + i) : -INFINITY;
+    const bool gt = v > tau;
+    const bool eq = (v == tau) && (v > -INFINITY);
+    const uint32_t eqm = __ballot_sync(0xffffffffu, eq);
+    const bool take = gt || (eq && (eq_taken + __popc(eqm & lt) < K));
+    eq_taken += __popc(eqm);
+    const uint32_t m = __ballot_sync(0xffffffffu, take);
+    const int pos = cnt + __popc(m & lt);
+    if (take && pos < selcap) sel[row * selcap + pos] = i;
+    cnt += __popc(m);
+  }
+  if (lane == 0) selcnt[row] = min(cnt, selcap);
+}
+
+// ---- top-K pass 2b: re-score the selected tiles of a row exactly (fp32 FMA over the stored operands),
+// skip seen ids, keep the K best by (score desc, id asc).  One warp per row; lane <-> item.
+template <typename TW, int E>
+__global__ void __launch_bounds__(128)
+topk_refine_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const float* __restrict__ bias, float scale, int d,
+                   long long n_rows, int n_items, const int* __restrict__ seen_crow, const int* __restrict__ seen_col,
+                   const int* __restrict__ sel, const int* __restrict__ selcnt, int selcap, int K, int id_add,
+                   float* __restrict__ out_vals, int* __restrict__ out_ids) {
+  __shared__ __align__(16) float u_s[4][256];
+  __shared__ unsigned long long cand_s[4][256];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * 4 + wib;
+  if (row >= n_rows) return;
+  float* u = u_s[wib];
+  unsigned long long* cand = cand_s[wib];
+  for (int k = lane; k < 256; k += 32) u[k] = (k < d) ? static_cast<float>(U[row * d + k]) : 0.f;
+  __syncwarp();
+  int s_lo = 0, s_hi = 0;
+  if (seen_crow != nullptr) { s_lo = seen_crow[row]; s_hi = seen_crow[row + 1]; }
+  unsigned long long best[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) best[e] = 0ull;
+  unsigned long long kth = 0ull;
+  int ncand = 0;
+  const uint32_t lt = (1u << lane) - 1u;
+  const int ns = selcnt[row];
+
+  auto flush = [&]() {
+    for (int base = 0; base < ncand; base += 32 * E) {
+      unsigned long long cur[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int i = base + lane * E + e;
+        cur[e] = (i < ncand) ? cand[i] : 0ull;
+      }
+      warp_bitonic_sort_desc<unsigned long long, E>(cur);
+      warp_topk_absorb<unsigned long long, E>(best, cur);
+    }
+    kth = warp_blocked_get<unsigned long long, E>(best, K - 1);
+    ncand = 0;
+    __syncwarp();
+  };
+
+  for (int si = 0; si < ns; ++si) {
+    const int tile = sel[row * selcap + si];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int item[4];
+    const TW* wrow[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      item[q] = tile * 128 + q * 32 + lane;
+      wrow[q] = W + static_cast<long long>(min(item[q], n_items - 1)) * d;
+    }
+    for (int k = 0; k < d; k += 8) {  // d % 8 == 0
+      const float4 ua = *reinterpret_cast<const float4*>(u + k);
+      const float4 ub = *reinterpret_cast<const float4*>(u + k + 4);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float w[8];
+        if constexpr (sizeof(TW) == 2) {
+          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(wrow[q] + k));
+          w[0] = __uint_as_float(raw.x << 16); w[1] = __uint_as_float(raw.x & 0xFFFF0000u);
+          w[2] = __uint_as_float(raw.y << 16); w[3] = __uint_as_float(raw.y & 0xFFFF0000u);
+          w[4] = __uint_as_float(raw.z << 16); w[5] = __uint_as_float(raw.z & 0xFFFF0000u);
+          w[6] = __uint_as_float(raw.w << 16); w[7] = __uint_as_float(raw.w & 0xFFFF0000u);
+        } else {
+          const float4 r0 = __ldg(reinterpret_cast<const float4*>(wrow[q] + k));
+          const float4 r1 = __ldg(reinterpret_cast<const float4*>(wrow[q] + k + 4));
+          w[0] = r0.x; w[1] = r0.y; w[2] = r0.z; w[3] = r0.w; w[4] = r1.x; w[5] = r1.y; w[6] = r1.z; w[7] = r1.w;
+        }
+        acc[q] = fmaf(ua.x, w[0], acc[q]); acc[q] = fmaf(ua.y, w[1], acc[q]);
+        acc[q] = fmaf(ua.z, w[2], acc[q]); acc[q] = fmaf(ua.w, w[3], acc[q]);
+        acc[q] = fmaf(ub.x, w[4], acc[q]); acc[q] = fmaf(ub.y, w[5], acc[q]);
+        acc[q] = fmaf(ub.z, w[6], acc[q]); acc[q] = fmaf(ub.w, w[7], acc[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const bool valid = item[q] < n_items;
+      float sc = acc[q] * scale;
+      if (bias != nullptr && valid) sc += __ldg(bias + item[q]);
+      const unsigned long long key = valid ? topk_key(sc, item[q]) : 0ull;
+      bool pass = key > kth;
+      if (pass && s_hi > s_lo) {  // seen items never rank (UniSRec/main.py:413)
+        int lo = s_lo, hi = s_hi;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (__ldg(seen_col + mid) < item[q]) lo = mid + 1; else hi = mid;
+        }
+        if (lo < s_hi && __ldg(seen_col + lo) == item[q]) pass = false;
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, pass);
+      if (pass) cand[ncand + __popc(m & lt)] = key;
+      ncand += __popc(m);
+      __syncwarp();
+      if (ncand > 256 - 32) flush();
+    }
+  }
+  flush();
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = lane * E + e;
+    if (i < K) {
+      const unsigned long long key = best[e];
+      float v = MASKED_SCORE_F;
+      int id = -1;
+      if (key != 0ull) {
+        v = f32_from_orderable(static_cast<uint32_t>(key >> 32));
+        id = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFu)) + id_add;
+      }
+      out_vals[row * K + i] = v;
+      out_ids[row * K + i] = id;
+    }
+  }
+}
+
+// ---- merge of R sorted per-shard lists (rb_topk_merge): list l of row i at (l*n_rows + i)*K + e
+template <int E>
+__global__ void topk_merge_kernel(const float* __restrict__ vals, const int* __restrict__ ids, int n_lists,
+                                  long long n_rows, int K, float* __restrict__ out_vals, int* __restrict__ out_ids) {
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n_rows) return;
@@ -289,26 +465,20 @@ __global__ void topk_merge_kernel(const float* __restrict__ vals, const int* __r
 #pragma unroll
   for (int e = 0; e < E; ++e) best[e] = 0ull;
   for (int l = 0; l < n_lists; ++l) {
-    const long long slot = l * list_stride + row;
-    const int n = cnt ? cnt[slot] : cap;
-    for (int base = 0; base < n; base += 32 * E) {
+    const long long ebase = (static_cast<long long>(l) * n_rows + row) * K;
+    for (int base = 0; base < K; base += 32 * E) {
       unsigned long long cur[E];
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         const int i = base + lane * E + e;
         cur[e] = 0ull;
-        if (i < n) {
-          const int id = ids[slot * cap + i];
-          if (id >= 0) cur[e] = topk_key(vals[slot * cap + i], id);
+        if (i < K) {
+          const int id = ids[ebase + i];
+          if (id >= 0) cur[e] = topk_key(vals[ebase + i], id);
         }
       }
-      warp_bitonic_sort64_desc<E>(cur);
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const unsigned long long rev = __shfl_sync(0xffffffffu, cur[E - 1 - e], 31 - lane);
-        best[e] = best[e] > rev ? best[e] : rev;
-      }
-      warp_bitonic_merge64_desc<E>(best);
+      warp_bitonic_sort_desc<unsigned long long, E>(cur);
+      warp_topk_absorb<unsigned long long, E>(best, cur);
     }
   }
 #pragma unroll
@@ -320,7 +490,7 @@ __global__ void topk_merge_kernel(const float* __restrict__ vals, const int* __r
       int id = -1;
       if (key != 0ull) {
         v = f32_from_orderable(static_cast<uint32_t>(key >> 32));
-        id = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFu)) + id_add;
+        id = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFu));
       }
       out_vals[row * K + i] = v;
       out_ids[row * K + i] = id;

@@ -4,13 +4,15 @@
 //
 //   EPI_DENSE  store S (compat path for recommend_from_full, reference SASRec/main.py:228)
 //   EPI_LSE    online (max, sum-exp) + label-logit pick   (F.cross_entropy fwd, SASRec/main.py:217-219)
-//   EPI_GRAD   P = exp2(S*c - lse2) -> bf16 tile G in SMEM -> second MMA  Acc += G x Y_strm
+//   EPI_GRAD   P = exp2(S*c - lse2) -> f16 tile G in SMEM -> second MMA  Acc += G x Y_strm
 //              (autograd of SASRec/main.py:217-219: dU = P.W with rows stationary,
 //               dW = P^T.U with items stationary) -- the (M,N) matrix is never written
-//   EPI_TOPK   masked running top-K per row (UniSRec/main.py:408-435 without dense (B,N))
+//   EPI_TOPK   masked maximum of every (row, 128-item tile): pass 1 of the exact top-K
+//              (UniSRec/main.py:408-435 without dense (B,N); simt.cuh finishes the selection)
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2..5 = epilogue (thread <-> TMEM lane <-> stationary row).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2..9 = two epilogue warpgroups (thread <-> TMEM lane <-> stationary row); warpgroup g owns
+// the S/G buffer g, i.e. the tiles of parity g, so two tiles are always in flight per SM.
 #pragma once
 #include "ptx.cuh"
 
@@ -22,6 +24,7 @@ enum : int { DT_BF16 = 0, DT_TF32X3 = 1 };
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 constexpr float MASKED_SCORE = -1e23f;  // UniSRec/main.py:413
+constexpr int SWEEP_THREADS = 320;
 
 struct SweepArgs {
   int n_stat;        // valid rows of the stationary operand
@@ -46,22 +49,16 @@ struct SweepArgs {
   const float* gscale_dev;  // optional device scalar multiplied into gscale (autograd's grad_output)
   float* acc_out;     // [n_splits][n_stat][d]
   float* rowsum_out;  // [n_splits][n_stat]  sum_j P (items stationary: dbias), nullable
-  // EPI_TOPK (rows stationary)
-  int K;              // list length kept per row
-  int id_base;        // global id of streamed row 0
+  // EPI_TOPK (rows stationary): pass 1 of the top-K = masked maximum of every (row, 128-item tile)
   const int* seen_crow;  // [n_stat+1] CSR of already-seen LOCAL item ids, sorted per row (nullable)
   const int* seen_col;
-  float* cand_val;    // [n_splits][n_stat_tiles*128][CAP]
-  int* cand_id;
-  int* cand_cnt;      // [n_splits][n_stat_tiles*128]
+  float* tile_max;    // [n_stat][n_strm_tiles]
 };
 
-template <int EPI_, int DT_, int KC_, int BN_, int NS_, bool STAT_ROWS_, int CAPE_ = 8>
+template <int EPI_, int DT_, int KC_, int BN_, int NS_, bool STAT_ROWS_>
 struct SweepCfg {
   static constexpr int EPI = EPI_, DT = DT_, KC = KC_, BN = BN_, NS = NS_;
   static constexpr bool STAT_ROWS = STAT_ROWS_;  // true: queries stationary, items streamed
-  static constexpr int CAPE = CAPE_;             // top-K candidate slots per lane (CAP = 32*CAPE)
-  static constexpr int CAP = 32 * CAPE_;
   // storage chunks (128-byte columns groups) per operand row
   static constexpr int KCS = (DT_ == DT_BF16) ? KC_ : 2 * KC_;  // tf32x3: [hi | lo], KC = d/32
   static constexpr int NPAIR = (DT_ == DT_BF16) ? KC_ : 3 * KC_;
@@ -70,8 +67,9 @@ struct SweepCfg {
   static constexpr int X_BYTES = KCS * 128 * 128;
   static constexpr int Y_BYTES = KCS * BN_ * 128;
   static constexpr int G_BYTES = (EPI_ == EPI_GRAD) ? (BN_ / 64) * 128 * 128 : 0;
-  static constexpr int NG = 2;  // G double buffer
-  static constexpr int SMEM_BYTES = X_BYTES + NS_ * Y_BYTES + NG * G_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
+  static constexpr int NG = 2;  // G double buffer (one per epilogue warpgroup)
+  static constexpr int CTRL_BYTES = 4096;  // barriers + cross-warpgroup exchange
+  static constexpr int SMEM_BYTES = X_BYTES + NS_ * Y_BYTES + NG * G_BYTES + CTRL_BYTES + 1024 /*align*/;
   static constexpr int ACC_COLS = (EPI_ == EPI_GRAD) ? DPAD : 0;
   static constexpr int TMEM_NEED = 2 * BN_ + ACC_COLS;
   static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
@@ -81,56 +79,35 @@ struct SweepCfg {
   static_assert(EPI_ != EPI_GRAD || DT_ == DT_BF16, "GRAD epilogue is bf16-only for now");
 };
 
-struct Barriers {
+struct Control {
   uint64_t full[8], empty[8];
   uint64_t x_full, x_empty;
   uint64_t s_full[2], s_empty[2];
   uint64_t g_full[2], g_empty[2];
   uint64_t acc_full, acc_empty;
   uint32_t tmem_base;
+  uint32_t pad_;
+  float xchg[3][128];  // warpgroup 1 -> warpgroup 0 hand-over of per-row partials
 };
+static_assert(sizeof(Control) <= 4096, "control block");
 
-// ---------------------------------------------------------------------------------------------
-// warp-level helpers for the top-K epilogue (bitonic sort of 32*E values held E per lane, blocked:
-// element index = lane*E + e), descending.
-template <int E>
-__device__ __forceinline__ void warp_bitonic_sort_desc(float (&v)[E]) {
-  const uint32_t lane = lane_id();
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+__device__ __forceinline__ float max32(const uint32_t (&r)[32]) {
+  float m[8];
 #pragma unroll
-  for (int k = 2; k <= 32 * E; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j >= 1; j >>= 1) {
-      if (j >= E) {
-        const int lj = j / E;
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          const int i = lane * E + e;
-          const float other = __shfl_xor_sync(0xffffffffu, v[e], lj);
-          const bool up = ((i & k) == 0);          // this block sorts descending when up
-          const bool lower = ((i & j) == 0);       // i is the lower index of the pair
-          const bool take_max = (up == lower);
-          v[e] = take_max ? fmaxf(v[e], other) : fminf(v[e], other);
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          if ((e & j) == 0) {
-            const int i = lane * E + e;
-            const bool up = ((i & k) == 0);
-            const float a = v[e], b = v[e + j];
-            const float hi = fmaxf(a, b), lo = fminf(a, b);
-            v[e] = up ? hi : lo;
-            v[e + j] = up ? lo : hi;
-          }
-        }
-      }
-    }
-  }
+  for (int i = 0; i < 8; ++i)
+    m[i] = fmaxf(fmaxf(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])),
+                 fmaxf(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+  return fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
 }
+
+// named barrier over the 256 epilogue threads (id 1; id 0 is __syncthreads)
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 template <class C>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(SWEEP_THREADS, 1)
 sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__ CUtensorMap tm_strm,
              const SweepArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -138,7 +115,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
   uint8_t* x_smem = smem;
   uint8_t* y_smem = x_smem + C::X_BYTES;
   uint8_t* g_smem = y_smem + C::NS * C::Y_BYTES;
-  Barriers* bar = reinterpret_cast<Barriers*>(g_smem + C::NG * C::G_BYTES);
+  Control* bar = reinterpret_cast<Control*>(g_smem + C::NG * C::G_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -157,7 +134,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
       mbar_init(&bar->g_empty[i], 1);
     }
     mbar_init(&bar->acc_full, 1);
-    mbar_init(&bar->acc_empty, 128);
+    mbar_init(&bar->acc_empty, 256);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -204,7 +181,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
     if (lane == 0) {
       constexpr uint32_t fmt = (C::DT == DT_BF16) ? FMT_BF16 : FMT_TF32;
       constexpr uint32_t idesc1 = make_idesc(fmt, 128, C::BN, 0, 0);
-      constexpr uint32_t idesc2 = make_idesc(fmt, 128, C::DPAD, 0, 1);
+      // second MMA: A = softmax tile P as f16 (packed-half exp2 in the epilogue), B = streamed bf16 tile
+      constexpr uint32_t idesc2 = make_idesc2(FMT_F16, fmt, 128, C::DPAD, 0, 1);
       const uint32_t x_addr = smem_u32(x_smem), y_addr = smem_u32(y_smem), g_addr = smem_u32(g_smem);
       uint32_t it = 0, k = 0;
 
@@ -272,10 +250,13 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
     }
   } else {
     // =========================================================================== epilogue
+    const int wg = (warp - 2) >> 2;    // warpgroup 0/1 == parity of the tiles it owns == S/G buffer
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;       // stationary row within the tile == TMEM lane
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + wg * C::BN;
     const float c2 = a.scale * LOG2E;
+    const bool plain = (a.bias == nullptr) && (c2 > 0.f);  // fast paths: no bias, positive scale
+    constexpr int NCH = C::BN / 32;
     uint32_t it = 0, k = 0;
 
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++k) {
@@ -285,34 +266,27 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
       const bool srow_ok = srow < a.n_stat;
       const long long pslot = static_cast<long long>(split) * a.n_stat_tiles * 128 + srow;
 
-      // ---- per-item state
+      // ---- per-item, per-warpgroup state
       float m2 = -INFINITY, l = 0.f, ll = 0.f;     // LSE
       int lab = -1;                                 // LSE / GRAD(rows)
-      float my_nb = 0.f;                            // GRAD: -lse2 (rows) or bias2 (items)
+      float my_nb = 0.f;                            // GRAD: -lse2 (rows) or bias*log2e (items)
       float rowsum = 0.f;                           // GRAD(items): sum_j P for dbias
-      // TOPK
-      float tau = -INFINITY;
-      int cnt = 0, seen_cur = 0, seen_end = 0, next_seen = 0x7fffffff;
-      float* cval = nullptr;
-      int* cid = nullptr;
+      int seen_cur = 0, seen_end = 0, next_seen = 0x7fffffff;   // TOPK: cursor into the row's seen list
 
       if (C::EPI == EPI_LSE) lab = srow_ok ? a.labels[srow] : -1;
       if (C::EPI == EPI_GRAD) {
         if (C::STAT_ROWS) {
           lab = srow_ok ? a.labels[srow] : -1;
-          my_nb = -a.lse2[srow];  // padded with +inf => P = 0 for rows >= n_stat
+          my_nb = -a.lse2[srow];  // lse2 is +inf for rows >= n_stat => P = 0 there
         } else {
-          my_nb = (a.bias != nullptr && srow_ok) ? a.bias[srow] * LOG2E : 0.f;
+          my_nb = srow_ok ? ((a.bias != nullptr) ? a.bias[srow] * LOG2E : 0.f) : -INFINITY;
         }
       }
       if (C::EPI == EPI_TOPK) {
-        cval = a.cand_val + pslot * C::CAP;
-        cid = a.cand_id + pslot * C::CAP;
         if (a.seen_crow != nullptr && srow_ok) {
           seen_cur = a.seen_crow[srow];
           seen_end = a.seen_crow[srow + 1];
-          // first seen id >= first streamed row of this split
-          const int first = t0 * C::BN;
+          const int first = t0 * C::BN;  // first streamed row of this split
           int lo = seen_cur, hi = seen_end;
           while (lo < hi) {
             const int mid = (lo + hi) >> 1;
@@ -321,47 +295,78 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
           seen_cur = lo;
           next_seen = (seen_cur < seen_end) ? a.seen_col[seen_cur] : 0x7fffffff;
         }
-        if (!srow_ok) tau = INFINITY;  // padding rows never collect candidates
       }
 
       for (int t = t0; t < t1; ++t, ++it) {
-        const uint32_t buf = it & 1, sph = (it >> 1) & 1;
+        if ((it & 1) != static_cast<uint32_t>(wg)) continue;
+        const uint32_t sph = (it >> 1) & 1;
         const int col_base = t * C::BN;                       // first streamed row of the tile
         const int n_valid = min(C::BN, a.n_strm - col_base);  // valid columns in this tile
-        mbar_wait(&bar->s_full[buf], sph);
+        const bool full_tile = (n_valid == C::BN);
+        mbar_wait(&bar->s_full[wg], sph);
         tc_fence_after();
-        if (C::EPI == EPI_GRAD) mbar_wait(&bar->g_empty[buf], sph ^ 1);
+        if (C::EPI == EPI_GRAD) mbar_wait(&bar->g_empty[wg], sph ^ 1);
 
-#pragma unroll 1
-        for (int ch = 0; ch < C::BN / 32; ++ch) {
-          uint32_t raw[32];
-          tmem_ld32(t_lane + buf * C::BN + ch * 32, raw);
+        float tmax = -INFINITY;   // TOPK: masked max of this tile for this row
+        bool tile_quick = false;
+        if (C::EPI == EPI_TOPK) {
+          while (next_seen < col_base) {  // skip seen ids that fell into the other warpgroup's tiles
+            ++seen_cur;
+            next_seen = (seen_cur < seen_end) ? __ldg(a.seen_col + seen_cur) : 0x7fffffff;
+          }
+          tile_quick = plain && full_tile && (next_seen >= col_base + C::BN);
+        }
+        uint32_t raw[2][32];
+        tmem_ld32(t_lane, raw[0]);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
           tmem_ld_wait();
+          if (ch + 1 < NCH) tmem_ld32(t_lane + (ch + 1) * 32, raw[(ch + 1) & 1]);
+          const uint32_t (&v)[32] = raw[ch & 1];
           const int c0 = ch * 32;                  // first column of the chunk within the tile
           const int nv = n_valid - c0;             // valid columns in this chunk (may be <= 0 or >= 32)
 
           if (C::EPI == EPI_DENSE) {
-            if (srow_ok) {
+            if (srow_ok && nv > 0) {
               float* o = a.out + static_cast<long long>(srow) * a.ld_out + col_base + c0;
+              if (a.bias == nullptr && nv >= 32) {
 #pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                if (c < nv) {
-                  float s = __uint_as_float(raw[c]) * a.scale;
-                  if (a.bias != nullptr) s += __ldg(a.bias + col_base + c0 + c);
-                  o[c] = s;
+                for (int c = 0; c < 32; ++c) o[c] = __uint_as_float(v[c]) * a.scale;
+              } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                  if (c < nv) {
+                    float s = __uint_as_float(v[c]) * a.scale;
+                    if (a.bias != nullptr) s += __ldg(a.bias + col_base + c0 + c);
+                    o[c] = s;
+                  }
                 }
               }
             }
           } else if (C::EPI == EPI_LSE) {
-            if (nv > 0) {
+            const int rel = lab - (col_base + c0);
+            if (plain && full_tile) {
+              const float cm2 = max32(v) * c2;
+              if (cm2 > m2) { l *= ex2_approx(m2 - cm2); m2 = cm2; }
+              const float nm = -m2;
+              float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int c = 0; c < 32; ++c) acc[c & 3] += ex2_approx(fmaf(__uint_as_float(v[c]), c2, nm));
+              l += (acc[0] + acc[1]) + (acc[2] + acc[3]);
+              if (__any_sync(0xffffffffu, static_cast<uint32_t>(rel) < 32u)) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                  if (c == rel) ll = __uint_as_float(v[c]) * a.scale;
+              }
+            } else if (nv > 0) {
               float x[32];
               float cmax = -INFINITY;
 #pragma unroll
               for (int c = 0; c < 32; ++c) {
                 float b2 = 0.f;
                 if (a.bias != nullptr) b2 = (c < nv) ? __ldg(a.bias + col_base + c0 + c) * LOG2E : 0.f;
-                x[c] = fmaf(__uint_as_float(raw[c]), c2, b2);
-                if (nv < 32 && c >= nv) x[c] = -INFINITY;
+                x[c] = fmaf(__uint_as_float(v[c]), c2, b2);
+                if (c >= nv) x[c] = -INFINITY;
                 cmax = fmaxf(cmax, x[c]);
               }
               const float m_new = fmaxf(m2, cmax);
@@ -370,43 +375,50 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
               for (int c = 0; c < 32; ++c) acc += ex2_approx(x[c] - m_new);
               l = l * ex2_approx(m2 - m_new) + acc;
               m2 = m_new;
-              const int rel = lab - (col_base + c0);
-              if (__any_sync(0xffffffffu, rel >= 0 && rel < 32)) {
+              if (__any_sync(0xffffffffu, static_cast<uint32_t>(rel) < 32u)) {
 #pragma unroll
                 for (int c = 0; c < 32; ++c)
                   if (c == rel) ll = x[c] * LN2;  // natural-log units: scale*s + bias
               }
             }
           } else if (C::EPI == EPI_GRAD) {
-            float p[32];
+            // P = 2^(s*c2 + bias2 - lse2) as packed f16 pairs {col 2i (low), col 2i+1 (high)}
+            uint32_t ph[16];
             if (C::STAT_ROWS) {
+              if (plain && full_tile) {
 #pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                float nb = my_nb;
-                if (a.bias != nullptr) nb += (c < nv) ? __ldg(a.bias + col_base + c0 + c) * LOG2E : 0.f;
-                p[c] = ex2_approx(fmaf(__uint_as_float(raw[c]), c2, nb));
-                if (nv < 32 && c >= nv) p[c] = 0.f;
+                for (int i = 0; i < 16; ++i)
+                  ph[i] = ex2_f16x2(fmaf(__uint_as_float(v[2 * i]), c2, my_nb), fmaf(__uint_as_float(v[2 * i + 1]), c2, my_nb));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  float x[2];
+#pragma unroll
+                  for (int h = 0; h < 2; ++h) {
+                    const int c = 2 * i + h;
+                    float nb = my_nb;
+                    if (a.bias != nullptr) nb += (c < nv) ? __ldg(a.bias + col_base + c0 + c) * LOG2E : 0.f;
+                    x[h] = (c < nv) ? fmaf(__uint_as_float(v[c]), c2, nb) : -INFINITY;
+                  }
+                  ph[i] = ex2_f16x2(x[0], x[1]);
+                }
               }
               const int rel = lab - (col_base + c0);
-              if (__any_sync(0xffffffffu, rel >= 0 && rel < 32)) {
+              if (__any_sync(0xffffffffu, static_cast<uint32_t>(rel) < 32u)) {
 #pragma unroll
                 for (int c = 0; c < 32; ++c)
-                  if (c == rel) p[c] -= 1.f;
+                  if (c == rel) ph[c >> 1] = hsub2_u32(ph[c >> 1], (c & 1) ? 0x3C000000u : 0x00003C00u);  // -= 1.0
               }
             } else {
-              // columns are query rows: lse2 is padded with +inf beyond n_strm => P = 0 there
+              // columns are query rows: lse2 is +inf beyond n_strm => P = 0 there (no tail special case)
               const float4* l4 = reinterpret_cast<const float4*>(a.lse2 + col_base + c0);
 #pragma unroll
               for (int c4 = 0; c4 < 8; ++c4) {
-                const float4 v = __ldg(l4 + c4);
-                p[c4 * 4 + 0] = ex2_approx(fmaf(__uint_as_float(raw[c4 * 4 + 0]), c2, my_nb - v.x));
-                p[c4 * 4 + 1] = ex2_approx(fmaf(__uint_as_float(raw[c4 * 4 + 1]), c2, my_nb - v.y));
-                p[c4 * 4 + 2] = ex2_approx(fmaf(__uint_as_float(raw[c4 * 4 + 2]), c2, my_nb - v.z));
-                p[c4 * 4 + 3] = ex2_approx(fmaf(__uint_as_float(raw[c4 * 4 + 3]), c2, my_nb - v.w));
-              }
-              if (!srow_ok) {
-#pragma unroll
-                for (int c = 0; c < 32; ++c) p[c] = 0.f;
+                const float4 w = __ldg(l4 + c4);
+                ph[c4 * 2 + 0] = ex2_f16x2(fmaf(__uint_as_float(v[c4 * 4 + 0]), c2, my_nb - w.x),
+                                           fmaf(__uint_as_float(v[c4 * 4 + 1]), c2, my_nb - w.y));
+                ph[c4 * 2 + 1] = ex2_f16x2(fmaf(__uint_as_float(v[c4 * 4 + 2]), c2, my_nb - w.z),
+                                           fmaf(__uint_as_float(v[c4 * 4 + 3]), c2, my_nb - w.w));
               }
               // one-hot: does any query row of this chunk have its label inside this item tile?
               int labc = -1;
@@ -417,167 +429,117 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
                 for (int c = 0; c < 32; ++c) {
                   if (hit & (1u << c)) {
                     const int lc = __shfl_sync(0xffffffffu, labc, c);
-                    if (lc == srow) p[c] -= 1.f;
+                    if (lc == srow) ph[c >> 1] = hsub2_u32(ph[c >> 1], (c & 1) ? 0x3C000000u : 0x00003C00u);
                   }
                 }
               }
               if (a.rowsum_out != nullptr) {
+                float rs[2] = {0.f, 0.f};
 #pragma unroll
-                for (int c = 0; c < 32; ++c) rowsum += p[c];
+                for (int i = 0; i < 16; ++i) {
+                  const float2 f = h2_to_f2(ph[i]);
+                  rs[0] += f.x;
+                  rs[1] += f.y;
+                }
+                rowsum += rs[0] + rs[1];
               }
             }
-            // G tile, K-major, 128-byte swizzle: [k-chunk of 64][row][64 bf16]
-            uint8_t* gdst = g_smem + buf * C::G_BYTES + (c0 / 64) * 128 * 128 + r * 128;
+            // G tile, K-major, 128-byte swizzle: [k-chunk of 64][row][64 x f16]
+            uint8_t* gdst = g_smem + wg * C::G_BYTES + (c0 / 64) * 128 * 128 + r * 128;
             const int v0 = (c0 % 64) / 8;
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              uint4 w;
-              w.x = pack_bf16x2(p[v * 8 + 0], p[v * 8 + 1]);
-              w.y = pack_bf16x2(p[v * 8 + 2], p[v * 8 + 3]);
-              w.z = pack_bf16x2(p[v * 8 + 4], p[v * 8 + 5]);
-              w.w = pack_bf16x2(p[v * 8 + 6], p[v * 8 + 7]);
-              *reinterpret_cast<uint4*>(gdst + (((v0 + v) ^ (r & 7)) << 4)) = w;
+            for (int vv = 0; vv < 4; ++vv) {
+              const uint4 w = make_uint4(ph[vv * 4 + 0], ph[vv * 4 + 1], ph[vv * 4 + 2], ph[vv * 4 + 3]);
+              *reinterpret_cast<uint4*>(gdst + (((v0 + vv) ^ (r & 7)) << 4)) = w;
             }
           } else if (C::EPI == EPI_TOPK) {
-            if (nv > 0) {
-              const int idc = col_base + c0;  // local item id of column 0 of this chunk
+            if (tile_quick) {
+              tmax = fmaxf(tmax, max32(v));  // raw scores; scaled once per tile (scale > 0)
+            } else if (nv > 0) {
+              float x[32];
 #pragma unroll
-              for (int g8 = 0; g8 < 4; ++g8) {
-                float gm = -INFINITY;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) gm = fmaxf(gm, __uint_as_float(raw[g8 * 8 + c]));
-                float gms = gm * a.scale;  // scale > 0 assumed for the filter (checked on host)
-                if (gms > tau || a.bias != nullptr) {
-#pragma unroll
-                  for (int c = 0; c < 8; ++c) {
-                    const int cc = g8 * 8 + c;
-                    if (cc < nv) {
-                      float s = __uint_as_float(raw[cc]) * a.scale;
-                      if (a.bias != nullptr) s += __ldg(a.bias + idc + cc);
-                      if (s > tau) {
-                        const int id = idc + cc;
-                        while (next_seen < id) {
-                          ++seen_cur;
-                          next_seen = (seen_cur < seen_end) ? a.seen_col[seen_cur] : 0x7fffffff;
-                        }
-                        if (next_seen != id) {
-                          cval[cnt] = s;
-                          cid[cnt] = id;
-                          ++cnt;
-                        }
-                      }
-                    }
-                  }
-                }
+              for (int c = 0; c < 32; ++c) {
+                float sc = __uint_as_float(v[c]) * a.scale;
+                if (a.bias != nullptr && c < nv) sc += __ldg(a.bias + col_base + c0 + c);
+                x[c] = (c < nv) ? sc : -INFINITY;
               }
-              // compress lists that could overflow during the next chunk
-              uint32_t need = __ballot_sync(0xffffffffu, cnt > C::CAP - 32);
-              while (need) {
-                const int src = __ffs(need) - 1;
-                need &= need - 1;
-                const int n = __shfl_sync(0xffffffffu, cnt, src);
-                float* lv = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(cval), src));
-                int* li = reinterpret_cast<int*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(cid), src));
-                __syncwarp();
-                float v[C::CAPE], keep_v[C::CAPE];
-                int keep_i[C::CAPE];
+              while (next_seen < col_base + c0 + 32) {  // seen ids inside this chunk (ascending)
+                const int rel = next_seen - (col_base + c0);
 #pragma unroll
-                for (int e = 0; e < C::CAPE; ++e) {
-                  const int i = lane * C::CAPE + e;
-                  keep_v[e] = (i < n) ? lv[i] : -INFINITY;
-                  keep_i[e] = (i < n) ? li[i] : 0;
-                  v[e] = keep_v[e];
-                }
-                warp_bitonic_sort_desc<C::CAPE>(v);
-                // K-th largest (sorted index K-1 lives in lane (K-1)/CAPE, slot (K-1)%CAPE)
-                float kth = -INFINITY;
-#pragma unroll
-                for (int e = 0; e < C::CAPE; ++e) {
-                  const float cand = __shfl_sync(0xffffffffu, v[e], (a.K - 1) / C::CAPE);
-                  if (e == (a.K - 1) % C::CAPE) kth = cand;
-                }
-                // keep everything > kth, plus the lowest-id ties == kth up to K in total
-                int n_gt = 0, n_eq = 0;
-#pragma unroll
-                for (int e = 0; e < C::CAPE; ++e) { n_gt += keep_v[e] > kth; n_eq += keep_v[e] == kth; }
-                int tot_gt = n_gt, pre_gt = n_gt, pre_eq = n_eq;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                  const int g1 = __shfl_up_sync(0xffffffffu, pre_gt, o);
-                  const int e1 = __shfl_up_sync(0xffffffffu, pre_eq, o);
-                  if (lane >= o) { pre_gt += g1; pre_eq += e1; }
-                }
-                tot_gt = __shfl_sync(0xffffffffu, pre_gt, 31);
-                pre_gt -= n_gt;  // exclusive
-                pre_eq -= n_eq;
-                const int eq_quota = a.K - tot_gt;  // >= 1 by construction
-                __syncwarp();
-                int w_gt = pre_gt, w_eq = pre_eq;
-#pragma unroll
-                for (int e = 0; e < C::CAPE; ++e) {
-                  const bool gt = keep_v[e] > kth;
-                  const bool eq = (keep_v[e] == kth) && (w_eq < eq_quota);
-                  if (gt || eq) {
-                    // stable position = (#kept before me): kept-gt before + kept-eq before
-                    const int pos = w_gt + min(w_eq, eq_quota);
-                    lv[pos] = keep_v[e];
-                    li[pos] = keep_i[e];
-                  }
-                  w_gt += gt;
-                  w_eq += (keep_v[e] == kth);
-                }
-                __syncwarp();
-                if (lane == src) { cnt = min(n, a.K); tau = (n >= a.K) ? kth : tau; }
+                for (int c = 0; c < 32; ++c)
+                  if (c == rel) x[c] = -INFINITY;
+                ++seen_cur;
+                next_seen = (seen_cur < seen_end) ? __ldg(a.seen_col + seen_cur) : 0x7fffffff;
               }
+              float cm = -INFINITY;
+#pragma unroll
+              for (int c = 0; c < 32; ++c) cm = fmaxf(cm, x[c]);
+              tmax = fmaxf(tmax, cm);
             }
           }
         }  // chunks
 
         // release the S buffer (all tcgen05.ld of this thread have completed)
         tc_fence_before();
-        mbar_arrive(&bar->s_empty[buf]);
+        mbar_arrive(&bar->s_empty[wg]);
+        if (C::EPI == EPI_TOPK && srow_ok)
+          a.tile_max[static_cast<long long>(srow) * a.n_strm_tiles + t] = tile_quick ? tmax * a.scale : tmax;
         if (C::EPI == EPI_GRAD) {
           fence_proxy_async_smem();
-          mbar_arrive(&bar->g_full[buf]);
+          mbar_arrive(&bar->g_full[wg]);
         }
       }  // tiles
 
       // ---- per-item outputs
       if (C::EPI == EPI_LSE) {
-        a.part_m2[pslot] = m2;
-        a.part_l[pslot] = l;
-        a.part_ll[pslot] = ll;
-      } else if (C::EPI == EPI_TOPK) {
-        a.cand_cnt[pslot] = cnt;
+        // warpgroup 1 hands its partial to warpgroup 0, which merges and writes one slot per row
+        if (wg == 1) { bar->xchg[0][r] = m2; bar->xchg[1][r] = l; bar->xchg[2][r] = ll; }
+        epi_bar_sync();
+        if (wg == 0) {
+          const float om = bar->xchg[0][r], ol = bar->xchg[1][r], oll = bar->xchg[2][r];
+          const float mm = fmaxf(m2, om);
+          float lm = 0.f;
+          if (mm > -INFINITY) lm = l * ex2_approx(m2 - mm) + ol * ex2_approx(om - mm);
+          a.part_m2[pslot] = mm;
+          a.part_l[pslot] = lm;
+          a.part_ll[pslot] = ll + oll;
+        }
+        epi_bar_sync();  // xchg is free again before the next item
       } else if (C::EPI == EPI_GRAD) {
         mbar_wait(&bar->acc_full, k & 1);
         tc_fence_after();
         const float gsc = a.gscale * (a.gscale_dev != nullptr ? __ldg(a.gscale_dev) : 1.f);
         float* o = a.acc_out + (static_cast<long long>(split) * a.n_stat + srow) * a.d;
+        const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 2 * C::BN;
 #pragma unroll 1
-        for (int ch = 0; ch < C::DPAD / 32; ++ch) {
-          uint32_t raw[32];
-          tmem_ld32(t_lane + 2 * C::BN + ch * 32, raw);
+        for (int ch = wg; ch < C::DPAD / 32; ch += 2) {  // the two warpgroups split the columns
+          uint32_t rawa[32];
+          tmem_ld32(t_acc + ch * 32, rawa);
           tmem_ld_wait();
           if (srow_ok) {
 #pragma unroll
             for (int c4 = 0; c4 < 8; ++c4) {
               const int col = ch * 32 + c4 * 4;
               if (col < a.d) {  // d % 4 == 0 (checked on host)
-                float4 v;
-                v.x = __uint_as_float(raw[c4 * 4 + 0]) * gsc;
-                v.y = __uint_as_float(raw[c4 * 4 + 1]) * gsc;
-                v.z = __uint_as_float(raw[c4 * 4 + 2]) * gsc;
-                v.w = __uint_as_float(raw[c4 * 4 + 3]) * gsc;
-                *reinterpret_cast<float4*>(o + col) = v;
+                float4 w;
+                w.x = __uint_as_float(rawa[c4 * 4 + 0]) * gsc;
+                w.y = __uint_as_float(rawa[c4 * 4 + 1]) * gsc;
+                w.z = __uint_as_float(rawa[c4 * 4 + 2]) * gsc;
+                w.w = __uint_as_float(rawa[c4 * 4 + 3]) * gsc;
+                *reinterpret_cast<float4*>(o + col) = w;
               }
             }
           }
         }
         tc_fence_before();
         mbar_arrive(&bar->acc_empty);
-        if (!C::STAT_ROWS && a.rowsum_out != nullptr && srow_ok)
-          a.rowsum_out[static_cast<long long>(split) * a.n_stat + srow] = rowsum * gsc;
+        if (!C::STAT_ROWS && a.rowsum_out != nullptr) {
+          if (wg == 1) bar->xchg[0][r] = rowsum;
+          epi_bar_sync();
+          if (wg == 0 && srow_ok)
+            a.rowsum_out[static_cast<long long>(split) * a.n_stat + srow] = (rowsum + bar->xchg[0][r]) * gsc;
+          epi_bar_sync();
+        }
       }
     }  // items
   }
