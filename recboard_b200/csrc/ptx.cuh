@@ -210,24 +210,22 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// {2^x0 (low half), 2^x1 (high half)} as packed f16: one MUFU op for two exponentials.
-// x = -inf (or below the f16 range) gives exactly 0.
-__device__ __forceinline__ uint32_t ex2_f16x2(float x0, float x1) {
+// {2^x0 (low half), 2^x1 (high half)} as packed bf16: one MUFU op for two exponentials.
+// x = -inf gives exactly 0.  (A kind::f16 MMA needs A and B in the same 16-bit format, and the
+// streamed operand is bf16, so the softmax tile is bf16 too.)
+__device__ __forceinline__ uint32_t ex2_bf16x2(float x0, float x1) {
   uint32_t h;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
-  asm("ex2.approx.f16x2 %0, %0;" : "+r"(h));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+  asm("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(h));
   return h;
 }
-__device__ __forceinline__ uint32_t hsub2_u32(uint32_t a, uint32_t b) {
+__device__ __forceinline__ uint32_t bsub2_u32(uint32_t a, uint32_t b) {
   uint32_t r;
-  asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
   return r;
 }
-__device__ __forceinline__ float2 h2_to_f2(uint32_t h) {
-  float lo, hi;
-  asm("{\n\t.reg .b16 l, u;\n\tmov.b32 {l, u}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, u;\n\t}\n"
-      : "=f"(lo), "=f"(hi) : "r"(h));
-  return make_float2(lo, hi);
+__device__ __forceinline__ float2 b2_to_f2(uint32_t h) {
+  return make_float2(__uint_as_float(h << 16), __uint_as_float(h & 0xFFFF0000u));
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;

@@ -4,7 +4,7 @@
 //
 //   EPI_DENSE  store S (compat path for recommend_from_full, reference SASRec/main.py:228)
 //   EPI_LSE    online (max, sum-exp) + label-logit pick   (F.cross_entropy fwd, SASRec/main.py:217-219)
-//   EPI_GRAD   P = exp2(S*c - lse2) -> f16 tile G in SMEM -> second MMA  Acc += G x Y_strm
+//   EPI_GRAD   P = exp2(S*c - lse2) -> bf16 tile G in SMEM -> second MMA  Acc += G x Y_strm
 //              (autograd of SASRec/main.py:217-219: dU = P.W with rows stationary,
 //               dW = P^T.U with items stationary) -- the (M,N) matrix is never written
 //   EPI_TOPK   masked maximum of every (row, 128-item tile): pass 1 of the exact top-K
@@ -181,8 +181,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
     if (lane == 0) {
       constexpr uint32_t fmt = (C::DT == DT_BF16) ? FMT_BF16 : FMT_TF32;
       constexpr uint32_t idesc1 = make_idesc(fmt, 128, C::BN, 0, 0);
-      // second MMA: A = softmax tile P as f16 (packed-half exp2 in the epilogue), B = streamed bf16 tile
-      constexpr uint32_t idesc2 = make_idesc2(FMT_F16, fmt, 128, C::DPAD, 0, 1);
+      // second MMA: A = softmax tile P as bf16 (packed exp2 in the epilogue), B = streamed bf16 tile
+      constexpr uint32_t idesc2 = make_idesc(fmt, 128, C::DPAD, 0, 1);
       const uint32_t x_addr = smem_u32(x_smem), y_addr = smem_u32(y_smem), g_addr = smem_u32(g_smem);
       uint32_t it = 0, k = 0;
 
@@ -382,13 +382,13 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
               }
             }
           } else if (C::EPI == EPI_GRAD) {
-            // P = 2^(s*c2 + bias2 - lse2) as packed f16 pairs {col 2i (low), col 2i+1 (high)}
+            // P = 2^(s*c2 + bias2 - lse2) as packed bf16 pairs {col 2i (low), col 2i+1 (high)}
             uint32_t ph[16];
             if (C::STAT_ROWS) {
               if (plain && full_tile) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-                  ph[i] = ex2_f16x2(fmaf(__uint_as_float(v[2 * i]), c2, my_nb), fmaf(__uint_as_float(v[2 * i + 1]), c2, my_nb));
+                  ph[i] = ex2_bf16x2(fmaf(__uint_as_float(v[2 * i]), c2, my_nb), fmaf(__uint_as_float(v[2 * i + 1]), c2, my_nb));
               } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -400,14 +400,14 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
                     if (a.bias != nullptr) nb += (c < nv) ? __ldg(a.bias + col_base + c0 + c) * LOG2E : 0.f;
                     x[h] = (c < nv) ? fmaf(__uint_as_float(v[c]), c2, nb) : -INFINITY;
                   }
-                  ph[i] = ex2_f16x2(x[0], x[1]);
+                  ph[i] = ex2_bf16x2(x[0], x[1]);
                 }
               }
               const int rel = lab - (col_base + c0);
               if (__any_sync(0xffffffffu, static_cast<uint32_t>(rel) < 32u)) {
 #pragma unroll
                 for (int c = 0; c < 32; ++c)
-                  if (c == rel) ph[c >> 1] = hsub2_u32(ph[c >> 1], (c & 1) ? 0x3C000000u : 0x00003C00u);  // -= 1.0
+                  if (c == rel) ph[c >> 1] = bsub2_u32(ph[c >> 1], (c & 1) ? 0x3F800000u : 0x00003F80u);  // -= 1.0
               }
             } else {
               // columns are query rows: lse2 is +inf beyond n_strm => P = 0 there (no tail special case)
@@ -415,9 +415,9 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
 #pragma unroll
               for (int c4 = 0; c4 < 8; ++c4) {
                 const float4 w = __ldg(l4 + c4);
-                ph[c4 * 2 + 0] = ex2_f16x2(fmaf(__uint_as_float(v[c4 * 4 + 0]), c2, my_nb - w.x),
+                ph[c4 * 2 + 0] = ex2_bf16x2(fmaf(__uint_as_float(v[c4 * 4 + 0]), c2, my_nb - w.x),
                                            fmaf(__uint_as_float(v[c4 * 4 + 1]), c2, my_nb - w.y));
-                ph[c4 * 2 + 1] = ex2_f16x2(fmaf(__uint_as_float(v[c4 * 4 + 2]), c2, my_nb - w.z),
+                ph[c4 * 2 + 1] = ex2_bf16x2(fmaf(__uint_as_float(v[c4 * 4 + 2]), c2, my_nb - w.z),
                                            fmaf(__uint_as_float(v[c4 * 4 + 3]), c2, my_nb - w.w));
               }
               // one-hot: does any query row of this chunk have its label inside this item tile?
@@ -429,7 +429,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
                 for (int c = 0; c < 32; ++c) {
                   if (hit & (1u << c)) {
                     const int lc = __shfl_sync(0xffffffffu, labc, c);
-                    if (lc == srow) ph[c >> 1] = hsub2_u32(ph[c >> 1], (c & 1) ? 0x3C000000u : 0x00003C00u);
+                    if (lc == srow) ph[c >> 1] = bsub2_u32(ph[c >> 1], (c & 1) ? 0x3F800000u : 0x00003F80u);
                   }
                 }
               }
@@ -437,14 +437,14 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
                 float rs[2] = {0.f, 0.f};
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                  const float2 f = h2_to_f2(ph[i]);
+                  const float2 f = b2_to_f2(ph[i]);
                   rs[0] += f.x;
                   rs[1] += f.y;
                 }
                 rowsum += rs[0] + rs[1];
               }
             }
-            // G tile, K-major, 128-byte swizzle: [k-chunk of 64][row][64 x f16]
+            // G tile, K-major, 128-byte swizzle: [k-chunk of 64][row][64 x bf16]
             uint8_t* gdst = g_smem + wg * C::G_BYTES + (c0 / 64) * 128 * 128 + r * 128;
             const int v0 = (c0 % 64) / 8;
 #pragma unroll
