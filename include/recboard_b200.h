@@ -57,26 +57,42 @@ int rb_score_dense(const void* U, const void* W, const float* bias, float scale,
                    int64_t M, int64_t N, int d, int dtype, int mode, void* ws, size_t ws_bytes,
                    rb_stream_t stream);
 
-/* Per-row softmax statistics of S = scale*U W^T + bias over this shard's N items, without
- * materialising S:  row_max[i] = max_j S_ij, row_sumexp[i] = sum_j exp(S_ij - row_max[i]),
- * label_logit[i] = S_i,(labels[i]-label_base) if that column lies in [0,N) else 0.
+/* Fused full-catalog cross-entropy, forward pass.  Per-row softmax statistics of
+ * S = scale*U W^T + bias over this shard's N items, without materialising S:
+ *   row_max[i] ~ max_j S_ij (any reference within 2^16 of it), row_sumexp[i] = sum_j exp(S_ij - row_max[i]),
+ *   label_logit[i] = S_i,(labels[i]-label_base) if that column lies in [0,N) else 0 (exact fp32 dot),
+ *   dU_unnorm[i,:] = sum_j exp(S_ij - row_max[i]) W_j   (nullable; the same sweep feeds a second MMA,
+ *                    so the gradient wrt U costs no extra pass -- bf16 mode, d <= 128, scale > 0).
  * loss = mean(row_max + log(row_sumexp) - label_logit) replaces
  * `einsum("MD,ND->MN")` + `self.criterion(logits, labels)` (SASRec/main.py:217-219,
  * GRU4Rec/main.py:175-178, BERT4Rec/main.py:181-182).  Row-sharded tables: merge
  * (max, sumexp, label_logit) across ranks. */
 int rb_ce_fwd(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
               int64_t label_base, int64_t M, int64_t N, int d, int dtype, int mode, float* row_max,
-              float* row_sumexp, float* label_logit, void* ws, size_t ws_bytes, rb_stream_t stream);
+              float* row_sumexp, float* label_logit, float* dU_unnorm, void* ws, size_t ws_bytes,
+              rb_stream_t stream);
+
+/* dU (M,d) = g*scale*( dU_unnorm * exp(row_max - lse) - [label in shard] W_label ): this shard's
+ * piece of the CE gradient wrt U from rb_ce_fwd's accumulator and the GLOBAL lse; pieces of
+ * different shards add up (one all-reduce).  g = grad_scale * (grad_scale_dev ? *grad_scale_dev : 1).
+ * Part of the autograd of SASRec/main.py:217-219 (`loss.backward()`, :249). */
+int rb_ce_du_finish(const float* dU_unnorm, const float* row_max, const float* lse, const void* W,
+                    const int64_t* labels, int64_t label_base, float scale, float grad_scale,
+                    const float* grad_scale_dev, int64_t M, int64_t N, int d, int dtype, float* dU,
+                    rb_stream_t stream);
 
 /* Gradients of g * sum_i (lse_i - S_i,label_i) given the GLOBAL lse (natural log), where
  * g = grad_scale * (grad_scale_dev ? *grad_scale_dev : 1)  (a device scalar lets autograd's
  * grad_output flow in without a host read):
- *   dU (M,d)  = g * scale * (softmax - onehot) W      (this shard's partial; nullable)
  *   dW (N,d)  = g * scale * (softmax - onehot)^T U    (nullable)
- *   dbias (N) = g * column sums of (softmax - onehot) (nullable)
- * Recomputes S tile by tile; P lives only in SMEM/TMEM.  Replaces the autograd of
- * SASRec/main.py:217-219 run by `loss.backward()` (:249): nll_loss_backward,
- * _log_softmax_backward_data and the two cuBLAS GEMMs. */
+ *   dbias (N) = g * column sums of (softmax - onehot) (nullable; needs dW)
+ *   dU (M,d)  = g * scale * (softmax - onehot) W      (this shard's partial; nullable.  Pass NULL when
+ *               rb_ce_fwd produced dU_unnorm -- rb_ce_du_finish is then all that is needed; otherwise
+ *               the forward sweep is re-run here)
+ * Recomputes S tile by tile; the softmax tile lives only in TMEM; the one-hot is applied exactly in
+ * fp32 by a sorted (deterministic) row update.  Replaces the autograd of SASRec/main.py:217-219 run
+ * by `loss.backward()` (:249): nll_loss_backward, _log_softmax_backward_data and the two cuBLAS
+ * GEMMs.  bf16 mode, d <= 128, scale > 0. */
 int rb_ce_bwd(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
               int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
               int64_t M, int64_t N, int d, int dtype, int mode, float* dU, float* dW, float* dbias,

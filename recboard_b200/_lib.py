@@ -25,7 +25,8 @@ SIGNATURES = {
     "rb_gather_rows": (_i32, [_p, _p, _p, _i64, _i64, _i32, _i32, _p]),
     "rb_scatter_add_rows": (_i32, [_p, _p, _p, _i64, _i64, _i32, _i32, _i64, _p, _sz, _p]),
     "rb_score_dense": (_i32, [_p, _p, _p, _f32, _p, _i64, _i64, _i32, _i32, _i32, _p, _sz, _p]),
-    "rb_ce_fwd": (_i32, [_p, _p, _p, _f32, _p, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _sz, _p]),
+    "rb_ce_fwd": (_i32, [_p, _p, _p, _f32, _p, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _sz, _p]),
+    "rb_ce_du_finish": (_i32, [_p, _p, _p, _p, _p, _i64, _f32, _f32, _p, _i64, _i64, _i32, _i32, _p, _p]),
     "rb_ce_bwd": (_i32, [_p, _p, _p, _f32, _p, _i64, _p, _f32, _p, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _sz, _p]),
     "rb_topk_eval": (_i32, [_p, _p, _p, _f32, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _p, _p, _p, _sz, _p]),
     "rb_topk_merge": (_i32, [_p, _p, _i32, _i64, _i32, _p, _p, _p]),

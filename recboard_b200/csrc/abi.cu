@@ -9,6 +9,7 @@
 
 #include "../../include/recboard_b200.h"
 #include "sweep.cuh"
+#include "pair.cuh"
 #include "simt.cuh"
 
 using namespace rb;
@@ -106,9 +107,10 @@ struct Plan { int n_stat_tiles, n_strm_tiles, n_splits, grid; };
 
 // Work item = (stationary tile, split of the streamed range).  Pick the smallest split count that
 // fills the SMs in whole waves (>= 97 %), keeping at least `min_tiles` streamed tiles per item.
-static Plan make_plan(long long n_stat, long long n_strm, int sms, int max_splits_cap, int min_tiles = 8) {
+static Plan make_plan(long long n_stat, long long n_strm, int sms, int max_splits_cap, int min_tiles = 8,
+                      int stat_rows = 128) {
   Plan p;
-  p.n_stat_tiles = static_cast<int>((n_stat + 127) / 128);
+  p.n_stat_tiles = static_cast<int>((n_stat + stat_rows - 1) / stat_rows);
   p.n_strm_tiles = static_cast<int>((n_strm + BN - 1) / BN);
   int max_s = std::max(1, std::min(p.n_strm_tiles / min_tiles, max_splits_cap));
   max_s = std::min(max_s, 8 * sms);
@@ -173,25 +175,38 @@ template <int EPI, bool ROWS>
 static int launch_sweep(int mode, int kc, const CUtensorMap& ts, const CUtensorMap& ty, const SweepArgs& a, int grid,
                         cudaStream_t st) {
   if (mode == RB_MODE_BF16) {
-    if constexpr (EPI == EPI_GRAD) {
-      if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 1, BN, 4, ROWS>>(ts, ty, a, grid, st);
-      if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 2, BN, 3, ROWS>>(ts, ty, a, grid, st);
-      return fail(RB_E_UNSUPPORTED, "CE backward supports d <= 128 in bf16 mode");
-    } else {
-      if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 1, BN, 6, ROWS>>(ts, ty, a, grid, st);
-      if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 2, BN, 4, ROWS>>(ts, ty, a, grid, st);
-      if (kc <= 4) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 4, BN, 2, ROWS>>(ts, ty, a, grid, st);
-    }
+    if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 1, BN, 6, ROWS>>(ts, ty, a, grid, st);
+    if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 2, BN, 4, ROWS>>(ts, ty, a, grid, st);
+    if (kc <= 4) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 4, BN, 2, ROWS>>(ts, ty, a, grid, st);
   } else {
-    if constexpr (EPI != EPI_GRAD) {
-      if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 1, BN, 4, ROWS>>(ts, ty, a, grid, st);
-      if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 2, BN, 2, ROWS>>(ts, ty, a, grid, st);
-    } else {
-      return fail(RB_E_UNSUPPORTED, "CE backward is bf16-mode only in this build");
-    }
+    if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 1, BN, 4, ROWS>>(ts, ty, a, grid, st);
+    if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 2, BN, 2, ROWS>>(ts, ty, a, grid, st);
   }
   return fail(RB_E_UNSUPPORTED, "unsupported feature width for mode %d (kc=%d)", mode, kc);
 }
+
+// ------------------------------------------------------------------- pair dispatch
+template <class C>
+static int launch_pair_t(const CUtensorMap& ts, const CUtensorMap& ty, const PairArgs& a, int grid, cudaStream_t st) {
+  RB_CUDA(cudaFuncSetAttribute(pair_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  pair_kernel<C><<<grid, PAIR_THREADS, C::SMEM_BYTES, st>>>(ts, ty, a);
+  RB_LAUNCH_CHECK("pair_kernel");
+  return 0;
+}
+template <int PASS>
+static int launch_pair(int kc, bool bias, const CUtensorMap& ts, const CUtensorMap& ty, const PairArgs& a, int grid,
+                       cudaStream_t st) {
+  if (kc == 1) {
+    if (bias) return launch_pair_t<PairCfg<PASS, 1, 6, true>>(ts, ty, a, grid, st);
+    return launch_pair_t<PairCfg<PASS, 1, 6, false>>(ts, ty, a, grid, st);
+  }
+  if (kc == 2) {
+    if (bias) return launch_pair_t<PairCfg<PASS, 2, 4, true>>(ts, ty, a, grid, st);
+    return launch_pair_t<PairCfg<PASS, 2, 4, false>>(ts, ty, a, grid, st);
+  }
+  return fail(RB_E_UNSUPPORTED, "the fused CE passes support d <= 128");
+}
+static bool pair_ok(int mode, int d, float scale) { return mode == RB_MODE_BF16 && d <= 128 && scale > 0.f; }
 
 // Operand staging: bf16 operands are used in place; fp32x3 operands are split into [hi|lo] in ws.
 struct Operand { const void* ptr; long long cols; bool bf16; };
@@ -237,11 +252,12 @@ static size_t scatter_ws_bytes(long long n_idx) {
   const long long chunks = (n_idx + RS_CHUNK - 1) / RS_CHUNK;
   return static_cast<size_t>(n_idx) * 4 * 4 + static_cast<size_t>(chunks) * 256 * 4 + 5 * 256;
 }
-extern "C" int rb_scatter_add_rows(const void* grad_out, const int64_t* idx, float* grad_table, int64_t n_idx,
-                                   int64_t n_rows, int d, int dtype, int64_t padding_idx, void* ws, size_t ws_bytes,
-                                   rb_stream_t stream) {
-  DevInfo dv; if (int r = get_dev(dv)) return r;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+// grad_table[idx[i]-idx_base] += alpha*(*alpha_dev) * grad_out[i] in a fixed order; optionally
+// cnt_out[row] += cnt_alpha*(*alpha_dev) * (#occurrences of row)
+static int scatter_add_impl(const void* grad_out, const int64_t* idx, long long idx_base, float* grad_table,
+                            int64_t n_idx, int64_t n_rows, int d, int dtype, int64_t padding_idx, float alpha,
+                            const float* alpha_dev, float* cnt_out, float cnt_alpha, void* ws, size_t ws_bytes,
+                            cudaStream_t st) {
   if (!grad_out || !idx || !grad_table) return fail(RB_E_ARG, "null pointer");
   if (n_idx < 0 || n_rows <= 0 || d <= 0 || d % 4) return fail(RB_E_ARG, "bad shape (d must be a multiple of 4)");
   if (n_idx >= (1ll << 31) || n_rows >= (1ll << 32) - 1) return fail(RB_E_ARG, "n_idx/n_rows too large");
@@ -253,7 +269,7 @@ extern "C" int rb_scatter_add_rows(const void* grad_out, const int64_t* idx, flo
   uint32_t* k0 = b.take<uint32_t>(n); uint32_t* v0 = b.take<uint32_t>(n);
   uint32_t* k1 = b.take<uint32_t>(n); uint32_t* v1 = b.take<uint32_t>(n);
   uint32_t* hist = b.take<uint32_t>(static_cast<size_t>(chunks) * 256);
-  rs_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(idx, k0, v0, n, n_rows);
+  rs_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(idx, idx_base, k0, v0, n, n_rows);
   RB_LAUNCH_CHECK("rs_init_kernel");
   int bits = 1;
   while ((1ull << bits) <= static_cast<unsigned long long>(n_rows)) ++bits;  // keys in [0, n_rows]
@@ -269,11 +285,18 @@ extern "C" int rb_scatter_add_rows(const void* grad_out, const int64_t* idx, flo
   const long long threads = 32ll * n;
   const int grid = static_cast<int>((threads + 255) / 256);
   if (dtype == RB_DTYPE_BF16)
-    scatter_segments_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(k0, v0, static_cast<const __nv_bfloat16*>(grad_out), grad_table, n, d, n_rows, padding_idx);
+    scatter_segments_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(k0, v0, static_cast<const __nv_bfloat16*>(grad_out), grad_table, n, d, n_rows, padding_idx, alpha, alpha_dev, cnt_out, cnt_alpha);
   else
-    scatter_segments_kernel<float><<<grid, 256, 0, st>>>(k0, v0, static_cast<const float*>(grad_out), grad_table, n, d, n_rows, padding_idx);
+    scatter_segments_kernel<float><<<grid, 256, 0, st>>>(k0, v0, static_cast<const float*>(grad_out), grad_table, n, d, n_rows, padding_idx, alpha, alpha_dev, cnt_out, cnt_alpha);
   RB_LAUNCH_CHECK("scatter_segments_kernel");
   return 0;
+}
+extern "C" int rb_scatter_add_rows(const void* grad_out, const int64_t* idx, float* grad_table, int64_t n_idx,
+                                   int64_t n_rows, int d, int dtype, int64_t padding_idx, void* ws, size_t ws_bytes,
+                                   rb_stream_t stream) {
+  DevInfo dv; if (int r = get_dev(dv)) return r;
+  return scatter_add_impl(grad_out, idx, 0, grad_table, n_idx, n_rows, d, dtype, padding_idx, 1.f, nullptr, nullptr, 0.f,
+                          ws, ws_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // ======================================================================= score dense
@@ -297,16 +320,61 @@ extern "C" int rb_score_dense(const void* U, const void* W, const float* bias, f
   return launch_sweep<EPI_DENSE, true>(mode, kc_for(d, mode), ts, ty, a, p.grid, st);
 }
 
+static size_t pair_fwd_ws(long long M, long long N, int d, int sms) {
+  Plan p = make_plan(M, N, sms, 1 << 20, 8, 256);
+  const size_t stat_pad = static_cast<size_t>(p.n_stat_tiles) * 256;
+  return 2 * stat_pad * p.n_splits * 4 + static_cast<size_t>(p.n_splits) * M * d * 4 +
+         static_cast<size_t>(p.n_strm_tiles) * 128 * 4 + 2048;
+}
+
 // ============================================================================ CE fwd
+// Fused pass (pair kernel, PASS_FWD) when dU_unnorm is requested; statistics-only sweep otherwise.
+static int ce_fwd_pair(const DevInfo& dv, const void* U, const void* W, const float* bias, float scale,
+                       const int64_t* labels, int64_t label_base, int64_t M, int64_t N, int d, float* row_max,
+                       float* row_sumexp, float* label_logit, float* dU_unnorm, Bump& b, cudaStream_t st) {
+  Plan p = make_plan(M, N, dv.sms, 1 << 20, 8, 256);
+  const long long stat_pad = 1ll * p.n_stat_tiles * 256;
+  const long long n_pad = 1ll * p.n_strm_tiles * 128;
+  float* pm2 = b.take<float>(stat_pad * p.n_splits);
+  float* pl = b.take<float>(stat_pad * p.n_splits);
+  float* pacc = b.take<float>(static_cast<size_t>(p.n_splits) * M * d);
+  float* bias2 = bias ? b.take<float>(n_pad) : nullptr;
+  if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
+  if (bias) {
+    bias2_kernel<<<(int)((n_pad + 255) / 256), 256, 0, st>>>(bias, bias2, N, n_pad);
+    RB_LAUNCH_CHECK("bias2_kernel");
+  }
+  CUtensorMap ts, ty;
+  if (int r = make_tmap(&ts, U, true, M, d, 128)) return r;
+  if (int r = make_tmap(&ty, W, true, N, d, 128)) return r;
+  PairArgs a{};
+  a.n_stat = (int)M; a.n_strm = (int)N; a.n_pair_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
+  a.n_splits = p.n_splits; a.d = d; a.stat_pad = (int)stat_pad; a.scale = scale; a.bias2 = bias2;
+  a.part_m2 = pm2; a.part_l = pl; a.acc_out = pacc;
+  if (int r = launch_pair<PASS_FWD>(kc_for(d, RB_MODE_BF16), bias != nullptr, ts, ty, a, p.grid, st)) return r;
+  const int grid = (int)((M * 32 + 255) / 256);
+  ce_fwd_finish_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
+      pm2, pl, pacc, p.n_splits, stat_pad, (int)M, d, static_cast<const __nv_bfloat16*>(U),
+      static_cast<const __nv_bfloat16*>(W), bias, labels, label_base, N, scale, row_max, row_sumexp, label_logit, dU_unnorm);
+  RB_LAUNCH_CHECK("ce_fwd_finish_kernel");
+  return 0;
+}
+
 extern "C" int rb_ce_fwd(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
                          int64_t label_base, int64_t M, int64_t N, int d, int dtype, int mode, float* row_max,
-                         float* row_sumexp, float* label_logit, void* ws, size_t ws_bytes, rb_stream_t stream) {
+                         float* row_sumexp, float* label_logit, float* dU_unnorm, void* ws, size_t ws_bytes,
+                         rb_stream_t stream) {
   DevInfo dv; if (int r = get_dev(dv)) return r;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (int r = check_common(U, W, M, N, d, dtype, mode)) return r;
   if (!labels || !row_max || !row_sumexp || !label_logit) return fail(RB_E_ARG, "null pointer");
   if (!ws) return fail(RB_E_WORKSPACE, "workspace required");
   Bump b(ws, ws_bytes);
+  if (dU_unnorm) {
+    if (!pair_ok(mode, d, scale))
+      return fail(RB_E_UNSUPPORTED, "the fused forward+dU pass needs bf16 mode, d <= 128 and scale > 0 (use rb_ce_bwd's dU instead)");
+    return ce_fwd_pair(dv, U, W, bias, scale, labels, label_base, M, N, d, row_max, row_sumexp, label_logit, dU_unnorm, b, st);
+  }
   Operand ou, ow;
   if (int r = stage_operand(U, M, d, mode, b, ou, st)) return r;
   if (int r = stage_operand(W, N, d, mode, b, ow, st)) return r;
@@ -332,7 +400,68 @@ extern "C" int rb_ce_fwd(const void* U, const void* W, const float* bias, float 
   return 0;
 }
 
+// dU from the forward pass's unnormalised accumulator (see ce_du_finish_kernel)
+extern "C" int rb_ce_du_finish(const float* dU_unnorm, const float* row_max, const float* lse, const void* W,
+                               const int64_t* labels, int64_t label_base, float scale, float grad_scale,
+                               const float* grad_scale_dev, int64_t M, int64_t N, int d, int dtype, float* dU,
+                               rb_stream_t stream) {
+  DevInfo dv; if (int r = get_dev(dv)) return r;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!dU_unnorm || !row_max || !lse || !W || !labels || !dU) return fail(RB_E_ARG, "null pointer");
+  if (M <= 0 || N <= 0 || d <= 0 || d % 8) return fail(RB_E_ARG, "bad shape M=%lld N=%lld d=%d", (long long)M, (long long)N, d);
+  const int grid = (int)((M * 32 + 255) / 256);
+  const float gs = grad_scale * scale;
+  if (dtype == RB_DTYPE_BF16)
+    ce_du_finish_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(dU_unnorm, row_max, lse, static_cast<const __nv_bfloat16*>(W), labels, label_base, N, gs, grad_scale_dev, (int)M, d, dU);
+  else if (dtype == RB_DTYPE_F32)
+    ce_du_finish_kernel<float><<<grid, 256, 0, st>>>(dU_unnorm, row_max, lse, static_cast<const float*>(W), labels, label_base, N, gs, grad_scale_dev, (int)M, d, dU);
+  else
+    return fail(RB_E_ARG, "unknown dtype %d", dtype);
+  RB_LAUNCH_CHECK("ce_du_finish_kernel");
+  return 0;
+}
+
 // ============================================================================ CE bwd
+// dW (+ dbias) through the pair kernel (PASS_DW): softmax tiles without the one-hot, then the exact
+// fp32 label correction dW[label_i] -= g*scale*u_i, dbias[label_i] -= g (sorted, deterministic).
+static int ce_bwd_dw_pair(const DevInfo& dv, const void* U, const void* W, const float* bias, float scale,
+                          const int64_t* labels, int64_t label_base, const float* lse2, float grad_scale,
+                          const float* grad_scale_dev, int64_t M, int64_t N, int d, float* dW, float* dbias, Bump& b,
+                          cudaStream_t st) {
+  Plan p = make_plan(N, M, dv.sms, 64, 8, 256);
+  const long long n_pad = 1ll * p.n_stat_tiles * 256;
+  float* part = (p.n_splits > 1) ? b.take<float>(static_cast<size_t>(p.n_splits) * N * d) : dW;
+  float* rs_part = nullptr;
+  if (dbias) rs_part = (p.n_splits > 1) ? b.take<float>(static_cast<size_t>(p.n_splits) * N) : dbias;
+  float* bias2 = bias ? b.take<float>(n_pad) : nullptr;
+  if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
+  if (bias) {
+    bias2_kernel<<<(int)((n_pad + 255) / 256), 256, 0, st>>>(bias, bias2, N, n_pad);
+    RB_LAUNCH_CHECK("bias2_kernel");
+  }
+  CUtensorMap ts, ty;
+  if (int r = make_tmap(&ts, W, true, N, d, 128)) return r;
+  if (int r = make_tmap(&ty, U, true, M, d, 128)) return r;
+  PairArgs a{};
+  a.n_stat = (int)N; a.n_strm = (int)M; a.n_pair_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
+  a.n_splits = p.n_splits; a.d = d; a.stat_pad = (int)n_pad; a.scale = scale; a.bias2 = bias2; a.lse2 = lse2;
+  a.gscale = grad_scale * scale; a.rscale = grad_scale; a.gscale_dev = grad_scale_dev; a.acc_out = part; a.rowsum_out = rs_part;
+  if (int r = launch_pair<PASS_DW>(kc_for(d, RB_MODE_BF16), bias != nullptr, ts, ty, a, p.grid, st)) return r;
+  if (p.n_splits > 1) {
+    const long long n = N * d;
+    partial_sum_kernel<<<(int)std::min<long long>((n + 255) / 256, dv.sms * 8), 256, 0, st>>>(part, p.n_splits, n, dW);
+    RB_LAUNCH_CHECK("partial_sum_kernel");
+    if (dbias) {
+      partial_sum_kernel<<<(int)std::min<long long>((N + 255) / 256, dv.sms * 8), 256, 0, st>>>(rs_part, p.n_splits, N, dbias);
+      RB_LAUNCH_CHECK("partial_sum_kernel");
+    }
+  }
+  void* sws = b.take<char>(scatter_ws_bytes(M));
+  if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
+  return scatter_add_impl(U, labels, label_base, dW, M, N, d, RB_DTYPE_BF16, -1, -grad_scale * scale, grad_scale_dev,
+                          dbias, -grad_scale, sws, scatter_ws_bytes(M), st);
+}
+
 extern "C" int rb_ce_bwd(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
                          int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
                          int64_t M, int64_t N, int d, int dtype, int mode, float* dU, float* dW, float* dbias,
@@ -342,62 +471,32 @@ extern "C" int rb_ce_bwd(const void* U, const void* W, const float* bias, float 
   if (int r = check_common(U, W, M, N, d, dtype, mode)) return r;
   if (mode != RB_MODE_BF16) return fail(RB_E_UNSUPPORTED, "CE backward is bf16-mode only in this build");
   if (d > 128) return fail(RB_E_UNSUPPORTED, "CE backward supports d <= 128");
+  if (!(scale > 0.f)) return fail(RB_E_UNSUPPORTED, "CE backward needs scale > 0");
   if (!labels || !lse) return fail(RB_E_ARG, "null pointer");
   if (!ws) return fail(RB_E_WORKSPACE, "workspace required");
   if (dbias && !dW) return fail(RB_E_ARG, "dbias is produced by the dW pass: pass dW too");
   Bump b(ws, ws_bytes);
-  const long long m_pad = ((M + 255) / 256) * 256 + 256;
-  int* lab32 = b.take<int>(m_pad);
-  float* lse2 = b.take<float>(m_pad);
-  if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small");
-  labels_local_kernel<<<(int)((m_pad + 255) / 256), 256, 0, st>>>(labels, label_base, N, lab32, (int)M, (int)m_pad);
-  RB_LAUNCH_CHECK("labels_local_kernel");
-  lse2_kernel<<<(int)((m_pad + 255) / 256), 256, 0, st>>>(lse, lse2, (int)M, (int)m_pad);
-  RB_LAUNCH_CHECK("lse2_kernel");
-  const int kc = kc_for(d, mode);
-  const float gs = grad_scale * scale;
 
-  if (dU) {  // rows stationary: dU_i = sum_j (P_ij - 1[j = label_i]) w_j
-    Plan p = make_plan(M, N, dv.sms, 1 << 20);
-    float* part = (p.n_splits > 1) ? b.take<float>(static_cast<size_t>(p.n_splits) * M * d) : dU;
+  if (dU) {  // no forward accumulator at hand: re-run the fused forward pass, then finish against the GLOBAL lse.
+             // (Callers that kept rb_ce_fwd's dU_unnorm use rb_ce_du_finish and pass dU = NULL here.)
+    float* rm = b.take<float>(M);
+    float* rl = b.take<float>(M);
+    float* rll = b.take<float>(M);
+    float* du_un = b.take<float>(static_cast<size_t>(M) * d);
     if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
-    CUtensorMap ts, ty;
-    if (int r = make_tmap(&ts, U, true, M, d, 128)) return r;
-    if (int r = make_tmap(&ty, W, true, N, d, BN)) return r;
-    SweepArgs a{};
-    a.n_stat = (int)M; a.n_strm = (int)N; a.n_stat_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
-    a.n_splits = p.n_splits; a.d = d; a.scale = scale; a.bias = bias; a.labels = lab32; a.lse2 = lse2;
-    a.gscale = gs; a.gscale_dev = grad_scale_dev; a.acc_out = part;
-    if (int r = launch_sweep<EPI_GRAD, true>(mode, kc, ts, ty, a, p.grid, st)) return r;
-    if (p.n_splits > 1) {
-      const long long n = M * d;
-      partial_sum_kernel<<<(int)std::min<long long>((n + 255) / 256, dv.sms * 8), 256, 0, st>>>(part, p.n_splits, n, dU);
-      RB_LAUNCH_CHECK("partial_sum_kernel");
-    }
+    if (int r = ce_fwd_pair(dv, U, W, bias, scale, labels, label_base, M, N, d, rm, rl, rll, du_un, b, st)) return r;
+    const int grid = (int)((M * 32 + 255) / 256);
+    ce_du_finish_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(du_un, rm, lse, static_cast<const __nv_bfloat16*>(W), labels,
+                                                               label_base, N, grad_scale * scale, grad_scale_dev, (int)M, d, dU);
+    RB_LAUNCH_CHECK("ce_du_finish_kernel");
   }
-  if (dW) {  // items stationary: dW_j = sum_i (P_ij - 1[j = label_i]) u_i
-    Plan p = make_plan(N, M, dv.sms, 64);
-    float* part = (p.n_splits > 1) ? b.take<float>(static_cast<size_t>(p.n_splits) * N * d) : dW;
-    float* rs_part = nullptr;
-    if (dbias) rs_part = (p.n_splits > 1) ? b.take<float>(static_cast<size_t>(p.n_splits) * N) : dbias;
-    if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
-    CUtensorMap ts, ty;
-    if (int r = make_tmap(&ts, W, true, N, d, 128)) return r;
-    if (int r = make_tmap(&ty, U, true, M, d, BN)) return r;
-    SweepArgs a{};
-    a.n_stat = (int)N; a.n_strm = (int)M; a.n_stat_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
-    a.n_splits = p.n_splits; a.d = d; a.scale = scale; a.bias = bias; a.labels = lab32; a.lse2 = lse2;
-    a.gscale = gs; a.gscale_dev = grad_scale_dev; a.acc_out = part; a.rowsum_out = rs_part;
-    if (int r = launch_sweep<EPI_GRAD, false>(mode, kc, ts, ty, a, p.grid, st)) return r;
-    if (p.n_splits > 1) {
-      const long long n = N * d;
-      partial_sum_kernel<<<(int)std::min<long long>((n + 255) / 256, dv.sms * 8), 256, 0, st>>>(part, p.n_splits, n, dW);
-      RB_LAUNCH_CHECK("partial_sum_kernel");
-      if (dbias) {
-        partial_sum_kernel<<<(int)std::min<long long>((N + 255) / 256, dv.sms * 8), 256, 0, st>>>(rs_part, p.n_splits, N, dbias);
-        RB_LAUNCH_CHECK("partial_sum_kernel");
-      }
-    }
+  if (dW) {
+    const long long m_pad = ((M + 127) / 128) * 128;
+    float* lse2 = b.take<float>(m_pad);
+    if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small");
+    lse2_kernel<<<(int)((m_pad + 255) / 256), 256, 0, st>>>(lse, lse2, (int)M, (int)m_pad);
+    RB_LAUNCH_CHECK("lse2_kernel");
+    return ce_bwd_dw_pair(dv, U, W, bias, scale, labels, label_base, lse2, grad_scale, grad_scale_dev, M, N, d, dW, dbias, b, st);
   }
   return 0;
 }
@@ -490,19 +589,19 @@ extern "C" size_t rb_workspace_bytes(int op, int64_t M, int64_t N, int d, int K,
   switch (op) {
     case RB_OP_SCATTER_ADD: return scatter_ws_bytes(nnz) + 4096;
     case RB_OP_SCORE_DENSE: return need + staged_bytes(M, d, mode) + staged_bytes(N, d, mode);
-    case RB_OP_CE_FWD: {
+    case RB_OP_CE_FWD: {  // the larger of the statistics-only sweep and the fused forward+dU pass
       Plan p = make_plan(M, N, sms, 1 << 20);
       const size_t m_pad = static_cast<size_t>(p.n_stat_tiles) * 128;
-      return need + staged_bytes(M, d, mode) + staged_bytes(N, d, mode) + m_pad * 4 + 3 * m_pad * p.n_splits * 4 + 2048;
+      const size_t stats = staged_bytes(M, d, mode) + staged_bytes(N, d, mode) + m_pad * 4 + 3 * m_pad * p.n_splits * 4 + 2048;
+      return need + std::max(stats, pair_fwd_ws(M, N, d, sms));
     }
     case RB_OP_CE_BWD: {
-      const size_t m_pad = ((M + 255) / 256) * 256 + 256;
-      size_t n = need + 2 * m_pad * 4 + 1024;
-      // split counts depend on the SM count of the device; bound them by the 8*sms cap of make_plan
-      Plan pu = make_plan(M, N, sms, 1 << 20);
-      Plan pw = make_plan(N, M, sms, 64);
-      n += (pu.n_splits > 1 ? static_cast<size_t>(pu.n_splits) * M * d * 4 : 0) + 512;
-      n += (pw.n_splits > 1 ? static_cast<size_t>(pw.n_splits) * N * (d + 1) * 4 : 0) + 512;
+      size_t n = need + static_cast<size_t>(M) * (d + 3) * 4 + 2048 + pair_fwd_ws(M, N, d, sms);  // dU by recompute
+      Plan pw = make_plan(N, M, sms, 64, 8, 256);
+      n += ((M + 127) / 128) * 128 * 4 + 512;
+      n += (pw.n_splits > 1 ? static_cast<size_t>(pw.n_splits) * N * (d + 1) * 4 : 0) + 1024;
+      n += static_cast<size_t>(pw.n_stat_tiles) * 256 * 4 + 512;  // bias2
+      n += scatter_ws_bytes(M) + 512;
       return n;
     }
     case RB_OP_TOPK_EVAL: {

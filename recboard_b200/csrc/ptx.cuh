@@ -8,9 +8,10 @@
 
 namespace rb {
 
-#ifndef RB_WATCHDOG_CYCLES
-// A mis-programmed pipeline must trap, never hang the GPU: every mbarrier spin is bounded.
-#define RB_WATCHDOG_CYCLES (4000000000ll)
+#ifndef RB_WATCHDOG_SPINS
+// A mis-programmed pipeline must trap, never hang the GPU: every mbarrier spin is bounded
+// (each failed try_wait already slept for the hardware's suspend-time hint; ~seconds in total).
+#define RB_WATCHDOG_SPINS (1u << 24)
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -57,15 +58,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __noinline__ void mbar_watchdog_trap(uint32_t bar, uint32_t parity) {
+  printf("rb: mbarrier watchdog block %d thread %d bar@%u parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+  __trap();
+}
+// try_wait suspends the warp in hardware for a bounded time, so the loop is not a hot spin; the
+// watchdog counts retries (no clock reads in the loop).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > RB_WATCHDOG_CYCLES) {
-      printf("rb: mbarrier watchdog block %d thread %d bar@%u parity %u\n", blockIdx.x,
-             threadIdx.x, smem_u32(bar), parity);
-      __trap();
-    }
+    if (++spins > RB_WATCHDOG_SPINS) mbar_watchdog_trap(smem_u32(bar), parity);
   }
 }
 
@@ -149,6 +151,32 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// same, into r[0..31] of a larger register array
+__device__ __forceinline__ void tmem_ld32p(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32p(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),
+        "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]),
+        "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -204,6 +232,12 @@ __device__ __forceinline__ uint32_t f32_orderable(float f) {
 }
 __device__ __forceinline__ float f32_from_orderable(uint32_t o) {
   return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
+}
+// three-input maximum (one FMNMX3 on sm_100)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
 }
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;

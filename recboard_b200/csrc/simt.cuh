@@ -99,11 +99,11 @@ __global__ void rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const ui
   }
 }
 
-__global__ void rs_init_kernel(const int64_t* __restrict__ idx, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                               int n, long long n_rows) {
+__global__ void rs_init_kernel(const int64_t* __restrict__ idx, long long base, uint32_t* __restrict__ keys,
+                               uint32_t* __restrict__ vals, int n, long long n_rows) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    const long long r = idx[i];
+    const long long r = idx[i] - base;
     keys[i] = (r >= 0 && r < n_rows) ? static_cast<uint32_t>(r) : static_cast<uint32_t>(n_rows);  // invalid ids sort last, skipped
     vals[i] = static_cast<uint32_t>(i);
   }
@@ -111,16 +111,27 @@ __global__ void rs_init_kernel(const int64_t* __restrict__ idx, uint32_t* __rest
 
 // One warp per sorted position that starts a run of equal row ids; sums the run in order.
 // (reference: embedding_dense_backward, autograd of SASRec/main.py:183 run at :249)
+// `alpha * (alpha_dev ? *alpha_dev : 1)` scales the added rows (1 for the plain embedding backward; the
+// CE backward uses it to subtract the one-hot rows, dW[label_i] -= g*scale*u_i, exactly in fp32);
+// cnt_out[key] += cnt_alpha * (alpha_dev) * run length (the matching dbias term), nullable.
 template <typename T>
 __global__ void scatter_segments_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ perm,
                                         const T* __restrict__ grad_out, float* __restrict__ grad_table, int n, int d,
-                                        long long n_rows, long long padding_idx) {
+                                        long long n_rows, long long padding_idx, float alpha,
+                                        const float* __restrict__ alpha_dev, float* __restrict__ cnt_out, float cnt_alpha) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= n) return;
   const uint32_t key = keys[w];
   if (static_cast<long long>(key) >= n_rows || static_cast<long long>(key) == padding_idx) return;
   if (w > 0 && keys[w - 1] == key) return;
+  const float adev = (alpha_dev != nullptr) ? __ldg(alpha_dev) : 1.f;
+  alpha *= adev;
+  if (cnt_out != nullptr && lane == 0) {
+    int run = 0;
+    for (int e = w; e < n && keys[e] == key; ++e) ++run;
+    cnt_out[key] += cnt_alpha * adev * static_cast<float>(run);
+  }
   for (int c = lane * 4; c < d; c += 128) {  // d % 4 == 0
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int e = w; e < n && keys[e] == key; ++e) {
@@ -137,7 +148,7 @@ __global__ void scatter_segments_kernel(const uint32_t* __restrict__ keys, const
     }
     float4* dst = reinterpret_cast<float4*>(grad_table + static_cast<long long>(key) * d + c);
     float4 o = *dst;
-    o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
+    o.x = fmaf(alpha, acc.x, o.x); o.y = fmaf(alpha, acc.y, o.y); o.z = fmaf(alpha, acc.z, o.z); o.w = fmaf(alpha, acc.w, o.w);
     *dst = o;
   }
 }
@@ -187,6 +198,92 @@ __global__ void csr_local_kernel(const int64_t* __restrict__ crow, const int64_t
     long long v = col[i] - id_base;
     v = v < -1 ? -1 : (v > 0x7ffffffe ? 0x7ffffffe : v);
     col32[i] = static_cast<int>(v);
+  }
+}
+
+// bias (N) -> bias*log2(e), zero-padded to n_pad
+__global__ void bias2_kernel(const float* __restrict__ bias, float* __restrict__ out, long long n, long long n_pad) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n_pad) out[i] = (i < n) ? bias[i] * 1.4426950408889634f : 0.f;
+}
+
+__device__ __forceinline__ float4 load4_as_float(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4_as_float(const __nv_bfloat16* p) {
+  const uint2 raw = *reinterpret_cast<const uint2*>(p);
+  return make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xFFFF0000u),
+                     __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xFFFF0000u));
+}
+
+// ---- finish of the fused CE forward (pair kernel, PASS_FWD): one warp per query row merges the
+// per-split partials (m2, l, A) and scores the label column exactly:
+//   row_max = m*ln2, row_sumexp = sum_s l_s 2^(m_s-m), dU_unnorm = sum_s A_s 2^(m_s-m)  (= sum_j e^(S_ij-row_max) w_j)
+//   label_logit = scale*<u_i, w_label> + bias[label]   (0 when the label is outside this shard)
+template <typename T>
+__global__ void ce_fwd_finish_kernel(const float* __restrict__ pm2, const float* __restrict__ pl,
+                                     const float* __restrict__ pacc, int n_splits, long long slot_stride, int m, int d,
+                                     const T* __restrict__ U, const T* __restrict__ W, const float* __restrict__ bias,
+                                     const int64_t* __restrict__ labels, long long label_base, long long n_items,
+                                     float scale, float* __restrict__ row_max, float* __restrict__ row_sumexp,
+                                     float* __restrict__ label_logit, float* __restrict__ du_unnorm) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= m) return;
+  float mx = -INFINITY;
+  for (int s = 0; s < n_splits; ++s) mx = fmaxf(mx, pm2[s * slot_stride + row]);
+  float l = 0.f;
+  for (int s = 0; s < n_splits; ++s) l += pl[s * slot_stride + row] * exp2f(pm2[s * slot_stride + row] - mx);
+  if (du_unnorm != nullptr) {
+    for (int c = lane * 4; c < d; c += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < n_splits; ++s) {
+        const float f = exp2f(pm2[s * slot_stride + row] - mx);
+        const float4 v = *reinterpret_cast<const float4*>(pacc + (static_cast<long long>(s) * m + row) * d + c);
+        acc.x = fmaf(f, v.x, acc.x); acc.y = fmaf(f, v.y, acc.y); acc.z = fmaf(f, v.z, acc.z); acc.w = fmaf(f, v.w, acc.w);
+      }
+      *reinterpret_cast<float4*>(du_unnorm + static_cast<long long>(row) * d + c) = acc;
+    }
+  }
+  const long long lab = labels[row] - label_base;
+  float ll = 0.f;
+  if (lab >= 0 && lab < n_items) {
+    float dot = 0.f;
+    for (int c = lane * 4; c < d; c += 128) {
+      const float4 u = load4_as_float(U + static_cast<long long>(row) * d + c);
+      const float4 w = load4_as_float(W + lab * d + c);
+      dot = fmaf(u.x, w.x, dot); dot = fmaf(u.y, w.y, dot); dot = fmaf(u.z, w.z, dot); dot = fmaf(u.w, w.w, dot);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    ll = dot * scale + (bias != nullptr ? __ldg(bias + lab) : 0.f);
+  }
+  if (lane == 0) {
+    row_max[row] = mx * 0.6931471805599453f;
+    row_sumexp[row] = l;
+    label_logit[row] = ll;
+  }
+}
+
+// dU (this shard's piece) = g*scale*( dU_unnorm * e^(row_max_local - lse) - [label in shard] w_label )
+// with g = grad_scale * (*grad_scale_dev); summed over shards it is the exact CE gradient wrt U.
+template <typename T>
+__global__ void ce_du_finish_kernel(const float* __restrict__ du_unnorm, const float* __restrict__ row_max,
+                                    const float* __restrict__ lse, const T* __restrict__ W,
+                                    const int64_t* __restrict__ labels, long long label_base, long long n_items,
+                                    float gs, const float* __restrict__ gs_dev, int m, int d, float* __restrict__ dU) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= m) return;
+  const float g = gs * (gs_dev != nullptr ? __ldg(gs_dev) : 1.f);
+  const float f = expf(row_max[row] - lse[row]);
+  const long long lab = labels[row] - label_base;
+  const bool has = lab >= 0 && lab < n_items;
+  for (int c = lane * 4; c < d; c += 128) {
+    const float4 a = *reinterpret_cast<const float4*>(du_unnorm + static_cast<long long>(row) * d + c);
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has) w = load4_as_float(W + lab * d + c);
+    float4 o;
+    o.x = g * (a.x * f - w.x); o.y = g * (a.y * f - w.y); o.z = g * (a.z * f - w.z); o.w = g * (a.w * f - w.w);
+    *reinterpret_cast<float4*>(dU + static_cast<long long>(row) * d + c) = o;
   }
 }
 

@@ -119,9 +119,16 @@ def score_dense(U: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] =
 # --------------------------------------------------------------------------------------
 # fused full-catalog cross-entropy
 # --------------------------------------------------------------------------------------
+def fused_du_supported(U, precision: Optional[str], scale: float) -> bool:
+    """Can rb_ce_fwd also produce the dU accumulator in the same sweep?  (bf16 mode, d <= 128, scale > 0)"""
+    return _mode_for(U, precision) == "bf16" and U.shape[1] <= 128 and scale > 0
+
+
 def ce_rowstats(U, W, labels, bias=None, scale: float = 1.0, label_base: int = 0,
-                precision: Optional[str] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """(row_max, row_sumexp, label_logit) of scale*U W^T + bias over this shard; (M,N) never exists."""
+                precision: Optional[str] = None, want_dU: bool = False):
+    """(row_max, row_sumexp, label_logit) of scale*U W^T + bias over this shard; (M,N) never exists.
+    With ``want_dU`` a fourth tensor is returned: dU_unnorm (M,d) = sum_j exp(S_ij - row_max_i) W_j,
+    accumulated by the same sweep (see ``ce_du_finish``)."""
     dev = L.require_cuda(U, W, labels, bias)
     Uc, Wc, mode = _prep(U.detach(), W.detach(), precision)
     M, d = Uc.shape
@@ -130,14 +137,37 @@ def ce_rowstats(U, W, labels, bias=None, scale: float = 1.0, label_base: int = 0
         raise TypeError("labels must be int64 of shape (M,)")
     b = None if bias is None else bias.detach().float().contiguous()
     out = torch.empty(3, M, dtype=torch.float32, device=dev)
+    du = torch.empty(M, d, dtype=torch.float32, device=dev) if want_dU else None
     ws, n = _ws(dev, L.OP_CE_FWD, M, N, d, mode=mode)
     L.check(
         L.lib().rb_ce_fwd(L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(labels.contiguous()), label_base,
-                          M, N, d, L.dtype_code(Uc), mode, L.ptr(out[0]), L.ptr(out[1]), L.ptr(out[2]),
+                          M, N, d, L.dtype_code(Uc), mode, L.ptr(out[0]), L.ptr(out[1]), L.ptr(out[2]), L.ptr(du),
                           L.ptr(ws), n, L.stream_ptr(dev)),
         "rb_ce_fwd",
     )
+    if want_dU:
+        return out[0], out[1], out[2], du
     return out[0], out[1], out[2]
+
+
+def ce_du_finish(du_unnorm, row_max, lse, W, labels, grad_scale: float, scale: float = 1.0, label_base: int = 0,
+                 grad_scale_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """This shard's piece of dU: g*scale*(du_unnorm*exp(row_max - lse) - [label in shard] W[label])."""
+    dev = L.require_cuda(du_unnorm, row_max, lse, W, labels, grad_scale_dev)
+    Wc = W.detach()
+    if Wc.dtype not in (torch.float32, torch.bfloat16):
+        Wc = Wc.float()
+    Wc = Wc.contiguous()
+    M, d = du_unnorm.shape
+    dU = torch.empty(M, d, dtype=torch.float32, device=dev)
+    L.check(
+        L.lib().rb_ce_du_finish(L.ptr(du_unnorm), L.ptr(row_max), L.ptr(lse.float().contiguous()), L.ptr(Wc),
+                                L.ptr(labels.contiguous()), label_base, float(scale), float(grad_scale),
+                                L.ptr(grad_scale_dev), M, Wc.shape[0], d, L.dtype_code(Wc), L.ptr(dU),
+                                L.stream_ptr(dev)),
+        "rb_ce_du_finish",
+    )
+    return dU
 
 
 def ce_backward(U, W, labels, lse, grad_scale: float, bias=None, scale: float = 1.0, label_base: int = 0,
@@ -169,10 +199,18 @@ def ce_backward(U, W, labels, lse, grad_scale: float, bias=None, scale: float = 
 class _FusedCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, U, W, labels, bias, scale, precision, reduction):
-        m, l, ll = ce_rowstats(U, W, labels, bias, scale, 0, precision)
+        # forward and dU share one sweep whenever the fused pass applies (ctx.needs_input_grad is set in forward)
+        ctx.fused_du = bool(ctx.needs_input_grad[0]) and fused_du_supported(U, precision, scale)
+        du = m = None
+        if ctx.fused_du:
+            m, l, ll, du = ce_rowstats(U, W, labels, bias, scale, 0, precision, want_dU=True)
+        else:
+            m, l, ll = ce_rowstats(U, W, labels, bias, scale, 0, precision)
         lse = m + torch.log(l)
         row_loss = lse - ll
-        ctx.save_for_backward(U, W, labels, bias if bias is not None else torch.empty(0, device=U.device), lse)
+        empty = torch.empty(0, device=U.device)
+        ctx.save_for_backward(U, W, labels, bias if bias is not None else empty, lse,
+                              du if du is not None else empty, m if du is not None else empty)
         ctx.has_bias = bias is not None
         ctx.scale, ctx.precision, ctx.reduction = scale, precision, reduction
         if reduction == "mean":
@@ -183,15 +221,23 @@ class _FusedCE(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        U, W, labels, bias, lse = ctx.saved_tensors
+        U, W, labels, bias, lse, du_un, row_max = ctx.saved_tensors
         bias = bias if ctx.has_bias else None
         M = U.shape[0]
         g = 1.0 / (M if ctx.reduction == "mean" else 1)
         need = ctx.needs_input_grad
         # the upstream scalar stays on the device: no host synchronisation in backward
-        dU, dW, db = ce_backward(U, W, labels, lse, g, bias, ctx.scale, 0, need[0], need[1],
-                                 ctx.has_bias and need[3], ctx.precision,
-                                 grad_scale_dev=grad_out.detach().float().reshape(1).contiguous())
+        gdev = grad_out.detach().float().reshape(1).contiguous()
+        need_db = ctx.has_bias and need[3]
+        dU = dW = db = None
+        if ctx.fused_du:
+            dU = ce_du_finish(du_un, row_max, lse, W, labels, g, ctx.scale, 0, gdev)
+            if need[1] or need_db:
+                _, dW, db = ce_backward(U, W, labels, lse, g, bias, ctx.scale, 0, False, need[1], need_db,
+                                        ctx.precision, grad_scale_dev=gdev)
+        else:
+            dU, dW, db = ce_backward(U, W, labels, lse, g, bias, ctx.scale, 0, need[0], need[1], need_db,
+                                     ctx.precision, grad_scale_dev=gdev)
         return (
             dU.to(U.dtype) if dU is not None else None,
             dW.to(W.dtype) if dW is not None else None,

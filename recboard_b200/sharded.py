@@ -58,9 +58,17 @@ class _ShardedCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, U, W_shard, labels, bias_shard, scale, row_start, group, precision):
         from . import ops
-        m, l, ll = ops.ce_rowstats(U, W_shard, labels, bias_shard, scale, label_base=row_start, precision=precision)
+        ctx.fused_du = bool(ctx.needs_input_grad[0]) and ops.fused_du_supported(U, precision, scale)
+        du = None
+        if ctx.fused_du:  # the forward sweep also accumulates this shard's unnormalised dU
+            m, l, ll, du = ops.ce_rowstats(U, W_shard, labels, bias_shard, scale, label_base=row_start,
+                                           precision=precision, want_dU=True)
+        else:
+            m, l, ll = ops.ce_rowstats(U, W_shard, labels, bias_shard, scale, label_base=row_start, precision=precision)
         lse, llg = merge_rowstats(allgather_rowstats(m, l, ll, group))
-        ctx.save_for_backward(U, W_shard, labels, bias_shard if bias_shard is not None else torch.empty(0, device=U.device), lse)
+        empty = torch.empty(0, device=U.device)
+        ctx.save_for_backward(U, W_shard, labels, bias_shard if bias_shard is not None else empty, lse,
+                              du if du is not None else empty, m if du is not None else empty)
         ctx.has_bias = bias_shard is not None
         ctx.scale, ctx.row_start, ctx.group, ctx.precision = scale, row_start, group, precision
         return (lse - llg).mean()
@@ -68,12 +76,21 @@ class _ShardedCE(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         from . import ops
-        U, W_shard, labels, bias, lse = ctx.saved_tensors
+        U, W_shard, labels, bias, lse, du_un, row_max = ctx.saved_tensors
         bias = bias if ctx.has_bias else None
         need = ctx.needs_input_grad
-        dU, dW, db = ops.ce_backward(U, W_shard, labels, lse, 1.0 / U.shape[0], bias, ctx.scale, ctx.row_start,
-                                     need[0], need[1], ctx.has_bias and need[3], ctx.precision,
-                                     grad_scale_dev=grad_out.detach().float().reshape(1).contiguous())
+        g = 1.0 / U.shape[0]
+        gdev = grad_out.detach().float().reshape(1).contiguous()
+        need_db = ctx.has_bias and need[3]
+        dU = dW = db = None
+        if ctx.fused_du:
+            dU = ops.ce_du_finish(du_un, row_max, lse, W_shard, labels, g, ctx.scale, ctx.row_start, gdev)
+            if need[1] or need_db:
+                _, dW, db = ops.ce_backward(U, W_shard, labels, lse, g, bias, ctx.scale, ctx.row_start, False,
+                                            need[1], need_db, ctx.precision, grad_scale_dev=gdev)
+        else:
+            dU, dW, db = ops.ce_backward(U, W_shard, labels, lse, g, bias, ctx.scale, ctx.row_start,
+                                         need[0], need[1], need_db, ctx.precision, grad_scale_dev=gdev)
         if dU is not None:
             dist.all_reduce(dU, op=dist.ReduceOp.SUM, group=ctx.group)
         return (dU.to(U.dtype) if dU is not None else None, dW.to(W_shard.dtype) if dW is not None else None, None,

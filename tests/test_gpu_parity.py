@@ -281,6 +281,37 @@ def test_sharded_partials_merge_like_multi_gpu(ops):
         dU_sum += dU
         assert_rel(dW, rdW[a:b], 2 * BF16_RTOL * float(rdW.abs().max() / rdW[a:b].abs().max()), f"dW shard {r}")
     assert_rel(dU_sum, rdU, 2 * BF16_RTOL, "dU")
+    # the fused forward+dU sweep: per-shard unnormalised accumulators finish against the global lse
+    dU_sum2 = torch.zeros(M, d, device="cuda")
+    for r in range(R):
+        a, b = sharded.shard_bounds(N, R, r)
+        Ws = Wd[a:b].contiguous()
+        m_, l_, ll_, du_un = ops.ce_rowstats(Ud, Ws, labd, label_base=a, want_dU=True)
+        assert torch.allclose((m_ + torch.log(l_)), stats[r][0] + torch.log(stats[r][1]), rtol=0, atol=2e-5)
+        dU_sum2 += ops.ce_du_finish(du_un, m_, lse, Ws, labd, 1.0 / M, label_base=a)
+    assert_rel(dU_sum2, rdU, 2 * BF16_RTOL, "dU (fused forward)")
+
+
+def test_fused_forward_lazy_reference_moves(ops):
+    """Rows whose maximum keeps growing by more than the rescale threshold from tile to tile (and a
+    huge first tile followed by small ones): the lazily updated reference must stay exact."""
+    g = torch.Generator().manual_seed(11)
+    M, N, d = 260, 128 * 9 + 17, 64
+    U = bf16_round(torch.randn(M, d, generator=g) / d ** 0.5)
+    W = bf16_round(torch.randn(N, d, generator=g) / d ** 0.5)
+    ramp = (torch.arange(N) // 128).float() * 3.0          # item norms grow tile by tile
+    W = bf16_round(W * (1.0 + ramp).unsqueeze(1))
+    U = bf16_round(U * 6.0)
+    W[:128] = bf16_round(W[:128] * torch.where(torch.arange(128) % 2 == 0, 40.0, 1.0).unsqueeze(1))  # huge first tile
+    lab = torch.randint(0, N, (M,), generator=g)
+    ref_loss, rdU, rdW, _ = orc.ce_fwd_bwd(U, W, lab)
+    Ud, Wd = dev(U).bfloat16().requires_grad_(True), dev(W).bfloat16().requires_grad_(True)
+    loss = ops.fused_ce(Ud, Wd, dev(lab))
+    loss.backward()
+    assert torch.isfinite(loss)
+    assert abs(float(loss) - float(ref_loss)) <= 1e-5 * abs(float(ref_loss))
+    assert_rel(Ud.grad, rdU, 2 * BF16_RTOL, "dU")
+    assert_rel(Wd.grad, rdW, 2 * BF16_RTOL, "dW")
 
 
 def test_full_size_properties(ops):
