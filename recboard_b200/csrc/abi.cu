@@ -502,9 +502,24 @@ extern "C" int rb_ce_bwd(const void* U, const void* W, const float* bias, float 
 }
 
 // ========================================================================= top-K eval
-// Three launches: (1) sweep with the tile-max epilogue, (2) per-row selection of the <= 2K-1 tiles that can
-// hold a top-K member, (3) exact re-scoring of those tiles + masked top-K.
-static int topk_selcap(int K) { return ((2 * K + 31) / 32) * 32; }
+// Exact masked top-K in two tensor-core sweeps (no dense (B,N), no per-element selection work):
+//   1. sweep<EPI_TOPK>: masked maximum of every (row, 128-item tile)
+//   2. tilemax_select:  tau[row] = K-th largest tile maximum  (>= K unseen items score >= tau, so every
+//                       top-K member does too) + the tile list the fallback uses
+//   3. tile_flag:       which (32-row group, tile) pairs can hold a candidate
+//   4. sweep<EPI_CAND>: recompute the scores, append every item with score >= tau to the (row, split,
+//                       warpgroup) sub-list (about K per row in total); flagged-off tiles are skipped
+//   5. topk_from_cand:  gather the sub-lists, drop seen items, sort, keep K.
+//   6. rows with an overflowed sub-list (massive ties / tiny catalogs): exact SIMT re-scoring of the
+//      selected tiles (topk_refine).
+static int topk_selcap(int K) { return ((2 * K + 64 + 31) / 32) * 32; }
+// capacity of one candidate sub-list: ~8x the expected share of a sub-list, a power of two in [32, 512]
+static int topk_candcap(int K, int n_sub) {
+  const int want = (8 * K + n_sub - 1) / n_sub;
+  int c = 32;
+  while (c < want && c < 512) c *= 2;
+  return c;
+}
 
 extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, float scale, const int64_t* seen_crow,
                             const int64_t* seen_col, int64_t seen_nnz, int64_t id_base, int64_t B, int64_t N, int d,
@@ -523,7 +538,8 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
   if (int r = stage_operand(U, B, d, mode, b, ou, st)) return r;
   if (int r = stage_operand(W, N, d, mode, b, ow, st)) return r;
   Plan p = make_plan(B, N, dv.sms, 1 << 20);
-  const int selcap = topk_selcap(K);
+  const int n_sub = 2 * p.n_splits;
+  const int selcap = topk_selcap(K), candcap = topk_candcap(K, n_sub);
   int* crow32 = nullptr; int* col32 = nullptr;
   long long nnz = 0;
   if (seen_crow) {
@@ -535,6 +551,11 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
   float* tmax = b.take<float>(static_cast<size_t>(B) * p.n_strm_tiles);
   int* sel = b.take<int>(static_cast<size_t>(B) * selcap);
   int* selcnt = b.take<int>(B);
+  float* tau = b.take<float>(B);
+  int* cand_cnt = b.take<int>(static_cast<size_t>(B) * n_sub);
+  int* overflow = b.take<int>(B);
+  unsigned char* flag = b.take<unsigned char>(static_cast<size_t>(p.n_stat_tiles) * 4 * p.n_strm_tiles);
+  unsigned long long* cand = b.take<unsigned long long>(static_cast<size_t>(B) * n_sub * candcap);
   if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
   if (seen_crow) {
     const long long n = std::max<long long>(B + 1, nnz);
@@ -548,21 +569,28 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
   a.n_stat = (int)B; a.n_strm = (int)N; a.n_stat_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
   a.n_splits = p.n_splits; a.d = d; a.scale = scale; a.bias = bias;
   a.seen_crow = crow32; a.seen_col = col32; a.tile_max = tmax;
+  a.tau = tau; a.tile_flag = flag; a.cand = cand; a.cand_cnt = cand_cnt; a.cand_cap = candcap;
   if (int r = launch_sweep<EPI_TOPK, true>(mode, kc_for(d, mode), ts, ty, a, p.grid, st)) return r;
   const int grid_w = static_cast<int>((B * 32 + 127) / 128);
-  if (K <= 128) tilemax_select_kernel<4><<<grid_w, 128, 0, st>>>(tmax, p.n_strm_tiles, B, K, selcap, sel, selcnt);
-  else tilemax_select_kernel<8><<<grid_w, 128, 0, st>>>(tmax, p.n_strm_tiles, B, K, selcap, sel, selcnt);
+  if (K <= 128) tilemax_select_kernel<4><<<grid_w, 128, 0, st>>>(tmax, p.n_strm_tiles, B, K, selcap, sel, selcnt, tau);
+  else tilemax_select_kernel<8><<<grid_w, 128, 0, st>>>(tmax, p.n_strm_tiles, B, K, selcap, sel, selcnt, tau);
   RB_LAUNCH_CHECK("tilemax_select_kernel");
-  const int grid_r = static_cast<int>((B + 3) / 4);
+  tile_flag_kernel<<<dim3((p.n_strm_tiles + 255) / 256, p.n_stat_tiles * 4), 256, 0, st>>>(tmax, tau, p.n_strm_tiles, B, flag);
+  RB_LAUNCH_CHECK("tile_flag_kernel");
+  if (int r = launch_sweep<EPI_CAND, true>(mode, kc_for(d, mode), ts, ty, a, p.grid, st)) return r;
   const int id_add = static_cast<int>(id_base);
+  if (K <= 128) topk_from_cand_kernel<4><<<grid_w, 128, 0, st>>>(cand, cand_cnt, n_sub, candcap, crow32, col32, B, K, id_add, top_vals, top_ids, overflow);
+  else topk_from_cand_kernel<8><<<grid_w, 128, 0, st>>>(cand, cand_cnt, n_sub, candcap, crow32, col32, B, K, id_add, top_vals, top_ids, overflow);
+  RB_LAUNCH_CHECK("topk_from_cand_kernel");
+  const int grid_r = static_cast<int>((B + 3) / 4);
   if (dtype == RB_DTYPE_BF16) {
     const __nv_bfloat16* Ub = static_cast<const __nv_bfloat16*>(U); const __nv_bfloat16* Wb = static_cast<const __nv_bfloat16*>(W);
-    if (K <= 128) topk_refine_kernel<__nv_bfloat16, 4><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, crow32, col32, sel, selcnt, selcap, K, id_add, top_vals, top_ids);
-    else topk_refine_kernel<__nv_bfloat16, 8><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, crow32, col32, sel, selcnt, selcap, K, id_add, top_vals, top_ids);
+    if (K <= 128) topk_refine_kernel<__nv_bfloat16, 4><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, crow32, col32, sel, selcnt, selcap, K, id_add, top_vals, top_ids, overflow);
+    else topk_refine_kernel<__nv_bfloat16, 8><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, crow32, col32, sel, selcnt, selcap, K, id_add, top_vals, top_ids, overflow);
   } else {
     const float* Uf = static_cast<const float*>(U); const float* Wf = static_cast<const float*>(W);
-    if (K <= 128) topk_refine_kernel<float, 4><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, crow32, col32, sel, selcnt, selcap, K, id_add, top_vals, top_ids);
-    else topk_refine_kernel<float, 8><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, crow32, col32, sel, selcnt, selcap, K, id_add, top_vals, top_ids);
+    if (K <= 128) topk_refine_kernel<float, 4><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, crow32, col32, sel, selcnt, selcap, K, id_add, top_vals, top_ids, overflow);
+    else topk_refine_kernel<float, 8><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, crow32, col32, sel, selcnt, selcap, K, id_add, top_vals, top_ids, overflow);
   }
   RB_LAUNCH_CHECK("topk_refine_kernel");
   return 0;
@@ -607,7 +635,9 @@ extern "C" size_t rb_workspace_bytes(int op, int64_t M, int64_t N, int d, int K,
     case RB_OP_TOPK_EVAL: {
       Plan p = make_plan(M, N, sms, 1 << 20);
       return need + staged_bytes(M, d, mode) + staged_bytes(N, d, mode) + (M + 1 + std::max<int64_t>(nnz, 1)) * 4 +
-             static_cast<size_t>(M) * (static_cast<size_t>(p.n_strm_tiles) + topk_selcap(K) + 1) * 4 + 2048;
+             static_cast<size_t>(M) * (static_cast<size_t>(p.n_strm_tiles) + topk_selcap(K) + 4) * 4 +
+             static_cast<size_t>(p.n_stat_tiles) * 4 * p.n_strm_tiles +
+             static_cast<size_t>(M) * 2 * p.n_splits * (topk_candcap(K, 2 * p.n_splits) * 8 + 4) + 4096;
     }
     default: return 0;
   }

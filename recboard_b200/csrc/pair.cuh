@@ -132,84 +132,95 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
 
   if (warp == 0) {
     // ======================================================================= TMA producer
-    if (lane == 0) {
-      uint32_t it = 0, k = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++k) {
-        int pt, split, t0, t1;
-        item_range(item, pt, split, t0, t1);
-        mbar_wait(&bar->x_empty, (k & 1) ^ 1);
+    // The whole warp runs the (uniform) control flow; one elected lane issues the copies.
+    uint32_t it = 0, k = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++k) {
+      int pt, split, t0, t1;
+      item_range(item, pt, split, t0, t1);
+      mbar_wait(&bar->x_empty, (k & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&bar->x_full, 2 * C::TILE_BYTES);
 #pragma unroll
         for (int g = 0; g < 2; ++g)
 #pragma unroll
           for (int c = 0; c < C::KC; ++c)
             tma_load_2d(x_smem + g * C::TILE_BYTES + c * 16384, &tm_stat, &bar->x_full, c * 64, (pt * 2 + g) * 128);
-        for (int t = t0; t < t1; ++t, ++it) {
-          const uint32_t st = it % C::NS, ph = (it / C::NS) & 1;
-          mbar_wait(&bar->empty[st], ph ^ 1);
+      }
+      __syncwarp();
+      for (int t = t0; t < t1; ++t, ++it) {
+        const uint32_t st = it % C::NS, ph = (it / C::NS) & 1;
+        mbar_wait(&bar->empty[st], ph ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&bar->full[st], C::TILE_BYTES);
 #pragma unroll
           for (int c = 0; c < C::KC; ++c)
             tma_load_2d(y_smem + st * C::TILE_BYTES + c * 16384, &tm_strm, &bar->full[st], c * 64, t * 128);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ========================================================================= MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc1 = make_idesc(FMT_BF16, 128, 128, 0, 0);
-      constexpr uint32_t idesc2 = make_idesc(FMT_BF16, 128, C::DPAD, 0, 1);  // A: P from TMEM, B: Y tile MN-major
-      const uint32_t x_addr = smem_u32(x_smem), y_addr = smem_u32(y_smem);
-      uint32_t it = 0, k = 0;
+    // Warp-converged loop (descriptor arithmetic stays in uniform registers); one elected lane issues
+    // the tcgen05.mma / commit instructions.
+    constexpr uint32_t idesc1 = make_idesc(FMT_BF16, 128, 128, 0, 0);
+    constexpr uint32_t idesc2 = make_idesc(FMT_BF16, 128, C::DPAD, 0, 1);  // A: P from TMEM, B: Y tile MN-major
+    constexpr uint32_t dhi = smem_desc_hi(1024);
+    const uint32_t x_lo = smem_desc_lo(smem_u32(x_smem), 16);
+    const uint32_t y_lo1 = smem_desc_lo(smem_u32(y_smem), 16);      // K-major view of a streamed tile (MMA1)
+    const uint32_t y_lo2 = smem_desc_lo(smem_u32(y_smem), 16384);   // MN-major view of the same tile (MMA2)
+    uint32_t it = 0, k = 0;
 
-      // S_g = X_g . Y^T
-      auto m1 = [&](int g, uint32_t st) {
-        const uint32_t d_tmem = tmem_base + g * 128;
+    // S_g = X_g . Y^T
+    auto m1 = [&](int g, uint32_t st) {
+      const uint32_t d_tmem = tmem_base + g * 128;
+      const uint32_t xg = x_lo + ((g * C::TILE_BYTES) >> 4), ys = y_lo1 + ((st * C::TILE_BYTES) >> 4);
 #pragma unroll
-        for (int c = 0; c < C::KC; ++c) {
+      for (int c = 0; c < C::KC; ++c) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t ad = make_smem_desc(x_addr + g * C::TILE_BYTES + c * 16384 + kk * 32, 16, 1024);
-            const uint64_t bd = make_smem_desc(y_addr + st * C::TILE_BYTES + c * 16384 + kk * 32, 16, 1024);
-            mma_f16_ss(d_tmem, ad, bd, idesc1, (c | kk) != 0);
-          }
-        }
-        tc_commit(&bar->s_full[g]);
-      };
-      // A_g (+)= P_g . Y      (P_g: bf16 pairs in columns [0,64) of S_g)
-      auto m2 = [&](int g, uint32_t st, bool first) {
-        const uint32_t d_tmem = tmem_base + (g == 0 ? C::ACC0 : C::ACC1);
-        const uint32_t a_tmem = tmem_base + g * 128;
+        for (int kk = 0; kk < 4; ++kk)
+          mma_f16_ss(d_tmem, smem_desc(dhi, xg + ((c * 16384 + kk * 32) >> 4)),
+                     smem_desc(dhi, ys + ((c * 16384 + kk * 32) >> 4)), idesc1, (c | kk) != 0);
+      }
+      tc_commit(&bar->s_full[g]);
+    };
+    // A_g (+)= P_g . Y      (P_g: bf16 pairs in columns [0,64) of S_g)
+    auto m2 = [&](int g, uint32_t st, bool first) {
+      const uint32_t d_tmem = tmem_base + (g == 0 ? C::ACC0 : C::ACC1);
+      const uint32_t a_tmem = tmem_base + g * 128;
+      const uint32_t ys = y_lo2 + ((st * C::TILE_BYTES) >> 4);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t bd = make_smem_desc(y_addr + st * C::TILE_BYTES + kk * 2048, 16384, 1024);
-          mma_f16_ts(d_tmem, a_tmem + kk * 8, bd, idesc2, !(first && kk == 0));
-        }
-      };
+      for (int kk = 0; kk < 8; ++kk)
+        mma_f16_ts(d_tmem, a_tmem + kk * 8, smem_desc(dhi, ys + ((kk * 2048) >> 4)), idesc2, !(first && kk == 0));
+    };
 
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++k) {
-        int pt, split, t0, t1;
-        item_range(item, pt, split, t0, t1);
-        const int n = t1 - t0;
-        mbar_wait(&bar->x_full, k & 1);
-        {
-          const uint32_t st = it % C::NS, ph = (it / C::NS) & 1;
-          mbar_wait(&bar->full[st], ph);
-          tc_fence_after();
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++k) {
+      int pt, split, t0, t1;
+      item_range(item, pt, split, t0, t1);
+      const int n = t1 - t0;
+      mbar_wait(&bar->x_full, k & 1);
+      {
+        const uint32_t st = it % C::NS, ph = (it / C::NS) & 1;
+        mbar_wait(&bar->full[st], ph);
+        tc_fence_after();
+        if (elect_one()) {
           m1(0, st);
           m1(1, st);
           if (n == 1) tc_commit(&bar->x_empty);
         }
-        for (int j = 0; j < n; ++j, ++it) {
-          const uint32_t st = it % C::NS;
-          const uint32_t st1 = (it + 1) % C::NS, ph1 = ((it + 1) / C::NS) & 1;
-          const uint32_t pph = it & 1;
-          if (j + 1 < n) mbar_wait(&bar->full[st1], ph1);
+        __syncwarp();
+      }
+      for (int j = 0; j < n; ++j, ++it) {
+        const uint32_t st = it % C::NS;
+        const uint32_t st1 = (it + 1) % C::NS, ph1 = ((it + 1) / C::NS) & 1;
+        const uint32_t pph = it & 1;
+        if (j + 1 < n) mbar_wait(&bar->full[st1], ph1);
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            mbar_wait(&bar->p_full[g], pph);
-            if (j == 0) mbar_wait(&bar->acc_empty[g], (k & 1) ^ 1);
-            tc_fence_after();
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&bar->p_full[g], pph);
+          if (j == 0) mbar_wait(&bar->acc_empty[g], (k & 1) ^ 1);
+          tc_fence_after();
+          if (elect_one()) {
             m2(g, st, j == 0);
             if (g == 1) tc_commit(&bar->empty[st]);          // all four MMAs on Y_j retire before this fires
             if (j + 1 == n) tc_commit(&bar->acc_full[g]);
@@ -218,6 +229,7 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
               if (g == 1 && j + 2 == n) tc_commit(&bar->x_empty);  // last use of X0/X1 in this item
             }
           }
+          __syncwarp();
         }
       }
     }

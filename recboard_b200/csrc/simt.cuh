@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include "ptx.cuh"
+#include "sweep.cuh"
 
 namespace rb {
 
@@ -316,10 +317,7 @@ __global__ void partial_sum_kernel(const float* __restrict__ part, int n_splits,
 }
 
 // ------------------------------------------------------------------------- top-K machinery
-// key order: score desc, then id asc
-__device__ __forceinline__ unsigned long long topk_key(float v, int id) {
-  return (static_cast<unsigned long long>(f32_orderable(v)) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(id));
-}
+// key order: score desc, then id asc (topk_key lives in sweep.cuh, shared with the sweep epilogues)
 
 // Warp-wide bitonic network over 32*E values held E per lane (blocked: element index = lane*E + e).
 // One compare-exchange stage (k = block size, j = partner distance); "up" blocks sort descending.
@@ -389,12 +387,13 @@ __device__ __forceinline__ T warp_blocked_get(const T (&v)[E], int idx) {
   return out;
 }
 
-// ---- top-K pass 2a: per row, the K-th largest tile maximum tau and the list of tiles that can hold
-// a top-K member: every tile with max > tau (at most K-1 of them) plus the first K tiles with
-// max == tau (lowest ids first: the tie rule), in ascending tile order.  One warp per row.
+// ---- top-K pass 2a: per row, the K-th largest CLEAN tile maximum tau (NaN marks a dirty tile, one that
+// holds a seen id) and, for the fallback, the list of tiles that can hold a top-K member: every tile
+// with max > tau (at most K-1 of them), the first K tiles with max == tau (lowest ids first: the tie
+// rule) and every dirty tile, in ascending tile order.  One warp per row.
 template <int E>
 __global__ void tilemax_select_kernel(const float* __restrict__ T, int n_tiles, long long n_rows, int K, int selcap,
-                                      int* __restrict__ sel, int* __restrict__ selcnt) {
+                                      int* __restrict__ sel, int* __restrict__ selcnt, float* __restrict__ tau_out) {
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n_rows) return;
@@ -410,6 +409,7 @@ __global__ void tilemax_select_kernel(const float* __restrict__ T, int n_tiles, 
     for (int e = 0; e < E; ++e) {
       const int i = base + e * 32 + lane;
       cur[e] = (i < n_tiles) ? __ldg(t + i) : -INFINITY;
+      if (cur[e] != cur[e]) cur[e] = -INFINITY;  // dirty tile (holds a seen id): never supports the threshold
       any |= cur[e] > tau;
     }
     if (!__any_sync(0xffffffffu, any)) continue;
@@ -417,6 +417,7 @@ __global__ void tilemax_select_kernel(const float* __restrict__ T, int n_tiles, 
     warp_topk_absorb<float, E>(best, cur);
     tau = warp_blocked_get<float, E>(best, K - 1);
   }
+  if (lane == 0) tau_out[row] = tau;  // -inf when fewer than K clean tiles exist
   int cnt = 0, eq_taken = 0;
   const uint32_t lt = (1u << lane) - 1u;
   for (int base = 0; base < n_tiles; base += 32) {
@@ -424,30 +425,130 @@ __global__ void tilemax_select_kernel(const float* __restrict__ T, int n_tiles, 
     const float v = (i < n_tiles) ? __ldg(t + i) : -INFINITY;
     const bool gt = v > tau;
     const bool eq = (v == tau) && (v > -INFINITY);
+    const bool dirty = v != v;  // may hold unseen items of any score: always part of the fallback's tile list
     const uint32_t eqm = __ballot_sync(0xffffffffu, eq);
-    const bool take = gt || (eq && (eq_taken + __popc(eqm & lt) < K));
+    const bool take = gt || dirty || (eq && (eq_taken + __popc(eqm & lt) < K));
     eq_taken += __popc(eqm);
     const uint32_t m = __ballot_sync(0xffffffffu, take);
     const int pos = cnt + __popc(m & lt);
     if (take && pos < selcap) sel[row * selcap + pos] = i;
     cnt += __popc(m);
   }
-  if (lane == 0) selcnt[row] = min(cnt, selcap);
+  if (lane == 0) selcnt[row] = cnt > selcap ? -1 : cnt;  // -1: list overflow, the fallback scans every tile
 }
 
-// ---- top-K pass 2b: re-score the selected tiles of a row exactly (fp32 FMA over the stored operands),
+// ---- flag table of the candidate sweep: flag[g][t] != 0 iff some row of the 32-row group g (= one
+// epilogue warp's rows) has tile maximum >= its threshold in streamed tile t.
+__global__ void tile_flag_kernel(const float* __restrict__ T, const float* __restrict__ tau, int n_tiles, long long n_rows,
+                                 unsigned char* __restrict__ flag) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long g = blockIdx.y;
+  if (t >= n_tiles) return;
+  const long long r0 = g * 32, r1 = min(n_rows, r0 + 32);
+  bool any = false;
+  for (long long r = r0; r < r1; ++r) {
+    const float v = __ldg(T + r * n_tiles + t);
+    any |= (v >= __ldg(tau + r)) || (v != v);  // NaN = dirty tile: always scanned
+  }
+  flag[g * n_tiles + t] = any ? 1 : 0;
+}
+
+// ---- top-K pass 3: gather the row's candidate sub-lists (the items with score >= tau found by the
+// EPI_CAND sweep), drop seen items (UniSRec/main.py:413), keep the K best by (score desc, id asc).
+// Rows with an overflowed sub-list are flagged for the exact fallback below.  One warp per row.
+template <int E>
+__global__ void __launch_bounds__(128)
+topk_from_cand_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ cand_cnt, int n_sub, int cap,
+                      const int* __restrict__ seen_crow, const int* __restrict__ seen_col,
+                      long long n_rows, int K, int id_add, float* __restrict__ out_vals, int* __restrict__ out_ids,
+                      int* __restrict__ overflow) {
+  __shared__ unsigned long long stage_s[4][256];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * 4 + wib;
+  if (row >= n_rows) return;
+  unsigned long long* stage = stage_s[wib];
+  const int* cnts = cand_cnt + row * n_sub;
+  bool ovf = false;
+  for (int s = lane; s < n_sub; s += 32) ovf |= cnts[s] > cap;
+  ovf = __any_sync(0xffffffffu, ovf);
+  if (lane == 0) overflow[row] = ovf ? 1 : 0;
+  if (ovf) return;
+  int s_lo = 0, s_hi = 0;
+  if (seen_crow != nullptr) { s_lo = seen_crow[row]; s_hi = seen_crow[row + 1]; }
+  unsigned long long best[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) best[e] = 0ull;
+  int ns = 0;
+  const uint32_t lt = (1u << lane) - 1u;
+  auto flush = [&]() {
+    __syncwarp();
+    for (int base = 0; base < ns; base += 32 * E) {
+      unsigned long long cur[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int i = base + lane * E + e;
+        cur[e] = (i < ns) ? stage[i] : 0ull;
+      }
+      warp_bitonic_sort_desc<unsigned long long, E>(cur);
+      warp_topk_absorb<unsigned long long, E>(best, cur);
+    }
+    ns = 0;
+    __syncwarp();
+  };
+  for (int s = 0; s < n_sub; ++s) {
+    const int cnt = cnts[s];
+    const unsigned long long* c = cand + (row * n_sub + s) * cap;
+    for (int base = 0; base < cnt; base += 32) {
+      const int i = base + lane;
+      unsigned long long key = (i < cnt) ? c[i] : 0ull;
+      bool pass = key != 0ull;
+      if (pass && s_hi > s_lo) {
+        const int item = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFu));
+        int lo = s_lo, hi = s_hi;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (__ldg(seen_col + mid) < item) lo = mid + 1; else hi = mid;
+        }
+        if (lo < s_hi && __ldg(seen_col + lo) == item) pass = false;
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, pass);
+      if (pass) stage[ns + __popc(m & lt)] = key;
+      ns += __popc(m);
+      if (ns > 256 - 32) flush();
+    }
+  }
+  flush();
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = lane * E + e;
+    if (i < K) {
+      const unsigned long long key = best[e];
+      float v = MASKED_SCORE_F;
+      int id = -1;
+      if (key != 0ull) {
+        v = f32_from_orderable(static_cast<uint32_t>(key >> 32));
+        id = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFu)) + id_add;
+      }
+      out_vals[row * K + i] = v;
+      out_ids[row * K + i] = id;
+    }
+  }
+}
+
+// ---- top-K fallback (rows flagged in `only`; all rows when `only` is null): re-score the selected tiles of a row exactly (fp32 FMA over the stored operands),
 // skip seen ids, keep the K best by (score desc, id asc).  One warp per row; lane <-> item.
 template <typename TW, int E>
 __global__ void __launch_bounds__(128)
 topk_refine_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const float* __restrict__ bias, float scale, int d,
                    long long n_rows, int n_items, const int* __restrict__ seen_crow, const int* __restrict__ seen_col,
                    const int* __restrict__ sel, const int* __restrict__ selcnt, int selcap, int K, int id_add,
-                   float* __restrict__ out_vals, int* __restrict__ out_ids) {
+                   float* __restrict__ out_vals, int* __restrict__ out_ids, const int* __restrict__ only) {
   __shared__ __align__(16) float u_s[4][256];
   __shared__ unsigned long long cand_s[4][256];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 4 + wib;
   if (row >= n_rows) return;
+  if (only != nullptr && only[row] == 0) return;
   float* u = u_s[wib];
   unsigned long long* cand = cand_s[wib];
   for (int k = lane; k < 256; k += 32) u[k] = (k < d) ? static_cast<float>(U[row * d + k]) : 0.f;
@@ -460,7 +561,9 @@ topk_refine_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const flo
   unsigned long long kth = 0ull;
   int ncand = 0;
   const uint32_t lt = (1u << lane) - 1u;
-  const int ns = selcnt[row];
+  const int n_tiles = (n_items + 127) / 128;
+  const int ns_raw = selcnt[row];
+  const int ns = ns_raw < 0 ? n_tiles : ns_raw;
 
   auto flush = [&]() {
     for (int base = 0; base < ncand; base += 32 * E) {
@@ -479,7 +582,7 @@ topk_refine_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const flo
   };
 
   for (int si = 0; si < ns; ++si) {
-    const int tile = sel[row * selcap + si];
+    const int tile = ns_raw < 0 ? si : sel[row * selcap + si];
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     int item[4];
     const TW* wrow[4];

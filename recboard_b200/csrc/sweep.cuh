@@ -5,8 +5,15 @@
 //
 //   EPI_DENSE  store S (compat path for recommend_from_full, reference SASRec/main.py:228)
 //   EPI_LSE    online (max, sum-exp) + label-logit pick   (F.cross_entropy fwd, SASRec/main.py:217-219)
-//   EPI_TOPK   masked maximum of every (row, 128-item tile): pass 1 of the exact top-K
-//              (UniSRec/main.py:408-435 without dense (B,N); simt.cuh finishes the selection)
+//   EPI_TOPK   maximum of every (row, 128-item tile): pass 1 of the exact top-K (UniSRec/main.py:408-435
+//              without dense (B,N)).  A tile holding one of the row's seen ids is reported as NaN
+//              ("dirty": it never supports the threshold but is always scanned by pass 2), so no
+//              per-item masking happens here.  simt.cuh turns the clean tile maxima into a per-row
+//              admission threshold tau = K-th largest (>= K unseen items reach it)
+//   EPI_CAND   pass 2: the same sweep again, emitting every (row, item) with score >= tau[row] (about K
+//              per row) into the (row, split, warpgroup) candidate sub-list -- a register counter and a
+//              plain store, no global-memory latency in the epilogue; tiles no row of a warp can hit
+//              (flag table) are skipped without touching TMEM.  Seen items are dropped by the finish kernel.
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
 // warps 2..9 = two epilogue warpgroups (thread <-> TMEM lane <-> stationary row); warpgroup g owns
@@ -16,7 +23,7 @@
 
 namespace rb {
 
-enum : int { EPI_DENSE = 0, EPI_LSE = 1, EPI_TOPK = 3 };
+enum : int { EPI_DENSE = 0, EPI_LSE = 1, EPI_TOPK = 3, EPI_CAND = 4 };
 enum : int { DT_BF16 = 0, DT_TF32X3 = 1 };
 
 constexpr float LOG2E = 1.4426950408889634f;
@@ -45,7 +52,23 @@ struct SweepArgs {
   const int* seen_crow;  // [n_stat+1] CSR of already-seen LOCAL item ids, sorted per row (nullable)
   const int* seen_col;
   float* tile_max;    // [n_stat][n_strm_tiles]
+  // EPI_CAND (rows stationary): pass 2 of the top-K
+  const float* tau;                 // [n_stat] admission threshold of the row (score >= tau is a candidate)
+  const unsigned char* tile_flag;   // [n_stat_tiles*4][n_strm_tiles] != 0: some row of that 32-row group can hit
+  unsigned long long* cand;         // [n_stat][2*n_splits][cand_cap] candidate keys, one sub-list per (split, warpgroup)
+  int* cand_cnt;                    // [n_stat][2*n_splits] candidates found per sub-list (> cand_cap: overflow)
+  int cand_cap;
 };
+
+// key order: score desc, then id asc (shared by every top-K stage)
+__device__ __forceinline__ unsigned long long topk_key(float v, int id) {
+  return (static_cast<unsigned long long>(f32_orderable(v)) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(id));
+}
+// logit of one (row, item): the single expression both top-K passes use, so they agree bit for bit
+__device__ __forceinline__ float logit_of(uint32_t raw, float scale, const float* bias, int col) {
+  if (bias != nullptr) return __fmaf_rn(__uint_as_float(raw), scale, __ldg(bias + col));
+  return __fmul_rn(__uint_as_float(raw), scale);  // explicit roundings: no contraction differences between call sites
+}
 
 template <int EPI_, int DT_, int KC_, int BN_, int NS_, bool STAT_ROWS_>
 struct SweepCfg {
@@ -136,71 +159,78 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
 
   if (warp == 0) {
     // ======================================================================= TMA producer
-    if (lane == 0) {
-      uint32_t it = 0, k = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++k) {
-        int stat_tile, split, t0, t1;
-        item_range(item, stat_tile, split, t0, t1);
-        mbar_wait(&bar->x_empty, (k & 1) ^ 1);
+    // The whole warp runs the (uniform) control flow; one elected lane issues the copies.
+    uint32_t it = 0, k = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++k) {
+      int stat_tile, split, t0, t1;
+      item_range(item, stat_tile, split, t0, t1);
+      mbar_wait(&bar->x_empty, (k & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&bar->x_full, C::X_BYTES);
 #pragma unroll
         for (int c = 0; c < C::KCS; ++c)
           tma_load_2d(x_smem + c * 128 * 128, &tm_stat, &bar->x_full, c * C::ELEMS_PER_CHUNK, stat_tile * 128);
-        for (int t = t0; t < t1; ++t, ++it) {
-          const uint32_t st = it % C::NS, ph = (it / C::NS) & 1;
-          mbar_wait(&bar->empty[st], ph ^ 1);
+      }
+      __syncwarp();
+      for (int t = t0; t < t1; ++t, ++it) {
+        const uint32_t st = it % C::NS, ph = (it / C::NS) & 1;
+        mbar_wait(&bar->empty[st], ph ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&bar->full[st], C::Y_BYTES);
 #pragma unroll
           for (int c = 0; c < C::KCS; ++c)
             tma_load_2d(y_smem + st * C::Y_BYTES + c * C::BN * 128, &tm_strm, &bar->full[st],
                         c * C::ELEMS_PER_CHUNK, t * C::BN);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ========================================================================= MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t fmt = (C::DT == DT_BF16) ? FMT_BF16 : FMT_TF32;
-      constexpr uint32_t idesc1 = make_idesc(fmt, 128, C::BN, 0, 0);
-      const uint32_t x_addr = smem_u32(x_smem), y_addr = smem_u32(y_smem);
-      uint32_t it = 0, k = 0;
-
-      auto issue_mma1 = [&](uint32_t tile_it) {
-        const uint32_t st = tile_it % C::NS, ph = (tile_it / C::NS) & 1;
-        const uint32_t buf = tile_it & 1, sph = (tile_it >> 1) & 1;
+    // Warp-converged loop (descriptor arithmetic stays in uniform registers); one elected lane issues
+    // the tcgen05.mma / commit instructions.
+    constexpr uint32_t fmt = (C::DT == DT_BF16) ? FMT_BF16 : FMT_TF32;
+    constexpr uint32_t idesc1 = make_idesc(fmt, 128, C::BN, 0, 0);
+    constexpr uint32_t dhi = smem_desc_hi(1024);
+    const uint32_t x_lo = smem_desc_lo(smem_u32(x_smem), 16), y_lo = smem_desc_lo(smem_u32(y_smem), 16);
+    uint32_t it = 0, k = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++k) {
+      int stat_tile, split, t0, t1;
+      item_range(item, stat_tile, split, t0, t1);
+      mbar_wait(&bar->x_full, k & 1);
+      for (int t = t0; t < t1; ++t, ++it) {
+        const uint32_t st = it % C::NS, ph = (it / C::NS) & 1;
+        const uint32_t buf = it & 1, sph = (it >> 1) & 1;
         mbar_wait(&bar->full[st], ph);
         mbar_wait(&bar->s_empty[buf], sph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * C::BN;
+        if (elect_one()) {
+          const uint32_t d_tmem = tmem_base + buf * C::BN;
+          const uint32_t ys_lo = y_lo + ((st * C::Y_BYTES) >> 4);
 #pragma unroll
-        for (int p = 0; p < C::NPAIR; ++p) {
-          int ac, bc;
-          if (C::DT == DT_BF16) { ac = p; bc = p; }
-          else {
-            const int c = p / 3, r = p % 3;  // small terms first: lo*hi, hi*lo, then hi*hi
-            ac = (r == 0) ? C::KC + c : c;
-            bc = (r == 1) ? C::KC + c : c;
-          }
-          const uint32_t ab = x_addr + ac * 128 * 128;
-          const uint32_t bb = y_addr + st * C::Y_BYTES + bc * C::BN * 128;
+          for (int p = 0; p < C::NPAIR; ++p) {
+            int ac, bc;
+            if (C::DT == DT_BF16) { ac = p; bc = p; }
+            else {
+              const int c = p / 3, r = p % 3;  // small terms first: lo*hi, hi*lo, then hi*hi
+              ac = (r == 0) ? C::KC + c : c;
+              bc = (r == 1) ? C::KC + c : c;
+            }
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t ad = make_smem_desc(ab + kk * 32, 16, 1024);
-            const uint64_t bd = make_smem_desc(bb + kk * 32, 16, 1024);
-            if (C::DT == DT_BF16) mma_f16_ss(d_tmem, ad, bd, idesc1, (p | kk) != 0);
-            else mma_tf32_ss(d_tmem, ad, bd, idesc1, (p | kk) != 0);
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t ad = smem_desc(dhi, x_lo + ((ac * 128 * 128 + kk * 32) >> 4));
+              const uint64_t bd = smem_desc(dhi, ys_lo + ((bc * C::BN * 128 + kk * 32) >> 4));
+              if (C::DT == DT_BF16) mma_f16_ss(d_tmem, ad, bd, idesc1, (p | kk) != 0);
+              else mma_tf32_ss(d_tmem, ad, bd, idesc1, (p | kk) != 0);
+            }
           }
+          tc_commit(&bar->s_full[buf]);
+          tc_commit(&bar->empty[st]);
         }
-        tc_commit(&bar->s_full[buf]);
-        tc_commit(&bar->empty[st]);
-      };
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++k) {
-        int stat_tile, split, t0, t1;
-        item_range(item, stat_tile, split, t0, t1);
-        mbar_wait(&bar->x_full, k & 1);
-        for (int t = t0; t < t1; ++t, ++it) issue_mma1(it);
-        tc_commit(&bar->x_empty);
+        __syncwarp();
       }
+      if (elect_one()) tc_commit(&bar->x_empty);
+      __syncwarp();
     }
   } else {
     // =========================================================================== epilogue
@@ -224,7 +254,13 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
       float m2 = -INFINITY, l = 0.f, ll = 0.f;     // LSE
       int lab = -1;                                 // LSE
       int seen_cur = 0, seen_end = 0, next_seen = 0x7fffffff;   // TOPK: cursor into the row's seen list
+      int next2_seen = 0x7fffffff;                              //       (one entry prefetched: no load latency on advance)
+      int n_cand = 0;                                           // CAND: entries in this thread's sub-list
+      unsigned long long* cand_list = nullptr;
+      unsigned int flag_next = 0;                               // CAND: flag of the next tile this warpgroup owns
 
+      float tau = INFINITY;                         // CAND: rows beyond n_stat never hit
+      if (C::EPI == EPI_CAND && srow_ok) tau = __ldg(a.tau + srow);
       if (C::EPI == EPI_LSE) lab = srow_ok ? a.labels[srow] : -1;
       if (C::EPI == EPI_TOPK) {
         if (a.seen_crow != nullptr && srow_ok) {
@@ -238,8 +274,22 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
           }
           seen_cur = lo;
           next_seen = (seen_cur < seen_end) ? a.seen_col[seen_cur] : 0x7fffffff;
+          next2_seen = (seen_cur + 1 < seen_end) ? a.seen_col[seen_cur + 1] : 0x7fffffff;
         }
       }
+      const unsigned char* flag_row = nullptr;
+      if (C::EPI == EPI_CAND) {
+        cand_list = a.cand + (static_cast<long long>(srow) * (2 * a.n_splits) + split * 2 + wg) * a.cand_cap;
+        flag_row = a.tile_flag + static_cast<long long>(stat_tile * 4 + q) * a.n_strm_tiles;
+        const int tf = t0 + ((wg - static_cast<int>(it & 1)) & 1);  // first tile of this item with parity wg
+        if (tf < t1) flag_next = __ldg(flag_row + tf);
+      }
+      // advance the seen cursor by one entry; the entry after next is already in a register
+      auto seen_advance = [&]() {
+        ++seen_cur;
+        next_seen = next2_seen;
+        next2_seen = (seen_cur + 1 < seen_end) ? __ldg(a.seen_col + seen_cur + 1) : 0x7fffffff;
+      };
 
       for (int t = t0; t < t1; ++t, ++it) {
         if ((it & 1) != static_cast<uint32_t>(wg)) continue;
@@ -247,18 +297,20 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
         const int col_base = t * C::BN;                       // first streamed row of the tile
         const int n_valid = min(C::BN, a.n_strm - col_base);  // valid columns in this tile
         const bool full_tile = (n_valid == C::BN);
+        bool tile_live = true;
+        if (C::EPI == EPI_CAND) {  // warp-uniform: can any of this warp's 32 rows reach its threshold in this tile?
+          tile_live = flag_next != 0;
+          if (t + 2 < t1) flag_next = __ldg(flag_row + t + 2);  // consumed two tiles from now
+        }
         mbar_wait(&bar->s_full[wg], sph);
         tc_fence_after();
-
-        float tmax = -INFINITY;   // TOPK: masked max of this tile for this row
-        bool tile_quick = false;
-        if (C::EPI == EPI_TOPK) {
-          while (next_seen < col_base) {  // skip seen ids that fell into the other warpgroup's tiles
-            ++seen_cur;
-            next_seen = (seen_cur < seen_end) ? __ldg(a.seen_col + seen_cur) : 0x7fffffff;
-          }
-          tile_quick = plain && full_tile && (next_seen >= col_base + C::BN);
+        if (C::EPI == EPI_CAND && !tile_live) {
+          tc_fence_before();
+          mbar_arrive(&bar->s_empty[wg]);
+          continue;
         }
+        float tmax = -INFINITY;   // TOPK: max of this tile for this row
+        const bool tile_quick = plain && full_tile;   // warp-uniform
         uint32_t raw[2][32];
         tmem_ld32(t_lane, raw[0]);
 #pragma unroll
@@ -327,26 +379,38 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
           } else if (C::EPI == EPI_TOPK) {
             if (tile_quick) {
               tmax = fmaxf(tmax, max32(v));  // raw scores; scaled once per tile (scale > 0)
-            } else if (nv > 0) {
-              float x[32];
-#pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                float sc = __uint_as_float(v[c]) * a.scale;
-                if (a.bias != nullptr && c < nv) sc += __ldg(a.bias + col_base + c0 + c);
-                x[c] = (c < nv) ? sc : -INFINITY;
-              }
-              while (next_seen < col_base + c0 + 32) {  // seen ids inside this chunk (ascending)
-                const int rel = next_seen - (col_base + c0);
-#pragma unroll
-                for (int c = 0; c < 32; ++c)
-                  if (c == rel) x[c] = -INFINITY;
-                ++seen_cur;
-                next_seen = (seen_cur < seen_end) ? __ldg(a.seen_col + seen_cur) : 0x7fffffff;
-              }
+            } else if (nv > 0) {  // bias and/or the last, partial tile
               float cm = -INFINITY;
 #pragma unroll
-              for (int c = 0; c < 32; ++c) cm = fmaxf(cm, x[c]);
+              for (int c = 0; c < 32; ++c)
+                if (c < nv) cm = fmaxf(cm, logit_of(v[c], a.scale, a.bias, col_base + c0 + c));
               tmax = fmaxf(tmax, cm);
+            }
+          } else if (C::EPI == EPI_CAND) {
+            // quick reject on the chunk maximum (exact: scale > 0, so max commutes with the scaling)
+            if (tile_quick) {
+              if (__fmul_rn(max32(v), a.scale) >= tau) {  // rare: straight-line predicated appends
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                  const float sc = __fmul_rn(__uint_as_float(v[c]), a.scale);
+                  if (sc >= tau) {
+                    if (n_cand < a.cand_cap) cand_list[n_cand] = topk_key(sc, col_base + c0 + c);
+                    ++n_cand;
+                  }
+                }
+              }
+            } else if (nv > 0) {
+#pragma unroll 4
+              for (int c = 0; c < 32; ++c) {
+                if (c < nv) {
+                  const int col = col_base + c0 + c;
+                  const float sc = logit_of(v[c], a.scale, a.bias, col);
+                  if (sc >= tau) {
+                    if (n_cand < a.cand_cap) cand_list[n_cand] = topk_key(sc, col);
+                    ++n_cand;
+                  }
+                }
+              }
             }
           }
         }  // chunks
@@ -354,11 +418,19 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
         // release the S buffer (all tcgen05.ld of this thread have completed)
         tc_fence_before();
         mbar_arrive(&bar->s_empty[wg]);
-        if (C::EPI == EPI_TOPK && srow_ok)
-          a.tile_max[static_cast<long long>(srow) * a.n_strm_tiles + t] = tile_quick ? tmax * a.scale : tmax;
+        if (C::EPI == EPI_TOPK) {
+          while (next_seen < col_base) seen_advance();  // seen ids that fell into the other warpgroup's tiles
+          const bool dirty = next_seen < col_base + C::BN;
+          while (next_seen < col_base + C::BN) seen_advance();
+          float out = tile_quick ? __fmul_rn(tmax, a.scale) : tmax;
+          if (dirty) out = __int_as_float(0x7fc00000);  // NaN
+          if (srow_ok) a.tile_max[static_cast<long long>(srow) * a.n_strm_tiles + t] = out;
+        }
       }  // tiles
 
       // ---- per-item outputs
+      if (C::EPI == EPI_CAND && srow_ok)
+        a.cand_cnt[static_cast<long long>(srow) * (2 * a.n_splits) + split * 2 + wg] = n_cand;
       if (C::EPI == EPI_LSE) {
         // warpgroup 1 hands its partial to warpgroup 0, which merges and writes one slot per row
         if (wg == 1) { bar->xchg[0][r] = m2; bar->xchg[1][r] = l; bar->xchg[2][r] = ll; }

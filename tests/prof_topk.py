@@ -1,0 +1,23 @@
+"""Probe: time the top-K pipeline (CUDA events) at bench sizes; RB_DBG selects skeleton probes."""
+import sys
+from pathlib import Path
+import torch
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from recboard_b200 import ops, synth  # noqa: E402
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+M, D, K = 4096, 128, 50
+dev = torch.device("cuda", 0)
+g = torch.Generator(device=dev).manual_seed(1)
+U = synth.embeddings(M, D, g, dev, torch.bfloat16, gain=1.5)
+W = synth.embeddings(N, D, g, dev, torch.bfloat16, gain=1.5)
+crow, col = synth.seen_csr(M, N, g, dev)
+for _ in range(3):
+    ops.topk_eval(U, W, K, crow, col)
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(10):
+    ops.topk_eval(U, W, K, crow, col)
+b.record(); torch.cuda.synchronize()
+print("topk_eval ms", a.elapsed_time(b) / 10)
