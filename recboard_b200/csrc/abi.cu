@@ -507,9 +507,10 @@ extern "C" int rb_ce_bwd(const void* U, const void* W, const float* bias, float 
 //   2. tilemax_select:  tau[row] = K-th largest tile maximum  (>= K unseen items score >= tau, so every
 //                       top-K member does too) + the tile list the fallback uses
 //   3. tile_flag:       which (32-row group, tile) pairs can hold a candidate
-//   4. sweep<EPI_CAND>: recompute the scores, append every item with score >= tau to the (row, split,
-//                       warpgroup) sub-list (about K per row in total); flagged-off tiles are skipped
-//   5. topk_from_cand:  gather the sub-lists, drop seen items, sort, keep K.
+//   4. sweep<EPI_CAND>: recompute the scores, append every aligned group of 8 items whose maximum reaches tau
+//                       to the (row, split, warpgroup) sub-list (about K groups per row in total);
+//                       flagged-off tiles are skipped
+//   5. topk_from_groups: exact fp32 re-scoring of the hit groups, drop seen items, sort, keep K.
 //   6. rows with an overflowed sub-list (massive ties / tiny catalogs): exact SIMT re-scoring of the
 //      selected tiles (topk_refine).
 static int topk_selcap(int K) { return ((2 * K + 64 + 31) / 32) * 32; }
@@ -555,7 +556,7 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
   int* cand_cnt = b.take<int>(static_cast<size_t>(B) * n_sub);
   int* overflow = b.take<int>(B);
   unsigned char* flag = b.take<unsigned char>(static_cast<size_t>(p.n_stat_tiles) * 4 * p.n_strm_tiles);
-  unsigned long long* cand = b.take<unsigned long long>(static_cast<size_t>(B) * n_sub * candcap);
+  int* cand = b.take<int>(static_cast<size_t>(B) * n_sub * candcap);
   if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
   if (seen_crow) {
     const long long n = std::max<long long>(B + 1, nnz);
@@ -579,16 +580,19 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
   RB_LAUNCH_CHECK("tile_flag_kernel");
   if (int r = launch_sweep<EPI_CAND, true>(mode, kc_for(d, mode), ts, ty, a, p.grid, st)) return r;
   const int id_add = static_cast<int>(id_base);
-  if (K <= 128) topk_from_cand_kernel<4><<<grid_w, 128, 0, st>>>(cand, cand_cnt, n_sub, candcap, crow32, col32, B, K, id_add, top_vals, top_ids, overflow);
-  else topk_from_cand_kernel<8><<<grid_w, 128, 0, st>>>(cand, cand_cnt, n_sub, candcap, crow32, col32, B, K, id_add, top_vals, top_ids, overflow);
-  RB_LAUNCH_CHECK("topk_from_cand_kernel");
   const int grid_r = static_cast<int>((B + 3) / 4);
   if (dtype == RB_DTYPE_BF16) {
     const __nv_bfloat16* Ub = static_cast<const __nv_bfloat16*>(U); const __nv_bfloat16* Wb = static_cast<const __nv_bfloat16*>(W);
+    if (K <= 128) topk_from_groups_kernel<__nv_bfloat16, 4><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, cand, cand_cnt, n_sub, candcap, crow32, col32, K, id_add, top_vals, top_ids, overflow);
+    else topk_from_groups_kernel<__nv_bfloat16, 8><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, cand, cand_cnt, n_sub, candcap, crow32, col32, K, id_add, top_vals, top_ids, overflow);
+    RB_LAUNCH_CHECK("topk_from_groups_kernel");
     if (K <= 128) topk_refine_kernel<__nv_bfloat16, 4><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, crow32, col32, sel, selcnt, selcap, K, id_add, top_vals, top_ids, overflow);
     else topk_refine_kernel<__nv_bfloat16, 8><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, crow32, col32, sel, selcnt, selcap, K, id_add, top_vals, top_ids, overflow);
   } else {
     const float* Uf = static_cast<const float*>(U); const float* Wf = static_cast<const float*>(W);
+    if (K <= 128) topk_from_groups_kernel<float, 4><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, cand, cand_cnt, n_sub, candcap, crow32, col32, K, id_add, top_vals, top_ids, overflow);
+    else topk_from_groups_kernel<float, 8><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, cand, cand_cnt, n_sub, candcap, crow32, col32, K, id_add, top_vals, top_ids, overflow);
+    RB_LAUNCH_CHECK("topk_from_groups_kernel");
     if (K <= 128) topk_refine_kernel<float, 4><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, crow32, col32, sel, selcnt, selcap, K, id_add, top_vals, top_ids, overflow);
     else topk_refine_kernel<float, 8><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, crow32, col32, sel, selcnt, selcap, K, id_add, top_vals, top_ids, overflow);
   }
@@ -637,7 +641,7 @@ extern "C" size_t rb_workspace_bytes(int op, int64_t M, int64_t N, int d, int K,
       return need + staged_bytes(M, d, mode) + staged_bytes(N, d, mode) + (M + 1 + std::max<int64_t>(nnz, 1)) * 4 +
              static_cast<size_t>(M) * (static_cast<size_t>(p.n_strm_tiles) + topk_selcap(K) + 4) * 4 +
              static_cast<size_t>(p.n_stat_tiles) * 4 * p.n_strm_tiles +
-             static_cast<size_t>(M) * 2 * p.n_splits * (topk_candcap(K, 2 * p.n_splits) * 8 + 4) + 4096;
+             static_cast<size_t>(M) * 2 * p.n_splits * (topk_candcap(K, 2 * p.n_splits) * 4 + 4) + 4096;
     }
     default: return 0;
   }

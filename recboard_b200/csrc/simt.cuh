@@ -453,31 +453,68 @@ __global__ void tile_flag_kernel(const float* __restrict__ T, const float* __res
   flag[g * n_tiles + t] = any ? 1 : 0;
 }
 
-// ---- top-K pass 3: gather the row's candidate sub-lists (the items with score >= tau found by the
-// EPI_CAND sweep), drop seen items (UniSRec/main.py:413), keep the K best by (score desc, id asc).
-// Rows with an overflowed sub-list are flagged for the exact fallback below.  One warp per row.
-template <int E>
+// exact fp32 logit of one (query, item) pair: a sequential FMA chain over k = 0..d-1 (the same order in
+// every top-K finishing path, so their values agree bit for bit), then scale and bias with explicit roundings
+template <typename TW>
+__device__ __forceinline__ float exact_logit(const float* __restrict__ u, const TW* __restrict__ w, int d, float scale,
+                                             const float* __restrict__ bias, int item) {
+  float acc = 0.f;
+  for (int k = 0; k < d; k += 8) {  // d % 8 == 0
+    const float4 ua = *reinterpret_cast<const float4*>(u + k);
+    const float4 ub = *reinterpret_cast<const float4*>(u + k + 4);
+    float x[8];
+    if constexpr (sizeof(TW) == 2) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(w + k));
+      x[0] = __uint_as_float(raw.x << 16); x[1] = __uint_as_float(raw.x & 0xFFFF0000u);
+      x[2] = __uint_as_float(raw.y << 16); x[3] = __uint_as_float(raw.y & 0xFFFF0000u);
+      x[4] = __uint_as_float(raw.z << 16); x[5] = __uint_as_float(raw.z & 0xFFFF0000u);
+      x[6] = __uint_as_float(raw.w << 16); x[7] = __uint_as_float(raw.w & 0xFFFF0000u);
+    } else {
+      const float4 r0 = __ldg(reinterpret_cast<const float4*>(w + k));
+      const float4 r1 = __ldg(reinterpret_cast<const float4*>(w + k + 4));
+      x[0] = r0.x; x[1] = r0.y; x[2] = r0.z; x[3] = r0.w; x[4] = r1.x; x[5] = r1.y; x[6] = r1.z; x[7] = r1.w;
+    }
+    acc = __fmaf_rn(ua.x, x[0], acc); acc = __fmaf_rn(ua.y, x[1], acc);
+    acc = __fmaf_rn(ua.z, x[2], acc); acc = __fmaf_rn(ua.w, x[3], acc);
+    acc = __fmaf_rn(ub.x, x[4], acc); acc = __fmaf_rn(ub.y, x[5], acc);
+    acc = __fmaf_rn(ub.z, x[6], acc); acc = __fmaf_rn(ub.w, x[7], acc);
+  }
+  if (bias != nullptr) return __fmaf_rn(acc, scale, __ldg(bias + item));
+  return __fmul_rn(acc, scale);
+}
+
+// ---- top-K pass 3: re-score the row's hit groups (aligned groups of 8 items whose maximum reached tau in
+// the EPI_CAND sweep) exactly, drop seen items (UniSRec/main.py:413), keep the K best by (score desc,
+// id asc).  Rows with an overflowed sub-list are flagged for the fallback below.  One warp per row; a
+// lane scores one item, four groups per step.
+template <typename TW, int E>
 __global__ void __launch_bounds__(128)
-topk_from_cand_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ cand_cnt, int n_sub, int cap,
-                      const int* __restrict__ seen_crow, const int* __restrict__ seen_col,
-                      long long n_rows, int K, int id_add, float* __restrict__ out_vals, int* __restrict__ out_ids,
-                      int* __restrict__ overflow) {
+topk_from_groups_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const float* __restrict__ bias, float scale,
+                        int d, long long n_rows, int n_items, const int* __restrict__ cand,
+                        const int* __restrict__ cand_cnt, int n_sub, int cap, const int* __restrict__ seen_crow,
+                        const int* __restrict__ seen_col, int K, int id_add, float* __restrict__ out_vals,
+                        int* __restrict__ out_ids, int* __restrict__ overflow) {
+  __shared__ __align__(16) float u_s[4][256];
   __shared__ unsigned long long stage_s[4][256];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 4 + wib;
   if (row >= n_rows) return;
-  unsigned long long* stage = stage_s[wib];
   const int* cnts = cand_cnt + row * n_sub;
   bool ovf = false;
   for (int s = lane; s < n_sub; s += 32) ovf |= cnts[s] > cap;
   ovf = __any_sync(0xffffffffu, ovf);
   if (lane == 0) overflow[row] = ovf ? 1 : 0;
   if (ovf) return;
+  float* u = u_s[wib];
+  unsigned long long* stage = stage_s[wib];
+  for (int k = lane; k < 256; k += 32) u[k] = (k < d) ? static_cast<float>(U[row * d + k]) : 0.f;
+  __syncwarp();
   int s_lo = 0, s_hi = 0;
   if (seen_crow != nullptr) { s_lo = seen_crow[row]; s_hi = seen_crow[row + 1]; }
   unsigned long long best[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) best[e] = 0ull;
+  unsigned long long kth = 0ull;
   int ns = 0;
   const uint32_t lt = (1u << lane) - 1u;
   auto flush = [&]() {
@@ -492,18 +529,20 @@ topk_from_cand_kernel(const unsigned long long* __restrict__ cand, const int* __
       warp_bitonic_sort_desc<unsigned long long, E>(cur);
       warp_topk_absorb<unsigned long long, E>(best, cur);
     }
+    kth = warp_blocked_get<unsigned long long, E>(best, K - 1);
     ns = 0;
     __syncwarp();
   };
   for (int s = 0; s < n_sub; ++s) {
     const int cnt = cnts[s];
-    const unsigned long long* c = cand + (row * n_sub + s) * cap;
-    for (int base = 0; base < cnt; base += 32) {
-      const int i = base + lane;
-      unsigned long long key = (i < cnt) ? c[i] : 0ull;
-      bool pass = key != 0ull;
-      if (pass && s_hi > s_lo) {
-        const int item = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFu));
+    const int* gl = cand + (row * n_sub + s) * cap;
+    for (int base = 0; base < cnt; base += 4) {
+      const int gi = base + (lane >> 3);
+      const int item = (gi < cnt) ? (__ldg(gl + gi) << 3) + (lane & 7) : n_items;
+      unsigned long long key = 0ull;
+      if (item < n_items) key = topk_key(exact_logit<TW>(u, W + static_cast<long long>(item) * d, d, scale, bias, item), item);
+      bool pass = key > kth;
+      if (pass && s_hi > s_lo) {  // seen items never rank
         int lo = s_lo, hi = s_hi;
         while (lo < hi) {
           const int mid = (lo + hi) >> 1;
@@ -608,17 +647,17 @@ topk_refine_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const flo
           const float4 r1 = __ldg(reinterpret_cast<const float4*>(wrow[q] + k + 4));
           w[0] = r0.x; w[1] = r0.y; w[2] = r0.z; w[3] = r0.w; w[4] = r1.x; w[5] = r1.y; w[6] = r1.z; w[7] = r1.w;
         }
-        acc[q] = fmaf(ua.x, w[0], acc[q]); acc[q] = fmaf(ua.y, w[1], acc[q]);
-        acc[q] = fmaf(ua.z, w[2], acc[q]); acc[q] = fmaf(ua.w, w[3], acc[q]);
-        acc[q] = fmaf(ub.x, w[4], acc[q]); acc[q] = fmaf(ub.y, w[5], acc[q]);
-        acc[q] = fmaf(ub.z, w[6], acc[q]); acc[q] = fmaf(ub.w, w[7], acc[q]);
+        acc[q] = __fmaf_rn(ua.x, w[0], acc[q]); acc[q] = __fmaf_rn(ua.y, w[1], acc[q]);  // same chain as exact_logit
+        acc[q] = __fmaf_rn(ua.z, w[2], acc[q]); acc[q] = __fmaf_rn(ua.w, w[3], acc[q]);
+        acc[q] = __fmaf_rn(ub.x, w[4], acc[q]); acc[q] = __fmaf_rn(ub.y, w[5], acc[q]);
+        acc[q] = __fmaf_rn(ub.z, w[6], acc[q]); acc[q] = __fmaf_rn(ub.w, w[7], acc[q]);
       }
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const bool valid = item[q] < n_items;
-      float sc = acc[q] * scale;
-      if (bias != nullptr && valid) sc += __ldg(bias + item[q]);
+      float sc = __fmul_rn(acc[q], scale);
+      if (bias != nullptr && valid) sc = __fmaf_rn(acc[q], scale, __ldg(bias + item[q]));
       const unsigned long long key = valid ? topk_key(sc, item[q]) : 0ull;
       bool pass = key > kth;
       if (pass && s_hi > s_lo) {  // seen items never rank (UniSRec/main.py:413)

@@ -10,10 +10,12 @@
 //              ("dirty": it never supports the threshold but is always scanned by pass 2), so no
 //              per-item masking happens here.  simt.cuh turns the clean tile maxima into a per-row
 //              admission threshold tau = K-th largest (>= K unseen items reach it)
-//   EPI_CAND   pass 2: the same sweep again, emitting every (row, item) with score >= tau[row] (about K
-//              per row) into the (row, split, warpgroup) candidate sub-list -- a register counter and a
-//              plain store, no global-memory latency in the epilogue; tiles no row of a warp can hit
-//              (flag table) are skipped without touching TMEM.  Seen items are dropped by the finish kernel.
+//   EPI_CAND   pass 2: the same sweep again, emitting every (row, aligned group of 8 items) whose maximum
+//              reaches tau[row] (about K groups per row) into the (row, split, warpgroup) sub-list -- a
+//              register counter and a plain store of a group index; the hit path is a dozen
+//              instructions (a rarely executed path must stay tiny: it runs from a cold I-cache).  Tiles
+//              no row of a warp can hit (flag table) are skipped without touching TMEM.  The finish
+//              kernel re-scores the groups exactly, drops seen items and sorts.
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
 // warps 2..9 = two epilogue warpgroups (thread <-> TMEM lane <-> stationary row); warpgroup g owns
@@ -55,8 +57,8 @@ struct SweepArgs {
   // EPI_CAND (rows stationary): pass 2 of the top-K
   const float* tau;                 // [n_stat] admission threshold of the row (score >= tau is a candidate)
   const unsigned char* tile_flag;   // [n_stat_tiles*4][n_strm_tiles] != 0: some row of that 32-row group can hit
-  unsigned long long* cand;         // [n_stat][2*n_splits][cand_cap] candidate keys, one sub-list per (split, warpgroup)
-  int* cand_cnt;                    // [n_stat][2*n_splits] candidates found per sub-list (> cand_cap: overflow)
+  int* cand;                        // [n_stat][2*n_splits][cand_cap] hit groups (item id >> 3), one sub-list per (split, warpgroup)
+  int* cand_cnt;                    // [n_stat][2*n_splits] groups found per sub-list (> cand_cap: overflow)
   int cand_cap;
 };
 
@@ -109,6 +111,16 @@ __device__ __forceinline__ float max32(const uint32_t (&r)[32]) {
     m[i] = fmaxf(fmaxf(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])),
                  fmaxf(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
   return fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+}
+
+// maxima of the four aligned groups of 8 values of a 32-value chunk
+__device__ __forceinline__ void group_max8(const uint32_t (&r)[32], float (&m)[4]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float a = fmax3(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1]), __uint_as_float(r[8 * g + 2]));
+    const float b = fmax3(__uint_as_float(r[8 * g + 3]), __uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
+    m[g] = fmaxf(fmax3(a, b, __uint_as_float(r[8 * g + 6])), __uint_as_float(r[8 * g + 7]));
+  }
 }
 
 // named barrier over the 256 epilogue threads (id 1; id 0 is __syncthreads)
@@ -256,7 +268,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
       int seen_cur = 0, seen_end = 0, next_seen = 0x7fffffff;   // TOPK: cursor into the row's seen list
       int next2_seen = 0x7fffffff;                              //       (one entry prefetched: no load latency on advance)
       int n_cand = 0;                                           // CAND: entries in this thread's sub-list
-      unsigned long long* cand_list = nullptr;
+      int* cand_list = nullptr;
       unsigned int flag_next = 0;                               // CAND: flag of the next tile this warpgroup owns
 
       float tau = INFINITY;                         // CAND: rows beyond n_stat never hit
@@ -388,27 +400,26 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
             }
           } else if (C::EPI == EPI_CAND) {
             // quick reject on the chunk maximum (exact: scale > 0, so max commutes with the scaling)
+            float m[4];
             if (tile_quick) {
-              if (__fmul_rn(max32(v), a.scale) >= tau) {  // rare: straight-line predicated appends
+              group_max8(v, m);
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                  const float sc = __fmul_rn(__uint_as_float(v[c]), a.scale);
-                  if (sc >= tau) {
-                    if (n_cand < a.cand_cap) cand_list[n_cand] = topk_key(sc, col_base + c0 + c);
-                    ++n_cand;
-                  }
-                }
+              for (int g = 0; g < 4; ++g) m[g] = __fmul_rn(m[g], a.scale);  // exact: scale > 0 commutes with max
+            } else {  // bias and/or the last, partial tile
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                m[g] = -INFINITY;
+#pragma unroll
+                for (int c = 8 * g; c < 8 * g + 8; ++c)
+                  if (c < nv) m[g] = fmaxf(m[g], logit_of(v[c], a.scale, a.bias, col_base + c0 + c));
               }
-            } else if (nv > 0) {
-#pragma unroll 4
-              for (int c = 0; c < 32; ++c) {
-                if (c < nv) {
-                  const int col = col_base + c0 + c;
-                  const float sc = logit_of(v[c], a.scale, a.bias, col);
-                  if (sc >= tau) {
-                    if (n_cand < a.cand_cap) cand_list[n_cand] = topk_key(sc, col);
-                    ++n_cand;
-                  }
+            }
+            if (fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])) >= tau) {  // rare, and tiny on purpose
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                if (m[g] >= tau) {
+                  if (n_cand < a.cand_cap) cand_list[n_cand] = (col_base + c0 + 8 * g) >> 3;
+                  ++n_cand;
                 }
               }
             }
