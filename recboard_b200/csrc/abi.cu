@@ -349,7 +349,7 @@ static int ce_fwd_pair(const DevInfo& dv, const void* U, const void* W, const fl
   if (int r = make_tmap(&ty, W, true, N, d, 128)) return r;
   PairArgs a{};
   a.n_stat = (int)M; a.n_strm = (int)N; a.n_pair_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
-  a.n_splits = p.n_splits; a.d = d; a.stat_pad = (int)stat_pad; a.scale = scale; a.bias2 = bias2;
+  a.n_splits = p.n_splits; a.d = d; a.stat_pad = (int)stat_pad; a.scale = scale; a.aux = bias2;
   a.part_m2 = pm2; a.part_l = pl; a.acc_out = pacc;
   if (int r = launch_pair<PASS_FWD>(kc_for(d, RB_MODE_BF16), bias != nullptr, ts, ty, a, p.grid, st)) return r;
   const int grid = (int)((M * 32 + 255) / 256);
@@ -444,7 +444,7 @@ static int ce_bwd_dw_pair(const DevInfo& dv, const void* U, const void* W, const
   if (int r = make_tmap(&ty, U, true, M, d, 128)) return r;
   PairArgs a{};
   a.n_stat = (int)N; a.n_strm = (int)M; a.n_pair_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
-  a.n_splits = p.n_splits; a.d = d; a.stat_pad = (int)n_pad; a.scale = scale; a.bias2 = bias2; a.lse2 = lse2;
+  a.n_splits = p.n_splits; a.d = d; a.stat_pad = (int)n_pad; a.scale = scale; a.bias2_stat = bias2; a.aux = lse2;
   a.gscale = grad_scale * scale; a.rscale = grad_scale; a.gscale_dev = grad_scale_dev; a.acc_out = part; a.rowsum_out = rs_part;
   if (int r = launch_pair<PASS_DW>(kc_for(d, RB_MODE_BF16), bias != nullptr, ts, ty, a, p.grid, st)) return r;
   if (p.n_splits > 1) {
