@@ -43,6 +43,13 @@ enum { RB_E_ARG = -1, RB_E_ALIGN = -2, RB_E_UNSUPPORTED = -3, RB_E_WORKSPACE = -
 int rb_gather_rows(const void* table, const int64_t* idx, void* out, int64_t n_idx, int64_t n_rows,
                    int d, int dtype, rb_stream_t stream);
 
+/* out[i,:] = x[i,:] / max(||x[i,:]||_2, eps); inv_norm[i] (nullable) = 1/max(norm, eps).  Replaces
+ * `F.normalize(self.Item.embeddings.weight[NUM_PADS:], dim=-1)` and the user-side normalisation
+ * (HSTU/main.py:180-184): one HBM read + one write, output optionally cast to bf16 (the operand copy of
+ * the cosine scoring sweep).  d % 8 == 0, d <= 1024; in/out may alias when the dtypes match. */
+int rb_normalize_rows(const void* x, void* out, float* inv_norm, int64_t n_rows, int d, int in_dtype,
+                      int out_dtype, float eps, rb_stream_t stream);
+
 /* grad_table[idx[i],:] += grad_out[i,:], row `padding_idx` untouched (pass -1 for none).
  * Deterministic (stable radix sort by row + in-order segment sums).  Replaces the autograd of the
  * gather above = ATen embedding_dense_backward, triggered by `loss.backward()` (SASRec/main.py:249). */

@@ -77,6 +77,11 @@ def ce_loss(U, W, labels, bias=None, scale: float = 1.0) -> torch.Tensor:
     return F.cross_entropy(score_dense(U, W, bias, scale), labels, reduction="mean")
 
 
+def normalize_rows(x, eps: float = 1e-12):
+    """``F.normalize(x, dim=-1)`` -- the table / user normalisation of HSTU/main.py:180-184."""
+    return torch.nn.functional.normalize(x.float(), dim=-1, eps=eps)
+
+
 def ce_fwd_bwd(U, W, labels, bias=None, scale: float = 1.0, grad_out: float = 1.0):
     """Loss and its gradients w.r.t. U, W (and bias) through autograd -- exactly what
     ``loss.backward()`` (SASRec/main.py:249) produces for the lines :217-219."""

@@ -19,7 +19,6 @@ from __future__ import annotations
 from typing import Dict, Optional, Tuple
 
 import torch
-import torch.nn.functional as F
 
 from . import ops
 
@@ -107,16 +106,32 @@ class BERT4RecFused(FusedFullCatalogMixin):
 
 
 class HSTUFused(FusedFullCatalogMixin):
-    """HSTU full ranking: cosine scores, both sides already L2-normalised by ``encode``
-    (HSTU/main.py:180-184,204-209).  Its ``fit`` is sampled softmax (not full-catalog) and is left
-    to the reference implementation."""
+    """HSTU full ranking: cosine scores of L2-normalised queries and items (HSTU/main.py:180-184,
+    204-209).  The reference re-normalises the whole (N,d) table inside ``encode`` for every batch;
+    here ``reset_ranking_buffers`` builds the normalised operand copy once per evaluation sweep
+    (``ops.normalize_rows``, one HBM pass, optionally bf16) and ``_eval_operands`` reuses it.  A model
+    that wants to skip the redundant per-batch table pass as well overrides ``encode_users``.
+    Its ``fit`` is sampled softmax (not full-catalog) and is left to the reference implementation."""
 
     def fit(self, data):  # keep the reference's sampled-softmax fit
         return super(FusedFullCatalogMixin, self).fit(data)
 
+    def reset_ranking_buffers(self):
+        sup = super()
+        if hasattr(sup, "reset_ranking_buffers"):
+            sup.reset_ranking_buffers()
+        out_dtype = torch.bfloat16 if self.fused_precision == "bf16" else None
+        self._fused_item = ops.normalize_rows(self.Item.embeddings.weight[self.NUM_PADS:], out_dtype=out_dtype)
+
+    def encode_users(self, data) -> torch.Tensor:
+        """(B, S, d) normalised user states; default = the reference's ``encode`` (HSTU/main.py:164-184)."""
+        return self.encode(data)[0]
+
     def _eval_operands(self, data):
-        userEmbds, itemEmbds = self.encode(data)
-        return userEmbds[:, -1, :], itemEmbds, None, 1.0, 0
+        if getattr(self, "_fused_item", None) is None or self.training:
+            userEmbds, itemEmbds = self.encode(data)
+            return userEmbds[:, -1, :], itemEmbds, None, 1.0, 0
+        return self.encode_users(data)[:, -1, :], self._fused_item, None, 1.0, 0
 
 
 class GenRecFused(FusedFullCatalogMixin):
@@ -141,7 +156,7 @@ class GenRecFused(FusedFullCatalogMixin):
         return U, self._fused_item, None, 1.0, 0
 
 
-def normalized_table(weight: torch.Tensor, num_pads: int = 1) -> torch.Tensor:
-    """``F.normalize(weight[NUM_PADS:], dim=-1)`` (HSTU/main.py:182-184) -- helper for callers that
-    cache the normalised table across an evaluation sweep instead of recomputing it per batch."""
-    return F.normalize(weight[num_pads:], dim=-1)
+def normalized_table(weight: torch.Tensor, num_pads: int = 1, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """``F.normalize(weight[NUM_PADS:], dim=-1)`` (HSTU/main.py:182-184) through ``rb_normalize_rows`` --
+    for callers that cache the normalised table across an evaluation sweep."""
+    return ops.normalize_rows(weight[num_pads:], out_dtype=out_dtype)

@@ -11,6 +11,7 @@
 #include "sweep.cuh"
 #include "pair.cuh"
 #include "simt.cuh"
+#include "f32grad.cuh"
 
 using namespace rb;
 
@@ -170,10 +171,23 @@ static int launch_sweep_t(const CUtensorMap& ts, const CUtensorMap& ty, const Sw
   return 0;
 }
 
+// Stationary tiles per CTA: two (256 rows) whenever the operands fit (bf16, d <= 128) and there is a
+// second tile to fill -- halves the L2->SM traffic of a sweep (see sweep.cuh).
+static int sweep_xt(int mode, int d, long long n_stat) {
+  return (mode == RB_MODE_BF16 && d <= 128 && n_stat > 128) ? 2 : 1;
+}
+
 // NS chosen so that SMEM stays under 227 KB
 template <int EPI, bool ROWS>
 static int launch_sweep(int mode, int kc, const CUtensorMap& ts, const CUtensorMap& ty, const SweepArgs& a, int grid,
-                        cudaStream_t st) {
+                        cudaStream_t st, int xt = 1) {
+  if (xt == 2) {
+    if constexpr (EPI != EPI_DENSE) {
+      if (mode == RB_MODE_BF16 && kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 1, BN, 6, ROWS, 2>>(ts, ty, a, grid, st);
+      if (mode == RB_MODE_BF16 && kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 2, BN, 4, ROWS, 2>>(ts, ty, a, grid, st);
+    }
+    return fail(RB_E_UNSUPPORTED, "two stationary tiles need bf16 mode and d <= 128");
+  }
   if (mode == RB_MODE_BF16) {
     if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 1, BN, 6, ROWS>>(ts, ty, a, grid, st);
     if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 2, BN, 4, ROWS>>(ts, ty, a, grid, st);
@@ -244,6 +258,26 @@ extern "C" int rb_gather_rows(const void* table, const int64_t* idx, void* out, 
   gather_rows_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(table), idx, static_cast<uint4*>(out), n_idx, n_rows, vpr);
   RB_LAUNCH_CHECK("gather_rows_kernel");
+  return 0;
+}
+
+// ========================================================================= normalise
+extern "C" int rb_normalize_rows(const void* x, void* out, float* inv_norm, int64_t n_rows, int d, int in_dtype,
+                                 int out_dtype, float eps, rb_stream_t stream) {
+  DevInfo dv; if (int r = get_dev(dv)) return r;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!x || !out) return fail(RB_E_ARG, "null pointer");
+  if (n_rows < 0 || d <= 0 || d % 8 || d > 1024) return fail(RB_E_ARG, "bad shape: d=%d must be a multiple of 8, <= 1024", d);
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) return fail(RB_E_ALIGN, "x/out must be 16-byte aligned");
+  if (n_rows == 0) return 0;
+  const int grid = static_cast<int>((n_rows * 32 + 255) / 256);
+  const bool ib = in_dtype == RB_DTYPE_BF16, ob = out_dtype == RB_DTYPE_BF16;
+  if ((!ib && in_dtype != RB_DTYPE_F32) || (!ob && out_dtype != RB_DTYPE_F32)) return fail(RB_E_ARG, "unknown dtype");
+  if (ib && ob) normalize_rows_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), inv_norm, n_rows, d, eps);
+  else if (ib) normalize_rows_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<float*>(out), inv_norm, n_rows, d, eps);
+  else if (ob) normalize_rows_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const float*>(x), static_cast<__nv_bfloat16*>(out), inv_norm, n_rows, d, eps);
+  else normalize_rows_kernel<float, float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), static_cast<float*>(out), inv_norm, n_rows, d, eps);
+  RB_LAUNCH_CHECK("normalize_rows_kernel");
   return 0;
 }
 
@@ -378,8 +412,9 @@ extern "C" int rb_ce_fwd(const void* U, const void* W, const float* bias, float 
   Operand ou, ow;
   if (int r = stage_operand(U, M, d, mode, b, ou, st)) return r;
   if (int r = stage_operand(W, N, d, mode, b, ow, st)) return r;
-  Plan p = make_plan(M, N, dv.sms, 1 << 20);
-  const long long m_pad = 1ll * p.n_stat_tiles * 128;
+  const int xt = sweep_xt(mode, d, M);
+  Plan p = make_plan(M, N, dv.sms, 1 << 20, 8, 128 * xt);
+  const long long m_pad = 1ll * p.n_stat_tiles * 128 * xt;
   int* lab32 = b.take<int>(m_pad);
   float* pm2 = b.take<float>(m_pad * p.n_splits);
   float* pl = b.take<float>(m_pad * p.n_splits);
@@ -394,7 +429,7 @@ extern "C" int rb_ce_fwd(const void* U, const void* W, const float* bias, float 
   a.n_stat = (int)M; a.n_strm = (int)N; a.n_stat_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
   a.n_splits = p.n_splits; a.d = d; a.scale = scale; a.bias = bias; a.labels = lab32;
   a.part_m2 = pm2; a.part_l = pl; a.part_ll = pll;
-  if (int r = launch_sweep<EPI_LSE, true>(mode, kc_for(d, mode), ts, ty, a, p.grid, st)) return r;
+  if (int r = launch_sweep<EPI_LSE, true>(mode, kc_for(d, mode), ts, ty, a, p.grid, st, xt)) return r;
   lse_merge_kernel<<<(int)((M + 255) / 256), 256, 0, st>>>(pm2, pl, pll, p.n_splits, m_pad, (int)M, row_max, row_sumexp, label_logit);
   RB_LAUNCH_CHECK("lse_merge_kernel");
   return 0;
@@ -462,6 +497,89 @@ static int ce_bwd_dw_pair(const DevInfo& dv, const void* U, const void* W, const
                           dbias, -grad_scale, sws, scatter_ws_bytes(M), st);
 }
 
+// ------------------------------------------------------------- fp32-parity CE backward
+// Exact fp32 passes (f32grad.cuh): 64-row stationary tiles, the streamed range cut so that about two
+// CTAs per SM are busy; split partials are summed in a fixed order.
+static int f32grad_splits(long long n_stat, long long n_strm, int sms) {
+  const long long tiles = (n_stat + F32G_TILE - 1) / F32G_TILE, strm_tiles = (n_strm + F32G_TILE - 1) / F32G_TILE;
+  long long s = (2ll * sms + tiles - 1) / tiles;
+  s = std::min<long long>(s, std::max<long long>(1, strm_tiles / 4));
+  return static_cast<int>(std::max<long long>(1, std::min<long long>(s, 64)));
+}
+static size_t f32grad_ws(long long M, long long N, int d, int sms) {
+  const size_t a = static_cast<size_t>(f32grad_splits(M, N, sms) + 1) * M * d * 4 + 1024;
+  const int sw = f32grad_splits(N, M, sms);
+  const size_t b = (sw > 1 ? static_cast<size_t>(sw) * N * (d + 1) * 4 : 0) + 1024;
+  return a + b;
+}
+static int launch_f32grad(const F32GradArgs& a, cudaStream_t st) {
+  const int tiles = (a.n_stat + F32G_TILE - 1) / F32G_TILE;
+  const int grid = tiles * a.n_splits;
+  if (a.d <= 64) {
+    RB_CUDA(cudaFuncSetAttribute(ce_grad_f32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, F32GradCfg<64>::SMEM_BYTES));
+    ce_grad_f32_kernel<64><<<grid, F32G_THREADS, F32GradCfg<64>::SMEM_BYTES, st>>>(a);
+  } else {
+    RB_CUDA(cudaFuncSetAttribute(ce_grad_f32_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, F32GradCfg<128>::SMEM_BYTES));
+    ce_grad_f32_kernel<128><<<grid, F32G_THREADS, F32GradCfg<128>::SMEM_BYTES, st>>>(a);
+  }
+  RB_LAUNCH_CHECK("ce_grad_f32_kernel");
+  return 0;
+}
+static int ce_bwd_f32(const DevInfo& dv, const float* U, const float* W, const float* bias, float scale,
+                      const int64_t* labels, int64_t label_base, const float* lse, float grad_scale,
+                      const float* grad_scale_dev, int64_t M, int64_t N, int d, float* dU, float* dW, float* dbias,
+                      Bump& b, cudaStream_t st) {
+  if (d > 128) return fail(RB_E_UNSUPPORTED, "fp32 CE backward supports d <= 128");
+  const float c2 = scale * 1.4426950408889634f;
+  if (dU) {  // rows stationary, items streamed: acc_i = sum_j softmax_ij w_j
+    const int ns = f32grad_splits(M, N, dv.sms);
+    float* acc = b.take<float>(static_cast<size_t>(M) * d);
+    float* part = (ns > 1) ? b.take<float>(static_cast<size_t>(ns) * M * d) : acc;
+    if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
+    F32GradArgs a{};
+    a.X = U; a.Y = W; a.n_stat = (int)M; a.n_strm = (int)N; a.d = d; a.n_splits = ns; a.c2 = c2;
+    a.stat_vec = lse; a.stat_mul = -1.f; a.strm_vec = bias; a.strm_mul = 1.f;
+    a.out_scale = 1.f; a.rowsum_scale = 0.f; a.scale_dev = nullptr; a.acc_out = part; a.rowsum_out = nullptr;
+    if (int r = launch_f32grad(a, st)) return r;
+    if (ns > 1) {
+      const long long n = M * d;
+      partial_sum_kernel<<<(int)std::min<long long>((n + 255) / 256, dv.sms * 8), 256, 0, st>>>(part, ns, n, acc);
+      RB_LAUNCH_CHECK("partial_sum_kernel");
+    }
+    // dU = g*scale*(acc - w_label): the finishing kernel of the fused pass with row_max == lse (factor 1)
+    ce_du_finish_kernel<float><<<(int)((M * 32 + 255) / 256), 256, 0, st>>>(acc, lse, lse, W, labels, label_base, N,
+                                                                            grad_scale * scale, grad_scale_dev, (int)M, d, dU);
+    RB_LAUNCH_CHECK("ce_du_finish_kernel");
+  }
+  if (dW) {  // items stationary, rows streamed: dW_j = g*scale*sum_i softmax_ij u_i, dbias_j = g*sum_i softmax_ij
+    const int ns = f32grad_splits(N, M, dv.sms);
+    float* part = (ns > 1) ? b.take<float>(static_cast<size_t>(ns) * N * d) : dW;
+    float* rs_part = nullptr;
+    if (dbias) rs_part = (ns > 1) ? b.take<float>(static_cast<size_t>(ns) * N) : dbias;
+    void* sws = b.take<char>(scatter_ws_bytes(M));
+    if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
+    F32GradArgs a{};
+    a.X = W; a.Y = U; a.n_stat = (int)N; a.n_strm = (int)M; a.d = d; a.n_splits = ns; a.c2 = c2;
+    a.stat_vec = bias; a.stat_mul = 1.f; a.strm_vec = lse; a.strm_mul = -1.f;
+    a.out_scale = grad_scale * scale; a.rowsum_scale = grad_scale; a.scale_dev = grad_scale_dev;
+    a.acc_out = part; a.rowsum_out = rs_part;
+    if (int r = launch_f32grad(a, st)) return r;
+    if (ns > 1) {
+      const long long n = N * d;
+      partial_sum_kernel<<<(int)std::min<long long>((n + 255) / 256, dv.sms * 8), 256, 0, st>>>(part, ns, n, dW);
+      RB_LAUNCH_CHECK("partial_sum_kernel");
+      if (dbias) {
+        partial_sum_kernel<<<(int)std::min<long long>((N + 255) / 256, dv.sms * 8), 256, 0, st>>>(rs_part, ns, N, dbias);
+        RB_LAUNCH_CHECK("partial_sum_kernel");
+      }
+    }
+    // exact one-hot correction: dW[label_i] -= g*scale*u_i, dbias[label_i] -= g   (sorted => deterministic)
+    return scatter_add_impl(U, labels, label_base, dW, M, N, d, RB_DTYPE_F32, -1, -grad_scale * scale, grad_scale_dev,
+                            dbias, -grad_scale, sws, scatter_ws_bytes(M), st);
+  }
+  return 0;
+}
+
 extern "C" int rb_ce_bwd(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
                          int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
                          int64_t M, int64_t N, int d, int dtype, int mode, float* dU, float* dW, float* dbias,
@@ -469,13 +587,15 @@ extern "C" int rb_ce_bwd(const void* U, const void* W, const float* bias, float 
   DevInfo dv; if (int r = get_dev(dv)) return r;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (int r = check_common(U, W, M, N, d, dtype, mode)) return r;
-  if (mode != RB_MODE_BF16) return fail(RB_E_UNSUPPORTED, "CE backward is bf16-mode only in this build");
   if (d > 128) return fail(RB_E_UNSUPPORTED, "CE backward supports d <= 128");
-  if (!(scale > 0.f)) return fail(RB_E_UNSUPPORTED, "CE backward needs scale > 0");
   if (!labels || !lse) return fail(RB_E_ARG, "null pointer");
   if (!ws) return fail(RB_E_WORKSPACE, "workspace required");
   if (dbias && !dW) return fail(RB_E_ARG, "dbias is produced by the dW pass: pass dW too");
   Bump b(ws, ws_bytes);
+  if (mode == RB_MODE_FP32X3)  // fp32 parity: exact fp32 passes (any sign of scale)
+    return ce_bwd_f32(dv, static_cast<const float*>(U), static_cast<const float*>(W), bias, scale, labels, label_base, lse,
+                      grad_scale, grad_scale_dev, M, N, d, dU, dW, dbias, b, st);
+  if (!(scale > 0.f)) return fail(RB_E_UNSUPPORTED, "CE backward needs scale > 0");
 
   if (dU) {  // no forward accumulator at hand: re-run the fused forward pass, then finish against the GLOBAL lse.
              // (Callers that kept rb_ce_fwd's dU_unnorm use rb_ce_du_finish and pass dU = NULL here.)
@@ -538,8 +658,10 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
   Operand ou, ow;
   if (int r = stage_operand(U, B, d, mode, b, ou, st)) return r;
   if (int r = stage_operand(W, N, d, mode, b, ow, st)) return r;
-  Plan p = make_plan(B, N, dv.sms, 1 << 20);
-  const int n_sub = 2 * p.n_splits;
+  const int xt = sweep_xt(mode, d, B);
+  Plan p = make_plan(B, N, dv.sms, 1 << 20, 8, 128 * xt);
+  const int n_sub = (xt == 2) ? p.n_splits : 2 * p.n_splits;
+  const int n_tiles128 = p.n_stat_tiles * xt;   // 128-row stationary tiles the sweeps touch
   const int selcap = topk_selcap(K), candcap = topk_candcap(K, n_sub);
   int* crow32 = nullptr; int* col32 = nullptr;
   long long nnz = 0;
@@ -555,7 +677,7 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
   float* tau = b.take<float>(B);
   int* cand_cnt = b.take<int>(static_cast<size_t>(B) * n_sub);
   int* overflow = b.take<int>(B);
-  unsigned char* flag = b.take<unsigned char>(static_cast<size_t>(p.n_stat_tiles) * 4 * p.n_strm_tiles);
+  unsigned char* flag = b.take<unsigned char>(static_cast<size_t>(n_tiles128) * 4 * p.n_strm_tiles);
   int* cand = b.take<int>(static_cast<size_t>(B) * n_sub * candcap);
   if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
   if (seen_crow) {
@@ -570,15 +692,15 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
   a.n_stat = (int)B; a.n_strm = (int)N; a.n_stat_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
   a.n_splits = p.n_splits; a.d = d; a.scale = scale; a.bias = bias;
   a.seen_crow = crow32; a.seen_col = col32; a.tile_max = tmax;
-  a.tau = tau; a.tile_flag = flag; a.cand = cand; a.cand_cnt = cand_cnt; a.cand_cap = candcap;
-  if (int r = launch_sweep<EPI_TOPK, true>(mode, kc_for(d, mode), ts, ty, a, p.grid, st)) return r;
+  a.tau = tau; a.tile_flag = flag; a.cand = cand; a.cand_cnt = cand_cnt; a.cand_cap = candcap; a.n_sub = n_sub;
+  if (int r = launch_sweep<EPI_TOPK, true>(mode, kc_for(d, mode), ts, ty, a, p.grid, st, xt)) return r;
   const int grid_w = static_cast<int>((B * 32 + 127) / 128);
   if (K <= 128) tilemax_select_kernel<4><<<grid_w, 128, 0, st>>>(tmax, p.n_strm_tiles, B, K, selcap, sel, selcnt, tau);
   else tilemax_select_kernel<8><<<grid_w, 128, 0, st>>>(tmax, p.n_strm_tiles, B, K, selcap, sel, selcnt, tau);
   RB_LAUNCH_CHECK("tilemax_select_kernel");
-  tile_flag_kernel<<<dim3((p.n_strm_tiles + 255) / 256, p.n_stat_tiles * 4), 256, 0, st>>>(tmax, tau, p.n_strm_tiles, B, flag);
+  tile_flag_kernel<<<dim3((p.n_strm_tiles + 255) / 256, n_tiles128 * 4), 256, 0, st>>>(tmax, tau, p.n_strm_tiles, B, flag);
   RB_LAUNCH_CHECK("tile_flag_kernel");
-  if (int r = launch_sweep<EPI_CAND, true>(mode, kc_for(d, mode), ts, ty, a, p.grid, st)) return r;
+  if (int r = launch_sweep<EPI_CAND, true>(mode, kc_for(d, mode), ts, ty, a, p.grid, st, xt)) return r;
   const int id_add = static_cast<int>(id_base);
   const int grid_r = static_cast<int>((B + 3) / 4);
   if (dtype == RB_DTYPE_BF16) {
@@ -622,12 +744,14 @@ extern "C" size_t rb_workspace_bytes(int op, int64_t M, int64_t N, int d, int K,
     case RB_OP_SCATTER_ADD: return scatter_ws_bytes(nnz) + 4096;
     case RB_OP_SCORE_DENSE: return need + staged_bytes(M, d, mode) + staged_bytes(N, d, mode);
     case RB_OP_CE_FWD: {  // the larger of the statistics-only sweep and the fused forward+dU pass
-      Plan p = make_plan(M, N, sms, 1 << 20);
-      const size_t m_pad = static_cast<size_t>(p.n_stat_tiles) * 128;
+      const int xt = sweep_xt(mode, d, M);
+      Plan p = make_plan(M, N, sms, 1 << 20, 8, 128 * xt);
+      const size_t m_pad = static_cast<size_t>(p.n_stat_tiles) * 128 * xt;
       const size_t stats = staged_bytes(M, d, mode) + staged_bytes(N, d, mode) + m_pad * 4 + 3 * m_pad * p.n_splits * 4 + 2048;
       return need + std::max(stats, pair_fwd_ws(M, N, d, sms));
     }
     case RB_OP_CE_BWD: {
+      if (mode == RB_MODE_FP32X3) return need + f32grad_ws(M, N, d, sms) + scatter_ws_bytes(M) + 1024;
       size_t n = need + static_cast<size_t>(M) * (d + 3) * 4 + 2048 + pair_fwd_ws(M, N, d, sms);  // dU by recompute
       Plan pw = make_plan(N, M, sms, 64, 8, 256);
       n += ((M + 127) / 128) * 128 * 4 + 512;
@@ -637,11 +761,13 @@ extern "C" size_t rb_workspace_bytes(int op, int64_t M, int64_t N, int d, int K,
       return n;
     }
     case RB_OP_TOPK_EVAL: {
-      Plan p = make_plan(M, N, sms, 1 << 20);
+      const int xt = sweep_xt(mode, d, M);
+      Plan p = make_plan(M, N, sms, 1 << 20, 8, 128 * xt);
+      const int n_sub = (xt == 2) ? p.n_splits : 2 * p.n_splits;
       return need + staged_bytes(M, d, mode) + staged_bytes(N, d, mode) + (M + 1 + std::max<int64_t>(nnz, 1)) * 4 +
              static_cast<size_t>(M) * (static_cast<size_t>(p.n_strm_tiles) + topk_selcap(K) + 4) * 4 +
-             static_cast<size_t>(p.n_stat_tiles) * 4 * p.n_strm_tiles +
-             static_cast<size_t>(M) * 2 * p.n_splits * (topk_candcap(K, 2 * p.n_splits) * 4 + 4) + 4096;
+             static_cast<size_t>(p.n_stat_tiles) * xt * 4 * p.n_strm_tiles +
+             static_cast<size_t>(M) * n_sub * (topk_candcap(K, n_sub) * 4 + 4) + 8192;
     }
     default: return 0;
   }

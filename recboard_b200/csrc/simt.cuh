@@ -38,6 +38,61 @@ __global__ void gather_rows_kernel(const uint4* __restrict__ table, const int64_
   }
 }
 
+// --------------------------------------------------------------------------- normalise
+// out[i,:] = x[i,:] / max(||x[i,:]||_2, eps)  (reference: F.normalize(weight[1:], dim=-1) and the user
+// side, HSTU/main.py:180-184; run once per evaluation sweep instead of once per batch).  One warp per
+// row, the row stays in registers between the norm and the scaling (one HBM read, one write);
+// d % 8 == 0, d <= 1024.  inv_norm (nullable) receives 1/max(norm, eps).
+template <typename TI, typename TO>
+__global__ void normalize_rows_kernel(const TI* __restrict__ x, TO* __restrict__ out, float* __restrict__ inv_norm,
+                                      long long n_rows, int d, float eps) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n_rows) return;
+  const TI* xr = x + row * d;
+  float v[4][8];
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int k = c * 256 + lane * 8;
+    if (k < d) {
+      if constexpr (sizeof(TI) == 2) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(xr + k));
+        v[c][0] = __uint_as_float(raw.x << 16); v[c][1] = __uint_as_float(raw.x & 0xFFFF0000u);
+        v[c][2] = __uint_as_float(raw.y << 16); v[c][3] = __uint_as_float(raw.y & 0xFFFF0000u);
+        v[c][4] = __uint_as_float(raw.z << 16); v[c][5] = __uint_as_float(raw.z & 0xFFFF0000u);
+        v[c][6] = __uint_as_float(raw.w << 16); v[c][7] = __uint_as_float(raw.w & 0xFFFF0000u);
+      } else {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(xr + k));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(xr + k + 4));
+        v[c][0] = a.x; v[c][1] = a.y; v[c][2] = a.z; v[c][3] = a.w; v[c][4] = b.x; v[c][5] = b.y; v[c][6] = b.z; v[c][7] = b.w;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ss = fmaf(v[c][e], v[c][e], ss);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float inv = 1.f / fmaxf(sqrtf(ss), eps);
+  if (inv_norm != nullptr && lane == 0) inv_norm[row] = inv;
+  TO* orow = out + row * d;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int k = c * 256 + lane * 8;
+    if (k < d) {
+      if constexpr (sizeof(TO) == 2) {
+        uint4 o;
+        o.x = pack_bf16x2(v[c][0] * inv, v[c][1] * inv); o.y = pack_bf16x2(v[c][2] * inv, v[c][3] * inv);
+        o.z = pack_bf16x2(v[c][4] * inv, v[c][5] * inv); o.w = pack_bf16x2(v[c][6] * inv, v[c][7] * inv);
+        *reinterpret_cast<uint4*>(orow + k) = o;
+      } else {
+        *reinterpret_cast<float4*>(orow + k) = make_float4(v[c][0] * inv, v[c][1] * inv, v[c][2] * inv, v[c][3] * inv);
+        *reinterpret_cast<float4*>(orow + k + 4) = make_float4(v[c][4] * inv, v[c][5] * inv, v[c][6] * inv, v[c][7] * inv);
+      }
+    }
+  }
+}
+
 // -------------------------------------------------------------------------- radix sort
 // Stable LSD radix sort of (key = row id, val = position) pairs, 8 bits per pass.
 // One warp owns a contiguous chunk; ranks inside the chunk come from __match_any_sync so equal

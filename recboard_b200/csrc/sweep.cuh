@@ -18,8 +18,14 @@
 //              kernel re-scores the groups exactly, drops seen items and sorts.
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2..9 = two epilogue warpgroups (thread <-> TMEM lane <-> stationary row); warpgroup g owns
-// the S buffer g, i.e. the tiles of parity g, so two tiles are always in flight per SM.
+// warps 2..9 = two epilogue warpgroups (thread <-> TMEM lane <-> stationary row).
+//   XT = 1: one stationary 128-row tile per CTA; warpgroup g owns the S buffer g, i.e. the streamed tiles
+//           of parity g, so two tiles are always in flight per SM.
+//   XT = 2: two stationary tiles X0, X1 per CTA (256 rows); every streamed tile feeds two MMAs and
+//           warpgroup g owns tile X_g with its own double-buffered S.  Each streamed byte fetched from L2
+//           now does twice the work: with XT = 1 a 4096-row sweep pulls 32 x the table through the
+//           L2->SM fabric (8.2 GB per sweep at N = 1M, d = 128: measured 9.4 TB/s, the binding limit of
+//           the plain sweeps), XT = 2 halves that and leaves the tensor pipe as the bound.
 #pragma once
 #include "ptx.cuh"
 
@@ -36,7 +42,7 @@ constexpr int SWEEP_THREADS = 320;
 struct SweepArgs {
   int n_stat;        // valid rows of the stationary operand
   int n_strm;        // valid rows of the streamed operand
-  int n_stat_tiles;  // ceil(n_stat / 128)
+  int n_stat_tiles;  // stationary units: ceil(n_stat / (128 * XT))
   int n_strm_tiles;  // ceil(n_strm / BN)
   int n_splits;      // the streamed range of every stationary tile is cut into n_splits work items
   int d;             // true feature width (<= KC*64)
@@ -57,9 +63,10 @@ struct SweepArgs {
   // EPI_CAND (rows stationary): pass 2 of the top-K
   const float* tau;                 // [n_stat] admission threshold of the row (score >= tau is a candidate)
   const unsigned char* tile_flag;   // [n_stat_tiles*4][n_strm_tiles] != 0: some row of that 32-row group can hit
-  int* cand;                        // [n_stat][2*n_splits][cand_cap] hit groups (item id >> 3), one sub-list per (split, warpgroup)
-  int* cand_cnt;                    // [n_stat][2*n_splits] groups found per sub-list (> cand_cap: overflow)
+  int* cand;                        // [n_stat][n_sub][cand_cap] hit groups (item id >> 3); one sub-list per (split, warpgroup)
+  int* cand_cnt;                    // [n_stat][n_sub] groups found per sub-list (> cand_cap: overflow)
   int cand_cap;
+  int n_sub;                        // XT = 1: 2*n_splits (two warpgroups share a row), XT = 2: n_splits
 };
 
 // key order: score desc, then id asc (shared by every top-K stage)
@@ -72,30 +79,32 @@ __device__ __forceinline__ float logit_of(uint32_t raw, float scale, const float
   return __fmul_rn(__uint_as_float(raw), scale);  // explicit roundings: no contraction differences between call sites
 }
 
-template <int EPI_, int DT_, int KC_, int BN_, int NS_, bool STAT_ROWS_>
+template <int EPI_, int DT_, int KC_, int BN_, int NS_, bool STAT_ROWS_, int XT_ = 1>
 struct SweepCfg {
-  static constexpr int EPI = EPI_, DT = DT_, KC = KC_, BN = BN_, NS = NS_;
+  static constexpr int EPI = EPI_, DT = DT_, KC = KC_, BN = BN_, NS = NS_, XT = XT_;
   static constexpr bool STAT_ROWS = STAT_ROWS_;  // true: queries stationary, items streamed
   // storage chunks (128-byte columns groups) per operand row
   static constexpr int KCS = (DT_ == DT_BF16) ? KC_ : 2 * KC_;  // tf32x3: [hi | lo], KC = d/32
   static constexpr int NPAIR = (DT_ == DT_BF16) ? KC_ : 3 * KC_;
   static constexpr int ELEMS_PER_CHUNK = (DT_ == DT_BF16) ? 64 : 32;
   static constexpr int DPAD = KC_ * ELEMS_PER_CHUNK;  // padded feature width
-  static constexpr int X_BYTES = KCS * 128 * 128;
+  static constexpr int XTILE_BYTES = KCS * 128 * 128;   // one stationary 128-row tile
+  static constexpr int X_BYTES = XT_ * XTILE_BYTES;
   static constexpr int Y_BYTES = KCS * BN_ * 128;
   static constexpr int CTRL_BYTES = 4096;  // barriers + cross-warpgroup exchange
   static constexpr int SMEM_BYTES = X_BYTES + NS_ * Y_BYTES + CTRL_BYTES + 1024 /*align*/;
-  static constexpr int TMEM_NEED = 2 * BN_;
+  static constexpr int TMEM_NEED = 2 * XT_ * BN_;
   static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
   static_assert(TMEM_NEED <= 512, "TMEM budget");
   static_assert(SMEM_BYTES <= 227 * 1024, "SMEM budget");
   static_assert(BN_ % 64 == 0 && BN_ <= 256, "BN");
+  static_assert(XT_ == 1 || XT_ == 2, "XT");
 };
 
 struct Control {
   uint64_t full[8], empty[8];
   uint64_t x_full, x_empty;
-  uint64_t s_full[2], s_empty[2];
+  uint64_t s_full[4], s_empty[4];
   uint32_t tmem_base;
   uint32_t pad_;
   float xchg[3][128];  // warpgroup 1 -> warpgroup 0 hand-over of per-row partials
@@ -147,7 +156,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
     for (int i = 0; i < C::NS; ++i) { mbar_init(&bar->full[i], 1); mbar_init(&bar->empty[i], 1); }
     mbar_init(&bar->x_full, 1);
     mbar_init(&bar->x_empty, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&bar->s_full[i], 1);
       mbar_init(&bar->s_empty[i], 128);
     }
@@ -180,8 +189,11 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
       if (elect_one()) {
         mbar_arrive_expect_tx(&bar->x_full, C::X_BYTES);
 #pragma unroll
-        for (int c = 0; c < C::KCS; ++c)
-          tma_load_2d(x_smem + c * 128 * 128, &tm_stat, &bar->x_full, c * C::ELEMS_PER_CHUNK, stat_tile * 128);
+        for (int x = 0; x < C::XT; ++x)
+#pragma unroll
+          for (int c = 0; c < C::KCS; ++c)
+            tma_load_2d(x_smem + x * C::XTILE_BYTES + c * 128 * 128, &tm_stat, &bar->x_full, c * C::ELEMS_PER_CHUNK,
+                        (stat_tile * C::XT + x) * 128);
       }
       __syncwarp();
       for (int t = t0; t < t1; ++t, ++it) {
@@ -214,32 +226,37 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
         const uint32_t st = it % C::NS, ph = (it / C::NS) & 1;
         const uint32_t buf = it & 1, sph = (it >> 1) & 1;
         mbar_wait(&bar->full[st], ph);
-        mbar_wait(&bar->s_empty[buf], sph ^ 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t d_tmem = tmem_base + buf * C::BN;
-          const uint32_t ys_lo = y_lo + ((st * C::Y_BYTES) >> 4);
 #pragma unroll
-          for (int p = 0; p < C::NPAIR; ++p) {
-            int ac, bc;
-            if (C::DT == DT_BF16) { ac = p; bc = p; }
-            else {
-              const int c = p / 3, r = p % 3;  // small terms first: lo*hi, hi*lo, then hi*hi
-              ac = (r == 0) ? C::KC + c : c;
-              bc = (r == 1) ? C::KC + c : c;
-            }
+        for (int x = 0; x < C::XT; ++x) {
+          const uint32_t bidx = (C::XT == 1) ? buf : x * 2 + buf;   // S buffer: XT=1 per tile parity, XT=2 per (X tile, parity)
+          mbar_wait(&bar->s_empty[bidx], sph ^ 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t d_tmem = tmem_base + bidx * C::BN;
+            const uint32_t xs_lo = x_lo + ((x * C::XTILE_BYTES) >> 4);
+            const uint32_t ys_lo = y_lo + ((st * C::Y_BYTES) >> 4);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t ad = smem_desc(dhi, x_lo + ((ac * 128 * 128 + kk * 32) >> 4));
-              const uint64_t bd = smem_desc(dhi, ys_lo + ((bc * C::BN * 128 + kk * 32) >> 4));
-              if (C::DT == DT_BF16) mma_f16_ss(d_tmem, ad, bd, idesc1, (p | kk) != 0);
-              else mma_tf32_ss(d_tmem, ad, bd, idesc1, (p | kk) != 0);
+            for (int p = 0; p < C::NPAIR; ++p) {
+              int ac, bc;
+              if (C::DT == DT_BF16) { ac = p; bc = p; }
+              else {
+                const int c = p / 3, r = p % 3;  // small terms first: lo*hi, hi*lo, then hi*hi
+                ac = (r == 0) ? C::KC + c : c;
+                bc = (r == 1) ? C::KC + c : c;
+              }
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t ad = smem_desc(dhi, xs_lo + ((ac * 128 * 128 + kk * 32) >> 4));
+                const uint64_t bd = smem_desc(dhi, ys_lo + ((bc * C::BN * 128 + kk * 32) >> 4));
+                if (C::DT == DT_BF16) mma_f16_ss(d_tmem, ad, bd, idesc1, (p | kk) != 0);
+                else mma_tf32_ss(d_tmem, ad, bd, idesc1, (p | kk) != 0);
+              }
             }
+            tc_commit(&bar->s_full[bidx]);
+            if (x == C::XT - 1) tc_commit(&bar->empty[st]);
           }
-          tc_commit(&bar->s_full[buf]);
-          tc_commit(&bar->empty[st]);
+          __syncwarp();
         }
-        __syncwarp();
       }
       if (elect_one()) tc_commit(&bar->x_empty);
       __syncwarp();
@@ -249,7 +266,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
     const int wg = (warp - 2) >> 2;    // warpgroup 0/1 == parity of the tiles it owns == S/G buffer
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;       // stationary row within the tile == TMEM lane
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + wg * C::BN;
+    const uint32_t t_lane0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float c2 = a.scale * LOG2E;
     const bool plain = (a.bias == nullptr) && (c2 > 0.f);  // fast paths: no bias, positive scale
     constexpr int NCH = C::BN / 32;
@@ -258,9 +275,10 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++k) {
       int stat_tile, split, t0, t1;
       item_range(item, stat_tile, split, t0, t1);
-      const int srow = stat_tile * 128 + r;  // global stationary row
+      const int stile = (C::XT == 1) ? stat_tile : stat_tile * 2 + wg;   // global 128-row stationary tile
+      const int srow = stile * 128 + r;  // global stationary row
       const bool srow_ok = srow < a.n_stat;
-      const long long pslot = static_cast<long long>(split) * a.n_stat_tiles * 128 + srow;
+      const long long pslot = static_cast<long long>(split) * a.n_stat_tiles * (128 * C::XT) + srow;
 
       // ---- per-item, per-warpgroup state
       float m2 = -INFINITY, l = 0.f, ll = 0.f;     // LSE
@@ -291,9 +309,9 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
       }
       const unsigned char* flag_row = nullptr;
       if (C::EPI == EPI_CAND) {
-        cand_list = a.cand + (static_cast<long long>(srow) * (2 * a.n_splits) + split * 2 + wg) * a.cand_cap;
-        flag_row = a.tile_flag + static_cast<long long>(stat_tile * 4 + q) * a.n_strm_tiles;
-        const int tf = t0 + ((wg - static_cast<int>(it & 1)) & 1);  // first tile of this item with parity wg
+        cand_list = a.cand + (static_cast<long long>(srow) * a.n_sub + (C::XT == 1 ? split * 2 + wg : split)) * a.cand_cap;
+        flag_row = a.tile_flag + static_cast<long long>(stile * 4 + q) * a.n_strm_tiles;
+        const int tf = (C::XT == 1) ? t0 + ((wg - static_cast<int>(it & 1)) & 1) : t0;  // first tile this warpgroup handles
         if (tf < t1) flag_next = __ldg(flag_row + tf);
       }
       // advance the seen cursor by one entry; the entry after next is already in a register
@@ -304,21 +322,23 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
       };
 
       for (int t = t0; t < t1; ++t, ++it) {
-        if ((it & 1) != static_cast<uint32_t>(wg)) continue;
+        if (C::XT == 1 && (it & 1) != static_cast<uint32_t>(wg)) continue;
         const uint32_t sph = (it >> 1) & 1;
+        const uint32_t bidx = (C::XT == 1) ? wg : wg * 2 + (it & 1);
+        const uint32_t t_lane = t_lane0 + bidx * C::BN;
         const int col_base = t * C::BN;                       // first streamed row of the tile
         const int n_valid = min(C::BN, a.n_strm - col_base);  // valid columns in this tile
         const bool full_tile = (n_valid == C::BN);
         bool tile_live = true;
         if (C::EPI == EPI_CAND) {  // warp-uniform: can any of this warp's 32 rows reach its threshold in this tile?
           tile_live = flag_next != 0;
-          if (t + 2 < t1) flag_next = __ldg(flag_row + t + 2);  // consumed two tiles from now
+          if (t + 3 - C::XT < t1) flag_next = __ldg(flag_row + t + 3 - C::XT);  // the next tile this warpgroup handles
         }
-        mbar_wait(&bar->s_full[wg], sph);
+        mbar_wait(&bar->s_full[bidx], sph);
         tc_fence_after();
         if (C::EPI == EPI_CAND && !tile_live) {
           tc_fence_before();
-          mbar_arrive(&bar->s_empty[wg]);
+          mbar_arrive(&bar->s_empty[bidx]);
           continue;
         }
         float tmax = -INFINITY;   // TOPK: max of this tile for this row
@@ -428,7 +448,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
 
         // release the S buffer (all tcgen05.ld of this thread have completed)
         tc_fence_before();
-        mbar_arrive(&bar->s_empty[wg]);
+        mbar_arrive(&bar->s_empty[bidx]);
         if (C::EPI == EPI_TOPK) {
           while (next_seen < col_base) seen_advance();  // seen ids that fell into the other warpgroup's tiles
           const bool dirty = next_seen < col_base + C::BN;
@@ -441,8 +461,13 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
 
       // ---- per-item outputs
       if (C::EPI == EPI_CAND && srow_ok)
-        a.cand_cnt[static_cast<long long>(srow) * (2 * a.n_splits) + split * 2 + wg] = n_cand;
-      if (C::EPI == EPI_LSE) {
+        a.cand_cnt[static_cast<long long>(srow) * a.n_sub + (C::XT == 1 ? split * 2 + wg : split)] = n_cand;
+      if (C::EPI == EPI_LSE && C::XT == 2) {  // each warpgroup owns its rows: no hand-over
+        a.part_m2[pslot] = m2;
+        a.part_l[pslot] = l;
+        a.part_ll[pslot] = ll;
+      }
+      if (C::EPI == EPI_LSE && C::XT == 1) {
         // warpgroup 1 hands its partial to warpgroup 0, which merges and writes one slot per row
         if (wg == 1) { bar->xchg[0][r] = m2; bar->xchg[1][r] = l; bar->xchg[2][r] = ll; }
         epi_bar_sync();

@@ -96,6 +96,35 @@ def gather_rows(table: torch.Tensor, idx: torch.Tensor, padding_idx: int = -1) -
 
 
 # --------------------------------------------------------------------------------------
+# row normalisation (cosine scoring operands)
+# --------------------------------------------------------------------------------------
+def normalize_rows(x: torch.Tensor, out_dtype: Optional[torch.dtype] = None, eps: float = 1e-12,
+                   return_inv_norm: bool = False):
+    """``F.normalize(x, dim=-1)`` for a (rows, d) matrix (HSTU/main.py:180-184) in one HBM pass,
+    optionally cast to ``out_dtype`` (bf16 operand copy for the cosine sweep).  No autograd: this is
+    the evaluation-side copy built once per sweep."""
+    dev = L.require_cuda(x)
+    if x.dim() != 2:
+        raise ValueError("normalize_rows expects a (rows, d) matrix")
+    xc = x.detach()
+    if xc.dtype not in (torch.float32, torch.bfloat16):
+        xc = xc.float()
+    xc = xc.contiguous()
+    out_dtype = out_dtype or xc.dtype
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("out_dtype must be float32 or bfloat16")
+    n, d = xc.shape
+    out = torch.empty(n, d, dtype=out_dtype, device=dev)
+    inv = torch.empty(n, dtype=torch.float32, device=dev) if return_inv_norm else None
+    L.check(
+        L.lib().rb_normalize_rows(L.ptr(xc), L.ptr(out), L.ptr(inv), n, d, L.dtype_code(xc), L.dtype_code(out),
+                                  float(eps), L.stream_ptr(dev)),
+        "rb_normalize_rows",
+    )
+    return (out, inv) if return_inv_norm else out
+
+
+# --------------------------------------------------------------------------------------
 # dense scores (compatibility path of recommend_from_full)
 # --------------------------------------------------------------------------------------
 def score_dense(U: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, scale: float = 1.0,

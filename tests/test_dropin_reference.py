@@ -23,6 +23,7 @@ def oracle_ops(monkeypatch):
         fused_ce=lambda U, W, labels, bias=None, scale=1.0, precision=None: orc.ce_loss(U, W, labels, bias, scale),
         score_dense=lambda U, W, bias=None, scale=1.0, precision=None: orc.score_dense(U, W, bias, scale),
         gather_rows_raw=lambda table, idx: table[idx],
+        normalize_rows=lambda x, out_dtype=None, eps=1e-12: orc.normalize_rows(x, eps),
         topk_eval=lambda U, W, K, crow=None, col=None, bias=None, scale=1.0, precision=None:
             orc.topk_sorted(orc.mask_seen(orc.score_dense(U, W, bias, scale), crow, col) if crow is not None
                             else orc.score_dense(U, W, bias, scale), K),
@@ -128,3 +129,6 @@ def test_hstu_full(oracle_ops):
     data = {model.ISeq: _seqs(g, 4, 10, 80), model.Time: torch.sort(torch.randint(0, 10**6, (4, 10), generator=g), 1).values}
     with torch.no_grad():
         assert torch.allclose(model(data, ranking="full"), ref.HSTU.recommend_from_full(model, data), rtol=1e-6, atol=1e-7)
+        model.reset_ranking_buffers()  # normalised table cached once per sweep (a11)
+        assert torch.allclose(model(data, ranking="full"), ref.HSTU.recommend_from_full(model, data), rtol=1e-6, atol=1e-7)
+        assert model._fused_item.shape == (80, 32)

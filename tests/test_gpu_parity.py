@@ -160,6 +160,47 @@ def test_ce_gradients_bf16(ops, M, N, d):
     assert_rel(Wd.grad, rdW, 2 * BF16_RTOL, "dW")
 
 
+@pytest.mark.parametrize("M,N,d,with_bias", [(1, 130, 64, False), (300, 1000, 64, True), (513, 4099, 32, False),
+                                               (3013, 12101, 64, False)])
+def test_ce_gradients_fp32(ops, M, N, d, with_bias):
+    """fp32-parity mode trains too: loss and all gradients within 1e-5 of the oracle (config 1 shape last)."""
+    g = torch.Generator().manual_seed(7 * M + N + d)
+    U = torch.randn(M, d, generator=g) * 1.5 / d ** 0.25
+    W = torch.randn(N, d, generator=g) * 1.5 / d ** 0.25
+    b = torch.randn(N, generator=g) * 0.3 if with_bias else None
+    lab = torch.randint(0, N, (M,), generator=g)
+    lab[: max(1, M // 8)] = 3
+    ref_loss, rdU, rdW, rdb = orc.ce_fwd_bwd(U, W, lab, b, scale=0.9, grad_out=2.0)
+    Ud, Wd = dev(U).requires_grad_(True), dev(W).requires_grad_(True)
+    bd = dev(b).requires_grad_(True) if with_bias else None
+    loss = ops.fused_ce(Ud, Wd, dev(lab), bias=bd, scale=0.9, precision="fp32")
+    (loss * 2.0).backward()
+    assert abs(float(loss.detach()) - float(ref_loss)) <= FP32_RTOL * abs(float(ref_loss))
+    assert_rel(Ud.grad, rdU, FP32_RTOL, "dU")
+    assert_rel(Wd.grad, rdW, FP32_RTOL, "dW")
+    if with_bias:
+        assert_rel(bd.grad, rdb, FP32_RTOL, "dbias")
+
+
+def test_golden_ce_fp32_gradients(ops, golden):
+    """Gradients in fp32-parity mode against the numbers the reference's own model files produced:
+    SASRec dU (SASRec/main.py:217-219 + autograd) and the BERT4Rec bias head's dU / dW / dbias."""
+    g = golden("sasrec_ce")
+    Ud, Wd = dev(T(g["U"])).requires_grad_(True), dev(T(g["W"])).requires_grad_(True)
+    loss = ops.fused_ce(Ud, Wd, dev(T(g["labels"])), precision="fp32")
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g["loss"])) <= FP32_RTOL * abs(float(g["loss"]))
+    assert_rel(Ud.grad, g["dU"], FP32_RTOL, "sasrec dU")
+    f = golden("bert4rec_ce")
+    Ud, Wd, bd = (dev(T(f[k])).requires_grad_(True) for k in ("U", "W", "bias"))
+    loss = ops.fused_ce(Ud, Wd, dev(T(f["labels"])), bias=bd, precision="fp32")
+    loss.backward()
+    assert abs(float(loss.detach()) - float(f["loss"])) <= FP32_RTOL * abs(float(f["loss"]))
+    assert_rel(Ud.grad, f["dU"], FP32_RTOL, "bert4rec dU")
+    assert_rel(Wd.grad, f["dW"], FP32_RTOL, "bert4rec dW")
+    assert_rel(bd.grad, f["dbias"], FP32_RTOL, "bert4rec dbias")
+
+
 def _seen_lists(g, B, N, max_len):
     return [torch.randperm(N, generator=g)[: int(torch.randint(0, max_len + 1, (1,), generator=g))].tolist() for _ in range(B)]
 
@@ -250,6 +291,24 @@ def test_topk_candidate_overflow_falls_back(ops):
     assert torch.equal(ids.cpu().long()[0], torch.arange(3, 3 + K))
     assert_rel(vals, rv, 2e-6, "overflow vals")
     _check_topk(vals, ids, masked, K, 2e-6)
+
+
+@pytest.mark.parametrize("n,d,in_dt,out_dt", [(1, 8, torch.float32, torch.float32), (1000, 256, torch.float32, torch.bfloat16),
+                                             (4097, 64, torch.bfloat16, torch.bfloat16), (333, 1024, torch.bfloat16, torch.float32)])
+def test_normalize_rows(ops, n, d, in_dt, out_dt):
+    """a11: F.normalize(weight[1:], dim=-1) (HSTU/main.py:182-184), including an all-zero row (eps clamp)."""
+    g = torch.Generator().manual_seed(n + d)
+    x = (torch.randn(n + 1, d, generator=g) * 3).to(in_dt)
+    x[n // 2 + 1] = 0
+    out, inv = ops.normalize_rows(dev(x)[1:], out_dtype=out_dt, return_inv_norm=True)   # the weight[NUM_PADS:] view
+    ref = orc.normalize_rows(x[1:].float())
+    assert out.dtype == out_dt and out.shape == (n, d)
+    tol = 1e-6 if out_dt == torch.float32 else 2.0 ** -8
+    assert float((out.float().cpu() - ref).abs().max()) <= tol
+    rn = x[1:].float().norm(dim=-1).clamp_min(1e-12)
+    nz = rn > 1e-6
+    assert torch.allclose(inv.cpu()[nz], 1.0 / rn[nz], rtol=1e-5)
+    assert torch.all(out[n // 2] == 0)
 
 
 def test_scatter_add_hot_rows_deterministic(ops):
