@@ -282,9 +282,11 @@ extern "C" int rb_normalize_rows(const void* x, void* out, float* inv_norm, int6
 }
 
 // ======================================================================= scatter-add
-static size_t scatter_ws_bytes(long long n_idx) {
+static size_t scatter_ws_bytes(long long n_idx, int d) {
   const long long chunks = (n_idx + RS_CHUNK - 1) / RS_CHUNK;
-  return static_cast<size_t>(n_idx) * 4 * 4 + static_cast<size_t>(chunks) * 256 * 4 + 5 * 256;
+  const long long blocks = (n_idx + SEG_BLOCK - 1) / SEG_BLOCK;
+  return static_cast<size_t>(n_idx) * 4 * 4 + static_cast<size_t>(chunks) * 256 * 4 +
+         2 * static_cast<size_t>(blocks) * d * 4 + 8 * 256;
 }
 // grad_table[idx[i]-idx_base] += alpha*(*alpha_dev) * grad_out[i] in a fixed order; optionally
 // cnt_out[row] += cnt_alpha*(*alpha_dev) * (#occurrences of row)
@@ -296,14 +298,17 @@ static int scatter_add_impl(const void* grad_out, const int64_t* idx, long long 
   if (n_idx < 0 || n_rows <= 0 || d <= 0 || d % 4) return fail(RB_E_ARG, "bad shape (d must be a multiple of 4)");
   if (n_idx >= (1ll << 31) || n_rows >= (1ll << 32) - 1) return fail(RB_E_ARG, "n_idx/n_rows too large");
   if (n_idx == 0) return 0;
-  if (!ws || ws_bytes < scatter_ws_bytes(n_idx)) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", scatter_ws_bytes(n_idx));
+  if (!ws || ws_bytes < scatter_ws_bytes(n_idx, d)) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", scatter_ws_bytes(n_idx, d));
   Bump b(ws, ws_bytes);
   const int n = static_cast<int>(n_idx);
   const int chunks = (n + RS_CHUNK - 1) / RS_CHUNK;
   uint32_t* k0 = b.take<uint32_t>(n); uint32_t* v0 = b.take<uint32_t>(n);
   uint32_t* k1 = b.take<uint32_t>(n); uint32_t* v1 = b.take<uint32_t>(n);
   uint32_t* hist = b.take<uint32_t>(static_cast<size_t>(chunks) * 256);
-  rs_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(idx, idx_base, k0, v0, n, n_rows);
+  const int seg_blocks = (n + SEG_BLOCK - 1) / SEG_BLOCK;
+  float* lead = b.take<float>(static_cast<size_t>(seg_blocks) * d);
+  float* trail = b.take<float>(static_cast<size_t>(seg_blocks) * d);
+  rs_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(idx, idx_base, k0, v0, n, n_rows, padding_idx);
   RB_LAUNCH_CHECK("rs_init_kernel");
   int bits = 1;
   while ((1ull << bits) <= static_cast<unsigned long long>(n_rows)) ++bits;  // keys in [0, n_rows]
@@ -312,17 +317,18 @@ static int scatter_add_impl(const void* grad_out, const int64_t* idx, long long 
     RB_LAUNCH_CHECK("rs_hist_kernel");
     rs_scan_kernel<<<1, 1024, 0, st>>>(hist, chunks * 256);
     RB_LAUNCH_CHECK("rs_scan_kernel");
-    rs_scatter_kernel<<<chunks, 32, 0, st>>>(k0, v0, k1, v1, n, shift, hist, chunks);
+    rs_scatter_kernel<<<(chunks + RS_SCATTER_WARPS - 1) / RS_SCATTER_WARPS, 32 * RS_SCATTER_WARPS, 0, st>>>(k0, v0, k1, v1, n, shift, hist, chunks);
     RB_LAUNCH_CHECK("rs_scatter_kernel");
     std::swap(k0, k1); std::swap(v0, v1);
   }
-  const long long threads = 32ll * n;
-  const int grid = static_cast<int>((threads + 255) / 256);
+  const int grid = (seg_blocks + 3) / 4;   // 4 warps (blocks of 32 sorted positions) per CTA
   if (dtype == RB_DTYPE_BF16)
-    scatter_segments_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(k0, v0, static_cast<const __nv_bfloat16*>(grad_out), grad_table, n, d, n_rows, padding_idx, alpha, alpha_dev, cnt_out, cnt_alpha);
+    scatter_segments_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(k0, v0, static_cast<const __nv_bfloat16*>(grad_out), grad_table, n, d, n_rows, alpha, alpha_dev, cnt_out, cnt_alpha, lead, trail);
   else
-    scatter_segments_kernel<float><<<grid, 256, 0, st>>>(k0, v0, static_cast<const float*>(grad_out), grad_table, n, d, n_rows, padding_idx, alpha, alpha_dev, cnt_out, cnt_alpha);
+    scatter_segments_kernel<float><<<grid, 128, 0, st>>>(k0, v0, static_cast<const float*>(grad_out), grad_table, n, d, n_rows, alpha, alpha_dev, cnt_out, cnt_alpha, lead, trail);
   RB_LAUNCH_CHECK("scatter_segments_kernel");
+  scatter_split_runs_kernel<<<grid, 128, 0, st>>>(k0, grad_table, n, d, n_rows, alpha, alpha_dev, cnt_out, cnt_alpha, lead, trail);
+  RB_LAUNCH_CHECK("scatter_split_runs_kernel");
   return 0;
 }
 extern "C" int rb_scatter_add_rows(const void* grad_out, const int64_t* idx, float* grad_table, int64_t n_idx,
@@ -468,10 +474,11 @@ static int ce_bwd_dw_pair(const DevInfo& dv, const void* U, const void* W, const
   float* part = (p.n_splits > 1) ? b.take<float>(static_cast<size_t>(p.n_splits) * N * d) : dW;
   float* rs_part = nullptr;
   if (dbias) rs_part = (p.n_splits > 1) ? b.take<float>(static_cast<size_t>(p.n_splits) * N) : dbias;
-  float* bias2 = bias ? b.take<float>(n_pad) : nullptr;
+  const bool bias_cfg = bias != nullptr || dbias != nullptr;   // the BIAS variant also carries the row sums (dbias)
+  float* bias2 = bias_cfg ? b.take<float>(n_pad) : nullptr;
   if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
-  if (bias) {
-    bias2_kernel<<<(int)((n_pad + 255) / 256), 256, 0, st>>>(bias, bias2, N, n_pad);
+  if (bias_cfg) {
+    bias2_kernel<<<(int)((n_pad + 255) / 256), 256, 0, st>>>(bias, bias2, N, n_pad);   // null bias -> zeros
     RB_LAUNCH_CHECK("bias2_kernel");
   }
   CUtensorMap ts, ty;
@@ -481,7 +488,7 @@ static int ce_bwd_dw_pair(const DevInfo& dv, const void* U, const void* W, const
   a.n_stat = (int)N; a.n_strm = (int)M; a.n_pair_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
   a.n_splits = p.n_splits; a.d = d; a.stat_pad = (int)n_pad; a.scale = scale; a.bias2_stat = bias2; a.aux = lse2;
   a.gscale = grad_scale * scale; a.rscale = grad_scale; a.gscale_dev = grad_scale_dev; a.acc_out = part; a.rowsum_out = rs_part;
-  if (int r = launch_pair<PASS_DW>(kc_for(d, RB_MODE_BF16), bias != nullptr, ts, ty, a, p.grid, st)) return r;
+  if (int r = launch_pair<PASS_DW>(kc_for(d, RB_MODE_BF16), bias_cfg, ts, ty, a, p.grid, st)) return r;
   if (p.n_splits > 1) {
     const long long n = N * d;
     partial_sum_kernel<<<(int)std::min<long long>((n + 255) / 256, dv.sms * 8), 256, 0, st>>>(part, p.n_splits, n, dW);
@@ -491,10 +498,10 @@ static int ce_bwd_dw_pair(const DevInfo& dv, const void* U, const void* W, const
       RB_LAUNCH_CHECK("partial_sum_kernel");
     }
   }
-  void* sws = b.take<char>(scatter_ws_bytes(M));
+  void* sws = b.take<char>(scatter_ws_bytes(M, d));
   if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
   return scatter_add_impl(U, labels, label_base, dW, M, N, d, RB_DTYPE_BF16, -1, -grad_scale * scale, grad_scale_dev,
-                          dbias, -grad_scale, sws, scatter_ws_bytes(M), st);
+                          dbias, -grad_scale, sws, scatter_ws_bytes(M, d), st);
 }
 
 // ------------------------------------------------------------- fp32-parity CE backward
@@ -556,7 +563,7 @@ static int ce_bwd_f32(const DevInfo& dv, const float* U, const float* W, const f
     float* part = (ns > 1) ? b.take<float>(static_cast<size_t>(ns) * N * d) : dW;
     float* rs_part = nullptr;
     if (dbias) rs_part = (ns > 1) ? b.take<float>(static_cast<size_t>(ns) * N) : dbias;
-    void* sws = b.take<char>(scatter_ws_bytes(M));
+    void* sws = b.take<char>(scatter_ws_bytes(M, d));
     if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
     F32GradArgs a{};
     a.X = W; a.Y = U; a.n_stat = (int)N; a.n_strm = (int)M; a.d = d; a.n_splits = ns; a.c2 = c2;
@@ -575,7 +582,7 @@ static int ce_bwd_f32(const DevInfo& dv, const float* U, const float* W, const f
     }
     // exact one-hot correction: dW[label_i] -= g*scale*u_i, dbias[label_i] -= g   (sorted => deterministic)
     return scatter_add_impl(U, labels, label_base, dW, M, N, d, RB_DTYPE_F32, -1, -grad_scale * scale, grad_scale_dev,
-                            dbias, -grad_scale, sws, scatter_ws_bytes(M), st);
+                            dbias, -grad_scale, sws, scatter_ws_bytes(M, d), st);
   }
   return 0;
 }
@@ -625,15 +632,14 @@ extern "C" int rb_ce_bwd(const void* U, const void* W, const float* bias, float 
 // Exact masked top-K in two tensor-core sweeps (no dense (B,N), no per-element selection work):
 //   1. sweep<EPI_TOPK>: masked maximum of every (row, 128-item tile)
 //   2. tilemax_select:  tau[row] = K-th largest tile maximum  (>= K unseen items score >= tau, so every
-//                       top-K member does too) + the tile list the fallback uses
+//                       top-K member does too)
 //   3. tile_flag:       which (32-row group, tile) pairs can hold a candidate
 //   4. sweep<EPI_CAND>: recompute the scores, append every aligned group of 8 items whose maximum reaches tau
 //                       to the (row, split, warpgroup) sub-list (about K groups per row in total);
 //                       flagged-off tiles are skipped
 //   5. topk_from_groups: exact fp32 re-scoring of the hit groups, drop seen items, sort, keep K.
-//   6. rows with an overflowed sub-list (massive ties / tiny catalogs): exact SIMT re-scoring of the
-//      selected tiles (topk_refine).
-static int topk_selcap(int K) { return ((2 * K + 64 + 31) / 32) * 32; }
+//   6. rows with an overflowed sub-list (massive ties / tiny catalogs): exact SIMT re-scoring of every
+//      tile whose maximum reaches tau or is unknown (topk_refine).
 // capacity of one candidate sub-list: ~8x the expected share of a sub-list, a power of two in [32, 512]
 static int topk_candcap(int K, int n_sub) {
   const int want = (8 * K + n_sub - 1) / n_sub;
@@ -662,7 +668,7 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
   Plan p = make_plan(B, N, dv.sms, 1 << 20, 8, 128 * xt);
   const int n_sub = (xt == 2) ? p.n_splits : 2 * p.n_splits;
   const int n_tiles128 = p.n_stat_tiles * xt;   // 128-row stationary tiles the sweeps touch
-  const int selcap = topk_selcap(K), candcap = topk_candcap(K, n_sub);
+  const int candcap = topk_candcap(K, n_sub);
   int* crow32 = nullptr; int* col32 = nullptr;
   long long nnz = 0;
   if (seen_crow) {
@@ -672,8 +678,6 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
     col32 = b.take<int>(std::max<long long>(nnz, 1));
   }
   float* tmax = b.take<float>(static_cast<size_t>(B) * p.n_strm_tiles);
-  int* sel = b.take<int>(static_cast<size_t>(B) * selcap);
-  int* selcnt = b.take<int>(B);
   float* tau = b.take<float>(B);
   int* cand_cnt = b.take<int>(static_cast<size_t>(B) * n_sub);
   int* overflow = b.take<int>(B);
@@ -695,8 +699,8 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
   a.tau = tau; a.tile_flag = flag; a.cand = cand; a.cand_cnt = cand_cnt; a.cand_cap = candcap; a.n_sub = n_sub;
   if (int r = launch_sweep<EPI_TOPK, true>(mode, kc_for(d, mode), ts, ty, a, p.grid, st, xt)) return r;
   const int grid_w = static_cast<int>((B * 32 + 127) / 128);
-  if (K <= 128) tilemax_select_kernel<4><<<grid_w, 128, 0, st>>>(tmax, p.n_strm_tiles, B, K, selcap, sel, selcnt, tau);
-  else tilemax_select_kernel<8><<<grid_w, 128, 0, st>>>(tmax, p.n_strm_tiles, B, K, selcap, sel, selcnt, tau);
+  if (K <= 128) tilemax_select_kernel<4><<<grid_w, 128, 0, st>>>(tmax, p.n_strm_tiles, B, K, tau);
+  else tilemax_select_kernel<8><<<grid_w, 128, 0, st>>>(tmax, p.n_strm_tiles, B, K, tau);
   RB_LAUNCH_CHECK("tilemax_select_kernel");
   tile_flag_kernel<<<dim3((p.n_strm_tiles + 255) / 256, n_tiles128 * 4), 256, 0, st>>>(tmax, tau, p.n_strm_tiles, B, flag);
   RB_LAUNCH_CHECK("tile_flag_kernel");
@@ -708,15 +712,15 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
     if (K <= 128) topk_from_groups_kernel<__nv_bfloat16, 4><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, cand, cand_cnt, n_sub, candcap, crow32, col32, K, id_add, top_vals, top_ids, overflow);
     else topk_from_groups_kernel<__nv_bfloat16, 8><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, cand, cand_cnt, n_sub, candcap, crow32, col32, K, id_add, top_vals, top_ids, overflow);
     RB_LAUNCH_CHECK("topk_from_groups_kernel");
-    if (K <= 128) topk_refine_kernel<__nv_bfloat16, 4><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, crow32, col32, sel, selcnt, selcap, K, id_add, top_vals, top_ids, overflow);
-    else topk_refine_kernel<__nv_bfloat16, 8><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, crow32, col32, sel, selcnt, selcap, K, id_add, top_vals, top_ids, overflow);
+    if (K <= 128) topk_refine_kernel<__nv_bfloat16, 4><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, crow32, col32, tmax, tau, K, id_add, top_vals, top_ids, overflow);
+    else topk_refine_kernel<__nv_bfloat16, 8><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, crow32, col32, tmax, tau, K, id_add, top_vals, top_ids, overflow);
   } else {
     const float* Uf = static_cast<const float*>(U); const float* Wf = static_cast<const float*>(W);
     if (K <= 128) topk_from_groups_kernel<float, 4><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, cand, cand_cnt, n_sub, candcap, crow32, col32, K, id_add, top_vals, top_ids, overflow);
     else topk_from_groups_kernel<float, 8><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, cand, cand_cnt, n_sub, candcap, crow32, col32, K, id_add, top_vals, top_ids, overflow);
     RB_LAUNCH_CHECK("topk_from_groups_kernel");
-    if (K <= 128) topk_refine_kernel<float, 4><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, crow32, col32, sel, selcnt, selcap, K, id_add, top_vals, top_ids, overflow);
-    else topk_refine_kernel<float, 8><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, crow32, col32, sel, selcnt, selcap, K, id_add, top_vals, top_ids, overflow);
+    if (K <= 128) topk_refine_kernel<float, 4><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, crow32, col32, tmax, tau, K, id_add, top_vals, top_ids, overflow);
+    else topk_refine_kernel<float, 8><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, crow32, col32, tmax, tau, K, id_add, top_vals, top_ids, overflow);
   }
   RB_LAUNCH_CHECK("topk_refine_kernel");
   return 0;
@@ -741,7 +745,7 @@ extern "C" size_t rb_workspace_bytes(int op, int64_t M, int64_t N, int d, int K,
   { DevInfo dv; if (get_dev(dv) == 0 && dv.sms > 0) sms = dv.sms; }
   size_t need = 4096;
   switch (op) {
-    case RB_OP_SCATTER_ADD: return scatter_ws_bytes(nnz) + 4096;
+    case RB_OP_SCATTER_ADD: return scatter_ws_bytes(nnz, d) + 4096;
     case RB_OP_SCORE_DENSE: return need + staged_bytes(M, d, mode) + staged_bytes(N, d, mode);
     case RB_OP_CE_FWD: {  // the larger of the statistics-only sweep and the fused forward+dU pass
       const int xt = sweep_xt(mode, d, M);
@@ -751,13 +755,13 @@ extern "C" size_t rb_workspace_bytes(int op, int64_t M, int64_t N, int d, int K,
       return need + std::max(stats, pair_fwd_ws(M, N, d, sms));
     }
     case RB_OP_CE_BWD: {
-      if (mode == RB_MODE_FP32X3) return need + f32grad_ws(M, N, d, sms) + scatter_ws_bytes(M) + 1024;
+      if (mode == RB_MODE_FP32X3) return need + f32grad_ws(M, N, d, sms) + scatter_ws_bytes(M, d) + 1024;
       size_t n = need + static_cast<size_t>(M) * (d + 3) * 4 + 2048 + pair_fwd_ws(M, N, d, sms);  // dU by recompute
       Plan pw = make_plan(N, M, sms, 64, 8, 256);
       n += ((M + 127) / 128) * 128 * 4 + 512;
       n += (pw.n_splits > 1 ? static_cast<size_t>(pw.n_splits) * N * (d + 1) * 4 : 0) + 1024;
       n += static_cast<size_t>(pw.n_stat_tiles) * 256 * 4 + 512;  // bias2
-      n += scatter_ws_bytes(M) + 512;
+      n += scatter_ws_bytes(M, d) + 512;
       return n;
     }
     case RB_OP_TOPK_EVAL: {
@@ -765,7 +769,7 @@ extern "C" size_t rb_workspace_bytes(int op, int64_t M, int64_t N, int d, int K,
       Plan p = make_plan(M, N, sms, 1 << 20, 8, 128 * xt);
       const int n_sub = (xt == 2) ? p.n_splits : 2 * p.n_splits;
       return need + staged_bytes(M, d, mode) + staged_bytes(N, d, mode) + (M + 1 + std::max<int64_t>(nnz, 1)) * 4 +
-             static_cast<size_t>(M) * (static_cast<size_t>(p.n_strm_tiles) + topk_selcap(K) + 4) * 4 +
+             static_cast<size_t>(M) * (static_cast<size_t>(p.n_strm_tiles) + 4) * 4 +
              static_cast<size_t>(p.n_stat_tiles) * xt * 4 * p.n_strm_tiles +
              static_cast<size_t>(M) * n_sub * (topk_candcap(K, n_sub) * 4 + 4) + 8192;
     }

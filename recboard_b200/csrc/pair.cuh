@@ -19,7 +19,7 @@
 //             outputs A = sum_i P_ij u_i -> dW (and row sums -> dbias)
 // The label one-hot never enters the tiles: dU subtracts w_label and dW subtracts u_i exactly, in
 // fp32, in the finishing kernels (simt.cuh).
-// A per-streamed-row fp32 vector ("aux": bias*log2e of the streamed items in PASS_FWD, lse*log2e of the
+// A per-streamed-row fp32 vector ("aux": bias*log2e of the streamed items in PASS_FWD, -lse*log2e of the
 // streamed query rows in PASS_DW) rides along with every streamed tile as a 512-byte bulk copy.
 #pragma once
 #include "ptx.cuh"
@@ -29,6 +29,12 @@ namespace rb {
 enum : int { PASS_FWD = 0, PASS_DW = 1 };
 constexpr int PAIR_THREADS = 320;
 constexpr float PAIR_RESCALE_TH = 16.f;  // log2 units: P stays below 2^16 before the row reference moves
+// Every PAIR_POLY_EVERY-th element pair takes its exponentials from the FMA pipe (ex2_poly2) instead of
+// the MUFU unit; 0 = all on MUFU.  At 3 the MUFU load drops by a third and the pipes are about level.
+#ifndef PAIR_POLY_EVERY
+#define PAIR_POLY_EVERY 3
+#endif
+__device__ __forceinline__ constexpr bool pair_use_poly(int i) { return PAIR_POLY_EVERY > 0 && (i % (PAIR_POLY_EVERY > 0 ? PAIR_POLY_EVERY : 1)) == PAIR_POLY_EVERY - 1; }
 
 struct PairArgs {
   int n_stat;        // valid rows of the stationary operand
@@ -40,7 +46,7 @@ struct PairArgs {
   int stat_pad;      // n_pair_tiles * 256 (row pitch of the per-row partial arrays)
   float scale;       // logits = scale * <u,w> + bias
   // per STREAMED row, padded to n_strm_tiles*128: FWD = bias*log2(e) (BIAS only, 0 padding),
-  //                                                DW  = lse*log2(e) (+inf padding => P = 0)
+  //                                                DW  = -lse*log2(e) (-inf padding => P = 0)
   const float* aux;
   const float* bias2_stat;  // DW with BIAS: bias*log2(e) of the stationary item rows
   // PASS_FWD outputs
@@ -343,42 +349,69 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
                 if (grow) m2 = cm2;
               }
             }
-            const float nm = -m2;
-            float ls[4] = {0.f, 0.f, 0.f, 0.f};
+            const uint64_t nm2 = pack2(-m2, -m2), c22 = pack2(c2, c2);
+            uint64_t ls2[2] = {0ull, 0ull};   // two packed running sums (4 fp32 lanes)
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
               uint32_t pk[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const float x0 = __uint_as_float(raw[ch * 32 + 2 * i]), x1 = __uint_as_float(raw[ch * 32 + 2 * i + 1]);
-                const float e0 = ex2_approx(C::BIAS ? x0 + nm : fmaf(x0, c2, nm));
-                const float e1 = ex2_approx(C::BIAS ? x1 + nm : fmaf(x1, c2, nm));
-                ls[i & 3] += e0 + e1;
+                const uint64_t xr = pack2(__uint_as_float(raw[ch * 32 + 2 * i]), __uint_as_float(raw[ch * 32 + 2 * i + 1]));
+                const uint64_t x2 = C::BIAS ? fadd2(xr, nm2) : ffma2(xr, c22, nm2);   // log2-domain argument
+                float e0, e1;
+                if (pair_use_poly(i)) {
+                  ex2_poly2(x2, e0, e1);
+                } else {
+                  float x0, x1;
+                  unpack2(x2, x0, x1);
+                  e0 = ex2_approx(x0);
+                  e1 = ex2_approx(x1);
+                }
+                ls2[i & 1] = fadd2(ls2[i & 1], pack2(e0, e1));
                 pk[i] = pack_bf16x2(e0, e1);
               }
               tmem_st16(t_sh + ch * 16, pk);
             }
-            l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+            {
+              float s0, s1, s2, s3;
+              unpack2(ls2[0], s0, s1);
+              unpack2(ls2[1], s2, s3);
+              l += (s0 + s1) + (s2 + s3);
+            }
           } else {
-            // P^T[item r][query row c] = 2^(s*c2 + bias2_r - lse2_c); lse2 = +inf beyond the last row => 0
-            float rs[4] = {0.f, 0.f, 0.f, 0.f};
+            // P^T[item r][query row c] = 2^(s*c2 + bias2_r + aux_c), aux_c = -lse2_c (-inf beyond the last row => 0)
+            const uint64_t c22 = pack2(c2, c2), nb2 = pack2(nb, nb);
+            uint64_t rs2[2] = {0ull, 0ull};
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
               uint32_t pk[16];
 #pragma unroll
-              for (int c4 = 0; c4 < 8; ++c4) {
-                const float4 w = aux4[h * 16 + ch * 8 + c4];
-                const float e0 = ex2_approx(fmaf(__uint_as_float(raw[ch * 32 + c4 * 4 + 0]), c2, nb - w.x));
-                const float e1 = ex2_approx(fmaf(__uint_as_float(raw[ch * 32 + c4 * 4 + 1]), c2, nb - w.y));
-                const float e2 = ex2_approx(fmaf(__uint_as_float(raw[ch * 32 + c4 * 4 + 2]), c2, nb - w.z));
-                const float e3 = ex2_approx(fmaf(__uint_as_float(raw[ch * 32 + c4 * 4 + 3]), c2, nb - w.w));
-                if (a.rowsum_out != nullptr) { rs[0] += e0; rs[1] += e1; rs[2] += e2; rs[3] += e3; }
-                pk[c4 * 2 + 0] = pack_bf16x2(e0, e1);
-                pk[c4 * 2 + 1] = pack_bf16x2(e2, e3);
+              for (int i = 0; i < 16; ++i) {
+                const float4 w = aux4[h * 16 + ch * 8 + (i >> 1)];
+                uint64_t off = (i & 1) ? pack2(w.z, w.w) : pack2(w.x, w.y);
+                if (C::BIAS) off = fadd2(off, nb2);
+                const uint64_t xr = pack2(__uint_as_float(raw[ch * 32 + 2 * i]), __uint_as_float(raw[ch * 32 + 2 * i + 1]));
+                const uint64_t x2 = ffma2(xr, c22, off);
+                float e0, e1;
+                if (pair_use_poly(i)) {
+                  ex2_poly2(x2, e0, e1);
+                } else {
+                  float x0, x1;
+                  unpack2(x2, x0, x1);
+                  e0 = ex2_approx(x0);
+                  e1 = ex2_approx(x1);
+                }
+                if (C::BIAS) rs2[i & 1] = fadd2(rs2[i & 1], pack2(e0, e1));   // row sums feed dbias only
+                pk[i] = pack_bf16x2(e0, e1);
               }
               tmem_st16(t_sh + ch * 16, pk);
             }
-            rowsum += (rs[0] + rs[1]) + (rs[2] + rs[3]);
+            if (C::BIAS) {
+              float s0, s1, s2, s3;
+              unpack2(rs2[0], s0, s1);
+              unpack2(rs2[1], s2, s3);
+              rowsum += (s0 + s1) + (s2 + s3);
+            }
           }
           tmem_st_wait();
           tc_fence_before();

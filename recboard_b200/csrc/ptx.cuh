@@ -256,6 +256,47 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// ---- packed fp32 pairs (sm_100 FFMA2 / FADD2: two fp32 lanes per instruction, 64-bit registers)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// 2^x for a packed pair on the FMA pipe instead of the MUFU unit (the softmax epilogues are MUFU-bound:
+// one ex2 per scored pair at 16/clk/SM is exactly the tensor pipe's pace at d = 128).  Cody-Waite split
+// x = n + f, f in [-0.5, 0.5] by the magic-number add, 2^f by a degree-3 minimax polynomial (max relative
+// error 7.5e-5, mean 5e-6 -- far inside the bf16 rounding the tile gets anyway), 2^n by an exponent add.
+// Inputs are clamped to >= -126 (=> results never underflow into garbage; -inf gives 2^-126 ~ 1e-38).
+__device__ __forceinline__ void ex2_poly2(uint64_t x, float& e0, float& e1) {
+  float x0, x1;
+  unpack2(x, x0, x1);
+  x = pack2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const uint64_t r = fadd2(x, pack2(12582912.f, 12582912.f));          // low mantissa bits = round(x)
+  const uint64_t rf = fadd2(r, pack2(-12582912.f, -12582912.f));       // round(x) as a float
+  const uint64_t f = ffma2(rf, pack2(-1.f, -1.f), x);                   // x - round(x)
+  uint64_t p = ffma2(f, pack2(0.0551716648042202f, 0.0551716648042202f), pack2(0.2426111251115799f, 0.2426111251115799f));
+  p = ffma2(p, f, pack2(0.6932609677314758f, 0.6932609677314758f));
+  p = ffma2(p, f, pack2(0.9999280571937561f, 0.9999280571937561f));
+  float p0, p1, r0, r1;
+  unpack2(p, p0, p1);
+  unpack2(r, r0, r1);
+  e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(r0) << 23));
+  e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(r1) << 23));
+}
+
 // {2^x0 (low half), 2^x1 (high half)} as packed bf16: one MUFU op for two exponentials.
 // x = -inf gives exactly 0.  (A kind::f16 MMA needs A and B in the same 16-bit format, and the
 // streamed operand is bf16, so the softmax tile is bf16 too.)

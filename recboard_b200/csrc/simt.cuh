@@ -97,7 +97,8 @@ __global__ void normalize_rows_kernel(const TI* __restrict__ x, TO* __restrict__
 // Stable LSD radix sort of (key = row id, val = position) pairs, 8 bits per pass.
 // One warp owns a contiguous chunk; ranks inside the chunk come from __match_any_sync so equal
 // keys keep their input order (=> the segment sums below run in a fixed order).
-constexpr int RS_CHUNK = 2048;
+constexpr int RS_CHUNK = 1024;
+constexpr int RS_SCATTER_WARPS = 4;   // chunks (one warp each) per block of the scatter pass
 
 __global__ void rs_hist_kernel(const uint32_t* __restrict__ keys, int n, int shift, uint32_t* __restrict__ hist,
                                int n_chunks) {
@@ -133,9 +134,11 @@ __global__ void rs_scan_kernel(uint32_t* __restrict__ hist, int total) {
 __global__ void rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                   uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n, int shift,
                                   const uint32_t* __restrict__ offs, int n_chunks) {
-  __shared__ uint32_t base[256];
-  const int chunk = blockIdx.x;  // one warp per block
-  const int lane = threadIdx.x;
+  __shared__ uint32_t base_s[RS_SCATTER_WARPS][256];
+  const int chunk = blockIdx.x * RS_SCATTER_WARPS + (threadIdx.x >> 5);  // one warp per chunk
+  const int lane = threadIdx.x & 31;
+  if (chunk >= n_chunks) return;
+  uint32_t* base = base_s[threadIdx.x >> 5];
   for (int i = lane; i < 256; i += 32) base[i] = offs[i * n_chunks + chunk];
   __syncwarp();
   const int beg = chunk * RS_CHUNK, end = min(n, beg + RS_CHUNK);
@@ -156,57 +159,149 @@ __global__ void rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const ui
 }
 
 __global__ void rs_init_kernel(const int64_t* __restrict__ idx, long long base, uint32_t* __restrict__ keys,
-                               uint32_t* __restrict__ vals, int n, long long n_rows) {
+                               uint32_t* __restrict__ vals, int n, long long n_rows, long long padding_idx) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     const long long r = idx[i] - base;
-    keys[i] = (r >= 0 && r < n_rows) ? static_cast<uint32_t>(r) : static_cast<uint32_t>(n_rows);  // invalid ids sort last, skipped
+    // invalid ids and the padding row sort last and are skipped
+    keys[i] = (r >= 0 && r < n_rows && r != padding_idx) ? static_cast<uint32_t>(r) : static_cast<uint32_t>(n_rows);
     vals[i] = static_cast<uint32_t>(i);
   }
 }
 
-// One warp per sorted position that starts a run of equal row ids; sums the run in order.
+// Segment sums over the sorted (row id, position) list, 32 sorted positions per warp (a "block").
 // (reference: embedding_dense_backward, autograd of SASRec/main.py:183 run at :249)
+//   pass 1  every warp walks its 32 entries in order (row loads batched 8 deep, adds in order).  A run
+//           of equal ids that lies inside the block is added to the table by this warp alone; a run that
+//           began in an earlier block goes to lead[b], one that starts here and continues goes to trail[b].
+//   pass 2  the warp whose block holds the START of a split run adds trail[b] + lead[b+1] + ... in block
+//           order and updates the table.  Hot rows (Zipf heads, thousands of entries) are thus summed by
+//           many warps in parallel, yet in a fixed order => bitwise reproducible.
 // `alpha * (alpha_dev ? *alpha_dev : 1)` scales the added rows (1 for the plain embedding backward; the
 // CE backward uses it to subtract the one-hot rows, dW[label_i] -= g*scale*u_i, exactly in fp32);
 // cnt_out[key] += cnt_alpha * (alpha_dev) * run length (the matching dbias term), nullable.
+constexpr int SEG_BLOCK = 32;
+
 template <typename T>
-__global__ void scatter_segments_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ perm,
-                                        const T* __restrict__ grad_out, float* __restrict__ grad_table, int n, int d,
-                                        long long n_rows, long long padding_idx, float alpha,
-                                        const float* __restrict__ alpha_dev, float* __restrict__ cnt_out, float cnt_alpha) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (w >= n) return;
-  const uint32_t key = keys[w];
-  if (static_cast<long long>(key) >= n_rows || static_cast<long long>(key) == padding_idx) return;
-  if (w > 0 && keys[w - 1] == key) return;
-  const float adev = (alpha_dev != nullptr) ? __ldg(alpha_dev) : 1.f;
-  alpha *= adev;
-  if (cnt_out != nullptr && lane == 0) {
-    int run = 0;
-    for (int e = w; e < n && keys[e] == key; ++e) ++run;
-    cnt_out[key] += cnt_alpha * adev * static_cast<float>(run);
+__device__ __forceinline__ float4 seg_load4(const T* p) {
+  if constexpr (sizeof(T) == 4) {
+    return *reinterpret_cast<const float4*>(p);
+  } else {
+    const uint2 raw = *reinterpret_cast<const uint2*>(p);
+    return make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xFFFF0000u),
+                       __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xFFFF0000u));
   }
-  for (int c = lane * 4; c < d; c += 128) {  // d % 4 == 0
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+scatter_segments_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ perm,
+                        const T* __restrict__ grad_out, float* __restrict__ grad_table, int n, int d, long long n_rows,
+                        float alpha, const float* __restrict__ alpha_dev, float* __restrict__ cnt_out, float cnt_alpha,
+                        float* __restrict__ lead, float* __restrict__ trail) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int p0 = b * SEG_BLOCK;
+  if (p0 >= n) return;
+  const int cnt = min(SEG_BLOCK, n - p0);
+  const uint32_t key = (lane < cnt) ? keys[p0 + lane] : 0xFFFFFFFFu;
+  const uint32_t first_key = __shfl_sync(0xffffffffu, key, 0);
+  if (static_cast<long long>(first_key) >= n_rows) return;  // sorted: nothing valid in this block
+  const uint32_t my_perm = (lane < cnt) ? perm[p0 + lane] : 0u;
+  const uint32_t prev_key = (p0 > 0) ? keys[p0 - 1] : 0xFFFFFFFFu;
+  const uint32_t next_key = (p0 + SEG_BLOCK < n) ? keys[p0 + SEG_BLOCK] : 0xFFFFFFFFu;
+  const uint32_t up = __shfl_up_sync(0xffffffffu, key, 1);
+  const bool head = (lane == 0) || (key != up);
+  const uint32_t heads = __ballot_sync(0xffffffffu, head && lane < cnt);
+  const uint32_t valid = __ballot_sync(0xffffffffu, lane < cnt && static_cast<long long>(key) < n_rows);
+  const float adev = (alpha_dev != nullptr) ? __ldg(alpha_dev) : 1.f;
+  const float al = alpha * adev;
+
+  for (int c0 = 0; c0 < d; c0 += 128) {  // d % 4 == 0
+    const int c = c0 + lane * 4;
+    const bool col_ok = c < d;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int e = w; e < n && keys[e] == key; ++e) {
-      const T* src = grad_out + static_cast<long long>(perm[e]) * d + c;
-      if constexpr (sizeof(T) == 4) {
-        const float4 v = *reinterpret_cast<const float4*>(src);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-      } else {
-        const uint2 raw = *reinterpret_cast<const uint2*>(src);
-        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
-        const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
-        acc.x += __low2float(a); acc.y += __high2float(a); acc.z += __low2float(b); acc.w += __high2float(b);
+    for (int e0 = 0; e0 < cnt; e0 += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint32_t pr = __shfl_sync(0xffffffffu, my_perm, (e0 + u) & 31);
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok && ((valid >> (e0 + u)) & 1u)) v[u] = seg_load4<T>(grad_out + static_cast<long long>(pr) * d + c);
       }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = e0 + u;
+        if (e < cnt && ((valid >> e) & 1u)) {
+          acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+          const bool run_ends = (e + 1 == cnt) || ((heads >> (e + 1)) & 1u);
+          if (run_ends) {  // warp-uniform
+            const uint32_t k = __shfl_sync(0xffffffffu, key, e);
+            const int j0 = 31 - __clz(heads & ((2u << e) - 1u));            // start of this run inside the block
+            const bool began_before = (j0 == 0) && (k == prev_key);
+            const bool continues = (e + 1 == SEG_BLOCK) && (k == next_key);
+            if (col_ok) {
+              if (began_before) {
+                *reinterpret_cast<float4*>(lead + static_cast<long long>(b) * d + c) = acc;
+              } else if (continues) {
+                *reinterpret_cast<float4*>(trail + static_cast<long long>(b) * d + c) = acc;
+              } else {
+                float4* dst = reinterpret_cast<float4*>(grad_table + static_cast<long long>(k) * d + c);
+                float4 o = *dst;
+                o.x = fmaf(al, acc.x, o.x); o.y = fmaf(al, acc.y, o.y); o.z = fmaf(al, acc.z, o.z); o.w = fmaf(al, acc.w, o.w);
+                *dst = o;
+              }
+            }
+            if (c0 == 0 && cnt_out != nullptr && lane == 0 && !began_before && !continues)
+              cnt_out[k] += cnt_alpha * adev * static_cast<float>(e - j0 + 1);
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+    }
+  }
+}
+
+// pass 2: runs split over several blocks (see above).  One warp per block; only the block holding the
+// start of a split run does work.
+__global__ void __launch_bounds__(128)
+scatter_split_runs_kernel(const uint32_t* __restrict__ keys, float* __restrict__ grad_table, int n, int d, long long n_rows,
+                          float alpha, const float* __restrict__ alpha_dev, float* __restrict__ cnt_out, float cnt_alpha,
+                          const float* __restrict__ lead, const float* __restrict__ trail) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int p0 = b * SEG_BLOCK;
+  if (p0 + SEG_BLOCK >= n) return;  // a run can only continue out of a full block that has a successor
+  const uint32_t key = keys[p0 + SEG_BLOCK - 1];
+  if (static_cast<long long>(key) >= n_rows || keys[p0 + SEG_BLOCK] != key) return;   // no run leaves this block
+  const uint32_t kl = keys[p0 + lane];
+  const uint32_t same = __ballot_sync(0xffffffffu, kl == key);
+  const int j0 = __ffs(same) - 1;
+  if (j0 == 0 && p0 > 0 && keys[p0 - 1] == key) return;  // the run began earlier: not the owner
+  // last block of the run and the run's length
+  int nb = b + 1;
+  while (true) {
+    const int q0 = nb * SEG_BLOCK;
+    if (q0 + SEG_BLOCK < n && keys[q0 + SEG_BLOCK - 1] == key && keys[q0 + SEG_BLOCK] == key) ++nb; else break;
+  }
+  const int q0 = nb * SEG_BLOCK;
+  const int qi = q0 + lane;
+  const uint32_t tail_same = __ballot_sync(0xffffffffu, qi < n && keys[qi] == key);
+  const int run_len = (SEG_BLOCK - j0) + (nb - b - 1) * SEG_BLOCK + __popc(tail_same);
+  const float adev = (alpha_dev != nullptr) ? __ldg(alpha_dev) : 1.f;
+  const float al = alpha * adev;
+  for (int c = lane * 4; c < d; c += 128) {
+    float4 acc = *reinterpret_cast<const float4*>(trail + static_cast<long long>(b) * d + c);
+    for (int x = b + 1; x <= nb; ++x) {
+      const float4 v = *reinterpret_cast<const float4*>(lead + static_cast<long long>(x) * d + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     float4* dst = reinterpret_cast<float4*>(grad_table + static_cast<long long>(key) * d + c);
     float4 o = *dst;
-    o.x = fmaf(alpha, acc.x, o.x); o.y = fmaf(alpha, acc.y, o.y); o.z = fmaf(alpha, acc.z, o.z); o.w = fmaf(alpha, acc.w, o.w);
+    o.x = fmaf(al, acc.x, o.x); o.y = fmaf(al, acc.y, o.y); o.z = fmaf(al, acc.z, o.z); o.w = fmaf(al, acc.w, o.w);
     *dst = o;
   }
+  if (cnt_out != nullptr && lane == 0) cnt_out[key] += cnt_alpha * adev * static_cast<float>(run_len);
 }
 
 // ------------------------------------------------------------------- operand preparation
@@ -224,10 +319,10 @@ __global__ void labels_local_kernel(const int64_t* __restrict__ labels, long lon
   }
 }
 
-// lse (natural log) -> lse * log2(e), padded with +inf (=> exp2(x - inf) = 0 for padding rows)
+// lse (natural log) -> -lse * log2(e), padded with -inf (=> exp2(x + aux) = 0 for padding rows)
 __global__ void lse2_kernel(const float* __restrict__ lse, float* __restrict__ out, int m, int m_pad) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < m_pad) out[i] = (i < m) ? lse[i] * 1.4426950408889634f : INFINITY;
+  if (i < m_pad) out[i] = (i < m) ? -lse[i] * 1.4426950408889634f : -INFINITY;
 }
 
 // fp32 (rows,d) -> [hi | lo] (rows, 2*dpad): hi = x with the 13 low mantissa bits cleared (exactly
@@ -257,10 +352,10 @@ __global__ void csr_local_kernel(const int64_t* __restrict__ crow, const int64_t
   }
 }
 
-// bias (N) -> bias*log2(e), zero-padded to n_pad
+// bias (N, null = zeros) -> bias*log2(e), zero-padded to n_pad
 __global__ void bias2_kernel(const float* __restrict__ bias, float* __restrict__ out, long long n, long long n_pad) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n_pad) out[i] = (i < n) ? bias[i] * 1.4426950408889634f : 0.f;
+  if (i < n_pad) out[i] = (i < n && bias != nullptr) ? bias[i] * 1.4426950408889634f : 0.f;
 }
 
 __device__ __forceinline__ float4 load4_as_float(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -443,12 +538,11 @@ __device__ __forceinline__ T warp_blocked_get(const T (&v)[E], int idx) {
 }
 
 // ---- top-K pass 2a: per row, the K-th largest CLEAN tile maximum tau (NaN marks a dirty tile, one that
-// holds a seen id) and, for the fallback, the list of tiles that can hold a top-K member: every tile
-// with max > tau (at most K-1 of them), the first K tiles with max == tau (lowest ids first: the tie
-// rule) and every dirty tile, in ascending tile order.  One warp per row.
+// holds a seen id: it never supports the threshold).  One warp per row; the next chunk of tile maxima is
+// in flight while the current one is examined, and a chunk is only sorted when it can raise tau.
 template <int E>
-__global__ void tilemax_select_kernel(const float* __restrict__ T, int n_tiles, long long n_rows, int K, int selcap,
-                                      int* __restrict__ sel, int* __restrict__ selcnt, float* __restrict__ tau_out) {
+__global__ void tilemax_select_kernel(const float* __restrict__ T, int n_tiles, long long n_rows, int K,
+                                      float* __restrict__ tau_out) {
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n_rows) return;
@@ -457,14 +551,21 @@ __global__ void tilemax_select_kernel(const float* __restrict__ T, int n_tiles, 
 #pragma unroll
   for (int e = 0; e < E; ++e) best[e] = -INFINITY;
   float tau = -INFINITY;
+  float nxt[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = e * 32 + lane;
+    nxt[e] = (i < n_tiles) ? __ldg(t + i) : -INFINITY;
+  }
   for (int base = 0; base < n_tiles; base += 32 * E) {
     float cur[E];
     bool any = false;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-      const int i = base + e * 32 + lane;
-      cur[e] = (i < n_tiles) ? __ldg(t + i) : -INFINITY;
-      if (cur[e] != cur[e]) cur[e] = -INFINITY;  // dirty tile (holds a seen id): never supports the threshold
+      cur[e] = nxt[e];
+      const int i = base + 32 * E + e * 32 + lane;
+      nxt[e] = (i < n_tiles) ? __ldg(t + i) : -INFINITY;
+      if (cur[e] != cur[e]) cur[e] = -INFINITY;  // dirty tile
       any |= cur[e] > tau;
     }
     if (!__any_sync(0xffffffffu, any)) continue;
@@ -473,23 +574,6 @@ __global__ void tilemax_select_kernel(const float* __restrict__ T, int n_tiles, 
     tau = warp_blocked_get<float, E>(best, K - 1);
   }
   if (lane == 0) tau_out[row] = tau;  // -inf when fewer than K clean tiles exist
-  int cnt = 0, eq_taken = 0;
-  const uint32_t lt = (1u << lane) - 1u;
-  for (int base = 0; base < n_tiles; base += 32) {
-    const int i = base + lane;
-    const float v = (i < n_tiles) ? __ldg(t + i) : -INFINITY;
-    const bool gt = v > tau;
-    const bool eq = (v == tau) && (v > -INFINITY);
-    const bool dirty = v != v;  // may hold unseen items of any score: always part of the fallback's tile list
-    const uint32_t eqm = __ballot_sync(0xffffffffu, eq);
-    const bool take = gt || dirty || (eq && (eq_taken + __popc(eqm & lt) < K));
-    eq_taken += __popc(eqm);
-    const uint32_t m = __ballot_sync(0xffffffffu, take);
-    const int pos = cnt + __popc(m & lt);
-    if (take && pos < selcap) sel[row * selcap + pos] = i;
-    cnt += __popc(m);
-  }
-  if (lane == 0) selcnt[row] = cnt > selcap ? -1 : cnt;  // -1: list overflow, the fallback scans every tile
 }
 
 // ---- flag table of the candidate sweep: flag[g][t] != 0 iff some row of the 32-row group g (= one
@@ -629,13 +713,14 @@ topk_from_groups_kernel(const TW* __restrict__ U, const TW* __restrict__ W, cons
   }
 }
 
-// ---- top-K fallback (rows flagged in `only`; all rows when `only` is null): re-score the selected tiles of a row exactly (fp32 FMA over the stored operands),
+// ---- top-K fallback (rows flagged in `only`; all rows when `only` is null): re-score every tile of the row whose
+// maximum reaches tau (or is unknown: dirty) exactly (fp32 FMA over the stored operands),
 // skip seen ids, keep the K best by (score desc, id asc).  One warp per row; lane <-> item.
 template <typename TW, int E>
 __global__ void __launch_bounds__(128)
 topk_refine_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const float* __restrict__ bias, float scale, int d,
                    long long n_rows, int n_items, const int* __restrict__ seen_crow, const int* __restrict__ seen_col,
-                   const int* __restrict__ sel, const int* __restrict__ selcnt, int selcap, int K, int id_add,
+                   const float* __restrict__ tmax, const float* __restrict__ tau, int K, int id_add,
                    float* __restrict__ out_vals, int* __restrict__ out_ids, const int* __restrict__ only) {
   __shared__ __align__(16) float u_s[4][256];
   __shared__ unsigned long long cand_s[4][256];
@@ -656,8 +741,8 @@ topk_refine_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const flo
   int ncand = 0;
   const uint32_t lt = (1u << lane) - 1u;
   const int n_tiles = (n_items + 127) / 128;
-  const int ns_raw = selcnt[row];
-  const int ns = ns_raw < 0 ? n_tiles : ns_raw;
+  const float* trow = tmax + row * n_tiles;
+  const float tau_r = tau[row];   // -inf (fewer than K clean tiles): every tile is scanned
 
   auto flush = [&]() {
     for (int base = 0; base < ncand; base += 32 * E) {
@@ -675,8 +760,13 @@ topk_refine_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const flo
     __syncwarp();
   };
 
-  for (int si = 0; si < ns; ++si) {
-    const int tile = ns_raw < 0 ? si : sel[row * selcap + si];
+  for (int tb = 0; tb < n_tiles; tb += 32) {
+   // tiles that can hold a top-K member: maximum >= tau, or dirty (NaN: holds a seen id, maximum unknown)
+   const float tv = (tb + lane < n_tiles) ? __ldg(trow + tb + lane) : -INFINITY;
+   uint32_t tmask = __ballot_sync(0xffffffffu, (tb + lane < n_tiles) && (tv >= tau_r || tv != tv));
+   while (tmask) {
+    const int tile = tb + __ffs(tmask) - 1;
+    tmask &= tmask - 1;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     int item[4];
     const TW* wrow[4];
@@ -729,6 +819,7 @@ topk_refine_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const flo
       __syncwarp();
       if (ncand > 256 - 32) flush();
     }
+   }
   }
   flush();
 #pragma unroll
