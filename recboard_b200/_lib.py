@@ -7,11 +7,12 @@ library is missing, or the device is not an sm_100 part, calls raise ``RuntimeEr
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import torch
 
-_SO = Path(__file__).resolve().parent / "_C" / "librecboard_b200.so"
+_SO = Path(__file__).resolve().parent / "_C" / ("librecboard_b200" + os.environ.get("RB_SO_SUFFIX", "") + ".so")
 
 DTYPE_F32, DTYPE_BF16 = 0, 1
 MODE_BF16, MODE_FP32X3 = 0, 1

@@ -8,7 +8,7 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 SRC = PKG / "csrc"
-OUT = PKG / "_C" / "librecboard_b200.so"
+OUT = PKG / "_C" / ("librecboard_b200" + os.environ.get("RB_SO_SUFFIX", "") + ".so")   # suffix: experiment builds
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 
@@ -29,6 +29,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         "-gencode", "arch=compute_100a,code=sm_100a",
         "-Xcompiler", "-fPIC", "-shared",
         "-Xptxas", "-v" if verbose else "-O3",
+        *os.environ.get("RB_EXTRA_NVCC_FLAGS", "").split(),
         "-o", str(OUT), str(SRC / "abi.cu"),
     ]
     r = subprocess.run(cmd, capture_output=True, text=True)
