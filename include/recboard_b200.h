@@ -57,6 +57,32 @@ int rb_scatter_add_rows(const void* grad_out, const int64_t* idx, float* grad_ta
                         int64_t n_rows, int d, int dtype, int64_t padding_idx, void* ws,
                         size_t ws_bytes, rb_stream_t stream);
 
+/* S[m,k] = scale * <U[m,:], table[idx[m,k],:]> (fp32), ids outside [0,n_rows) score 0.  The gathered
+ * (M,K,d) tensor is never materialised.  Replaces the gather + row-wise dot of every sampled / pool path:
+ * `itemEmbds[data[IUnseen]]` + einsum("BD,BKD->BK") (recommend_from_pool, SASRec/main.py:230-236,
+ * MF-BPR/main.py:106-109); `itemEmbds[cat(pos,negs)]` + einsum("MD,MKD->MK") (sampled softmax,
+ * HSTU/main.py:192-197); the BPR / BCE positive and negative logits (SASRec/main.py:203-206,
+ * MF-BPR/main.py:84-91).  Rows must be a multiple of 16 bytes. */
+int rb_gather_dot(const void* U, const void* table, const int64_t* idx, float scale, float* S, int64_t M,
+                  int64_t K, int64_t n_rows, int d, int dtype, rb_stream_t stream);
+
+/* Backward of rb_gather_dot for an upstream gradient G (M,K) fp32:
+ *   dU (M,d)          = scale * sum_k G[m,k] * table[idx[m,k],:]      (nullable)
+ *   dTable (n_rows,d) += scale * G[m,k] * U[m,:] at row idx[m,k]       (nullable; row padding_idx skipped;
+ *                        sorted segment sums => deterministic; workspace RB_OP_SCATTER_ADD with nnz = M*K)
+ * Replaces the autograd of the lines above (index backward + bmm backward). */
+int rb_gather_dot_bwd(const void* U, const void* table, const int64_t* idx, const float* G, float scale,
+                      float* dU, float* dTable, int64_t M, int64_t K, int64_t n_rows, int d, int dtype,
+                      int64_t padding_idx, void* ws, size_t ws_bytes, rb_stream_t stream);
+
+/* Y = A X for a CSR matrix A (n_rows x n_cols, int64 indices, fp32 values) and dense fp32 X (n_cols, d);
+ * optionally acc += beta * Y in the same pass (Y or acc may be NULL, not both).  Rows are summed in
+ * index order (deterministic).  Replaces the LightGCN propagation step
+ * `allEmbds = self.Adj @ allEmbds; avgEmbds += allEmbds / (self.num_layers + 1)` (LightGCN/main.py:83-85),
+ * the step in front of `reset_ranking_buffers`.  d % 4 == 0. */
+int rb_spmm_csr(const int64_t* crow, const int64_t* col, const float* val, const float* X, float* Y,
+                float* acc, float beta, int64_t n_rows, int64_t n_cols, int d, rb_stream_t stream);
+
 /* S = scale * U W^T + bias  (M,N) fp32.          replaces `torch.einsum("BD,ND->BN", ...)`
  * (SASRec/main.py:228; MF-BPR/main.py:104; LightGCN/main.py:120; HSTU/main.py:209) and
  * `self.fc(userEmbds)` (BERT4Rec/main.py:189).  Compatibility path: it materialises (M,N). */

@@ -77,6 +77,17 @@ def ce_loss(U, W, labels, bias=None, scale: float = 1.0) -> torch.Tensor:
     return F.cross_entropy(score_dense(U, W, bias, scale), labels, reduction="mean")
 
 
+def gather_dot(U, table, idx, scale: float = 1.0):
+    """``einsum("MD,MKD->MK", U, table[idx]) * scale`` -- the pool / sampled scoring lines
+    (SASRec/main.py:230-236, HSTU/main.py:192-197, MF-BPR/main.py:84-91,106-109)."""
+    return torch.einsum("MD,MKD->MK", U.float(), table.float()[idx]) * scale
+
+
+def spmm(A, X):
+    """``self.Adj @ allEmbds`` (LightGCN/main.py:83) on the host."""
+    return torch.sparse.mm(A, X.float()) if A.layout != torch.sparse_csr else A @ X.float()
+
+
 def normalize_rows(x, eps: float = 1e-12):
     """``F.normalize(x, dim=-1)`` -- the table / user normalisation of HSTU/main.py:180-184."""
     return torch.nn.functional.normalize(x.float(), dim=-1, eps=eps)

@@ -26,6 +26,9 @@ SIGNATURES = {
     "rb_gather_rows": (_i32, [_p, _p, _p, _i64, _i64, _i32, _i32, _p]),
     "rb_normalize_rows": (_i32, [_p, _p, _p, _i64, _i32, _i32, _i32, _f32, _p]),
     "rb_scatter_add_rows": (_i32, [_p, _p, _p, _i64, _i64, _i32, _i32, _i64, _p, _sz, _p]),
+    "rb_gather_dot": (_i32, [_p, _p, _p, _f32, _p, _i64, _i64, _i64, _i32, _i32, _p]),
+    "rb_gather_dot_bwd": (_i32, [_p, _p, _p, _p, _f32, _p, _p, _i64, _i64, _i64, _i32, _i32, _i64, _p, _sz, _p]),
+    "rb_spmm_csr": (_i32, [_p, _p, _p, _p, _p, _p, _f32, _i64, _i64, _i32, _p]),
     "rb_score_dense": (_i32, [_p, _p, _p, _f32, _p, _i64, _i64, _i32, _i32, _i32, _p, _sz, _p]),
     "rb_ce_fwd": (_i32, [_p, _p, _p, _f32, _p, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _sz, _p]),
     "rb_ce_du_finish": (_i32, [_p, _p, _p, _p, _p, _i64, _f32, _f32, _p, _i64, _i64, _i32, _i32, _p, _p]),

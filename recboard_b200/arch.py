@@ -10,6 +10,7 @@ freerec arch class in the bases) replaces only the hot-path lines:
     fit                 lines SASRec/main.py:217-219  -> ops.fused_ce        (no (M,N) logits)
     recommend_from_full lines SASRec/main.py:223-228  -> ops.score_dense     (strict-compat dense path)
     recommend_topk      (new) UniSRec/main.py:408-413 -> ops.topk_eval       (mask + top-K fused)
+    recommend_from_pool lines SASRec/main.py:230-236  -> ops.gather_dot      (no (B,K,D) gather)
 
 Every mixin states how the reference picks the query rows (U), the item table view (W), the labels
 and the optional bias / temperature; nothing else differs between the six models.
@@ -48,6 +49,15 @@ class FusedFullCatalogMixin:
         U, W, bias, scale, n_skip = self._eval_operands(data)
         S = ops.score_dense(U, W, bias=bias, scale=scale, precision=self.fused_precision)
         return S[:, n_skip:] if n_skip else S
+
+    def recommend_from_pool(self, data: Dict) -> torch.Tensor:
+        """Scores of the per-row candidate pool ``data[IUnseen]`` (B,K) -- the sampled-ranking protocol
+        (SASRec/main.py:230-236, MF-BPR/main.py:106-109) -- through the fused gather-dot: the (B,K,D)
+        gathered tensor of the reference is never built."""
+        U, W, bias, scale, n_skip = self._eval_operands(data)
+        pool = data[self.IUnseen] + n_skip
+        S = ops.gather_dot(U, W, pool, scale=scale)
+        return S if bias is None else S + bias[pool]
 
     @torch.no_grad()
     def recommend_topk(self, data: Dict, K: int, seen_crow: Optional[torch.Tensor] = None,
@@ -111,10 +121,32 @@ class HSTUFused(FusedFullCatalogMixin):
     here ``reset_ranking_buffers`` builds the normalised operand copy once per evaluation sweep
     (``ops.normalize_rows``, one HBM pass, optionally bf16) and ``_eval_operands`` reuses it.  A model
     that wants to skip the redundant per-batch table pass as well overrides ``encode_users``.
-    Its ``fit`` is sampled softmax (not full-catalog) and is left to the reference implementation."""
+    ``fit`` is sampled softmax over 1 positive + ``num_negs`` sampled negatives (HSTU/main.py:186-202): the
+    reference gathers an (M, 1+num_negs, D) tensor (~200 MB per step at the Beauty shape) and contracts it
+    row-wise; here ``ops.gather_dot`` scores the ids in place."""
 
-    def fit(self, data):  # keep the reference's sampled-softmax fit
-        return super(FusedFullCatalogMixin, self).fit(data)
+    #: softmax temperature; None = ``cfg.temperature`` of the reference module the model class comes from
+    fused_temperature: Optional[float] = None
+
+    def _temperature(self) -> float:
+        if self.fused_temperature is not None:
+            return float(self.fused_temperature)
+        for klass in type(self).__mro__:   # the reference keeps its config in a module-level ``cfg`` (HSTU/main.py:16-40)
+            fn = vars(klass).get("_sample_negatives") or vars(klass).get("encode")
+            cfg = getattr(fn, "__globals__", {}).get("cfg")
+            if cfg is not None and hasattr(cfg, "temperature"):
+                return float(cfg.temperature)
+        raise AttributeError("set fused_temperature: no cfg.temperature found for this model")
+
+    def fit(self, data):
+        userEmbds, itemEmbds = self.encode(data)
+        indices = data[self.ISeq] != self.PADDING_VALUE
+        userEmbds = userEmbds[indices]                                              # (M, D)
+        positives = data[self.IPos][indices].unsqueeze(-1)                          # (M, 1)
+        candidates = torch.cat((positives, self._sample_negatives(userEmbds)), dim=1)   # (M, 1 + num_negs)
+        logits = ops.gather_dot(userEmbds, itemEmbds, candidates, scale=1.0 / self._temperature())
+        labels = torch.zeros(logits.shape[0], dtype=torch.long, device=logits.device)   # the positive sits in column 0
+        return {"rec_loss": self.criterion(logits, labels)}
 
     def reset_ranking_buffers(self):
         sup = super()
@@ -154,6 +186,20 @@ class GenRecFused(FusedFullCatalogMixin):
         users = data[self.User]
         U = ops.gather_rows_raw(self._fused_user, users.reshape(-1).contiguous())  # "BKD" with K == 1
         return U, self._fused_item, None, 1.0, 0
+
+
+class LightGCNFused(GenRecFused):
+    """LightGCN: the propagation in front of the ranking buffers, ``allEmbds = self.Adj @ allEmbds`` x L with
+    the layer average (LightGCN/main.py:77-88), runs through ``ops.spmm`` (rb_spmm_csr; the symmetric
+    normalisation makes the backward the same product).  Everything after it is ``GenRecFused``."""
+
+    def encode(self):
+        allEmbds = torch.cat((self.User.embeddings.weight, self.Item.embeddings.weight), dim=0)
+        avgEmbds = allEmbds / (self.num_layers + 1)
+        for _ in range(self.num_layers):
+            allEmbds = ops.spmm(self.Adj, allEmbds, symmetric=True)
+            avgEmbds = avgEmbds + allEmbds / (self.num_layers + 1)
+        return torch.split(avgEmbds, (self.User.count, self.Item.count))
 
 
 def normalized_table(weight: torch.Tensor, num_pads: int = 1, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:

@@ -293,7 +293,7 @@ static size_t scatter_ws_bytes(long long n_idx, int d) {
 static int scatter_add_impl(const void* grad_out, const int64_t* idx, long long idx_base, float* grad_table,
                             int64_t n_idx, int64_t n_rows, int d, int dtype, int64_t padding_idx, float alpha,
                             const float* alpha_dev, float* cnt_out, float cnt_alpha, void* ws, size_t ws_bytes,
-                            cudaStream_t st) {
+                            cudaStream_t st, int row_div = 1, const float* ew = nullptr) {
   if (!grad_out || !idx || !grad_table) return fail(RB_E_ARG, "null pointer");
   if (n_idx < 0 || n_rows <= 0 || d <= 0 || d % 4) return fail(RB_E_ARG, "bad shape (d must be a multiple of 4)");
   if (n_idx >= (1ll << 31) || n_rows >= (1ll << 32) - 1) return fail(RB_E_ARG, "n_idx/n_rows too large");
@@ -323,9 +323,9 @@ static int scatter_add_impl(const void* grad_out, const int64_t* idx, long long 
   }
   const int grid = (seg_blocks + 3) / 4;   // 4 warps (blocks of 32 sorted positions) per CTA
   if (dtype == RB_DTYPE_BF16)
-    scatter_segments_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(k0, v0, static_cast<const __nv_bfloat16*>(grad_out), grad_table, n, d, n_rows, alpha, alpha_dev, cnt_out, cnt_alpha, lead, trail);
+    scatter_segments_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(k0, v0, static_cast<const __nv_bfloat16*>(grad_out), grad_table, n, d, n_rows, alpha, alpha_dev, cnt_out, cnt_alpha, lead, trail, row_div, ew);
   else
-    scatter_segments_kernel<float><<<grid, 128, 0, st>>>(k0, v0, static_cast<const float*>(grad_out), grad_table, n, d, n_rows, alpha, alpha_dev, cnt_out, cnt_alpha, lead, trail);
+    scatter_segments_kernel<float><<<grid, 128, 0, st>>>(k0, v0, static_cast<const float*>(grad_out), grad_table, n, d, n_rows, alpha, alpha_dev, cnt_out, cnt_alpha, lead, trail, row_div, ew);
   RB_LAUNCH_CHECK("scatter_segments_kernel");
   scatter_split_runs_kernel<<<grid, 128, 0, st>>>(k0, grad_table, n, d, n_rows, alpha, alpha_dev, cnt_out, cnt_alpha, lead, trail);
   RB_LAUNCH_CHECK("scatter_split_runs_kernel");
@@ -337,6 +337,76 @@ extern "C" int rb_scatter_add_rows(const void* grad_out, const int64_t* idx, flo
   DevInfo dv; if (int r = get_dev(dv)) return r;
   return scatter_add_impl(grad_out, idx, 0, grad_table, n_idx, n_rows, d, dtype, padding_idx, 1.f, nullptr, nullptr, 0.f,
                           ws, ws_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ========================================================================= gather-dot
+static int gather_dot_gl(int d, int dtype) {
+  const int vpr = d / (dtype == RB_DTYPE_BF16 ? 8 : 4);
+  int gl = 1;
+  while (gl < vpr && gl < 32) gl <<= 1;
+  return gl;
+}
+static int gather_dot_check(const void* U, const void* table, const int64_t* idx, int64_t M, int64_t K, int64_t n_rows,
+                            int d, int dtype) {
+  if (!U || !table || !idx) return fail(RB_E_ARG, "null pointer");
+  if (M < 0 || K <= 0 || K >= (1ll << 31) || n_rows <= 0 || d <= 0) return fail(RB_E_ARG, "bad shape M=%lld K=%lld d=%d", (long long)M, (long long)K, d);
+  if (dtype != RB_DTYPE_BF16 && dtype != RB_DTYPE_F32) return fail(RB_E_ARG, "unknown dtype %d", dtype);
+  if (d % (dtype == RB_DTYPE_BF16 ? 8 : 4)) return fail(RB_E_ALIGN, "rows must be a multiple of 16 bytes");
+  if ((reinterpret_cast<uintptr_t>(U) | reinterpret_cast<uintptr_t>(table)) & 15) return fail(RB_E_ALIGN, "U/table must be 16-byte aligned");
+  return 0;
+}
+extern "C" int rb_gather_dot(const void* U, const void* table, const int64_t* idx, float scale, float* S, int64_t M,
+                             int64_t K, int64_t n_rows, int d, int dtype, rb_stream_t stream) {
+  DevInfo dv; if (int r = get_dev(dv)) return r;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (int r = gather_dot_check(U, table, idx, M, K, n_rows, d, dtype)) return r;
+  if (!S) return fail(RB_E_ARG, "null output");
+  if (M == 0) return 0;
+  const int grid = static_cast<int>((M * 32 + 255) / 256), gl = gather_dot_gl(d, dtype);
+  if (dtype == RB_DTYPE_BF16)
+    gather_dot_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(U), static_cast<const __nv_bfloat16*>(table), idx, scale, S, M, (int)K, n_rows, d, gl);
+  else
+    gather_dot_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(U), static_cast<const float*>(table), idx, scale, S, M, (int)K, n_rows, d, gl);
+  RB_LAUNCH_CHECK("gather_dot_kernel");
+  return 0;
+}
+extern "C" int rb_gather_dot_bwd(const void* U, const void* table, const int64_t* idx, const float* G, float scale,
+                                 float* dU, float* dTable, int64_t M, int64_t K, int64_t n_rows, int d, int dtype,
+                                 int64_t padding_idx, void* ws, size_t ws_bytes, rb_stream_t stream) {
+  DevInfo dv; if (int r = get_dev(dv)) return r;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (int r = gather_dot_check(U, table, idx, M, K, n_rows, d, dtype)) return r;
+  if (!G) return fail(RB_E_ARG, "null upstream gradient");
+  if (M == 0) return 0;
+  if (dU) {
+    const int grid = static_cast<int>((M * 32 + 255) / 256), gl = gather_dot_gl(d, dtype);
+    if (dtype == RB_DTYPE_BF16)
+      gather_dot_du_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(table), idx, G, scale, dU, M, (int)K, n_rows, d, gl);
+    else
+      gather_dot_du_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(table), idx, G, scale, dU, M, (int)K, n_rows, d, gl);
+    RB_LAUNCH_CHECK("gather_dot_du_kernel");
+  }
+  if (dTable)  // dTable[idx[m,k]] += scale * G[m,k] * U[m]: the sorted, deterministic scatter with per-entry weights
+    return scatter_add_impl(U, idx, 0, dTable, M * K, n_rows, d, dtype, padding_idx, scale, nullptr, nullptr, 0.f, ws, ws_bytes,
+                            st, static_cast<int>(K), G);
+  return 0;
+}
+
+// =============================================================================== SpMM
+extern "C" int rb_spmm_csr(const int64_t* crow, const int64_t* col, const float* val, const float* X, float* Y,
+                           float* acc, float beta, int64_t n_rows, int64_t n_cols, int d, rb_stream_t stream) {
+  DevInfo dv; if (int r = get_dev(dv)) return r;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!crow || !col || !val || !X || (!Y && !acc)) return fail(RB_E_ARG, "null pointer");
+  if (n_rows < 0 || n_cols <= 0 || d <= 0 || d % 4) return fail(RB_E_ARG, "bad shape (d must be a multiple of 4)");
+  if ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(acc)) & 15) return fail(RB_E_ALIGN, "X/Y/acc must be 16-byte aligned");
+  if (n_rows == 0) return 0;
+  int gl = 1;
+  while (gl < d / 4 && gl < 32) gl <<= 1;
+  const long long warps = (n_rows + (32 / gl) - 1) / (32 / gl);
+  spmm_csr_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, st>>>(crow, col, val, X, Y, acc, beta, n_rows, n_cols, d, gl);
+  RB_LAUNCH_CHECK("spmm_csr_kernel");
+  return 0;
 }
 
 // ======================================================================= score dense

@@ -93,6 +93,146 @@ __global__ void normalize_rows_kernel(const TI* __restrict__ x, TO* __restrict__
   }
 }
 
+// -------------------------------------------------------------------------- gather-dot
+// S[m,k] = scale * <U[m,:], table[idx[m,k],:]> without materialising the gathered (M,K,d) tensor
+// (reference: itemEmbds[data[IUnseen]] + einsum("BD,BKD->BK"), SASRec/main.py:230-236; sampled softmax
+// itemEmbds[cat(pos,negs)] + einsum("MD,MKD->MK"), HSTU/main.py:192-197; BPR/BCE logits, SASRec/main.py:203-206).
+// One warp per query row; a group of GL lanes (GL = 16-byte vectors per row, rounded up to a power of
+// two, <= 32) covers one table row, so 32/GL gathered rows are in flight per warp and every load is a
+// full 16-byte vector.  Ids outside [0, n_rows) score 0.
+template <typename T>
+__device__ __forceinline__ void load_vec_as_float(const T* p, float (&f)[8]) {
+  if constexpr (sizeof(T) == 2) {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+    f[0] = __uint_as_float(raw.x << 16); f[1] = __uint_as_float(raw.x & 0xFFFF0000u);
+    f[2] = __uint_as_float(raw.y << 16); f[3] = __uint_as_float(raw.y & 0xFFFF0000u);
+    f[4] = __uint_as_float(raw.z << 16); f[5] = __uint_as_float(raw.z & 0xFFFF0000u);
+    f[6] = __uint_as_float(raw.w << 16); f[7] = __uint_as_float(raw.w & 0xFFFF0000u);
+  } else {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = f[5] = f[6] = f[7] = 0.f;
+  }
+}
+template <typename T> struct VecElems { static constexpr int value = 16 / sizeof(T); };
+
+template <typename T>
+__global__ void gather_dot_kernel(const T* __restrict__ U, const T* __restrict__ table, const int64_t* __restrict__ idx,
+                                  float scale, float* __restrict__ S, long long M, int K, long long n_rows, int d, int gl) {
+  constexpr int VE = VecElems<T>::value;
+  const long long m = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (m >= M) return;
+  const int vpr = d / VE;                 // 16-byte vectors per row
+  const int sub = lane & (gl - 1), slot = lane / gl, nslot = 32 / gl;
+  for (int k0 = 0; k0 < K; k0 += nslot) {
+    const int k = k0 + slot;
+    long long row = -1;
+    if (k < K) row = __ldg(idx + m * K + k);
+    const bool ok = row >= 0 && row < n_rows;
+    float acc = 0.f;
+    for (int c = sub; c < vpr; c += gl) {
+      float u[8], w[8];
+      load_vec_as_float<T>(U + m * d + c * VE, u);
+      if (ok) load_vec_as_float<T>(table + row * d + c * VE, w);
+      else { for (int e = 0; e < 8; ++e) w[e] = 0.f; }
+#pragma unroll
+      for (int e = 0; e < VE; ++e) acc = fmaf(u[e], w[e], acc);
+    }
+    for (int o = gl >> 1; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (sub == 0 && k < K) S[m * K + k] = acc * scale;
+  }
+}
+
+// dU[m,:] = scale * sum_k G[m,k] * table[idx[m,k],:]   (k ascending inside a slot, slots combined in a fixed
+// butterfly order => deterministic)
+template <typename T>
+__global__ void gather_dot_du_kernel(const T* __restrict__ table, const int64_t* __restrict__ idx, const float* __restrict__ G,
+                                     float scale, float* __restrict__ dU, long long M, int K, long long n_rows, int d, int gl) {
+  constexpr int VE = VecElems<T>::value;
+  const long long m = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (m >= M) return;
+  const int vpr = d / VE;
+  const int sub = lane & (gl - 1), slot = lane / gl, nslot = 32 / gl;
+  for (int c0 = 0; c0 < vpr; c0 += gl) {   // warp-uniform trip count (the shuffles below need every lane)
+    const int c = c0 + sub;
+    const bool c_ok = c < vpr;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int k = slot; k < K; k += nslot) {
+      const long long row = __ldg(idx + m * K + k);
+      if (c_ok && row >= 0 && row < n_rows) {
+        const float g = __ldg(G + m * K + k);
+        float w[8];
+        load_vec_as_float<T>(table + row * d + c * VE, w);
+#pragma unroll
+        for (int e = 0; e < VE; ++e) acc[e] = fmaf(g, w[e], acc[e]);
+      }
+    }
+    for (int o = gl; o < 32; o <<= 1) {
+#pragma unroll
+      for (int e = 0; e < VE; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
+    }
+    if (slot == 0 && c_ok) {
+      float* o = dU + m * d + c * VE;
+#pragma unroll
+      for (int e = 0; e < VE; e += 4)
+        *reinterpret_cast<float4*>(o + e) = make_float4(acc[e] * scale, acc[e + 1] * scale, acc[e + 2] * scale, acc[e + 3] * scale);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------- SpMM
+// Y = A X for CSR A (fp32 values) and dense fp32 X (cols, d); optionally acc += beta * Y in the same pass
+// (reference: `allEmbds = self.Adj @ allEmbds; avgEmbds += allEmbds / (L+1)`, LightGCN/main.py:83-85).
+// A group of GL = d/4 lanes (power of two, <= 32) owns one output row, 32/GL rows per warp; the row's
+// non-zeros are walked in order (deterministic), four gathers in flight per lane.
+__global__ void spmm_csr_kernel(const int64_t* __restrict__ crow, const int64_t* __restrict__ col,
+                                const float* __restrict__ val, const float* __restrict__ X, float* __restrict__ Y,
+                                float* __restrict__ acc_out, float beta, long long n_rows, long long n_cols, int d, int gl) {
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (gl - 1), slot = lane / gl, nslot = 32 / gl;
+  const long long row = warp * nslot + slot;
+  if (row >= n_rows) return;
+  const long long e0 = crow[row], e1 = crow[row + 1];
+  for (int c = sub * 4; c < d; c += gl * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    long long e = e0;
+    for (; e + 4 <= e1; e += 4) {
+      float4 x[4];
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long j = __ldg(col + e + u);
+        v[u] = __ldg(val + e + u);
+        x[u] = (j >= 0 && j < n_cols) ? __ldg(reinterpret_cast<const float4*>(X + j * d + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc.x = fmaf(v[u], x[u].x, acc.x); acc.y = fmaf(v[u], x[u].y, acc.y);
+        acc.z = fmaf(v[u], x[u].z, acc.z); acc.w = fmaf(v[u], x[u].w, acc.w);
+      }
+    }
+    for (; e < e1; ++e) {
+      const long long j = __ldg(col + e);
+      const float v = __ldg(val + e);
+      if (j >= 0 && j < n_cols) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(X + j * d + c));
+        acc.x = fmaf(v, x.x, acc.x); acc.y = fmaf(v, x.y, acc.y); acc.z = fmaf(v, x.z, acc.z); acc.w = fmaf(v, x.w, acc.w);
+      }
+    }
+    if (Y != nullptr) *reinterpret_cast<float4*>(Y + row * d + c) = acc;
+    if (acc_out != nullptr) {
+      float4* o = reinterpret_cast<float4*>(acc_out + row * d + c);
+      float4 t = *o;
+      t.x = fmaf(beta, acc.x, t.x); t.y = fmaf(beta, acc.y, t.y); t.z = fmaf(beta, acc.z, t.z); t.w = fmaf(beta, acc.w, t.w);
+      *o = t;
+    }
+  }
+}
+
 // -------------------------------------------------------------------------- radix sort
 // Stable LSD radix sort of (key = row id, val = position) pairs, 8 bits per pass.
 // One warp owns a contiguous chunk; ranks inside the chunk come from __match_any_sync so equal
@@ -198,7 +338,7 @@ __global__ void __launch_bounds__(128)
 scatter_segments_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ perm,
                         const T* __restrict__ grad_out, float* __restrict__ grad_table, int n, int d, long long n_rows,
                         float alpha, const float* __restrict__ alpha_dev, float* __restrict__ cnt_out, float cnt_alpha,
-                        float* __restrict__ lead, float* __restrict__ trail) {
+                        float* __restrict__ lead, float* __restrict__ trail, int row_div, const float* __restrict__ ew) {
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int p0 = b * SEG_BLOCK;
@@ -207,7 +347,10 @@ scatter_segments_kernel(const uint32_t* __restrict__ keys, const uint32_t* __res
   const uint32_t key = (lane < cnt) ? keys[p0 + lane] : 0xFFFFFFFFu;
   const uint32_t first_key = __shfl_sync(0xffffffffu, key, 0);
   if (static_cast<long long>(first_key) >= n_rows) return;  // sorted: nothing valid in this block
+  // entry p adds  ew[p] * grad_out[p / row_div]  (plain embedding backward: row_div = 1, ew = null)
   const uint32_t my_perm = (lane < cnt) ? perm[p0 + lane] : 0u;
+  const uint32_t my_src = (row_div > 1) ? my_perm / static_cast<uint32_t>(row_div) : my_perm;
+  const float my_w = (ew != nullptr && lane < cnt) ? __ldg(ew + my_perm) : 1.f;
   const uint32_t prev_key = (p0 > 0) ? keys[p0 - 1] : 0xFFFFFFFFu;
   const uint32_t next_key = (p0 + SEG_BLOCK < n) ? keys[p0 + SEG_BLOCK] : 0xFFFFFFFFu;
   const uint32_t up = __shfl_up_sync(0xffffffffu, key, 1);
@@ -225,9 +368,13 @@ scatter_segments_kernel(const uint32_t* __restrict__ keys, const uint32_t* __res
       float4 v[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const uint32_t pr = __shfl_sync(0xffffffffu, my_perm, (e0 + u) & 31);
+        const uint32_t pr = __shfl_sync(0xffffffffu, my_src, (e0 + u) & 31);
         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (col_ok && ((valid >> (e0 + u)) & 1u)) v[u] = seg_load4<T>(grad_out + static_cast<long long>(pr) * d + c);
+        if (ew != nullptr) {  // warp-uniform
+          const float w = __shfl_sync(0xffffffffu, my_w, (e0 + u) & 31);
+          v[u].x *= w; v[u].y *= w; v[u].z *= w; v[u].w *= w;
+        }
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {

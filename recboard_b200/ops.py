@@ -96,6 +96,108 @@ def gather_rows(table: torch.Tensor, idx: torch.Tensor, padding_idx: int = -1) -
 
 
 # --------------------------------------------------------------------------------------
+# fused gather + row-wise dot (pool ranking, sampled softmax, BPR / BCE logits)
+# --------------------------------------------------------------------------------------
+def _same_storage(U, table):
+    dt = torch.bfloat16 if (U.dtype == torch.bfloat16 and table.dtype == torch.bfloat16) else torch.float32
+    return U.detach().to(dt).contiguous(), table.detach().to(dt).contiguous()
+
+
+class _GatherDot(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, U, table, idx, scale, padding_idx):
+        dev = L.require_cuda(U, table, idx)
+        if idx.dtype != torch.int64 or idx.dim() != 2 or idx.shape[0] != U.shape[0]:
+            raise TypeError("idx must be int64 of shape (M, K)")
+        Uc, Tc = _same_storage(U, table)
+        idc = idx.contiguous()
+        M, d = Uc.shape
+        K = idc.shape[1]
+        S = torch.empty(M, K, dtype=torch.float32, device=dev)
+        L.check(
+            L.lib().rb_gather_dot(L.ptr(Uc), L.ptr(Tc), L.ptr(idc), float(scale), L.ptr(S), M, K, Tc.shape[0], d,
+                                  L.dtype_code(Uc), L.stream_ptr(dev)),
+            "rb_gather_dot",
+        )
+        ctx.save_for_backward(Uc, Tc, idc)
+        ctx.scale, ctx.padding_idx, ctx.dtypes = float(scale), int(padding_idx), (U.dtype, table.dtype)
+        return S
+
+    @staticmethod
+    def backward(ctx, G):
+        Uc, Tc, idc = ctx.saved_tensors
+        dev = Uc.device
+        M, d = Uc.shape
+        K = idc.shape[1]
+        need_u, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dU = torch.empty(M, d, dtype=torch.float32, device=dev) if need_u else None
+        dT = torch.zeros(Tc.shape[0], d, dtype=torch.float32, device=dev) if need_t else None
+        ws, n = _ws(dev, L.OP_SCATTER_ADD, 0, 0, d, nnz=M * K)
+        L.check(
+            L.lib().rb_gather_dot_bwd(L.ptr(Uc), L.ptr(Tc), L.ptr(idc), L.ptr(G.float().contiguous()), ctx.scale, L.ptr(dU),
+                                      L.ptr(dT), M, K, Tc.shape[0], d, L.dtype_code(Uc), ctx.padding_idx, L.ptr(ws), n,
+                                      L.stream_ptr(dev)),
+            "rb_gather_dot_bwd",
+        )
+        return (dU.to(ctx.dtypes[0]) if need_u else None, dT.to(ctx.dtypes[1]) if need_t else None, None, None, None)
+
+
+def gather_dot(U: torch.Tensor, table: torch.Tensor, idx: torch.Tensor, scale: float = 1.0, padding_idx: int = -1) -> torch.Tensor:
+    """``torch.einsum("MD,MKD->MK", U, table[idx]) * scale`` -> fp32 (M,K) without the (M,K,D) gather
+    (recommend_from_pool SASRec/main.py:230-236; sampled softmax HSTU/main.py:192-197; BPR/BCE logits
+    SASRec/main.py:203-206).  Differentiable w.r.t. ``U`` and ``table`` (dense, deterministic)."""
+    return _GatherDot.apply(U, table, idx, scale, padding_idx)
+
+
+# --------------------------------------------------------------------------------------
+# CSR x dense (LightGCN propagation)
+# --------------------------------------------------------------------------------------
+def _csr_parts(A: torch.Tensor):
+    if A.layout != torch.sparse_csr:
+        A = A.to_sparse_csr()
+    return (A.crow_indices().to(torch.int64).contiguous(), A.col_indices().to(torch.int64).contiguous(),
+            A.values().float().contiguous(), A.shape)
+
+
+def spmm_raw(A: torch.Tensor, X: torch.Tensor, acc: Optional[torch.Tensor] = None, beta: float = 1.0,
+             want_y: bool = True) -> Optional[torch.Tensor]:
+    """Y = A @ X (fp32) through rb_spmm_csr; with ``acc`` also ``acc += beta * Y`` in the same pass."""
+    crow, col, val, shape = _csr_parts(A)
+    dev = L.require_cuda(crow, col, val, X, acc)
+    Xc = X.detach().float().contiguous()
+    d = Xc.shape[1]
+    Y = torch.empty(shape[0], d, dtype=torch.float32, device=dev) if want_y else None
+    if val.numel() == 0:   # empty matrix: nothing to launch
+        return Y.zero_() if want_y else None
+    L.check(
+        L.lib().rb_spmm_csr(L.ptr(crow), L.ptr(col), L.ptr(val), L.ptr(Xc), L.ptr(Y), L.ptr(acc), float(beta), shape[0], shape[1],
+                            d, L.stream_ptr(dev)),
+        "rb_spmm_csr",
+    )
+    return Y
+
+
+class _SpMM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, A, At, X):
+        ctx.At = At
+        return spmm_raw(A, X)
+
+    @staticmethod
+    def backward(ctx, dY):
+        return None, None, spmm_raw(ctx.At, dY.contiguous())
+
+
+def spmm(A: torch.Tensor, X: torch.Tensor, symmetric: bool = False, At: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``A @ X`` for a sparse CSR ``A`` (LightGCN/main.py:83), differentiable w.r.t. ``X``.  The backward is
+    ``A^T @ dY``: pass ``symmetric=True`` for the symmetric-normalised adjacency (no transpose needed) or a
+    cached ``At``; otherwise the transpose is built here."""
+    if At is None:
+        At = A if symmetric else A.t().to_sparse_csr()
+    return _SpMM.apply(A, At, X)
+
+
+# --------------------------------------------------------------------------------------
 # row normalisation (cosine scoring operands)
 # --------------------------------------------------------------------------------------
 def normalize_rows(x: torch.Tensor, out_dtype: Optional[torch.dtype] = None, eps: float = 1e-12,

@@ -293,6 +293,69 @@ def test_topk_candidate_overflow_falls_back(ops):
     _check_topk(vals, ids, masked, K, 2e-6)
 
 
+@pytest.mark.parametrize("M,K,N,d,dt", [(3, 1, 50, 64, torch.float32), (300, 101, 4000, 64, torch.float32),
+                                         (513, 513, 12101, 128, torch.bfloat16), (64, 7, 900, 96, torch.bfloat16),
+                                         (40, 33, 700, 256, torch.float32)])
+def test_gather_dot_forward_backward(ops, M, K, N, d, dt):
+    """pool / sampled-softmax scoring without the (M,K,d) gather; hot ids, out-of-range ids and
+    a padding row included.  fp32 storage 1e-5, bf16 storage: same inputs as the oracle, fp32 accumulate."""
+    g = torch.Generator().manual_seed(M * 31 + K)
+    U = (torch.randn(M, d, generator=g) / d ** 0.25).to(dt)
+    tab = (torch.randn(N, d, generator=g) / d ** 0.25).to(dt)
+    idx = torch.randint(0, N, (M, K), generator=g)
+    idx[:, 0] = 5                       # hot row: every query hits it
+    if K > 2:
+        idx[0, 1] = 0                   # the padding row
+    Gup = torch.randn(M, K, generator=g)
+    Ur, Tr = U.float().clone().requires_grad_(True), tab.float().clone().requires_grad_(True)
+    ref = orc.gather_dot(Ur, Tr, idx, 0.7)
+    (ref * Gup).sum().backward()
+    rdT = Tr.grad.clone()
+    rdT[0] = 0                          # padding_idx = 0 keeps row 0 at zero (nn.Embedding contract)
+    Ud, Td = dev(U).requires_grad_(True), dev(tab).requires_grad_(True)
+    S = ops.gather_dot(Ud, Td, dev(idx), scale=0.7, padding_idx=0)
+    (S * dev(Gup)).sum().backward()
+    tol = FP32_RTOL
+    assert_rel(S, ref.detach(), tol, "scores")
+    assert_rel(Ud.grad, Ur.grad, tol if dt == torch.float32 else 2.0 ** -8, "dU")
+    assert_rel(Td.grad, rdT, tol if dt == torch.float32 else 2.0 ** -8, "dTable")
+    # determinism: the table gradient is bitwise reproducible
+    Ud2, Td2 = dev(U).requires_grad_(True), dev(tab).requires_grad_(True)
+    (ops.gather_dot(Ud2, Td2, dev(idx), scale=0.7, padding_idx=0) * dev(Gup)).sum().backward()
+    assert torch.equal(Td.grad, Td2.grad) and torch.equal(Ud.grad, Ud2.grad)
+
+
+@pytest.mark.parametrize("R,d,avg_deg", [(1, 64, 3), (700, 64, 9), (2049, 128, 40), (300, 32, 0), (513, 8, 5)])
+def test_spmm_csr(ops, R, d, avg_deg):
+    """LightGCN propagation (LightGCN/main.py:83-85), forward, fused average and backward."""
+    g = torch.Generator().manual_seed(R + d)
+    nnz = R * avg_deg
+    r = torch.randint(0, R, (nnz,), generator=g)
+    c = torch.randint(0, R, (nnz,), generator=g)
+    v = torch.rand(nnz, generator=g)
+    A = torch.sparse_coo_tensor(torch.stack([torch.cat([r, c]), torch.cat([c, r])]), torch.cat([v, v]), (R, R)).coalesce().to_sparse_csr()
+    X = torch.randn(R, d, generator=g)
+    Xr = X.clone().requires_grad_(True)
+    ref = orc.spmm(A, Xr)
+    Gup = torch.randn(R, d, generator=g)
+    (ref * Gup).sum().backward()
+    Xd = dev(X).requires_grad_(True)
+    Y = ops.spmm(dev(A), Xd, symmetric=True)
+    (Y * dev(Gup)).sum().backward()
+    assert_rel(Y, ref.detach(), FP32_RTOL, "A @ X")
+    assert_rel(Xd.grad, Xr.grad, FP32_RTOL, "dX")
+    acc = dev(X).clone()
+    ops.spmm_raw(dev(A), dev(X), acc=acc, beta=0.25, want_y=False)
+    assert_rel(acc, X + 0.25 * ref.detach(), FP32_RTOL, "fused average")
+    # general (non-symmetric) matrices take the transposed CSR in backward
+    B = torch.sparse_coo_tensor(torch.stack([r, c]), v, (R, R)).coalesce().to_sparse_csr() if nnz else A
+    Xr2 = X.clone().requires_grad_(True)
+    (orc.spmm(B, Xr2) * Gup).sum().backward()
+    Xd2 = dev(X).requires_grad_(True)
+    (ops.spmm(dev(B), Xd2) * dev(Gup)).sum().backward()
+    assert_rel(Xd2.grad, Xr2.grad, FP32_RTOL, "dX (general)")
+
+
 @pytest.mark.parametrize("n,d,in_dt,out_dt", [(1, 8, torch.float32, torch.float32), (1000, 256, torch.float32, torch.bfloat16),
                                              (4097, 64, torch.bfloat16, torch.bfloat16), (333, 1024, torch.bfloat16, torch.float32)])
 def test_normalize_rows(ops, n, d, in_dt, out_dt):
