@@ -39,8 +39,8 @@ SEQ = 50
 TOPK = 50
 METRIC = "full-catalog scored user-item pairs/sec (CE train + top-K eval)"
 # dram__bytes_read.sum + dram__bytes_write.sum of one pair_kernel<PASS_DW> launch at this workload (ncu --set full)
-PROFILED_TRAFFIC_BYTES = 258_533_888 + 460_901_376
-PROFILED_TRAFFIC_SOURCE = "profiles/r1e_ncu_summary.md (ncu --set full, one launch, N=1M shard)"
+PROFILED_TRAFFIC_BYTES = 257_289_216 + 459_547_904
+PROFILED_TRAFFIC_SOURCE = "profiles/r1f_ncu_summary.md (ncu --set full, one launch, N=1M shard)"
 UNIT = "pairs/s"
 
 
@@ -161,6 +161,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     L.lib()
 
