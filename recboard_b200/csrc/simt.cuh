@@ -282,10 +282,19 @@ __global__ void rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const ui
   for (int i = lane; i < 256; i += 32) base[i] = offs[i * n_chunks + chunk];
   __syncwarp();
   const int beg = chunk * RS_CHUNK, end = min(n, beg + RS_CHUNK);
-  for (int i0 = beg; i0 < end; i0 += 32) {
-    const int i = i0 + lane;
+  constexpr int PER = RS_CHUNK / 32;
+  uint32_t kreg[PER], vreg[PER];   // the whole chunk in registers: the ranking loop below never waits on memory
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = beg + j * 32 + lane;
+    kreg[j] = (i < end) ? keys_in[i] : 0u;
+    vreg[j] = (i < end) ? vals_in[i] : 0u;
+  }
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = beg + j * 32 + lane;
     const bool ok = i < end;
-    const uint32_t k = ok ? keys_in[i] : 0u;
+    const uint32_t k = kreg[j];
     const uint32_t dgt = ok ? ((k >> shift) & 255u) : 256u + lane;  // inactive lanes never match
     const uint32_t peers = __match_any_sync(0xffffffffu, dgt);
     const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
@@ -294,7 +303,7 @@ __global__ void rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const ui
     __syncwarp();
     if (ok && rank == __popc(peers) - 1) base[dgt] += __popc(peers);  // last peer bumps the counter
     __syncwarp();
-    if (ok) { keys_out[pos] = k; vals_out[pos] = vals_in[i]; }
+    if (ok) { keys_out[pos] = k; vals_out[pos] = vreg[j]; }
   }
 }
 
@@ -685,19 +694,39 @@ __device__ __forceinline__ T warp_blocked_get(const T (&v)[E], int idx) {
 }
 
 // ---- top-K pass 2a: per row, the K-th largest CLEAN tile maximum tau (NaN marks a dirty tile, one that
-// holds a seen id: it never supports the threshold).  One warp per row; the next chunk of tile maxima is
-// in flight while the current one is examined, and a chunk is only sorted when it can raise tau.
+// holds a seen id: it never supports the threshold).  One warp per row; only values above the current
+// threshold are staged (ballot compaction into shared memory) and the staged block is sorted and merged
+// into the running top list when it fills up -- about 128 + K ln(n/128) insertions per row instead of a
+// sort per 128-value chunk; the next chunk of tile maxima is in flight while the current one is examined.
 template <int E>
-__global__ void tilemax_select_kernel(const float* __restrict__ T, int n_tiles, long long n_rows, int K,
-                                      float* __restrict__ tau_out) {
+__global__ void __launch_bounds__(128)
+tilemax_select_kernel(const float* __restrict__ T, int n_tiles, long long n_rows, int K, float* __restrict__ tau_out) {
+  __shared__ float stage_s[4][32 * E];
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n_rows) return;
+  float* stage = stage_s[threadIdx.x >> 5];
   const float* t = T + row * n_tiles;
+  const uint32_t lt = (1u << lane) - 1u;
   float best[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) best[e] = -INFINITY;
   float tau = -INFINITY;
+  int ns = 0;
+  auto flush = [&]() {
+    __syncwarp();
+    float cur[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = lane * E + e;
+      cur[e] = (i < ns) ? stage[i] : -INFINITY;
+    }
+    warp_bitonic_sort_desc<float, E>(cur);
+    warp_topk_absorb<float, E>(best, cur);
+    tau = warp_blocked_get<float, E>(best, K - 1);
+    ns = 0;
+    __syncwarp();
+  };
   float nxt[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) {
@@ -706,20 +735,24 @@ __global__ void tilemax_select_kernel(const float* __restrict__ T, int n_tiles, 
   }
   for (int base = 0; base < n_tiles; base += 32 * E) {
     float cur[E];
-    bool any = false;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       cur[e] = nxt[e];
       const int i = base + 32 * E + e * 32 + lane;
       nxt[e] = (i < n_tiles) ? __ldg(t + i) : -INFINITY;
-      if (cur[e] != cur[e]) cur[e] = -INFINITY;  // dirty tile
-      any |= cur[e] > tau;
     }
-    if (!__any_sync(0xffffffffu, any)) continue;
-    warp_bitonic_sort_desc<float, E>(cur);
-    warp_topk_absorb<float, E>(best, cur);
-    tau = warp_blocked_get<float, E>(best, K - 1);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const bool pass = cur[e] > tau;   // false for NaN (dirty tile) and for values that cannot raise the threshold
+      const uint32_t m = __ballot_sync(0xffffffffu, pass);
+      if (m != 0u) {
+        if (pass) stage[ns + __popc(m & lt)] = cur[e];
+        ns += __popc(m);
+        if (ns > 32 * E - 32) flush();
+      }
+    }
   }
+  if (ns > 0) flush();
   if (lane == 0) tau_out[row] = tau;  // -inf when fewer than K clean tiles exist
 }
 
