@@ -48,6 +48,19 @@ check("CE loss", loss.detach().reshape(1), ref_loss.detach().reshape(1), 1e-5)
 check("CE dU", Us.grad, Uf.grad, 2.0 ** -7)   # both sides are bf16 tensors: one ulp of the largest element is 2^-8
 check("CE dW shard", Ws.grad, Wf.grad[lo:hi], 2.0 ** -7)
 
+# ---- BERT4Rec-style bias head (config 5 shape scaled down): bias shard + dbias shard
+bias = (torch.randn(N, device=dev, generator=g) * 0.2)
+Ub, Wb, bb = U.clone().requires_grad_(True), W.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+ref_b = ops.fused_ce(Ub, Wb, labels, bias=bb)
+ref_b.backward()
+Us2, Ws2, bs2 = U.clone().requires_grad_(True), W[lo:hi].clone().requires_grad_(True), bias[lo:hi].clone().requires_grad_(True)
+loss_b = sharded.sharded_fused_ce(Us2, Ws2, labels, lo, bias_shard=bs2)
+loss_b.backward()
+check("CE+bias loss", loss_b.detach().reshape(1), ref_b.detach().reshape(1), 1e-5)
+check("CE+bias dU", Us2.grad, Ub.grad, 2.0 ** -7)
+check("CE+bias dW shard", Ws2.grad, Wb.grad[lo:hi], 2.0 ** -7)
+check("CE+bias dbias shard", bs2.grad, bb.grad[lo:hi], 1e-4)
+
 # ---- HSTU-style retrieval: d=256, K=100, cosine scores, sharded table
 B, N2, d2, K = 512, 300_011, 256, 100
 Uq = ops.normalize_rows(synth.embeddings(B, d2, g, dev, torch.float32), out_dtype=torch.bfloat16)

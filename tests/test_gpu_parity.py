@@ -495,3 +495,62 @@ def test_full_size_properties(ops):
     S[torch.arange(8, device="cuda").repeat_interleave(4), col[:32]] = -1e23
     rv, ri = torch.sort(S, dim=1, descending=True, stable=True)
     assert torch.equal(ri[:, :K], ids[:8].long()) or float((rv[:, :K] - vals[:8]).abs().max()) < 1e-5
+
+
+def test_full_size_config4_hstu_retrieval_shard(ops):
+    """BASELINE configs[3] per-GPU shard (10M items / 8 = 1.25M, d=256, cosine scores, K=100), B=256 and 4096:
+    normalised operands through rb_normalize_rows; sorted, unmasked, true scores; shard split-invariance."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    N, d, K = 1_250_000, 256, 100
+    W = ops.normalize_rows(torch.randn(N, d, generator=g, device="cuda"), out_dtype=torch.bfloat16)
+    for B in (256, 4096):
+        U = ops.normalize_rows(torch.randn(B, d, generator=g, device="cuda"), out_dtype=torch.bfloat16)
+        crow = torch.arange(0, (B + 1) * 3, 3, device="cuda")
+        col = torch.sort(torch.randint(0, N, (B, 3), generator=g, device="cuda"), dim=1).values.reshape(-1)
+        vals, ids = ops.topk_eval(U, W, K, crow, col, id_base=0)
+        assert torch.all(vals[:, :-1] >= vals[:, 1:]) and torch.all(ids >= 0)
+        assert float(vals.max()) <= 1.0 + 1e-2                       # cosine of bf16-rounded unit vectors
+        true = (U[:64].float().unsqueeze(1) * W[ids[:64].long()].float()).sum(-1)
+        assert_rel(vals[:64], true.cpu(), 1e-5, "top-K values")
+        assert not torch.any(ids.unsqueeze(-1) == col.view(B, 1, 3))
+        # two half shards + merge == one shard
+        h = N // 2
+        v0, i0 = ops.topk_eval(U, W[:h], K, crow, col, id_base=0)
+        v1, i1 = ops.topk_eval(U, W[h:], K, crow, col, id_base=h)
+        mv, mi = ops.topk_merge(torch.stack([v0, v1]), torch.stack([i0, i1]))
+        assert torch.equal(mi, ids) and torch.equal(mv, vals)
+        # dense spot check of 4 rows
+        S = U[:4].float() @ W.float().T
+        S[torch.arange(4, device="cuda").repeat_interleave(3), col[:12]] = -1e23
+        rv, ri = torch.sort(S, dim=1, descending=True, stable=True)
+        assert torch.equal(ri[:, :K], ids[:4].long()) or float((rv[:, :K] - vals[:4]).abs().max()) < 1e-5
+
+
+def test_full_size_config5_bert4rec_shard(ops):
+    """BASELINE configs[4] per-GPU shard (50M items / 8 = 6.25M rows + 2 pad columns, d=128, bias head,
+    M=4096 masked rows): no logit materialisation (the (M,N) fp32 matrix would be 102 GB), loss / gradient
+    properties, label offset of the pad columns."""
+    g = torch.Generator(device="cuda").manual_seed(10)
+    M, N, d = 4096, 6_250_002, 128
+    U = (torch.randn(M, d, generator=g, device="cuda") / d ** 0.25).bfloat16()
+    W = (torch.randn(N, d, generator=g, device="cuda") / d ** 0.25).bfloat16()
+    bias = torch.randn(N, generator=g, device="cuda") * 0.2
+    lab = torch.randint(2, N, (M,), generator=g, device="cuda")      # labels live in [2, N+2) of the N+2 columns
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    m, l, ll, du_un = ops.ce_rowstats(U, W, lab, bias=bias, want_dU=True)
+    lse = m + torch.log(l)
+    direct = (U.float() * W[lab].float()).sum(-1) + bias[lab]
+    assert_rel(ll, direct.cpu(), 1e-5, "label logit")
+    assert torch.all(lse >= m) and torch.all(lse <= m + np.log(N) + float(bias.max()) + 1e-3)
+    _, dW, db = ops.ce_backward(U, W, lab, lse, 1.0 / M, bias=bias, need_dU=False, need_dW=True, need_dbias=True)
+    peak = torch.cuda.max_memory_allocated() - base   # before the checks below allocate anything large
+    # rows of (softmax - onehot) sum to zero: sum_j dbias_j == 0 and sum_j dW_j == sum_i (sum_j G_ij) u_i == 0
+    assert abs(float(db.double().sum())) <= 1e-3 * float(db.double().abs().sum())
+    col_sum = dW.sum(0, dtype=torch.float64)
+    assert float(col_sum.abs().max()) <= 5e-3 * float(torch.linalg.vector_norm(dW, ord=1, dim=0, dtype=torch.float64).max())
+    # dbias of a label column: softmax mass minus the label count / M
+    j = int(lab[0])
+    pj = torch.exp((U.float() @ W[j].float()) + bias[j] - lse).sum() / M - float((lab == j).sum()) / M
+    assert abs(float(db[j]) - float(pj)) <= 1e-5 + 2e-3 * abs(float(pj))
+    assert peak < 6 * 2 ** 30, f"peak extra memory {peak / 2**30:.1f} GiB: the logits must never be materialised"
