@@ -171,30 +171,38 @@ static int launch_sweep_t(const CUtensorMap& ts, const CUtensorMap& ty, const Sw
   return 0;
 }
 
-// Stationary tiles per CTA: two (256 rows) whenever the operands fit (bf16, d <= 128) and there is a
-// second tile to fill -- halves the L2->SM traffic of a sweep (see sweep.cuh).
+// Stationary tiles per CTA: two (256 rows) whenever there is a second tile to fill -- halves the L2->SM
+// traffic of a sweep (see sweep.cuh).
 static int sweep_xt(int mode, int d, long long n_stat) {
-  return (mode == RB_MODE_BF16 && d <= 128 && n_stat > 128) ? 2 : 1;
+  (void)mode; (void)d;
+  return n_stat > 128 ? 2 : 1;
 }
 
-// NS chosen so that SMEM stays under 227 KB
+// NS = pipeline stages (whole 32 KB tiles up to two K-chunks, single 16 KB chunks beyond: SweepCfg::SC),
+// chosen so that SMEM stays under 227 KB next to the stationary tile(s)
 template <int EPI, bool ROWS>
 static int launch_sweep(int mode, int kc, const CUtensorMap& ts, const CUtensorMap& ty, const SweepArgs& a, int grid,
                         cudaStream_t st, int xt = 1) {
   if (xt == 2) {
     if constexpr (EPI != EPI_DENSE) {
-      if (mode == RB_MODE_BF16 && kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 1, BN, 6, ROWS, 2>>(ts, ty, a, grid, st);
-      if (mode == RB_MODE_BF16 && kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 2, BN, 4, ROWS, 2>>(ts, ty, a, grid, st);
+      if (mode == RB_MODE_BF16) {
+        if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 1, BN, 10, ROWS, 2>>(ts, ty, a, grid, st);
+        if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 2, BN, 4, ROWS, 2>>(ts, ty, a, grid, st);
+        if (kc <= 4) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 4, BN, 5, ROWS, 2>>(ts, ty, a, grid, st);
+      } else {
+        if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 1, BN, 4, ROWS, 2>>(ts, ty, a, grid, st);
+        if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 2, BN, 5, ROWS, 2>>(ts, ty, a, grid, st);
+      }
     }
-    return fail(RB_E_UNSUPPORTED, "two stationary tiles need bf16 mode and d <= 128");
+    return fail(RB_E_UNSUPPORTED, "unsupported feature width for two stationary tiles (mode %d, kc=%d)", mode, kc);
   }
   if (mode == RB_MODE_BF16) {
-    if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 1, BN, 6, ROWS>>(ts, ty, a, grid, st);
-    if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 2, BN, 4, ROWS>>(ts, ty, a, grid, st);
-    if (kc <= 4) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 4, BN, 2, ROWS>>(ts, ty, a, grid, st);
+    if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 1, BN, 10, ROWS>>(ts, ty, a, grid, st);
+    if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 2, BN, 5, ROWS>>(ts, ty, a, grid, st);
+    if (kc <= 4) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 4, BN, 8, ROWS>>(ts, ty, a, grid, st);
   } else {
-    if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 1, BN, 4, ROWS>>(ts, ty, a, grid, st);
-    if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 2, BN, 2, ROWS>>(ts, ty, a, grid, st);
+    if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 1, BN, 5, ROWS>>(ts, ty, a, grid, st);
+    if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 2, BN, 8, ROWS>>(ts, ty, a, grid, st);
   }
   return fail(RB_E_UNSUPPORTED, "unsupported feature width for mode %d (kc=%d)", mode, kc);
 }

@@ -804,8 +804,12 @@ __device__ __forceinline__ float exact_logit(const float* __restrict__ u, const 
 
 // ---- top-K pass 3: re-score the row's hit groups (aligned groups of 8 items whose maximum reached tau in
 // the EPI_CAND sweep) exactly, drop seen items (UniSRec/main.py:413), keep the K best by (score desc,
-// id asc).  Rows with an overflowed sub-list are flagged for the fallback below.  One warp per row; a
-// lane scores one item, four groups per step.
+// id asc).  Rows with an overflowed sub-list (or more than GROUPS_CAP groups in total) are flagged for the
+// fallback below.  One warp per row: the sub-lists are first flattened into shared memory (counts scanned 32
+// sub-lists at a time), then a lane scores one item, four groups per step -- the number of dependent
+// memory round trips is total/4 + n_sub/32, not n_sub.
+constexpr int GROUPS_CAP = 1024;
+
 template <typename TW, int E>
 __global__ void __launch_bounds__(128)
 topk_from_groups_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const float* __restrict__ bias, float scale,
@@ -815,13 +819,33 @@ topk_from_groups_kernel(const TW* __restrict__ U, const TW* __restrict__ W, cons
                         int* __restrict__ out_ids, int* __restrict__ overflow) {
   __shared__ __align__(16) float u_s[4][256];
   __shared__ unsigned long long stage_s[4][256];
+  __shared__ int glist_s[4][GROUPS_CAP];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 4 + wib;
   if (row >= n_rows) return;
   const int* cnts = cand_cnt + row * n_sub;
+  int* glist = glist_s[wib];
+  // ---- flatten the sub-lists
+  int total = 0;
   bool ovf = false;
-  for (int s = lane; s < n_sub; s += 32) ovf |= cnts[s] > cap;
-  ovf = __any_sync(0xffffffffu, ovf);
+  for (int sb = 0; sb < n_sub; sb += 32) {
+    const int sidx = sb + lane;
+    int c = (sidx < n_sub) ? cnts[sidx] : 0;
+    if (c > cap) { ovf = true; c = 0; }
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int off = total + incl - c;
+    if (off + c <= GROUPS_CAP) {
+      const int* gl = cand + (row * n_sub + sidx) * cap;
+      for (int e = 0; e < c; ++e) glist[off + e] = __ldg(gl + e);
+    }
+    total += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  ovf = __any_sync(0xffffffffu, ovf) || total > GROUPS_CAP;
   if (lane == 0) overflow[row] = ovf ? 1 : 0;
   if (ovf) return;
   float* u = u_s[wib];
@@ -852,28 +876,24 @@ topk_from_groups_kernel(const TW* __restrict__ U, const TW* __restrict__ W, cons
     ns = 0;
     __syncwarp();
   };
-  for (int s = 0; s < n_sub; ++s) {
-    const int cnt = cnts[s];
-    const int* gl = cand + (row * n_sub + s) * cap;
-    for (int base = 0; base < cnt; base += 4) {
-      const int gi = base + (lane >> 3);
-      const int item = (gi < cnt) ? (__ldg(gl + gi) << 3) + (lane & 7) : n_items;
-      unsigned long long key = 0ull;
-      if (item < n_items) key = topk_key(exact_logit<TW>(u, W + static_cast<long long>(item) * d, d, scale, bias, item), item);
-      bool pass = key > kth;
-      if (pass && s_hi > s_lo) {  // seen items never rank
-        int lo = s_lo, hi = s_hi;
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (__ldg(seen_col + mid) < item) lo = mid + 1; else hi = mid;
-        }
-        if (lo < s_hi && __ldg(seen_col + lo) == item) pass = false;
+  for (int base = 0; base < total; base += 4) {
+    const int gi = base + (lane >> 3);
+    const int item = (gi < total) ? (glist[gi] << 3) + (lane & 7) : n_items;
+    unsigned long long key = 0ull;
+    if (item < n_items) key = topk_key(exact_logit<TW>(u, W + static_cast<long long>(item) * d, d, scale, bias, item), item);
+    bool pass = key > kth;
+    if (pass && s_hi > s_lo) {  // seen items never rank
+      int lo = s_lo, hi = s_hi;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(seen_col + mid) < item) lo = mid + 1; else hi = mid;
       }
-      const uint32_t m = __ballot_sync(0xffffffffu, pass);
-      if (pass) stage[ns + __popc(m & lt)] = key;
-      ns += __popc(m);
-      if (ns > 256 - 32) flush();
+      if (lo < s_hi && __ldg(seen_col + lo) == item) pass = false;
     }
+    const uint32_t m = __ballot_sync(0xffffffffu, pass);
+    if (pass) stage[ns + __popc(m & lt)] = key;
+    ns += __popc(m);
+    if (ns > 256 - 32) flush();
   }
   flush();
 #pragma unroll

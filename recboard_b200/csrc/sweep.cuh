@@ -90,19 +90,26 @@ struct SweepCfg {
   static constexpr int DPAD = KC_ * ELEMS_PER_CHUNK;  // padded feature width
   static constexpr int XTILE_BYTES = KCS * 128 * 128;   // one stationary 128-row tile
   static constexpr int X_BYTES = XT_ * XTILE_BYTES;
-  static constexpr int Y_BYTES = KCS * BN_ * 128;
+  // One pipeline stage = SC 128-byte K-chunks of a streamed tile (BN rows x 128 B each).  Tiles of up to two
+  // chunks travel whole (SC = KCS); wider tiles (d = 256 bf16, d = 64 fp32x3: four chunks) travel chunk by
+  // chunk (SC = 1): the MMAs of a chunk start as soon as it lands and its slot goes back to the producer as
+  // soon as they retire, so the ring stays deep even when X takes 128 KB.
+  static constexpr int SC = (KCS <= 2) ? KCS : 1;
+  static constexpr int SPT = KCS / SC;              // stages per streamed tile
+  static constexpr int STAGE_BYTES = SC * BN_ * 128;
   static constexpr int CTRL_BYTES = 4096;  // barriers + cross-warpgroup exchange
-  static constexpr int SMEM_BYTES = X_BYTES + NS_ * Y_BYTES + CTRL_BYTES + 1024 /*align*/;
+  static constexpr int SMEM_BYTES = X_BYTES + NS_ * STAGE_BYTES + CTRL_BYTES + 1024 /*align*/;
   static constexpr int TMEM_NEED = 2 * XT_ * BN_;
   static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
   static_assert(TMEM_NEED <= 512, "TMEM budget");
   static_assert(SMEM_BYTES <= 227 * 1024, "SMEM budget");
   static_assert(BN_ % 64 == 0 && BN_ <= 256, "BN");
   static_assert(XT_ == 1 || XT_ == 2, "XT");
+  static_assert(NS_ <= 16 && NS_ >= 2, "stage count");
 };
 
 struct Control {
-  uint64_t full[8], empty[8];
+  uint64_t full[16], empty[16];
   uint64_t x_full, x_empty;
   uint64_t s_full[4], s_empty[4];
   uint32_t tmem_base;
@@ -144,7 +151,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* x_smem = smem;
   uint8_t* y_smem = x_smem + C::X_BYTES;
-  Control* bar = reinterpret_cast<Control*>(y_smem + C::NS * C::Y_BYTES);
+  Control* bar = reinterpret_cast<Control*>(y_smem + C::NS * C::STAGE_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -181,7 +188,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
   if (warp == 0) {
     // ======================================================================= TMA producer
     // The whole warp runs the (uniform) control flow; one elected lane issues the copies.
-    uint32_t it = 0, k = 0;
+    uint32_t cs = 0, k = 0;   // cs: stages issued so far
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++k) {
       int stat_tile, split, t0, t1;
       item_range(item, stat_tile, split, t0, t1);
@@ -196,17 +203,20 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
                         (stat_tile * C::XT + x) * 128);
       }
       __syncwarp();
-      for (int t = t0; t < t1; ++t, ++it) {
-        const uint32_t st = it % C::NS, ph = (it / C::NS) & 1;
-        mbar_wait(&bar->empty[st], ph ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&bar->full[st], C::Y_BYTES);
+      for (int t = t0; t < t1; ++t) {
 #pragma unroll
-          for (int c = 0; c < C::KCS; ++c)
-            tma_load_2d(y_smem + st * C::Y_BYTES + c * C::BN * 128, &tm_strm, &bar->full[st],
-                        c * C::ELEMS_PER_CHUNK, t * C::BN);
+        for (int sg = 0; sg < C::SPT; ++sg, ++cs) {
+          const uint32_t st = cs % C::NS, ph = (cs / C::NS) & 1;
+          mbar_wait(&bar->empty[st], ph ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&bar->full[st], C::STAGE_BYTES);
+#pragma unroll
+            for (int c = 0; c < C::SC; ++c)
+              tma_load_2d(y_smem + st * C::STAGE_BYTES + c * C::BN * 128, &tm_strm, &bar->full[st],
+                          (sg * C::SC + c) * C::ELEMS_PER_CHUNK, t * C::BN);
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else if (warp == 1) {
@@ -223,37 +233,47 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
       item_range(item, stat_tile, split, t0, t1);
       mbar_wait(&bar->x_full, k & 1);
       for (int t = t0; t < t1; ++t, ++it) {
-        const uint32_t st = it % C::NS, ph = (it / C::NS) & 1;
         const uint32_t buf = it & 1, sph = (it >> 1) & 1;
-        mbar_wait(&bar->full[st], ph);
+        const uint32_t cs = it * C::SPT;   // first stage of this streamed tile
 #pragma unroll
-        for (int x = 0; x < C::XT; ++x) {
-          const uint32_t bidx = (C::XT == 1) ? buf : x * 2 + buf;   // S buffer: XT=1 per tile parity, XT=2 per (X tile, parity)
-          mbar_wait(&bar->s_empty[bidx], sph ^ 1);
+        for (int x = 0; x < C::XT; ++x)    // S buffer: XT=1 per tile parity, XT=2 per (X tile, parity)
+          mbar_wait(&bar->s_empty[(C::XT == 1) ? buf : x * 2 + buf], sph ^ 1);
+        uint32_t waited = 0;               // stages of this tile already seen full
+#pragma unroll
+        for (int p = 0; p < C::NPAIR; ++p) {
+          int ac, bc, last_use;            // X chunk, Y chunk, last pair that reads Y chunk bc
+          if (C::DT == DT_BF16) { ac = p; bc = p; last_use = p; }
+          else {
+            const int c = p / 3, r = p % 3;  // small terms first: lo*hi, hi*lo, then hi*hi
+            ac = (r == 0) ? C::KC + c : c;
+            bc = (r == 1) ? C::KC + c : c;
+            last_use = (r == 1) ? p : 3 * c + 2;
+          }
+          const int sg = bc / C::SC;       // stage of the tile that holds Y chunk bc
+          if (C::SC > 1) last_use = C::NPAIR - 1;   // whole-tile stages are released after the tile's last MMA
+          const uint32_t sidx = cs + sg, st = sidx % C::NS;
+          if (!((waited >> sg) & 1u)) {
+            mbar_wait(&bar->full[st], (sidx / C::NS) & 1);
+            waited |= 1u << sg;
+          }
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t d_tmem = tmem_base + bidx * C::BN;
-            const uint32_t xs_lo = x_lo + ((x * C::XTILE_BYTES) >> 4);
-            const uint32_t ys_lo = y_lo + ((st * C::Y_BYTES) >> 4);
+            const uint32_t ys_lo = y_lo + ((st * C::STAGE_BYTES + (bc % C::SC) * C::BN * 128) >> 4);
 #pragma unroll
-            for (int p = 0; p < C::NPAIR; ++p) {
-              int ac, bc;
-              if (C::DT == DT_BF16) { ac = p; bc = p; }
-              else {
-                const int c = p / 3, r = p % 3;  // small terms first: lo*hi, hi*lo, then hi*hi
-                ac = (r == 0) ? C::KC + c : c;
-                bc = (r == 1) ? C::KC + c : c;
-              }
+            for (int x = 0; x < C::XT; ++x) {
+              const uint32_t bidx = (C::XT == 1) ? buf : x * 2 + buf;
+              const uint32_t d_tmem = tmem_base + bidx * C::BN;
+              const uint32_t xs_lo = x_lo + ((x * C::XTILE_BYTES + ac * 128 * 128) >> 4);
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) {
-                const uint64_t ad = smem_desc(dhi, xs_lo + ((ac * 128 * 128 + kk * 32) >> 4));
-                const uint64_t bd = smem_desc(dhi, ys_lo + ((bc * C::BN * 128 + kk * 32) >> 4));
+                const uint64_t ad = smem_desc(dhi, xs_lo + ((kk * 32) >> 4));
+                const uint64_t bd = smem_desc(dhi, ys_lo + ((kk * 32) >> 4));
                 if (C::DT == DT_BF16) mma_f16_ss(d_tmem, ad, bd, idesc1, (p | kk) != 0);
                 else mma_tf32_ss(d_tmem, ad, bd, idesc1, (p | kk) != 0);
               }
+              if (p == C::NPAIR - 1) tc_commit(&bar->s_full[bidx]);
             }
-            tc_commit(&bar->s_full[bidx]);
-            if (x == C::XT - 1) tc_commit(&bar->empty[st]);
+            if (p == last_use) tc_commit(&bar->empty[st]);   // every MMA that reads this stage retires before this fires
           }
           __syncwarp();
         }

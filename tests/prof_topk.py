@@ -1,4 +1,4 @@
-"""Probe: time the top-K pipeline (CUDA events) at bench sizes; RB_DBG selects skeleton probes."""
+"""Probe: time the top-K pipeline (CUDA events).  usage: prof_topk.py [N] [d] [B] [K] [reps]"""
 import sys
 from pathlib import Path
 import torch
@@ -6,7 +6,10 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from recboard_b200 import ops, synth  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
-M, D, K = 4096, 128, 50
+D = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+M = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
+K = int(sys.argv[4]) if len(sys.argv) > 4 else 50
+reps = int(sys.argv[5]) if len(sys.argv) > 5 else 10
 dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev).manual_seed(1)
 U = synth.embeddings(M, D, g, dev, torch.bfloat16, gain=1.5)
@@ -17,7 +20,7 @@ for _ in range(3):
 torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record()
-for _ in range(10):
+for _ in range(reps):
     ops.topk_eval(U, W, K, crow, col)
 b.record(); torch.cuda.synchronize()
-print("topk_eval ms", a.elapsed_time(b) / 10)
+print("topk_eval ms", a.elapsed_time(b) / reps)
