@@ -146,6 +146,13 @@ int rb_topk_eval(const void* U, const void* W, const float* bias, float scale,
 int rb_topk_merge(const float* vals, const int32_t* ids, int R, int64_t B, int K, float* out_vals,
                   int32_t* out_ids, rb_stream_t stream);
 
+/* hits[b,k] = 1.0 if top_ids[b,k] (global item id, -1 = missing) is one of row b's targets, else 0.0.
+ * Targets: CSR (target_crow[B+1], target_col[nnz]) of `Item.to_csr(data[IUnseen])`, ids sorted per row
+ * (UniSRec/main.py:414; the reference builds the dense (B,N) multi-hot and gathers it at the top-k ids once
+ * per metric@k, :428-435).  HR/NDCG/RECALL/PRECISION/MRR@k are prefix reductions of this (B,K) matrix. */
+int rb_topk_hits(const int32_t* top_ids, const int64_t* target_crow, const int64_t* target_col, int64_t B,
+                 int K, float* hits, rb_stream_t stream);
+
 /* Upper bound of the workspace an op needs (bytes). nnz = seen-list entries for RB_OP_TOPK_EVAL,
  * number of indices for RB_OP_SCATTER_ADD, else ignored. */
 size_t rb_workspace_bytes(int op, int64_t M, int64_t N, int d, int K, int mode, int64_t nnz);

@@ -34,6 +34,7 @@ SIGNATURES = {
     "rb_ce_du_finish": (_i32, [_p, _p, _p, _p, _p, _i64, _f32, _f32, _p, _i64, _i64, _i32, _i32, _p, _p]),
     "rb_ce_bwd": (_i32, [_p, _p, _p, _f32, _p, _i64, _p, _f32, _p, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _sz, _p]),
     "rb_topk_eval": (_i32, [_p, _p, _p, _f32, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _p, _p, _p, _sz, _p]),
+    "rb_topk_hits": (_i32, [_p, _p, _p, _i64, _i32, _p, _p]),
     "rb_topk_merge": (_i32, [_p, _p, _i32, _i64, _i32, _p, _p, _p]),
     "rb_workspace_bytes": (_sz, [_i32, _i64, _i64, _i32, _i32, _i32, _i64]),
     "rb_launch_count": (_i64, []),

@@ -817,6 +817,19 @@ extern "C" int rb_topk_merge(const float* vals, const int32_t* ids, int R, int64
   return 0;
 }
 
+extern "C" int rb_topk_hits(const int32_t* top_ids, const int64_t* target_crow, const int64_t* target_col, int64_t B,
+                            int K, float* hits, rb_stream_t stream) {
+  DevInfo dv; if (int r = get_dev(dv)) return r;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!top_ids || !target_crow || !hits) return fail(RB_E_ARG, "null pointer");
+  if (B < 0 || K < 1) return fail(RB_E_ARG, "bad shape B=%lld K=%d", (long long)B, K);
+  if (B == 0) return 0;
+  const long long n = B * K;
+  topk_hits_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(top_ids, target_crow, target_col, B, K, hits);
+  RB_LAUNCH_CHECK("topk_hits_kernel");
+  return 0;
+}
+
 // ========================================================================== workspace
 extern "C" size_t rb_workspace_bytes(int op, int64_t M, int64_t N, int d, int K, int mode, int64_t nnz) {
   int sms = 148;  // B200; refined from the current device when there is one

@@ -1039,6 +1039,28 @@ topk_refine_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const flo
   }
 }
 
+// ---- hit matrix of a ranked list: hits[b,k] = 1 if top_ids[b,k] is one of row b's targets (sorted CSR of
+// data[IUnseen], UniSRec/main.py:414), else 0; missing entries (id < 0) never hit.  HR / NDCG / RECALL /
+// PRECISION / MRR @k are prefix reductions of this (B,K) matrix (metrics.py).
+__global__ void topk_hits_kernel(const int* __restrict__ top_ids, const int64_t* __restrict__ tcrow,
+                                 const int64_t* __restrict__ tcol, long long n_rows, int K, float* __restrict__ hits) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_rows * K) return;
+  const long long row = i / K;
+  const long long id = top_ids[i];
+  float h = 0.f;
+  if (id >= 0) {
+    long long lo = tcrow[row], hi = tcrow[row + 1];
+    const long long end = hi;
+    while (lo < hi) {
+      const long long mid = (lo + hi) >> 1;
+      if (__ldg(tcol + mid) < id) lo = mid + 1; else hi = mid;
+    }
+    if (lo < end && __ldg(tcol + lo) == id) h = 1.f;
+  }
+  hits[i] = h;
+}
+
 // ---- merge of R sorted per-shard lists (rb_topk_merge): list l of row i at (l*n_rows + i)*K + e
 template <int E>
 __global__ void topk_merge_kernel(const float* __restrict__ vals, const int* __restrict__ ids, int n_lists,

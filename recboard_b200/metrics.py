@@ -24,6 +24,15 @@ def hits_from_topk(top_ids: torch.Tensor, target_crow: torch.Tensor, target_col:
     ``target_crow/col`` is the CSR of ``data[IUnseen]`` (``Item.to_csr``, UniSRec/main.py:414);
     LOU evaluation has exactly one target per row."""
     B, K = top_ids.shape
+    if top_ids.is_cuda:   # product path: one kernel (rb_topk_hits); the torch lines below serve host-side tests only
+        from . import _lib as L
+        dev = L.require_cuda(top_ids, target_crow, target_col)
+        ids32 = top_ids.to(torch.int32).contiguous()
+        hits = torch.empty(B, K, dtype=torch.float32, device=dev)
+        L.check(L.lib().rb_topk_hits(L.ptr(ids32), L.ptr(target_crow.to(torch.int64).contiguous()),
+                                     L.ptr(target_col.to(torch.int64).contiguous()), B, K, L.ptr(hits), L.stream_ptr(dev)),
+                "rb_topk_hits")
+        return hits
     ids = top_ids.long()
     rows = torch.arange(B, device=ids.device).unsqueeze(1)
     keys = rows * n_items + ids.clamp_min(0)
