@@ -64,6 +64,54 @@ def evaluate_sweep(model, batches: Iterable[Dict], monitors: Sequence[str], n_it
     return {k: m.avg for k, m in meters.items()}
 
 
+class DeviceEvalSplit:
+    """Device-resident seen / target CSR of a whole evaluation split, built ONCE.
+
+    The reference rebuilds the per-row seen and target lists in Python for every batch of every evaluation
+    sweep (row format ``{User, ISeq, IUnseen, ISeen}``, HSTU/sampler.py:107-125; ``Item.to_csr(...)`` per
+    batch, UniSRec/main.py:410-414).  Here the ragged lists of all evaluation rows are turned into two CSRs on
+    the device when the split is set up; a batch is a contiguous row range whose CSR is two slices and one
+    subtraction -- no host work, no host->device copy of id lists during the sweep."""
+
+    def __init__(self, seen_rows, target_rows, device):
+        self.seen_crow, self.seen_col = MX.lists_to_csr(seen_rows, device)
+        self.tgt_crow, self.tgt_col = MX.lists_to_csr(target_rows, device)
+        if self.seen_crow.numel() != self.tgt_crow.numel():
+            raise ValueError("seen and target lists must describe the same rows")
+        self.n_rows = self.seen_crow.numel() - 1
+        # row offsets are read on the host when a batch is cut (two ints per CSR per batch)
+        self._seen_crow_host = self.seen_crow.cpu()
+        self._tgt_crow_host = self.tgt_crow.cpu()
+
+    @staticmethod
+    def _cut(crow, crow_host, col, lo, hi):
+        a, b = int(crow_host[lo]), int(crow_host[hi])
+        return (crow[lo:hi + 1] - a).contiguous(), col[a:b].contiguous()
+
+    def batch(self, lo: int, hi: int):
+        """-> (seen_crow, seen_col, target_crow, target_col) of rows [lo, hi), row offsets rebased to 0."""
+        if not (0 <= lo <= hi <= self.n_rows):
+            raise IndexError(f"rows [{lo}, {hi}) outside the split of {self.n_rows} rows")
+        return (*self._cut(self.seen_crow, self._seen_crow_host, self.seen_col, lo, hi),
+                *self._cut(self.tgt_crow, self._tgt_crow_host, self.tgt_col, lo, hi))
+
+
+@torch.no_grad()
+def evaluate_split(score_topk, split: DeviceEvalSplit, monitors: Sequence[str], n_items: int, batch_size: int,
+                   remove_seen: bool = True, exact: bool = True) -> Dict[str, float]:
+    """The sweep of ``evaluate_sweep`` over a ``DeviceEvalSplit``: ``score_topk(lo, hi, K, seen_crow, seen_col)``
+    returns the sorted (vals, ids) of rows [lo, hi) (e.g. a closure over ``model.recommend_topk``)."""
+    kmax = MX.kmax_of(monitors)
+    meters = {m.upper(): MX.AverageMeter() for m in monitors}
+    for lo in range(0, split.n_rows, batch_size):
+        hi = min(lo + batch_size, split.n_rows)
+        s_crow, s_col, t_crow, t_col = split.batch(lo, hi)
+        _, ids = score_topk(lo, hi, kmax, s_crow if remove_seen else None, s_col if remove_seen else None)
+        for name, v in MX.batch_metrics(ids, t_crow, t_col, n_items, monitors, exact=exact).items():
+            meters[name].update(v, hi - lo)                                         # UniSRec/main.py:428-435, n=bsz
+    return {k: m.avg for k, m in meters.items()}
+
+
 class FusedEvalCoach:
     """Mixin for a ``freerec.launcher.Coach`` subclass (listed before ``Coach`` in the bases).
 

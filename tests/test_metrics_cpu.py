@@ -77,3 +77,37 @@ def test_synth_shapes_and_invariants():
     assert all(int(t[r]) in col[crow[r]:crow[r + 1]].tolist() for r in range(64))
     s = synth.sequences(16, 50, 1000, g, dev)
     assert s.shape == (16, 50) and (s[:, -1] > 0).all() and s.max() <= 1000
+
+
+def test_device_eval_split_matches_per_batch_csr():
+    """SURVEY 8f-4 host logic: the split-wide CSR cut per batch equals the CSR rebuilt from that batch's lists,
+    and the sweep over it reproduces the oracle's bsz-weighted metrics."""
+    import torch
+    from oracle import reference_path as orc
+    from recboard_b200 import evaluate as EV, metrics as MX
+    g = torch.Generator().manual_seed(11)
+    R, N, K = 37, 200, 10
+    seen = [torch.randperm(N, generator=g)[: int(torch.randint(0, 9, (1,), generator=g))].tolist() for _ in range(R)]
+    tgt = [[int(torch.randint(0, N, (1,), generator=g))] for _ in range(R)]
+    split = EV.DeviceEvalSplit(seen, tgt, torch.device("cpu"))
+    for lo, hi in ((0, 16), (16, 32), (32, 37), (5, 5)):
+        sc, sl, tc, tl = split.batch(lo, hi)
+        rc, rl = orc.lists_to_csr(seen[lo:hi])
+        assert torch.equal(sc, rc) and torch.equal(sl, rl)
+        rc, rl = orc.lists_to_csr(tgt[lo:hi])
+        assert torch.equal(tc, rc) and torch.equal(tl, rl)
+    U, W = torch.randn(R, 16, generator=g), torch.randn(N, 16, generator=g)
+    mons = ["HITRATE@5", "NDCG@10", "HITRATE@10"]
+
+    def score_topk(lo, hi, k, crow, col):
+        S = orc.score_dense(U[lo:hi], W)
+        return orc.topk_sorted(orc.mask_seen(S, crow, col) if crow is not None else S, k)
+
+    got = EV.evaluate_split(score_topk, split, mons, N, batch_size=16)
+    meters = {m: MX.AverageMeter() for m in mons}
+    for lo in range(0, R, 16):
+        hi = min(lo + 16, R)
+        sc, sl = orc.lists_to_csr(seen[lo:hi]); tc, tl = orc.lists_to_csr(tgt[lo:hi])
+        for m, v in orc.evaluate_batch(orc.score_dense(U[lo:hi], W), sc, sl, tc, tl, mons).items():
+            meters[m].update(v, hi - lo)
+    assert got == {m: meters[m].avg for m in mons}
