@@ -254,25 +254,56 @@ def run_ours(args):
     pairs_per_step = 2 * ROWS * n_total
     value = pairs_per_step * args.steps / (ms * 1e-3)
 
-    # ---- end-to-end: host buffers in, host results out, every step
+    # ---- end-to-end: host buffers in, host results out, every step.  Written the way a training / evaluation
+    #      loop is: the pinned inputs of step i+1 travel on a copy stream while step i computes, and the host
+    #      reduction of step i's results (loss value, exact float32 metric means from the (B,K) hit matrix)
+    #      runs while step i+1 is on the GPU.  Every step's inputs are copied in and every step's results are
+    #      copied out and consumed inside the timed region.
     pin = lambda x: x.cpu().pin_memory()
-    hU, hl, hs, hUe, hc, hcol = pin(U_train), pin(labels), pin(seqs), pin(U_eval), pin(seen_crow), pin(seen_col)
-    h2d = sum(x.numel() * x.element_size() for x in (hU, hl, hs, hUe, hc, hcol))
+    hosts = [pin(x) for x in (U_train, labels, seqs, U_eval, seen_crow, seen_col)]
+    h2d = sum(x.numel() * x.element_size() for x in hosts)
     d2h = 4 + ROWS * TOPK * 4
+    copy_stream = torch.cuda.Stream(device=dev)
+    h_loss = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    h_hits = [torch.empty(ROWS, TOPK, dtype=torch.float32).pin_memory() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+    n_t_host = (tgt_crow[1:] - tgt_crow[:-1]).float().cpu()
 
-    def e2e_step():
-        dU_, dl, dsq, dUe, dc, dcol = (x.to(dev, non_blocking=True) for x in (hU, hl, hs, hUe, hc, hcol))
-        loss, ids, _ = hot_path(dU_, dl, dsq, dUe, dc, dcol)
-        loss_host = loss.item()
-        res = MX.batch_metrics(ids, tgt_crow, tgt, n_total, monitors, exact=True)   # reads the (B,K) hit matrix back
-        return loss_host, res
+    def stage_inputs():
+        with torch.cuda.stream(copy_stream):
+            ts = [x.to(dev, non_blocking=True) for x in hosts]
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ts, ev
 
-    for _ in range(2):
-        e2e_step()
+    def consume(slot):
+        done[slot].synchronize()
+        return float(h_loss[slot][0]), MX.metrics_from_hits(h_hits[slot], n_t_host, monitors)
+
+    def e2e_loop(n):
+        out = None
+        staged = stage_inputs()
+        for i in range(n):
+            cur, ev = staged
+            main = torch.cuda.current_stream()
+            main.wait_event(ev)
+            for t_ in cur:
+                t_.record_stream(main)
+            if i + 1 < n:
+                staged = stage_inputs()
+            loss, ids, _ = hot_path(*cur)
+            hits = MX.hits_from_topk(ids, tgt_crow, tgt, n_total)
+            h_loss[i & 1].copy_(loss.detach().reshape(1), non_blocking=True)
+            h_hits[i & 1].copy_(hits, non_blocking=True)
+            done[i & 1].record()
+            if i > 0:
+                out = consume((i - 1) & 1)
+        return consume((n - 1) & 1) if n > 0 else out
+
+    e2e_loop(2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        loss_host, res = e2e_step()
+    loss_host, res = e2e_loop(args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None   # sampled over both timed regions (device-timed and end-to-end)
@@ -351,7 +382,9 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (256 MB table shard streamed per sweep); no flush"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "loss": loss_host, "metrics": res},
+                    "loss": loss_host, "metrics": res,
+                    "how": "pinned host inputs copied in and loss + (B,K) hit matrix copied out every step; the copy of step "
+                           "i+1 and the host metric reduction of step i-1 overlap step i"},
             "gpu_launches": launches,
             "roofline": roofline, "breakdown": breakdown, "cpu_baseline": cpu_baseline,
         }

@@ -79,6 +79,12 @@ def batch_metrics(top_ids: torch.Tensor, target_crow: torch.Tensor, target_col: 
     n_t = (target_crow[1:] - target_crow[:-1]).float()
     if exact:
         hits, n_t = hits.cpu(), n_t.cpu()
+    return metrics_from_hits(hits, n_t, monitors)
+
+
+def metrics_from_hits(hits: torch.Tensor, n_t: torch.Tensor, monitors: Sequence[str]) -> Dict[str, float]:
+    """Batch means of every ``METRIC@k`` from a (B,K) hit matrix and the per-row target counts (same float32
+    torch reductions as the oracle when both live on the host)."""
     out = {}
     for mon in monitors:
         name, k = mon.split("@")
