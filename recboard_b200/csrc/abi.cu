@@ -294,7 +294,7 @@ static size_t scatter_ws_bytes(long long n_idx, int d) {
   const long long chunks = (n_idx + RS_CHUNK - 1) / RS_CHUNK;
   const long long blocks = (n_idx + SEG_BLOCK - 1) / SEG_BLOCK;
   return static_cast<size_t>(n_idx) * 4 * 4 + static_cast<size_t>(chunks) * 256 * 4 +
-         2 * static_cast<size_t>(blocks) * d * 4 + 8 * 256;
+         2 * static_cast<size_t>(blocks) * d * 4 + 256 * 4 + 10 * 256;
 }
 // grad_table[idx[i]-idx_base] += alpha*(*alpha_dev) * grad_out[i] in a fixed order; optionally
 // cnt_out[row] += cnt_alpha*(*alpha_dev) * (#occurrences of row)
@@ -313,6 +313,7 @@ static int scatter_add_impl(const void* grad_out, const int64_t* idx, long long 
   uint32_t* k0 = b.take<uint32_t>(n); uint32_t* v0 = b.take<uint32_t>(n);
   uint32_t* k1 = b.take<uint32_t>(n); uint32_t* v1 = b.take<uint32_t>(n);
   uint32_t* hist = b.take<uint32_t>(static_cast<size_t>(chunks) * 256);
+  uint32_t* totals = b.take<uint32_t>(256);
   const int seg_blocks = (n + SEG_BLOCK - 1) / SEG_BLOCK;
   float* lead = b.take<float>(static_cast<size_t>(seg_blocks) * d);
   float* trail = b.take<float>(static_cast<size_t>(seg_blocks) * d);
@@ -323,8 +324,15 @@ static int scatter_add_impl(const void* grad_out, const int64_t* idx, long long 
   for (int shift = 0; shift < bits; shift += 8) {
     rs_hist_kernel<<<chunks, 256, 0, st>>>(k0, n, shift, hist, chunks);
     RB_LAUNCH_CHECK("rs_hist_kernel");
-    rs_scan_kernel<<<1, 1024, 0, st>>>(hist, chunks * 256);
-    RB_LAUNCH_CHECK("rs_scan_kernel");
+    if (chunks <= 256) {   // small: one block scans everything
+      rs_scan_kernel<<<1, 1024, 0, st>>>(hist, chunks * 256);
+      RB_LAUNCH_CHECK("rs_scan_kernel");
+    } else {               // large: one block per digit, coalesced
+      rs_digit_totals_kernel<<<256, 256, 0, st>>>(hist, chunks, totals);
+      RB_LAUNCH_CHECK("rs_digit_totals_kernel");
+      rs_scan_rows_kernel<<<256, 256, 0, st>>>(hist, chunks, totals);
+      RB_LAUNCH_CHECK("rs_scan_rows_kernel");
+    }
     rs_scatter_kernel<<<(chunks + RS_SCATTER_WARPS - 1) / RS_SCATTER_WARPS, 32 * RS_SCATTER_WARPS, 0, st>>>(k0, v0, k1, v1, n, shift, hist, chunks);
     RB_LAUNCH_CHECK("rs_scatter_kernel");
     std::swap(k0, k1); std::swap(v0, v1);

@@ -271,6 +271,55 @@ __global__ void rs_scan_kernel(uint32_t* __restrict__ hist, int total) {
   for (int i = beg; i < end; ++i) { const uint32_t v = hist[i]; hist[i] = run; run += v; }
 }
 
+// Large inputs: the same exclusive scan in two coalesced kernels, one block per digit.
+//   rs_digit_totals: totals[d] = sum of row d of hist (256 rows of n_chunks counters)
+//   rs_scan_rows:    row d becomes its exclusive scan, offset by the sum of the totals of all smaller digits
+__global__ void rs_digit_totals_kernel(const uint32_t* __restrict__ hist, int n_chunks, uint32_t* __restrict__ totals) {
+  __shared__ uint32_t red[256];
+  const uint32_t* row = hist + static_cast<long long>(blockIdx.x) * n_chunks;
+  uint32_t s = 0;
+  for (int i = threadIdx.x; i < n_chunks; i += 256) s += row[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o >= 1; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) totals[blockIdx.x] = red[0];
+}
+__global__ void rs_scan_rows_kernel(uint32_t* __restrict__ hist, int n_chunks, const uint32_t* __restrict__ totals) {
+  __shared__ uint32_t part[256];
+  __shared__ uint32_t carry_s;
+  uint32_t* row = hist + static_cast<long long>(blockIdx.x) * n_chunks;
+  // base = sum of totals of smaller digits
+  uint32_t b = (threadIdx.x < blockIdx.x) ? totals[threadIdx.x] : 0u;
+  part[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o >= 1; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) carry_s = part[0];
+  __syncthreads();
+  for (int base = 0; base < n_chunks; base += 256) {
+    const int i = base + threadIdx.x;
+    const uint32_t v = (i < n_chunks) ? row[i] : 0u;
+    part[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {   // inclusive Hillis-Steele scan of the 256-entry tile
+      const uint32_t u = (threadIdx.x >= o) ? part[threadIdx.x - o] : 0u;
+      __syncthreads();
+      part[threadIdx.x] += u;
+      __syncthreads();
+    }
+    const uint32_t carry = carry_s;
+    if (i < n_chunks) row[i] = carry + part[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 255) carry_s = carry + part[255];
+    __syncthreads();
+  }
+}
+
 __global__ void rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                   uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n, int shift,
                                   const uint32_t* __restrict__ offs, int n_chunks) {
@@ -434,21 +483,29 @@ scatter_split_runs_kernel(const uint32_t* __restrict__ keys, float* __restrict__
   const uint32_t same = __ballot_sync(0xffffffffu, kl == key);
   const int j0 = __ffs(same) - 1;
   if (j0 == 0 && p0 > 0 && keys[p0 - 1] == key) return;  // the run began earlier: not the owner
-  // last block of the run and the run's length
-  int nb = b + 1;
-  while (true) {
-    const int q0 = nb * SEG_BLOCK;
-    if (q0 + SEG_BLOCK < n && keys[q0 + SEG_BLOCK - 1] == key && keys[q0 + SEG_BLOCK] == key) ++nb; else break;
+  // end of the run (first position whose key differs) by binary search over the sorted keys; hot rows span
+  // thousands of blocks
+  int lo = p0 + SEG_BLOCK, hi = n;   // keys[lo] == key is known
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (keys[mid] == key) lo = mid + 1; else hi = mid;
   }
-  const int q0 = nb * SEG_BLOCK;
-  const int qi = q0 + lane;
-  const uint32_t tail_same = __ballot_sync(0xffffffffu, qi < n && keys[qi] == key);
-  const int run_len = (SEG_BLOCK - j0) + (nb - b - 1) * SEG_BLOCK + __popc(tail_same);
+  const int run_end = lo;                              // exclusive
+  const int nb = (run_end - 1) / SEG_BLOCK;            // last block that holds a piece of the run
+  const int run_len = run_end - (p0 + j0);
   const float adev = (alpha_dev != nullptr) ? __ldg(alpha_dev) : 1.f;
   const float al = alpha * adev;
   for (int c = lane * 4; c < d; c += 128) {
     float4 acc = *reinterpret_cast<const float4*>(trail + static_cast<long long>(b) * d + c);
-    for (int x = b + 1; x <= nb; ++x) {
+    int x = b + 1;
+    for (; x + 8 <= nb + 1; x += 8) {   // eight partials in flight, added in block order
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float4*>(lead + static_cast<long long>(x + u) * d + c);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
+    for (; x <= nb; ++x) {
       const float4 v = *reinterpret_cast<const float4*>(lead + static_cast<long long>(x) * d + c);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
