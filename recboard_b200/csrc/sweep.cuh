@@ -232,9 +232,27 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
       int stat_tile, split, t0, t1;
       item_range(item, stat_tile, split, t0, t1);
       mbar_wait(&bar->x_full, k & 1);
+      // EPI_CAND: a (stationary tile, streamed tile) pair in which no 32-row group is flagged (no row can reach
+      // its threshold there: ~44 % of the pairs at K = 50, N = 1M) needs no scores at all -- its MMAs are
+      // skipped, only the S-buffer hand-shake is kept.  Lanes 0..4*XT-1 fetch one group flag each, one tile ahead.
+      unsigned int f_next = 1u;
+      auto fetch_flags = [&](int t) -> unsigned int {
+        if (lane < 4 * C::XT) {
+          const int stile = (C::XT == 1) ? stat_tile : stat_tile * 2 + (lane >> 2);
+          return __ldg(a.tile_flag + static_cast<long long>(stile * 4 + (lane & 3)) * a.n_strm_tiles + t);
+        }
+        return 0u;
+      };
+      if (C::EPI == EPI_CAND) f_next = fetch_flags(t0);
       for (int t = t0; t < t1; ++t, ++it) {
         const uint32_t buf = it & 1, sph = (it >> 1) & 1;
         const uint32_t cs = it * C::SPT;   // first stage of this streamed tile
+        uint32_t live = 3u;                // bit x: stationary tile x needs this streamed tile's scores
+        if (C::EPI == EPI_CAND) {
+          const uint32_t m = __ballot_sync(0xffffffffu, f_next != 0u);
+          live = ((m & 0x0Fu) ? 1u : 0u) | ((m & 0xF0u) ? 2u : 0u);
+          if (t + 1 < t1) f_next = fetch_flags(t + 1);
+        }
 #pragma unroll
         for (int x = 0; x < C::XT; ++x)    // S buffer: XT=1 per tile parity, XT=2 per (X tile, parity)
           mbar_wait(&bar->s_empty[(C::XT == 1) ? buf : x * 2 + buf], sph ^ 1);
@@ -264,12 +282,14 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
               const uint32_t bidx = (C::XT == 1) ? buf : x * 2 + buf;
               const uint32_t d_tmem = tmem_base + bidx * C::BN;
               const uint32_t xs_lo = x_lo + ((x * C::XTILE_BYTES + ac * 128 * 128) >> 4);
+              if ((live >> x) & 1u) {
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                const uint64_t ad = smem_desc(dhi, xs_lo + ((kk * 32) >> 4));
-                const uint64_t bd = smem_desc(dhi, ys_lo + ((kk * 32) >> 4));
-                if (C::DT == DT_BF16) mma_f16_ss(d_tmem, ad, bd, idesc1, (p | kk) != 0);
-                else mma_tf32_ss(d_tmem, ad, bd, idesc1, (p | kk) != 0);
+                for (int kk = 0; kk < 4; ++kk) {
+                  const uint64_t ad = smem_desc(dhi, xs_lo + ((kk * 32) >> 4));
+                  const uint64_t bd = smem_desc(dhi, ys_lo + ((kk * 32) >> 4));
+                  if (C::DT == DT_BF16) mma_f16_ss(d_tmem, ad, bd, idesc1, (p | kk) != 0);
+                  else mma_tf32_ss(d_tmem, ad, bd, idesc1, (p | kk) != 0);
+                }
               }
               if (p == C::NPAIR - 1) tc_commit(&bar->s_full[bidx]);
             }
