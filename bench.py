@@ -39,8 +39,8 @@ SEQ = 50
 TOPK = 50
 METRIC = "full-catalog scored user-item pairs/sec (CE train + top-K eval)"
 # dram__bytes_read.sum + dram__bytes_write.sum of one pair_kernel<PASS_DW> launch at this workload (ncu --set full)
-PROFILED_TRAFFIC_BYTES = 257_265_664 + 458_226_176
-PROFILED_TRAFFIC_SOURCE = "profiles/r1l_ncu_summary.md (ncu --set full, one launch, N=1M shard)"
+PROFILED_TRAFFIC_BYTES = 257_902_592 + 458_749_440
+PROFILED_TRAFFIC_SOURCE = "profiles/r1m_ncu_summary.md (ncu --set full, one launch, N=1M shard)"
 UNIT = "pairs/s"
 
 
