@@ -240,6 +240,85 @@ def gen_gather_backward():
     print("embedding_bwd ok")
 
 
+def gen_pool_and_sampled():
+    """pool ranking of SASRec (SASRec/main.py:230-236) and HSTU (cosine), HSTU's table
+    normalisation (HSTU/main.py:180-184) and its sampled-softmax fit (HSTU/main.py:186-202) with the
+    negatives recorded, so the fused gather-dot can be checked against the reference's own numbers."""
+    N, d, B, S = 150, 32, 8, 10
+    torch.manual_seed(2032)
+    ref = shim.load_reference("SASRec", loss="CE", embedding_dim=d, maxlen=S, dropout_rate=0.0)
+    model = ref.SASRec(shim.RecDataSet(n_users=B, n_items=N))
+    model.eval()
+    g = torch.Generator().manual_seed(17)
+    ISeq = _seqs(g, B, S, N)
+    pool = torch.randint(0, N, (B, 21), generator=g)
+    data = {model.ISeq: ISeq, model.IUnseen: pool}
+    with torch.no_grad():
+        uE, iE = model.encode(data)
+        scores = model(data, ranking="pool")
+    np.savez_compressed(OUT / "sasrec_pool.npz", U=_np(uE[:, -1, :]), W=_np(iE), pool=_np(pool), scores_pool=_np(scores))
+    print("sasrec_pool: scores", tuple(scores.shape))
+
+    torch.manual_seed(2033)
+    ref = shim.load_reference("HSTU", embedding_dim=d, maxlen=S)
+    model = ref.HSTU(shim.RecDataSet(n_users=B, n_items=N))
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    g = torch.Generator().manual_seed(18)
+    ISeq = _seqs(g, B, S, N)
+    Time = torch.sort(torch.randint(0, 10_000_000, (B, S), generator=g), dim=1).values
+    IPos = torch.randint(0, N, (B, S), generator=g)
+    model.eval()
+    with torch.no_grad():
+        data = {model.ISeq: ISeq, model.Time: Time, model.IUnseen: pool}
+        uE, iE = model.encode(data)
+        pool_scores = model(data, ranking="pool")
+    # the sampled-softmax fit, with the negatives it drew recorded from outside
+    model.train()
+    drawn = {}
+    orig = model._sample_negatives
+
+    def recording(userEmbds):
+        drawn["neg"] = orig(userEmbds)
+        return drawn["neg"]
+
+    model._sample_negatives = recording
+    cache = _capture_encode(model)
+    data = {model.ISeq: ISeq, model.Time: Time, model.IPos: IPos}
+    loss = model(data)["rec_loss"]
+    loss.backward()
+    uE_t, iE_t = cache["out"]
+    indices = ISeq != 0
+    np.savez_compressed(
+        OUT / "hstu_sampled.npz", table=_np(model.Item.embeddings.weight), W_norm=_np(iE),
+        U_pool=_np(uE[:, -1, :]), pool=_np(pool), scores_pool=_np(pool_scores),
+        U_fit=_np(uE_t[indices]), W_fit=_np(iE_t), positives=_np(IPos[indices]), negatives=_np(drawn["neg"]),
+        temperature=np.float32(ref.cfg.temperature), loss=_np(loss),
+        dU_fit=_np(uE_t.grad[indices]), dW_fit=_np(iE_t.grad),
+    )
+    print("hstu_sampled: loss", float(loss), "negatives", tuple(drawn["neg"].shape))
+
+
+def gen_lightgcn_propagation():
+    """LightGCN.encode (LightGCN/main.py:77-88) -- adjacency in CSR, tables in, propagated tables out."""
+    U_, N, d = 60, 140, 32
+    torch.manual_seed(2034)
+    ref = shim.load_reference("LightGCN", embedding_dim=d)
+    model = ref.LightGCN(shim.RecDataSet(n_users=U_, n_items=N))
+    with torch.no_grad():
+        model.User.embeddings.weight.normal_(0, 0.3)
+        model.Item.embeddings.weight.normal_(0, 0.3)
+        uE, iE = model.encode()
+    A = model.Adj
+    np.savez_compressed(
+        OUT / "lightgcn_prop.npz", crow=_np(A.crow_indices()), col=_np(A.col_indices()), val=_np(A.values()),
+        user_table=_np(model.User.embeddings.weight), item_table=_np(model.Item.embeddings.weight),
+        num_layers=np.int64(model.num_layers), user_out=_np(uE), item_out=_np(iE),
+    )
+    print("lightgcn_prop: nnz", int(A.values().numel()), "layers", int(model.num_layers))
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(1)  # deterministic summation order for the committed vectors
@@ -249,6 +328,8 @@ def main():
     gen_mf_lightgcn()
     gen_hstu()
     gen_gather_backward()
+    gen_pool_and_sampled()
+    gen_lightgcn_propagation()
 
 
 if __name__ == "__main__":

@@ -102,6 +102,36 @@ def test_golden_hstu_and_gru4rec_scores(ops, golden):
         assert_rel(ops.score_dense(dev(T(g[Uk])), dev(T(g["W"])), precision="fp32"), g["scores_full"], FP32_RTOL, name)
 
 
+def test_golden_pool_sampled_and_propagation(ops, golden):
+    """The f-rows against the numbers the reference's own model files produced: SASRec / HSTU pool scores,
+    HSTU table normalisation + sampled-softmax fit (loss, dU, dense dW), LightGCN propagation."""
+    g = golden("sasrec_pool")
+    assert_rel(ops.gather_dot(dev(T(g["U"])), dev(T(g["W"])), dev(T(g["pool"]))), g["scores_pool"], FP32_RTOL, "sasrec pool")
+    h = golden("hstu_sampled")
+    Wn = ops.normalize_rows(dev(T(h["table"]))[1:])
+    assert_rel(Wn, h["W_norm"], 1e-6, "normalised table")
+    assert_rel(ops.gather_dot(dev(T(h["U_pool"])), Wn, dev(T(h["pool"]))), h["scores_pool"], FP32_RTOL, "hstu pool")
+    U, W = dev(T(h["U_fit"])).requires_grad_(True), dev(T(h["W_fit"])).requires_grad_(True)
+    cand = torch.cat((T(h["positives"]).unsqueeze(-1), T(h["negatives"])), dim=1)
+    logits = ops.gather_dot(U, W, dev(cand), scale=1.0 / float(h["temperature"]))
+    loss = torch.nn.functional.cross_entropy(logits, torch.zeros(len(U), dtype=torch.long, device="cuda"))
+    loss.backward()
+    assert abs(float(loss.detach()) - float(h["loss"])) <= FP32_RTOL * abs(float(h["loss"]))
+    assert_rel(U.grad, h["dU_fit"], 2e-5, "sampled-softmax dU")
+    assert_rel(W.grad, h["dW_fit"], 2e-5, "sampled-softmax dW")
+    p = golden("lightgcn_prop")
+    nU = p["user_table"].shape[0]
+    n = nU + p["item_table"].shape[0]
+    A = torch.sparse_csr_tensor(T(p["crow"]), T(p["col"]), T(p["val"]), (n, n)).cuda()
+    L = int(p["num_layers"])
+    x = dev(torch.cat((T(p["user_table"]), T(p["item_table"]))))
+    avg = x / (L + 1)
+    for _ in range(L):
+        x = ops.spmm_raw(A, x, acc=avg, beta=1.0 / (L + 1))    # propagation + layer average in one pass
+    assert_rel(avg[:nU], p["user_out"], FP32_RTOL, "lightgcn users")
+    assert_rel(avg[nU:], p["item_out"], FP32_RTOL, "lightgcn items")
+
+
 def test_golden_embedding_forward_backward(ops, golden):
     g = golden("embedding_bwd")
     table, idx, go = T(g["table"]), T(g["idx"]), T(g["grad_out"])

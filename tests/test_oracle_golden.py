@@ -128,3 +128,38 @@ def test_topk_tie_policy_and_topk_metrics_agree():
         parts.append((v, i + a))
     mv, mi = orc.merge_topk(parts, 10)
     assert torch.equal(mi, ids) and torch.equal(mv, vals)
+
+
+def test_pool_scores_and_hstu_sampled_fit(golden):
+    """the oracle's gather-dot, normalisation and sampled-softmax restatement against the
+    reference's own recommend_from_pool / encode / fit outputs (SASRec/main.py:230-236, HSTU/main.py:180-202)."""
+    g = golden("sasrec_pool")
+    close(orc.gather_dot(T(g["U"]), T(g["W"]), T(g["pool"])), g["scores_pool"])
+    h = golden("hstu_sampled")
+    close(orc.normalize_rows(T(h["table"])[1:]), h["W_norm"], rtol=1e-6)
+    close(orc.gather_dot(T(h["U_pool"]), T(h["W_norm"]), T(h["pool"])), h["scores_pool"])
+    U = T(h["U_fit"]).clone().requires_grad_(True)
+    W = T(h["W_fit"]).clone().requires_grad_(True)
+    cand = torch.cat((T(h["positives"]).unsqueeze(-1), T(h["negatives"])), dim=1)
+    logits = orc.gather_dot(U, W, cand, 1.0 / float(h["temperature"]))
+    loss = torch.nn.functional.cross_entropy(logits, torch.zeros(len(U), dtype=torch.long))
+    loss.backward()
+    assert abs(float(loss) - float(h["loss"])) <= 1e-5 * abs(float(h["loss"]))
+    close(U.grad, h["dU_fit"], rtol=2e-5)
+    close(W.grad, h["dW_fit"], rtol=2e-5)
+
+
+def test_lightgcn_propagation(golden):
+    """L rounds of A @ X with the layer average (LightGCN/main.py:77-88)."""
+    g = golden("lightgcn_prop")
+    nU = g["user_table"].shape[0]
+    n = nU + g["item_table"].shape[0]
+    A = torch.sparse_csr_tensor(T(g["crow"]), T(g["col"]), T(g["val"]), (n, n))
+    L = int(g["num_layers"])
+    x = torch.cat((T(g["user_table"]), T(g["item_table"])))
+    avg = x / (L + 1)
+    for _ in range(L):
+        x = orc.spmm(A, x)
+        avg = avg + x / (L + 1)
+    close(avg[:nU], g["user_out"])
+    close(avg[nU:], g["item_out"])
