@@ -132,6 +132,16 @@ int rb_ce_bwd(const void* U, const void* W, const float* bias, float scale, cons
               int64_t M, int64_t N, int d, int dtype, int mode, float* dU, float* dW, float* dbias,
               void* ws, size_t ws_bytes, rb_stream_t stream);
 
+/* rb_ce_bwd's dW (+ dbias) with the gradient stored in bf16 (the dtype of a bf16 parameter): the pass
+ * writes bf16 rows directly instead of an fp32 (N,d) matrix that the caller would cast (1.5 N d bytes less
+ * traffic, one pass less); rows that receive the exact fp32 one-hot correction go through an fp32 side
+ * table first, so every element is the correctly rounded fp32 value rb_ce_bwd would have produced.
+ * bf16 mode, d <= 128, scale > 0; workspace RB_OP_CE_BWD. */
+int rb_ce_bwd_dw_bf16(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
+                      int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
+                      int64_t M, int64_t N, int d, void* dW_bf16, float* dbias, void* ws, size_t ws_bytes,
+                      rb_stream_t stream);
+
 /* Masked full-catalog top-K: for every query row the K best (score desc, id asc) items among this
  * shard's N items, skipping ids in the row's seen list (CSR over GLOBAL ids, sorted ascending per
  * row; pass NULL/NULL to keep seen items).  top_ids are global (id_base + local); missing entries

@@ -33,6 +33,7 @@ SIGNATURES = {
     "rb_ce_fwd": (_i32, [_p, _p, _p, _f32, _p, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _sz, _p]),
     "rb_ce_du_finish": (_i32, [_p, _p, _p, _p, _p, _i64, _f32, _f32, _p, _i64, _i64, _i32, _i32, _p, _p]),
     "rb_ce_bwd": (_i32, [_p, _p, _p, _f32, _p, _i64, _p, _f32, _p, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _sz, _p]),
+    "rb_ce_bwd_dw_bf16": (_i32, [_p, _p, _p, _f32, _p, _i64, _p, _f32, _p, _i64, _i64, _i32, _p, _p, _p, _sz, _p]),
     "rb_topk_eval": (_i32, [_p, _p, _p, _f32, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _p, _p, _p, _sz, _p]),
     "rb_topk_hits": (_i32, [_p, _p, _p, _i64, _i32, _p, _p]),
     "rb_topk_merge": (_i32, [_p, _p, _i32, _i64, _i32, _p, _p, _p]),
@@ -102,13 +103,15 @@ def require_cuda(*tensors) -> torch.device:
 
 
 class Workspace:
-    """Grow-only per-device scratch buffer handed to the C ABI (the library never allocates)."""
+    """Grow-only scratch buffer handed to the C ABI (the library never allocates), one per (device, stream):
+    calls on the same stream are ordered and may share it, calls on different streams must not."""
 
     _bufs = {}
 
     @classmethod
     def get(cls, device: torch.device, nbytes: int) -> torch.Tensor:
-        key = (device.index if device.index is not None else torch.cuda.current_device())
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        key = (index, torch.cuda.current_stream(device).cuda_stream)
         buf = cls._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)

@@ -554,9 +554,28 @@ extern "C" int rb_ce_du_finish(const float* dU_unnorm, const float* row_max, con
 static int ce_bwd_dw_pair(const DevInfo& dv, const void* U, const void* W, const float* bias, float scale,
                           const int64_t* labels, int64_t label_base, const float* lse2, float grad_scale,
                           const float* grad_scale_dev, int64_t M, int64_t N, int d, float* dW, float* dbias, Bump& b,
-                          cudaStream_t st) {
+                          cudaStream_t st, __nv_bfloat16* dW_bf16 = nullptr) {
   Plan p = make_plan(N, M, dv.sms, 64, 8, 256);
   const long long n_pad = 1ll * p.n_stat_tiles * 256;
+  // bf16 gradient requested: with one split the kernel stores bf16 rows directly (label rows also in fp32 in a
+  // side table, corrected there, then rounded); with several splits the fp32 path runs in the workspace and
+  // is rounded at the end.
+  const bool direct_bf16 = dW_bf16 != nullptr && p.n_splits == 1;
+  if (dW_bf16 != nullptr && !direct_bf16) dW = b.take<float>(static_cast<size_t>(N) * d);
+  int* slot_of_row = nullptr; int64_t* slot_idx = nullptr; float* side = nullptr; float* cnt_side = nullptr;
+  if (direct_bf16) {
+    slot_of_row = b.take<int>(N);
+    slot_idx = b.take<int64_t>(M);
+    side = b.take<float>(static_cast<size_t>(M) * d);
+    cnt_side = b.take<float>(M);
+    if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
+    RB_CUDA(cudaMemsetAsync(slot_of_row, 0xFF, static_cast<size_t>(N) * 4, st));
+    RB_CUDA(cudaMemsetAsync(cnt_side, 0, static_cast<size_t>(M) * 4, st));
+    dw_slot_assign_kernel<<<(int)((M + 255) / 256), 256, 0, st>>>(labels, label_base, N, (int)M, slot_of_row);
+    RB_LAUNCH_CHECK("dw_slot_assign_kernel");
+    dw_slot_index_kernel<<<(int)((M + 255) / 256), 256, 0, st>>>(labels, label_base, N, (int)M, slot_of_row, slot_idx);
+    RB_LAUNCH_CHECK("dw_slot_index_kernel");
+  }
   float* part = (p.n_splits > 1) ? b.take<float>(static_cast<size_t>(p.n_splits) * N * d) : dW;
   float* rs_part = nullptr;
   if (dbias) rs_part = (p.n_splits > 1) ? b.take<float>(static_cast<size_t>(p.n_splits) * N) : dbias;
@@ -574,6 +593,7 @@ static int ce_bwd_dw_pair(const DevInfo& dv, const void* U, const void* W, const
   a.n_stat = (int)N; a.n_strm = (int)M; a.n_pair_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
   a.n_splits = p.n_splits; a.d = d; a.stat_pad = (int)n_pad; a.scale = scale; a.bias2_stat = bias2; a.aux = lse2;
   a.gscale = grad_scale * scale; a.rscale = grad_scale; a.gscale_dev = grad_scale_dev; a.acc_out = part; a.rowsum_out = rs_part;
+  if (direct_bf16) { a.out_bf16 = dW_bf16; a.slot_of_row = slot_of_row; a.side = side; }
   if (int r = launch_pair<PASS_DW>(kc_for(d, RB_MODE_BF16), bias_cfg, ts, ty, a, p.grid, st)) return r;
   if (p.n_splits > 1) {
     const long long n = N * d;
@@ -586,8 +606,23 @@ static int ce_bwd_dw_pair(const DevInfo& dv, const void* U, const void* W, const
   }
   void* sws = b.take<char>(scatter_ws_bytes(M, d));
   if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
-  return scatter_add_impl(U, labels, label_base, dW, M, N, d, RB_DTYPE_BF16, -1, -grad_scale * scale, grad_scale_dev,
-                          dbias, -grad_scale, sws, scatter_ws_bytes(M, d), st);
+  if (direct_bf16) {
+    // one-hot correction on the side table (keys = slots), then the corrected rows are rounded into dW
+    if (int r = scatter_add_impl(U, slot_idx, 0, side, M, M, d, RB_DTYPE_BF16, -1, -grad_scale * scale, grad_scale_dev,
+                                 dbias ? cnt_side : nullptr, -grad_scale, sws, scatter_ws_bytes(M, d), st)) return r;
+    dw_side_finish_kernel<<<(int)((M * 32 + 255) / 256), 256, 0, st>>>(labels, label_base, N, (int)M, d, slot_of_row, side,
+                                                                        cnt_side, dW_bf16, dbias);
+    RB_LAUNCH_CHECK("dw_side_finish_kernel");
+    return 0;
+  }
+  if (int r = scatter_add_impl(U, labels, label_base, dW, M, N, d, RB_DTYPE_BF16, -1, -grad_scale * scale, grad_scale_dev,
+                               dbias, -grad_scale, sws, scatter_ws_bytes(M, d), st)) return r;
+  if (dW_bf16 != nullptr) {
+    const long long n = N * d;
+    cast_f32_bf16_kernel<<<(int)std::min<long long>((n / 4 + 255) / 256, dv.sms * 16), 256, 0, st>>>(dW, dW_bf16, n);
+    RB_LAUNCH_CHECK("cast_f32_bf16_kernel");
+  }
+  return 0;
 }
 
 // ------------------------------------------------------------- fp32-parity CE backward
@@ -673,17 +708,40 @@ static int ce_bwd_f32(const DevInfo& dv, const float* U, const float* W, const f
   return 0;
 }
 
+static int ce_bwd_impl(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
+                       int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
+                       int64_t M, int64_t N, int d, int dtype, int mode, float* dU, float* dW, float* dbias,
+                       void* ws, size_t ws_bytes, rb_stream_t stream, void* dW_bf16);
+
 extern "C" int rb_ce_bwd(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
                          int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
                          int64_t M, int64_t N, int d, int dtype, int mode, float* dU, float* dW, float* dbias,
                          void* ws, size_t ws_bytes, rb_stream_t stream) {
+  return ce_bwd_impl(U, W, bias, scale, labels, label_base, lse, grad_scale, grad_scale_dev, M, N, d, dtype, mode, dU, dW,
+                     dbias, ws, ws_bytes, stream, nullptr);
+}
+
+extern "C" int rb_ce_bwd_dw_bf16(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
+                                 int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
+                                 int64_t M, int64_t N, int d, void* dW_bf16, float* dbias, void* ws, size_t ws_bytes,
+                                 rb_stream_t stream) {
+  if (!dW_bf16) return fail(RB_E_ARG, "null output");
+  if (reinterpret_cast<uintptr_t>(dW_bf16) & 15) return fail(RB_E_ALIGN, "dW must be 16-byte aligned");
+  return ce_bwd_impl(U, W, bias, scale, labels, label_base, lse, grad_scale, grad_scale_dev, M, N, d, RB_DTYPE_BF16,
+                     RB_MODE_BF16, nullptr, nullptr, dbias, ws, ws_bytes, stream, dW_bf16);
+}
+
+static int ce_bwd_impl(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
+                       int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
+                       int64_t M, int64_t N, int d, int dtype, int mode, float* dU, float* dW, float* dbias,
+                       void* ws, size_t ws_bytes, rb_stream_t stream, void* dW_bf16) {
   DevInfo dv; if (int r = get_dev(dv)) return r;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (int r = check_common(U, W, M, N, d, dtype, mode)) return r;
   if (d > 128) return fail(RB_E_UNSUPPORTED, "CE backward supports d <= 128");
   if (!labels || !lse) return fail(RB_E_ARG, "null pointer");
   if (!ws) return fail(RB_E_WORKSPACE, "workspace required");
-  if (dbias && !dW) return fail(RB_E_ARG, "dbias is produced by the dW pass: pass dW too");
+  if (dbias && !dW && !dW_bf16) return fail(RB_E_ARG, "dbias is produced by the dW pass: pass dW too");
   Bump b(ws, ws_bytes);
   if (mode == RB_MODE_FP32X3)  // fp32 parity: exact fp32 passes (any sign of scale)
     return ce_bwd_f32(dv, static_cast<const float*>(U), static_cast<const float*>(W), bias, scale, labels, label_base, lse,
@@ -703,13 +761,14 @@ extern "C" int rb_ce_bwd(const void* U, const void* W, const float* bias, float 
                                                                label_base, N, grad_scale * scale, grad_scale_dev, (int)M, d, dU);
     RB_LAUNCH_CHECK("ce_du_finish_kernel");
   }
-  if (dW) {
+  if (dW || dW_bf16) {
     const long long m_pad = ((M + 127) / 128) * 128;
     float* lse2 = b.take<float>(m_pad);
     if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small");
     lse2_kernel<<<(int)((m_pad + 255) / 256), 256, 0, st>>>(lse, lse2, (int)M, (int)m_pad);
     RB_LAUNCH_CHECK("lse2_kernel");
-    return ce_bwd_dw_pair(dv, U, W, bias, scale, labels, label_base, lse2, grad_scale, grad_scale_dev, M, N, d, dW, dbias, b, st);
+    return ce_bwd_dw_pair(dv, U, W, bias, scale, labels, label_base, lse2, grad_scale, grad_scale_dev, M, N, d, dW, dbias, b, st,
+                          static_cast<__nv_bfloat16*>(dW_bf16));
   }
   return 0;
 }
@@ -860,6 +919,8 @@ extern "C" size_t rb_workspace_bytes(int op, int64_t M, int64_t N, int d, int K,
       n += ((M + 127) / 128) * 128 * 4 + 512;
       n += (pw.n_splits > 1 ? static_cast<size_t>(pw.n_splits) * N * (d + 1) * 4 : 0) + 1024;
       n += static_cast<size_t>(pw.n_stat_tiles) * 256 * 4 + 512;  // bias2
+      // rb_ce_bwd_dw_bf16: slot map + side table (one split) or an fp32 staging copy of dW (several splits)
+      n += (pw.n_splits > 1 ? static_cast<size_t>(N) * d * 4 : static_cast<size_t>(N) * 4 + static_cast<size_t>(M) * (d * 4 + 12)) + 2048;
       n += scatter_ws_bytes(M, d) + 512;
       return n;
     }

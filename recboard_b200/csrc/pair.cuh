@@ -59,6 +59,12 @@ struct PairArgs {
   float* rowsum_out;         // [n_splits][n_stat] sum over streamed rows of P (dbias), nullable
   // both
   float* acc_out;    // [n_splits][n_stat][d]
+  // PASS_DW with a bf16 gradient (n_splits == 1): rows are stored as bf16 here instead of fp32 in acc_out;
+  // rows that still get an exact fp32 one-hot correction (slot_of_row[row] >= 0) are ALSO stored in fp32
+  // at side[slot][d], where the correction is applied before they are rounded.
+  void* out_bf16;              // [n_stat][d] bf16, nullable
+  const int* slot_of_row;      // [n_stat]
+  float* side;                 // [n_slots][d]
 };
 
 template <int PASS_, int KC_, int NS_, bool BIAS_>
@@ -425,12 +431,39 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
       float osc = 1.f;
       if (C::PASS == PASS_DW) osc = a.gscale * (a.gscale_dev != nullptr ? __ldg(a.gscale_dev) : 1.f);
       float* o = a.acc_out + (static_cast<long long>(split) * a.n_stat + srow) * a.d;
+      const bool bf16_out = (C::PASS == PASS_DW) && a.out_bf16 != nullptr;   // kernel-uniform
+      uint32_t* ob = nullptr;   // bf16 row as packed pairs
+      if (bf16_out) {
+        ob = reinterpret_cast<uint32_t*>(a.out_bf16) + (static_cast<long long>(srow) * a.d >> 1);
+        const int slot = srow_ok ? __ldg(a.slot_of_row + srow) : -1;
+        o = (slot >= 0) ? a.side + static_cast<long long>(slot) * a.d : nullptr;
+      }
 #pragma unroll 1
       for (int ch = 0; ch < C::DPAD / 32; ++ch) {
         uint32_t v[32];
         tmem_ld32(t_acc + ch * 32, v);
         tmem_ld_wait();
-        if (srow_ok) {
+        if (bf16_out) {
+          if (srow_ok) {
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+              const int col = ch * 32 + c8 * 8;
+              if (col < a.d) {  // d % 8 == 0 (checked on the host)
+                float w[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) w[e] = __uint_as_float(v[c8 * 8 + e]) * osc;
+                uint4 pk;
+                pk.x = pack_bf16x2(w[0], w[1]); pk.y = pack_bf16x2(w[2], w[3]);
+                pk.z = pack_bf16x2(w[4], w[5]); pk.w = pack_bf16x2(w[6], w[7]);
+                *reinterpret_cast<uint4*>(ob + (col >> 1)) = pk;
+                if (o != nullptr) {
+                  *reinterpret_cast<float4*>(o + col) = make_float4(w[0], w[1], w[2], w[3]);
+                  *reinterpret_cast<float4*>(o + col + 4) = make_float4(w[4], w[5], w[6], w[7]);
+                }
+              }
+            }
+          }
+        } else if (srow_ok) {
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
             const int col = ch * 32 + c4 * 4;

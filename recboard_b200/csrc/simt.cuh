@@ -517,6 +517,55 @@ scatter_split_runs_kernel(const uint32_t* __restrict__ keys, float* __restrict__
   if (cnt_out != nullptr && lane == 0) cnt_out[key] += cnt_alpha * adev * static_cast<float>(run_len);
 }
 
+// ----------------------------------------------------- bf16 dW: label rows through a side table
+// slot_of_row[label_i - base] = i for every query row whose label lies in this shard (any winner among
+// duplicates: the slot only says where the row's fp32 copy lives)
+__global__ void dw_slot_assign_kernel(const int64_t* __restrict__ labels, long long base, long long n_items, int m,
+                                      int* __restrict__ slot_of_row) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const long long l = labels[i] - base;
+  if (l >= 0 && l < n_items) slot_of_row[l] = i;
+}
+// slot_idx[i] = slot of query row i's label (or -1): the keys of the sorted one-hot correction on the side table
+__global__ void dw_slot_index_kernel(const int64_t* __restrict__ labels, long long base, long long n_items, int m,
+                                     const int* __restrict__ slot_of_row, int64_t* __restrict__ slot_idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const long long l = labels[i] - base;
+  slot_idx[i] = (l >= 0 && l < n_items) ? slot_of_row[l] : -1;
+}
+// corrected fp32 rows -> bf16 gradient rows (one warp per slot owner), dbias[label] += the slot's count term
+__global__ void dw_side_finish_kernel(const int64_t* __restrict__ labels, long long base, long long n_items, int m, int d,
+                                      const int* __restrict__ slot_of_row, const float* __restrict__ side,
+                                      const float* __restrict__ cnt_side, __nv_bfloat16* __restrict__ dW,
+                                      float* __restrict__ dbias) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= m) return;
+  const long long l = labels[i] - base;
+  if (l < 0 || l >= n_items || slot_of_row[l] != i) return;   // not the owner of this label's slot
+  for (int c = lane * 4; c < d; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(side + static_cast<long long>(i) * d + c);
+    uint2 pk;
+    pk.x = pack_bf16x2(v.x, v.y);
+    pk.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(dW + l * d + c) = pk;
+  }
+  if (dbias != nullptr && lane == 0) dbias[l] += cnt_side[i];
+}
+// fp32 (n) -> bf16
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
+  for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    const float4 v = *reinterpret_cast<const float4*>(x + i);   // n % 8 == 0
+    uint2 pk;
+    pk.x = pack_bf16x2(v.x, v.y);
+    pk.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(y + i) = pk;
+  }
+}
+
 // ------------------------------------------------------------------- operand preparation
 // labels (int64, global) -> int32 local (label - base) or -1 when outside [0, n_items)
 __global__ void labels_local_kernel(const int64_t* __restrict__ labels, long long base, long long n_items,

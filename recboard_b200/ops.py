@@ -303,9 +303,12 @@ def ce_du_finish(du_unnorm, row_max, lse, W, labels, grad_scale: float, scale: f
 
 def ce_backward(U, W, labels, lse, grad_scale: float, bias=None, scale: float = 1.0, label_base: int = 0,
                 need_dU: bool = True, need_dW: bool = True, need_dbias: bool = False,
-                precision: Optional[str] = None, grad_scale_dev: Optional[torch.Tensor] = None):
+                precision: Optional[str] = None, grad_scale_dev: Optional[torch.Tensor] = None,
+                dw_dtype: Optional[torch.dtype] = None):
     """Gradients of ``g * sum_i (lse_i - S_i,label_i)`` -> (dU, dW, dbias) fp32, with
-    ``g = grad_scale * grad_scale_dev`` (the latter an optional fp32 device scalar)."""
+    ``g = grad_scale * grad_scale_dev`` (the latter an optional fp32 device scalar).
+    ``dw_dtype=torch.bfloat16`` (bf16 mode) makes the pass store dW in bf16 itself -- the correctly rounded
+    fp32 result, without the fp32 (N,d) matrix and the cast pass a bf16 parameter would otherwise need."""
     dev = L.require_cuda(U, W, labels, lse, bias, grad_scale_dev)
     if grad_scale_dev is not None and (grad_scale_dev.dtype != torch.float32 or grad_scale_dev.numel() != 1):
         raise TypeError("grad_scale_dev must be a float32 scalar tensor")
@@ -314,9 +317,25 @@ def ce_backward(U, W, labels, lse, grad_scale: float, bias=None, scale: float = 
     N = Wc.shape[0]
     b = None if bias is None else bias.detach().float().contiguous()
     dU = torch.empty(M, d, dtype=torch.float32, device=dev) if need_dU else None
-    dW = torch.empty(N, d, dtype=torch.float32, device=dev) if (need_dW or need_dbias) else None
     db = torch.empty(N, dtype=torch.float32, device=dev) if need_dbias else None
     ws, n = _ws(dev, L.OP_CE_BWD, M, N, d, mode=mode)
+    if need_dW and dw_dtype == torch.bfloat16 and mode == L.MODE_BF16:
+        if need_dU:   # dU alone through the generic entry, dW (+ dbias) through the bf16-output pass
+            L.check(
+                L.lib().rb_ce_bwd(L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(labels.contiguous()), label_base,
+                                  L.ptr(lse.float().contiguous()), float(grad_scale), L.ptr(grad_scale_dev), M, N, d,
+                                  L.dtype_code(Uc), mode, L.ptr(dU), None, None, L.ptr(ws), n, L.stream_ptr(dev)),
+                "rb_ce_bwd",
+            )
+        dWb = torch.empty(N, d, dtype=torch.bfloat16, device=dev)
+        L.check(
+            L.lib().rb_ce_bwd_dw_bf16(L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(labels.contiguous()), label_base,
+                                      L.ptr(lse.float().contiguous()), float(grad_scale), L.ptr(grad_scale_dev), M, N, d,
+                                      L.ptr(dWb), L.ptr(db), L.ptr(ws), n, L.stream_ptr(dev)),
+            "rb_ce_bwd_dw_bf16",
+        )
+        return dU, dWb, db
+    dW = torch.empty(N, d, dtype=torch.float32, device=dev) if (need_dW or need_dbias) else None
     L.check(
         L.lib().rb_ce_bwd(L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(labels.contiguous()), label_base,
                           L.ptr(lse.float().contiguous()), float(grad_scale), L.ptr(grad_scale_dev), M, N, d,
@@ -365,10 +384,10 @@ class _FusedCE(torch.autograd.Function):
             dU = ce_du_finish(du_un, row_max, lse, W, labels, g, ctx.scale, 0, gdev)
             if need[1] or need_db:
                 _, dW, db = ce_backward(U, W, labels, lse, g, bias, ctx.scale, 0, False, need[1], need_db,
-                                        ctx.precision, grad_scale_dev=gdev)
+                                        ctx.precision, grad_scale_dev=gdev, dw_dtype=W.dtype)
         else:
             dU, dW, db = ce_backward(U, W, labels, lse, g, bias, ctx.scale, 0, need[0], need[1], need_db,
-                                     ctx.precision, grad_scale_dev=gdev)
+                                     ctx.precision, grad_scale_dev=gdev, dw_dtype=W.dtype)
         return (
             dU.to(U.dtype) if dU is not None else None,
             dW.to(W.dtype) if dW is not None else None,

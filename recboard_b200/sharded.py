@@ -87,10 +87,11 @@ class _ShardedCE(torch.autograd.Function):
             dU = ops.ce_du_finish(du_un, row_max, lse, W_shard, labels, g, ctx.scale, ctx.row_start, gdev)
             if need[1] or need_db:
                 _, dW, db = ops.ce_backward(U, W_shard, labels, lse, g, bias, ctx.scale, ctx.row_start, False,
-                                            need[1], need_db, ctx.precision, grad_scale_dev=gdev)
+                                            need[1], need_db, ctx.precision, grad_scale_dev=gdev, dw_dtype=W_shard.dtype)
         else:
             dU, dW, db = ops.ce_backward(U, W_shard, labels, lse, g, bias, ctx.scale, ctx.row_start,
-                                         need[0], need[1], need_db, ctx.precision, grad_scale_dev=gdev)
+                                         need[0], need[1], need_db, ctx.precision, grad_scale_dev=gdev,
+                                         dw_dtype=W_shard.dtype)
         if dU is not None:
             dist.all_reduce(dU, op=dist.ReduceOp.SUM, group=ctx.group)
         return (dU.to(U.dtype) if dU is not None else None, dW.to(W_shard.dtype) if dW is not None else None, None,

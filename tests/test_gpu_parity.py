@@ -231,6 +231,28 @@ def test_golden_ce_fp32_gradients(ops, golden):
     assert_rel(bd.grad, f["dbias"], FP32_RTOL, "bert4rec dbias")
 
 
+@pytest.mark.parametrize("M,N,d,with_bias", [(300, 1000, 64, True), (513, 40_000, 128, False), (2000, 70_000, 128, True)])
+def test_ce_dw_bf16_output_is_the_rounded_fp32_gradient(ops, M, N, d, with_bias):
+    """rb_ce_bwd_dw_bf16 (one split: direct bf16 rows + fp32 side table for label rows; several splits: fp32
+    staging) must equal the fp32 gradient of rb_ce_bwd rounded to bf16, bit for bit; dbias to the last ulp."""
+    g = torch.Generator().manual_seed(M + N)
+    U = dev((torch.randn(M, d, generator=g) * 1.5 / d ** 0.25).bfloat16())
+    W = dev((torch.randn(N, d, generator=g) * 1.5 / d ** 0.25).bfloat16())
+    b = dev(torch.randn(N, generator=g) * 0.3) if with_bias else None
+    lab = torch.randint(0, N, (M,), generator=g)
+    lab[: M // 8] = 7        # hot label
+    lab = dev(lab)
+    m, l, ll = ops.ce_rowstats(U, W, lab, bias=b)
+    lse = m + torch.log(l)
+    _, dW32, db32 = ops.ce_backward(U, W, lab, lse, 1.0 / M, bias=b, need_dU=False, need_dW=True, need_dbias=with_bias)
+    _, dWb, dbb = ops.ce_backward(U, W, lab, lse, 1.0 / M, bias=b, need_dU=False, need_dW=True, need_dbias=with_bias,
+                                  dw_dtype=torch.bfloat16)
+    assert dWb.dtype == torch.bfloat16
+    assert torch.equal(dWb, dW32.bfloat16())
+    if with_bias:   # the count term is folded in by one FMA in one path and by multiply + add in the other: 1 ulp
+        assert torch.allclose(dbb, db32, rtol=1e-6, atol=1e-9)
+
+
 def _seen_lists(g, B, N, max_len):
     return [torch.randperm(N, generator=g)[: int(torch.randint(0, max_len + 1, (1,), generator=g))].tolist() for _ in range(B)]
 
