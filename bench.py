@@ -39,8 +39,8 @@ SEQ = 50
 TOPK = 50
 METRIC = "full-catalog scored user-item pairs/sec (CE train + top-K eval)"
 # dram__bytes_read.sum + dram__bytes_write.sum of one pair_kernel<PASS_DW> launch at this workload (ncu --set full)
-PROFILED_TRAFFIC_BYTES = 257_902_592 + 458_749_440
-PROFILED_TRAFFIC_SOURCE = "profiles/r1m_ncu_summary.md (ncu --set full, one launch, N=1M shard)"
+PROFILED_TRAFFIC_BYTES = 262_347_520 + 206_989_568
+PROFILED_TRAFFIC_SOURCE = "profiles/r1o_ncu_summary.md (ncu --set full, one launch, N=1M shard)"
 UNIT = "pairs/s"
 
 
@@ -344,7 +344,8 @@ def run_ours(args):
             lse = m_ + torch.log(l_)
             t_stats = time_op(lambda: ops.ce_rowstats(U_train, Wd, labels, label_base=row_start))
             t_fwd = time_op(lambda: ops.ce_rowstats(U_train, Wd, labels, label_base=row_start, want_dU=True))
-            t_dW = time_op(lambda: ops.ce_backward(U_train, Wd, labels, lse, 1.0 / ROWS, label_base=row_start, need_dU=False, need_dW=True))
+            t_dW = time_op(lambda: ops.ce_backward(U_train, Wd, labels, lse, 1.0 / ROWS, label_base=row_start, need_dU=False,
+                                                   need_dW=True, dw_dtype=torch.bfloat16))   # what the step runs: bf16 gradient rows
             t_topk = time_op(lambda: ops.topk_eval(U_eval, Wd, TOPK, seen_crow, seen_col, id_base=row_start))
             t_gather = time_op(lambda: ops.gather_rows_raw(table, seqs))
             t_scatter = time_op(lambda: ops.scatter_add_rows_(table_grad, gather_grad, seqs.view(-1), padding_idx=0))
@@ -374,7 +375,7 @@ def run_ours(args):
                     "traffic": PROFILED_TRAFFIC_BYTES, "kernel": "pair_kernel<PASS_DW> (dW = (softmax - onehot)^T U)",
                     "executed_tflops": 2 * ach,
                     "traffic_source": PROFILED_TRAFFIC_SOURCE,
-                    "algorithmic_bytes": n_shard * D * 2 + n_shard * D * 4 + ROWS * D * 2,
+                    "algorithmic_bytes": n_shard * D * 2 + n_shard * D * 2 + ROWS * D * 2,   # W in, bf16 dW out, U
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.59 PFLOP/s"}
 
     cpu_baseline = None

@@ -25,7 +25,7 @@ if "fwd" in which:
 if "dU" in which:
     ops.ce_backward(U, W, labels, lse, 1.0 / M, need_dU=True, need_dW=False)
 if "dW" in which:
-    ops.ce_backward(U, W, labels, lse, 1.0 / M, need_dU=False, need_dW=True)
+    ops.ce_backward(U, W, labels, lse, 1.0 / M, need_dU=False, need_dW=True, dw_dtype=torch.bfloat16)   # as in the bench step
 if "topk" in which:
     ops.topk_eval(U, W, K, crow, col)
 torch.cuda.synchronize()
