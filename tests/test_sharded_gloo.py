@@ -59,3 +59,91 @@ def test_two_rank_merges_match_unsharded():
     for rank, loss, mv, mi in outs:
         assert abs(loss - float(ref_loss)) < 1e-5
         assert torch.equal(mi, ri) and torch.equal(mv, rv)
+
+
+# ---- the autograd plumbing of sharded.py (all-gather of stats, all-reduce of dU, local dW / dbias shard,
+#      all-gather + merge of top-K) with oracle stand-ins for the per-shard kernels
+def _install_oracle_ops():
+    from recboard_b200 import ops
+
+    def ce_rowstats(U, W, labels, bias=None, scale=1.0, label_base=0, precision=None, want_dU=False):
+        S = orc.score_dense(U, W, bias, scale)
+        m = S.max(1).values
+        l = torch.exp(S - m[:, None]).sum(1)
+        loc = labels - label_base
+        inside = (loc >= 0) & (loc < W.shape[0])
+        ll = torch.where(inside, S.gather(1, loc.clamp(0, W.shape[0] - 1)[:, None]).squeeze(1), torch.zeros_like(m))
+        return m, l, ll
+
+    def ce_backward(U, W, labels, lse, grad_scale, bias=None, scale=1.0, label_base=0, need_dU=True, need_dW=True,
+                    need_dbias=False, precision=None, grad_scale_dev=None, dw_dtype=None):
+        S = orc.score_dense(U, W, bias, scale)
+        G = torch.exp(S - lse[:, None])
+        loc = labels - label_base
+        inside = (loc >= 0) & (loc < W.shape[0])
+        G[torch.arange(len(U))[inside], loc[inside]] -= 1.0
+        G = G * grad_scale * (float(grad_scale_dev) if grad_scale_dev is not None else 1.0)
+        return (scale * G @ W.float() if need_dU else None, scale * G.T @ U.float() if need_dW else None,
+                G.sum(0) if need_dbias else None)
+
+    def topk_eval(U, W, K, seen_crow=None, seen_col=None, bias=None, scale=1.0, id_base=0, precision=None):
+        S = orc.score_dense(U, W, bias, scale)
+        if seen_crow is not None:
+            rows = torch.repeat_interleave(torch.arange(len(U)), seen_crow[1:] - seen_crow[:-1])
+            loc = seen_col - id_base
+            ok = (loc >= 0) & (loc < W.shape[0])
+            S[rows[ok], loc[ok]] = orc.MASK_VALUE
+        v, i = orc.topk_sorted(S, K)
+        return v, (i + id_base).int()
+
+    ops.fused_du_supported = lambda U, precision, scale: False
+    ops.ce_rowstats, ops.ce_backward, ops.topk_eval = ce_rowstats, ce_backward, topk_eval
+    ops.topk_merge = lambda av, ai: orc.merge_topk([(av[r], ai[r]) for r in range(av.shape[0])], av.shape[2])
+
+
+def _inputs():
+    g = torch.Generator().manual_seed(12)
+    M, N, d, K = 20, 203, 16, 9
+    U, W = torch.randn(M, d, generator=g), torch.randn(N, d, generator=g)
+    bias = torch.randn(N, generator=g) * 0.3
+    labels = torch.randint(0, N, (M,), generator=g)
+    seen = [torch.randperm(N, generator=g)[:5].tolist() for _ in range(M)]
+    return M, N, d, K, U, W, bias, labels, seen
+
+
+def _autograd_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    _install_oracle_ops()
+    M, N, d, K, U, W, bias, labels, seen = _inputs()
+    a, b = sharded.shard_bounds(N, world, rank)
+    Us, Ws, bs = U.clone().requires_grad_(True), W[a:b].clone().requires_grad_(True), bias[a:b].clone().requires_grad_(True)
+    loss = sharded.sharded_fused_ce(Us, Ws, labels, a, bias_shard=bs, scale=0.8)
+    (loss * 3.0).backward()
+    crow, col = orc.lists_to_csr(seen)
+    v, i = sharded.sharded_topk(U, W[a:b], K, a, crow, col, bias_shard=bias[a:b], scale=0.8)
+    q.put((rank, a, b, float(loss), Us.grad, Ws.grad, bs.grad, v, i))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_autograd_and_topk():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_autograd_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    M, N, d, K, U, W, bias, labels, seen = _inputs()
+    ref_loss, rdU, rdW, rdb = orc.ce_fwd_bwd(U, W, labels, bias, scale=0.8, grad_out=3.0)
+    crow, col = orc.lists_to_csr(seen)
+    rv, ri = orc.topk_sorted(orc.mask_seen(orc.score_dense(U, W, bias, 0.8), crow, col), K)
+    for rank, a, b, loss, dU, dW, db, v, i in outs:
+        assert abs(loss - float(ref_loss)) < 1e-5
+        assert torch.allclose(dU, rdU, rtol=1e-4, atol=1e-6)          # the all-reduced full gradient on every rank
+        assert torch.allclose(dW, rdW[a:b], rtol=1e-4, atol=1e-6)     # the local shard, never communicated
+        assert torch.allclose(db, rdb[a:b], rtol=1e-4, atol=1e-6)
+        assert torch.equal(i.long(), ri) and torch.allclose(v, rv)
