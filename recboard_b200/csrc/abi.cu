@@ -557,24 +557,22 @@ static int ce_bwd_dw_pair(const DevInfo& dv, const void* U, const void* W, const
                           cudaStream_t st, __nv_bfloat16* dW_bf16 = nullptr) {
   Plan p = make_plan(N, M, dv.sms, 64, 8, 256);
   const long long n_pad = 1ll * p.n_stat_tiles * 256;
-  // bf16 gradient requested: with one split the kernel stores bf16 rows directly (label rows also in fp32 in a
-  // side table, corrected there, then rounded); with several splits the fp32 path runs in the workspace and
-  // is rounded at the end.
-  const bool direct_bf16 = dW_bf16 != nullptr && p.n_splits == 1;
+  // One-hot correction: up to LABEL_FIX_MAX query rows without a sort (label_owner + label_fix), beyond that
+  // through the sorted scatter.  bf16 gradient requested: with one split and the sort-free correction the
+  // kernel stores bf16 rows directly (label rows also in fp32 in a side table, corrected there, then rounded);
+  // otherwise the fp32 path runs in the workspace and is rounded at the end.
+  constexpr long long LABEL_FIX_MAX = 16384;
+  const bool small_fix = M <= LABEL_FIX_MAX;
+  const bool direct_bf16 = dW_bf16 != nullptr && p.n_splits == 1 && small_fix;
   if (dW_bf16 != nullptr && !direct_bf16) dW = b.take<float>(static_cast<size_t>(N) * d);
-  int* slot_of_row = nullptr; int64_t* slot_idx = nullptr; float* side = nullptr; float* cnt_side = nullptr;
-  if (direct_bf16) {
-    slot_of_row = b.take<int>(N);
-    slot_idx = b.take<int64_t>(M);
-    side = b.take<float>(static_cast<size_t>(M) * d);
-    cnt_side = b.take<float>(M);
+  int* first_of = nullptr; float* side = nullptr;
+  if (small_fix) {
+    first_of = b.take<int>(N);
+    if (direct_bf16) side = b.take<float>(static_cast<size_t>(M) * d);
     if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
-    RB_CUDA(cudaMemsetAsync(slot_of_row, 0xFF, static_cast<size_t>(N) * 4, st));
-    RB_CUDA(cudaMemsetAsync(cnt_side, 0, static_cast<size_t>(M) * 4, st));
-    dw_slot_assign_kernel<<<(int)((M + 255) / 256), 256, 0, st>>>(labels, label_base, N, (int)M, slot_of_row);
-    RB_LAUNCH_CHECK("dw_slot_assign_kernel");
-    dw_slot_index_kernel<<<(int)((M + 255) / 256), 256, 0, st>>>(labels, label_base, N, (int)M, slot_of_row, slot_idx);
-    RB_LAUNCH_CHECK("dw_slot_index_kernel");
+    RB_CUDA(cudaMemsetAsync(first_of, 0x7F, static_cast<size_t>(N) * 4, st));
+    label_owner_kernel<<<(int)((M + 255) / 256), 256, 0, st>>>(labels, label_base, N, (int)M, first_of);
+    RB_LAUNCH_CHECK("label_owner_kernel");
   }
   float* part = (p.n_splits > 1) ? b.take<float>(static_cast<size_t>(p.n_splits) * N * d) : dW;
   float* rs_part = nullptr;
@@ -593,7 +591,7 @@ static int ce_bwd_dw_pair(const DevInfo& dv, const void* U, const void* W, const
   a.n_stat = (int)N; a.n_strm = (int)M; a.n_pair_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
   a.n_splits = p.n_splits; a.d = d; a.stat_pad = (int)n_pad; a.scale = scale; a.bias2_stat = bias2; a.aux = lse2;
   a.gscale = grad_scale * scale; a.rscale = grad_scale; a.gscale_dev = grad_scale_dev; a.acc_out = part; a.rowsum_out = rs_part;
-  if (direct_bf16) { a.out_bf16 = dW_bf16; a.slot_of_row = slot_of_row; a.side = side; }
+  if (direct_bf16) { a.out_bf16 = dW_bf16; a.slot_of_row = first_of; a.side = side; }
   if (int r = launch_pair<PASS_DW>(kc_for(d, RB_MODE_BF16), bias_cfg, ts, ty, a, p.grid, st)) return r;
   if (p.n_splits > 1) {
     const long long n = N * d;
@@ -604,19 +602,24 @@ static int ce_bwd_dw_pair(const DevInfo& dv, const void* U, const void* W, const
       RB_LAUNCH_CHECK("partial_sum_kernel");
     }
   }
-  void* sws = b.take<char>(scatter_ws_bytes(M, d));
-  if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
+  const __nv_bfloat16* Ub = static_cast<const __nv_bfloat16*>(U);
+  const int fix_grid = (int)((M * 32 + 255) / 256);
   if (direct_bf16) {
-    // one-hot correction on the side table (keys = slots), then the corrected rows are rounded into dW
-    if (int r = scatter_add_impl(U, slot_idx, 0, side, M, M, d, RB_DTYPE_BF16, -1, -grad_scale * scale, grad_scale_dev,
-                                 dbias ? cnt_side : nullptr, -grad_scale, sws, scatter_ws_bytes(M, d), st)) return r;
-    dw_side_finish_kernel<<<(int)((M * 32 + 255) / 256), 256, 0, st>>>(labels, label_base, N, (int)M, d, slot_of_row, side,
-                                                                        cnt_side, dW_bf16, dbias);
-    RB_LAUNCH_CHECK("dw_side_finish_kernel");
+    label_fix_kernel<__nv_bfloat16, true><<<fix_grid, 256, 0, st>>>(labels, label_base, N, (int)M, d, first_of, Ub, grad_scale * scale,
+                                                                     grad_scale, grad_scale_dev, side, nullptr, dW_bf16, dbias);
+    RB_LAUNCH_CHECK("label_fix_kernel");
     return 0;
   }
-  if (int r = scatter_add_impl(U, labels, label_base, dW, M, N, d, RB_DTYPE_BF16, -1, -grad_scale * scale, grad_scale_dev,
-                               dbias, -grad_scale, sws, scatter_ws_bytes(M, d), st)) return r;
+  if (small_fix) {
+    label_fix_kernel<__nv_bfloat16, false><<<fix_grid, 256, 0, st>>>(labels, label_base, N, (int)M, d, first_of, Ub, grad_scale * scale,
+                                                                      grad_scale, grad_scale_dev, nullptr, dW, nullptr, dbias);
+    RB_LAUNCH_CHECK("label_fix_kernel");
+  } else {
+    void* sws = b.take<char>(scatter_ws_bytes(M, d));
+    if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
+    if (int r = scatter_add_impl(U, labels, label_base, dW, M, N, d, RB_DTYPE_BF16, -1, -grad_scale * scale, grad_scale_dev,
+                                 dbias, -grad_scale, sws, scatter_ws_bytes(M, d), st)) return r;
+  }
   if (dW_bf16 != nullptr) {
     const long long n = N * d;
     cast_f32_bf16_kernel<<<(int)std::min<long long>((n / 4 + 255) / 256, dv.sms * 16), 256, 0, st>>>(dW, dW_bf16, n);
@@ -701,7 +704,19 @@ static int ce_bwd_f32(const DevInfo& dv, const float* U, const float* W, const f
         RB_LAUNCH_CHECK("partial_sum_kernel");
       }
     }
-    // exact one-hot correction: dW[label_i] -= g*scale*u_i, dbias[label_i] -= g   (sorted => deterministic)
+    // exact one-hot correction: dW[label_i] -= g*scale*u_i, dbias[label_i] -= g   (index order => deterministic)
+    if (M <= 16384) {
+      int* first_of = b.take<int>(N);
+      if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
+      RB_CUDA(cudaMemsetAsync(first_of, 0x7F, static_cast<size_t>(N) * 4, st));
+      label_owner_kernel<<<(int)((M + 255) / 256), 256, 0, st>>>(labels, label_base, N, (int)M, first_of);
+      RB_LAUNCH_CHECK("label_owner_kernel");
+      label_fix_kernel<float, false><<<(int)((M * 32 + 255) / 256), 256, 0, st>>>(labels, label_base, N, (int)M, d, first_of, U,
+                                                                                   grad_scale * scale, grad_scale, grad_scale_dev,
+                                                                                   nullptr, dW, nullptr, dbias);
+      RB_LAUNCH_CHECK("label_fix_kernel");
+      return 0;
+    }
     return scatter_add_impl(U, labels, label_base, dW, M, N, d, RB_DTYPE_F32, -1, -grad_scale * scale, grad_scale_dev,
                             dbias, -grad_scale, sws, scatter_ws_bytes(M, d), st);
   }
@@ -913,14 +928,15 @@ extern "C" size_t rb_workspace_bytes(int op, int64_t M, int64_t N, int d, int K,
       return need + std::max(stats, pair_fwd_ws(M, N, d, sms));
     }
     case RB_OP_CE_BWD: {
-      if (mode == RB_MODE_FP32X3) return need + f32grad_ws(M, N, d, sms) + scatter_ws_bytes(M, d) + 1024;
+      if (mode == RB_MODE_FP32X3) return need + f32grad_ws(M, N, d, sms) + scatter_ws_bytes(M, d) + static_cast<size_t>(N) * 4 + 2048;
       size_t n = need + static_cast<size_t>(M) * (d + 3) * 4 + 2048 + pair_fwd_ws(M, N, d, sms);  // dU by recompute
       Plan pw = make_plan(N, M, sms, 64, 8, 256);
       n += ((M + 127) / 128) * 128 * 4 + 512;
       n += (pw.n_splits > 1 ? static_cast<size_t>(pw.n_splits) * N * (d + 1) * 4 : 0) + 1024;
       n += static_cast<size_t>(pw.n_stat_tiles) * 256 * 4 + 512;  // bias2
       // rb_ce_bwd_dw_bf16: slot map + side table (one split) or an fp32 staging copy of dW (several splits)
-      n += (pw.n_splits > 1 ? static_cast<size_t>(N) * d * 4 : static_cast<size_t>(N) * 4 + static_cast<size_t>(M) * (d * 4 + 12)) + 2048;
+      n += static_cast<size_t>(N) * 4 + static_cast<size_t>(M) * (d * 4 + 12) + 2048;   // label owners + side table
+      if (pw.n_splits > 1 || M > 16384) n += static_cast<size_t>(N) * d * 4 + 512;        // fp32 staging copy of dW
       n += scatter_ws_bytes(M, d) + 512;
       return n;
     }

@@ -60,8 +60,8 @@ struct PairArgs {
   // both
   float* acc_out;    // [n_splits][n_stat][d]
   // PASS_DW with a bf16 gradient (n_splits == 1): rows are stored as bf16 here instead of fp32 in acc_out;
-  // rows that still get an exact fp32 one-hot correction (slot_of_row[row] >= 0) are ALSO stored in fp32
-  // at side[slot][d], where the correction is applied before they are rounded.
+  // rows that still get an exact fp32 one-hot correction (slot_of_row[row] < n_strm: the first query row with
+  // that label) are ALSO stored in fp32 at side[slot][d], where the correction is applied before rounding.
   void* out_bf16;              // [n_stat][d] bf16, nullable
   const int* slot_of_row;      // [n_stat]
   float* side;                 // [n_slots][d]
@@ -435,8 +435,8 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
       uint32_t* ob = nullptr;   // bf16 row as packed pairs
       if (bf16_out) {
         ob = reinterpret_cast<uint32_t*>(a.out_bf16) + (static_cast<long long>(srow) * a.d >> 1);
-        const int slot = srow_ok ? __ldg(a.slot_of_row + srow) : -1;
-        o = (slot >= 0) ? a.side + static_cast<long long>(slot) * a.d : nullptr;
+        const int slot = srow_ok ? __ldg(a.slot_of_row + srow) : 0x7F7F7F7F;   // owner query row of this label, if any
+        o = (slot < a.n_strm) ? a.side + static_cast<long long>(slot) * a.d : nullptr;
       }
 #pragma unroll 1
       for (int ch = 0; ch < C::DPAD / 32; ++ch) {

@@ -517,43 +517,78 @@ scatter_split_runs_kernel(const uint32_t* __restrict__ keys, float* __restrict__
   if (cnt_out != nullptr && lane == 0) cnt_out[key] += cnt_alpha * adev * static_cast<float>(run_len);
 }
 
-// ----------------------------------------------------- bf16 dW: label rows through a side table
-// slot_of_row[label_i - base] = i for every query row whose label lies in this shard (any winner among
-// duplicates: the slot only says where the row's fp32 copy lives)
-__global__ void dw_slot_assign_kernel(const int64_t* __restrict__ labels, long long base, long long n_items, int m,
-                                      int* __restrict__ slot_of_row) {
+__device__ __forceinline__ float4 load4_as_float(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4_as_float(const __nv_bfloat16* p) {
+  const uint2 raw = *reinterpret_cast<const uint2*>(p);
+  return make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xFFFF0000u),
+                     __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xFFFF0000u));
+}
+
+// ------------------------------------------------ exact one-hot correction of dW (small M: no sort)
+// dW[label_i] -= g*scale*u_i, dbias[label_i] -= g, summed over the query rows that share a label in index
+// order (deterministic).  For the few thousand query rows of a training step a sort is overkill: the first
+// query row with a given label owns it (atomicMin), and its warp scans the label vector once for the others.
+//   first_of[l] = smallest i with label_i - base == l   (memset to 0x7F7F7F7F before)
+__global__ void label_owner_kernel(const int64_t* __restrict__ labels, long long base, long long n_items, int m,
+                                   int* __restrict__ first_of) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const long long l = labels[i] - base;
-  if (l >= 0 && l < n_items) slot_of_row[l] = i;
+  if (l >= 0 && l < n_items) atomicMin(first_of + l, i);
 }
-// slot_idx[i] = slot of query row i's label (or -1): the keys of the sorted one-hot correction on the side table
-__global__ void dw_slot_index_kernel(const int64_t* __restrict__ labels, long long base, long long n_items, int m,
-                                     const int* __restrict__ slot_of_row, int64_t* __restrict__ slot_idx) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  const long long l = labels[i] - base;
-  slot_idx[i] = (l >= 0 && l < n_items) ? slot_of_row[l] : -1;
-}
-// corrected fp32 rows -> bf16 gradient rows (one warp per slot owner), dbias[label] += the slot's count term
-__global__ void dw_side_finish_kernel(const int64_t* __restrict__ labels, long long base, long long n_items, int m, int d,
-                                      const int* __restrict__ slot_of_row, const float* __restrict__ side,
-                                      const float* __restrict__ cnt_side, __nv_bfloat16* __restrict__ dW,
-                                      float* __restrict__ dbias) {
+// One warp per query row; only owners work.  TU: storage type of U.  OUT_BF16: the row's fp32 value comes from
+// side[i] (written by the dW pass for rows with an owner) and is rounded into dW_bf16; otherwise dW (fp32) is
+// updated in place.
+template <typename TU, bool OUT_BF16>
+__global__ void label_fix_kernel(const int64_t* __restrict__ labels, long long base, long long n_items, int m, int d,
+                                 const int* __restrict__ first_of, const TU* __restrict__ U, float gs,
+                                 float g_bias, const float* __restrict__ g_dev, const float* __restrict__ side,
+                                 float* __restrict__ dW, __nv_bfloat16* __restrict__ dW_bf16, float* __restrict__ dbias) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (i >= m) return;
-  const long long l = labels[i] - base;
-  if (l < 0 || l >= n_items || slot_of_row[l] != i) return;   // not the owner of this label's slot
-  for (int c = lane * 4; c < d; c += 128) {
-    const float4 v = *reinterpret_cast<const float4*>(side + static_cast<long long>(i) * d + c);
-    uint2 pk;
-    pk.x = pack_bf16x2(v.x, v.y);
-    pk.y = pack_bf16x2(v.z, v.w);
-    *reinterpret_cast<uint2*>(dW + l * d + c) = pk;
+  const long long mine = labels[i];
+  const long long l = mine - base;
+  if (l < 0 || l >= n_items || first_of[l] != i) return;
+  const float gd = (g_dev != nullptr) ? __ldg(g_dev) : 1.f;
+  int count = 0;
+  for (int c0 = 0; c0 < d; c0 += 128) {
+    const int c = c0 + lane * 4;
+    const bool col_ok = c < d;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    count = 0;
+    for (int jb = i & ~31; jb < m; jb += 32) {   // matches can only sit at or after the owner
+      const int j = jb + lane;
+      uint32_t hit = __ballot_sync(0xffffffffu, j >= i && j < m && labels[j] == mine);
+      count += __popc(hit);
+      while (hit) {
+        const int jj = jb + __ffs(hit) - 1;
+        hit &= hit - 1;
+        if (col_ok) {
+          const float4 u = load4_as_float(U + static_cast<long long>(jj) * d + c);
+          acc.x += u.x; acc.y += u.y; acc.z += u.z; acc.w += u.w;
+        }
+      }
+    }
+    if (col_ok) {
+      const float al = -gs * gd;
+      if constexpr (OUT_BF16) {
+        const float4 v = *reinterpret_cast<const float4*>(side + static_cast<long long>(i) * d + c);
+        uint2 pk;
+        pk.x = pack_bf16x2(fmaf(al, acc.x, v.x), fmaf(al, acc.y, v.y));
+        pk.y = pack_bf16x2(fmaf(al, acc.z, v.z), fmaf(al, acc.w, v.w));
+        *reinterpret_cast<uint2*>(dW_bf16 + l * d + c) = pk;
+      } else {
+        float4* dst = reinterpret_cast<float4*>(dW + l * d + c);
+        float4 o = *dst;
+        o.x = fmaf(al, acc.x, o.x); o.y = fmaf(al, acc.y, o.y); o.z = fmaf(al, acc.z, o.z); o.w = fmaf(al, acc.w, o.w);
+        *dst = o;
+      }
+    }
   }
-  if (dbias != nullptr && lane == 0) dbias[l] += cnt_side[i];
+  if (dbias != nullptr && lane == 0) dbias[l] += -g_bias * gd * static_cast<float>(count);
 }
+
 // fp32 (n) -> bf16
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
@@ -620,12 +655,6 @@ __global__ void bias2_kernel(const float* __restrict__ bias, float* __restrict__
   if (i < n_pad) out[i] = (i < n && bias != nullptr) ? bias[i] * 1.4426950408889634f : 0.f;
 }
 
-__device__ __forceinline__ float4 load4_as_float(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ float4 load4_as_float(const __nv_bfloat16* p) {
-  const uint2 raw = *reinterpret_cast<const uint2*>(p);
-  return make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xFFFF0000u),
-                     __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xFFFF0000u));
-}
 
 // ---- finish of the fused CE forward (pair kernel, PASS_FWD): one warp per query row merges the
 // per-split partials (m2, l, A) and scores the label column exactly:

@@ -174,7 +174,8 @@ def test_scores_and_rowstats(ops, M, N, d, precision):
         assert_rel(ll, rll, rtol, "label logit")
 
 
-@pytest.mark.parametrize("M,N,d", [(1, 130, 64), (300, 1000, 64), (513, 4099, 128), (3013, 12101, 64)])
+@pytest.mark.parametrize("M,N,d", [(1, 130, 64), (300, 1000, 64), (513, 4099, 128), (3013, 12101, 64),
+                                   (17000, 700, 64)])   # > 16384 rows: one-hot correction through the sorted scatter
 def test_ce_gradients_bf16(ops, M, N, d):
     g = torch.Generator().manual_seed(M + N + d)
     U = bf16_round(torch.randn(M, d, generator=g) * 1.5 / d ** 0.25)
@@ -231,7 +232,8 @@ def test_golden_ce_fp32_gradients(ops, golden):
     assert_rel(bd.grad, f["dbias"], FP32_RTOL, "bert4rec dbias")
 
 
-@pytest.mark.parametrize("M,N,d,with_bias", [(300, 1000, 64, True), (513, 40_000, 128, False), (2000, 70_000, 128, True)])
+@pytest.mark.parametrize("M,N,d,with_bias", [(300, 1000, 64, True), (513, 40_000, 128, False), (2000, 70_000, 128, True),
+                                             (17000, 50_000, 64, True)])
 def test_ce_dw_bf16_output_is_the_rounded_fp32_gradient(ops, M, N, d, with_bias):
     """rb_ce_bwd_dw_bf16 (one split: direct bf16 rows + fp32 side table for label rows; several splits: fp32
     staging) must equal the fp32 gradient of rb_ce_bwd rounded to bf16, bit for bit; dbias to the last ulp."""
