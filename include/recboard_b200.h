@@ -123,7 +123,7 @@ int rb_ce_du_finish(const float* dU_unnorm, const float* row_max, const float* l
  *               rb_ce_fwd produced dU_unnorm -- rb_ce_du_finish is then all that is needed; otherwise
  *               the forward sweep is re-run here)
  * Recomputes S tile by tile; the softmax tile lives only in TMEM; the one-hot is applied exactly in
- * fp32 by a sorted (deterministic) row update.  Replaces the autograd of SASRec/main.py:217-219 run
+ * fp32 by an index-ordered (deterministic) row update.  Replaces the autograd of SASRec/main.py:217-219 run
  * by `loss.backward()` (:249): nll_loss_backward, _log_softmax_backward_data and the two cuBLAS
  * GEMMs.  bf16 mode: d <= 128, scale > 0.  fp32x3 mode (fp32 parity, d <= 64): the same gradients from
  * exact fp32 FFMA passes (64 x 64 softmax tiles in shared memory), any sign of scale. */
