@@ -41,8 +41,11 @@ def test_no_cpu_fallback():
     from recboard_b200 import ops
     U, W = torch.zeros(8, 64), torch.zeros(16, 64)
     lab = torch.zeros(8, dtype=torch.int64)
+    idx = torch.zeros(8, 3, dtype=torch.int64)
+    A = torch.eye(16).to_sparse_csr()
     for fn in (lambda: ops.score_dense(U, W), lambda: ops.fused_ce(U, W, lab), lambda: ops.topk_eval(U, W, 4),
-               lambda: ops.gather_rows(W, lab)):
+               lambda: ops.gather_rows(W, lab), lambda: ops.gather_dot(U, W, idx), lambda: ops.normalize_rows(W),
+               lambda: ops.spmm(A, W), lambda: ops.ce_backward(U, W, lab, torch.zeros(8), 1.0)):
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             fn()
 
