@@ -14,12 +14,16 @@ What is restated here, and from where (paths relative to /root/reference):
   * CE loss                ``CrossEntropy4Logits(reduction="mean")`` = ``F.cross_entropy`` SASRec/main.py:126,219
   * evaluate               line-for-line from UniSRec/main.py:400-447 (mask value -1e23 applied
                            BEFORE ranking, dense multi-hot targets, ``n=bsz`` weighting)
+  * pool / sampled scoring ``itemEmbds[ids]`` + ``einsum("MD,MKD->MK")``  SASRec/main.py:230-236, HSTU/main.py:192-197
+  * row normalisation      ``F.normalize(weight[NUM_PADS:], dim=-1)``       HSTU/main.py:180-184
+  * LightGCN propagation   ``self.Adj @ allEmbds``                            LightGCN/main.py:83
   * HR@k / NDCG@k / RECALL / PRECISION / MRR: ``freerec.metrics`` is NOT in the tree.  The
     formulas below are the standard ones (topk -> gather -> hit / DCG/IDCG); for the LOU
     protocol (exactly one target per row, HSTU/sampler.py:124) they are unambiguous.
 
 PARITY PIN STATUS
-  * model half (gather, contraction, CE, gradients): PINNED against outputs of the reference's
+  * model half (gather, contraction, CE, gradients, pool / sampled scoring, normalisation,
+    propagation): PINNED against outputs of the reference's
     own unmodified code imported in the build container (``oracle/gen_golden.py`` ->
     ``tests/golden/*.npz``; checked by ``tests/test_oracle_golden.py``).
   * evaluate/metric half: restated from the in-tree ``UniSRec/main.py:400-447`` override; the
