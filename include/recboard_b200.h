@@ -13,7 +13,7 @@
  *   - dtype: storage type of U / W / table.  mode: arithmetic of the contraction.
  *   - Matrices are row-major and contiguous: U (M,d), W (N,d) ("TN" GEMM, both K-major).
  *   - d must be a multiple of 8; bf16 mode supports d <= 256 (CE backward: d <= 128),
- *     fp32x3 mode supports d <= 64.  Base pointers must be 16-byte aligned.
+ *     fp32x3 mode supports d <= 128.  Base pointers must be 16-byte aligned.
  *   - There is no CPU fallback: without a CUDA device every compute entry returns an error.
  */
 #ifndef RECBOARD_B200_H
@@ -125,7 +125,7 @@ int rb_ce_du_finish(const float* dU_unnorm, const float* row_max, const float* l
  * Recomputes S tile by tile; the softmax tile lives only in TMEM; the one-hot is applied exactly in
  * fp32 by an index-ordered (deterministic) row update.  Replaces the autograd of SASRec/main.py:217-219 run
  * by `loss.backward()` (:249): nll_loss_backward, _log_softmax_backward_data and the two cuBLAS
- * GEMMs.  bf16 mode: d <= 128, scale > 0.  fp32x3 mode (fp32 parity, d <= 64): the same gradients from
+ * GEMMs.  bf16 mode: d <= 128, scale > 0.  fp32x3 mode (fp32 parity, d <= 128): the same gradients from
  * exact fp32 FFMA passes (64 x 64 softmax tiles in shared memory), any sign of scale. */
 int rb_ce_bwd(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
               int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,

@@ -143,7 +143,8 @@ struct Bump {
 
 static int kc_for(int d, int mode) {
   const int per = (mode == RB_MODE_BF16) ? 64 : 32;
-  return (d + per - 1) / per;
+  const int kc = (d + per - 1) / per;
+  return (mode != RB_MODE_BF16 && kc == 3) ? 4 : kc;   // fp32x3 tiles come in 1, 2 or 4 chunks ([hi|lo] pitch = kc*32)
 }
 static int check_common(const void* U, const void* W, long long M, long long N, int d, int dtype, int mode) {
   if (!U || !W) return fail(RB_E_ARG, "null operand");
@@ -155,7 +156,7 @@ static int check_common(const void* U, const void* W, long long M, long long N, 
     if (d > 256) return fail(RB_E_UNSUPPORTED, "bf16 mode supports d <= 256 (got %d)", d);
   } else if (mode == RB_MODE_FP32X3) {
     if (dtype != RB_DTYPE_F32) return fail(RB_E_UNSUPPORTED, "fp32x3 mode needs fp32 operands");
-    if (d > 64) return fail(RB_E_UNSUPPORTED, "fp32x3 mode supports d <= 64 (got %d)", d);
+    if (d > 128) return fail(RB_E_UNSUPPORTED, "fp32x3 mode supports d <= 128 (got %d)", d);
   } else {
     return fail(RB_E_ARG, "unknown mode %d", mode);
   }
@@ -174,7 +175,7 @@ static int launch_sweep_t(const CUtensorMap& ts, const CUtensorMap& ty, const Sw
 // Stationary tiles per CTA: two (256 rows) whenever there is a second tile to fill -- halves the L2->SM
 // traffic of a sweep (see sweep.cuh).
 static int sweep_xt(int mode, int d, long long n_stat) {
-  (void)mode; (void)d;
+  if (mode != RB_MODE_BF16 && d > 64) return 1;   // fp32x3 at d = 128: one [hi|lo] stationary tile is already 128 KB
   return n_stat > 128 ? 2 : 1;
 }
 
@@ -203,6 +204,7 @@ static int launch_sweep(int mode, int kc, const CUtensorMap& ts, const CUtensorM
   } else {
     if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 1, BN, 5, ROWS>>(ts, ty, a, grid, st);
     if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 2, BN, 8, ROWS>>(ts, ty, a, grid, st);
+    if (kc == 4) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 4, BN, 5, ROWS>>(ts, ty, a, grid, st);
   }
   return fail(RB_E_UNSUPPORTED, "unsupported feature width for mode %d (kc=%d)", mode, kc);
 }
