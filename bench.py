@@ -228,9 +228,10 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     # A GPU that has idled through process start-up and input generation needs a few hundred milliseconds of
-    # load before its clocks settle (a cold first region once measured 8.6 ms/step against 5.5 warm): run the
-    # step untimed ~0.7 s first (120 times), then the W warm-up steps.
-    n_pre = 120   # a fixed count: every rank must issue the same collectives
+    # load before its clocks and the power controller settle (first regions of a fresh process measured 7.3-8.6
+    # ms/step against 5.8 sustained, also after a 0.7 s pre-warm): run the step untimed ~2.3 s first (400
+    # times), then the W warm-up steps.
+    n_pre = 400   # a fixed count (~2.3 s): every rank must issue the same collectives
     for _ in range(n_pre):
         hot_path(U_train, labels, seqs, U_eval, seen_crow, seen_col)
     torch.cuda.synchronize()
@@ -401,7 +402,7 @@ def run_ours(args):
             "config": {"workload": "configs[2]: SASRec bf16 full-softmax CE train + masked top-50 eval, 1M-item catalog per GPU (row-sharded), d=128, 4096 query rows, gather 4096x50",
                        "rows": ROWS, "n_items_total": n_total, "d": D, "topk": TOPK, "parallelism": f"row-sharded table x{world}",
                        "l2": "inputs larger than L2 (256 MB table shard streamed per sweep); no flush",
-                       "pre_warm": f"{n_pre} untimed steps (~0.7 s) before the {max(args.warmup, 3)} warm-up steps"},
+                       "pre_warm": f"{n_pre} untimed steps (~2.3 s) before the {max(args.warmup, 3)} warm-up steps"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "loss": loss_host, "metrics": res,
