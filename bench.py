@@ -42,6 +42,8 @@ METRIC = "full-catalog scored user-item pairs/sec (CE train + top-K eval)"
 PROFILED_TRAFFIC_BYTES = 262_347_520 + 206_989_568
 PROFILED_TRAFFIC_SOURCE = "profiles/r1o_ncu_summary.md (ncu --set full, one launch, N=1M shard)"
 UNIT = "pairs/s"
+WORKLOAD = ("configs[2]: SASRec bf16 full-softmax CE train + masked top-50 eval, "
+            "1M-item catalog per GPU (row-sharded), d=128, 4096 query rows, gather 4096x50")
 
 
 # ------------------------------------------------------------------------------ CPU arm
@@ -86,8 +88,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[2]: SASRec full-softmax CE train + top-50 eval, 1M-item catalog/GPU, d=128, 4096 rows",
-                   "note": "reference arm = oracle port of the reference's PyTorch lines on the host CPU, bounded sample"},
+        "config": {"workload": WORKLOAD, "rows": ROWS, "n_items_total": N_ITEMS_PER_GPU * max(args.gpus, 1), "d": D, "topk": TOPK,
+                   "note": "reference arm = oracle port of the reference's PyTorch lines (fp32) on the host CPU; every step is "
+                           "a bounded sample of this workload: " + sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -399,7 +402,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "configs[2]: SASRec bf16 full-softmax CE train + masked top-50 eval, 1M-item catalog per GPU (row-sharded), d=128, 4096 query rows, gather 4096x50",
+            "config": {"workload": WORKLOAD,
                        "rows": ROWS, "n_items_total": n_total, "d": D, "topk": TOPK, "parallelism": f"row-sharded table x{world}",
                        "l2": "inputs larger than L2 (256 MB table shard streamed per sweep); no flush",
                        "pre_warm": f"{n_pre} untimed steps (~2.3 s) before the {max(args.warmup, 3)} warm-up steps"},
