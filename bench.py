@@ -21,6 +21,7 @@ the reference lines; freerec is not installable here) on the host cores, on a bo
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -234,12 +235,15 @@ def run_ours(args):
     # load before its clocks and the power controller settle (first regions of a fresh process measured 7.3-8.6
     # ms/step against 5.8 sustained, also after a 0.7 s pre-warm): run the step untimed ~2.3 s first (400
     # times), then the W warm-up steps.
+    # The warm-up loops keep the previous step's results alive while the next step is enqueued, exactly as the
+    # timed loop does: otherwise the timed loop's second step needs fresh blocks from the caching allocator, and
+    # that cudaMalloc blocked the launching thread for 2-80 ms (GPU idle meanwhile: 9 ms/step outliers).
     n_pre = 400   # a fixed count (~2.3 s): every rank must issue the same collectives
     for _ in range(n_pre):
-        hot_path(U_train, labels, seqs, U_eval, seen_crow, seen_col)
+        loss, ids, _ = hot_path(U_train, labels, seqs, U_eval, seen_crow, seen_col)
     torch.cuda.synchronize()
     for i in range(max(args.warmup, 3)):
-        hot_path(U_train, labels, seqs, U_eval, seen_crow, seen_col)
+        loss, ids, _ = hot_path(U_train, labels, seqs, U_eval, seen_crow, seen_col)
         if i == 0:
             barrier()
             if rank == 0:
@@ -249,14 +253,30 @@ def run_ours(args):
     # ---- device-resident timing of exactly K steps (inputs > L2: the 256 MB table shard is streamed
     #      from HBM several times per step, so no L2 flush is needed between iterations)
     launches0 = L.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]   # one per step boundary
     barrier()
-    e0.record()
-    for _ in range(args.steps):
+    gc.collect()
+    gc.disable()   # no collector pause on the launching thread inside the timed regions
+    mallocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
+    host_ms = []
+    barrier()
+    evs[0].record()
+    for i in range(args.steps):
+        th = time.perf_counter()
         loss, ids, _ = hot_path(U_train, labels, seqs, U_eval, seen_crow, seen_col)
-    e1.record()
+        evs[i + 1].record()
+        host_ms.append(1e3 * (time.perf_counter() - th))
     barrier()
-    ms = e0.elapsed_time(e1)
+    if os.environ.get("RB_BENCH_DEBUG") and rank == 0:
+        print("host enqueue ms:", " ".join(f"{x:.2f}" for x in host_ms), file=sys.stderr)
+    ms = evs[0].elapsed_time(evs[-1])   # the K steps, first launch to last completion
+    per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    if os.environ.get("RB_BENCH_DEBUG") and rank == 0:
+        print("per-step ms:", " ".join(f"{x:.2f}" for x in per_step), file=sys.stderr)
+    per_step.sort()
+    step_ms = {"min": per_step[0], "median": statistics.median(per_step), "max": per_step[-1],
+               "host_enqueue_ms_max": max(host_ms),
+               "cuda_mallocs_in_region": torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs0}
     launches = L.launch_count() - launches0
     t = torch.tensor([ms], device=dev)
     if world > 1:
@@ -331,6 +351,7 @@ def run_ours(args):
     if os.environ.get("RB_E2E_DEBUG"):
         print(f"rank {rank}: e2e loop {1e3 * e2e_s:.2f} ms for {args.steps} steps", file=sys.stderr)
     clocks = sampler.stop() if rank == 0 else None   # sampled over both timed regions (device-timed and end-to-end)
+    gc.enable()
     t = torch.tensor([e2e_s], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -401,7 +422,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
+            "dtype": "bf16", "data": "synthetic", "step_ms": step_ms,
             "config": {"workload": WORKLOAD,
                        "rows": ROWS, "n_items_total": n_total, "d": D, "topk": TOPK, "parallelism": f"row-sharded table x{world}",
                        "l2": "inputs larger than L2 (256 MB table shard streamed per sweep); no flush",
