@@ -238,7 +238,9 @@ def run_ours(args):
     # The warm-up loops keep the previous step's results alive while the next step is enqueued, exactly as the
     # timed loop does: otherwise the timed loop's second step needs fresh blocks from the caching allocator, and
     # that cudaMalloc blocked the launching thread for 2-80 ms (GPU idle meanwhile: 9 ms/step outliers).
-    n_pre = 400   # a fixed count (~2.3 s): every rank must issue the same collectives
+    n_pre = int(os.environ.get("RB_BENCH_PREWARM", "400"))   # a fixed count (~2.3 s): every rank must issue the same
+    # collectives.  RB_BENCH_PREWARM=0 is for the ncu launch-list pass of this command (tools/gpu_round.sh), where
+    # every launch costs milliseconds of profiler overhead; never for a reported number.
     for _ in range(n_pre):
         loss, ids, _ = hot_path(U_train, labels, seqs, U_eval, seen_crow, seen_col)
     torch.cuda.synchronize()

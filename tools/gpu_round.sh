@@ -8,6 +8,8 @@ tail -3 gpurun_out/${tag}_pytest.log
 timeout 300 python bench.py --steps 20 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
 cat gpurun_out/${tag}_bench.json; tail -3 gpurun_out/${tag}_bench.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches.csv python tests/prof_target.py > gpurun_out/${tag}_ncu.log 2>&1
+# launch list of the bench command itself (2 timed steps, no pre-warm: the kernels' SHARES of a step, not a bench value)
+RB_BENCH_PREWARM=0 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_bench_launches.csv python bench.py --steps 2 --warmup 1 > gpurun_out/${tag}_bench_ncu.log 2>&1
 python - <<PY
 import csv
 rows=[r for r in csv.reader(open("gpurun_out/${tag}_launches.csv")) if len(r)>10 and r[0].isdigit()]
