@@ -624,3 +624,29 @@ def test_full_size_config5_bert4rec_shard(ops):
     pj = torch.exp((U.float() @ W[j].float()) + bias[j] - lse).sum() / M - float((lab == j).sum()) / M
     assert abs(float(db[j]) - float(pj)) <= 1e-5 + 2e-3 * abs(float(pj))
     assert peak < 6 * 2 ** 30, f"peak extra memory {peak / 2**30:.1f} GiB: the logits must never be materialised"
+
+
+@pytest.mark.parametrize("M,N,d", [(513, 4099, 128), (3013, 12101, 64)])
+def test_ce_dw_scattered_hot_label(ops, M, N, d):
+    """One-hot correction when the rows that share a label are scattered through the batch (every third row,
+    as a Zipf-head label is at the bench shape): the owner's warp meets its matches a few per 32-row chunk, so its
+    index queue fills across chunks and is flushed with a remainder carried over.  Checked against the oracle
+    gradient (whose max-norm these label rows dominate) and, bit for bit, against the fp32 path rounded to bf16."""
+    g = torch.Generator().manual_seed(M * 3 + N + d)
+    U = bf16_round(torch.randn(M, d, generator=g) * 1.5 / d ** 0.25)
+    W = bf16_round(torch.randn(N, d, generator=g) * 1.5 / d ** 0.25)
+    lab = torch.randint(0, N, (M,), generator=g)
+    lab[1::3] = 11          # scattered hot label whose owner (row 1) is not chunk-aligned
+    lab[5::7] = N - 2       # a second one, in the last (partial) item tile
+    ref_loss, rdU, rdW, _ = orc.ce_fwd_bwd(U, W, lab)
+    Ud, Wd = dev(U).bfloat16().requires_grad_(True), dev(W).bfloat16().requires_grad_(True)
+    loss = ops.fused_ce(Ud, Wd, dev(lab))
+    loss.backward()
+    assert abs(float(loss) - float(ref_loss)) <= 1e-5 * abs(float(ref_loss))
+    assert_rel(Wd.grad, rdW, 2 * BF16_RTOL, "dW")
+    Ub, Wb, labd = dev(U).bfloat16(), dev(W).bfloat16(), dev(lab)
+    m, l, ll = ops.ce_rowstats(Ub, Wb, labd)
+    lse = m + torch.log(l)
+    _, dW32, _ = ops.ce_backward(Ub, Wb, labd, lse, 1.0 / M, need_dU=False, need_dW=True)
+    _, dWb, _ = ops.ce_backward(Ub, Wb, labd, lse, 1.0 / M, need_dU=False, need_dW=True, dw_dtype=torch.bfloat16)
+    assert torch.equal(dWb, dW32.bfloat16())
