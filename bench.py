@@ -344,12 +344,14 @@ def run_ours(args):
 
     e2e_loop(4)
     barrier()
+    mallocs1 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     t0 = time.perf_counter()
     loss_host, res = e2e_loop(args.steps)
     if os.environ.get("RB_E2E_DEBUG"):
         print(f"rank {rank}: before barrier {1e3 * (time.perf_counter() - t0):.2f} ms", file=sys.stderr)
     barrier()
     e2e_s = time.perf_counter() - t0
+    e2e_mallocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs1
     if os.environ.get("RB_E2E_DEBUG"):
         print(f"rank {rank}: e2e loop {1e3 * e2e_s:.2f} ms for {args.steps} steps", file=sys.stderr)
     clocks = sampler.stop() if rank == 0 else None   # sampled over both timed regions (device-timed and end-to-end)
@@ -431,7 +433,7 @@ def run_ours(args):
                        "pre_warm": f"{n_pre} untimed steps (~2.3 s) before the {max(args.warmup, 3)} warm-up steps"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "loss": loss_host, "metrics": res,
+                    "loss": loss_host, "metrics": res, "cuda_mallocs_in_region": e2e_mallocs,
                     "how": "pinned host inputs copied in and loss + (B,K) hit matrix copied out every step; the copy of step "
                            "i+1 and the host metric reduction of step i-1 overlap step i"},
             "gpu_launches": launches,
