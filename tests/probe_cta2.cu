@@ -166,6 +166,84 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(long long* __restrict__ c
   if (warp == 0) p_tmem_dealloc<CTAS>(tmem, 512);
 }
 
+// The MMA mix of one step of the fused CE passes (pair.cuh), issued back to back with no hand-shakes: per step
+// 16 SS instructions (S_g[h] = X_g . Y_half^T: 2 stationary tiles x 2 K-chunks x 4 slices, N = 64) and 8 TS
+// instructions (A_g += P_g[h] . Y_half: 2 tiles x 4 slices, N = 128, A = the S columns reinterpreted as bf16, B =
+// the MN-major view of the same half tile).  Single CTA: the "raw" floor of the experiments file (1405 clk per
+// step).  CTA pair: the same instruction count covers four stationary tiles (two per SM), the streamed half tile
+// split by rows for MMA1 and by feature columns for MMA2.  Timing only (accumulators are not checked).
+constexpr int MIX_X_BYTES = 65536;   // X0 | X1, two 16 KB K-chunks each
+constexpr int MIX_Y_BYTES = 32768;   // one streamed tile: two 16 KB K-chunks of 128 rows
+constexpr int MIX_SMEM_BYTES = MIX_X_BYTES + MIX_Y_BYTES + 1024;
+template <int CTAS>
+__global__ void __launch_bounds__(128, 1) mix_kernel(long long* __restrict__ cycles, float* __restrict__ d00, int reps) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* x_smem = smem;
+  uint8_t* y_smem = smem + MIX_X_BYTES;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = cluster_ctarank();
+  for (int i = threadIdx.x; i < (MIX_X_BYTES + MIX_Y_BYTES) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = FILL;
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    p_tmem_alloc<CTAS>(&tmem_slot, 512);
+    p_tmem_relinquish<CTAS>();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (warp == 0) {
+    if (rank == 0) {
+      constexpr uint32_t idesc1 = make_idesc(FMT_BF16, 128 * CTAS, 64, 0, 0);
+      constexpr uint32_t idesc2 = make_idesc(FMT_BF16, 128 * CTAS, 128, 0, 1);
+      constexpr uint32_t dhi = smem_desc_hi(1024);
+      const uint32_t x_lo = smem_desc_lo(smem_u32(x_smem), 16);
+      const uint32_t y_lo1 = smem_desc_lo(smem_u32(y_smem), 16);
+      const uint32_t y_lo2 = smem_desc_lo(smem_u32(y_smem), 16384);
+      constexpr uint32_t half1 = 8192 / CTAS;   // MMA1: rows [64h, 64h+64) of the tile, split by rows across a pair
+      if (elect_one()) {
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+          const uint32_t h = r & 1;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const uint32_t s_tmem = tmem + g * 128 + h * 64;
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                p_mma_ss<CTAS>(s_tmem, smem_desc(dhi, x_lo + ((g * 32768 + c * 16384 + kk * 32) >> 4)),
+                               smem_desc(dhi, y_lo1 + ((c * 16384 + h * half1 + kk * 32) >> 4)), idesc1, (c | kk) != 0);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)   // a pair holds 64 of the 128 feature columns per SM: one 16 KB group, no LBO step
+              p_mma_ts<CTAS>(tmem + 256 + g * 128, s_tmem + kk * 8, smem_desc(dhi, y_lo2 + ((h * 8192 + kk * 2048) >> 4)),
+                             idesc2, (r | kk) != 0);
+          }
+        }
+        p_commit<CTAS>(&bar, static_cast<uint16_t>((1u << CTAS) - 1u));
+        mbar_wait(&bar, 0);
+        const long long t1 = clock64();
+        cycles[blockIdx.x / CTAS] = t1 - t0;
+      }
+      __syncwarp();
+    } else {
+      mbar_wait(&bar, 0);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  if (threadIdx.x == 0) d00[blockIdx.x] = 0.f;
+  if (warp == 0) p_tmem_dealloc<CTAS>(tmem, 512);
+}
+
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
   fprintf(stderr, "%s:%d %s: %s\n", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); exit(1); } } while (0)
 
@@ -212,6 +290,43 @@ static void run(int sms, int reps) {
   CK(cudaFree(cyc)); CK(cudaFree(d00));
 }
 
+template <int CTAS>
+static void run_mix(int sms, int reps) {
+  auto kern = mix_kernel<CTAS>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MIX_SMEM_BYTES));
+  const int grid = (sms / CTAS) * CTAS, clusters = grid / CTAS;
+  long long* cyc; float* d00;
+  CK(cudaMalloc(&cyc, clusters * sizeof(long long)));
+  CK(cudaMalloc(&d00, grid * sizeof(float)));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = MIX_SMEM_BYTES;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  float ms = 0.f;
+  for (int it = 0; it < 3; ++it) {
+    CK(cudaEventRecord(e0));
+    CK(cudaLaunchKernelEx(&cfg, kern, cyc, d00, reps));
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+  }
+  std::vector<long long> hc(clusters);
+  CK(cudaMemcpy(hc.data(), cyc, clusters * sizeof(long long), cudaMemcpyDeviceToHost));
+  double sum = 0;
+  for (long long c : hc) sum += static_cast<double>(c) / reps;
+  // executed flops per step and SM: 2 tiles x (128 x 64 x 128 scores + 128 x 128 x 64 accumulate) x 2 = 8.4 MFLOP
+  const double flop = static_cast<double>(grid) * reps * 2.0 * (2.0 * 128 * 64 * 128 + 2.0 * 128 * 128 * 64);
+  printf("{\"mix\": \"pair-kernel step: 16 SS N=64 + 8 TS N=128\", \"ctas\": %d, \"clk_per_step\": %.0f, "
+         "\"clk_per_step_per_sm_work\": %.0f, \"kernel_ms\": %.3f, \"executed_tflops\": %.0f}\n",
+         CTAS, sum / clusters, sum / clusters / CTAS, ms, flop / (ms * 1e-3) / 1e12);
+  fflush(stdout);
+  CK(cudaFree(cyc)); CK(cudaFree(d00));
+}
+
 int main(int argc, char** argv) {
   const int reps = argc > 1 ? atoi(argv[1]) : 2048;
   cudaDeviceProp p;
@@ -229,5 +344,8 @@ int main(int argc, char** argv) {
   run<2, 256, false, false>(sms, reps);
   run<2, 128, true, true>(sms, reps);
   run<2, 256, true, true>(sms, reps);
+  // the fused CE passes' instruction mix, single CTA (known floor: ~1405 clk per step) against a pair
+  run_mix<1>(sms, reps);
+  run_mix<2>(sms, reps);
   return 0;
 }
