@@ -412,7 +412,10 @@ def run_ours(args):
                     "executed_tflops": 2 * ach,
                     "traffic_source": PROFILED_TRAFFIC_SOURCE,
                     "algorithmic_bytes": n_shard * D * 2 + n_shard * D * 2 + ROWS * D * 2,   # W in, bf16 dW out, U
-                    "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.59 PFLOP/s"}
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst: the kernel is timed alone)" if peaks else "fallback 1.59 PFLOP/s"}
+        if peaks.get("bf16_tflops_sustained"):   # for reference: the same launches against the sustained cuBLAS figure
+            roofline["peak_sustained"] = peaks["bf16_tflops_sustained"]
+            roofline["frac_of_sustained"] = ach / peaks["bf16_tflops_sustained"]
 
     cpu_baseline = None
     if rank == 0 and world == 1:
