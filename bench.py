@@ -231,10 +231,10 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # A GPU that has idled through process start-up and input generation needs a few hundred milliseconds of
-    # load before its clocks and the power controller settle (first regions of a fresh process measured 7.3-8.6
-    # ms/step against 5.8 sustained, also after a 0.7 s pre-warm): run the step untimed ~2.3 s first (400
-    # times), then the W warm-up steps.
+    # A GPU that has idled through process start-up and input generation boosts for a few hundred milliseconds
+    # before the 1 kW power cap pulls the SM clock down (5.2-5.4 ms/step cool against 5.7-5.9 sustained): run the
+    # step untimed ~2.3 s first (400 times), then the W warm-up steps, so that the timed region is the sustained
+    # state.  (The 7-9 ms/step first regions earlier builds saw were not clocks but the allocator stall below.)
     # The warm-up loops keep the previous step's results alive while the next step is enqueued, exactly as the
     # timed loop does: otherwise the timed loop's second step needs fresh blocks from the caching allocator, and
     # that cudaMalloc blocked the launching thread for 2-80 ms (GPU idle meanwhile: 9 ms/step outliers).
