@@ -19,3 +19,9 @@ def test_probe_cta2_compiles_to_2cta_mma():
     assert "UTCHMMA.2CTA" in sass          # tcgen05.mma.cta_group::2
     assert "UTCBAR.2CTA.MULTICAST" in sass  # tcgen05.commit ... multicast::cluster
     assert "UTCHMMA " in sass or "UTCHMMA\n" in sass or sass.count("UTCHMMA") > sass.count("UTCHMMA.2CTA")  # single-CTA lines too
+    # the protocol probe: 2-CTA TMA loads, pair MMA, multicast commits (tests/probe_cta2_tma.cu)
+    exe2 = ROOT / "tests" / "_probe" / "probe_cta2_tma"
+    assert exe2.exists()
+    sass2 = subprocess.run([cuobjdump, "-sass", str(exe2)], check=True, capture_output=True, text=True).stdout
+    for mnemonic in ("UTMALDG.2D.2CTA", "UTCHMMA.2CTA", "UTCBAR.2CTA.MULTICAST"):
+        assert mnemonic in sass2, mnemonic

@@ -7,3 +7,5 @@ mkdir -p tests/_probe
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 $NVCC -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -o tests/_probe/probe_cta2 tests/probe_cta2.cu "$@"
 echo built tests/_probe/probe_cta2
+$NVCC -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -o tests/_probe/probe_cta2_tma tests/probe_cta2_tma.cu "$@"
+echo built tests/_probe/probe_cta2_tma
