@@ -25,3 +25,9 @@ def test_probe_cta2_compiles_to_2cta_mma():
     sass2 = subprocess.run([cuobjdump, "-sass", str(exe2)], check=True, capture_output=True, text=True).stdout
     for mnemonic in ("UTMALDG.2D.2CTA", "UTCHMMA.2CTA", "UTCBAR.2CTA.MULTICAST"):
         assert mnemonic in sass2, mnemonic
+    # the stand-alone CTA-pair scoring sweep (tests/probe_cta2_sweep.cu)
+    exe3 = ROOT / "tests" / "_probe" / "probe_cta2_sweep"
+    assert exe3.exists()
+    sass3 = subprocess.run([cuobjdump, "-sass", str(exe3)], check=True, capture_output=True, text=True).stdout
+    for mnemonic in ("UTMALDG.2D.2CTA", "UTCHMMA.2CTA", "UTCBAR.2CTA.MULTICAST"):
+        assert mnemonic in sass3, mnemonic

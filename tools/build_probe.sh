@@ -9,3 +9,5 @@ $NVCC -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -o tests/
 echo built tests/_probe/probe_cta2
 $NVCC -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -o tests/_probe/probe_cta2_tma tests/probe_cta2_tma.cu "$@"
 echo built tests/_probe/probe_cta2_tma
+$NVCC -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -o tests/_probe/probe_cta2_sweep tests/probe_cta2_sweep.cu "$@"
+echo built tests/_probe/probe_cta2_sweep
