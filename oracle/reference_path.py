@@ -272,6 +272,13 @@ def merge_topk(parts: List[Tuple[torch.Tensor, torch.Tensor]], k: int):
     return vals.gather(1, o)[:, :k], ids.gather(1, o)[:, :k]
 
 
+def hits_from_topk(top_ids: torch.Tensor, target_crow, target_col, n_items: int) -> torch.Tensor:
+    """(B,K) float32 hit matrix of a ranked id list against the dense multi-hot targets of
+    UniSRec/main.py:414 (``targets.gather(1, idx)``); missing entries (id < 0) never hit."""
+    targets = csr_to_dense(target_crow, target_col, n_items)
+    return targets.gather(1, top_ids.long().clamp_min(0)) * (top_ids >= 0).float()
+
+
 def metrics_from_topk(top_ids: torch.Tensor, target_crow, target_col, n_items: int, monitors):
     """Same metric values computed from a (B,Kmax) id list instead of dense scores
     (the fused path's route; must agree with ``evaluate_batch`` whenever ranks agree)."""

@@ -70,7 +70,20 @@ def check(code: int, what: str) -> None:
 
 
 def ptr(t):
-    return None if t is None else C.c_void_p(t.data_ptr())
+    """Raw device pointer of a tensor handed to the C ABI (dense row-major layout is part of the contract)."""
+    if t is None:
+        return None
+    if not t.is_contiguous():
+        raise RuntimeError("recboard_b200: a non-contiguous tensor reached the C ABI (call .contiguous() first)")
+    return C.c_void_p(t.data_ptr())
+
+
+def call(device, name: str, *args) -> None:
+    """One C-ABI call with ``device`` made current for its duration: the library reads the SM count, sets
+    function attributes and launches on the *current* device, while the pointers and the stream belong to
+    the tensors' device -- the two must agree also when a process drives several GPUs."""
+    with torch.cuda.device(device):
+        check(getattr(lib(), name)(*args), name)
 
 
 def stream_ptr(device) -> C.c_void_p:
@@ -94,8 +107,6 @@ def require_cuda(*tensors) -> torch.device:
             raise RuntimeError(
                 "recboard_b200 ops run on a CUDA device only (no CPU fallback); got a CPU tensor"
             )
-        if not t.is_contiguous():
-            raise RuntimeError("recboard_b200 ops need contiguous tensors")
         dev = t.device if dev is None else dev
         if t.device != dev:
             raise RuntimeError("all tensors must live on the same device")
@@ -107,20 +118,29 @@ class Workspace:
     calls on the same stream are ordered and may share it, calls on different streams must not."""
 
     _bufs = {}
+    MAX_STREAMS = 8   # buffers kept per device; the least recently used one goes first (short-lived side streams)
 
     @classmethod
     def get(cls, device: torch.device, nbytes: int) -> torch.Tensor:
-        index = device.index if device.index is not None else torch.cuda.current_device()
-        key = (index, torch.cuda.current_stream(device).cuda_stream)
-        buf = cls._bufs.get(key)
+        if device.index is None:
+            raise RuntimeError("recboard_b200: tensors must carry an explicit CUDA device index")
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+        buf = cls._bufs.pop(key, None)
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
-            cls._bufs[key] = buf
+        cls._bufs[key] = buf   # re-inserted last: dict order is the LRU order
+        same_dev = [k for k in cls._bufs if k[0] == device.index]
+        for k in same_dev[:-cls.MAX_STREAMS]:
+            del cls._bufs[k]   # the caching allocator keeps the block alive until queued work on it has run
         return buf
 
 
-def workspace_bytes(op: int, M: int, N: int, d: int, K: int = 0, mode: int = MODE_BF16, nnz: int = 0) -> int:
-    return int(lib().rb_workspace_bytes(op, M, N, d, K, mode, nnz))
+def workspace_bytes(op: int, M: int, N: int, d: int, K: int = 0, mode: int = MODE_BF16, nnz: int = 0,
+                    device=None) -> int:
+    if device is None:
+        return int(lib().rb_workspace_bytes(op, M, N, d, K, mode, nnz))
+    with torch.cuda.device(device):   # the plan depends on the SM count of the device the call will run on
+        return int(lib().rb_workspace_bytes(op, M, N, d, K, mode, nnz))
 
 
 def launch_count() -> int:

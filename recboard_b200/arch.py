@@ -153,15 +153,19 @@ class HSTUFused(FusedFullCatalogMixin):
         if hasattr(sup, "reset_ranking_buffers"):
             sup.reset_ranking_buffers()
         out_dtype = torch.bfloat16 if self.fused_precision == "bf16" else None
-        self._fused_item = ops.normalize_rows(self.Item.embeddings.weight[self.NUM_PADS:], out_dtype=out_dtype)
+        w = self.Item.embeddings.weight
+        self._fused_item = ops.normalize_rows(w[self.NUM_PADS:], out_dtype=out_dtype)
+        self._fused_item_key = (w.data_ptr(), w._version)   # the cache is only valid for these exact weights
 
     def encode_users(self, data) -> torch.Tensor:
         """(B, S, d) normalised user states; default = the reference's ``encode`` (HSTU/main.py:164-184)."""
         return self.encode(data)[0]
 
     def _eval_operands(self, data):
-        if getattr(self, "_fused_item", None) is None or self.training:
-            userEmbds, itemEmbds = self.encode(data)
+        w = self.Item.embeddings.weight
+        stale = getattr(self, "_fused_item_key", None) != (w.data_ptr(), w._version)   # optimizer step / load_state_dict since
+        if getattr(self, "_fused_item", None) is None or self.training or stale:
+            userEmbds, itemEmbds = self.encode(data)   # the reference's own per-call normalisation (HSTU/main.py:180-184)
             return userEmbds[:, -1, :], itemEmbds, None, 1.0, 0
         return self.encode_users(data)[:, -1, :], self._fused_item, None, 1.0, 0
 

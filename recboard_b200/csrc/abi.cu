@@ -820,6 +820,8 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
   if (!top_vals || !top_ids) return fail(RB_E_ARG, "null output");
   if (K < 1 || K > 256) return fail(RB_E_UNSUPPORTED, "K=%d outside [1,256]", K);
   if (!(scale > 0.f)) return fail(RB_E_UNSUPPORTED, "top-K needs scale > 0");
+  if (id_base < 0 || id_base + N > 0x7fffffffll) return fail(RB_E_ARG, "id_base + N = %lld does not fit the int32 ids this entry returns", (long long)(id_base + N));
+  if (seen_nnz > 0x7fffffffll) return fail(RB_E_ARG, "seen_nnz = %lld does not fit int32 row offsets", (long long)seen_nnz);
   if ((seen_crow == nullptr) != (seen_col == nullptr)) return fail(RB_E_ARG, "seen_crow/seen_col must both be given");
   if (!ws) return fail(RB_E_WORKSPACE, "workspace required");
   Bump b(ws, ws_bytes);

@@ -6,9 +6,9 @@ metric functions are freerec's).  The fused path gets the sorted (B,Kmax) id lis
 ``ops.topk_eval`` once and derives every metric@k from it.
 
 Reduction contract: per batch a float32 mean, then a bsz-weighted running mean
-(``monitor(..., n=bsz, reduction="mean")``).  ``hits_from_topk`` runs on the device; the tiny (B,K)
-hit matrix is reduced with the same float32 torch ops the CPU oracle uses, so metric values are
-bit-identical whenever the ranked ids agree.
+(``monitor(..., n=bsz, reduction="mean")``).  ``hits_from_topk`` is a kernel (``rb_topk_hits``; CUDA tensors
+only); the tiny (B,K) hit matrix is reduced with the same float32 torch ops the CPU oracle uses, so metric
+values are bit-identical whenever the ranked ids agree.
 """
 from __future__ import annotations
 
@@ -23,24 +23,14 @@ def hits_from_topk(top_ids: torch.Tensor, target_crow: torch.Tensor, target_col:
 
     ``target_crow/col`` is the CSR of ``data[IUnseen]`` (``Item.to_csr``, UniSRec/main.py:414);
     LOU evaluation has exactly one target per row."""
+    from . import _lib as L
     B, K = top_ids.shape
-    if top_ids.is_cuda:   # product path: one kernel (rb_topk_hits); the torch lines below serve host-side tests only
-        from . import _lib as L
-        dev = L.require_cuda(top_ids, target_crow, target_col)
-        ids32 = top_ids.to(torch.int32).contiguous()
-        hits = torch.empty(B, K, dtype=torch.float32, device=dev)
-        L.check(L.lib().rb_topk_hits(L.ptr(ids32), L.ptr(target_crow.to(torch.int64).contiguous()),
-                                     L.ptr(target_col.to(torch.int64).contiguous()), B, K, L.ptr(hits), L.stream_ptr(dev)),
-                "rb_topk_hits")
-        return hits
-    ids = top_ids.long()
-    rows = torch.arange(B, device=ids.device).unsqueeze(1)
-    keys = rows * n_items + ids.clamp_min(0)
-    trow = torch.repeat_interleave(torch.arange(B, device=ids.device), target_crow[1:] - target_crow[:-1])
-    tkeys = trow * n_items + target_col  # sorted: rows ascending, cols ascending inside a row
-    pos = torch.searchsorted(tkeys, keys.reshape(-1)).clamp_max(max(tkeys.numel() - 1, 0))
-    hit = (tkeys[pos] == keys.reshape(-1)).reshape(B, K) if tkeys.numel() else torch.zeros(B, K, dtype=torch.bool, device=ids.device)
-    return (hit & (top_ids >= 0)).float()
+    dev = L.require_cuda(top_ids, target_crow, target_col)   # raises on CPU tensors: the product has no CPU path
+    ids32 = top_ids.to(torch.int32).contiguous()
+    hits = torch.empty(B, K, dtype=torch.float32, device=dev)
+    L.call(dev, "rb_topk_hits", L.ptr(ids32), L.ptr(target_crow.to(torch.int64).contiguous()),
+           L.ptr(target_col.to(torch.int64).contiguous()), B, K, L.ptr(hits), L.stream_ptr(dev))
+    return hits
 
 
 def _dcg_weights(k: int) -> torch.Tensor:

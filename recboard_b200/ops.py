@@ -33,7 +33,7 @@ def _prep(U, W, precision):
 
 
 def _ws(dev, op, M, N, d, K=0, mode=L.MODE_BF16, nnz=0):
-    n = L.workspace_bytes(op, M, N, d, K, mode, nnz)
+    n = L.workspace_bytes(op, M, N, d, K, mode, nnz, device=dev)
     return L.Workspace.get(dev, n), n
 
 
@@ -44,13 +44,11 @@ def gather_rows_raw(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     dev = L.require_cuda(table, idx)
     if idx.dtype != torch.int64:
         raise TypeError("idx must be int64")
+    table, idx = table.contiguous(), idx.contiguous()
     n_rows, d = table.shape
     out = torch.empty(*idx.shape, d, dtype=table.dtype, device=dev)
-    L.check(
-        L.lib().rb_gather_rows(L.ptr(table), L.ptr(idx), L.ptr(out), idx.numel(), n_rows, d,
-                               L.dtype_code(table), L.stream_ptr(dev)),
-        "rb_gather_rows",
-    )
+    L.call(dev, "rb_gather_rows", L.ptr(table), L.ptr(idx), L.ptr(out), idx.numel(), n_rows, d,
+                               L.dtype_code(table), L.stream_ptr(dev))
     return out
 
 
@@ -62,12 +60,10 @@ def scatter_add_rows_(grad_table: torch.Tensor, grad_out: torch.Tensor, idx: tor
         raise TypeError("grad_table must be float32")
     n_rows, d = grad_table.shape
     n_idx = idx.numel()
+    grad_out, idx = grad_out.contiguous(), idx.contiguous()   # grad_table is updated in place: it must be dense already
     ws, n = _ws(dev, L.OP_SCATTER_ADD, 0, 0, d, nnz=n_idx)
-    L.check(
-        L.lib().rb_scatter_add_rows(L.ptr(grad_out), L.ptr(idx), L.ptr(grad_table), n_idx, n_rows, d,
-                                    L.dtype_code(grad_out), padding_idx, L.ptr(ws), n, L.stream_ptr(dev)),
-        "rb_scatter_add_rows",
-    )
+    L.call(dev, "rb_scatter_add_rows", L.ptr(grad_out), L.ptr(idx), L.ptr(grad_table), n_idx, n_rows, d,
+                                    L.dtype_code(grad_out), padding_idx, L.ptr(ws), n, L.stream_ptr(dev))
     return grad_table
 
 
@@ -114,11 +110,8 @@ class _GatherDot(torch.autograd.Function):
         M, d = Uc.shape
         K = idc.shape[1]
         S = torch.empty(M, K, dtype=torch.float32, device=dev)
-        L.check(
-            L.lib().rb_gather_dot(L.ptr(Uc), L.ptr(Tc), L.ptr(idc), float(scale), L.ptr(S), M, K, Tc.shape[0], d,
-                                  L.dtype_code(Uc), L.stream_ptr(dev)),
-            "rb_gather_dot",
-        )
+        L.call(dev, "rb_gather_dot", L.ptr(Uc), L.ptr(Tc), L.ptr(idc), float(scale), L.ptr(S), M, K, Tc.shape[0], d,
+                                  L.dtype_code(Uc), L.stream_ptr(dev))
         ctx.save_for_backward(Uc, Tc, idc)
         ctx.scale, ctx.padding_idx, ctx.dtypes = float(scale), int(padding_idx), (U.dtype, table.dtype)
         return S
@@ -133,12 +126,9 @@ class _GatherDot(torch.autograd.Function):
         dU = torch.empty(M, d, dtype=torch.float32, device=dev) if need_u else None
         dT = torch.zeros(Tc.shape[0], d, dtype=torch.float32, device=dev) if need_t else None
         ws, n = _ws(dev, L.OP_SCATTER_ADD, 0, 0, d, nnz=M * K)
-        L.check(
-            L.lib().rb_gather_dot_bwd(L.ptr(Uc), L.ptr(Tc), L.ptr(idc), L.ptr(G.float().contiguous()), ctx.scale, L.ptr(dU),
+        L.call(dev, "rb_gather_dot_bwd", L.ptr(Uc), L.ptr(Tc), L.ptr(idc), L.ptr(G.float().contiguous()), ctx.scale, L.ptr(dU),
                                       L.ptr(dT), M, K, Tc.shape[0], d, L.dtype_code(Uc), ctx.padding_idx, L.ptr(ws), n,
-                                      L.stream_ptr(dev)),
-            "rb_gather_dot_bwd",
-        )
+                                      L.stream_ptr(dev))
         return (dU.to(ctx.dtypes[0]) if need_u else None, dT.to(ctx.dtypes[1]) if need_t else None, None, None, None)
 
 
@@ -169,11 +159,8 @@ def spmm_raw(A: torch.Tensor, X: torch.Tensor, acc: Optional[torch.Tensor] = Non
     Y = torch.empty(shape[0], d, dtype=torch.float32, device=dev) if want_y else None
     if val.numel() == 0:   # empty matrix: nothing to launch
         return Y.zero_() if want_y else None
-    L.check(
-        L.lib().rb_spmm_csr(L.ptr(crow), L.ptr(col), L.ptr(val), L.ptr(Xc), L.ptr(Y), L.ptr(acc), float(beta), shape[0], shape[1],
-                            d, L.stream_ptr(dev)),
-        "rb_spmm_csr",
-    )
+    L.call(dev, "rb_spmm_csr", L.ptr(crow), L.ptr(col), L.ptr(val), L.ptr(Xc), L.ptr(Y), L.ptr(acc), float(beta), shape[0], shape[1],
+                            d, L.stream_ptr(dev))
     return Y
 
 
@@ -218,11 +205,8 @@ def normalize_rows(x: torch.Tensor, out_dtype: Optional[torch.dtype] = None, eps
     n, d = xc.shape
     out = torch.empty(n, d, dtype=out_dtype, device=dev)
     inv = torch.empty(n, dtype=torch.float32, device=dev) if return_inv_norm else None
-    L.check(
-        L.lib().rb_normalize_rows(L.ptr(xc), L.ptr(out), L.ptr(inv), n, d, L.dtype_code(xc), L.dtype_code(out),
-                                  float(eps), L.stream_ptr(dev)),
-        "rb_normalize_rows",
-    )
+    L.call(dev, "rb_normalize_rows", L.ptr(xc), L.ptr(out), L.ptr(inv), n, d, L.dtype_code(xc), L.dtype_code(out),
+                                  float(eps), L.stream_ptr(dev))
     return (out, inv) if return_inv_norm else out
 
 
@@ -239,11 +223,8 @@ def score_dense(U: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] =
     b = None if bias is None else bias.detach().float().contiguous()
     S = torch.empty(M, N, dtype=torch.float32, device=dev)
     ws, n = _ws(dev, L.OP_SCORE_DENSE, M, N, d, mode=mode)
-    L.check(
-        L.lib().rb_score_dense(L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(S), M, N, d,
-                               L.dtype_code(Uc), mode, L.ptr(ws), n, L.stream_ptr(dev)),
-        "rb_score_dense",
-    )
+    L.call(dev, "rb_score_dense", L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(S), M, N, d,
+                               L.dtype_code(Uc), mode, L.ptr(ws), n, L.stream_ptr(dev))
     return S
 
 
@@ -270,12 +251,9 @@ def ce_rowstats(U, W, labels, bias=None, scale: float = 1.0, label_base: int = 0
     out = torch.empty(3, M, dtype=torch.float32, device=dev)
     du = torch.empty(M, d, dtype=torch.float32, device=dev) if want_dU else None
     ws, n = _ws(dev, L.OP_CE_FWD, M, N, d, mode=mode)
-    L.check(
-        L.lib().rb_ce_fwd(L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(labels.contiguous()), label_base,
+    L.call(dev, "rb_ce_fwd", L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(labels.contiguous()), label_base,
                           M, N, d, L.dtype_code(Uc), mode, L.ptr(out[0]), L.ptr(out[1]), L.ptr(out[2]), L.ptr(du),
-                          L.ptr(ws), n, L.stream_ptr(dev)),
-        "rb_ce_fwd",
-    )
+                          L.ptr(ws), n, L.stream_ptr(dev))
     if want_dU:
         return out[0], out[1], out[2], du
     return out[0], out[1], out[2]
@@ -291,13 +269,10 @@ def ce_du_finish(du_unnorm, row_max, lse, W, labels, grad_scale: float, scale: f
     Wc = Wc.contiguous()
     M, d = du_unnorm.shape
     dU = torch.empty(M, d, dtype=torch.float32, device=dev)
-    L.check(
-        L.lib().rb_ce_du_finish(L.ptr(du_unnorm), L.ptr(row_max), L.ptr(lse.float().contiguous()), L.ptr(Wc),
+    L.call(dev, "rb_ce_du_finish", L.ptr(du_unnorm), L.ptr(row_max), L.ptr(lse.float().contiguous()), L.ptr(Wc),
                                 L.ptr(labels.contiguous()), label_base, float(scale), float(grad_scale),
                                 L.ptr(grad_scale_dev), M, Wc.shape[0], d, L.dtype_code(Wc), L.ptr(dU),
-                                L.stream_ptr(dev)),
-        "rb_ce_du_finish",
-    )
+                                L.stream_ptr(dev))
     return dU
 
 
@@ -321,28 +296,19 @@ def ce_backward(U, W, labels, lse, grad_scale: float, bias=None, scale: float = 
     ws, n = _ws(dev, L.OP_CE_BWD, M, N, d, mode=mode)
     if need_dW and dw_dtype == torch.bfloat16 and mode == L.MODE_BF16:
         if need_dU:   # dU alone through the generic entry, dW (+ dbias) through the bf16-output pass
-            L.check(
-                L.lib().rb_ce_bwd(L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(labels.contiguous()), label_base,
+            L.call(dev, "rb_ce_bwd", L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(labels.contiguous()), label_base,
                                   L.ptr(lse.float().contiguous()), float(grad_scale), L.ptr(grad_scale_dev), M, N, d,
-                                  L.dtype_code(Uc), mode, L.ptr(dU), None, None, L.ptr(ws), n, L.stream_ptr(dev)),
-                "rb_ce_bwd",
-            )
+                                  L.dtype_code(Uc), mode, L.ptr(dU), None, None, L.ptr(ws), n, L.stream_ptr(dev))
         dWb = torch.empty(N, d, dtype=torch.bfloat16, device=dev)
-        L.check(
-            L.lib().rb_ce_bwd_dw_bf16(L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(labels.contiguous()), label_base,
+        L.call(dev, "rb_ce_bwd_dw_bf16", L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(labels.contiguous()), label_base,
                                       L.ptr(lse.float().contiguous()), float(grad_scale), L.ptr(grad_scale_dev), M, N, d,
-                                      L.ptr(dWb), L.ptr(db), L.ptr(ws), n, L.stream_ptr(dev)),
-            "rb_ce_bwd_dw_bf16",
-        )
+                                      L.ptr(dWb), L.ptr(db), L.ptr(ws), n, L.stream_ptr(dev))
         return dU, dWb, db
     dW = torch.empty(N, d, dtype=torch.float32, device=dev) if (need_dW or need_dbias) else None
-    L.check(
-        L.lib().rb_ce_bwd(L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(labels.contiguous()), label_base,
+    L.call(dev, "rb_ce_bwd", L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(labels.contiguous()), label_base,
                           L.ptr(lse.float().contiguous()), float(grad_scale), L.ptr(grad_scale_dev), M, N, d,
                           L.dtype_code(Uc), mode,
-                          L.ptr(dU), L.ptr(dW), L.ptr(db), L.ptr(ws), n, L.stream_ptr(dev)),
-        "rb_ce_bwd",
-    )
+                          L.ptr(dU), L.ptr(dW), L.ptr(db), L.ptr(ws), n, L.stream_ptr(dev))
     return dU, (dW if need_dW else None), db
 
 
@@ -402,6 +368,11 @@ def fused_ce(U: torch.Tensor, W: torch.Tensor, labels: torch.Tensor, bias: Optio
     """Drop-in for ``self.criterion(torch.einsum("MD,ND->MN", U, W), labels)`` with
     ``criterion = CrossEntropy4Logits(reduction="mean")`` (SASRec/main.py:126,217-219): same value,
     same gradients, no (M,N) logit matrix in forward or backward."""
+    if U.shape[0] == 0:
+        # no query rows (e.g. a BERT4Rec step whose random mask selected nothing): F.cross_entropy returns
+        # NaN for "mean" and 0 for "sum", with zero gradients -- reproduced without a launch
+        zero = (U.sum() + W.sum() * 0 + (bias.sum() * 0 if bias is not None else 0)).float()
+        return zero / 0 if reduction == "mean" else zero
     return _FusedCE.apply(U, W, labels, bias, float(scale), precision, reduction)
 
 
@@ -429,15 +400,14 @@ def topk_eval(U: torch.Tensor, W: torch.Tensor, K: int, seen_crow: Optional[torc
         nnz = seen_col.numel()
         if nnz == 0:  # nothing to mask: same as no seen lists
             seen_crow = seen_col = None
+        else:
+            seen_crow, seen_col = seen_crow.contiguous(), seen_col.contiguous()
     vals = torch.empty(B, K, dtype=torch.float32, device=dev)
     ids = torch.empty(B, K, dtype=torch.int32, device=dev)
     ws, n = _ws(dev, L.OP_TOPK_EVAL, B, N, d, K=K, mode=mode, nnz=nnz)
-    L.check(
-        L.lib().rb_topk_eval(L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(seen_crow), L.ptr(seen_col), nnz,
+    L.call(dev, "rb_topk_eval", L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(seen_crow), L.ptr(seen_col), nnz,
                              id_base, B, N, d, L.dtype_code(Uc), mode, K, L.ptr(vals), L.ptr(ids), L.ptr(ws), n,
-                             L.stream_ptr(dev)),
-        "rb_topk_eval",
-    )
+                             L.stream_ptr(dev))
     return vals, ids
 
 
@@ -447,9 +417,6 @@ def topk_merge(vals: torch.Tensor, ids: torch.Tensor) -> Tuple[torch.Tensor, tor
     R, B, K = vals.shape
     ov = torch.empty(B, K, dtype=torch.float32, device=dev)
     oi = torch.empty(B, K, dtype=torch.int32, device=dev)
-    L.check(
-        L.lib().rb_topk_merge(L.ptr(vals.float().contiguous()), L.ptr(ids.int().contiguous()), R, B, K,
-                              L.ptr(ov), L.ptr(oi), L.stream_ptr(dev)),
-        "rb_topk_merge",
-    )
+    L.call(dev, "rb_topk_merge", L.ptr(vals.float().contiguous()), L.ptr(ids.int().contiguous()), R, B, K,
+                              L.ptr(ov), L.ptr(oi), L.stream_ptr(dev))
     return ov, oi

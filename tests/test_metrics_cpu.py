@@ -9,6 +9,21 @@ from recboard_b200 import sharded, synth
 MONS = ["HITRATE@1", "HITRATE@5", "HITRATE@10", "NDCG@5", "NDCG@10", "RECALL@10", "PRECISION@5", "MRR@10"]
 
 
+def _batch_metrics(ids, tcrow, tcol, n_items, mons):
+    """The product's host-side reduction (metrics_from_hits) fed with the oracle's hit matrix: the product's own
+    hit matrix is a kernel (rb_topk_hits) and exists on a GPU only."""
+    n_t = (tcrow[1:] - tcrow[:-1]).float()
+    return MX.metrics_from_hits(orc.hits_from_topk(ids, tcrow, tcol, n_items), n_t, mons)
+
+
+def test_hit_matrix_has_no_cpu_path():
+    import pytest
+    ids = torch.zeros(2, 3, dtype=torch.int32)
+    tcrow, tcol = MX.lists_to_csr([[0], [1]])
+    with pytest.raises(RuntimeError):
+        MX.hits_from_topk(ids, tcrow, tcol, 5)
+
+
 def _case(seed, B=33, N=257, multi=False):
     g = torch.Generator().manual_seed(seed)
     scores = torch.randn(B, N, generator=g)
@@ -22,14 +37,14 @@ def test_metrics_from_topk_bit_identical_to_dense_oracle():
         scores, (crow, col), (tcrow, tcol) = _case(seed, multi=multi)
         dense = orc.evaluate_batch(scores, crow, col, tcrow, tcol, MONS)
         _, ids = orc.topk_sorted(orc.mask_seen(scores, crow, col), 10)
-        got = MX.batch_metrics(ids.int(), tcrow, tcol, scores.shape[1], MONS, exact=True)
+        got = _batch_metrics(ids.int(), tcrow, tcol, scores.shape[1], MONS)
         assert got == dense  # bit-identical floats
 
 
 def test_missing_entries_never_hit():
     ids = torch.tensor([[3, -1, -1]], dtype=torch.int32)
     tcrow, tcol = MX.lists_to_csr([[0]])
-    assert MX.batch_metrics(ids, tcrow, tcol, 5, ["HITRATE@3"])["HITRATE@3"] == 0.0
+    assert _batch_metrics(ids, tcrow, tcol, 5, ["HITRATE@3"])["HITRATE@3"] == 0.0
 
 
 def test_average_meter_weighting():
@@ -79,12 +94,12 @@ def test_synth_shapes_and_invariants():
     assert s.shape == (16, 50) and (s[:, -1] > 0).all() and s.max() <= 1000
 
 
-def test_device_eval_split_matches_per_batch_csr():
+def test_device_eval_split_matches_per_batch_csr(monkeypatch):
     """SURVEY 8f-4 host logic: the split-wide CSR cut per batch equals the CSR rebuilt from that batch's lists,
-    and the sweep over it reproduces the oracle's bsz-weighted metrics."""
-    import torch
-    from oracle import reference_path as orc
-    from recboard_b200 import evaluate as EV, metrics as MX
+    and the sweep over it reproduces the oracle's bsz-weighted metrics (the hit-matrix kernel is a GPU-only
+    product path: the oracle's dense-target gather stands in for it here)."""
+    from recboard_b200 import evaluate as EV
+    monkeypatch.setattr(MX, "hits_from_topk", orc.hits_from_topk)
     g = torch.Generator().manual_seed(11)
     R, N, K = 37, 200, 10
     seen = [torch.randperm(N, generator=g)[: int(torch.randint(0, 9, (1,), generator=g))].tolist() for _ in range(R)]

@@ -35,7 +35,7 @@ def _worker(rank, world, port, q):
     v, i = orc.topk_sorted(S, K)
     av, ai = sharded.allgather_topk(v, (i + a).int())
     mv, mi = orc.merge_topk([(av[r], ai[r]) for r in range(world)], K)
-    q.put((rank, float(loss), mv, mi))
+    q.put((rank, float(loss), mv.numpy(), mi.numpy()))   # plain arrays: nothing fd-shared outlives the worker
     dist.destroy_process_group()
 
 
@@ -57,6 +57,7 @@ def test_two_rank_merges_match_unsharded():
     ref_loss = orc.ce_loss(U, W, labels)
     rv, ri = orc.topk_sorted(orc.score_dense(U, W), K)
     for rank, loss, mv, mi in outs:
+        mv, mi = torch.from_numpy(mv), torch.from_numpy(mi)
         assert abs(loss - float(ref_loss)) < 1e-5
         assert torch.equal(mi, ri) and torch.equal(mv, rv)
 
@@ -122,7 +123,7 @@ def _autograd_worker(rank, world, port, q):
     (loss * 3.0).backward()
     crow, col = orc.lists_to_csr(seen)
     v, i = sharded.sharded_topk(U, W[a:b], K, a, crow, col, bias_shard=bias[a:b], scale=0.8)
-    q.put((rank, a, b, float(loss), Us.grad, Ws.grad, bs.grad, v, i))
+    q.put((rank, a, b, float(loss), *(t.detach().numpy() for t in (Us.grad, Ws.grad, bs.grad, v, i))))
     dist.destroy_process_group()
 
 
@@ -142,6 +143,7 @@ def test_two_rank_sharded_autograd_and_topk():
     crow, col = orc.lists_to_csr(seen)
     rv, ri = orc.topk_sorted(orc.mask_seen(orc.score_dense(U, W, bias, 0.8), crow, col), K)
     for rank, a, b, loss, dU, dW, db, v, i in outs:
+        dU, dW, db, v, i = (torch.from_numpy(x) for x in (dU, dW, db, v, i))
         assert abs(loss - float(ref_loss)) < 1e-5
         assert torch.allclose(dU, rdU, rtol=1e-4, atol=1e-6)          # the all-reduced full gradient on every rank
         assert torch.allclose(dW, rdW[a:b], rtol=1e-4, atol=1e-6)     # the local shard, never communicated
