@@ -12,6 +12,7 @@
 #include "pair.cuh"
 #include "simt.cuh"
 #include "f32grad.cuh"
+#include "launch.cuh"
 
 using namespace rb;
 
@@ -102,7 +103,7 @@ static int make_tmap(CUtensorMap* m, const void* base, bool bf16, long long rows
 }
 
 // --------------------------------------------------------------------------- planning
-constexpr int BN = 128;  // streamed tile rows
+using rb::BN;   // streamed tile rows (launch.cuh)
 
 struct Plan { int n_stat_tiles, n_strm_tiles, n_splits, grid; };
 
@@ -163,72 +164,18 @@ static int check_common(const void* U, const void* W, long long M, long long N, 
   return 0;
 }
 
-// ------------------------------------------------------------------- sweep dispatch
-template <class C>
-static int launch_sweep_t(const CUtensorMap& ts, const CUtensorMap& ty, const SweepArgs& a, int grid, cudaStream_t st) {
-  RB_CUDA(cudaFuncSetAttribute(sweep_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-  sweep_kernel<C><<<grid, SWEEP_THREADS, C::SMEM_BYTES, st>>>(ts, ty, a);
-  RB_LAUNCH_CHECK("sweep_kernel");
-  return 0;
-}
+// ------------------------------------------------------------------- kernel dispatch
+// The tcgen05 kernel templates are instantiated in their own translation units (inst_*.cu, one per epilogue /
+// pass, compiled in parallel by build.py); this file keeps the host-side planning and the SIMT kernels.
+int rb::host_fail(int code, const char* msg) { return fail(code, "%s", msg); }
+int rb::host_cuda_fail(cudaError_t e, const char* what) { return cuda_fail(e, what); }
+void rb::count_launch() { ++g_launches; }
 
 // Stationary tiles per CTA: two (256 rows) whenever there is a second tile to fill -- halves the L2->SM
 // traffic of a sweep (see sweep.cuh).
 static int sweep_xt(int mode, int d, long long n_stat) {
   if (mode != RB_MODE_BF16 && d > 64) return 1;   // fp32x3 at d = 128: one [hi|lo] stationary tile is already 128 KB
   return n_stat > 128 ? 2 : 1;
-}
-
-// NS = pipeline stages (whole 32 KB tiles up to two K-chunks, single 16 KB chunks beyond: SweepCfg::SC),
-// chosen so that SMEM stays under 227 KB next to the stationary tile(s)
-template <int EPI, bool ROWS>
-static int launch_sweep(int mode, int kc, const CUtensorMap& ts, const CUtensorMap& ty, const SweepArgs& a, int grid,
-                        cudaStream_t st, int xt = 1) {
-  if (xt == 2) {
-    if constexpr (EPI != EPI_DENSE) {
-      if (mode == RB_MODE_BF16) {
-        if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 1, BN, 10, ROWS, 2>>(ts, ty, a, grid, st);
-        if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 2, BN, 4, ROWS, 2>>(ts, ty, a, grid, st);
-        if (kc <= 4) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 4, BN, 5, ROWS, 2>>(ts, ty, a, grid, st);
-      } else {
-        if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 1, BN, 4, ROWS, 2>>(ts, ty, a, grid, st);
-        if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 2, BN, 5, ROWS, 2>>(ts, ty, a, grid, st);
-      }
-    }
-    return fail(RB_E_UNSUPPORTED, "unsupported feature width for two stationary tiles (mode %d, kc=%d)", mode, kc);
-  }
-  if (mode == RB_MODE_BF16) {
-    if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 1, BN, 10, ROWS>>(ts, ty, a, grid, st);
-    if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 2, BN, 5, ROWS>>(ts, ty, a, grid, st);
-    if (kc <= 4) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 4, BN, 8, ROWS>>(ts, ty, a, grid, st);
-  } else {
-    if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 1, BN, 5, ROWS>>(ts, ty, a, grid, st);
-    if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 2, BN, 8, ROWS>>(ts, ty, a, grid, st);
-    if (kc == 4) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 4, BN, 5, ROWS>>(ts, ty, a, grid, st);
-  }
-  return fail(RB_E_UNSUPPORTED, "unsupported feature width for mode %d (kc=%d)", mode, kc);
-}
-
-// ------------------------------------------------------------------- pair dispatch
-template <class C>
-static int launch_pair_t(const CUtensorMap& ts, const CUtensorMap& ty, const PairArgs& a, int grid, cudaStream_t st) {
-  RB_CUDA(cudaFuncSetAttribute(pair_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-  pair_kernel<C><<<grid, PAIR_THREADS, C::SMEM_BYTES, st>>>(ts, ty, a);
-  RB_LAUNCH_CHECK("pair_kernel");
-  return 0;
-}
-template <int PASS>
-static int launch_pair(int kc, bool bias, const CUtensorMap& ts, const CUtensorMap& ty, const PairArgs& a, int grid,
-                       cudaStream_t st) {
-  if (kc == 1) {
-    if (bias) return launch_pair_t<PairCfg<PASS, 1, 6, true>>(ts, ty, a, grid, st);
-    return launch_pair_t<PairCfg<PASS, 1, 6, false>>(ts, ty, a, grid, st);
-  }
-  if (kc == 2) {
-    if (bias) return launch_pair_t<PairCfg<PASS, 2, 4, true>>(ts, ty, a, grid, st);
-    return launch_pair_t<PairCfg<PASS, 2, 4, false>>(ts, ty, a, grid, st);
-  }
-  return fail(RB_E_UNSUPPORTED, "the fused CE passes support d <= 128");
 }
 static bool pair_ok(int mode, int d, float scale) { return mode == RB_MODE_BF16 && d <= 128 && scale > 0.f; }
 
@@ -445,7 +392,7 @@ extern "C" int rb_score_dense(const void* U, const void* W, const float* bias, f
   SweepArgs a{};
   a.n_stat = (int)M; a.n_strm = (int)N; a.n_stat_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
   a.n_splits = p.n_splits; a.d = d; a.scale = scale; a.bias = bias; a.out = S; a.ld_out = N;
-  return launch_sweep<EPI_DENSE, true>(mode, kc_for(d, mode), ts, ty, a, p.grid, st);
+  return launch_sweep_dense(mode, kc_for(d, mode), ts, ty, a, p.grid, st);
 }
 
 static size_t pair_fwd_ws(long long M, long long N, int d, int sms) {
@@ -479,7 +426,7 @@ static int ce_fwd_pair(const DevInfo& dv, const void* U, const void* W, const fl
   a.n_stat = (int)M; a.n_strm = (int)N; a.n_pair_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
   a.n_splits = p.n_splits; a.d = d; a.stat_pad = (int)stat_pad; a.scale = scale; a.aux = bias2;
   a.part_m2 = pm2; a.part_l = pl; a.acc_out = pacc;
-  if (int r = launch_pair<PASS_FWD>(kc_for(d, RB_MODE_BF16), bias != nullptr, ts, ty, a, p.grid, st)) return r;
+  if (int r = launch_pair_fwd(kc_for(d, RB_MODE_BF16), bias != nullptr, ts, ty, a, p.grid, st)) return r;
   const int grid = (int)((M * 32 + 255) / 256);
   ce_fwd_finish_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
       pm2, pl, pacc, p.n_splits, stat_pad, (int)M, d, static_cast<const __nv_bfloat16*>(U),
@@ -523,7 +470,7 @@ extern "C" int rb_ce_fwd(const void* U, const void* W, const float* bias, float 
   a.n_stat = (int)M; a.n_strm = (int)N; a.n_stat_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
   a.n_splits = p.n_splits; a.d = d; a.scale = scale; a.bias = bias; a.labels = lab32;
   a.part_m2 = pm2; a.part_l = pl; a.part_ll = pll;
-  if (int r = launch_sweep<EPI_LSE, true>(mode, kc_for(d, mode), ts, ty, a, p.grid, st, xt)) return r;
+  if (int r = launch_sweep_lse(mode, kc_for(d, mode), ts, ty, a, p.grid, st, xt)) return r;
   lse_merge_kernel<<<(int)((M + 255) / 256), 256, 0, st>>>(pm2, pl, pll, p.n_splits, m_pad, (int)M, row_max, row_sumexp, label_logit);
   RB_LAUNCH_CHECK("lse_merge_kernel");
   return 0;
@@ -594,7 +541,7 @@ static int ce_bwd_dw_pair(const DevInfo& dv, const void* U, const void* W, const
   a.n_splits = p.n_splits; a.d = d; a.stat_pad = (int)n_pad; a.scale = scale; a.bias2_stat = bias2; a.aux = lse2;
   a.gscale = grad_scale * scale; a.rscale = grad_scale; a.gscale_dev = grad_scale_dev; a.acc_out = part; a.rowsum_out = rs_part;
   if (direct_bf16) { a.out_bf16 = dW_bf16; a.slot_of_row = first_of; a.side = side; }
-  if (int r = launch_pair<PASS_DW>(kc_for(d, RB_MODE_BF16), bias_cfg, ts, ty, a, p.grid, st)) return r;
+  if (int r = launch_pair_dw(kc_for(d, RB_MODE_BF16), bias_cfg, ts, ty, a, p.grid, st)) return r;
   if (p.n_splits > 1) {
     const long long n = N * d;
     partial_sum_kernel<<<(int)std::min<long long>((n + 255) / 256, dv.sms * 8), 256, 0, st>>>(part, p.n_splits, n, dW);
@@ -861,14 +808,14 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
   a.n_splits = p.n_splits; a.d = d; a.scale = scale; a.bias = bias;
   a.seen_crow = crow32; a.seen_col = col32; a.tile_max = tmax;
   a.tau = tau; a.tile_flag = flag; a.cand = cand; a.cand_cnt = cand_cnt; a.cand_cap = candcap; a.n_sub = n_sub;
-  if (int r = launch_sweep<EPI_TOPK, true>(mode, kc_for(d, mode), ts, ty, a, p.grid, st, xt)) return r;
+  if (int r = launch_sweep_topk(mode, kc_for(d, mode), ts, ty, a, p.grid, st, xt)) return r;
   const int grid_w = static_cast<int>((B * 32 + 127) / 128);
   if (K <= 128) tilemax_select_kernel<4><<<grid_w, 128, 0, st>>>(tmax, p.n_strm_tiles, B, K, tau);
   else tilemax_select_kernel<8><<<grid_w, 128, 0, st>>>(tmax, p.n_strm_tiles, B, K, tau);
   RB_LAUNCH_CHECK("tilemax_select_kernel");
   tile_flag_kernel<<<dim3((p.n_strm_tiles + 255) / 256, n_tiles128 * 4), 256, 0, st>>>(tmax, tau, p.n_strm_tiles, B, flag);
   RB_LAUNCH_CHECK("tile_flag_kernel");
-  if (int r = launch_sweep<EPI_CAND, true>(mode, kc_for(d, mode), ts, ty, a, p.grid, st, xt)) return r;
+  if (int r = launch_sweep_cand(mode, kc_for(d, mode), ts, ty, a, p.grid, st, xt)) return r;
   const int id_add = static_cast<int>(id_base);
   const int grid_r = static_cast<int>((B + 3) / 4);
   if (dtype == RB_DTYPE_BF16) {

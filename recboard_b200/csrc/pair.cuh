@@ -102,7 +102,7 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
 }
 
 // acc[lane][col0 .. col0+ncols) *= f   (TMEM round trip; rare: only when a row reference moves)
-__device__ __noinline__ void pair_rescale_acc(uint32_t t_acc, int ncols, float f) {
+static __device__ __noinline__ void pair_rescale_acc(uint32_t t_acc, int ncols, float f) {
   for (int c = 0; c < ncols; c += 32) {
     uint32_t v[32];
     tmem_ld32(t_acc + c, v);

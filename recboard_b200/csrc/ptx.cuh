@@ -3,6 +3,7 @@
 // the UMMA descriptors follow the PTX ISA tcgen05 chapter.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -58,7 +59,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __noinline__ void mbar_watchdog_trap(uint32_t bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_watchdog_trap(uint32_t bar, uint32_t parity) {
   printf("rb: mbarrier watchdog block %d thread %d bar@%u parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
   __trap();
 }
