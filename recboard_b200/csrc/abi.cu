@@ -738,20 +738,26 @@ static int ce_bwd_impl(const void* U, const void* W, const float* bias, float sc
 }
 
 // ========================================================================= top-K eval
-// Exact masked top-K in two tensor-core sweeps (no dense (B,N), no per-element selection work):
-//   1. sweep<EPI_TOPK>: masked maximum of every (row, 128-item tile)
-//   2. tilemax_select:  tau[row] = K-th largest tile maximum  (>= K unseen items score >= tau, so every
-//                       top-K member does too)
-//   3. tile_flag:       which (32-row group, tile) pairs can hold a candidate
-//   4. sweep<EPI_CAND>: recompute the scores, append every aligned group of 8 items whose maximum reaches tau
-//                       to the (row, split, warpgroup) sub-list (about K groups per row in total);
-//                       flagged-off tiles are skipped
-//   5. topk_from_groups: exact fp32 re-scoring of the hit groups, drop seen items, sort, keep K.
-//   6. rows with an overflowed sub-list (massive ties / tiny catalogs): exact SIMT re-scoring of every
-//      tile whose maximum reaches tau or is unknown (topk_refine).
-// capacity of one candidate sub-list: ~8x the expected share of a sub-list, a power of two in [32, 512]
-static int topk_candcap(int K, int n_sub) {
-  const int want = (8 * K + n_sub - 1) / n_sub;
+// Exact masked top-K in ONE tensor-core sweep over the catalog plus a short seeding sweep (no dense (B,N), no
+// (B, N/128) tile-maximum matrix, no per-element selection work):
+//   1. sweep<EPI_TOPK> over a PREFIX of the catalog (max(4K tiles, 2.5 % of the tiles); the whole catalog when it
+//      is that small): masked maximum of every (row, 128-item tile)
+//   2. tilemax_select:  per row the ladder tau0 = K-th largest clean tile maximum of the prefix (>= K unseen items
+//      reach it, so every top-K member does too) and the checkpoints c_k = (K >> k)-th largest
+//   3. sweep<EPI_CAND> over the whole catalog: every aligned group of 8 items whose maximum reaches the row's
+//      running threshold is appended to the (row, split, warpgroup) sub-list as (maximum, group id); the threshold
+//      climbs the ladder as the shared counters show >= K unseen items above a checkpoint (sweep.cuh)
+//   4. topk_from_cands: cut at the K-th largest clean group maximum, exact fp32 re-scoring of the ~K groups left,
+//      drop seen items, sort, keep K
+//   5. rows with an overflowed sub-list (massive ties / catalogs too small for a threshold): exact scan of the row's
+//      whole catalog (topk_refine).
+// capacity of one candidate sub-list: ~6x the expected share of a sub-list (K (3 + log2(N/prefix)) candidates per
+// row in total), a power of two in [32, 512]
+static int topk_prefix_tiles(int n_tiles, int K) { return std::min(n_tiles, std::max(4 * K, (n_tiles + 39) / 40)); }
+static int topk_candcap(int K, int n_sub, int n_tiles, int prefix_tiles) {
+  int phases = 3;
+  for (long long t = prefix_tiles; t < n_tiles; t *= 2) ++phases;
+  const int want = (6 * K * phases + n_sub - 1) / n_sub;
   int c = 32;
   while (c < want && c < 512) c *= 2;
   return c;
@@ -777,9 +783,11 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
   if (int r = stage_operand(W, N, d, mode, b, ow, st)) return r;
   const int xt = sweep_xt(mode, d, B);
   Plan p = make_plan(B, N, dv.sms, 1 << 20, 8, 128 * xt);
+  const int n0_tiles = topk_prefix_tiles(p.n_strm_tiles, K);
+  const long long n0 = std::min<long long>(N, 1ll * n0_tiles * BN);
+  Plan pp = make_plan(B, n0, dv.sms, 1 << 20, 8, 128 * xt);   // the seeding sweep over the prefix
   const int n_sub = (xt == 2) ? p.n_splits : 2 * p.n_splits;
-  const int n_tiles128 = p.n_stat_tiles * xt;   // 128-row stationary tiles the sweeps touch
-  const int candcap = topk_candcap(K, n_sub);
+  const int candcap = topk_candcap(K, n_sub, p.n_strm_tiles, n0_tiles);
   int* crow32 = nullptr; int* col32 = nullptr;
   long long nnz = 0;
   if (seen_crow) {
@@ -788,12 +796,11 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
     crow32 = b.take<int>(B + 1);
     col32 = b.take<int>(std::max<long long>(nnz, 1));
   }
-  float* tmax = b.take<float>(static_cast<size_t>(B) * p.n_strm_tiles);
-  float* tau = b.take<float>(B);
+  float* tmax = b.take<float>(static_cast<size_t>(B) * n0_tiles);
+  RowLadder* ladder = b.take<RowLadder>(B);
   int* cand_cnt = b.take<int>(static_cast<size_t>(B) * n_sub);
   int* overflow = b.take<int>(B);
-  unsigned char* flag = b.take<unsigned char>(static_cast<size_t>(n_tiles128) * 4 * p.n_strm_tiles);
-  int* cand = b.take<int>(static_cast<size_t>(B) * n_sub * candcap);
+  uint2* cand = b.take<uint2>(static_cast<size_t>(B) * n_sub * candcap);
   if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
   if (seen_crow) {
     const long long n = std::max<long long>(B + 1, nnz);
@@ -804,34 +811,37 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
   if (int r = make_tmap(&ts, ou.ptr, ou.bf16, B, ou.cols, 128)) return r;
   if (int r = make_tmap(&ty, ow.ptr, ow.bf16, N, ow.cols, BN)) return r;
   SweepArgs a{};
-  a.n_stat = (int)B; a.n_strm = (int)N; a.n_stat_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
-  a.n_splits = p.n_splits; a.d = d; a.scale = scale; a.bias = bias;
+  a.n_stat = (int)B; a.d = d; a.scale = scale; a.bias = bias;
   a.seen_crow = crow32; a.seen_col = col32; a.tile_max = tmax;
-  a.tau = tau; a.tile_flag = flag; a.cand = cand; a.cand_cnt = cand_cnt; a.cand_cap = candcap; a.n_sub = n_sub;
-  if (int r = launch_sweep_topk(mode, kc_for(d, mode), ts, ty, a, p.grid, st, xt)) return r;
+  a.ladder = ladder; a.k_need = K; a.cand = cand; a.cand_cnt = cand_cnt; a.cand_cap = candcap; a.n_sub = n_sub;
+  // 1. seeding sweep over the prefix
+  a.n_strm = (int)n0; a.n_stat_tiles = pp.n_stat_tiles; a.n_strm_tiles = pp.n_strm_tiles; a.n_splits = pp.n_splits;
+  if (int r = launch_sweep_topk(mode, kc_for(d, mode), ts, ty, a, pp.grid, st, xt)) return r;
+  // 2. the ladder
   const int grid_w = static_cast<int>((B * 32 + 127) / 128);
-  if (K <= 128) tilemax_select_kernel<4><<<grid_w, 128, 0, st>>>(tmax, p.n_strm_tiles, B, K, tau);
-  else tilemax_select_kernel<8><<<grid_w, 128, 0, st>>>(tmax, p.n_strm_tiles, B, K, tau);
+  if (K <= 128) tilemax_select_kernel<4><<<grid_w, 128, 0, st>>>(tmax, n0_tiles, B, K, ladder);
+  else tilemax_select_kernel<8><<<grid_w, 128, 0, st>>>(tmax, n0_tiles, B, K, ladder);
   RB_LAUNCH_CHECK("tilemax_select_kernel");
-  tile_flag_kernel<<<dim3((p.n_strm_tiles + 255) / 256, n_tiles128 * 4), 256, 0, st>>>(tmax, tau, p.n_strm_tiles, B, flag);
-  RB_LAUNCH_CHECK("tile_flag_kernel");
+  // 3. the candidate sweep over the whole catalog
+  a.n_strm = (int)N; a.n_stat_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles; a.n_splits = p.n_splits;
   if (int r = launch_sweep_cand(mode, kc_for(d, mode), ts, ty, a, p.grid, st, xt)) return r;
+  // 4. + 5. finish
   const int id_add = static_cast<int>(id_base);
   const int grid_r = static_cast<int>((B + 3) / 4);
   if (dtype == RB_DTYPE_BF16) {
     const __nv_bfloat16* Ub = static_cast<const __nv_bfloat16*>(U); const __nv_bfloat16* Wb = static_cast<const __nv_bfloat16*>(W);
-    if (K <= 128) topk_from_groups_kernel<__nv_bfloat16, 4><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, cand, cand_cnt, n_sub, candcap, crow32, col32, K, id_add, top_vals, top_ids, overflow);
-    else topk_from_groups_kernel<__nv_bfloat16, 8><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, cand, cand_cnt, n_sub, candcap, crow32, col32, K, id_add, top_vals, top_ids, overflow);
-    RB_LAUNCH_CHECK("topk_from_groups_kernel");
-    if (K <= 128) topk_refine_kernel<__nv_bfloat16, 4><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, crow32, col32, tmax, tau, K, id_add, top_vals, top_ids, overflow);
-    else topk_refine_kernel<__nv_bfloat16, 8><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, crow32, col32, tmax, tau, K, id_add, top_vals, top_ids, overflow);
+    if (K <= 128) topk_from_cands_kernel<__nv_bfloat16, 4><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, cand, cand_cnt, n_sub, candcap, crow32, col32, K, id_add, top_vals, top_ids, overflow);
+    else topk_from_cands_kernel<__nv_bfloat16, 8><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, cand, cand_cnt, n_sub, candcap, crow32, col32, K, id_add, top_vals, top_ids, overflow);
+    RB_LAUNCH_CHECK("topk_from_cands_kernel");
+    if (K <= 128) topk_refine_kernel<__nv_bfloat16, 4><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, crow32, col32, K, id_add, top_vals, top_ids, overflow);
+    else topk_refine_kernel<__nv_bfloat16, 8><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, crow32, col32, K, id_add, top_vals, top_ids, overflow);
   } else {
     const float* Uf = static_cast<const float*>(U); const float* Wf = static_cast<const float*>(W);
-    if (K <= 128) topk_from_groups_kernel<float, 4><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, cand, cand_cnt, n_sub, candcap, crow32, col32, K, id_add, top_vals, top_ids, overflow);
-    else topk_from_groups_kernel<float, 8><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, cand, cand_cnt, n_sub, candcap, crow32, col32, K, id_add, top_vals, top_ids, overflow);
-    RB_LAUNCH_CHECK("topk_from_groups_kernel");
-    if (K <= 128) topk_refine_kernel<float, 4><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, crow32, col32, tmax, tau, K, id_add, top_vals, top_ids, overflow);
-    else topk_refine_kernel<float, 8><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, crow32, col32, tmax, tau, K, id_add, top_vals, top_ids, overflow);
+    if (K <= 128) topk_from_cands_kernel<float, 4><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, cand, cand_cnt, n_sub, candcap, crow32, col32, K, id_add, top_vals, top_ids, overflow);
+    else topk_from_cands_kernel<float, 8><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, cand, cand_cnt, n_sub, candcap, crow32, col32, K, id_add, top_vals, top_ids, overflow);
+    RB_LAUNCH_CHECK("topk_from_cands_kernel");
+    if (K <= 128) topk_refine_kernel<float, 4><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, crow32, col32, K, id_add, top_vals, top_ids, overflow);
+    else topk_refine_kernel<float, 8><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, crow32, col32, K, id_add, top_vals, top_ids, overflow);
   }
   RB_LAUNCH_CHECK("topk_refine_kernel");
   return 0;
@@ -895,10 +905,10 @@ extern "C" size_t rb_workspace_bytes(int op, int64_t M, int64_t N, int d, int K,
       const int xt = sweep_xt(mode, d, M);
       Plan p = make_plan(M, N, sms, 1 << 20, 8, 128 * xt);
       const int n_sub = (xt == 2) ? p.n_splits : 2 * p.n_splits;
+      const int n0_tiles = topk_prefix_tiles(p.n_strm_tiles, K);
       return need + staged_bytes(M, d, mode) + staged_bytes(N, d, mode) + (M + 1 + std::max<int64_t>(nnz, 1)) * 4 +
-             static_cast<size_t>(M) * (static_cast<size_t>(p.n_strm_tiles) + 4) * 4 +
-             static_cast<size_t>(p.n_stat_tiles) * xt * 4 * p.n_strm_tiles +
-             static_cast<size_t>(M) * n_sub * (topk_candcap(K, n_sub) * 4 + 4) + 8192;
+             static_cast<size_t>(M) * (static_cast<size_t>(n0_tiles) * 4 + sizeof(RowLadder) + 4) +
+             static_cast<size_t>(M) * n_sub * (topk_candcap(K, n_sub, p.n_strm_tiles, n0_tiles) * 8 + 4) + 8192;
     }
     default: return 0;
   }

@@ -857,9 +857,13 @@ __device__ __forceinline__ T warp_blocked_get(const T (&v)[E], int idx) {
 // threshold are staged (ballot compaction into shared memory) and the staged block is sorted and merged
 // into the running top list when it fills up -- about 128 + K ln(n/128) insertions per row instead of a
 // sort per 128-value chunk; the next chunk of tile maxima is in flight while the current one is examined.
+// The ladder of the candidate sweep comes from the same sorted list: thr[0] = tau0 = K-th largest, checkpoint
+// thr[k] = (K >> k)-th largest (k = 1..TOPK_LEVELS while K >> k >= 1, +inf beyond), each lowered by 2^-18 of its
+// magnitude so that a top-K member whose tensor-core score differs from a supporter's in the last bits still
+// passes; the level counters are zeroed.
 template <int E>
 __global__ void __launch_bounds__(128)
-tilemax_select_kernel(const float* __restrict__ T, int n_tiles, long long n_rows, int K, float* __restrict__ tau_out) {
+tilemax_select_kernel(const float* __restrict__ T, int n_tiles, long long n_rows, int K, RowLadder* __restrict__ ladder) {
   __shared__ float stage_s[4][32 * E];
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -912,23 +916,21 @@ tilemax_select_kernel(const float* __restrict__ T, int n_tiles, long long n_rows
     }
   }
   if (ns > 0) flush();
-  if (lane == 0) tau_out[row] = tau;  // -inf when fewer than K clean tiles exist
-}
-
-// ---- flag table of the candidate sweep: flag[g][t] != 0 iff some row of the 32-row group g (= one
-// epilogue warp's rows) has tile maximum >= its threshold in streamed tile t.
-__global__ void tile_flag_kernel(const float* __restrict__ T, const float* __restrict__ tau, int n_tiles, long long n_rows,
-                                 unsigned char* __restrict__ flag) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const long long g = blockIdx.y;
-  if (t >= n_tiles) return;
-  const long long r0 = g * 32, r1 = min(n_rows, r0 + 32);
-  bool any = false;
-  for (long long r = r0; r < r1; ++r) {
-    const float v = __ldg(T + r * n_tiles + t);
-    any |= (v >= __ldg(tau + r)) || (v != v);  // NaN = dirty tile: always scanned
+  float mine = INFINITY;   // lane l holds thr[l]
+  if (lane == 0) mine = tau;   // -inf when fewer than K clean tiles exist
+#pragma unroll
+  for (int k = 1; k <= TOPK_LEVELS; ++k) {
+    const int rank = K >> k;   // warp-uniform
+    if (rank >= 1) {
+      const float v = warp_blocked_get<float, E>(best, rank - 1);
+      if (lane == k) mine = v;
+    }
   }
-  flag[g * n_tiles + t] = any ? 1 : 0;
+  if (mine > -INFINITY && mine < INFINITY) mine -= fabsf(mine) * 3.8146973e-06f;
+  if (lane < 8) {
+    ladder[row].thr[lane] = mine;
+    ladder[row].hist[lane] = 0u;
+  }
 }
 
 // exact fp32 logit of one (query, item) pair: a sequential FMA chain over k = 0..d-1 (the same order in
@@ -961,29 +963,31 @@ __device__ __forceinline__ float exact_logit(const float* __restrict__ u, const 
   return __fmul_rn(acc, scale);
 }
 
-// ---- top-K pass 3: re-score the row's hit groups (aligned groups of 8 items whose maximum reached tau in
-// the EPI_CAND sweep) exactly, drop seen items (UniSRec/main.py:413), keep the K best by (score desc,
-// id asc).  Rows with an overflowed sub-list (or more than GROUPS_CAP groups in total) are flagged for the
-// fallback below.  One warp per row: the sub-lists are first flattened into shared memory (counts scanned 32
-// sub-lists at a time), then a lane scores one item, four groups per step -- the number of dependent
-// memory round trips is total/4 + n_sub/32, not n_sub.
+// ---- top-K finish: the row's candidates are (group maximum, group id) pairs of aligned groups of 8 items that
+// reached the row's running threshold in the EPI_CAND sweep.  First the cut T = K-th largest maximum among
+// the CLEAN groups (each is the score of a distinct unseen item, so the K-th best item scores >= T and every
+// top-K member sits in a group whose maximum reaches T); then only the groups that reach T (about K of the few
+// hundred candidates, plus the dirty ones) are re-scored exactly, seen items dropped (UniSRec/main.py:413), and
+// the K best by (score desc, id asc) kept.  Rows with an overflowed sub-list (or more than GROUPS_CAP candidates)
+// are flagged for the fallback below.  One warp per row: the sub-lists are first flattened into shared memory
+// (counts scanned 32 sub-lists at a time), then a lane scores one item, four groups per step.
 constexpr int GROUPS_CAP = 1024;
 
 template <typename TW, int E>
 __global__ void __launch_bounds__(128)
-topk_from_groups_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const float* __restrict__ bias, float scale,
-                        int d, long long n_rows, int n_items, const int* __restrict__ cand,
-                        const int* __restrict__ cand_cnt, int n_sub, int cap, const int* __restrict__ seen_crow,
-                        const int* __restrict__ seen_col, int K, int id_add, float* __restrict__ out_vals,
-                        int* __restrict__ out_ids, int* __restrict__ overflow) {
+topk_from_cands_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const float* __restrict__ bias, float scale,
+                       int d, long long n_rows, int n_items, const uint2* __restrict__ cand,
+                       const int* __restrict__ cand_cnt, int n_sub, int cap, const int* __restrict__ seen_crow,
+                       const int* __restrict__ seen_col, int K, int id_add, float* __restrict__ out_vals,
+                       int* __restrict__ out_ids, int* __restrict__ overflow) {
   __shared__ __align__(16) float u_s[4][256];
   __shared__ unsigned long long stage_s[4][256];
-  __shared__ int glist_s[4][GROUPS_CAP];
+  __shared__ uint2 clist_s[4][GROUPS_CAP];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 4 + wib;
   if (row >= n_rows) return;
   const int* cnts = cand_cnt + row * n_sub;
-  int* glist = glist_s[wib];
+  uint2* clist = clist_s[wib];
   // ---- flatten the sub-lists
   int total = 0;
   bool ovf = false;
@@ -999,14 +1003,52 @@ topk_from_groups_kernel(const TW* __restrict__ U, const TW* __restrict__ W, cons
     }
     const int off = total + incl - c;
     if (off + c <= GROUPS_CAP) {
-      const int* gl = cand + (row * n_sub + sidx) * cap;
-      for (int e = 0; e < c; ++e) glist[off + e] = __ldg(gl + e);
+      const uint2* gl = cand + (row * n_sub + sidx) * cap;
+      for (int e = 0; e < c; ++e) clist[off + e] = __ldg(gl + e);
     }
     total += __shfl_sync(0xffffffffu, incl, 31);
   }
   ovf = __any_sync(0xffffffffu, ovf) || total > GROUPS_CAP;
   if (lane == 0) overflow[row] = ovf ? 1 : 0;
   if (ovf) return;
+  __syncwarp();
+  // ---- the cut: K-th largest maximum among the clean groups (-inf when there are fewer than K)
+  float cut = -INFINITY;
+  {
+    float bestf[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) bestf[e] = -INFINITY;
+    for (int base = 0; base < total; base += 32 * E) {
+      float cur[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int i = base + lane * E + e;
+        cur[e] = -INFINITY;
+        if (i < total) {
+          const uint2 c = clist[i];
+          if (!(c.y & CAND_DIRTY)) cur[e] = __uint_as_float(c.x);
+        }
+      }
+      warp_bitonic_sort_desc<float, E>(cur);
+      warp_topk_absorb<float, E>(bestf, cur);
+    }
+    cut = warp_blocked_get<float, E>(bestf, K - 1);
+    if (cut > -INFINITY) cut -= fabsf(cut) * 3.8146973e-06f;   // tensor-core vs exact fp32 scores differ in the last bits
+  }
+  // ---- keep the groups that reach the cut (compaction in place: the write index never passes the read index)
+  int kept = 0;
+  for (int base = 0; base < total; base += 32) {
+    const int i = base + lane;
+    uint2 c = make_uint2(0u, 0u);
+    bool keep = false;
+    if (i < total) { c = clist[i]; keep = __uint_as_float(c.x) >= cut; }
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    __syncwarp();
+    if (keep) clist[kept + __popc(m & ((1u << lane) - 1u))] = c;
+    kept += __popc(m);
+    __syncwarp();
+  }
+  total = kept;
   float* u = u_s[wib];
   unsigned long long* stage = stage_s[wib];
   for (int k = lane; k < 256; k += 32) u[k] = (k < d) ? static_cast<float>(U[row * d + k]) : 0.f;
@@ -1037,7 +1079,7 @@ topk_from_groups_kernel(const TW* __restrict__ U, const TW* __restrict__ W, cons
   };
   for (int base = 0; base < total; base += 4) {
     const int gi = base + (lane >> 3);
-    const int item = (gi < total) ? (glist[gi] << 3) + (lane & 7) : n_items;
+    const int item = (gi < total) ? (static_cast<int>(clist[gi].y & ~CAND_DIRTY) << 3) + (lane & 7) : n_items;
     unsigned long long key = 0ull;
     if (item < n_items) key = topk_key(exact_logit<TW>(u, W + static_cast<long long>(item) * d, d, scale, bias, item), item);
     bool pass = key > kth;
@@ -1072,15 +1114,16 @@ topk_from_groups_kernel(const TW* __restrict__ U, const TW* __restrict__ W, cons
   }
 }
 
-// ---- top-K fallback (rows flagged in `only`; all rows when `only` is null): re-score every tile of the row whose
-// maximum reaches tau (or is unknown: dirty) exactly (fp32 FMA over the stored operands),
-// skip seen ids, keep the K best by (score desc, id asc).  One warp per row; lane <-> item.
+// ---- top-K fallback (rows flagged in `only`; all rows when `only` is null): an exact scan of the row's whole
+// catalog (fp32 FMA over the stored operands), skipping seen ids, keeping the K best by (score desc, id asc).
+// Only rows whose candidate lists overflowed come here (massive ties, catalogs too small for a threshold).
+// One warp per row; lane <-> item.
 template <typename TW, int E>
 __global__ void __launch_bounds__(128)
 topk_refine_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const float* __restrict__ bias, float scale, int d,
                    long long n_rows, int n_items, const int* __restrict__ seen_crow, const int* __restrict__ seen_col,
-                   const float* __restrict__ tmax, const float* __restrict__ tau, int K, int id_add,
-                   float* __restrict__ out_vals, int* __restrict__ out_ids, const int* __restrict__ only) {
+                   int K, int id_add, float* __restrict__ out_vals, int* __restrict__ out_ids,
+                   const int* __restrict__ only) {
   __shared__ __align__(16) float u_s[4][256];
   __shared__ unsigned long long cand_s[4][256];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1100,8 +1143,6 @@ topk_refine_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const flo
   int ncand = 0;
   const uint32_t lt = (1u << lane) - 1u;
   const int n_tiles = (n_items + 127) / 128;
-  const float* trow = tmax + row * n_tiles;
-  const float tau_r = tau[row];   // -inf (fewer than K clean tiles): every tile is scanned
 
   auto flush = [&]() {
     for (int base = 0; base < ncand; base += 32 * E) {
@@ -1119,13 +1160,8 @@ topk_refine_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const flo
     __syncwarp();
   };
 
-  for (int tb = 0; tb < n_tiles; tb += 32) {
-   // tiles that can hold a top-K member: maximum >= tau, or dirty (NaN: holds a seen id, maximum unknown)
-   const float tv = (tb + lane < n_tiles) ? __ldg(trow + tb + lane) : -INFINITY;
-   uint32_t tmask = __ballot_sync(0xffffffffu, (tb + lane < n_tiles) && (tv >= tau_r || tv != tv));
-   while (tmask) {
-    const int tile = tb + __ffs(tmask) - 1;
-    tmask &= tmask - 1;
+  {
+   for (int tile = 0; tile < n_tiles; ++tile) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     int item[4];
     const TW* wrow[4];

@@ -5,17 +5,23 @@
 //
 //   EPI_DENSE  store S (compat path for recommend_from_full, reference SASRec/main.py:228)
 //   EPI_LSE    online (max, sum-exp) + label-logit pick   (F.cross_entropy fwd, SASRec/main.py:217-219)
-//   EPI_TOPK   maximum of every (row, 128-item tile): pass 1 of the exact top-K (UniSRec/main.py:408-435
-//              without dense (B,N)).  A tile holding one of the row's seen ids is reported as NaN
-//              ("dirty": it never supports the threshold but is always scanned by pass 2), so no
-//              per-item masking happens here.  simt.cuh turns the clean tile maxima into a per-row
-//              admission threshold tau = K-th largest (>= K unseen items reach it)
-//   EPI_CAND   pass 2: the same sweep again, emitting every (row, aligned group of 8 items) whose maximum
-//              reaches tau[row] (about K groups per row) into the (row, split, warpgroup) sub-list -- a
-//              register counter and a plain store of a group index; the hit path is a dozen
-//              instructions (a rarely executed path must stay tiny: it runs from a cold I-cache).  Tiles
-//              no row of a warp can hit (flag table) are skipped without touching TMEM.  The finish
-//              kernel re-scores the groups exactly, drops seen items and sorts.
+//   EPI_TOPK   maximum of every (row, 128-item tile) of a short PREFIX of the catalog (a few percent): the
+//              seed of the exact top-K (UniSRec/main.py:408-435 without dense (B,N)).  A tile holding one of
+//              the row's seen ids is reported as NaN ("dirty": it never supports a threshold), so no per-item
+//              masking happens here.  simt.cuh turns the clean tile maxima of the prefix into the row's
+//              starting threshold tau0 = K-th largest (>= K unseen items reach it) and a ladder of
+//              checkpoints c_k = (K >> k)-th largest.
+//   EPI_CAND   the one sweep over the whole catalog: every (row, aligned group of 8 items) whose maximum
+//              reaches the row's RUNNING threshold goes to the (row, split[, warpgroup]) sub-list as
+//              (group maximum, group id).  The threshold climbs the ladder while the sweep runs: every
+//              candidate of a clean tile bumps a per-row counter of the highest checkpoint it reaches
+//              (one RED), all splits of a row share the counters, and once >= K unseen items are known to
+//              reach c_k the row's threshold becomes c_k (threads re-read their row's counters every
+//              fourth tile, the load in flight behind the tile's arithmetic).  About K (2 + log2(N/prefix))
+//              candidates per row instead of the K ln(N/K) of an exact running K-th best -- with a hit path of
+//              two dozen instructions (a rarely executed path must stay tiny: it runs from a cold I-cache).
+//              The finish kernel keeps the groups that can still matter (maximum >= the K-th largest clean
+//              group maximum), re-scores them exactly, drops seen items and sorts.
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
 // warps 2..9 = two epilogue warpgroups (thread <-> TMEM lane <-> stationary row).
@@ -39,6 +45,16 @@ constexpr float LN2 = 0.6931471805599453f;
 constexpr float MASKED_SCORE = -1e23f;  // UniSRec/main.py:413
 constexpr int SWEEP_THREADS = 320;
 
+// Per-row threshold ladder of the top-K candidate sweep (64 bytes = two sectors):
+//   thr[0] = tau0, thr[1..TOPK_LEVELS] = checkpoints (non-decreasing; +inf = unused),
+//   hist[l] = candidates of clean tiles whose group maximum reaches thr[l] but not thr[l+1]  (l >= 1)
+constexpr int TOPK_LEVELS = 6;
+struct __align__(32) RowLadder {
+  float thr[8];
+  unsigned int hist[8];
+};
+constexpr unsigned int CAND_DIRTY = 0x80000000u;   // the group's tile holds a seen id of the row
+
 struct SweepArgs {
   int n_stat;        // valid rows of the stationary operand
   int n_strm;        // valid rows of the streamed operand
@@ -60,10 +76,10 @@ struct SweepArgs {
   const int* seen_crow;  // [n_stat+1] CSR of already-seen LOCAL item ids, sorted per row (nullable)
   const int* seen_col;
   float* tile_max;    // [n_stat][n_strm_tiles]
-  // EPI_CAND (rows stationary): pass 2 of the top-K
-  const float* tau;                 // [n_stat] admission threshold of the row (score >= tau is a candidate)
-  const unsigned char* tile_flag;   // [n_stat_tiles*4][n_strm_tiles] != 0: some row of that 32-row group can hit
-  int* cand;                        // [n_stat][n_sub][cand_cap] hit groups (item id >> 3); one sub-list per (split, warpgroup)
+  // EPI_CAND (rows stationary): the candidate sweep of the top-K
+  RowLadder* ladder;                // [n_stat] thresholds (read-only here) + shared level counters (RED + re-read)
+  int k_need;                       // K: a checkpoint becomes the threshold once this many unseen items reach it
+  uint2* cand;                      // [n_stat][n_sub][cand_cap] (group maximum bits, item id >> 3 | dirty << 31)
   int* cand_cnt;                    // [n_stat][n_sub] groups found per sub-list (> cand_cap: overflow)
   int cand_cap;
   int n_sub;                        // XT = 1: 2*n_splits (two warpgroups share a row), XT = 2: n_splits
@@ -232,27 +248,9 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
       int stat_tile, split, t0, t1;
       item_range(item, stat_tile, split, t0, t1);
       mbar_wait(&bar->x_full, k & 1);
-      // EPI_CAND: a (stationary tile, streamed tile) pair in which no 32-row group is flagged (no row can reach
-      // its threshold there: ~44 % of the pairs at K = 50, N = 1M) needs no scores at all -- its MMAs are
-      // skipped, only the S-buffer hand-shake is kept.  Lanes 0..4*XT-1 fetch one group flag each, one tile ahead.
-      unsigned int f_next = 1u;
-      auto fetch_flags = [&](int t) -> unsigned int {
-        if (lane < 4 * C::XT) {
-          const int stile = (C::XT == 1) ? stat_tile : stat_tile * 2 + (lane >> 2);
-          return __ldg(a.tile_flag + static_cast<long long>(stile * 4 + (lane & 3)) * a.n_strm_tiles + t);
-        }
-        return 0u;
-      };
-      if (C::EPI == EPI_CAND) f_next = fetch_flags(t0);
       for (int t = t0; t < t1; ++t, ++it) {
         const uint32_t buf = it & 1, sph = (it >> 1) & 1;
         const uint32_t cs = it * C::SPT;   // first stage of this streamed tile
-        uint32_t live = 3u;                // bit x: stationary tile x needs this streamed tile's scores
-        if (C::EPI == EPI_CAND) {
-          const uint32_t m = __ballot_sync(0xffffffffu, f_next != 0u);
-          live = ((m & 0x0Fu) ? 1u : 0u) | ((m & 0xF0u) ? 2u : 0u);
-          if (t + 1 < t1) f_next = fetch_flags(t + 1);
-        }
 #pragma unroll
         for (int x = 0; x < C::XT; ++x)    // S buffer: XT=1 per tile parity, XT=2 per (X tile, parity)
           mbar_wait(&bar->s_empty[(C::XT == 1) ? buf : x * 2 + buf], sph ^ 1);
@@ -282,14 +280,12 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
               const uint32_t bidx = (C::XT == 1) ? buf : x * 2 + buf;
               const uint32_t d_tmem = tmem_base + bidx * C::BN;
               const uint32_t xs_lo = x_lo + ((x * C::XTILE_BYTES + ac * 128 * 128) >> 4);
-              if ((live >> x) & 1u) {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                  const uint64_t ad = smem_desc(dhi, xs_lo + ((kk * 32) >> 4));
-                  const uint64_t bd = smem_desc(dhi, ys_lo + ((kk * 32) >> 4));
-                  if (C::DT == DT_BF16) mma_f16_ss(d_tmem, ad, bd, idesc1, (p | kk) != 0);
-                  else mma_tf32_ss(d_tmem, ad, bd, idesc1, (p | kk) != 0);
-                }
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t ad = smem_desc(dhi, xs_lo + ((kk * 32) >> 4));
+                const uint64_t bd = smem_desc(dhi, ys_lo + ((kk * 32) >> 4));
+                if (C::DT == DT_BF16) mma_f16_ss(d_tmem, ad, bd, idesc1, (p | kk) != 0);
+                else mma_tf32_ss(d_tmem, ad, bd, idesc1, (p | kk) != 0);
               }
               if (p == C::NPAIR - 1) tc_commit(&bar->s_full[bidx]);
             }
@@ -326,13 +322,23 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
       int seen_cur = 0, seen_end = 0, next_seen = 0x7fffffff;   // TOPK: cursor into the row's seen list
       int next2_seen = 0x7fffffff;                              //       (one entry prefetched: no load latency on advance)
       int n_cand = 0;                                           // CAND: entries in this thread's sub-list
-      int* cand_list = nullptr;
-      unsigned int flag_next = 0;                               // CAND: flag of the next tile this warpgroup owns
+      uint2* cand_list = nullptr;
+      float tau = INFINITY;                         // CAND: running threshold; rows beyond n_stat never hit
+      float th[TOPK_LEVELS];                        // CAND: the row's checkpoints c_1 <= c_2 <= ... (+inf = unused)
+#pragma unroll
+      for (int l = 0; l < TOPK_LEVELS; ++l) th[l] = INFINITY;
+      unsigned int* hist = nullptr;                 // CAND: the row's shared level counters
+      uint32_t my_tiles = 0;                        // CAND: tiles this thread has handled in this work item
 
-      float tau = INFINITY;                         // CAND: rows beyond n_stat never hit
-      if (C::EPI == EPI_CAND && srow_ok) tau = __ldg(a.tau + srow);
+      if (C::EPI == EPI_CAND && srow_ok) {
+        const RowLadder* ld = a.ladder + srow;
+        const float4 ta = __ldg(reinterpret_cast<const float4*>(ld->thr));
+        const float4 tb = __ldg(reinterpret_cast<const float4*>(ld->thr) + 1);
+        tau = ta.x; th[0] = ta.y; th[1] = ta.z; th[2] = ta.w; th[3] = tb.x; th[4] = tb.y; th[5] = tb.z;
+        hist = a.ladder[srow].hist;
+      }
       if (C::EPI == EPI_LSE) lab = srow_ok ? a.labels[srow] : -1;
-      if (C::EPI == EPI_TOPK) {
+      if (C::EPI == EPI_TOPK || C::EPI == EPI_CAND) {
         if (a.seen_crow != nullptr && srow_ok) {
           seen_cur = a.seen_crow[srow];
           seen_end = a.seen_crow[srow + 1];
@@ -347,13 +353,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
           next2_seen = (seen_cur + 1 < seen_end) ? a.seen_col[seen_cur + 1] : 0x7fffffff;
         }
       }
-      const unsigned char* flag_row = nullptr;
-      if (C::EPI == EPI_CAND) {
+      if (C::EPI == EPI_CAND)
         cand_list = a.cand + (static_cast<long long>(srow) * a.n_sub + (C::XT == 1 ? split * 2 + wg : split)) * a.cand_cap;
-        flag_row = a.tile_flag + static_cast<long long>(stile * 4 + q) * a.n_strm_tiles;
-        const int tf = (C::XT == 1) ? t0 + ((wg - static_cast<int>(it & 1)) & 1) : t0;  // first tile this warpgroup handles
-        if (tf < t1) flag_next = __ldg(flag_row + tf);
-      }
       // advance the seen cursor by one entry; the entry after next is already in a register
       auto seen_advance = [&]() {
         ++seen_cur;
@@ -369,18 +370,22 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
         const int col_base = t * C::BN;                       // first streamed row of the tile
         const int n_valid = min(C::BN, a.n_strm - col_base);  // valid columns in this tile
         const bool full_tile = (n_valid == C::BN);
-        bool tile_live = true;
-        if (C::EPI == EPI_CAND) {  // warp-uniform: can any of this warp's 32 rows reach its threshold in this tile?
-          tile_live = flag_next != 0;
-          if (t + 3 - C::XT < t1) flag_next = __ldg(flag_row + t + 3 - C::XT);  // the next tile this warpgroup handles
+        // CAND: every fourth tile the thread re-reads its row's level counters (L2: other CTAs bump them);
+        // the two loads are in flight behind this tile's arithmetic and are consumed after it
+        bool refresh = false;
+        uint4 h_lo = make_uint4(0u, 0u, 0u, 0u), h_hi = make_uint4(0u, 0u, 0u, 0u);
+        unsigned int dirty_bit = 0u;
+        if (C::EPI == EPI_CAND) {
+          refresh = (hist != nullptr) && ((my_tiles++ & 3u) == 3u);
+          if (refresh) {
+            h_lo = __ldcg(reinterpret_cast<const uint4*>(hist));
+            h_hi = __ldcg(reinterpret_cast<const uint4*>(hist) + 1);
+          }
+          while (next_seen < col_base) seen_advance();   // seen ids that fell into the other warpgroup's tiles
+          dirty_bit = (next_seen < col_base + C::BN) ? CAND_DIRTY : 0u;
         }
         mbar_wait(&bar->s_full[bidx], sph);
         tc_fence_after();
-        if (C::EPI == EPI_CAND && !tile_live) {
-          tc_fence_before();
-          mbar_arrive(&bar->s_empty[bidx]);
-          continue;
-        }
         float tmax = -INFINITY;   // TOPK: max of this tile for this row
         const bool tile_quick = plain && full_tile;   // warp-uniform
         uint32_t raw[2][32];
@@ -506,8 +511,15 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 if (m[g] >= tau) {
-                  if (n_cand < a.cand_cap) cand_list[n_cand] = (col_base + c0 + 8 * g) >> 3;
+                  if (n_cand < a.cand_cap)
+                    cand_list[n_cand] = make_uint2(__float_as_uint(m[g]), static_cast<unsigned int>((col_base + c0 + 8 * g) >> 3) | dirty_bit);
                   ++n_cand;
+                  if (dirty_bit == 0u) {  // a clean group's maximum is an unseen item: it supports every checkpoint it reaches
+                    int lvl = 0;
+#pragma unroll
+                    for (int l = 0; l < TOPK_LEVELS; ++l) lvl += (m[g] >= th[l]) ? 1 : 0;
+                    if (lvl > 0) atomicAdd(hist + lvl, 1u);   // result unused: a RED
+                  }
                 }
               }
             }
@@ -517,6 +529,18 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
         // release the S buffer (all tcgen05.ld of this thread have completed)
         tc_fence_before();
         mbar_arrive(&bar->s_empty[bidx]);
+        if (C::EPI == EPI_CAND) {
+          while (next_seen < col_base + C::BN) seen_advance();
+          if (refresh) {  // counts of candidates reaching c_l or more, from the top of the ladder down
+            const unsigned int hv[8] = {h_lo.x, h_lo.y, h_lo.z, h_lo.w, h_hi.x, h_hi.y, h_hi.z, h_hi.w};
+            unsigned int c = 0u;
+#pragma unroll
+            for (int l = TOPK_LEVELS; l >= 1; --l) {
+              c += hv[l];
+              if (c >= static_cast<unsigned int>(a.k_need)) tau = fmaxf(tau, th[l - 1]);
+            }
+          }
+        }
         if (C::EPI == EPI_TOPK) {
           while (next_seen < col_base) seen_advance();  // seen ids that fell into the other warpgroup's tiles
           const bool dirty = next_seen < col_base + C::BN;
