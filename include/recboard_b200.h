@@ -153,6 +153,13 @@ int rb_topk_eval(const void* U, const void* W, const float* bias, float scale,
                  int64_t B, int64_t N, int d, int dtype, int mode, int K, float* top_vals,
                  int32_t* top_ids, void* ws, size_t ws_bytes, rb_stream_t stream);
 
+/* Diagnostics (tests, profiling): where rb_topk_eval leaves its intermediate results inside the workspace it was
+ * given, for the same (B, N, d, K, mode, nnz) on the same device.  out[8] = { n_sub, cand_cap, prefix tiles, byte
+ * offset of the per-row threshold ladders (64 B each: float thr[8], uint32 cnt[8]), offset of cand_cnt
+ * (int32 [B][n_sub]), offset of the overflow flags (int32 [B]), offset of the candidate lists
+ * ({f32 score, u32 group id} [B][n_sub][cand_cap]), bytes used }. */
+int rb_topk_debug_layout(int64_t B, int64_t N, int d, int K, int mode, int64_t nnz, int64_t* out);
+
 /* Merge R sorted per-shard lists (vals,ids)[R][B][K] into the global top-K (rb_topk_eval order). */
 int rb_topk_merge(const float* vals, const int32_t* ids, int R, int64_t B, int K, float* out_vals,
                   int32_t* out_ids, rb_stream_t stream);

@@ -763,6 +763,56 @@ static int topk_candcap(int K, int n_sub, int n_tiles, int prefix_tiles) {
   return c;
 }
 
+// Workspace layout of rb_topk_eval behind the staged operands (one place: the entry, the size query and the
+// debug hook below agree by construction).
+struct TopkLayout {
+  int xt, n0_tiles, n_sub, candcap;
+  long long n0;
+  Plan p, pp;
+  int* crow32; int* col32; float* tmax; RowLadder* ladder; int* cand_cnt; int* overflow; uint2* cand;
+};
+static TopkLayout topk_layout(Bump& b, long long B, long long N, int d, int mode, int K, bool seen, long long nnz, int sms) {
+  TopkLayout l{};
+  l.xt = sweep_xt(mode, d, B);
+  l.p = make_plan(B, N, sms, 1 << 20, 8, 128 * l.xt);
+  l.n0_tiles = topk_prefix_tiles(l.p.n_strm_tiles, K);
+  l.n0 = std::min<long long>(N, 1ll * l.n0_tiles * BN);
+  l.pp = make_plan(B, l.n0, sms, 1 << 20, 8, 128 * l.xt);   // the seeding sweep over the prefix
+  l.n_sub = 2 * l.p.n_splits;   // one sub-list per (split, tile parity): sweep.cuh, SUBS
+  l.candcap = topk_candcap(K, l.n_sub, l.p.n_strm_tiles, l.n0_tiles);
+  if (seen) {
+    l.crow32 = b.take<int>(B + 1);
+    l.col32 = b.take<int>(std::max<long long>(nnz, 1));
+  }
+  l.tmax = b.take<float>(static_cast<size_t>(B) * l.n0_tiles);
+  l.ladder = b.take<RowLadder>(B);
+  l.cand_cnt = b.take<int>(static_cast<size_t>(B) * l.n_sub);
+  l.overflow = b.take<int>(B);
+  l.cand = b.take<uint2>(static_cast<size_t>(B) * l.n_sub * l.candcap);
+  return l;
+}
+
+// Diagnostics for tests and profiling: where rb_topk_eval leaves its intermediate results in the workspace it was
+// given (byte offsets; valid for the same arguments on the same device, bf16 mode or fp32x3 mode alike).
+//   out[0] = n_sub, out[1] = cand_cap, out[2] = prefix tiles, out[3] = offset of the ladders (64 B per row),
+//   out[4] = offset of cand_cnt (int32 [B][n_sub]), out[5] = offset of the overflow flags (int32 [B]),
+//   out[6] = offset of the candidate lists (8 B entries [B][n_sub][cand_cap]), out[7] = bytes needed
+extern "C" int rb_topk_debug_layout(int64_t B, int64_t N, int d, int K, int mode, int64_t nnz, int64_t* out) {
+  DevInfo dv; if (int r = get_dev(dv)) return r;
+  if (!out) return fail(RB_E_ARG, "null output");
+  Bump b(nullptr, ~size_t(0));
+  b.take<char>(staged_bytes(B, d, mode) ? staged_bytes(B, d, mode) - 256 : 0);
+  b.take<char>(staged_bytes(N, d, mode) ? staged_bytes(N, d, mode) - 256 : 0);
+  TopkLayout l = topk_layout(b, B, N, d, mode, K, nnz > 0, nnz, dv.sms);
+  out[0] = l.n_sub; out[1] = l.candcap; out[2] = l.n0_tiles;
+  out[3] = reinterpret_cast<char*>(l.ladder) - static_cast<char*>(nullptr);
+  out[4] = reinterpret_cast<char*>(l.cand_cnt) - static_cast<char*>(nullptr);
+  out[5] = reinterpret_cast<char*>(l.overflow) - static_cast<char*>(nullptr);
+  out[6] = reinterpret_cast<char*>(l.cand) - static_cast<char*>(nullptr);
+  out[7] = static_cast<int64_t>(b.off);
+  return 0;
+}
+
 extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, float scale, const int64_t* seen_crow,
                             const int64_t* seen_col, int64_t seen_nnz, int64_t id_base, int64_t B, int64_t N, int d,
                             int dtype, int mode, int K, float* top_vals, int32_t* top_ids, void* ws, size_t ws_bytes,
@@ -781,27 +831,16 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
   Operand ou, ow;
   if (int r = stage_operand(U, B, d, mode, b, ou, st)) return r;
   if (int r = stage_operand(W, N, d, mode, b, ow, st)) return r;
-  const int xt = sweep_xt(mode, d, B);
-  Plan p = make_plan(B, N, dv.sms, 1 << 20, 8, 128 * xt);
-  const int n0_tiles = topk_prefix_tiles(p.n_strm_tiles, K);
-  const long long n0 = std::min<long long>(N, 1ll * n0_tiles * BN);
-  Plan pp = make_plan(B, n0, dv.sms, 1 << 20, 8, 128 * xt);   // the seeding sweep over the prefix
-  const int n_sub = (xt == 2) ? p.n_splits : 2 * p.n_splits;
-  const int candcap = topk_candcap(K, n_sub, p.n_strm_tiles, n0_tiles);
-  int* crow32 = nullptr; int* col32 = nullptr;
-  long long nnz = 0;
-  if (seen_crow) {
-    if (seen_nnz < 0) return fail(RB_E_ARG, "seen_nnz < 0");
-    nnz = seen_nnz;
-    crow32 = b.take<int>(B + 1);
-    col32 = b.take<int>(std::max<long long>(nnz, 1));
-  }
-  float* tmax = b.take<float>(static_cast<size_t>(B) * n0_tiles);
-  RowLadder* ladder = b.take<RowLadder>(B);
-  int* cand_cnt = b.take<int>(static_cast<size_t>(B) * n_sub);
-  int* overflow = b.take<int>(B);
-  uint2* cand = b.take<uint2>(static_cast<size_t>(B) * n_sub * candcap);
+  if (seen_crow && seen_nnz < 0) return fail(RB_E_ARG, "seen_nnz < 0");
+  const long long nnz = seen_crow ? seen_nnz : 0;
+  TopkLayout lay = topk_layout(b, B, N, d, mode, K, seen_crow != nullptr, nnz, dv.sms);
   if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
+  const int xt = lay.xt, n0_tiles = lay.n0_tiles, n_sub = lay.n_sub, candcap = lay.candcap;
+  const Plan p = lay.p, pp = lay.pp;
+  const long long n0 = lay.n0;
+  int* crow32 = lay.crow32; int* col32 = lay.col32;
+  float* tmax = lay.tmax; RowLadder* ladder = lay.ladder; int* cand_cnt = lay.cand_cnt; int* overflow = lay.overflow;
+  uint2* cand = lay.cand;
   if (seen_crow) {
     const long long n = std::max<long long>(B + 1, nnz);
     csr_local_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(seen_crow, seen_col, id_base, crow32, col32, B, nnz);
@@ -902,13 +941,11 @@ extern "C" size_t rb_workspace_bytes(int op, int64_t M, int64_t N, int d, int K,
       return n;
     }
     case RB_OP_TOPK_EVAL: {
-      const int xt = sweep_xt(mode, d, M);
-      Plan p = make_plan(M, N, sms, 1 << 20, 8, 128 * xt);
-      const int n_sub = (xt == 2) ? p.n_splits : 2 * p.n_splits;
-      const int n0_tiles = topk_prefix_tiles(p.n_strm_tiles, K);
-      return need + staged_bytes(M, d, mode) + staged_bytes(N, d, mode) + (M + 1 + std::max<int64_t>(nnz, 1)) * 4 +
-             static_cast<size_t>(M) * (static_cast<size_t>(n0_tiles) * 4 + sizeof(RowLadder) + 4) +
-             static_cast<size_t>(M) * n_sub * (topk_candcap(K, n_sub, p.n_strm_tiles, n0_tiles) * 8 + 4) + 8192;
+      Bump b(nullptr, ~size_t(0));
+      b.take<char>(staged_bytes(M, d, mode));
+      b.take<char>(staged_bytes(N, d, mode));
+      topk_layout(b, M, N, d, mode, K, nnz > 0, nnz, sms);
+      return need + b.off + 8192;
     }
     default: return 0;
   }

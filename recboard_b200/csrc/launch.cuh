@@ -27,7 +27,7 @@ template <class C>
 int launch_sweep_t(const CUtensorMap& ts, const CUtensorMap& ty, const SweepArgs& a, int grid, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(sweep_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
   if (e != cudaSuccess) return host_cuda_fail(e, "cudaFuncSetAttribute(sweep_kernel)");
-  sweep_kernel<C><<<grid, SWEEP_THREADS, C::SMEM_BYTES, st>>>(ts, ty, a);
+  sweep_kernel<C><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ts, ty, a);
   count_launch();
   e = cudaGetLastError();
   return e != cudaSuccess ? host_cuda_fail(e, "sweep_kernel") : 0;
@@ -40,13 +40,15 @@ int launch_sweep(int mode, int kc, const CUtensorMap& ts, const CUtensorMap& ty,
                  cudaStream_t st, int xt) {
   if (xt == 2) {
     if constexpr (EPI != EPI_DENSE) {
+      // the top-K sweeps are bound by their epilogue's own instruction stream: four epilogue warpgroups (one per S buffer)
+      constexpr int NWG = (EPI == EPI_CAND || EPI == EPI_TOPK) ? 4 : 2;
       if (mode == RB_MODE_BF16) {
-        if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 1, BN, 10, ROWS, 2>>(ts, ty, a, grid, st);
-        if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 2, BN, 4, ROWS, 2>>(ts, ty, a, grid, st);
-        if (kc <= 4) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 4, BN, 5, ROWS, 2>>(ts, ty, a, grid, st);
+        if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 1, BN, 10, ROWS, 2, NWG>>(ts, ty, a, grid, st);
+        if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 2, BN, 4, ROWS, 2, NWG>>(ts, ty, a, grid, st);
+        if (kc <= 4) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 4, BN, 5, ROWS, 2, NWG>>(ts, ty, a, grid, st);
       } else {
-        if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 1, BN, 4, ROWS, 2>>(ts, ty, a, grid, st);
-        if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 2, BN, 5, ROWS, 2>>(ts, ty, a, grid, st);
+        if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 1, BN, 4, ROWS, 2, NWG>>(ts, ty, a, grid, st);
+        if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_TF32X3, 2, BN, 5, ROWS, 2, NWG>>(ts, ty, a, grid, st);
       }
     }
     return host_fail(RB_E_UNSUPPORTED, "unsupported feature width for two stationary tiles");

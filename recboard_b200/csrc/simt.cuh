@@ -929,7 +929,7 @@ tilemax_select_kernel(const float* __restrict__ T, int n_tiles, long long n_rows
   if (mine > -INFINITY && mine < INFINITY) mine -= fabsf(mine) * 3.8146973e-06f;
   if (lane < 8) {
     ladder[row].thr[lane] = mine;
-    ladder[row].hist[lane] = 0u;
+    ladder[row].cnt[lane] = 0u;
   }
 }
 
@@ -939,38 +939,44 @@ template <typename TW>
 __device__ __forceinline__ float exact_logit(const float* __restrict__ u, const TW* __restrict__ w, int d, float scale,
                                              const float* __restrict__ bias, int item) {
   float acc = 0.f;
-  for (int k = 0; k < d; k += 8) {  // d % 8 == 0
-    const float4 ua = *reinterpret_cast<const float4*>(u + k);
-    const float4 ub = *reinterpret_cast<const float4*>(u + k + 4);
-    float x[8];
-    if constexpr (sizeof(TW) == 2) {
-      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(w + k));
-      x[0] = __uint_as_float(raw.x << 16); x[1] = __uint_as_float(raw.x & 0xFFFF0000u);
-      x[2] = __uint_as_float(raw.y << 16); x[3] = __uint_as_float(raw.y & 0xFFFF0000u);
-      x[4] = __uint_as_float(raw.z << 16); x[5] = __uint_as_float(raw.z & 0xFFFF0000u);
-      x[6] = __uint_as_float(raw.w << 16); x[7] = __uint_as_float(raw.w & 0xFFFF0000u);
-    } else {
-      const float4 r0 = __ldg(reinterpret_cast<const float4*>(w + k));
-      const float4 r1 = __ldg(reinterpret_cast<const float4*>(w + k + 4));
-      x[0] = r0.x; x[1] = r0.y; x[2] = r0.z; x[3] = r0.w; x[4] = r1.x; x[5] = r1.y; x[6] = r1.z; x[7] = r1.w;
+  constexpr int VE = 16 / sizeof(TW);   // elements per 16-byte vector
+  constexpr int NV = 8;                 // vectors fetched ahead of the chain (bf16: 64 elements = one 128-byte line)
+  for (int k0 = 0; k0 < d; k0 += NV * VE) {  // d % 8 == 0
+    uint4 raw[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      if (k0 + v * VE < d) raw[v] = __ldg(reinterpret_cast<const uint4*>(w + k0 + v * VE));
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int k = k0 + v * VE;
+      if (k < d) {
+        if constexpr (sizeof(TW) == 2) {
+          const float4 ua = *reinterpret_cast<const float4*>(u + k);
+          const float4 ub = *reinterpret_cast<const float4*>(u + k + 4);
+          acc = __fmaf_rn(ua.x, __uint_as_float(raw[v].x << 16), acc); acc = __fmaf_rn(ua.y, __uint_as_float(raw[v].x & 0xFFFF0000u), acc);
+          acc = __fmaf_rn(ua.z, __uint_as_float(raw[v].y << 16), acc); acc = __fmaf_rn(ua.w, __uint_as_float(raw[v].y & 0xFFFF0000u), acc);
+          acc = __fmaf_rn(ub.x, __uint_as_float(raw[v].z << 16), acc); acc = __fmaf_rn(ub.y, __uint_as_float(raw[v].z & 0xFFFF0000u), acc);
+          acc = __fmaf_rn(ub.z, __uint_as_float(raw[v].w << 16), acc); acc = __fmaf_rn(ub.w, __uint_as_float(raw[v].w & 0xFFFF0000u), acc);
+        } else {
+          const float4 ua = *reinterpret_cast<const float4*>(u + k);
+          acc = __fmaf_rn(ua.x, __uint_as_float(raw[v].x), acc); acc = __fmaf_rn(ua.y, __uint_as_float(raw[v].y), acc);
+          acc = __fmaf_rn(ua.z, __uint_as_float(raw[v].z), acc); acc = __fmaf_rn(ua.w, __uint_as_float(raw[v].w), acc);
+        }
+      }
     }
-    acc = __fmaf_rn(ua.x, x[0], acc); acc = __fmaf_rn(ua.y, x[1], acc);
-    acc = __fmaf_rn(ua.z, x[2], acc); acc = __fmaf_rn(ua.w, x[3], acc);
-    acc = __fmaf_rn(ub.x, x[4], acc); acc = __fmaf_rn(ub.y, x[5], acc);
-    acc = __fmaf_rn(ub.z, x[6], acc); acc = __fmaf_rn(ub.w, x[7], acc);
   }
   if (bias != nullptr) return __fmaf_rn(acc, scale, __ldg(bias + item));
   return __fmul_rn(acc, scale);
 }
 
-// ---- top-K finish: the row's candidates are (group maximum, group id) pairs of aligned groups of 8 items that
-// reached the row's running threshold in the EPI_CAND sweep.  First the cut T = K-th largest maximum among
-// the CLEAN groups (each is the score of a distinct unseen item, so the K-th best item scores >= T and every
-// top-K member sits in a group whose maximum reaches T); then only the groups that reach T (about K of the few
-// hundred candidates, plus the dirty ones) are re-scored exactly, seen items dropped (UniSRec/main.py:413), and
-// the K best by (score desc, id asc) kept.  Rows with an overflowed sub-list (or more than GROUPS_CAP candidates)
-// are flagged for the fallback below.  One warp per row: the sub-lists are first flattened into shared memory
-// (counts scanned 32 sub-lists at a time), then a lane scores one item, four groups per step.
+// ---- top-K finish: the row's candidates are (group maximum, group id) pairs of aligned groups of 4 items that
+// reached the row's running threshold in the EPI_CAND sweep (a few hundred).  First the cut T = K-th largest
+// maximum among the CLEAN groups (each is the score of a distinct unseen item, so the K-th best item scores >= T
+// and every top-K member sits in a group whose maximum reaches T); then only the groups that reach T (about K,
+// plus the dirty ones) are re-scored exactly in fp32, seen items dropped (UniSRec/main.py:413), and the K best by
+// (score desc, id asc) kept.  Rows with an overflowed sub-list (or more than GROUPS_CAP candidates) are flagged
+// for the fallback below.  One warp per row: the sub-lists are first flattened into shared memory (counts
+// scanned 32 sub-lists at a time), then a lane scores one item, eight groups per step.
 constexpr int GROUPS_CAP = 1024;
 
 template <typename TW, int E>
@@ -1002,11 +1008,20 @@ topk_from_cands_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const
       if (lane >= o) incl += v;
     }
     const int off = total + incl - c;
-    if (off + c <= GROUPS_CAP) {
-      const uint2* gl = cand + (row * n_sub + sidx) * cap;
-      for (int e = 0; e < c; ++e) clist[off + e] = __ldg(gl + e);
+    const int block_total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total + block_total <= GROUPS_CAP) {
+      if (n_sub <= 32) {   // few long sub-lists (large batches): the whole warp copies each one, coalesced
+        for (int j = 0; j < n_sub; ++j) {
+          const int cj = __shfl_sync(0xffffffffu, c, j), oj = __shfl_sync(0xffffffffu, off, j);
+          const uint2* gl = cand + (row * n_sub + j) * cap;
+          for (int e = lane; e < cj; e += 32) clist[oj + e] = __ldg(gl + e);
+        }
+      } else {             // many short sub-lists (small batches, many splits): one lane per sub-list
+        const uint2* gl = cand + (row * n_sub + sidx) * cap;
+        for (int e = 0; e < c; ++e) clist[off + e] = __ldg(gl + e);
+      }
     }
-    total += __shfl_sync(0xffffffffu, incl, 31);
+    total += block_total;
   }
   ovf = __any_sync(0xffffffffu, ovf) || total > GROUPS_CAP;
   if (lane == 0) overflow[row] = ovf ? 1 : 0;
@@ -1077,9 +1092,9 @@ topk_from_cands_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const
     ns = 0;
     __syncwarp();
   };
-  for (int base = 0; base < total; base += 4) {
-    const int gi = base + (lane >> 3);
-    const int item = (gi < total) ? (static_cast<int>(clist[gi].y & ~CAND_DIRTY) << 3) + (lane & 7) : n_items;
+  for (int base = 0; base < total; base += 8) {
+    const int gi = base + (lane >> 2);
+    const int item = (gi < total) ? (static_cast<int>(clist[gi].y & ~CAND_DIRTY) << 2) + (lane & 3) : n_items;
     unsigned long long key = 0ull;
     if (item < n_items) key = topk_key(exact_logit<TW>(u, W + static_cast<long long>(item) * d, d, scale, bias, item), item);
     bool pass = key > kth;

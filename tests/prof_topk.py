@@ -24,3 +24,17 @@ for _ in range(reps):
     ops.topk_eval(U, W, K, crow, col)
 b.record(); torch.cuda.synchronize()
 print("topk_eval ms", a.elapsed_time(b) / reps)
+
+# ---- what the candidate sweep left behind (rb_topk_debug_layout): candidates per row, overflowed rows, ladder state
+import ctypes
+from recboard_b200 import _lib as L
+out = (ctypes.c_int64 * 8)()
+L.check(L.lib().rb_topk_debug_layout(M, N, D, K, L.MODE_BF16, col.numel(), out), "rb_topk_debug_layout")
+n_sub, cap, n0_tiles, off_lad, off_cnt, off_ovf, off_cand, used = list(out)
+ws = next(iter(L.Workspace._bufs.values()))
+cnt = ws[off_cnt:off_cnt + 4 * M * n_sub].view(torch.int32).view(M, n_sub)
+ovf = ws[off_ovf:off_ovf + 4 * M].view(torch.int32)
+lad = ws[off_lad:off_lad + 64 * M].view(torch.int32).view(M, 16)
+per_row = cnt.sum(1).float()
+print(f"n_sub {n_sub} cand_cap {cap} prefix tiles {n0_tiles}; candidates/row mean {per_row.mean():.1f} max {per_row.max():.0f}; "
+      f"max sub-list {int(cnt.max())}; overflow rows {int(ovf.sum())}; ladder counters (mean) {lad[:, 8:].float().mean(0).tolist()}")
