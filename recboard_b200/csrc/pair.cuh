@@ -1,20 +1,28 @@
 // The training sweep engine ("pair kernel"): the two passes of the fused full-catalog cross-entropy
 // (reference: einsum("MD,ND->MN") + F.cross_entropy and its autograd, SASRec/main.py:217-219,249).
 //
-// One CTA keeps TWO stationary 128-row tiles X0, X1 in shared memory (one per epilogue warpgroup) and
-// streams 128-row tiles Y_j of the other operand through a TMA ring.  Every streamed tile is consumed
-// as two 64-row halves ("steps"); per step and warpgroup g the tensor pipe runs
-//     MMA1   S_g[h]  = X_g . Y_half^T        (SMEM x SMEM -> TMEM, 128 x 64 fp32)
-//     MMA2   A_g    += P_g[h] . Y_half       (TMEM x SMEM -> TMEM, 128 x d fp32)
-// where P_g[h] = 2^(c*S - ref) is produced by warpgroup g straight from TMEM registers, rounded to bf16
-// and written back over the first 32 columns of S_g[h] (the A operand of MMA2 is read from TMEM: the
-// softmax tile never touches shared or global memory).  S is double-buffered per warpgroup (h = half
-// index), so MMA1 of the next step runs while the warpgroup exponentiates the current one; issue order
-// per step:   m2_0(s) m1_0(s+2) m2_1(s) m1_1(s+2)
-// TMEM map (512 columns): S_0[0] S_0[1] S_1[0] S_1[1] (64 each) | A_0 | A_1 (d each).
+// One CTA keeps TWO stationary 128-row tiles X0, X1 in shared memory and streams 128-row tiles Y_t of the other
+// operand through a TMA ring.  Per streamed tile and stationary tile g the tensor pipe runs
+//     MMA1   S_g  = X_g . Y_t^T          (SMEM x SMEM -> TMEM, 128 x 128 fp32: eight N = 128 instructions at d = 128)
+//     MMA2   A_g += P_g . Y_t            (TMEM x SMEM -> TMEM, 128 x d fp32, K = the 128 streamed rows)
+// where P_g = 2^(c*S - ref) is produced straight from TMEM registers, rounded to bf16 and written back over S_g
+// (the A operand of MMA2 is read from TMEM: the softmax tile never touches shared or global memory).
 //
-//   PASS_FWD  rows stationary, items streamed: ref = lazily updated running row maximum;
-//             outputs per (row, split): (m, l = sum P, A = sum_j P_ij w_j)  -> lse and dU
+// TMEM map (512 columns): A_0 | A_1 (128 each, d of them used) | S_0 | S_1 (128 each): ONE score buffer per
+// stationary tile, so the chain of a tile is serial -- MMA1(t) -> softmax(t) -> MMA2(t) -> MMA1(t+1) -- and the
+// tensor pipe alternates between the two chains: while the epilogue turns S_0 into P_0 it runs MMA2_1 and the next
+// MMA1_1 (1024 clk at d = 128).  That only pays if the softmax of a 128 x 128 tile takes well under those 1024 clk,
+// which two warps per scheduler cannot do (round 1 measured such a design at 1.94 ms against 1.60 for 64-column
+// MMA1s with double-buffered S, although the N = 64 instructions waste 25 % of the tensor pipe: 48 clk for half the
+// work of a 64-clk N = 128 instruction, tests/probe_cta2.cu).  So the epilogue is FOUR warpgroups, two per
+// stationary tile, each taking 64 of the tile's 128 score columns (thread <-> TMEM lane <-> stationary row; the two
+// threads of a row sit in different warpgroups): four warps per scheduler hide each other's latencies and every
+// thread has half the work.  576 threads: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..17 =
+// epilogue warpgroups (g = stationary tile, ch = column half).
+//
+//   PASS_FWD  rows stationary, items streamed: ref = lazily updated running row maximum, agreed between the two
+//             threads of a row through shared memory once per tile; outputs per (row, split):
+//             (m, l = sum P, A = sum_j P_ij w_j)  -> lse and dU
 //   PASS_DW   items stationary, rows streamed: ref = lse of the streamed row (global softmax);
 //             outputs A = sum_i P_ij u_i -> dW (and row sums -> dbias)
 // The label one-hot never enters the tiles: dU subtracts w_label and dW subtracts u_i exactly, in
@@ -27,7 +35,7 @@
 namespace rb {
 
 enum : int { PASS_FWD = 0, PASS_DW = 1 };
-constexpr int PAIR_THREADS = 320;
+constexpr int PAIR_THREADS = 576;
 constexpr float PAIR_RESCALE_TH = 16.f;  // log2 units: P stays below 2^16 before the row reference moves
 // Every PAIR_POLY_EVERY-th element pair takes its exponentials from the FMA pipe (ex2_poly2) instead of
 // the MUFU unit; 0 = all on MUFU.  At 3 the MUFU load drops by a third and the pipes are about level.
@@ -75,10 +83,10 @@ struct PairCfg {
   static constexpr int DPAD = KC_ * 64;
   static constexpr int TILE_BYTES = KC_ * 128 * 128;  // one 128-row operand tile
   static constexpr int AUX_BYTES = 512;
-  static constexpr int CTRL_BYTES = 1024;
+  static constexpr int CTRL_BYTES = 1024 + 4096;      // barriers + the row exchange between the column halves
   static constexpr int SMEM_BYTES = (2 + NS_) * TILE_BYTES + NS_ * AUX_BYTES + CTRL_BYTES + 1024 /*align*/;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int ACC0 = 256, ACC1 = 256 + DPAD;
+  static constexpr int ACC0 = 0, ACC1 = 128, S0 = 256;   // S_g at S0 + 128 g
   static_assert(KC_ == 1 || KC_ == 2, "d <= 128");
   static_assert(SMEM_BYTES <= 227 * 1024, "SMEM budget");
 };
@@ -86,12 +94,15 @@ struct PairCfg {
 struct PairControl {
   uint64_t full[8], empty[8];
   uint64_t x_full, x_empty;
-  uint64_t s_full[2][2], p_full[2][2];   // [warpgroup][half]
-  uint64_t m2_done[2];                   // one completion per MMA2 of warpgroup g (rescale safety)
+  uint64_t s_full[2];                    // per stationary tile
+  uint64_t p_full[2][4];                 // per stationary tile and 32-column piece (column half * 2 + piece of the half)
+  uint64_t m2_done[2];                   // one completion per MMA2 of tile g (rescale safety)
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_base;
+  uint32_t pad_[31];
+  float xchg[2][2][2][128];              // [tile parity][g][column half][row]: hand-over between the two threads of a row
 };
-static_assert(sizeof(PairControl) <= 1024, "control block");
+static_assert(sizeof(PairControl) <= 1024 + 4096, "control block");
 
 // 1-D bulk copy global -> shared, completion on an mbarrier
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -114,6 +125,19 @@ static __device__ __noinline__ void pair_rescale_acc(uint32_t t_acc, int ncols, 
   tmem_st_wait();
 }
 
+// 16-byte shared-memory load by shared-window address (the aux vectors: a pointer derived from the dynamic shared
+// array through casts compiles to generic loads otherwise)
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
+// named barrier over the 256 epilogue threads of stationary tile g (ids 1, 2; id 0 is __syncthreads)
+__device__ __forceinline__ void pair_bar_sync(int g) { asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory"); }
+
+// 576 threads leave 96 registers per thread (the register file is handed out as if the CTA had 20 warps); the
+// epilogues below are written to fit without spilling.
 template <class C>
 __global__ void __launch_bounds__(PAIR_THREADS, 1)
 pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__ CUtensorMap tm_strm,
@@ -136,13 +160,11 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
     mbar_init(&bar->x_full, 1);
     mbar_init(&bar->x_empty, 1);
     for (int g = 0; g < 2; ++g) {
-      for (int h = 0; h < 2; ++h) {
-        mbar_init(&bar->s_full[g][h], 1);
-        mbar_init(&bar->p_full[g][h], 128);
-      }
+      mbar_init(&bar->s_full[g], 1);
+      for (int pz = 0; pz < 4; ++pz) mbar_init(&bar->p_full[g][pz], 128);
       mbar_init(&bar->m2_done[g], 1);
       mbar_init(&bar->acc_full[g], 1);
-      mbar_init(&bar->acc_empty[g], 128);
+      mbar_init(&bar->acc_empty[g], 256);
     }
     fence_barrier_init();
   }
@@ -197,18 +219,18 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
     // ========================================================================= MMA issuer
     // Warp-converged loop (descriptor arithmetic stays in uniform registers); one elected lane issues
     // the tcgen05.mma / commit instructions.
-    constexpr uint32_t idesc1 = make_idesc(FMT_BF16, 128, 64, 0, 0);
-    constexpr uint32_t idesc2 = make_idesc(FMT_BF16, 128, C::DPAD, 0, 1);  // A: P from TMEM, B: Y half MN-major
+    constexpr uint32_t idesc1 = make_idesc(FMT_BF16, 128, 128, 0, 0);
+    constexpr uint32_t idesc2 = make_idesc(FMT_BF16, 128, C::DPAD, 0, 1);  // A: P from TMEM, B: Y tile MN-major
     constexpr uint32_t dhi = smem_desc_hi(1024);
     const uint32_t x_lo = smem_desc_lo(smem_u32(x_smem), 16);
     const uint32_t y_lo1 = smem_desc_lo(smem_u32(y_smem), 16);      // K-major view of a streamed tile (MMA1)
     const uint32_t y_lo2 = smem_desc_lo(smem_u32(y_smem), 16384);   // MN-major view of the same tile (MMA2)
     uint32_t it = 0, k = 0;
 
-    // S_g[h] = X_g . Y_half^T   (rows [64h, 64h+64) of the streamed tile in stage st)
-    auto m1 = [&](int g, int h, uint32_t st) {
-      const uint32_t d_tmem = tmem_base + g * 128 + h * 64;
-      const uint32_t xg = x_lo + ((g * C::TILE_BYTES) >> 4), ys = y_lo1 + ((st * C::TILE_BYTES + h * 8192) >> 4);
+    // S_g = X_g . Y^T   (the streamed tile in stage st)
+    auto m1 = [&](int g, uint32_t st) {
+      const uint32_t d_tmem = tmem_base + C::S0 + g * 128;
+      const uint32_t xg = x_lo + ((g * C::TILE_BYTES) >> 4), ys = y_lo1 + ((st * C::TILE_BYTES) >> 4);
 #pragma unroll
       for (int c = 0; c < C::KC; ++c) {
 #pragma unroll
@@ -216,17 +238,17 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
           mma_f16_ss(d_tmem, smem_desc(dhi, xg + ((c * 16384 + kk * 32) >> 4)),
                      smem_desc(dhi, ys + ((c * 16384 + kk * 32) >> 4)), idesc1, (c | kk) != 0);
       }
-      tc_commit(&bar->s_full[g][h]);
+      tc_commit(&bar->s_full[g]);
     };
-    // A_g (+)= P_g[h] . Y_half      (P_g[h]: bf16 pairs in columns [0,32) of S_g[h])
-    auto m2 = [&](int g, int h, uint32_t st, bool first) {
+    // A_g (+)= P_g . Y for the 32 streamed rows of one piece (pz = column half * 2 + piece): two K = 16 steps.
+    // P_g: bf16 pairs; streamed rows [0,64) sit in columns [0,32) of S_g, rows [64,128) in [64,96).
+    auto m2_piece = [&](int g, int pz, uint32_t st, bool first) {
       const uint32_t d_tmem = tmem_base + (g == 0 ? C::ACC0 : C::ACC1);
-      const uint32_t a_tmem = tmem_base + g * 128 + h * 64;
-      const uint32_t ys = y_lo2 + ((st * C::TILE_BYTES + h * 8192) >> 4);
+      const uint32_t a_tmem = tmem_base + C::S0 + g * 128 + (pz >> 1) * 64 + (pz & 1) * 16;
+      const uint32_t ys = y_lo2 + ((st * C::TILE_BYTES + pz * 4096) >> 4);
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
+      for (int kk = 0; kk < 2; ++kk)
         mma_f16_ts(d_tmem, a_tmem + kk * 8, smem_desc(dhi, ys + ((kk * 2048) >> 4)), idesc2, !(first && kk == 0));
-      if (C::PASS == PASS_FWD) tc_commit(&bar->m2_done[g]);
     };
 
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++k) {
@@ -234,15 +256,14 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
       item_range(item, pt, split, t0, t1);
       const int n = t1 - t0;
       mbar_wait(&bar->x_full, k & 1);
-      {  // fill both S buffers of both warpgroups from the first streamed tile
+      {  // the first streamed tile of the item: both score buffers are free (the MMA2s of the previous item were issued
+         // before this point and the tensor pipe executes in order)
         const uint32_t st = it % C::NS, ph = (it / C::NS) & 1;
         mbar_wait(&bar->full[st], ph);
         tc_fence_after();
         if (elect_one()) {
-          m1(0, 0, st);
-          m1(1, 0, st);
-          m1(0, 1, st);
-          m1(1, 1, st);
+          m1(0, st);
+          m1(1, st);
           if (n == 1) tc_commit(&bar->x_empty);
         }
         __syncwarp();
@@ -250,38 +271,46 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
       for (int j = 0; j < n; ++j, ++it) {
         const uint32_t st = it % C::NS;
         const uint32_t st1 = (it + 1) % C::NS, ph1 = ((it + 1) / C::NS) & 1;
-        const uint32_t pph = it & 1;
         const bool more = j + 1 < n;
         if (more) mbar_wait(&bar->full[st1], ph1);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int g = 0; g < 2; ++g) {
+          if (j == 0) mbar_wait(&bar->acc_empty[g], (k & 1) ^ 1);
+          // the softmax pieces arrive in the order (half 0, piece 0), (half 1, piece 0), (half 0, piece 1), (half 1,
+          // piece 1) -- the two column halves work side by side -- and MMA2 starts on the first while the last are
+          // still being exponentiated
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            mbar_wait(&bar->p_full[g][h], pph);
-            if (j == 0 && h == 0) mbar_wait(&bar->acc_empty[g], (k & 1) ^ 1);
+          for (int o = 0; o < 4; ++o) {
+            const int pz = (o & 1) * 2 + (o >> 1);
+            mbar_wait(&bar->p_full[g][pz], it & 1);
             tc_fence_after();
-            if (elect_one()) {
-              m2(g, h, st, j == 0 && h == 0);
-              if (g == 1 && h == 1) tc_commit(&bar->empty[st]);   // every MMA on Y_j retires before this fires
-              if (!more && h == 1) tc_commit(&bar->acc_full[g]);
-              if (more) {
-                m1(g, h, st1);
-                if (g == 1 && h == 1 && j + 2 == n) tc_commit(&bar->x_empty);  // last use of X0/X1 in this item
-              }
-            }
+            if (elect_one()) m2_piece(g, pz, st, j == 0 && o == 0);
             __syncwarp();
           }
+          if (elect_one()) {
+            if (C::PASS == PASS_FWD) tc_commit(&bar->m2_done[g]);
+            if (g == 1) tc_commit(&bar->empty[st]);   // every MMA on Y_j retires before this fires
+            if (!more) tc_commit(&bar->acc_full[g]);
+            if (more) {
+              m1(g, st1);                              // in order behind MMA2_g: S_g / P_g is free again
+              if (g == 1 && j + 2 == n) tc_commit(&bar->x_empty);  // last use of X0/X1 in this item
+            }
+          }
+          __syncwarp();
         }
       }
     }
   } else {
     // =========================================================================== epilogue
-    const int g = (warp - 2) >> 2;     // warpgroup == stationary tile of the pair
+    const int wgi = (warp - 2) >> 2;   // epilogue warpgroup 0..3
+    const int g = wgi & 1;             // stationary tile of the pair
+    const int ch = wgi >> 1;           // column half of the score tile this warpgroup handles
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;       // row within the stationary tile == TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t t_s = tmem_base + lane_base + g * 128;
-    const uint32_t t_acc = tmem_base + lane_base + (g == 0 ? C::ACC0 : C::ACC1);
+    const uint32_t t_s = tmem_base + lane_base + C::S0 + g * 128 + ch * 64;   // this thread's 64 score columns; P goes to the first 32
+    constexpr int HALF = C::DPAD / 2;  // accumulator columns this thread rescales / writes out
+    const uint32_t t_acc = tmem_base + lane_base + (g == 0 ? C::ACC0 : C::ACC1) + ch * HALF;
     const float c2 = a.scale * 1.4426950408889634f;   // scale > 0 (checked on the host)
     uint32_t it = 0, k = 0;
 
@@ -291,81 +320,90 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
       const int srow = (pt * 2 + g) * 128 + r;   // global stationary row
       const bool srow_ok = srow < a.n_stat;
 
-      float m2 = 0.f, l = 0.f;      // FWD: row reference (log2 domain) and sum of P
+      float m2 = 0.f, l = 0.f;      // FWD: row reference (log2 domain) and this thread's share of sum P
       float nb = 0.f;               // DW: bias2 of this item row
-      float rowsum = 0.f;           // DW: sum_i P (dbias)
+      float rowsum = 0.f;           // DW: this thread's share of sum_i P (dbias)
       if (C::PASS == PASS_DW && C::BIAS) nb = srow_ok ? __ldg(a.bias2_stat + srow) : 0.f;
 
       for (int t = t0; t < t1; ++t, ++it) {
         const uint32_t st = it % C::NS;
-        const float4* aux4 = reinterpret_cast<const float4*>(aux_smem + st * 128);
+        const uint32_t aux_s = smem_u32(aux_smem + st * 128 + ch * 64);   // this thread's 64 aux values
         // the aux vector arrived with the tile (same mbarrier); the stage cannot be refilled before this
-        // warpgroup's last p_full arrival of the tile, so the phase is stable while we look at it
+        // warpgroup's p_full arrival of the tile, so the phase is stable while we look at it
         if (C::AUX) mbar_wait(&bar->full[st], (it / C::NS) & 1);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int col_base = t * 128 + h * 64;
-          const uint32_t t_sh = t_s + h * 64;
-          mbar_wait(&bar->s_full[g][h], it & 1);
-          tc_fence_after();
-          uint32_t raw[64];
-          tmem_ld32p(t_sh, raw);
-          tmem_ld32p(t_sh + 32, raw + 32);
-          tmem_ld_wait();
-
-          if (C::PASS == PASS_FWD) {
+        const int col_base = t * 128 + ch * 64;
+        mbar_wait(&bar->s_full[g], it & 1);
+        tc_fence_after();
+        if (C::PASS == PASS_FWD) {
+          // Two trips through the thread's 64 score columns, 32 at a time: first the row maximum (the reference has to
+          // be settled, and agreed with the row's other thread, before the first exponential), then the exponentials.
+          // Holding all 64 values instead needs more than the 96 registers a 576-thread CTA leaves per thread, and a
+          // spill here goes to L2 (200 KB of the SM's 256 KB are shared memory): measured 6.5 ms against 1.6.
+          const int n_valid = a.n_strm - col_base;   // < 64 only in the last, partial tile: columns beyond the catalog never count
+          auto load_piece = [&](int hf, uint32_t (&raw)[32]) {
+            tmem_ld32p(t_s + hf * 32, raw);
+            tmem_ld_wait();
             if (C::BIAS) {  // x = s*c2 + bias2[col]
 #pragma unroll
-              for (int c4 = 0; c4 < 16; ++c4) {
-                const float4 w = aux4[h * 16 + c4];
+              for (int c4 = 0; c4 < 8; ++c4) {
+                const float4 w = lds128(aux_s + (hf * 8 + c4) * 16);
                 raw[c4 * 4 + 0] = __float_as_uint(fmaf(__uint_as_float(raw[c4 * 4 + 0]), c2, w.x));
                 raw[c4 * 4 + 1] = __float_as_uint(fmaf(__uint_as_float(raw[c4 * 4 + 1]), c2, w.y));
                 raw[c4 * 4 + 2] = __float_as_uint(fmaf(__uint_as_float(raw[c4 * 4 + 2]), c2, w.z));
                 raw[c4 * 4 + 3] = __float_as_uint(fmaf(__uint_as_float(raw[c4 * 4 + 3]), c2, w.w));
               }
             }
-            const int n_valid = a.n_strm - col_base;
-            if (n_valid < 64) {  // last, partial tile: columns beyond the catalog never count
+            if (n_valid - hf * 32 < 32) {
 #pragma unroll
-              for (int c = 0; c < 64; ++c)
-                if (c >= n_valid) raw[c] = 0xff800000u;  // -inf
+              for (int c = 0; c < 32; ++c)
+                if (hf * 32 + c >= n_valid) raw[c] = 0xff800000u;  // -inf
             }
-            float mx[2];
+          };
+          float cm2 = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              mx[i] = fmax3(__uint_as_float(raw[i * 32]), __uint_as_float(raw[i * 32 + 1]), __uint_as_float(raw[i * 32 + 2]));
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t raw[32];
+            load_piece(hf, raw);
+            float mx = fmax3(__uint_as_float(raw[0]), __uint_as_float(raw[1]), __uint_as_float(raw[2]));
 #pragma unroll
-              for (int c = 3; c < 31; c += 2) mx[i] = fmax3(mx[i], __uint_as_float(raw[i * 32 + c]), __uint_as_float(raw[i * 32 + c + 1]));
-              mx[i] = fmaxf(mx[i], __uint_as_float(raw[i * 32 + 31]));
+            for (int c = 3; c < 31; c += 2) mx = fmax3(mx, __uint_as_float(raw[c]), __uint_as_float(raw[c + 1]));
+            cm2 = fmax3(cm2, mx, __uint_as_float(raw[31]));
+          }
+          if (!C::BIAS) cm2 *= c2;
+          // the two threads of a row (column halves, different warpgroups) agree on the tile maximum
+          bar->xchg[it & 1][g][ch][r] = cm2;
+          pair_bar_sync(g);
+          cm2 = fmaxf(cm2, bar->xchg[it & 1][g][ch ^ 1][r]);
+          if (t == t0) {
+            m2 = cm2;
+          } else {
+            const bool grow = cm2 > m2 + PAIR_RESCALE_TH;
+            if (__any_sync(0xffffffffu, grow)) {
+              // A_g must be quiescent.  MMA2 of the previous tile is the it-th completion of m2_done[g]
+              // (parity (it-1)&1); MMA2 of this tile cannot start before our p_full arrivals.
+              mbar_wait(&bar->m2_done[g], (it & 1) ^ 1);
+              tc_fence_after();
+              const float f = grow ? ex2_approx(m2 - cm2) : 1.f;
+              pair_rescale_acc(t_acc, HALF, f);   // this thread's half of the row's accumulator
+              l *= f;
+              if (grow) m2 = cm2;
             }
-            float cm2 = fmaxf(mx[0], mx[1]);
-            if (!C::BIAS) cm2 *= c2;
-            if (t == t0 && h == 0) {
-              m2 = cm2;
-            } else {
-              const bool grow = cm2 > m2 + PAIR_RESCALE_TH;
-              if (__any_sync(0xffffffffu, grow)) {
-                // A_g must be quiescent.  MMA2 of the previous step is the (2*it+h-1)-th completion of
-                // m2_done[g] (parity h^1); MMA2 of this step cannot start before our p_full arrival.
-                mbar_wait(&bar->m2_done[g], (h ^ 1) & 1);
-                tc_fence_after();
-                const float f = grow ? ex2_approx(m2 - cm2) : 1.f;
-                pair_rescale_acc(t_acc, C::DPAD, f);
-                l *= f;
-                if (grow) m2 = cm2;
-              }
-            }
-            const uint64_t nm2 = pack2(-m2, -m2), c22 = pack2(c2, c2);
-            uint64_t ls2[2] = {0ull, 0ull};   // two packed running sums (4 fp32 lanes)
+          }
+          const uint64_t nm2 = pack2(-m2, -m2), c22 = pack2(c2, c2);
+          uint64_t ls2[2] = {0ull, 0ull};   // two packed running sums (4 fp32 lanes)
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-              uint32_t pk[16];
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t raw[32];
+            load_piece(hf, raw);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const uint64_t xr = pack2(__uint_as_float(raw[ch * 32 + 2 * i]), __uint_as_float(raw[ch * 32 + 2 * i + 1]));
+            for (int pc = 0; pc < 2; ++pc) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint64_t xr = pack2(__uint_as_float(raw[pc * 16 + 2 * i]), __uint_as_float(raw[pc * 16 + 2 * i + 1]));
                 const uint64_t x2 = C::BIAS ? fadd2(xr, nm2) : ffma2(xr, c22, nm2);   // log2-domain argument
                 float e0, e1;
-                if (pair_use_poly(i)) {
+                if (pair_use_poly(pc * 8 + i)) {
                   ex2_poly2(x2, e0, e1);
                 } else {
                   float x0, x1;
@@ -376,30 +414,40 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
                 ls2[i & 1] = fadd2(ls2[i & 1], pack2(e0, e1));
                 pk[i] = pack_bf16x2(e0, e1);
               }
-              tmem_st16(t_sh + ch * 16, pk);
+              tmem_st8(t_s + hf * 16 + pc * 8, pk);
             }
-            {
-              float s0, s1, s2, s3;
-              unpack2(ls2[0], s0, s1);
-              unpack2(ls2[1], s2, s3);
-              l += (s0 + s1) + (s2 + s3);
-            }
-          } else {
-            // P^T[item r][query row c] = 2^(s*c2 + bias2_r + aux_c), aux_c = -lse2_c (-inf beyond the last row => 0)
-            const uint64_t c22 = pack2(c2, c2), nb2 = pack2(nb, nb);
-            uint64_t rs2[2] = {0ull, 0ull};
+            tmem_st_wait();   // a 32-column piece of P is complete: MMA2 may start on it
+            tc_fence_before();
+            mbar_arrive(&bar->p_full[g][ch * 2 + hf]);
+          }
+          {
+            float s0, s1, s2, s3;
+            unpack2(ls2[0], s0, s1);
+            unpack2(ls2[1], s2, s3);
+            l += (s0 + s1) + (s2 + s3);
+          }
+        } else {
+          // P^T[item r][query row c] = 2^(s*c2 + bias2_r + aux_c), aux_c = -lse2_c (-inf beyond the last row => 0).
+          // Element-wise, so the 64 columns go through the registers 32 at a time.
+          const uint64_t c22 = pack2(c2, c2), nb2 = pack2(nb, nb);
+          uint64_t rs2[2] = {0ull, 0ull};
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-              uint32_t pk[16];
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t raw[32];
+            tmem_ld32p(t_s + hf * 32, raw);
+            tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float4 w = aux4[h * 16 + ch * 8 + (i >> 1)];
+            for (int pc = 0; pc < 2; ++pc) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 w = lds128(aux_s + (hf * 8 + pc * 4 + (i >> 1)) * 16);
                 uint64_t off = (i & 1) ? pack2(w.z, w.w) : pack2(w.x, w.y);
                 if (C::BIAS) off = fadd2(off, nb2);
-                const uint64_t xr = pack2(__uint_as_float(raw[ch * 32 + 2 * i]), __uint_as_float(raw[ch * 32 + 2 * i + 1]));
+                const uint64_t xr = pack2(__uint_as_float(raw[pc * 16 + 2 * i]), __uint_as_float(raw[pc * 16 + 2 * i + 1]));
                 const uint64_t x2 = ffma2(xr, c22, off);
                 float e0, e1;
-                if (pair_use_poly(i)) {
+                if (pair_use_poly(pc * 8 + i)) {
                   ex2_poly2(x2, e0, e1);
                 } else {
                   float x0, x1;
@@ -410,22 +458,33 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
                 if (C::BIAS) rs2[i & 1] = fadd2(rs2[i & 1], pack2(e0, e1));   // row sums feed dbias only
                 pk[i] = pack_bf16x2(e0, e1);
               }
-              tmem_st16(t_sh + ch * 16, pk);
+              tmem_st8(t_s + hf * 16 + pc * 8, pk);
             }
-            if (C::BIAS) {
-              float s0, s1, s2, s3;
-              unpack2(rs2[0], s0, s1);
-              unpack2(rs2[1], s2, s3);
-              rowsum += (s0 + s1) + (s2 + s3);
-            }
+            tmem_st_wait();   // a 32-column piece of P is complete: MMA2 may start on it
+            tc_fence_before();
+            mbar_arrive(&bar->p_full[g][ch * 2 + hf]);
           }
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(&bar->p_full[g][h]);
-        }  // halves
+          if (C::BIAS) {
+            float s0, s1, s2, s3;
+            unpack2(rs2[0], s0, s1);
+            unpack2(rs2[1], s2, s3);
+            rowsum += (s0 + s1) + (s2 + s3);
+          }
+        }
       }  // tiles
 
-      // ---- per-item outputs: the accumulator row of this thread
+      // ---- per-item outputs: the two threads of a row first combine their partial sums (the column-half-1 thread
+      //      hands its share to the column-half-0 thread), then each writes its half of the accumulator row
+      if (C::PASS == PASS_FWD || C::BIAS) {
+        const uint32_t xb = (it & 1);   // the slot of the NEXT tile's parity: idle between two items
+        if (ch == 1) bar->xchg[xb][g][1][r] = (C::PASS == PASS_FWD) ? l : rowsum;
+        pair_bar_sync(g);
+        if (ch == 0) {
+          const float other = bar->xchg[xb][g][1][r];
+          if (C::PASS == PASS_FWD) l += other; else rowsum += other;
+        }
+        pair_bar_sync(g);   // the slot is free again before the next item's first tile uses it
+      }
       mbar_wait(&bar->acc_full[g], k & 1);
       tc_fence_after();
       float osc = 1.f;
@@ -439,15 +498,16 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
         o = (slot < a.n_strm) ? a.side + static_cast<long long>(slot) * a.d : nullptr;
       }
 #pragma unroll 1
-      for (int ch = 0; ch < C::DPAD / 32; ++ch) {
+      for (int cc = 0; cc < HALF / 32; ++cc) {
         uint32_t v[32];
-        tmem_ld32(t_acc + ch * 32, v);
+        tmem_ld32(t_acc + cc * 32, v);
         tmem_ld_wait();
+        const int col0 = ch * HALF + cc * 32;   // first accumulator column of this chunk
         if (bf16_out) {
           if (srow_ok) {
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
-              const int col = ch * 32 + c8 * 8;
+              const int col = col0 + c8 * 8;
               if (col < a.d) {  // d % 8 == 0 (checked on the host)
                 float w[8];
 #pragma unroll
@@ -466,7 +526,7 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
         } else if (srow_ok) {
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
-            const int col = ch * 32 + c4 * 4;
+            const int col = col0 + c4 * 4;
             if (col < a.d) {  // d % 8 == 0 (checked on the host)
               float4 w;
               w.x = __uint_as_float(v[c4 * 4 + 0]) * osc;
@@ -480,13 +540,15 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
       }
       tc_fence_before();
       mbar_arrive(&bar->acc_empty[g]);
-      if (C::PASS == PASS_FWD) {
-        const long long pslot = static_cast<long long>(split) * a.stat_pad + (pt * 2 + g) * 128 + r;
-        a.part_m2[pslot] = m2;
-        a.part_l[pslot] = l;
-      } else if (a.rowsum_out != nullptr && srow_ok) {
-        a.rowsum_out[static_cast<long long>(split) * a.n_stat + srow] =
-            rowsum * a.rscale * (a.gscale_dev != nullptr ? __ldg(a.gscale_dev) : 1.f);
+      if (ch == 0) {
+        if (C::PASS == PASS_FWD) {
+          const long long pslot = static_cast<long long>(split) * a.stat_pad + (pt * 2 + g) * 128 + r;
+          a.part_m2[pslot] = m2;
+          a.part_l[pslot] = l;
+        } else if (a.rowsum_out != nullptr && srow_ok) {
+          a.rowsum_out[static_cast<long long>(split) * a.n_stat + srow] =
+              rowsum * a.rscale * (a.gscale_dev != nullptr ? __ldg(a.gscale_dev) : 1.f);
+        }
       }
     }  // items
   }
