@@ -38,9 +38,13 @@ enum : int { PASS_FWD = 0, PASS_DW = 1 };
 constexpr int PAIR_THREADS = 576;
 constexpr float PAIR_RESCALE_TH = 16.f;  // log2 units: P stays below 2^16 before the row reference moves
 // Every PAIR_POLY_EVERY-th element pair takes its exponentials from the FMA pipe (ex2_poly2) instead of
-// the MUFU unit; 0 = all on MUFU.  At 3 the MUFU load drops by a third and the pipes are about level.
+// the MUFU unit; 0 = all on MUFU.  With four epilogue warpgroups the passes are bound by the latency of the serial
+// MMA1 -> softmax -> MMA2 chain, not by MUFU throughput: measured fwd+dU / dW 1.56 / 1.58 ms all-MUFU, 1.59 / 1.69 ms
+// with every third pair on the FMA pipe, 1.63 / 1.72 ms with every second -- fewer instructions win.  (A build whose
+// dW epilogue does no exponentials at all runs 1.60 ms: the softmax arithmetic is hidden; at 2.15 TFLOP executed per
+// pass, 1.55 ms is the rate the measured sustained cuBLAS bf16 figure, 1.41 PFLOP/s under the 1 kW cap, allows.)
 #ifndef PAIR_POLY_EVERY
-#define PAIR_POLY_EVERY 3
+#define PAIR_POLY_EVERY 0
 #endif
 __device__ __forceinline__ constexpr bool pair_use_poly(int i) { return PAIR_POLY_EVERY > 0 && (i % (PAIR_POLY_EVERY > 0 ? PAIR_POLY_EVERY : 1)) == PAIR_POLY_EVERY - 1; }
 
