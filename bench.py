@@ -188,17 +188,20 @@ def run_ours(args):
     row_start, row_end = sharded.shard_bounds(n_total, world, rank)
     n_shard = row_end - row_start
 
-    # ---- parameters (resident): this rank's shard of the item table, bf16 + its fp32 gradient
+    # ---- parameters (resident): this rank's shard of the item table as ONE bf16 parameter (n_shard + 1 rows, row 0 =
+    #      padding, SASRec/main.py:70-77) with its gradient buffer kept allocated, as a training loop that calls
+    #      optimizer.zero_grad(set_to_none=False) has it
     gw = torch.Generator(device=dev).manual_seed(1000 + rank)
-    W = synth.embeddings(n_shard, D, gw, dev, torch.bfloat16, gain=1.5).requires_grad_(True)
+    table = torch.cat([torch.zeros(1, D, dtype=torch.bfloat16, device=dev),
+                       synth.embeddings(n_shard, D, gw, dev, torch.bfloat16, gain=1.5)]).requires_grad_(True)
+    table.grad = torch.zeros_like(table)
+    W = table.detach()[1:]                                            # the scored view weight[NUM_PADS:] (:193)
     # ---- one batch of inputs (identical on every rank: queries are replicated)
     g = torch.Generator(device=dev).manual_seed(2026 + 3)
     U_train = synth.embeddings(ROWS, D, g, dev, torch.bfloat16, gain=1.5)
     labels = synth.zipf_ids(ROWS, n_total, g, dev)
     seqs = synth.sequences(ROWS, SEQ, n_shard, g, dev)               # ids into the local shard (+1 pad row)
-    table = torch.cat([torch.zeros(1, D, dtype=torch.bfloat16, device=dev), W.detach()])  # (n_shard+1, d), row 0 = pad
-    gather_grad = synth.embeddings(ROWS * SEQ, D, g, dev, torch.bfloat16, gain=0.01)
-    table_grad = torch.zeros(n_shard + 1, D, dtype=torch.float32, device=dev)
+    gather_grad = synth.embeddings(ROWS * SEQ, D, g, dev, torch.bfloat16, gain=0.01).view(ROWS, SEQ, D)
     U_eval = synth.embeddings(ROWS, D, g, dev, torch.bfloat16, gain=1.5)
     seen_crow, seen_col = synth.seen_csr(ROWS, n_total, g, dev)
     tgt = synth.targets(ROWS, n_total, g, dev, (seen_crow, seen_col))
@@ -206,20 +209,21 @@ def run_ours(args):
     monitors = ["HITRATE@1", "HITRATE@5", "HITRATE@10", "HITRATE@20", "HITRATE@50", "NDCG@5", "NDCG@10", "NDCG@20", "NDCG@50"]
 
     def hot_path(U_tr, lab, sq, U_ev, s_crow, s_col):
-        """One pass of the path through the public API (recboard_b200.ops / .sharded)."""
-        emb = ops.gather_rows_raw(table, sq)                                      # a2
+        """One pass of the path through the public API (recboard_b200.ops / .sharded), gradients through autograd:
+        the table's gradient -- the gather's scatter-add rows plus the scoring head's dW -- ends up in table.grad."""
+        table.grad.zero_()                                                        # zero_grad(set_to_none=False)
+        emb = ops.gather_rows(table, sq, padding_idx=0, accumulate=True)          # a2
         Uq = U_tr.detach().requires_grad_(True)
-        W.grad = None
         if world > 1:
-            loss = sharded.sharded_fused_ce(Uq, W, lab, row_start)                # a5+a6 (+ all-gather)
+            loss = sharded.sharded_fused_ce(Uq, table, lab, row_start, n_skip=1, accumulate=True)   # a5+a6 (+ all-gather)
         else:
-            loss = ops.fused_ce(Uq, W, lab)
-        loss.backward()                                                           # a7 (+ all-reduce of dU)
-        ops.scatter_add_rows_(table_grad, gather_grad, sq.view(-1), padding_idx=0)  # a3
+            loss = ops.fused_ce(Uq, table, lab, n_skip=1, accumulate=True)
+        # a7 (+ all-reduce of dU) and a3: gather_grad stands in for what the encoder's backward hands to the gathered rows
+        torch.autograd.backward([loss, emb], [None, gather_grad])
         if world > 1:
-            vals, ids = sharded.sharded_topk(U_ev, W.detach(), TOPK, row_start, s_crow, s_col)  # a8-a10
+            vals, ids = sharded.sharded_topk(U_ev, W, TOPK, row_start, s_crow, s_col)  # a8-a10
         else:
-            vals, ids = ops.topk_eval(U_ev, W.detach(), TOPK, s_crow, s_col)
+            vals, ids = ops.topk_eval(U_ev, W, TOPK, s_crow, s_col)
         return loss, ids, emb
 
     def barrier():
@@ -374,7 +378,9 @@ def run_ours(args):
     breakdown = None
     roofline = None
     if rank == 0:
-        Wd = W.detach()
+        Wd = W
+        table_grad = torch.zeros(n_shard + 1, D, dtype=torch.bfloat16, device=dev)
+        gather_flat = gather_grad.view(-1, D)
         with torch.no_grad():
             m_, l_, ll_ = ops.ce_rowstats(U_train, Wd, labels, label_base=row_start)
             lse = m_ + torch.log(l_)
@@ -383,8 +389,8 @@ def run_ours(args):
             t_dW = time_op(lambda: ops.ce_backward(U_train, Wd, labels, lse, 1.0 / ROWS, label_base=row_start, need_dU=False,
                                                    need_dW=True, dw_dtype=torch.bfloat16))   # what the step runs: bf16 gradient rows
             t_topk = time_op(lambda: ops.topk_eval(U_eval, Wd, TOPK, seen_crow, seen_col, id_base=row_start))
-            t_gather = time_op(lambda: ops.gather_rows_raw(table, seqs))
-            t_scatter = time_op(lambda: ops.scatter_add_rows_(table_grad, gather_grad, seqs.view(-1), padding_idx=0))
+            t_gather = time_op(lambda: ops.gather_rows_raw(table.detach(), seqs))
+            t_scatter = time_op(lambda: ops.scatter_add_rows_(table_grad, gather_flat, seqs.view(-1), padding_idx=0))
         flop_tile = 2.0 * ROWS * n_shard * D   # one (rows x items x d) contraction
         breakdown = {
             "ce_fwd_dU_ms": t_fwd, "ce_bwd_dW_ms": t_dW, "ce_stats_only_ms": t_stats, "topk_ms": t_topk, "gather_ms": t_gather,

@@ -57,6 +57,14 @@ int rb_scatter_add_rows(const void* grad_out, const int64_t* idx, float* grad_ta
                         int64_t n_rows, int d, int dtype, int64_t padding_idx, void* ws,
                         size_t ws_bytes, rb_stream_t stream);
 
+/* Same, accumulating into a table gradient of either dtype (table_dtype = RB_DTYPE_F32 | RB_DTYPE_BF16): the
+ * embedding gradient of a bf16 parameter is added in place -- read, fp32 add, one rounding per touched row -- instead
+ * of through a dense fp32 (n_rows, d) matrix and a cast pass (what ATen's embedding_dense_backward + autograd's
+ * accumulation do for the reference, SASRec/main.py:183,249). */
+int rb_scatter_add_rows_into(const void* grad_out, const int64_t* idx, void* grad_table, int64_t n_idx,
+                             int64_t n_rows, int d, int dtype, int table_dtype, int64_t padding_idx, void* ws,
+                             size_t ws_bytes, rb_stream_t stream);
+
 /* S[m,k] = scale * <U[m,:], table[idx[m,k],:]> (fp32), ids outside [0,n_rows) score 0.  The gathered
  * (M,K,d) tensor is never materialised.  Replaces the gather + row-wise dot of every sampled / pool path:
  * `itemEmbds[data[IUnseen]]` + einsum("BD,BKD->BK") (recommend_from_pool, SASRec/main.py:230-236,
@@ -141,6 +149,16 @@ int rb_ce_bwd_dw_bf16(const void* U, const void* W, const float* bias, float sca
                       int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
                       int64_t M, int64_t N, int d, void* dW_bf16, float* dbias, void* ws, size_t ws_bytes,
                       rb_stream_t stream);
+
+/* The same pass ADDING its rows to what dW_bf16 already holds: dW_bf16 is the parameter's existing gradient buffer
+ * (e.g. already carrying the embedding gather's rows), so the scoring head's dW and the gather's scatter-add end up
+ * in ONE (N+P,d) gradient, as in the reference's autograd (SASRec/main.py:183,217,249), without a separate
+ * gradient tensor and an accumulation pass over it.  RB_E_UNSUPPORTED when the direct bf16 pass does not apply
+ * (several splits of the query range, or M > 16384): accumulate on the caller's side then. */
+int rb_ce_bwd_dw_bf16_acc(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
+                          int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
+                          int64_t M, int64_t N, int d, void* dW_bf16, float* dbias, void* ws, size_t ws_bytes,
+                          rb_stream_t stream);
 
 /* Masked full-catalog top-K: for every query row the K best (score desc, id asc) items among this
  * shard's N items, skipping ids in the row's seen list (CSR over GLOBAL ids, sorted ascending per

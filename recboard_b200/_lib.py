@@ -26,6 +26,7 @@ SIGNATURES = {
     "rb_gather_rows": (_i32, [_p, _p, _p, _i64, _i64, _i32, _i32, _p]),
     "rb_normalize_rows": (_i32, [_p, _p, _p, _i64, _i32, _i32, _i32, _f32, _p]),
     "rb_scatter_add_rows": (_i32, [_p, _p, _p, _i64, _i64, _i32, _i32, _i64, _p, _sz, _p]),
+    "rb_scatter_add_rows_into": (_i32, [_p, _p, _p, _i64, _i64, _i32, _i32, _i32, _i64, _p, _sz, _p]),
     "rb_gather_dot": (_i32, [_p, _p, _p, _f32, _p, _i64, _i64, _i64, _i32, _i32, _p]),
     "rb_gather_dot_bwd": (_i32, [_p, _p, _p, _p, _f32, _p, _p, _i64, _i64, _i64, _i32, _i32, _i64, _p, _sz, _p]),
     "rb_spmm_csr": (_i32, [_p, _p, _p, _p, _p, _p, _f32, _i64, _i64, _i32, _p]),
@@ -34,6 +35,7 @@ SIGNATURES = {
     "rb_ce_du_finish": (_i32, [_p, _p, _p, _p, _p, _i64, _f32, _f32, _p, _i64, _i64, _i32, _i32, _p, _p]),
     "rb_ce_bwd": (_i32, [_p, _p, _p, _f32, _p, _i64, _p, _f32, _p, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _sz, _p]),
     "rb_ce_bwd_dw_bf16": (_i32, [_p, _p, _p, _f32, _p, _i64, _p, _f32, _p, _i64, _i64, _i32, _p, _p, _p, _sz, _p]),
+    "rb_ce_bwd_dw_bf16_acc": (_i32, [_p, _p, _p, _f32, _p, _i64, _p, _f32, _p, _i64, _i64, _i32, _p, _p, _p, _sz, _p]),
     "rb_topk_eval": (_i32, [_p, _p, _p, _f32, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _p, _p, _p, _sz, _p]),
     "rb_topk_debug_layout": (_i32, [_i64, _i64, _i32, _i32, _i32, _i64, _p]),
     "rb_topk_hits": (_i32, [_p, _p, _p, _i64, _i32, _p, _p]),
@@ -62,6 +64,9 @@ def lib() -> C.CDLL:
             fn.restype, fn.argtypes = res, args
         _lib = h
     return _lib
+
+
+E_UNSUPPORTED = -3
 
 
 def check(code: int, what: str) -> None:

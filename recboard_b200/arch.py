@@ -40,10 +40,24 @@ class FusedFullCatalogMixin:
         non-item rows (BERT4Rec's pad/mask columns, BERT4Rec/main.py:189)."""
         raise NotImplementedError
 
+    def _whole_table(self, W: torch.Tensor) -> Tuple[torch.Tensor, int]:
+        """``W`` is ``self.Item.embeddings.weight[NUM_PADS:]`` itself (SASRec/main.py:193)?  Then hand ``fused_ce`` the
+        parameter and the number of pad rows, so that the table gradient comes back as ONE (N+P,d) tensor."""
+        weight = getattr(getattr(getattr(self, "Item", None), "embeddings", None), "weight", None)
+        P = int(getattr(self, "NUM_PADS", 0))
+        if (weight is not None and P > 0 and W.dim() == 2 and W._base is weight and W.is_contiguous()
+                and W.shape == (weight.shape[0] - P, weight.shape[1])
+                and W.data_ptr() == weight.data_ptr() + P * weight.stride(0) * weight.element_size()):
+            return weight, P
+        return W, 0
+
     # -- RecSysArch contract ------------------------------------------------------------
     def fit(self, data: Dict) -> Dict[str, torch.Tensor]:
         U, W, labels, bias, scale = self._train_operands(data)
-        return {"rec_loss": ops.fused_ce(U, W, labels, bias=bias, scale=scale, precision=self.fused_precision)}
+        n_skip = 0
+        if bias is None:
+            W, n_skip = self._whole_table(W)
+        return {"rec_loss": ops.fused_ce(U, W, labels, bias=bias, scale=scale, precision=self.fused_precision, n_skip=n_skip)}
 
     def recommend_from_full(self, data: Dict) -> torch.Tensor:
         U, W, bias, scale, n_skip = self._eval_operands(data)
@@ -204,6 +218,30 @@ class LightGCNFused(GenRecFused):
             allEmbds = ops.spmm(self.Adj, allEmbds, symmetric=True)
             avgEmbds = avgEmbds + allEmbds / (self.num_layers + 1)
         return torch.split(avgEmbds, (self.User.count, self.Item.count))
+
+
+class FusedEmbedding(torch.nn.Embedding):
+    """``nn.Embedding`` whose lookup and dense backward run through ``rb_gather_rows`` / the one-launch deterministic
+    scatter-add (``self.Item.embeddings(seqs)``, SASRec/main.py:183, and its autograd at :249).  With
+    ``accumulate_grad=True`` the backward adds the rows straight into ``weight.grad`` once that buffer exists
+    (``zero_grad(set_to_none=False)``): no fresh dense (N+P,d) gradient per step."""
+
+    accumulate_grad: bool = False
+
+    def forward(self, idx: torch.Tensor) -> torch.Tensor:
+        pad = -1 if self.padding_idx is None else int(self.padding_idx)
+        return ops.gather_rows(self.weight, idx, padding_idx=pad, accumulate=self.accumulate_grad)
+
+
+def fuse_item_embedding(model, accumulate_grad: bool = False):
+    """Swap ``model.Item.embeddings`` for a ``FusedEmbedding`` that shares the same weight Parameter (state_dict keys
+    and optimizer state are unaffected)."""
+    old = model.Item.embeddings
+    new = FusedEmbedding(old.num_embeddings, old.embedding_dim, padding_idx=old.padding_idx, device="meta")
+    new.weight = old.weight
+    new.accumulate_grad = accumulate_grad
+    model.Item.embeddings = new
+    return model
 
 
 def normalized_table(weight: torch.Tensor, num_pads: int = 1, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:

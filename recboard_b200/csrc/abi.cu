@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -11,6 +12,7 @@
 #include "sweep.cuh"
 #include "pair.cuh"
 #include "simt.cuh"
+#include "scatter.cuh"
 #include "f32grad.cuh"
 #include "launch.cuh"
 
@@ -239,62 +241,65 @@ extern "C" int rb_normalize_rows(const void* x, void* out, float* inv_norm, int6
 }
 
 // ======================================================================= scatter-add
+static int scatter_passes(long long n_rows) {
+  int bits = 1;
+  while ((1ull << bits) <= static_cast<unsigned long long>(n_rows)) ++bits;  // keys in [0, n_rows]
+  return (bits + RS_BITS - 1) / RS_BITS;
+}
 static size_t scatter_ws_bytes(long long n_idx, int d) {
   const long long chunks = (n_idx + RS_CHUNK - 1) / RS_CHUNK;
   const long long blocks = (n_idx + SEG_BLOCK - 1) / SEG_BLOCK;
-  return static_cast<size_t>(n_idx) * 4 * 4 + static_cast<size_t>(chunks) * 256 * 4 +
-         2 * static_cast<size_t>(blocks) * d * 4 + 256 * 4 + 10 * 256;
+  return static_cast<size_t>(n_idx) * 4 * 4 + static_cast<size_t>(chunks) * RS_BINS * 4 + 3 * RS_BINS * 4 +
+         2 * static_cast<size_t>(blocks) * d * 4 + 10 * 256;
 }
-// grad_table[idx[i]-idx_base] += alpha*(*alpha_dev) * grad_out[i] in a fixed order; optionally
-// cnt_out[row] += cnt_alpha*(*alpha_dev) * (#occurrences of row)
-static int scatter_add_impl(const void* grad_out, const int64_t* idx, long long idx_base, float* grad_table,
+template <typename T, typename TG>
+static int scatter_launch(const ScatterArgs& a, int sms, cudaStream_t st) {
+  auto kern = scatter_add_coop_kernel<T, TG>;
+  RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM_BYTES));
+  int per_sm = 0;
+  RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SC_THREADS, SC_SMEM_BYTES));
+  if (per_sm < 1) return fail(RB_E_UNSUPPORTED, "scatter_add_coop_kernel does not fit on this device");
+  // enough co-resident blocks for the widest phase (one warp per 32 sorted positions), never more than fit at once
+  const long long want = (static_cast<long long>(a.n) + SEG_BLOCK * SC_WARPS - 1) / (SEG_BLOCK * SC_WARPS);
+  int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want, 1ll * per_sm * sms)));
+  if (const char* e = getenv("RB_SCATTER_GRID")) grid = std::max(1, std::min(atoi(e), per_sm * sms));   // tuning hook
+  void* params[] = {const_cast<ScatterArgs*>(&a)};
+  RB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(grid), dim3(SC_THREADS), params, SC_SMEM_BYTES, st));
+  RB_LAUNCH_CHECK("scatter_add_coop_kernel");
+  return 0;
+}
+// dst[idx[i]-idx_base] += alpha*(*alpha_dev) * ew[i] * src[i / row_div] in a fixed order; optionally
+// cnt_out[row] += cnt_alpha*(*alpha_dev) * (#occurrences of row).  dst is fp32 or bf16 (dst_dtype).
+static int scatter_add_impl(const void* grad_out, const int64_t* idx, long long idx_base, void* grad_table,
                             int64_t n_idx, int64_t n_rows, int d, int dtype, int64_t padding_idx, float alpha,
                             const float* alpha_dev, float* cnt_out, float cnt_alpha, void* ws, size_t ws_bytes,
-                            cudaStream_t st, int row_div = 1, const float* ew = nullptr) {
+                            cudaStream_t st, int row_div = 1, const float* ew = nullptr, int dst_dtype = RB_DTYPE_F32) {
   if (!grad_out || !idx || !grad_table) return fail(RB_E_ARG, "null pointer");
   if (n_idx < 0 || n_rows <= 0 || d <= 0 || d % 4) return fail(RB_E_ARG, "bad shape (d must be a multiple of 4)");
   if (n_idx >= (1ll << 31) || n_rows >= (1ll << 32) - 1) return fail(RB_E_ARG, "n_idx/n_rows too large");
   if (n_idx == 0) return 0;
   if (!ws || ws_bytes < scatter_ws_bytes(n_idx, d)) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", scatter_ws_bytes(n_idx, d));
+  DevInfo dv; if (int r = get_dev(dv)) return r;
   Bump b(ws, ws_bytes);
   const int n = static_cast<int>(n_idx);
   const int chunks = (n + RS_CHUNK - 1) / RS_CHUNK;
-  uint32_t* k0 = b.take<uint32_t>(n); uint32_t* v0 = b.take<uint32_t>(n);
-  uint32_t* k1 = b.take<uint32_t>(n); uint32_t* v1 = b.take<uint32_t>(n);
-  uint32_t* hist = b.take<uint32_t>(static_cast<size_t>(chunks) * 256);
-  uint32_t* totals = b.take<uint32_t>(256);
   const int seg_blocks = (n + SEG_BLOCK - 1) / SEG_BLOCK;
-  float* lead = b.take<float>(static_cast<size_t>(seg_blocks) * d);
-  float* trail = b.take<float>(static_cast<size_t>(seg_blocks) * d);
-  rs_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(idx, idx_base, k0, v0, n, n_rows, padding_idx);
-  RB_LAUNCH_CHECK("rs_init_kernel");
-  int bits = 1;
-  while ((1ull << bits) <= static_cast<unsigned long long>(n_rows)) ++bits;  // keys in [0, n_rows]
-  for (int shift = 0; shift < bits; shift += 8) {
-    rs_hist_kernel<<<chunks, 256, 0, st>>>(k0, n, shift, hist, chunks);
-    RB_LAUNCH_CHECK("rs_hist_kernel");
-    if (chunks <= 256) {   // small: one block scans everything
-      rs_scan_kernel<<<1, 1024, 0, st>>>(hist, chunks * 256);
-      RB_LAUNCH_CHECK("rs_scan_kernel");
-    } else {               // large: one block per digit, coalesced
-      rs_digit_totals_kernel<<<256, 256, 0, st>>>(hist, chunks, totals);
-      RB_LAUNCH_CHECK("rs_digit_totals_kernel");
-      rs_scan_rows_kernel<<<256, 256, 0, st>>>(hist, chunks, totals);
-      RB_LAUNCH_CHECK("rs_scan_rows_kernel");
-    }
-    rs_scatter_kernel<<<(chunks + RS_SCATTER_WARPS - 1) / RS_SCATTER_WARPS, 32 * RS_SCATTER_WARPS, 0, st>>>(k0, v0, k1, v1, n, shift, hist, chunks);
-    RB_LAUNCH_CHECK("rs_scatter_kernel");
-    std::swap(k0, k1); std::swap(v0, v1);
-  }
-  const int grid = (seg_blocks + 3) / 4;   // 4 warps (blocks of 32 sorted positions) per CTA
-  if (dtype == RB_DTYPE_BF16)
-    scatter_segments_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(k0, v0, static_cast<const __nv_bfloat16*>(grad_out), grad_table, n, d, n_rows, alpha, alpha_dev, cnt_out, cnt_alpha, lead, trail, row_div, ew);
-  else
-    scatter_segments_kernel<float><<<grid, 128, 0, st>>>(k0, v0, static_cast<const float*>(grad_out), grad_table, n, d, n_rows, alpha, alpha_dev, cnt_out, cnt_alpha, lead, trail, row_div, ew);
-  RB_LAUNCH_CHECK("scatter_segments_kernel");
-  scatter_split_runs_kernel<<<grid, 128, 0, st>>>(k0, grad_table, n, d, n_rows, alpha, alpha_dev, cnt_out, cnt_alpha, lead, trail);
-  RB_LAUNCH_CHECK("scatter_split_runs_kernel");
-  return 0;
+  ScatterArgs a{};
+  a.src = grad_out; a.idx = idx; a.idx_base = idx_base; a.dst = grad_table; a.n = n; a.n_rows = n_rows; a.d = d;
+  a.padding_idx = padding_idx; a.alpha = alpha; a.alpha_dev = alpha_dev; a.cnt_out = cnt_out; a.cnt_alpha = cnt_alpha;
+  a.row_div = row_div; a.ew = ew; a.passes = scatter_passes(n_rows);
+  a.k0 = b.take<uint32_t>(n); a.v0 = b.take<uint32_t>(n); a.k1 = b.take<uint32_t>(n); a.v1 = b.take<uint32_t>(n);
+  a.hist = b.take<uint32_t>(static_cast<size_t>(chunks) * RS_BINS);
+  a.totals = b.take<uint32_t>(3 * RS_BINS);
+  a.lead = b.take<float>(static_cast<size_t>(seg_blocks) * d);
+  a.trail = b.take<float>(static_cast<size_t>(seg_blocks) * d);
+  if (!b.ok() || a.passes > 3) return fail(RB_E_WORKSPACE, "scatter workspace layout");
+  RB_CUDA(cudaMemsetAsync(a.totals, 0, static_cast<size_t>(a.passes) * RS_BINS * 4, st));
+  const bool sb = dtype == RB_DTYPE_BF16, db = dst_dtype == RB_DTYPE_BF16;
+  if (sb && db) return scatter_launch<__nv_bfloat16, __nv_bfloat16>(a, dv.sms, st);
+  if (sb) return scatter_launch<__nv_bfloat16, float>(a, dv.sms, st);
+  if (db) return scatter_launch<float, __nv_bfloat16>(a, dv.sms, st);
+  return scatter_launch<float, float>(a, dv.sms, st);
 }
 extern "C" int rb_scatter_add_rows(const void* grad_out, const int64_t* idx, float* grad_table, int64_t n_idx,
                                    int64_t n_rows, int d, int dtype, int64_t padding_idx, void* ws, size_t ws_bytes,
@@ -302,6 +307,15 @@ extern "C" int rb_scatter_add_rows(const void* grad_out, const int64_t* idx, flo
   DevInfo dv; if (int r = get_dev(dv)) return r;
   return scatter_add_impl(grad_out, idx, 0, grad_table, n_idx, n_rows, d, dtype, padding_idx, 1.f, nullptr, nullptr, 0.f,
                           ws, ws_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int rb_scatter_add_rows_into(const void* grad_out, const int64_t* idx, void* grad_table, int64_t n_idx,
+                                        int64_t n_rows, int d, int dtype, int table_dtype, int64_t padding_idx, void* ws,
+                                        size_t ws_bytes, rb_stream_t stream) {
+  DevInfo dv; if (int r = get_dev(dv)) return r;
+  if (table_dtype != RB_DTYPE_F32 && table_dtype != RB_DTYPE_BF16) return fail(RB_E_ARG, "unknown table dtype %d", table_dtype);
+  if (table_dtype == RB_DTYPE_BF16 && (d % 4 || (reinterpret_cast<uintptr_t>(grad_table) & 7))) return fail(RB_E_ALIGN, "bf16 table rows must be 8-byte aligned");
+  return scatter_add_impl(grad_out, idx, 0, grad_table, n_idx, n_rows, d, dtype, padding_idx, 1.f, nullptr, nullptr, 0.f,
+                          ws, ws_bytes, reinterpret_cast<cudaStream_t>(stream), 1, nullptr, table_dtype);
 }
 
 // ========================================================================= gather-dot
@@ -503,7 +517,7 @@ extern "C" int rb_ce_du_finish(const float* dU_unnorm, const float* row_max, con
 static int ce_bwd_dw_pair(const DevInfo& dv, const void* U, const void* W, const float* bias, float scale,
                           const int64_t* labels, int64_t label_base, const float* lse2, float grad_scale,
                           const float* grad_scale_dev, int64_t M, int64_t N, int d, float* dW, float* dbias, Bump& b,
-                          cudaStream_t st, __nv_bfloat16* dW_bf16 = nullptr) {
+                          cudaStream_t st, __nv_bfloat16* dW_bf16 = nullptr, bool accumulate = false) {
   Plan p = make_plan(N, M, dv.sms, 64, 8, 256);
   const long long n_pad = 1ll * p.n_stat_tiles * 256;
   // One-hot correction: up to LABEL_FIX_MAX query rows without a sort (label_owner + label_fix), beyond that
@@ -513,6 +527,8 @@ static int ce_bwd_dw_pair(const DevInfo& dv, const void* U, const void* W, const
   constexpr long long LABEL_FIX_MAX = 16384;
   const bool small_fix = M <= LABEL_FIX_MAX;
   const bool direct_bf16 = dW_bf16 != nullptr && p.n_splits == 1 && small_fix;
+  if (accumulate && !direct_bf16)
+    return fail(RB_E_UNSUPPORTED, "in-place accumulation needs the direct bf16 pass (one split of the query range, M <= 16384)");
   if (dW_bf16 != nullptr && !direct_bf16) dW = b.take<float>(static_cast<size_t>(N) * d);
   int* first_of = nullptr; float* side = nullptr;
   if (small_fix) {
@@ -540,7 +556,7 @@ static int ce_bwd_dw_pair(const DevInfo& dv, const void* U, const void* W, const
   a.n_stat = (int)N; a.n_strm = (int)M; a.n_pair_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
   a.n_splits = p.n_splits; a.d = d; a.stat_pad = (int)n_pad; a.scale = scale; a.bias2_stat = bias2; a.aux = lse2;
   a.gscale = grad_scale * scale; a.rscale = grad_scale; a.gscale_dev = grad_scale_dev; a.acc_out = part; a.rowsum_out = rs_part;
-  if (direct_bf16) { a.out_bf16 = dW_bf16; a.slot_of_row = first_of; a.side = side; }
+  if (direct_bf16) { a.out_bf16 = dW_bf16; a.slot_of_row = first_of; a.side = side; a.accumulate = accumulate ? 1 : 0; }
   if (int r = launch_pair_dw(kc_for(d, RB_MODE_BF16), bias_cfg, ts, ty, a, p.grid, st)) return r;
   if (p.n_splits > 1) {
     const long long n = N * d;
@@ -675,7 +691,7 @@ static int ce_bwd_f32(const DevInfo& dv, const float* U, const float* W, const f
 static int ce_bwd_impl(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
                        int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
                        int64_t M, int64_t N, int d, int dtype, int mode, float* dU, float* dW, float* dbias,
-                       void* ws, size_t ws_bytes, rb_stream_t stream, void* dW_bf16);
+                       void* ws, size_t ws_bytes, rb_stream_t stream, void* dW_bf16, bool accumulate = false);
 
 extern "C" int rb_ce_bwd(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
                          int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
@@ -695,10 +711,20 @@ extern "C" int rb_ce_bwd_dw_bf16(const void* U, const void* W, const float* bias
                      RB_MODE_BF16, nullptr, nullptr, dbias, ws, ws_bytes, stream, dW_bf16);
 }
 
+extern "C" int rb_ce_bwd_dw_bf16_acc(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
+                                     int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
+                                     int64_t M, int64_t N, int d, void* dW_bf16, float* dbias, void* ws, size_t ws_bytes,
+                                     rb_stream_t stream) {
+  if (!dW_bf16) return fail(RB_E_ARG, "null output");
+  if (reinterpret_cast<uintptr_t>(dW_bf16) & 15) return fail(RB_E_ALIGN, "dW must be 16-byte aligned");
+  return ce_bwd_impl(U, W, bias, scale, labels, label_base, lse, grad_scale, grad_scale_dev, M, N, d, RB_DTYPE_BF16,
+                     RB_MODE_BF16, nullptr, nullptr, dbias, ws, ws_bytes, stream, dW_bf16, true);
+}
+
 static int ce_bwd_impl(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
                        int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
                        int64_t M, int64_t N, int d, int dtype, int mode, float* dU, float* dW, float* dbias,
-                       void* ws, size_t ws_bytes, rb_stream_t stream, void* dW_bf16) {
+                       void* ws, size_t ws_bytes, rb_stream_t stream, void* dW_bf16, bool accumulate) {
   DevInfo dv; if (int r = get_dev(dv)) return r;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (int r = check_common(U, W, M, N, d, dtype, mode)) return r;
@@ -732,7 +758,7 @@ static int ce_bwd_impl(const void* U, const void* W, const float* bias, float sc
     lse2_kernel<<<(int)((m_pad + 255) / 256), 256, 0, st>>>(lse, lse2, (int)M, (int)m_pad);
     RB_LAUNCH_CHECK("lse2_kernel");
     return ce_bwd_dw_pair(dv, U, W, bias, scale, labels, label_base, lse2, grad_scale, grad_scale_dev, M, N, d, dW, dbias, b, st,
-                          static_cast<__nv_bfloat16*>(dW_bf16));
+                          static_cast<__nv_bfloat16*>(dW_bf16), accumulate);
   }
   return 0;
 }

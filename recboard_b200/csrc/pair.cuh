@@ -77,6 +77,7 @@ struct PairArgs {
   void* out_bf16;              // [n_stat][d] bf16, nullable
   const int* slot_of_row;      // [n_stat]
   float* side;                 // [n_slots][d]
+  int accumulate;              // bf16 output only: rows are ADDED to what out_bf16 already holds (the parameter's existing gradient)
 };
 
 template <int PASS_, int KC_, int NS_, bool BIAS_>
@@ -516,6 +517,13 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
                 float w[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) w[e] = __uint_as_float(v[c8 * 8 + e]) * osc;
+                if (a.accumulate) {   // kernel-uniform: the gradient buffer already holds a value (e.g. the gather's rows)
+                  const uint4 old = *reinterpret_cast<const uint4*>(ob + (col >> 1));
+                  w[0] += __uint_as_float(old.x << 16); w[1] += __uint_as_float(old.x & 0xFFFF0000u);
+                  w[2] += __uint_as_float(old.y << 16); w[3] += __uint_as_float(old.y & 0xFFFF0000u);
+                  w[4] += __uint_as_float(old.z << 16); w[5] += __uint_as_float(old.z & 0xFFFF0000u);
+                  w[6] += __uint_as_float(old.w << 16); w[7] += __uint_as_float(old.w & 0xFFFF0000u);
+                }
                 uint4 pk;
                 pk.x = pack_bf16x2(w[0], w[1]); pk.y = pack_bf16x2(w[2], w[3]);
                 pk.z = pack_bf16x2(w[4], w[5]); pk.w = pack_bf16x2(w[6], w[7]);

@@ -1,5 +1,5 @@
-// HBM-bound helper kernels around the sweep engine: row gather, deterministic scatter-add
-// (stable LSD radix sort + in-order segment sums), operand preparation, partial merges.
+// HBM-bound helper kernels around the sweep engine: row gather, operand preparation, partial merges, the top-K
+// finishing kernels (the deterministic scatter-add lives in scatter.cuh).
 #pragma once
 #include <cuda_bf16.h>
 #include "ptx.cuh"
@@ -231,290 +231,6 @@ __global__ void spmm_csr_kernel(const int64_t* __restrict__ crow, const int64_t*
       *o = t;
     }
   }
-}
-
-// -------------------------------------------------------------------------- radix sort
-// Stable LSD radix sort of (key = row id, val = position) pairs, 8 bits per pass.
-// One warp owns a contiguous chunk; ranks inside the chunk come from __match_any_sync so equal
-// keys keep their input order (=> the segment sums below run in a fixed order).
-constexpr int RS_CHUNK = 1024;
-constexpr int RS_SCATTER_WARPS = 4;   // chunks (one warp each) per block of the scatter pass
-
-__global__ void rs_hist_kernel(const uint32_t* __restrict__ keys, int n, int shift, uint32_t* __restrict__ hist,
-                               int n_chunks) {
-  __shared__ uint32_t h[256];
-  const int chunk = blockIdx.x;
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) h[i] = 0;
-  __syncthreads();
-  const int beg = chunk * RS_CHUNK, end = min(n, beg + RS_CHUNK);
-  for (int i = beg + threadIdx.x; i < end; i += blockDim.x) atomicAdd(&h[(keys[i] >> shift) & 255], 1u);
-  __syncthreads();
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i * n_chunks + chunk] = h[i];  // digit-major
-}
-
-// exclusive scan over hist[256 * n_chunks] (digit-major) by one block
-__global__ void rs_scan_kernel(uint32_t* __restrict__ hist, int total) {
-  __shared__ uint32_t part[1024];
-  const int per = (total + 1023) / 1024;
-  const int beg = threadIdx.x * per, end = min(total, beg + per);
-  uint32_t s = 0;
-  for (int i = beg; i < end; ++i) s += hist[i];
-  part[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {
-    uint32_t v = (threadIdx.x >= o) ? part[threadIdx.x - o] : 0;
-    __syncthreads();
-    part[threadIdx.x] += v;
-    __syncthreads();
-  }
-  uint32_t run = part[threadIdx.x] - s;
-  for (int i = beg; i < end; ++i) { const uint32_t v = hist[i]; hist[i] = run; run += v; }
-}
-
-// Large inputs: the same exclusive scan in two coalesced kernels, one block per digit.
-//   rs_digit_totals: totals[d] = sum of row d of hist (256 rows of n_chunks counters)
-//   rs_scan_rows:    row d becomes its exclusive scan, offset by the sum of the totals of all smaller digits
-__global__ void rs_digit_totals_kernel(const uint32_t* __restrict__ hist, int n_chunks, uint32_t* __restrict__ totals) {
-  __shared__ uint32_t red[256];
-  const uint32_t* row = hist + static_cast<long long>(blockIdx.x) * n_chunks;
-  uint32_t s = 0;
-  for (int i = threadIdx.x; i < n_chunks; i += 256) s += row[i];
-  red[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = 128; o >= 1; o >>= 1) {
-    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) totals[blockIdx.x] = red[0];
-}
-__global__ void rs_scan_rows_kernel(uint32_t* __restrict__ hist, int n_chunks, const uint32_t* __restrict__ totals) {
-  __shared__ uint32_t part[256];
-  __shared__ uint32_t carry_s;
-  uint32_t* row = hist + static_cast<long long>(blockIdx.x) * n_chunks;
-  // base = sum of totals of smaller digits
-  uint32_t b = (threadIdx.x < blockIdx.x) ? totals[threadIdx.x] : 0u;
-  part[threadIdx.x] = b;
-  __syncthreads();
-  for (int o = 128; o >= 1; o >>= 1) {
-    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) carry_s = part[0];
-  __syncthreads();
-  for (int base = 0; base < n_chunks; base += 256) {
-    const int i = base + threadIdx.x;
-    const uint32_t v = (i < n_chunks) ? row[i] : 0u;
-    part[threadIdx.x] = v;
-    __syncthreads();
-    for (int o = 1; o < 256; o <<= 1) {   // inclusive Hillis-Steele scan of the 256-entry tile
-      const uint32_t u = (threadIdx.x >= o) ? part[threadIdx.x - o] : 0u;
-      __syncthreads();
-      part[threadIdx.x] += u;
-      __syncthreads();
-    }
-    const uint32_t carry = carry_s;
-    if (i < n_chunks) row[i] = carry + part[threadIdx.x] - v;
-    __syncthreads();
-    if (threadIdx.x == 255) carry_s = carry + part[255];
-    __syncthreads();
-  }
-}
-
-__global__ void rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n, int shift,
-                                  const uint32_t* __restrict__ offs, int n_chunks) {
-  __shared__ uint32_t base_s[RS_SCATTER_WARPS][256];
-  const int chunk = blockIdx.x * RS_SCATTER_WARPS + (threadIdx.x >> 5);  // one warp per chunk
-  const int lane = threadIdx.x & 31;
-  if (chunk >= n_chunks) return;
-  uint32_t* base = base_s[threadIdx.x >> 5];
-  for (int i = lane; i < 256; i += 32) base[i] = offs[i * n_chunks + chunk];
-  __syncwarp();
-  const int beg = chunk * RS_CHUNK, end = min(n, beg + RS_CHUNK);
-  constexpr int PER = RS_CHUNK / 32;
-  uint32_t kreg[PER], vreg[PER];   // the whole chunk in registers: the ranking loop below never waits on memory
-#pragma unroll
-  for (int j = 0; j < PER; ++j) {
-    const int i = beg + j * 32 + lane;
-    kreg[j] = (i < end) ? keys_in[i] : 0u;
-    vreg[j] = (i < end) ? vals_in[i] : 0u;
-  }
-#pragma unroll
-  for (int j = 0; j < PER; ++j) {
-    const int i = beg + j * 32 + lane;
-    const bool ok = i < end;
-    const uint32_t k = kreg[j];
-    const uint32_t dgt = ok ? ((k >> shift) & 255u) : 256u + lane;  // inactive lanes never match
-    const uint32_t peers = __match_any_sync(0xffffffffu, dgt);
-    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-    uint32_t pos = 0;
-    if (ok) pos = base[dgt] + rank;
-    __syncwarp();
-    if (ok && rank == __popc(peers) - 1) base[dgt] += __popc(peers);  // last peer bumps the counter
-    __syncwarp();
-    if (ok) { keys_out[pos] = k; vals_out[pos] = vreg[j]; }
-  }
-}
-
-__global__ void rs_init_kernel(const int64_t* __restrict__ idx, long long base, uint32_t* __restrict__ keys,
-                               uint32_t* __restrict__ vals, int n, long long n_rows, long long padding_idx) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    const long long r = idx[i] - base;
-    // invalid ids and the padding row sort last and are skipped
-    keys[i] = (r >= 0 && r < n_rows && r != padding_idx) ? static_cast<uint32_t>(r) : static_cast<uint32_t>(n_rows);
-    vals[i] = static_cast<uint32_t>(i);
-  }
-}
-
-// Segment sums over the sorted (row id, position) list, 32 sorted positions per warp (a "block").
-// (reference: embedding_dense_backward, autograd of SASRec/main.py:183 run at :249)
-//   pass 1  every warp walks its 32 entries in order (row loads batched 8 deep, adds in order).  A run
-//           of equal ids that lies inside the block is added to the table by this warp alone; a run that
-//           began in an earlier block goes to lead[b], one that starts here and continues goes to trail[b].
-//   pass 2  the warp whose block holds the START of a split run adds trail[b] + lead[b+1] + ... in block
-//           order and updates the table.  Hot rows (Zipf heads, thousands of entries) are thus summed by
-//           many warps in parallel, yet in a fixed order => bitwise reproducible.
-// `alpha * (alpha_dev ? *alpha_dev : 1)` scales the added rows (1 for the plain embedding backward; the
-// CE backward uses it to subtract the one-hot rows, dW[label_i] -= g*scale*u_i, exactly in fp32);
-// cnt_out[key] += cnt_alpha * (alpha_dev) * run length (the matching dbias term), nullable.
-constexpr int SEG_BLOCK = 32;
-
-template <typename T>
-__device__ __forceinline__ float4 seg_load4(const T* p) {
-  if constexpr (sizeof(T) == 4) {
-    return *reinterpret_cast<const float4*>(p);
-  } else {
-    const uint2 raw = *reinterpret_cast<const uint2*>(p);
-    return make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xFFFF0000u),
-                       __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xFFFF0000u));
-  }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(128)
-scatter_segments_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ perm,
-                        const T* __restrict__ grad_out, float* __restrict__ grad_table, int n, int d, long long n_rows,
-                        float alpha, const float* __restrict__ alpha_dev, float* __restrict__ cnt_out, float cnt_alpha,
-                        float* __restrict__ lead, float* __restrict__ trail, int row_div, const float* __restrict__ ew) {
-  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const int p0 = b * SEG_BLOCK;
-  if (p0 >= n) return;
-  const int cnt = min(SEG_BLOCK, n - p0);
-  const uint32_t key = (lane < cnt) ? keys[p0 + lane] : 0xFFFFFFFFu;
-  const uint32_t first_key = __shfl_sync(0xffffffffu, key, 0);
-  if (static_cast<long long>(first_key) >= n_rows) return;  // sorted: nothing valid in this block
-  // entry p adds  ew[p] * grad_out[p / row_div]  (plain embedding backward: row_div = 1, ew = null)
-  const uint32_t my_perm = (lane < cnt) ? perm[p0 + lane] : 0u;
-  const uint32_t my_src = (row_div > 1) ? my_perm / static_cast<uint32_t>(row_div) : my_perm;
-  const float my_w = (ew != nullptr && lane < cnt) ? __ldg(ew + my_perm) : 1.f;
-  const uint32_t prev_key = (p0 > 0) ? keys[p0 - 1] : 0xFFFFFFFFu;
-  const uint32_t next_key = (p0 + SEG_BLOCK < n) ? keys[p0 + SEG_BLOCK] : 0xFFFFFFFFu;
-  const uint32_t up = __shfl_up_sync(0xffffffffu, key, 1);
-  const bool head = (lane == 0) || (key != up);
-  const uint32_t heads = __ballot_sync(0xffffffffu, head && lane < cnt);
-  const uint32_t valid = __ballot_sync(0xffffffffu, lane < cnt && static_cast<long long>(key) < n_rows);
-  const float adev = (alpha_dev != nullptr) ? __ldg(alpha_dev) : 1.f;
-  const float al = alpha * adev;
-
-  for (int c0 = 0; c0 < d; c0 += 128) {  // d % 4 == 0
-    const int c = c0 + lane * 4;
-    const bool col_ok = c < d;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int e0 = 0; e0 < cnt; e0 += 8) {
-      float4 v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const uint32_t pr = __shfl_sync(0xffffffffu, my_src, (e0 + u) & 31);
-        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (col_ok && ((valid >> (e0 + u)) & 1u)) v[u] = seg_load4<T>(grad_out + static_cast<long long>(pr) * d + c);
-        if (ew != nullptr) {  // warp-uniform
-          const float w = __shfl_sync(0xffffffffu, my_w, (e0 + u) & 31);
-          v[u].x *= w; v[u].y *= w; v[u].z *= w; v[u].w *= w;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int e = e0 + u;
-        if (e < cnt && ((valid >> e) & 1u)) {
-          acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
-          const bool run_ends = (e + 1 == cnt) || ((heads >> (e + 1)) & 1u);
-          if (run_ends) {  // warp-uniform
-            const uint32_t k = __shfl_sync(0xffffffffu, key, e);
-            const int j0 = 31 - __clz(heads & ((2u << e) - 1u));            // start of this run inside the block
-            const bool began_before = (j0 == 0) && (k == prev_key);
-            const bool continues = (e + 1 == SEG_BLOCK) && (k == next_key);
-            if (col_ok) {
-              if (began_before) {
-                *reinterpret_cast<float4*>(lead + static_cast<long long>(b) * d + c) = acc;
-              } else if (continues) {
-                *reinterpret_cast<float4*>(trail + static_cast<long long>(b) * d + c) = acc;
-              } else {
-                float4* dst = reinterpret_cast<float4*>(grad_table + static_cast<long long>(k) * d + c);
-                float4 o = *dst;
-                o.x = fmaf(al, acc.x, o.x); o.y = fmaf(al, acc.y, o.y); o.z = fmaf(al, acc.z, o.z); o.w = fmaf(al, acc.w, o.w);
-                *dst = o;
-              }
-            }
-            if (c0 == 0 && cnt_out != nullptr && lane == 0 && !began_before && !continues)
-              cnt_out[k] += cnt_alpha * adev * static_cast<float>(e - j0 + 1);
-            acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-      }
-    }
-  }
-}
-
-// pass 2: runs split over several blocks (see above).  One warp per block; only the block holding the
-// start of a split run does work.
-__global__ void __launch_bounds__(128)
-scatter_split_runs_kernel(const uint32_t* __restrict__ keys, float* __restrict__ grad_table, int n, int d, long long n_rows,
-                          float alpha, const float* __restrict__ alpha_dev, float* __restrict__ cnt_out, float cnt_alpha,
-                          const float* __restrict__ lead, const float* __restrict__ trail) {
-  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const int p0 = b * SEG_BLOCK;
-  if (p0 + SEG_BLOCK >= n) return;  // a run can only continue out of a full block that has a successor
-  const uint32_t key = keys[p0 + SEG_BLOCK - 1];
-  if (static_cast<long long>(key) >= n_rows || keys[p0 + SEG_BLOCK] != key) return;   // no run leaves this block
-  const uint32_t kl = keys[p0 + lane];
-  const uint32_t same = __ballot_sync(0xffffffffu, kl == key);
-  const int j0 = __ffs(same) - 1;
-  if (j0 == 0 && p0 > 0 && keys[p0 - 1] == key) return;  // the run began earlier: not the owner
-  // end of the run (first position whose key differs) by binary search over the sorted keys; hot rows span
-  // thousands of blocks
-  int lo = p0 + SEG_BLOCK, hi = n;   // keys[lo] == key is known
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (keys[mid] == key) lo = mid + 1; else hi = mid;
-  }
-  const int run_end = lo;                              // exclusive
-  const int nb = (run_end - 1) / SEG_BLOCK;            // last block that holds a piece of the run
-  const int run_len = run_end - (p0 + j0);
-  const float adev = (alpha_dev != nullptr) ? __ldg(alpha_dev) : 1.f;
-  const float al = alpha * adev;
-  for (int c = lane * 4; c < d; c += 128) {
-    float4 acc = *reinterpret_cast<const float4*>(trail + static_cast<long long>(b) * d + c);
-    int x = b + 1;
-    for (; x + 8 <= nb + 1; x += 8) {   // eight partials in flight, added in block order
-      float4 v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float4*>(lead + static_cast<long long>(x + u) * d + c);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
-    }
-    for (; x <= nb; ++x) {
-      const float4 v = *reinterpret_cast<const float4*>(lead + static_cast<long long>(x) * d + c);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
-    float4* dst = reinterpret_cast<float4*>(grad_table + static_cast<long long>(key) * d + c);
-    float4 o = *dst;
-    o.x = fmaf(al, acc.x, o.x); o.y = fmaf(al, acc.y, o.y); o.z = fmaf(al, acc.z, o.z); o.w = fmaf(al, acc.w, o.w);
-    *dst = o;
-  }
-  if (cnt_out != nullptr && lane == 0) cnt_out[key] += cnt_alpha * adev * static_cast<float>(run_len);
 }
 
 __device__ __forceinline__ float4 load4_as_float(const float* p) { return *reinterpret_cast<const float4*>(p); }

@@ -54,41 +54,58 @@ def gather_rows_raw(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
 
 def scatter_add_rows_(grad_table: torch.Tensor, grad_out: torch.Tensor, idx: torch.Tensor,
                       padding_idx: int = -1) -> torch.Tensor:
-    """grad_table[idx[i]] += grad_out[i] (fp32 accumulate, fixed summation order)."""
+    """grad_table[idx[i]] += grad_out[i] in place (fp32 accumulate, fixed summation order); ``grad_table`` is fp32
+    or bf16 (one rounding per touched row).  One cooperative launch (csrc/scatter.cuh)."""
     dev = L.require_cuda(grad_table, grad_out, idx)
-    if grad_table.dtype != torch.float32:
-        raise TypeError("grad_table must be float32")
+    if grad_table.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("grad_table must be float32 or bfloat16")
     n_rows, d = grad_table.shape
     n_idx = idx.numel()
     grad_out, idx = grad_out.contiguous(), idx.contiguous()   # grad_table is updated in place: it must be dense already
     ws, n = _ws(dev, L.OP_SCATTER_ADD, 0, 0, d, nnz=n_idx)
-    L.call(dev, "rb_scatter_add_rows", L.ptr(grad_out), L.ptr(idx), L.ptr(grad_table), n_idx, n_rows, d,
-                                    L.dtype_code(grad_out), padding_idx, L.ptr(ws), n, L.stream_ptr(dev))
+    L.call(dev, "rb_scatter_add_rows_into", L.ptr(grad_out), L.ptr(idx), L.ptr(grad_table), n_idx, n_rows, d,
+           L.dtype_code(grad_out), L.dtype_code(grad_table), padding_idx, L.ptr(ws), n, L.stream_ptr(dev))
     return grad_table
 
 
 class _GatherRows(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, table, idx, padding_idx):
+    def forward(ctx, table, idx, padding_idx, accumulate):
         ctx.save_for_backward(idx)
         ctx.shape, ctx.dtype, ctx.padding_idx = table.shape, table.dtype, padding_idx
+        # accumulate=True: the backward adds straight into ``table.grad`` (a leaf's persistent gradient buffer)
+        ctx.leaf = table if (accumulate and table.is_leaf and table.requires_grad) else None
         return gather_rows_raw(table.contiguous(), idx.contiguous())
 
     @staticmethod
     def backward(ctx, grad_out):
         (idx,) = ctx.saved_tensors
-        g = torch.zeros(ctx.shape, dtype=torch.float32, device=grad_out.device)
         go = grad_out.contiguous()
         if go.dtype not in (torch.float32, torch.bfloat16):
             go = go.float()
-        scatter_add_rows_(g, go.view(-1, ctx.shape[1]), idx.contiguous().view(-1), ctx.padding_idx)
-        return g.to(ctx.dtype), None, None
+        go, flat = go.view(-1, ctx.shape[1]), idx.contiguous().view(-1)
+        leaf = ctx.leaf
+        if leaf is not None and leaf.grad is not None and leaf.grad.is_contiguous() and leaf.grad.shape == ctx.shape \
+                and leaf.grad.dtype in (torch.float32, torch.bfloat16):
+            # the table's existing gradient gets the rows added in place (it may already hold, or later receive, the
+            # dW of the scoring head: the reference's autograd sums both into this one (N+P,d) tensor too)
+            scatter_add_rows_(leaf.grad, go, flat, ctx.padding_idx)
+            return None, None, None, None
+        gdt = ctx.dtype if ctx.dtype in (torch.float32, torch.bfloat16) else torch.float32
+        g = torch.zeros(ctx.shape, dtype=gdt, device=grad_out.device)   # in the parameter's dtype: no fp32 copy + cast
+        scatter_add_rows_(g, go, flat, ctx.padding_idx)
+        return g.to(ctx.dtype), None, None, None
 
 
-def gather_rows(table: torch.Tensor, idx: torch.Tensor, padding_idx: int = -1) -> torch.Tensor:
+def gather_rows(table: torch.Tensor, idx: torch.Tensor, padding_idx: int = -1, accumulate: bool = False) -> torch.Tensor:
     """``self.Item.embeddings(seqs)`` (SASRec/main.py:183) with the ``nn.Embedding(padding_idx=)``
-    backward contract: dense table gradient, ``padding_idx`` row left at zero."""
-    return _GatherRows.apply(table, idx, padding_idx)
+    backward contract: dense table gradient, ``padding_idx`` row left at zero.
+
+    ``accumulate=True`` (training loops that keep ``table.grad`` allocated, ``zero_grad(set_to_none=False)``): the
+    backward adds the rows directly into ``table.grad`` instead of returning a fresh dense (N+P,d) tensor for
+    autograd to add -- the zero-fill and the extra read-modify-write of the whole table disappear.  Not for
+    ``torch.autograd.grad`` / double backward (the side effect is on ``.grad``)."""
+    return _GatherRows.apply(table, idx, padding_idx, accumulate)
 
 
 # --------------------------------------------------------------------------------------
@@ -279,11 +296,15 @@ def ce_du_finish(du_unnorm, row_max, lse, W, labels, grad_scale: float, scale: f
 def ce_backward(U, W, labels, lse, grad_scale: float, bias=None, scale: float = 1.0, label_base: int = 0,
                 need_dU: bool = True, need_dW: bool = True, need_dbias: bool = False,
                 precision: Optional[str] = None, grad_scale_dev: Optional[torch.Tensor] = None,
-                dw_dtype: Optional[torch.dtype] = None):
+                dw_dtype: Optional[torch.dtype] = None, dw_out: Optional[torch.Tensor] = None,
+                accumulate: bool = False):
     """Gradients of ``g * sum_i (lse_i - S_i,label_i)`` -> (dU, dW, dbias) fp32, with
     ``g = grad_scale * grad_scale_dev`` (the latter an optional fp32 device scalar).
     ``dw_dtype=torch.bfloat16`` (bf16 mode) makes the pass store dW in bf16 itself -- the correctly rounded
-    fp32 result, without the fp32 (N,d) matrix and the cast pass a bf16 parameter would otherwise need."""
+    fp32 result, without the fp32 (N,d) matrix and the cast pass a bf16 parameter would otherwise need.
+    ``dw_out``: a contiguous (N,d) tensor (e.g. rows [P:] of a full (N+P,d) gradient) that receives dW;
+    with ``accumulate`` (bf16 ``dw_out`` only) the rows are ADDED to its content inside the pass -- raises
+    ``NotImplementedError`` when the direct bf16 pass does not apply (the caller adds a separate dW then)."""
     dev = L.require_cuda(U, W, labels, lse, bias, grad_scale_dev)
     if grad_scale_dev is not None and (grad_scale_dev.dtype != torch.float32 or grad_scale_dev.numel() != 1):
         raise TypeError("grad_scale_dev must be a float32 scalar tensor")
@@ -299,12 +320,28 @@ def ce_backward(U, W, labels, lse, grad_scale: float, bias=None, scale: float = 
             L.call(dev, "rb_ce_bwd", L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(labels.contiguous()), label_base,
                                   L.ptr(lse.float().contiguous()), float(grad_scale), L.ptr(grad_scale_dev), M, N, d,
                                   L.dtype_code(Uc), mode, L.ptr(dU), None, None, L.ptr(ws), n, L.stream_ptr(dev))
-        dWb = torch.empty(N, d, dtype=torch.bfloat16, device=dev)
-        L.call(dev, "rb_ce_bwd_dw_bf16", L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(labels.contiguous()), label_base,
-                                      L.ptr(lse.float().contiguous()), float(grad_scale), L.ptr(grad_scale_dev), M, N, d,
-                                      L.ptr(dWb), L.ptr(db), L.ptr(ws), n, L.stream_ptr(dev))
+        dWb = dw_out if dw_out is not None else torch.empty(N, d, dtype=torch.bfloat16, device=dev)
+        if dWb.dtype != torch.bfloat16 or dWb.shape != (N, d):
+            raise TypeError("dw_out must be a bfloat16 (N,d) tensor here")
+        args = (L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(labels.contiguous()), label_base,
+                L.ptr(lse.float().contiguous()), float(grad_scale), L.ptr(grad_scale_dev), M, N, d,
+                L.ptr(dWb), L.ptr(db), L.ptr(ws), n, L.stream_ptr(dev))
+        if accumulate:
+            with torch.cuda.device(dev):
+                code = L.lib().rb_ce_bwd_dw_bf16_acc(*args)
+            if code == L.E_UNSUPPORTED:
+                raise NotImplementedError("in-place accumulation of dW is not available for this shape")
+            L.check(code, "rb_ce_bwd_dw_bf16_acc")
+        else:
+            L.call(dev, "rb_ce_bwd_dw_bf16", *args)
         return dU, dWb, db
-    dW = torch.empty(N, d, dtype=torch.float32, device=dev) if (need_dW or need_dbias) else None
+    if accumulate:
+        raise NotImplementedError("in-place accumulation of dW needs a bf16 gradient in bf16 mode")
+    dW = None
+    if need_dW or need_dbias:
+        dW = dw_out if (dw_out is not None and dw_out.dtype == torch.float32) else torch.empty(N, d, dtype=torch.float32, device=dev)
+        if dW.shape != (N, d):
+            raise TypeError("dw_out must be an (N,d) tensor")
     L.call(dev, "rb_ce_bwd", L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(labels.contiguous()), label_base,
                           L.ptr(lse.float().contiguous()), float(grad_scale), L.ptr(grad_scale_dev), M, N, d,
                           L.dtype_code(Uc), mode,
@@ -314,7 +351,13 @@ def ce_backward(U, W, labels, lse, grad_scale: float, bias=None, scale: float = 
 
 class _FusedCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, U, W, labels, bias, scale, precision, reduction):
+    def forward(ctx, U, Wfull, labels, bias, scale, precision, reduction, n_skip, accumulate):
+        # ``Wfull`` is the whole parameter (N+P, d); the scored table is the view Wfull[n_skip:] (SASRec/main.py:193).
+        # Taking the parameter itself lets the backward hand autograd ONE (N+P,d) gradient, written in place by the
+        # dW pass, instead of a (N,d) one that the slice's backward would pad into a fresh zero-filled copy.
+        W = Wfull[n_skip:] if n_skip else Wfull
+        ctx.n_skip = n_skip
+        ctx.leaf = Wfull if (accumulate and Wfull.is_leaf and Wfull.requires_grad) else None
         # forward and dU share one sweep whenever the fused pass applies (ctx.needs_input_grad is set in forward)
         ctx.fused_du = bool(ctx.needs_input_grad[0]) and fused_du_supported(U, precision, scale)
         du = m = None
@@ -325,7 +368,7 @@ class _FusedCE(torch.autograd.Function):
         lse = m + torch.log(l)
         row_loss = lse - ll
         empty = torch.empty(0, device=U.device)
-        ctx.save_for_backward(U, W, labels, bias if bias is not None else empty, lse,
+        ctx.save_for_backward(U, Wfull, labels, bias if bias is not None else empty, lse,
                               du if du is not None else empty, m if du is not None else empty)
         ctx.has_bias = bias is not None
         ctx.scale, ctx.precision, ctx.reduction = scale, precision, reduction
@@ -337,43 +380,86 @@ class _FusedCE(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        U, W, labels, bias, lse, du_un, row_max = ctx.saved_tensors
+        U, Wfull, labels, bias, lse, du_un, row_max = ctx.saved_tensors
         bias = bias if ctx.has_bias else None
+        P = ctx.n_skip
+        W = Wfull[P:] if P else Wfull
         M = U.shape[0]
         g = 1.0 / (M if ctx.reduction == "mean" else 1)
         need = ctx.needs_input_grad
         # the upstream scalar stays on the device: no host synchronisation in backward
         gdev = grad_out.detach().float().reshape(1).contiguous()
         need_db = ctx.has_bias and need[3]
-        dU = dW = db = None
+        dU = None
         if ctx.fused_du:
             dU = ce_du_finish(du_un, row_max, lse, W, labels, g, ctx.scale, 0, gdev)
-            if need[1] or need_db:
-                _, dW, db = ce_backward(U, W, labels, lse, g, bias, ctx.scale, 0, False, need[1], need_db,
-                                        ctx.precision, grad_scale_dev=gdev, dw_dtype=W.dtype)
-        else:
-            dU, dW, db = ce_backward(U, W, labels, lse, g, bias, ctx.scale, 0, need[0], need[1], need_db,
-                                     ctx.precision, grad_scale_dev=gdev, dw_dtype=W.dtype)
+        dU2, dW, db = table_gradient(U, Wfull, P, labels, lse, g, bias, ctx.scale, 0, ctx.precision, gdev,
+                                     need[0] and not ctx.fused_du, need[1], need_db, ctx.leaf)
+        dU = dU if dU is not None else dU2
         return (
             dU.to(U.dtype) if dU is not None else None,
-            dW.to(W.dtype) if dW is not None else None,
+            dW,
             None,
             db.to(bias.dtype) if db is not None else None,
-            None, None, None,
+            None, None, None, None, None,
         )
 
 
+def table_gradient(U, Wfull, P, labels, lse, g, bias, scale, label_base, precision, gdev, need_du, need_dw, need_db, leaf):
+    """The CE backward's dW / dbias (and dU when the forward did not accumulate it) for a scored table
+    ``Wfull[P:]`` -> (dU | None, gradient for ``Wfull`` as autograd wants it | None, dbias | None).
+
+    * ``leaf`` (the parameter itself, accumulate mode) with an allocated bf16 ``.grad``: the dW pass ADDS its rows
+      into ``leaf.grad[P:]`` and autograd gets ``None`` for the table;
+    * otherwise one (N+P,d) tensor in the parameter's dtype, rows [P:] written in place by the pass, pad rows zero."""
+    W = Wfull[P:] if P else Wfull
+    bf16_mode = _mode_for(U, precision) == "bf16"
+    if (need_dw and not need_du and leaf is not None and leaf.grad is not None and leaf.grad.dtype == torch.bfloat16
+            and leaf.grad.is_contiguous() and leaf.grad.shape == Wfull.shape and Wfull.dtype == torch.bfloat16 and bf16_mode):
+        try:
+            _, _, db = ce_backward(U, W, labels, lse, g, bias, scale, label_base, False, True, need_db, precision,
+                                   grad_scale_dev=gdev, dw_dtype=torch.bfloat16, dw_out=leaf.grad[P:], accumulate=True)
+            return None, None, db
+        except NotImplementedError:
+            pass   # several splits / very many query rows: a separate dW below, autograd accumulates it
+    dfull = dw_out = None
+    if need_dw and P and (Wfull.dtype == torch.float32 or (Wfull.dtype == torch.bfloat16 and bf16_mode)):
+        dfull = torch.empty_like(Wfull)     # the pass writes rows [P:] in place, the P pad rows are zero
+        dfull[:P].zero_()
+        dw_out = dfull[P:]
+    dU, dW, db = ce_backward(U, W, labels, lse, g, bias, scale, label_base, need_du, need_dw, need_db, precision,
+                             grad_scale_dev=gdev, dw_dtype=W.dtype, dw_out=dw_out)
+    if dW is not None:
+        if dfull is not None:
+            dW = dfull
+        elif P:   # dtype combinations the in-place route does not cover
+            dW = torch.cat([torch.zeros(P, dW.shape[1], dtype=dW.dtype, device=dW.device), dW])
+        dW = dW.to(Wfull.dtype)
+    return dU, dW, db
+
+
 def fused_ce(U: torch.Tensor, W: torch.Tensor, labels: torch.Tensor, bias: Optional[torch.Tensor] = None,
-             scale: float = 1.0, precision: Optional[str] = None, reduction: str = "mean") -> torch.Tensor:
+             scale: float = 1.0, precision: Optional[str] = None, reduction: str = "mean", n_skip: int = 0,
+             accumulate: bool = False) -> torch.Tensor:
     """Drop-in for ``self.criterion(torch.einsum("MD,ND->MN", U, W), labels)`` with
     ``criterion = CrossEntropy4Logits(reduction="mean")`` (SASRec/main.py:126,217-219): same value,
-    same gradients, no (M,N) logit matrix in forward or backward."""
+    same gradients, no (M,N) logit matrix in forward or backward.
+
+    ``n_skip = P``: ``W`` is the whole (N+P, d) embedding parameter and the scored table is ``W[P:]``
+    (``self.Item.embeddings.weight[self.NUM_PADS:]``, SASRec/main.py:193; labels index that view).  The gradient
+    then comes back as one (N+P,d) tensor written in place -- no zero-padded copy from the slice's backward.
+
+    ``accumulate=True`` (bf16 parameter whose ``.grad`` buffer is kept allocated): the dW pass adds its rows
+    straight into ``W.grad`` -- together with ``gather_rows(..., accumulate=True)`` the table's gradient is built
+    in ONE buffer without any table-sized temporary.  Same caveat as there: not for ``torch.autograd.grad``."""
     if U.shape[0] == 0:
         # no query rows (e.g. a BERT4Rec step whose random mask selected nothing): F.cross_entropy returns
         # NaN for "mean" and 0 for "sum", with zero gradients -- reproduced without a launch
         zero = (U.sum() + W.sum() * 0 + (bias.sum() * 0 if bias is not None else 0)).float()
         return zero / 0 if reduction == "mean" else zero
-    return _FusedCE.apply(U, W, labels, bias, float(scale), precision, reduction)
+    if n_skip and bias is not None:
+        raise ValueError("n_skip is for bias-free embedding tables (a bias head scores every row of its weight)")
+    return _FusedCE.apply(U, W, labels, bias, float(scale), precision, reduction, int(n_skip), bool(accumulate))
 
 
 # --------------------------------------------------------------------------------------

@@ -6,7 +6,8 @@ dense (N,d) table gradient every step (``ddp_backend: nccl``, E4SRec/README.md:2
 exchange steps are tiny and explicit:
 
   CE forward   one all-gather of the per-rank (row_max, row_sumexp, label_logit)  [3*M floats/rank]
-  CE backward  one all-reduce (SUM) of the partial dU (M,d); the dW shard is purely local
+  CE backward  one all-reduce (SUM) of the partial dU (M,d), issued asynchronously in front of the dW pass (which
+               does not depend on it); the dW shard is purely local
   top-K eval   one all-gather of the per-rank sorted (vals, ids) (B,K) + a K-way merge kernel
 
 The collectives and the elementwise merge math below are device-agnostic torch (they are exercised
@@ -56,8 +57,9 @@ def allgather_topk(vals: torch.Tensor, ids: torch.Tensor, group=None) -> Tuple[t
 
 class _ShardedCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, U, W_shard, labels, bias_shard, scale, row_start, group, precision):
+    def forward(ctx, U, W_full, labels, bias_shard, scale, row_start, group, precision, n_skip, accumulate):
         from . import ops
+        W_shard = W_full[n_skip:] if n_skip else W_full
         ctx.fused_du = bool(ctx.needs_input_grad[0]) and ops.fused_du_supported(U, precision, scale)
         du = None
         if ctx.fused_du:  # the forward sweep also accumulates this shard's unnormalised dU
@@ -67,44 +69,52 @@ class _ShardedCE(torch.autograd.Function):
             m, l, ll = ops.ce_rowstats(U, W_shard, labels, bias_shard, scale, label_base=row_start, precision=precision)
         lse, llg = merge_rowstats(allgather_rowstats(m, l, ll, group))
         empty = torch.empty(0, device=U.device)
-        ctx.save_for_backward(U, W_shard, labels, bias_shard if bias_shard is not None else empty, lse,
+        ctx.save_for_backward(U, W_full, labels, bias_shard if bias_shard is not None else empty, lse,
                               du if du is not None else empty, m if du is not None else empty)
         ctx.has_bias = bias_shard is not None
-        ctx.scale, ctx.row_start, ctx.group, ctx.precision = scale, row_start, group, precision
+        ctx.scale, ctx.row_start, ctx.group, ctx.precision, ctx.n_skip = scale, row_start, group, precision, n_skip
+        ctx.leaf = W_full if (accumulate and W_full.is_leaf and W_full.requires_grad) else None
         return (lse - llg).mean()
 
     @staticmethod
     def backward(ctx, grad_out):
         from . import ops
-        U, W_shard, labels, bias, lse, du_un, row_max = ctx.saved_tensors
+        U, W_full, labels, bias, lse, du_un, row_max = ctx.saved_tensors
         bias = bias if ctx.has_bias else None
         need = ctx.needs_input_grad
+        P = ctx.n_skip
+        W_shard = W_full[P:] if P else W_full
         g = 1.0 / U.shape[0]
         gdev = grad_out.detach().float().reshape(1).contiguous()
         need_db = ctx.has_bias and need[3]
-        dU = dW = db = None
+        dU = None
         if ctx.fused_du:
             dU = ops.ce_du_finish(du_un, row_max, lse, W_shard, labels, g, ctx.scale, ctx.row_start, gdev)
-            if need[1] or need_db:
-                _, dW, db = ops.ce_backward(U, W_shard, labels, lse, g, bias, ctx.scale, ctx.row_start, False,
-                                            need[1], need_db, ctx.precision, grad_scale_dev=gdev, dw_dtype=W_shard.dtype)
-        else:
-            dU, dW, db = ops.ce_backward(U, W_shard, labels, lse, g, bias, ctx.scale, ctx.row_start,
-                                         need[0], need[1], need_db, ctx.precision, grad_scale_dev=gdev,
-                                         dw_dtype=W_shard.dtype)
+        # the partial dU travels while the dW pass (which does not depend on it) runs: the all-reduce is asynchronous
+        work = None
         if dU is not None:
-            dist.all_reduce(dU, op=dist.ReduceOp.SUM, group=ctx.group)
-        return (dU.to(U.dtype) if dU is not None else None, dW.to(W_shard.dtype) if dW is not None else None, None,
-                db.to(bias.dtype) if db is not None else None, None, None, None, None)
+            work = dist.all_reduce(dU, op=dist.ReduceOp.SUM, group=ctx.group, async_op=True)
+        dU2, dW, db = ops.table_gradient(U, W_full, P, labels, lse, g, bias, ctx.scale, ctx.row_start, ctx.precision, gdev,
+                                         need[0] and not ctx.fused_du, need[1], need_db, ctx.leaf)
+        if dU is None and dU2 is not None:
+            dU = dU2
+            work = dist.all_reduce(dU, op=dist.ReduceOp.SUM, group=ctx.group, async_op=True)
+        if work is not None:
+            work.wait()
+        return (dU.to(U.dtype) if dU is not None else None, dW, None,
+                db.to(bias.dtype) if db is not None else None, None, None, None, None, None, None)
 
 
 def sharded_fused_ce(U: torch.Tensor, W_shard: torch.Tensor, labels: torch.Tensor, row_start: int,
                      bias_shard: Optional[torch.Tensor] = None, scale: float = 1.0, group=None,
-                     precision: Optional[str] = None) -> torch.Tensor:
-    """Full-catalog CE where this rank scores only rows [row_start, row_start+len(W_shard)) of the
-    table.  ``labels`` are GLOBAL item ids; every rank returns the same loss; ``W_shard.grad`` is the
-    local gradient shard (never all-reduced), ``U.grad`` is the full gradient."""
-    return _ShardedCE.apply(U, W_shard, labels, bias_shard, float(scale), int(row_start), group, precision)
+                     precision: Optional[str] = None, n_skip: int = 0, accumulate: bool = False) -> torch.Tensor:
+    """Full-catalog CE where this rank scores only rows [row_start, row_start+len(shard)) of the
+    table.  ``labels`` are GLOBAL item ids; every rank returns the same loss; the table gradient is the
+    local shard's (never all-reduced), ``U.grad`` is the full gradient.  ``n_skip`` / ``accumulate`` as in
+    ``ops.fused_ce``: ``W_shard`` may be the rank's whole parameter (pad rows first) and its existing bf16 ``.grad``
+    may receive dW inside the pass."""
+    return _ShardedCE.apply(U, W_shard, labels, bias_shard, float(scale), int(row_start), group, precision, int(n_skip),
+                            bool(accumulate))
 
 
 @torch.no_grad()

@@ -169,6 +169,29 @@ def test_genrec_fused(cuda, base, mixin):
     _check_eval(fused, eager, data_fn, N)
 
 
+def test_fused_embedding_swaps_in_and_trains(cuda):
+    """``arch.fuse_item_embedding``: the lookup and its dense backward through the C ABI, same weight Parameter;
+    with ``accumulate_grad`` the rows land in the existing ``weight.grad`` next to the head's dW."""
+    N = 300
+    data_fn = _seq_data(cuda, N=N)
+    F_ = fuse(arch.SASRecFused, DM.TinySASRec)
+    fused, eager, (lf, gf), (le, ge) = _fit_pair(F_, DM.TinySASRec, data_fn, cuda, n_users=9, n_items=N)
+    for accumulate in (False, True):
+        m2 = F_(n_users=9, n_items=N).to(cuda).train()
+        m2.load_state_dict(eager.state_dict())
+        arch.fuse_item_embedding(m2, accumulate_grad=accumulate)
+        assert set(m2.state_dict()) == set(eager.state_dict())
+        if accumulate:
+            for p in m2.parameters():
+                p.grad = torch.zeros_like(p)
+        torch.manual_seed(123)
+        loss = m2(data_fn(m2))["rec_loss"]
+        loss.backward()
+        assert abs(float(loss) - float(le)) <= FP32_RTOL * abs(float(le))
+        for name, p in m2.named_parameters():
+            assert rel(p.grad, ge[name]) <= 2e-5, (name, accumulate)
+
+
 # ------------------------------------------------------------------------------ evaluation sweeps
 MONS = ["HITRATE@1", "HITRATE@5", "HITRATE@10", "NDCG@5", "NDCG@10"]
 

@@ -463,6 +463,91 @@ def test_scatter_add_hot_rows_deterministic(ops):
     assert_rel(tb, orc.scatter_add_rows(bf16_round(go), idx, n_rows, 0), 1e-5, "scatter-add bf16")
 
 
+@pytest.mark.parametrize("n_rows,n", [(5000, 40000), (1_000_001, 204_800), (5_000_000, 7), (300, 1)])
+def test_scatter_add_sizes_and_bf16_table(ops, n_rows, n):
+    """The one-launch scatter-add at the bench size (two 11-bit passes), beyond 4M rows (three passes), tiny inputs;
+    into an fp32 table that already holds values, and into a bf16 table (fp32 add, one rounding per touched row)."""
+    g = torch.Generator().manual_seed(n)
+    d = 64
+    idx = (torch.rand(n, generator=g) ** 4 * n_rows).long().clamp_(0, n_rows - 1)
+    go = torch.randn(n, d, generator=g).bfloat16()
+    add = orc.scatter_add_rows(go.float(), idx, n_rows, padding_idx=0)
+    touched = torch.unique(idx)
+    base = torch.zeros(n_rows, d)
+    base[touched] = torch.randn(len(touched), d, generator=g)
+    t32 = dev(base.clone())
+    ops.scatter_add_rows_(t32, dev(go), dev(idx), padding_idx=0)
+    got = t32[dev(touched)].cpu()
+    assert_rel(got, (base + add)[touched], 1e-5, "accumulate into fp32")
+    untouched = torch.ones(n_rows, dtype=torch.bool); untouched[touched] = False
+    assert bool((t32.cpu()[untouched] == 0).all())
+    tb = dev(base.bfloat16())
+    ops.scatter_add_rows_(tb, dev(go), dev(idx), padding_idx=0)
+    ref_b = (base.bfloat16().float() + add).bfloat16()
+    assert torch.equal(tb[dev(touched)].cpu(), ref_b[touched]) or \
+        float((tb[dev(touched)].cpu().float() - ref_b[touched].float()).abs().max()) <= 2 ** -7 * float(ref_b[touched].float().abs().max())
+
+
+def test_gather_rows_backward_accumulates_into_existing_grad(ops):
+    """autograd of the gather (SASRec/main.py:183 at :249): without a gradient buffer a dense gradient in the
+    parameter's dtype is returned; with ``accumulate=True`` and an existing ``.grad`` the rows are added in place --
+    and the sum with the scoring head's dW (fused_ce with n_skip) is the reference's single (N+P,d) gradient."""
+    g = torch.Generator().manual_seed(4)
+    N, P, d, B, S, M = 900, 1, 64, 16, 10, 50
+    W0 = torch.randn(N + P, d, generator=g) * 0.3
+    W0[0] = 0
+    idx = torch.randint(0, N + P, (B, S), generator=g)
+    U = torch.randn(M, d, generator=g) * 0.3
+    labels = torch.randint(0, N, (M,), generator=g)
+    # reference: plain torch autograd on the CPU (nn.Embedding with padding_idx + einsum + cross_entropy)
+    Wr = W0.clone().requires_grad_(True)
+    emb = torch.nn.functional.embedding(idx, Wr, padding_idx=0)
+    loss = torch.nn.functional.cross_entropy(U @ Wr[P:].T, labels) + (emb * emb).sum() * 0.01
+    loss.backward()
+    for accumulate in (False, True):
+        Wd = dev(W0).requires_grad_(True)
+        if accumulate:
+            Wd.grad = torch.zeros_like(Wd)
+        buf = Wd.grad
+        embd = ops.gather_rows(Wd, dev(idx), padding_idx=0, accumulate=accumulate)
+        lossd = ops.fused_ce(dev(U), Wd, dev(labels), n_skip=P) + (embd * embd).sum() * 0.01
+        lossd.backward()
+        assert abs(float(lossd) - float(loss)) <= 1e-5 * abs(float(loss))
+        assert_rel(Wd.grad, Wr.grad, 2e-5, f"table gradient (accumulate={accumulate})")
+        assert bool((Wd.grad[0] == 0).all())                     # the padding row stays zero
+        if accumulate:
+            assert Wd.grad.data_ptr() == buf.data_ptr()           # still the same buffer: nothing was re-allocated
+
+
+def test_bf16_table_gradient_built_in_one_buffer(ops):
+    """bf16 parameter, ``.grad`` kept allocated: the gather's rows and the head's dW are both added inside their own
+    kernels into that ONE (N+P,d) buffer (gather_rows(accumulate=True) + fused_ce(n_skip, accumulate=True))."""
+    g = torch.Generator().manual_seed(6)
+    N, P, d, B, S, M = 3000, 1, 128, 32, 12, 300
+    W0 = bf16_round(torch.randn(N + P, d, generator=g) * 0.3)
+    W0[0] = 0
+    idx = torch.randint(0, N + P, (B, S), generator=g)
+    U = bf16_round(torch.randn(M, d, generator=g) * 0.3)
+    labels = torch.randint(0, N, (M,), generator=g)
+    gemb = bf16_round(torch.randn(B, S, d, generator=g) * 0.01)
+    Wr = W0.clone().requires_grad_(True)
+    emb = torch.nn.functional.embedding(idx, Wr, padding_idx=0)
+    loss = torch.nn.functional.cross_entropy(U @ Wr[P:].T, labels)
+    torch.autograd.backward([loss, emb], [None, gemb])
+    old = bf16_round(torch.randn(N + P, d, generator=g) * 1e-3)
+    Wd = dev(W0).bfloat16().requires_grad_(True)
+    Wd.grad = dev(old).bfloat16()
+    buf = Wd.grad
+    Ud = dev(U).bfloat16().requires_grad_(True)
+    embd = ops.gather_rows(Wd, dev(idx), padding_idx=0, accumulate=True)
+    lossd = ops.fused_ce(Ud, Wd, dev(labels), n_skip=P, accumulate=True)
+    torch.autograd.backward([lossd, embd], [None, dev(gemb).bfloat16()])
+    assert Wd.grad.data_ptr() == buf.data_ptr()
+    assert abs(float(lossd) - float(loss)) <= 1e-5 * abs(float(loss))
+    assert_rel(Wd.grad.float() - dev(old), Wr.grad, 3 * BF16_RTOL, "bf16 table gradient (two roundings: gather rows, dW)")
+    assert bool((Wd.grad[0].float().cpu() == old[0]).all())     # the padding row received nothing
+
+
 def test_sharded_partials_merge_like_multi_gpu(ops):
     """Single-GPU simulation of R row shards: sharded stats/top-K/dW == unsharded."""
     from recboard_b200 import sharded

@@ -77,15 +77,18 @@ def _install_oracle_ops():
         return m, l, ll
 
     def ce_backward(U, W, labels, lse, grad_scale, bias=None, scale=1.0, label_base=0, need_dU=True, need_dW=True,
-                    need_dbias=False, precision=None, grad_scale_dev=None, dw_dtype=None):
+                    need_dbias=False, precision=None, grad_scale_dev=None, dw_dtype=None, dw_out=None, accumulate=False):
         S = orc.score_dense(U, W, bias, scale)
         G = torch.exp(S - lse[:, None])
         loc = labels - label_base
         inside = (loc >= 0) & (loc < W.shape[0])
         G[torch.arange(len(U))[inside], loc[inside]] -= 1.0
         G = G * grad_scale * (float(grad_scale_dev) if grad_scale_dev is not None else 1.0)
-        return (scale * G @ W.float() if need_dU else None, scale * G.T @ U.float() if need_dW else None,
-                G.sum(0) if need_dbias else None)
+        dW = scale * G.T @ U.float() if need_dW else None
+        if dW is not None and dw_out is not None:
+            dw_out.copy_(dW)
+            dW = dw_out
+        return (scale * G @ W.float() if need_dU else None, dW, G.sum(0) if need_dbias else None)
 
     def topk_eval(U, W, K, seen_crow=None, seen_col=None, bias=None, scale=1.0, id_base=0, precision=None):
         S = orc.score_dense(U, W, bias, scale)
