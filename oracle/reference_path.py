@@ -66,12 +66,14 @@ def scatter_add_rows(
 def score_dense(
     U: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, scale: float = 1.0
 ) -> torch.Tensor:
-    """S = scale * (U @ W^T) + bias   (SASRec/main.py:217,228; BERT4Rec/main.py:181)."""
-    S = torch.einsum("MD,ND->MN", U.float(), W.float())
+    """S = scale * (U @ W^T) + bias   (SASRec/main.py:217,228; BERT4Rec/main.py:181).  float32 like the reference;
+    float64 inputs stay float64 (the high-precision arbiter of the full-size parity checks)."""
+    dt = torch.float64 if U.dtype == torch.float64 else torch.float32
+    S = torch.einsum("MD,ND->MN", U.to(dt), W.to(dt))
     if scale != 1.0:
         S = S * scale
     if bias is not None:
-        S = S + bias.float()
+        S = S + bias.to(dt)
     return S
 
 
@@ -100,9 +102,10 @@ def normalize_rows(x, eps: float = 1e-12):
 def ce_fwd_bwd(U, W, labels, bias=None, scale: float = 1.0, grad_out: float = 1.0):
     """Loss and its gradients w.r.t. U, W (and bias) through autograd -- exactly what
     ``loss.backward()`` (SASRec/main.py:249) produces for the lines :217-219."""
-    U = U.detach().float().requires_grad_(True)
-    W = W.detach().float().requires_grad_(True)
-    b = bias.detach().float().requires_grad_(True) if bias is not None else None
+    dt = torch.float64 if U.dtype == torch.float64 else torch.float32
+    U = U.detach().to(dt).requires_grad_(True)
+    W = W.detach().to(dt).requires_grad_(True)
+    b = bias.detach().to(dt).requires_grad_(True) if bias is not None else None
     loss = ce_loss(U, W, labels, b, scale)
     (loss * grad_out).backward()
     return (

@@ -1,5 +1,6 @@
-"""Multi-GPU parity check (run under torchrun on a GPU box; not collected by pytest):
-the row-sharded path over NCCL must reproduce the single-GPU full-table results.
+"""Multi-GPU parity check (run under torchrun on a GPU box; not collected by pytest): the row-sharded path over
+NCCL against the CPU ORACLE in float64 (oracle/reference_path.py on the same bf16-rounded inputs, computed on rank 0
+and broadcast) -- loss, the all-reduced dU, every rank's local dW / dbias shard, and the merged masked top-100.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 tests/multi_gpu_check.py
 
@@ -13,6 +14,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from oracle import reference_path as orc  # noqa: E402  (test infrastructure: the checker)
 from recboard_b200 import ops, sharded, synth  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -31,48 +33,85 @@ def check(name, got, ref, tol):
         print(f"[rank {rank}] {name}: max err / max|ref| = {err:.3e} (tol {tol:.0e}) {'ok' if good else 'FAIL'}", flush=True)
 
 
+def from_rank0(fn, shapes_dtypes):
+    """Run ``fn`` (CPU oracle, float64) on rank 0 only and broadcast its fp32 results."""
+    outs = [torch.empty(shape, dtype=dt, device=dev) for shape, dt in shapes_dtypes]
+    if rank == 0:
+        for o, r in zip(outs, fn()):
+            o.copy_(r.to(o.dtype))
+    for o in outs:
+        dist.broadcast(o, 0)
+    return outs
+
+
 # ---- CE train step, bf16, M=1024, N=200k (+37 to make the shards ragged), d=128
 g = torch.Generator(device=dev).manual_seed(11)
 M, N, d = 1024, 200_037, 128
 U = synth.embeddings(M, d, g, dev, torch.bfloat16, gain=1.5)
 W = synth.embeddings(N, d, g, dev, torch.bfloat16, gain=1.5)
 labels = synth.zipf_ids(M, N, g, dev)
-Uf, Wf = U.clone().requires_grad_(True), W.clone().requires_grad_(True)
-ref_loss = ops.fused_ce(Uf, Wf, labels)
-ref_loss.backward()
+bias = (torch.randn(N, device=dev, generator=g) * 0.2)
 lo, hi = sharded.shard_bounds(N, world, rank)
+
+
+def oracle_ce(with_bias):
+    torch.set_num_threads(os.cpu_count() or 1)
+    loss, dU, dW, db = orc.ce_fwd_bwd(U.cpu().double(), W.cpu().double(), labels.cpu(), bias.cpu().double() if with_bias else None)
+    return [loss.reshape(1), dU, dW] + ([db] if with_bias else [])
+
+
+ref_loss, ref_dU, ref_dW = from_rank0(lambda: oracle_ce(False), [((1,), torch.float32), ((M, d), torch.float32), ((N, d), torch.float32)])
 Us, Ws = U.clone().requires_grad_(True), W[lo:hi].clone().requires_grad_(True)
 loss = sharded.sharded_fused_ce(Us, Ws, labels, lo)
 loss.backward()
-check("CE loss", loss.detach().reshape(1), ref_loss.detach().reshape(1), 1e-5)
-check("CE dU", Us.grad, Uf.grad, 2.0 ** -7)   # both sides are bf16 tensors: one ulp of the largest element is 2^-8
-check("CE dW shard", Ws.grad, Wf.grad[lo:hi], 2.0 ** -7)
+check("CE loss vs fp64 oracle", loss.detach().reshape(1), ref_loss, 1e-5)
+check("CE dU vs fp64 oracle", Us.grad, ref_dU, 2e-3 + 2.0 ** -8)    # north_star bf16 tolerance + the bf16 storage of the gradient
+check("CE dW shard vs fp64 oracle", Ws.grad, ref_dW[lo:hi], 2e-3 + 2.0 ** -8)
+
+# the parameter-with-pad-row route: the rank's whole (n_shard + 1, d) parameter, dW added into its existing gradient
+Wp = torch.cat([torch.zeros(1, d, dtype=torch.bfloat16, device=dev), W[lo:hi]]).requires_grad_(True)
+Wp.grad = torch.zeros_like(Wp)
+Us1 = U.clone().requires_grad_(True)
+loss1 = sharded.sharded_fused_ce(Us1, Wp, labels, lo, n_skip=1, accumulate=True)
+loss1.backward()
+check("CE (n_skip, accumulate) loss", loss1.detach().reshape(1), ref_loss, 1e-5)
+check("CE (n_skip, accumulate) dW shard", Wp.grad[1:], ref_dW[lo:hi], 2e-3 + 2.0 ** -8)
+ok &= bool((Wp.grad[0] == 0).all())
 
 # ---- BERT4Rec-style bias head (config 5 shape scaled down): bias shard + dbias shard
-bias = (torch.randn(N, device=dev, generator=g) * 0.2)
-Ub, Wb, bb = U.clone().requires_grad_(True), W.clone().requires_grad_(True), bias.clone().requires_grad_(True)
-ref_b = ops.fused_ce(Ub, Wb, labels, bias=bb)
-ref_b.backward()
+ref_lb, ref_dUb, ref_dWb, ref_db = from_rank0(lambda: oracle_ce(True), [((1,), torch.float32), ((M, d), torch.float32),
+                                                                         ((N, d), torch.float32), ((N,), torch.float32)])
 Us2, Ws2, bs2 = U.clone().requires_grad_(True), W[lo:hi].clone().requires_grad_(True), bias[lo:hi].clone().requires_grad_(True)
 loss_b = sharded.sharded_fused_ce(Us2, Ws2, labels, lo, bias_shard=bs2)
 loss_b.backward()
-check("CE+bias loss", loss_b.detach().reshape(1), ref_b.detach().reshape(1), 1e-5)
-check("CE+bias dU", Us2.grad, Ub.grad, 2.0 ** -7)
-check("CE+bias dW shard", Ws2.grad, Wb.grad[lo:hi], 2.0 ** -7)
-check("CE+bias dbias shard", bs2.grad, bb.grad[lo:hi], 1e-4)
+check("CE+bias loss vs fp64 oracle", loss_b.detach().reshape(1), ref_lb, 1e-5)
+check("CE+bias dU vs fp64 oracle", Us2.grad, ref_dUb, 2e-3 + 2.0 ** -8)
+check("CE+bias dW shard vs fp64 oracle", Ws2.grad, ref_dWb[lo:hi], 2e-3 + 2.0 ** -8)
+check("CE+bias dbias shard vs fp64 oracle", bs2.grad, ref_db[lo:hi], 2e-3)
 
 # ---- HSTU-style retrieval: d=256, K=100, cosine scores, sharded table
 B, N2, d2, K = 512, 300_011, 256, 100
 Uq = ops.normalize_rows(synth.embeddings(B, d2, g, dev, torch.float32), out_dtype=torch.bfloat16)
 W2 = ops.normalize_rows(synth.embeddings(N2, d2, g, dev, torch.float32), out_dtype=torch.bfloat16)
 crow, col = synth.seen_csr(B, N2, g, dev)
-rv, ri = ops.topk_eval(Uq, W2, K, crow, col)
+
+
+def oracle_topk():
+    S = orc.mask_seen(orc.score_dense(Uq.cpu().double(), W2.cpu().double()), crow.cpu(), col.cpu())
+    v, i = orc.topk_sorted(S, K + 1)
+    return [v, i]
+
+
+rv, ri = from_rank0(oracle_topk, [((B, K + 1), torch.float32), ((B, K + 1), torch.int64)])
 lo2, hi2 = sharded.shard_bounds(N2, world, rank)
 sv, si = sharded.sharded_topk(Uq, W2[lo2:hi2].contiguous(), K, lo2, crow, col)
-check("top-100 values", sv, rv, 1e-6)
-same = float((si == ri).float().mean())
+check("top-100 values vs fp64 oracle", sv, rv[:, :K], 2e-6)
+gap_ok = (rv[:, :-1] - rv[:, 1:]) > 4e-6                           # neighbours the fp32 arithmetic can tell apart
+agree = (si.long() == ri[:, :K]) | ~gap_ok[:, :K] | ~torch.cat([torch.ones_like(gap_ok[:, :1]), gap_ok[:, :K - 1]], 1)
+same = float(agree.float().mean())
 if rank == 0:
-    print(f"[rank 0] top-100 ids identical: {same:.6f}", flush=True)
+    print(f"[rank 0] top-100 ids identical wherever the oracle's neighbours are > 4e-6 apart: {same:.6f} "
+          f"(exactly identical: {float((si.long() == ri[:, :K]).float().mean()):.6f})", flush=True)
 ok &= same == 1.0
 
 flag = torch.tensor([1.0 if ok else 0.0], device=dev)
