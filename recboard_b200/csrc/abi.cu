@@ -796,6 +796,7 @@ struct TopkLayout {
   long long n0;
   Plan p, pp;
   int* crow32; int* col32; float* tmax; RowLadder* ladder; int* cand_cnt; int* overflow; uint2* cand;
+  int* fb_count; int* fb_list; unsigned long long* fb_part;
 };
 static TopkLayout topk_layout(Bump& b, long long B, long long N, int d, int mode, int K, bool seen, long long nnz, int sms) {
   TopkLayout l{};
@@ -815,6 +816,9 @@ static TopkLayout topk_layout(Bump& b, long long B, long long N, int d, int mode
   l.cand_cnt = b.take<int>(static_cast<size_t>(B) * l.n_sub);
   l.overflow = b.take<int>(B);
   l.cand = b.take<uint2>(static_cast<size_t>(B) * l.n_sub * l.candcap);
+  l.fb_count = b.take<int>(1);
+  l.fb_list = b.take<int>(B);
+  l.fb_part = b.take<unsigned long long>(static_cast<size_t>(FB_ROWS) * FB_PARTS * 256);
   return l;
 }
 
@@ -884,8 +888,8 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
   if (int r = launch_sweep_topk(mode, kc_for(d, mode), ts, ty, a, pp.grid, st, xt)) return r;
   // 2. the ladder
   const int grid_w = static_cast<int>((B * 32 + 127) / 128);
-  if (K <= 128) tilemax_select_kernel<4><<<grid_w, 128, 0, st>>>(tmax, n0_tiles, B, K, ladder);
-  else tilemax_select_kernel<8><<<grid_w, 128, 0, st>>>(tmax, n0_tiles, B, K, ladder);
+  if (K <= 128) tilemax_select_kernel<4><<<grid_w, 128, 0, st>>>(tmax, n0_tiles, B, K, ladder, lay.fb_count);
+  else tilemax_select_kernel<8><<<grid_w, 128, 0, st>>>(tmax, n0_tiles, B, K, ladder, lay.fb_count);
   RB_LAUNCH_CHECK("tilemax_select_kernel");
   // 3. the candidate sweep over the whole catalog
   a.n_strm = (int)N; a.n_stat_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles; a.n_splits = p.n_splits;
@@ -893,23 +897,36 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
   // 4. + 5. finish
   const int id_add = static_cast<int>(id_base);
   const int grid_r = static_cast<int>((B + 3) / 4);
+  const int n_items = static_cast<int>(N);
+  long long n_rows_ll = B;
+  auto fallback = [&](auto kern, const void* Up, const void* Wp) -> int {
+    int per_sm = 0;
+    RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FB_THREADS, 0));
+    if (per_sm < 1) return fail(RB_E_UNSUPPORTED, "topk_fallback_coop_kernel does not fit on this device");
+    const int grid = std::min(per_sm, 2) * dv.sms;
+    int dd = d, kk = K, ia = id_add, ni = n_items;
+    float sc = scale;
+    const int* ovf = overflow;
+    void* params[] = {&Up, &Wp, (void*)&bias, &sc, &dd, &n_rows_ll, &ni, (void*)&crow32, (void*)&col32, &kk, &ia, (void*)&top_vals,
+                      (void*)&top_ids, (void*)&ovf, (void*)&lay.fb_count, (void*)&lay.fb_list, (void*)&lay.fb_part};
+    RB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(grid), dim3(FB_THREADS), params, 0, st));
+    RB_LAUNCH_CHECK("topk_fallback_coop_kernel");
+    return 0;
+  };
   if (dtype == RB_DTYPE_BF16) {
     const __nv_bfloat16* Ub = static_cast<const __nv_bfloat16*>(U); const __nv_bfloat16* Wb = static_cast<const __nv_bfloat16*>(W);
     if (K <= 128) topk_from_cands_kernel<__nv_bfloat16, 4><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, cand, cand_cnt, n_sub, candcap, crow32, col32, K, id_add, top_vals, top_ids, overflow);
     else topk_from_cands_kernel<__nv_bfloat16, 8><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, cand, cand_cnt, n_sub, candcap, crow32, col32, K, id_add, top_vals, top_ids, overflow);
     RB_LAUNCH_CHECK("topk_from_cands_kernel");
-    if (K <= 128) topk_refine_kernel<__nv_bfloat16, 4><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, crow32, col32, K, id_add, top_vals, top_ids, overflow);
-    else topk_refine_kernel<__nv_bfloat16, 8><<<grid_r, 128, 0, st>>>(Ub, Wb, bias, scale, d, B, (int)N, crow32, col32, K, id_add, top_vals, top_ids, overflow);
-  } else {
-    const float* Uf = static_cast<const float*>(U); const float* Wf = static_cast<const float*>(W);
-    if (K <= 128) topk_from_cands_kernel<float, 4><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, cand, cand_cnt, n_sub, candcap, crow32, col32, K, id_add, top_vals, top_ids, overflow);
-    else topk_from_cands_kernel<float, 8><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, cand, cand_cnt, n_sub, candcap, crow32, col32, K, id_add, top_vals, top_ids, overflow);
-    RB_LAUNCH_CHECK("topk_from_cands_kernel");
-    if (K <= 128) topk_refine_kernel<float, 4><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, crow32, col32, K, id_add, top_vals, top_ids, overflow);
-    else topk_refine_kernel<float, 8><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, crow32, col32, K, id_add, top_vals, top_ids, overflow);
+    if (K <= 128) return fallback(topk_fallback_coop_kernel<__nv_bfloat16, 4>, U, W);
+    return fallback(topk_fallback_coop_kernel<__nv_bfloat16, 8>, U, W);
   }
-  RB_LAUNCH_CHECK("topk_refine_kernel");
-  return 0;
+  const float* Uf = static_cast<const float*>(U); const float* Wf = static_cast<const float*>(W);
+  if (K <= 128) topk_from_cands_kernel<float, 4><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, cand, cand_cnt, n_sub, candcap, crow32, col32, K, id_add, top_vals, top_ids, overflow);
+  else topk_from_cands_kernel<float, 8><<<grid_r, 128, 0, st>>>(Uf, Wf, bias, scale, d, B, (int)N, cand, cand_cnt, n_sub, candcap, crow32, col32, K, id_add, top_vals, top_ids, overflow);
+  RB_LAUNCH_CHECK("topk_from_cands_kernel");
+  if (K <= 128) return fallback(topk_fallback_coop_kernel<float, 4>, U, W);
+  return fallback(topk_fallback_coop_kernel<float, 8>, U, W);
 }
 
 extern "C" int rb_topk_merge(const float* vals, const int32_t* ids, int R, int64_t B, int K, float* out_vals,

@@ -1,6 +1,7 @@
 // HBM-bound helper kernels around the sweep engine: row gather, operand preparation, partial merges, the top-K
 // finishing kernels (the deterministic scatter-add lives in scatter.cuh).
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include "ptx.cuh"
 #include "sweep.cuh"
@@ -579,11 +580,13 @@ __device__ __forceinline__ T warp_blocked_get(const T (&v)[E], int idx) {
 // passes; the level counters are zeroed.
 template <int E>
 __global__ void __launch_bounds__(128)
-tilemax_select_kernel(const float* __restrict__ T, int n_tiles, long long n_rows, int K, RowLadder* __restrict__ ladder) {
+tilemax_select_kernel(const float* __restrict__ T, int n_tiles, long long n_rows, int K, RowLadder* __restrict__ ladder,
+                      int* __restrict__ fb_count) {
   __shared__ float stage_s[4][32 * E];
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n_rows) return;
+  if (row == 0 && lane == 0) *fb_count = 0;   // the fallback's slot counter starts every call at zero
   float* stage = stage_s[threadIdx.x >> 5];
   const float* t = T + row * n_tiles;
   const uint32_t lt = (1u << lane) - 1u;
@@ -686,15 +689,13 @@ __device__ __forceinline__ float exact_logit(const float* __restrict__ u, const 
 }
 
 // ---- top-K finish: the row's candidates are (group maximum, group id) pairs of aligned groups of 4 items that
-// reached the row's running threshold in the EPI_CAND sweep (a few hundred).  First the cut T = K-th largest
-// maximum among the CLEAN groups (each is the score of a distinct unseen item, so the K-th best item scores >= T
-// and every top-K member sits in a group whose maximum reaches T); then only the groups that reach T (about K,
-// plus the dirty ones) are re-scored exactly in fp32, seen items dropped (UniSRec/main.py:413), and the K best by
-// (score desc, id asc) kept.  Rows with an overflowed sub-list (or more than GROUPS_CAP candidates) are flagged
-// for the fallback below.  One warp per row: the sub-lists are first flattened into shared memory (counts
-// scanned 32 sub-lists at a time), then a lane scores one item, eight groups per step.
-constexpr int GROUPS_CAP = 1024;
-
+// reached the row's running threshold in the EPI_CAND sweep (a few hundred, in n_sub sub-lists in global memory,
+// L2-resident).  Two streaming trips over them, nothing table-sized in shared memory:
+//   1. the cut T = K-th largest maximum among the CLEAN groups (each is the score of a distinct unseen item, so the
+//      K-th best item scores >= T and every top-K member sits in a group whose maximum reaches T);
+//   2. the groups that reach T (about K, plus the dirty ones) are re-scored exactly in fp32, eight groups = 32 items
+//      per step as they come, seen items dropped (UniSRec/main.py:413), the K best by (score desc, id asc) kept.
+// Only a sub-list that ran over its own capacity flags the row for the fallback below.  One warp per row.
 template <typename TW, int E>
 __global__ void __launch_bounds__(128)
 topk_from_cands_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const float* __restrict__ bias, float scale,
@@ -704,84 +705,70 @@ topk_from_cands_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const
                        int* __restrict__ out_ids, int* __restrict__ overflow) {
   __shared__ __align__(16) float u_s[4][256];
   __shared__ unsigned long long stage_s[4][256];
-  __shared__ uint2 clist_s[4][GROUPS_CAP];
+  __shared__ float fstage_s[4][32 * E];
+  __shared__ unsigned int queue_s[4][64];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 4 + wib;
   if (row >= n_rows) return;
   const int* cnts = cand_cnt + row * n_sub;
-  uint2* clist = clist_s[wib];
-  // ---- flatten the sub-lists
-  int total = 0;
+  const uint2* lists = cand + row * n_sub * cap;
+  const uint32_t lt = (1u << lane) - 1u;
+  // ---- a sub-list that overflowed its capacity lost candidates: the row goes to the exact scan
   bool ovf = false;
-  for (int sb = 0; sb < n_sub; sb += 32) {
-    const int sidx = sb + lane;
-    int c = (sidx < n_sub) ? cnts[sidx] : 0;
-    if (c > cap) { ovf = true; c = 0; }
-    int incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const int off = total + incl - c;
-    const int block_total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total + block_total <= GROUPS_CAP) {
-      if (n_sub <= 32) {   // few long sub-lists (large batches): the whole warp copies each one, coalesced
-        for (int j = 0; j < n_sub; ++j) {
-          const int cj = __shfl_sync(0xffffffffu, c, j), oj = __shfl_sync(0xffffffffu, off, j);
-          const uint2* gl = cand + (row * n_sub + j) * cap;
-          for (int e = lane; e < cj; e += 32) clist[oj + e] = __ldg(gl + e);
-        }
-      } else {             // many short sub-lists (small batches, many splits): one lane per sub-list
-        const uint2* gl = cand + (row * n_sub + sidx) * cap;
-        for (int e = 0; e < c; ++e) clist[off + e] = __ldg(gl + e);
-      }
-    }
-    total += block_total;
-  }
-  ovf = __any_sync(0xffffffffu, ovf) || total > GROUPS_CAP;
+  for (int sb = lane; sb < n_sub; sb += 32) ovf |= cnts[sb] > cap;
+  ovf = __any_sync(0xffffffffu, ovf);
   if (lane == 0) overflow[row] = ovf ? 1 : 0;
   if (ovf) return;
-  __syncwarp();
-  // ---- the cut: K-th largest maximum among the clean groups (-inf when there are fewer than K)
+  // ---- trip 1: the cut = K-th largest maximum among the clean groups (-inf when there are fewer than K)
   float cut = -INFINITY;
   {
+    float* fstage = fstage_s[wib];
     float bestf[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) bestf[e] = -INFINITY;
-    for (int base = 0; base < total; base += 32 * E) {
+    float kthf = -INFINITY;
+    int ns = 0;
+    auto flushf = [&]() {
+      __syncwarp();
       float cur[E];
 #pragma unroll
       for (int e = 0; e < E; ++e) {
-        const int i = base + lane * E + e;
-        cur[e] = -INFINITY;
-        if (i < total) {
-          const uint2 c = clist[i];
-          if (!(c.y & CAND_DIRTY)) cur[e] = __uint_as_float(c.x);
-        }
+        const int i = lane * E + e;
+        cur[e] = (i < ns) ? fstage[i] : -INFINITY;
       }
       warp_bitonic_sort_desc<float, E>(cur);
       warp_topk_absorb<float, E>(bestf, cur);
+      kthf = warp_blocked_get<float, E>(bestf, K - 1);
+      ns = 0;
+      __syncwarp();
+    };
+    for (int j = 0; j < n_sub; ++j) {
+      const int c = cnts[j];
+      const uint2* gl = lists + static_cast<long long>(j) * cap;
+      for (int e0 = 0; e0 < c; e0 += 32) {
+        const int e = e0 + lane;
+        float v = -INFINITY;
+        if (e < c) {
+          const uint2 x = __ldg(gl + e);
+          if (!(x.y & CAND_DIRTY)) v = __uint_as_float(x.x);
+        }
+        const bool pass = v > kthf;
+        const uint32_t m = __ballot_sync(0xffffffffu, pass);
+        if (m != 0u) {
+          if (pass) fstage[ns + __popc(m & lt)] = v;
+          ns += __popc(m);
+          if (ns > 32 * E - 32) flushf();
+        }
+      }
     }
-    cut = warp_blocked_get<float, E>(bestf, K - 1);
+    if (ns > 0) flushf();
+    cut = kthf;
     if (cut > -INFINITY) cut -= fabsf(cut) * 3.8146973e-06f;   // tensor-core vs exact fp32 scores differ in the last bits
   }
-  // ---- keep the groups that reach the cut (compaction in place: the write index never passes the read index)
-  int kept = 0;
-  for (int base = 0; base < total; base += 32) {
-    const int i = base + lane;
-    uint2 c = make_uint2(0u, 0u);
-    bool keep = false;
-    if (i < total) { c = clist[i]; keep = __uint_as_float(c.x) >= cut; }
-    const uint32_t m = __ballot_sync(0xffffffffu, keep);
-    __syncwarp();
-    if (keep) clist[kept + __popc(m & ((1u << lane) - 1u))] = c;
-    kept += __popc(m);
-    __syncwarp();
-  }
-  total = kept;
+  // ---- trip 2: exact scores of the groups that reach the cut
   float* u = u_s[wib];
   unsigned long long* stage = stage_s[wib];
+  unsigned int* queue = queue_s[wib];
   for (int k = lane; k < 256; k += 32) u[k] = (k < d) ? static_cast<float>(U[row * d + k]) : 0.f;
   __syncwarp();
   int s_lo = 0, s_hi = 0;
@@ -791,7 +778,6 @@ topk_from_cands_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const
   for (int e = 0; e < E; ++e) best[e] = 0ull;
   unsigned long long kth = 0ull;
   int ns = 0;
-  const uint32_t lt = (1u << lane) - 1u;
   auto flush = [&]() {
     __syncwarp();
     for (int base = 0; base < ns; base += 32 * E) {
@@ -808,9 +794,10 @@ topk_from_cands_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const
     ns = 0;
     __syncwarp();
   };
-  for (int base = 0; base < total; base += 8) {
-    const int gi = base + (lane >> 2);
-    const int item = (gi < total) ? (static_cast<int>(clist[gi].y & ~CAND_DIRTY) << 2) + (lane & 3) : n_items;
+  // eight queued groups = 32 items, one per lane
+  auto score_step = [&](int n_groups) {
+    const int gi = lane >> 2;
+    const int item = (gi < n_groups) ? (static_cast<int>(queue[gi]) << 2) + (lane & 3) : n_items;
     unsigned long long key = 0ull;
     if (item < n_items) key = topk_key(exact_logit<TW>(u, W + static_cast<long long>(item) * d, d, scale, bias, item), item);
     bool pass = key > kth;
@@ -826,7 +813,36 @@ topk_from_cands_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const
     if (pass) stage[ns + __popc(m & lt)] = key;
     ns += __popc(m);
     if (ns > 256 - 32) flush();
+  };
+  int nq = 0;   // groups waiting in the queue (< 8 between steps, up to 8 + 31 inside one)
+  for (int j = 0; j < n_sub; ++j) {
+    const int c = cnts[j];
+    const uint2* gl = lists + static_cast<long long>(j) * cap;
+    for (int e0 = 0; e0 < c; e0 += 32) {
+      const int e = e0 + lane;
+      bool keep = false;
+      unsigned int gid = 0u;
+      if (e < c) {
+        const uint2 x = __ldg(gl + e);
+        keep = __uint_as_float(x.x) >= cut;
+        gid = x.y & ~CAND_DIRTY;
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, keep);
+      if (keep) queue[nq + __popc(m & lt)] = gid;
+      nq += __popc(m);
+      __syncwarp();
+      while (nq >= 8) {
+        score_step(8);
+        __syncwarp();
+        const unsigned int moved = (lane + 8 < nq) ? queue[lane + 8] : 0u;   // nq <= 39: one lane-wide shift suffices
+        __syncwarp();
+        if (lane + 8 < nq) queue[lane] = moved;
+        nq -= 8;
+        __syncwarp();
+      }
+    }
   }
+  if (nq > 0) score_step(nq);
   flush();
 #pragma unroll
   for (int e = 0; e < E; ++e) {
@@ -845,123 +861,167 @@ topk_from_cands_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const
   }
 }
 
-// ---- top-K fallback (rows flagged in `only`; all rows when `only` is null): an exact scan of the row's whole
-// catalog (fp32 FMA over the stored operands), skipping seen ids, keeping the K best by (score desc, id asc).
-// Only rows whose candidate lists overflowed come here (massive ties, catalogs too small for a threshold).
-// One warp per row; lane <-> item.
+// ---- top-K fallback: an exact scan of a row's whole catalog (fp32 FMA over the stored operands), skipping seen ids,
+// keeping the K best by (score desc, id asc), for the rows whose candidate lists overflowed (massive ties, catalogs too
+// small for a threshold; essentially never on a large catalog with spread scores, but then it must not take 0.4 s per
+// row either).  ONE cooperative launch that returns at once when no row is flagged:
+//   phase 0  the flagged rows are compacted into a list (atomic slot counter)
+//   phase 1  work items (flagged row, part of the catalog): one WARP scans FB_PARTS-th of the tiles (lane <-> item) and
+//            leaves its sorted top-K keys in the workspace
+//   phase 2  one warp per flagged row merges the parts' lists.
+// More than FB_ROWS flagged rows go through several rounds of phases 1-2.
+constexpr int FB_PARTS = 128;
+constexpr int FB_ROWS = 64;
+constexpr int FB_THREADS = 256;
+
 template <typename TW, int E>
-__global__ void __launch_bounds__(128)
-topk_refine_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const float* __restrict__ bias, float scale, int d,
-                   long long n_rows, int n_items, const int* __restrict__ seen_crow, const int* __restrict__ seen_col,
-                   int K, int id_add, float* __restrict__ out_vals, int* __restrict__ out_ids,
-                   const int* __restrict__ only) {
-  __shared__ __align__(16) float u_s[4][256];
-  __shared__ unsigned long long cand_s[4][256];
+__global__ void __launch_bounds__(FB_THREADS)
+topk_fallback_coop_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const float* __restrict__ bias, float scale, int d,
+                          long long n_rows, int n_items, const int* __restrict__ seen_crow, const int* __restrict__ seen_col,
+                          int K, int id_add, float* __restrict__ out_vals, int* __restrict__ out_ids,
+                          const int* __restrict__ overflow, int* __restrict__ fb_count, int* __restrict__ fb_list,
+                          unsigned long long* __restrict__ fb_part) {
+  __shared__ __align__(16) float u_s[FB_THREADS / 32][256];
+  __shared__ unsigned long long cand_s[FB_THREADS / 32][256];
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * 4 + wib;
-  if (row >= n_rows) return;
-  if (only != nullptr && only[row] == 0) return;
+  const long long gtid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long gthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+  const int gwarp = static_cast<int>(gtid >> 5), n_gwarps = static_cast<int>(gthreads >> 5);
+  for (long long i = gtid; i < n_rows; i += gthreads)
+    if (overflow[i] != 0) fb_list[atomicAdd(fb_count, 1)] = static_cast<int>(i);
+  grid.sync();
+  const int n_flag = *fb_count;
+  if (n_flag == 0) return;   // grid-uniform
   float* u = u_s[wib];
   unsigned long long* cand = cand_s[wib];
-  for (int k = lane; k < 256; k += 32) u[k] = (k < d) ? static_cast<float>(U[row * d + k]) : 0.f;
-  __syncwarp();
-  int s_lo = 0, s_hi = 0;
-  if (seen_crow != nullptr) { s_lo = seen_crow[row]; s_hi = seen_crow[row + 1]; }
-  unsigned long long best[E];
-#pragma unroll
-  for (int e = 0; e < E; ++e) best[e] = 0ull;
-  unsigned long long kth = 0ull;
-  int ncand = 0;
   const uint32_t lt = (1u << lane) - 1u;
   const int n_tiles = (n_items + 127) / 128;
-
-  auto flush = [&]() {
-    for (int base = 0; base < ncand; base += 32 * E) {
-      unsigned long long cur[E];
+  const int KP = 32 * E;   // keys kept per part (>= K)
+  for (int r0 = 0; r0 < n_flag; r0 += FB_ROWS) {
+    const int n_round = min(FB_ROWS, n_flag - r0);
+    // ---- phase 1
+    for (int w = gwarp; w < n_round * FB_PARTS; w += n_gwarps) {
+      const int ri = w / FB_PARTS, part = w % FB_PARTS;
+      const long long row = fb_list[r0 + ri];
+      const int tb = static_cast<int>(static_cast<long long>(part) * n_tiles / FB_PARTS);
+      const int te = static_cast<int>(static_cast<long long>(part + 1) * n_tiles / FB_PARTS);
+      __syncwarp();
+      for (int k = lane; k < 256; k += 32) u[k] = (k < d) ? static_cast<float>(U[row * d + k]) : 0.f;
+      __syncwarp();
+      int s_lo = 0, s_hi = 0;
+      if (seen_crow != nullptr) { s_lo = seen_crow[row]; s_hi = seen_crow[row + 1]; }
+      unsigned long long best[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) best[e] = 0ull;
+      unsigned long long kth = 0ull;
+      int ncand = 0;
+      auto flush = [&]() {
+        for (int base = 0; base < ncand; base += 32 * E) {
+          unsigned long long cur[E];
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const int i = base + lane * E + e;
+            cur[e] = (i < ncand) ? cand[i] : 0ull;
+          }
+          warp_bitonic_sort_desc<unsigned long long, E>(cur);
+          warp_topk_absorb<unsigned long long, E>(best, cur);
+        }
+        kth = warp_blocked_get<unsigned long long, E>(best, K - 1);
+        ncand = 0;
+        __syncwarp();
+      };
+      for (int tile = tb; tile < te; ++tile) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        int item[4];
+        const TW* wrow[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          item[q] = tile * 128 + q * 32 + lane;
+          wrow[q] = W + static_cast<long long>(min(item[q], n_items - 1)) * d;
+        }
+        for (int k = 0; k < d; k += 8) {  // d % 8 == 0
+          const float4 ua = *reinterpret_cast<const float4*>(u + k);
+          const float4 ub = *reinterpret_cast<const float4*>(u + k + 4);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float w8[8];
+            if constexpr (sizeof(TW) == 2) {
+              const uint4 raw = __ldg(reinterpret_cast<const uint4*>(wrow[q] + k));
+              w8[0] = __uint_as_float(raw.x << 16); w8[1] = __uint_as_float(raw.x & 0xFFFF0000u);
+              w8[2] = __uint_as_float(raw.y << 16); w8[3] = __uint_as_float(raw.y & 0xFFFF0000u);
+              w8[4] = __uint_as_float(raw.z << 16); w8[5] = __uint_as_float(raw.z & 0xFFFF0000u);
+              w8[6] = __uint_as_float(raw.w << 16); w8[7] = __uint_as_float(raw.w & 0xFFFF0000u);
+            } else {
+              const float4 r0v = __ldg(reinterpret_cast<const float4*>(wrow[q] + k));
+              const float4 r1v = __ldg(reinterpret_cast<const float4*>(wrow[q] + k + 4));
+              w8[0] = r0v.x; w8[1] = r0v.y; w8[2] = r0v.z; w8[3] = r0v.w; w8[4] = r1v.x; w8[5] = r1v.y; w8[6] = r1v.z; w8[7] = r1v.w;
+            }
+            acc[q] = __fmaf_rn(ua.x, w8[0], acc[q]); acc[q] = __fmaf_rn(ua.y, w8[1], acc[q]);  // same chain as exact_logit
+            acc[q] = __fmaf_rn(ua.z, w8[2], acc[q]); acc[q] = __fmaf_rn(ua.w, w8[3], acc[q]);
+            acc[q] = __fmaf_rn(ub.x, w8[4], acc[q]); acc[q] = __fmaf_rn(ub.y, w8[5], acc[q]);
+            acc[q] = __fmaf_rn(ub.z, w8[6], acc[q]); acc[q] = __fmaf_rn(ub.w, w8[7], acc[q]);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bool valid = item[q] < n_items;
+          float sc = __fmul_rn(acc[q], scale);
+          if (bias != nullptr && valid) sc = __fmaf_rn(acc[q], scale, __ldg(bias + item[q]));
+          const unsigned long long key = valid ? topk_key(sc, item[q]) : 0ull;
+          bool pass = key > kth;
+          if (pass && s_hi > s_lo) {  // seen items never rank (UniSRec/main.py:413)
+            int lo = s_lo, hi = s_hi;
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if (__ldg(seen_col + mid) < item[q]) lo = mid + 1; else hi = mid;
+            }
+            if (lo < s_hi && __ldg(seen_col + lo) == item[q]) pass = false;
+          }
+          const uint32_t m = __ballot_sync(0xffffffffu, pass);
+          if (pass) cand[ncand + __popc(m & lt)] = key;
+          ncand += __popc(m);
+          __syncwarp();
+          if (ncand > 256 - 32) flush();
+        }
+      }
+      flush();
+      unsigned long long* dstp = fb_part + (static_cast<long long>(ri) * FB_PARTS + part) * KP;
+#pragma unroll
+      for (int e = 0; e < E; ++e) dstp[lane * E + e] = best[e];
+    }
+    grid.sync();
+    // ---- phase 2
+    for (int ri = gwarp; ri < n_round; ri += n_gwarps) {
+      const long long row = fb_list[r0 + ri];
+      unsigned long long best[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) best[e] = 0ull;
+      for (int part = 0; part < FB_PARTS; ++part) {
+        const unsigned long long* srcp = fb_part + (static_cast<long long>(ri) * FB_PARTS + part) * KP;
+        unsigned long long cur[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) cur[e] = srcp[lane * E + e];   // already sorted descending, blocked layout
+        warp_topk_absorb<unsigned long long, E>(best, cur);
+      }
 #pragma unroll
       for (int e = 0; e < E; ++e) {
-        const int i = base + lane * E + e;
-        cur[e] = (i < ncand) ? cand[i] : 0ull;
-      }
-      warp_bitonic_sort_desc<unsigned long long, E>(cur);
-      warp_topk_absorb<unsigned long long, E>(best, cur);
-    }
-    kth = warp_blocked_get<unsigned long long, E>(best, K - 1);
-    ncand = 0;
-    __syncwarp();
-  };
-
-  {
-   for (int tile = 0; tile < n_tiles; ++tile) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    int item[4];
-    const TW* wrow[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      item[q] = tile * 128 + q * 32 + lane;
-      wrow[q] = W + static_cast<long long>(min(item[q], n_items - 1)) * d;
-    }
-    for (int k = 0; k < d; k += 8) {  // d % 8 == 0
-      const float4 ua = *reinterpret_cast<const float4*>(u + k);
-      const float4 ub = *reinterpret_cast<const float4*>(u + k + 4);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float w[8];
-        if constexpr (sizeof(TW) == 2) {
-          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(wrow[q] + k));
-          w[0] = __uint_as_float(raw.x << 16); w[1] = __uint_as_float(raw.x & 0xFFFF0000u);
-          w[2] = __uint_as_float(raw.y << 16); w[3] = __uint_as_float(raw.y & 0xFFFF0000u);
-          w[4] = __uint_as_float(raw.z << 16); w[5] = __uint_as_float(raw.z & 0xFFFF0000u);
-          w[6] = __uint_as_float(raw.w << 16); w[7] = __uint_as_float(raw.w & 0xFFFF0000u);
-        } else {
-          const float4 r0 = __ldg(reinterpret_cast<const float4*>(wrow[q] + k));
-          const float4 r1 = __ldg(reinterpret_cast<const float4*>(wrow[q] + k + 4));
-          w[0] = r0.x; w[1] = r0.y; w[2] = r0.z; w[3] = r0.w; w[4] = r1.x; w[5] = r1.y; w[6] = r1.z; w[7] = r1.w;
+        const int i = lane * E + e;
+        if (i < K) {
+          const unsigned long long key = best[e];
+          float v = MASKED_SCORE_F;
+          int id = -1;
+          if (key != 0ull) {
+            v = f32_from_orderable(static_cast<uint32_t>(key >> 32));
+            id = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFu)) + id_add;
+          }
+          out_vals[row * K + i] = v;
+          out_ids[row * K + i] = id;
         }
-        acc[q] = __fmaf_rn(ua.x, w[0], acc[q]); acc[q] = __fmaf_rn(ua.y, w[1], acc[q]);  // same chain as exact_logit
-        acc[q] = __fmaf_rn(ua.z, w[2], acc[q]); acc[q] = __fmaf_rn(ua.w, w[3], acc[q]);
-        acc[q] = __fmaf_rn(ub.x, w[4], acc[q]); acc[q] = __fmaf_rn(ub.y, w[5], acc[q]);
-        acc[q] = __fmaf_rn(ub.z, w[6], acc[q]); acc[q] = __fmaf_rn(ub.w, w[7], acc[q]);
       }
     }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const bool valid = item[q] < n_items;
-      float sc = __fmul_rn(acc[q], scale);
-      if (bias != nullptr && valid) sc = __fmaf_rn(acc[q], scale, __ldg(bias + item[q]));
-      const unsigned long long key = valid ? topk_key(sc, item[q]) : 0ull;
-      bool pass = key > kth;
-      if (pass && s_hi > s_lo) {  // seen items never rank (UniSRec/main.py:413)
-        int lo = s_lo, hi = s_hi;
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (__ldg(seen_col + mid) < item[q]) lo = mid + 1; else hi = mid;
-        }
-        if (lo < s_hi && __ldg(seen_col + lo) == item[q]) pass = false;
-      }
-      const uint32_t m = __ballot_sync(0xffffffffu, pass);
-      if (pass) cand[ncand + __popc(m & lt)] = key;
-      ncand += __popc(m);
-      __syncwarp();
-      if (ncand > 256 - 32) flush();
-    }
-   }
-  }
-  flush();
-#pragma unroll
-  for (int e = 0; e < E; ++e) {
-    const int i = lane * E + e;
-    if (i < K) {
-      const unsigned long long key = best[e];
-      float v = MASKED_SCORE_F;
-      int id = -1;
-      if (key != 0ull) {
-        v = f32_from_orderable(static_cast<uint32_t>(key >> 32));
-        id = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFu)) + id_add;
-      }
-      out_vals[row * K + i] = v;
-      out_ids[row * K + i] = id;
-    }
+    if (r0 + FB_ROWS < n_flag) grid.sync();   // the part lists are reused by the next round
   }
 }
 
