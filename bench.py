@@ -164,6 +164,12 @@ class ClockSampler:
 
 
 def run_ours(args):
+    # rank 0 prints ONE JSON line on stdout.  Libraries that log to file descriptor 1 (NCCL prints its version banner
+    # there at NCCL_DEBUG=VERSION and above) must not get in front of it: fd 1 is pointed at stderr for the whole run
+    # and the line goes to a duplicate of the original stdout.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
@@ -464,7 +470,8 @@ def run_ours(args):
             "roofline": roofline, "breakdown": breakdown, "cpu_baseline": cpu_baseline,
             "strong_10m": strong, "config5_50m": c5, "gpu_eager_baseline": eager,
         }
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
     return 0

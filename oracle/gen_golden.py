@@ -319,6 +319,64 @@ def gen_lightgcn_propagation():
     print("lightgcn_prop: nnz", int(A.values().numel()), "layers", int(model.num_layers))
 
 
+def gen_unisrec_evaluate():
+    """the in-tree statement of ``Coach.evaluate`` (UniSRec/main.py:400-447), run UNMODIFIED with a
+    stub ``self`` whose ``monitor`` records what the reference hands to the metric functions: the seen-masked dense
+    ``scores`` (``scores[seen] = -1e23``, :409-413) and the dense multi-hot ``targets`` (:414), per batch, together
+    with the batch size it weights them by (``n=bsz``, :403,430).  Two batches (the second ragged), rows with empty
+    seen lists, a target inside the seen list, multi-target rows."""
+    import types
+    ref = shim.load_reference("UniSRec")
+    N, d = 211, 16
+    g = torch.Generator().manual_seed(2035)
+    W = torch.randn(N, d, generator=g)
+    Item = shim.Field("Item", N)
+    ISeen, IUnseen, Size = shim.Field("ISeen"), shim.Field("IUnseen"), shim.Field("Size")
+    batches, raw = [], []
+    for b, B in enumerate((24, 13)):
+        U = torch.randn(B, d, generator=g)
+        seen = [torch.randperm(N, generator=g)[: int(torch.randint(0, 12, (1,), generator=g))].tolist() for _ in range(B)]
+        seen[0] = []
+        unseen = [torch.randperm(N, generator=g)[: (3 if r % 5 == 4 else 1)].tolist() for r in range(B)]
+        if seen[1]:
+            unseen[1] = [seen[1][0]]          # a target the user has already seen: masked before ranking, never hit
+        scores = U @ W.T
+        batches.append({"dataset": "D", "scores": scores, ISeen: seen, IUnseen: unseen, Size: B})
+        raw.append((U, seen, unseen))
+    recorded = []
+
+    class _Self:
+        pass
+
+    me = _Self()
+    me.dataloader = batches
+    me.Size, me.ISeen, me.IUnseen = Size, ISeen, IUnseen
+    me.device = torch.device("cpu")
+    me.remove_seen = True
+    me.cfg = types.SimpleNamespace(ranking="full")
+    me.datasets = {"D": types.SimpleNamespace(fields=shim._FieldTable({shim.ITEM: Item}))}
+    me.get_res_sys_arch = lambda: types.SimpleNamespace(reset_ranking_buffers=lambda: None)
+    me.dict_to_device = lambda data: data
+    me.model = lambda data, ranking="full": data["scores"].clone()
+    me.monitor = lambda scores, targets, n, reduction, mode, pool: recorded.append((scores.clone(), targets.clone(), n, list(pool)))
+    ref.CoachForUniSRec.evaluate(me, epoch=0, mode="test")
+    out = {"item_table": _np(W), "n_batches": np.int64(len(batches))}
+    for b, (U, seen, unseen) in enumerate(raw):
+        s_m, t_d, n, pool = recorded[2 * b]                     # two monitor calls per batch (:428-447), same tensors
+        assert torch.equal(recorded[2 * b + 1][0], s_m) and pool == ["HITRATE", "PRECISION", "RECALL", "NDCG", "MRR"]
+        crow, col = [0], []
+        for r in seen:
+            col += sorted(set(r)); crow.append(len(col))
+        tcrow, tcol = [0], []
+        for r in unseen:
+            tcol += sorted(set(r)); tcrow.append(len(tcol))
+        out.update({f"U{b}": _np(U), f"seen_crow{b}": np.asarray(crow, np.int64), f"seen_col{b}": np.asarray(col, np.int64),
+                    f"tgt_crow{b}": np.asarray(tcrow, np.int64), f"tgt_col{b}": np.asarray(tcol, np.int64),
+                    f"scores_masked{b}": _np(s_m), f"targets{b}": _np(t_d), f"bsz{b}": np.int64(n)})
+    np.savez_compressed(OUT / "unisrec_evaluate.npz", **out)
+    print("unisrec_evaluate: batches", len(batches), "masked entries", int(sum((r[0] == -1e23).sum() for r in recorded[::2])))
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(1)  # deterministic summation order for the committed vectors
@@ -330,6 +388,7 @@ def main():
     gen_gather_backward()
     gen_pool_and_sampled()
     gen_lightgcn_propagation()
+    gen_unisrec_evaluate()
 
 
 if __name__ == "__main__":

@@ -26,9 +26,12 @@ PARITY PIN STATUS
     propagation): PINNED against outputs of the reference's
     own unmodified code imported in the build container (``oracle/gen_golden.py`` ->
     ``tests/golden/*.npz``; checked by ``tests/test_oracle_golden.py``).
-  * evaluate/metric half: restated from the in-tree ``UniSRec/main.py:400-447`` override; the
-    metric functions themselves live in un-vendored ``freerec==1.0.1`` -> "parity unpinned"
-    for the multi-target IDCG convention (single-target LOU case is convention-free).
+  * evaluate half -- seen masking (``scores[seen] = -1e23`` before ranking) and dense targets: PINNED against the
+    tensors the reference's own ``CoachForUniSRec.evaluate`` (UniSRec/main.py:400-447, imported unmodified) hands to
+    its metric functions (``gen_golden.gen_unisrec_evaluate`` -> ``tests/golden/unisrec_evaluate.npz``).
+  * metric functions (HITRATE / NDCG / RECALL / PRECISION / MRR): they live in un-vendored ``freerec==1.0.1`` and
+    cannot be executed here -> "parity unpinned" for the multi-target IDCG convention (the single-target LOU case
+    every shipped config uses is convention-free: hit = rank < k, ndcg = 1 / log2(rank + 2)).
 """
 from __future__ import annotations
 
@@ -113,6 +116,35 @@ def ce_fwd_bwd(U, W, labels, bias=None, scale: float = 1.0, grad_out: float = 1.
     )
 
 
+def ce_fwd_bwd_chunked(U, W, labels, bias=None, scale: float = 1.0, chunk: int = 512):
+    """The same loss and gradients as ``ce_fwd_bwd`` from the closed form of the CE gradient
+    (G = (softmax(S) - onehot) / M; dU = scale G W; dW = scale G^T U; dbias = sum_i G), query rows ``chunk`` at a time so
+    that only a (chunk, N) block of logits exists -- the arbiter of the full-size parity tests (run in float64, on
+    whatever device the inputs live on; checked against ``ce_fwd_bwd`` itself in tests/test_oracle_golden.py)."""
+    dt = torch.float64 if U.dtype == torch.float64 else torch.float32
+    U, W = U.to(dt), W.to(dt)
+    b = bias.to(dt) if bias is not None else None
+    M = U.shape[0]
+    dU = torch.empty_like(U)
+    dW = torch.zeros_like(W)
+    db = torch.zeros(W.shape[0], dtype=dt, device=W.device) if b is not None else None
+    loss = torch.zeros((), dtype=dt, device=U.device)
+    for lo in range(0, M, chunk):
+        hi = min(lo + chunk, M)
+        S = score_dense(U[lo:hi], W, b, scale)
+        lse = torch.logsumexp(S, dim=1)
+        lab = labels[lo:hi]
+        loss += (lse - S.gather(1, lab[:, None]).squeeze(1)).sum()
+        G = torch.exp(S - lse[:, None])
+        G[torch.arange(hi - lo, device=G.device), lab] -= 1.0
+        G /= M
+        dU[lo:hi] = scale * (G @ W)
+        dW += scale * (G.T @ U[lo:hi])
+        if db is not None:
+            db += G.sum(0)
+    return loss / M, dU, dW, db
+
+
 def ce_rowstats(U, W, labels, bias=None, scale: float = 1.0):
     """(row_max, row_sumexp, label_logit) -- the partials a shard reports."""
     S = score_dense(U, W, bias, scale)
@@ -135,8 +167,8 @@ def lists_to_csr(rows: Sequence[Sequence[int]]) -> Tuple[torch.Tensor, torch.Ten
 
 def csr_to_dense(crow: torch.Tensor, col: torch.Tensor, n_cols: int) -> torch.Tensor:
     B = crow.numel() - 1
-    dense = torch.zeros(B, n_cols, dtype=torch.float32)
-    rows = torch.repeat_interleave(torch.arange(B), crow[1:] - crow[:-1])
+    dense = torch.zeros(B, n_cols, dtype=torch.float32, device=crow.device)
+    rows = torch.repeat_interleave(torch.arange(B, device=crow.device), crow[1:] - crow[:-1])
     dense[rows, col] = 1.0
     return dense
 

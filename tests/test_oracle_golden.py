@@ -163,3 +163,35 @@ def test_lightgcn_propagation(golden):
         avg = avg + x / (L + 1)
     close(avg[:nU], g["user_out"])
     close(avg[nU:], g["item_out"])
+
+
+def test_evaluate_mask_and_targets_match_reference_evaluate(golden):
+    """a8/a9 pinned: the oracle's ``mask_seen`` / ``csr_to_dense`` against what the reference's own
+    ``CoachForUniSRec.evaluate`` (UniSRec/main.py:400-447, run unmodified by oracle/gen_golden.py) handed to its metric
+    functions -- seen-masked scores (-1e23 before ranking, also when the target itself was seen) and dense targets."""
+    g = golden("unisrec_evaluate")
+    W = T(g["item_table"])
+    for b in range(int(g["n_batches"])):
+        U = T(g[f"U{b}"])
+        crow, col = T(g[f"seen_crow{b}"]), T(g[f"seen_col{b}"])
+        tcrow, tcol = T(g[f"tgt_crow{b}"]), T(g[f"tgt_col{b}"])
+        masked = orc.mask_seen(orc.score_dense(U, W), crow, col)
+        assert torch.equal(masked == orc.MASK_VALUE, T(g[f"scores_masked{b}"]) == -1e23)
+        torch.testing.assert_close(masked, T(g[f"scores_masked{b}"]), rtol=1e-6, atol=1e-6)
+        assert torch.equal(orc.csr_to_dense(tcrow, tcol, W.shape[0]), T(g[f"targets{b}"]))
+        assert int(g[f"bsz{b}"]) == U.shape[0]
+
+
+def test_chunked_closed_form_gradients_equal_autograd():
+    """The chunked closed-form arbiter of the full-size tests == the oracle's autograd route (float64)."""
+    g = torch.Generator().manual_seed(5)
+    M, N, d = 37, 211, 16
+    U, W = torch.randn(M, d, generator=g).double(), torch.randn(N, d, generator=g).double()
+    b = torch.randn(N, generator=g).double() * 0.3
+    lab = torch.randint(0, N, (M,), generator=g)
+    for bias in (None, b):
+        ref = orc.ce_fwd_bwd(U, W, lab, bias, scale=0.7)
+        got = orc.ce_fwd_bwd_chunked(U, W, lab, bias, scale=0.7, chunk=8)
+        for r, x in zip(ref, got):
+            if r is not None:
+                torch.testing.assert_close(x, r, rtol=1e-10, atol=1e-12)
