@@ -11,7 +11,8 @@ rows, bf16 operands / fp32 accumulate):
 
 metric = full-catalog scored user-item pairs / s = (train rows + eval rows) x catalog size / time.
 With N GPUs the item table is row-sharded (1M rows per GPU => weak scaling; queries replicated);
-the exchange steps are one all-gather (CE stats), one all-reduce (dU) and one all-gather (top-K).
+the exchange steps are one all-reduce (the gathered input rows: global ids over the sharded table), one all-gather
+(CE stats), one all-reduce (dU) and one all-gather (top-K).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
@@ -207,7 +208,7 @@ def run_ours(args):
     g = torch.Generator(device=dev).manual_seed(2026 + 3)
     U_train = synth.embeddings(ROWS, D, g, dev, torch.bfloat16, gain=1.5)
     labels = synth.zipf_ids(ROWS, n_total, g, dev)
-    seqs = synth.sequences(ROWS, SEQ, n_shard, g, dev)               # ids into the local shard (+1 pad row)
+    seqs = synth.sequences(ROWS, SEQ, n_total, g, dev)               # GLOBAL item ids + 1, 0 = padding (lpad_, SASRec/main.py:150-154)
     gather_grad = synth.embeddings(ROWS * SEQ, D, g, dev, torch.bfloat16, gain=0.01).view(ROWS, SEQ, D)
     U_eval = synth.embeddings(ROWS, D, g, dev, torch.bfloat16, gain=1.5)
     seen_crow, seen_col = synth.seen_csr(ROWS, n_total, g, dev)
@@ -219,7 +220,10 @@ def run_ours(args):
         """One pass of the path through the public API (recboard_b200.ops / .sharded), gradients through autograd:
         the table's gradient -- the gather's scatter-add rows plus the scoring head's dW -- ends up in table.grad."""
         table.grad.zero_()                                                        # zero_grad(set_to_none=False)
-        emb = ops.gather_rows(table, sq, padding_idx=0, accumulate=True)          # a2
+        if world > 1:   # a2 over the row-sharded table: owners gather, one all-reduce assembles the replicated rows
+            emb = sharded.sharded_gather_rows(table, sq - 1, row_start - 1, padding_idx=-1, accumulate=True)
+        else:
+            emb = ops.gather_rows(table, sq, padding_idx=0, accumulate=True)      # a2
         Uq = U_tr.detach().requires_grad_(True)
         if world > 1:
             loss = sharded.sharded_fused_ce(Uq, table, lab, row_start, n_skip=1, accumulate=True)   # a5+a6 (+ all-gather)

@@ -8,6 +8,8 @@
 #include <cstring>
 #include <string>
 
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges cost nothing unless a profiler is attached
+
 #include "../../include/recboard_b200.h"
 #include "sweep.cuh"
 #include "pair.cuh"
@@ -46,6 +48,13 @@ static int cuda_fail(cudaError_t e, const char* what) {
     cudaError_t e_ = cudaGetLastError();                      \
     if (e_ != cudaSuccess) return cuda_fail(e_, name);        \
   } while (0)
+
+// One NVTX range per C-ABI entry (nsys / ncu timelines show the path's entry points by name).
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+#define RB_RANGE(name) NvtxRange rb_nvtx_range_(name)
 
 extern "C" const char* rb_last_error(void) { return g_err.c_str(); }
 extern "C" const char* rb_version(void) { return "recboard_b200 0.1 (sm_100a)"; }
@@ -203,6 +212,7 @@ static size_t staged_bytes(long long rows, int d, int mode) {
 // ============================================================================ gather
 extern "C" int rb_gather_rows(const void* table, const int64_t* idx, void* out, int64_t n_idx, int64_t n_rows,
                               int d, int dtype, rb_stream_t stream) {
+  RB_RANGE("rb_gather_rows");
   DevInfo dv; if (int r = get_dev(dv)) return r;
   if (!table || !idx || !out) return fail(RB_E_ARG, "null pointer");
   if (n_idx < 0 || n_rows <= 0 || d <= 0) return fail(RB_E_ARG, "bad shape");
@@ -223,6 +233,7 @@ extern "C" int rb_gather_rows(const void* table, const int64_t* idx, void* out, 
 // ========================================================================= normalise
 extern "C" int rb_normalize_rows(const void* x, void* out, float* inv_norm, int64_t n_rows, int d, int in_dtype,
                                  int out_dtype, float eps, rb_stream_t stream) {
+  RB_RANGE("rb_normalize_rows");
   DevInfo dv; if (int r = get_dev(dv)) return r;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (!x || !out) return fail(RB_E_ARG, "null pointer");
@@ -304,6 +315,7 @@ static int scatter_add_impl(const void* grad_out, const int64_t* idx, long long 
 extern "C" int rb_scatter_add_rows(const void* grad_out, const int64_t* idx, float* grad_table, int64_t n_idx,
                                    int64_t n_rows, int d, int dtype, int64_t padding_idx, void* ws, size_t ws_bytes,
                                    rb_stream_t stream) {
+  RB_RANGE("rb_scatter_add_rows");
   DevInfo dv; if (int r = get_dev(dv)) return r;
   return scatter_add_impl(grad_out, idx, 0, grad_table, n_idx, n_rows, d, dtype, padding_idx, 1.f, nullptr, nullptr, 0.f,
                           ws, ws_bytes, reinterpret_cast<cudaStream_t>(stream));
@@ -311,6 +323,7 @@ extern "C" int rb_scatter_add_rows(const void* grad_out, const int64_t* idx, flo
 extern "C" int rb_scatter_add_rows_into(const void* grad_out, const int64_t* idx, void* grad_table, int64_t n_idx,
                                         int64_t n_rows, int d, int dtype, int table_dtype, int64_t padding_idx, void* ws,
                                         size_t ws_bytes, rb_stream_t stream) {
+  RB_RANGE("rb_scatter_add_rows_into");
   DevInfo dv; if (int r = get_dev(dv)) return r;
   if (table_dtype != RB_DTYPE_F32 && table_dtype != RB_DTYPE_BF16) return fail(RB_E_ARG, "unknown table dtype %d", table_dtype);
   if (table_dtype == RB_DTYPE_BF16 && (d % 4 || (reinterpret_cast<uintptr_t>(grad_table) & 7))) return fail(RB_E_ALIGN, "bf16 table rows must be 8-byte aligned");
@@ -336,6 +349,7 @@ static int gather_dot_check(const void* U, const void* table, const int64_t* idx
 }
 extern "C" int rb_gather_dot(const void* U, const void* table, const int64_t* idx, float scale, float* S, int64_t M,
                              int64_t K, int64_t n_rows, int d, int dtype, rb_stream_t stream) {
+  RB_RANGE("rb_gather_dot");
   DevInfo dv; if (int r = get_dev(dv)) return r;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (int r = gather_dot_check(U, table, idx, M, K, n_rows, d, dtype)) return r;
@@ -352,6 +366,7 @@ extern "C" int rb_gather_dot(const void* U, const void* table, const int64_t* id
 extern "C" int rb_gather_dot_bwd(const void* U, const void* table, const int64_t* idx, const float* G, float scale,
                                  float* dU, float* dTable, int64_t M, int64_t K, int64_t n_rows, int d, int dtype,
                                  int64_t padding_idx, void* ws, size_t ws_bytes, rb_stream_t stream) {
+  RB_RANGE("rb_gather_dot_bwd");
   DevInfo dv; if (int r = get_dev(dv)) return r;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (int r = gather_dot_check(U, table, idx, M, K, n_rows, d, dtype)) return r;
@@ -374,6 +389,7 @@ extern "C" int rb_gather_dot_bwd(const void* U, const void* table, const int64_t
 // =============================================================================== SpMM
 extern "C" int rb_spmm_csr(const int64_t* crow, const int64_t* col, const float* val, const float* X, float* Y,
                            float* acc, float beta, int64_t n_rows, int64_t n_cols, int d, rb_stream_t stream) {
+  RB_RANGE("rb_spmm_csr");
   DevInfo dv; if (int r = get_dev(dv)) return r;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (!crow || !col || !val || !X || (!Y && !acc)) return fail(RB_E_ARG, "null pointer");
@@ -391,6 +407,7 @@ extern "C" int rb_spmm_csr(const int64_t* crow, const int64_t* col, const float*
 // ======================================================================= score dense
 extern "C" int rb_score_dense(const void* U, const void* W, const float* bias, float scale, float* S, int64_t M,
                               int64_t N, int d, int dtype, int mode, void* ws, size_t ws_bytes, rb_stream_t stream) {
+  RB_RANGE("rb_score_dense");
   DevInfo dv; if (int r = get_dev(dv)) return r;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (int r = check_common(U, W, M, N, d, dtype, mode)) return r;
@@ -453,6 +470,7 @@ extern "C" int rb_ce_fwd(const void* U, const void* W, const float* bias, float 
                          int64_t label_base, int64_t M, int64_t N, int d, int dtype, int mode, float* row_max,
                          float* row_sumexp, float* label_logit, float* dU_unnorm, void* ws, size_t ws_bytes,
                          rb_stream_t stream) {
+  RB_RANGE("rb_ce_fwd");
   DevInfo dv; if (int r = get_dev(dv)) return r;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (int r = check_common(U, W, M, N, d, dtype, mode)) return r;
@@ -495,6 +513,7 @@ extern "C" int rb_ce_du_finish(const float* dU_unnorm, const float* row_max, con
                                const int64_t* labels, int64_t label_base, float scale, float grad_scale,
                                const float* grad_scale_dev, int64_t M, int64_t N, int d, int dtype, float* dU,
                                rb_stream_t stream) {
+  RB_RANGE("rb_ce_du_finish");
   DevInfo dv; if (int r = get_dev(dv)) return r;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (!dU_unnorm || !row_max || !lse || !W || !labels || !dU) return fail(RB_E_ARG, "null pointer");
@@ -697,6 +716,7 @@ extern "C" int rb_ce_bwd(const void* U, const void* W, const float* bias, float 
                          int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
                          int64_t M, int64_t N, int d, int dtype, int mode, float* dU, float* dW, float* dbias,
                          void* ws, size_t ws_bytes, rb_stream_t stream) {
+  RB_RANGE("rb_ce_bwd");
   return ce_bwd_impl(U, W, bias, scale, labels, label_base, lse, grad_scale, grad_scale_dev, M, N, d, dtype, mode, dU, dW,
                      dbias, ws, ws_bytes, stream, nullptr);
 }
@@ -705,6 +725,7 @@ extern "C" int rb_ce_bwd_dw_bf16(const void* U, const void* W, const float* bias
                                  int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
                                  int64_t M, int64_t N, int d, void* dW_bf16, float* dbias, void* ws, size_t ws_bytes,
                                  rb_stream_t stream) {
+  RB_RANGE("rb_ce_bwd_dw_bf16");
   if (!dW_bf16) return fail(RB_E_ARG, "null output");
   if (reinterpret_cast<uintptr_t>(dW_bf16) & 15) return fail(RB_E_ALIGN, "dW must be 16-byte aligned");
   return ce_bwd_impl(U, W, bias, scale, labels, label_base, lse, grad_scale, grad_scale_dev, M, N, d, RB_DTYPE_BF16,
@@ -715,6 +736,7 @@ extern "C" int rb_ce_bwd_dw_bf16_acc(const void* U, const void* W, const float* 
                                      int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
                                      int64_t M, int64_t N, int d, void* dW_bf16, float* dbias, void* ws, size_t ws_bytes,
                                      rb_stream_t stream) {
+  RB_RANGE("rb_ce_bwd_dw_bf16_acc");
   if (!dW_bf16) return fail(RB_E_ARG, "null output");
   if (reinterpret_cast<uintptr_t>(dW_bf16) & 15) return fail(RB_E_ALIGN, "dW must be 16-byte aligned");
   return ce_bwd_impl(U, W, bias, scale, labels, label_base, lse, grad_scale, grad_scale_dev, M, N, d, RB_DTYPE_BF16,
@@ -828,6 +850,7 @@ static TopkLayout topk_layout(Bump& b, long long B, long long N, int d, int mode
 //   out[4] = offset of cand_cnt (int32 [B][n_sub]), out[5] = offset of the overflow flags (int32 [B]),
 //   out[6] = offset of the candidate lists (8 B entries [B][n_sub][cand_cap]), out[7] = bytes needed
 extern "C" int rb_topk_debug_layout(int64_t B, int64_t N, int d, int K, int mode, int64_t nnz, int64_t* out) {
+  RB_RANGE("rb_topk_debug_layout");
   DevInfo dv; if (int r = get_dev(dv)) return r;
   if (!out) return fail(RB_E_ARG, "null output");
   Bump b(nullptr, ~size_t(0));
@@ -847,6 +870,7 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
                             const int64_t* seen_col, int64_t seen_nnz, int64_t id_base, int64_t B, int64_t N, int d,
                             int dtype, int mode, int K, float* top_vals, int32_t* top_ids, void* ws, size_t ws_bytes,
                             rb_stream_t stream) {
+  RB_RANGE("rb_topk_eval");
   DevInfo dv; if (int r = get_dev(dv)) return r;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (int r = check_common(U, W, B, N, d, dtype, mode)) return r;
@@ -931,6 +955,7 @@ extern "C" int rb_topk_eval(const void* U, const void* W, const float* bias, flo
 
 extern "C" int rb_topk_merge(const float* vals, const int32_t* ids, int R, int64_t B, int K, float* out_vals,
                              int32_t* out_ids, rb_stream_t stream) {
+  RB_RANGE("rb_topk_merge");
   DevInfo dv; if (int r = get_dev(dv)) return r;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (!vals || !ids || !out_vals || !out_ids) return fail(RB_E_ARG, "null pointer");
@@ -944,6 +969,7 @@ extern "C" int rb_topk_merge(const float* vals, const int32_t* ids, int R, int64
 
 extern "C" int rb_topk_hits(const int32_t* top_ids, const int64_t* target_crow, const int64_t* target_col, int64_t B,
                             int K, float* hits, rb_stream_t stream) {
+  RB_RANGE("rb_topk_hits");
   DevInfo dv; if (int r = get_dev(dv)) return r;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (!top_ids || !target_crow || !hits) return fail(RB_E_ARG, "null pointer");

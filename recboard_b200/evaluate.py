@@ -83,6 +83,35 @@ class DeviceEvalSplit:
         self._seen_crow_host = self.seen_crow.cpu()
         self._tgt_crow_host = self.tgt_crow.cpu()
 
+    @classmethod
+    def from_rows(cls, rows, user_key, seq_key, unseen_key, seen_key, device, maxlen: Optional[int] = None,
+                  num_pads: int = 1, padding_value: int = 0) -> "DeviceEvalSplit":
+        """The DataLoader-facing half: consume ONCE the rows the reference's evaluation samplers yield
+        -- ``{User: user, ISeq: seq, IUnseen: (positive, ...), ISeen: seen}``, HSTU/sampler.py:107-125
+        (``_nextitem_from_full``) -- and keep on the device what every later sweep needs: the seen / target CSRs, the
+        user ids, and (with ``maxlen``) the input sequences exactly as the reference's pipes finish them --
+        truncated to the last ``maxlen`` items, ids shifted by ``NUM_PADS`` (``add_``) and left-padded with
+        ``PADDING_VALUE`` (``lpad_``), SASRec/main.py:150-154.  No DataLoader workers, no per-batch Python after this."""
+        users, seen_rows, tgt_rows, seqs = [], [], [], []
+        for row in rows:
+            users.append(int(row[user_key]))
+            seen_rows.append(row[seen_key])
+            tgt_rows.append(row[unseen_key])
+            if maxlen is not None:
+                seq = [int(x) + num_pads for x in row[seq_key]][-maxlen:]
+                seqs.append([padding_value] * (maxlen - len(seq)) + seq)
+        split = cls(seen_rows, tgt_rows, device)
+        split.users = torch.tensor(users, dtype=torch.int64, device=device).unsqueeze(1)        # (R, 1) like data[User]
+        split.seqs = torch.tensor(seqs, dtype=torch.int64, device=device) if maxlen is not None else None
+        return split
+
+    def data(self, lo: int, hi: int, model) -> Dict:
+        """The ``data`` dict of rows [lo, hi) in the reference's batch format (views of the device-resident split)."""
+        d = {model.User: self.users[lo:hi]}
+        if getattr(self, "seqs", None) is not None:
+            d[model.ISeq] = self.seqs[lo:hi]
+        return d
+
     @staticmethod
     def _cut(crow, crow_host, col, lo, hi):
         a, b = int(crow_host[lo]), int(crow_host[hi])
@@ -110,6 +139,16 @@ def evaluate_split(score_topk, split: DeviceEvalSplit, monitors: Sequence[str], 
         for name, v in MX.batch_metrics(ids, t_crow, t_col, n_items, monitors, exact=exact).items():
             meters[name].update(v, hi - lo)                                         # UniSRec/main.py:428-435, n=bsz
     return {k: m.avg for k, m in meters.items()}
+
+
+@torch.no_grad()
+def evaluate_split_model(model, split: DeviceEvalSplit, monitors: Sequence[str], batch_size: int,
+                         remove_seen: bool = True, exact: bool = True) -> Dict[str, float]:
+    """A whole evaluation sweep of ``model`` (any fused mixin of ``arch.py``) over a ``DeviceEvalSplit.from_rows`` split:
+    ``reset_ranking_buffers()`` once (UniSRec/main.py:401), then contiguous row ranges of the device-resident split."""
+    model.reset_ranking_buffers()
+    return evaluate_split(lambda lo, hi, k, crow, col: model.recommend_topk(split.data(lo, hi, model), k, crow, col),
+                          split, monitors, model.Item.count, batch_size, remove_seen=remove_seen, exact=exact)
 
 
 class FusedEvalCoach:

@@ -9,11 +9,17 @@ scores agree with an fp32 SGEMM to ~1e-6 (configs 1-2).  Default: taken from the
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
 
 from . import _lib as L
+
+
+#: RB_CHECK_FINITE=1 (or ``ops.CHECK_FINITE = True``): every fused_ce forward verifies that the row log-sum-exps are
+#: finite and raises FloatingPointError otherwise.  Off by default: the check reads one flag back from the device.
+CHECK_FINITE = os.environ.get("RB_CHECK_FINITE", "0") not in ("", "0")
 
 
 def _mode_for(U: torch.Tensor, precision: Optional[str]) -> str:
@@ -366,6 +372,8 @@ class _FusedCE(torch.autograd.Function):
         else:
             m, l, ll = ce_rowstats(U, W, labels, bias, scale, 0, precision)
         lse = m + torch.log(l)
+        if CHECK_FINITE and not bool(torch.isfinite(lse).all()):   # debugging aid: costs a device->host sync
+            raise FloatingPointError("fused_ce: non-finite log-sum-exp (inf/nan logits, or an empty / all -inf row)")
         row_loss = lse - ll
         empty = torch.empty(0, device=U.device)
         ctx.save_for_backward(U, Wfull, labels, bias if bias is not None else empty, lse,

@@ -130,3 +130,93 @@ def sharded_topk(U: torch.Tensor, W_shard: torch.Tensor, K: int, row_start: int,
                               id_base=row_start, precision=precision)
     av, ai = allgather_topk(vals, ids, group)
     return (merge_fn or ops.topk_merge)(av, ai)
+
+
+# --------------------------------------------------------------------------------------
+# input-side gather over a row-sharded table: self.Item.embeddings(seqs), SASRec/main.py:183
+# --------------------------------------------------------------------------------------
+class _ShardedGather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, table_shard, idx, row_start, padding_idx, group, accumulate):
+        from . import ops
+        # ids this rank does not own (and the global padding id) fall outside [0, n_shard) after the shift: rb_gather_rows
+        # returns zero rows for them, so the SUM over ranks is the gathered tensor
+        local = idx - row_start
+        if padding_idx >= 0:
+            local = torch.where(idx == padding_idx, torch.full_like(local, -1), local)
+        out = ops.gather_rows_raw(table_shard.detach(), local.contiguous())
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+        ctx.save_for_backward(local)
+        ctx.shape, ctx.dtype = table_shard.shape, table_shard.dtype
+        ctx.leaf = table_shard if (accumulate and table_shard.is_leaf and table_shard.requires_grad) else None
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from . import ops
+        # the gathered tensor is replicated, so is its gradient: every rank adds the rows of the ids IT owns (the
+        # scatter-add skips ids outside its shard) -- no communication in the backward
+        (local,) = ctx.saved_tensors
+        go = grad_out.contiguous()
+        if go.dtype not in (torch.float32, torch.bfloat16):
+            go = go.float()
+        go, flat = go.view(-1, ctx.shape[1]), local.view(-1)
+        leaf = ctx.leaf
+        if leaf is not None and leaf.grad is not None and leaf.grad.is_contiguous() and leaf.grad.shape == ctx.shape \
+                and leaf.grad.dtype in (torch.float32, torch.bfloat16):
+            ops.scatter_add_rows_(leaf.grad, go, flat, -1)
+            return None, None, None, None, None, None
+        gdt = ctx.dtype if ctx.dtype in (torch.float32, torch.bfloat16) else torch.float32
+        g = torch.zeros(ctx.shape, dtype=gdt, device=grad_out.device)
+        ops.scatter_add_rows_(g, go, flat, -1)
+        return g.to(ctx.dtype), None, None, None, None, None
+
+
+def sharded_gather_rows(table_shard: torch.Tensor, idx: torch.Tensor, row_start: int, padding_idx: int = -1, group=None,
+                        accumulate: bool = False) -> torch.Tensor:
+    """``table[idx]`` for GLOBAL row ids over a row-sharded table: every rank gathers the rows it owns (zeros
+    elsewhere) and one all-reduce (SUM) assembles the replicated (..., d) result; rows with ``idx == padding_idx`` are
+    zero.  The backward needs no communication: each rank scatter-adds the (replicated) upstream gradient of its own
+    ids into its shard's gradient (``accumulate`` as in ``ops.gather_rows``)."""
+    return _ShardedGather.apply(table_shard, idx, int(row_start), int(padding_idx), group, bool(accumulate))
+
+
+# --------------------------------------------------------------------------------------
+# checkpoint contract: the shards (de)serialise to the reference's single state_dict key
+# (``Item.embeddings.weight``, benchmark/Amazon2014Beauty_550_LOU/SASRec.json:236-252 records the module tree)
+# --------------------------------------------------------------------------------------
+def unshard_table(shard: torch.Tensor, n_rows: int, group=None) -> torch.Tensor:
+    """All ranks' row blocks (``shard_bounds`` order, possibly ragged) -> the full (n_rows, d) table on every rank."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = [shard_bounds(n_rows, world, r) for r in range(world)]
+    pad = max(b - a for a, b in sizes)
+    mine = torch.zeros(pad, *shard.shape[1:], dtype=shard.dtype, device=shard.device)
+    a, b = sizes[rank]
+    if shard.shape[0] != b - a:
+        raise ValueError(f"rank {rank} holds {shard.shape[0]} rows, shard_bounds says {b - a}")
+    mine[:b - a] = shard.detach()
+    out = torch.empty(world * pad, *shard.shape[1:], dtype=shard.dtype, device=shard.device)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    out = out.view(world, pad, *shard.shape[1:])
+    return torch.cat([out[r, :sizes[r][1] - sizes[r][0]] for r in range(world)], dim=0)
+
+
+def sharded_state_dict(state_dict: dict, key: str, shard: torch.Tensor, n_rows: int, n_pads: int = 0,
+                       pad_rows=None, group=None) -> dict:
+    """A copy of ``state_dict`` whose ``key`` holds the reference's single (n_pads + n_rows, d) table assembled from
+    the ranks' shards (every rank gets the same dict; save it on rank 0 as the reference's Coach does)."""
+    full = unshard_table(shard, n_rows, group)
+    if n_pads:
+        head = pad_rows if pad_rows is not None else torch.zeros(n_pads, full.shape[1], dtype=full.dtype, device=full.device)
+        full = torch.cat([head.to(full), full], dim=0)
+    out = dict(state_dict)
+    out[key] = full
+    return out
+
+
+def load_table_shard(state_dict: dict, key: str, world_size: int, rank: int, n_pads: int = 0) -> torch.Tensor:
+    """This rank's row block of the reference's single-table checkpoint entry (pad rows dropped)."""
+    full = state_dict[key][n_pads:]
+    a, b = shard_bounds(full.shape[0], world_size, rank)
+    return full[a:b].clone()

@@ -78,6 +78,20 @@ check("CE (n_skip, accumulate) loss", loss1.detach().reshape(1), ref_loss, 1e-5)
 check("CE (n_skip, accumulate) dW shard", Wp.grad[1:], ref_dW[lo:hi], 2e-3 + 2.0 ** -8)
 ok &= bool((Wp.grad[0] == 0).all())
 
+# ---- input-side gather with GLOBAL ids over the sharded table (self.Item.embeddings(seqs), SASRec/main.py:183) and its backward
+Bq, Sq = 64, 20
+seqs = synth.sequences(Bq, Sq, N, g, dev)                 # 0 = padding, items 1..N
+gout = synth.embeddings(Bq * Sq, d, g, dev, torch.bfloat16, gain=0.05).view(Bq, Sq, d)
+Wg = W[lo:hi].clone().requires_grad_(True)
+emb = sharded.sharded_gather_rows(Wg, seqs - 1, lo, padding_idx=-1)
+emb.backward(gout)
+ref_emb = orc.gather_rows(torch.cat([torch.zeros(1, d), W.cpu().float()]), seqs.cpu())
+ref_gW = orc.scatter_add_rows(gout.cpu().float(), seqs.cpu(), N + 1, padding_idx=0)[1:]
+ok &= bool(torch.equal(emb.float().cpu(), ref_emb))
+check("sharded gather backward shard", Wg.grad, ref_gW[lo:hi].to(dev), 2.0 ** -8)
+if rank == 0:
+    print(f"[rank 0] sharded gather forward bit-exact: {bool(torch.equal(emb.float().cpu(), ref_emb))}", flush=True)
+
 # ---- BERT4Rec-style bias head (config 5 shape scaled down): bias shard + dbias shard
 ref_lb, ref_dUb, ref_dWb, ref_db = from_rank0(lambda: oracle_ce(True), [((1,), torch.float32), ((M, d), torch.float32),
                                                                          ((N, d), torch.float32), ((N,), torch.float32)])

@@ -236,6 +236,20 @@ def test_evaluate_sweep_and_split_match_oracle(cuda):
     assert EV.evaluate_split(score_topk, split, MONS, model.Item.count, batch_size=32) == ref
 
 
+def test_evaluate_split_model_from_reference_rows(cuda):
+    """8f-4 end to end on the GPU: rows in the reference samplers' format -> DeviceEvalSplit.from_rows -> a whole
+    evaluation sweep without per-batch host work, equal to the oracle's sweep over the same rows."""
+    model, seqs, seen, tgt, batches = _eval_setup(cuda)
+    rows = []
+    for r in range(len(seen)):
+        items = (seqs[r][seqs[r] > 0] - 1).tolist()                        # 0-based item ids, no padding
+        rows.append({"U": r, "S": tuple(items), "UNSEEN": tuple(tgt[r]), "SEEN": tuple(seen[r])})
+    split = EV.DeviceEvalSplit.from_rows(rows, "U", "S", "UNSEEN", "SEEN", cuda, maxlen=12)
+    assert torch.equal(split.seqs.cpu(), seqs)                              # the pipes' add_(NUM_PADS) + lpad_ reproduced
+    got = EV.evaluate_split_model(model, split, MONS, batch_size=32)
+    assert got == _oracle_sweep(model, seqs, seen, tgt, 32, cuda)
+
+
 class _StubCoach:
     """What ``FusedEvalCoach`` needs from freerec's ``Coach`` (UniSRec/main.py:400-447): cfg, fields, dataloader,
     dict_to_device, register_metric and a ``monitor`` that keeps bsz-weighted means."""

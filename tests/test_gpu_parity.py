@@ -40,19 +40,19 @@ def assert_rel(got, ref, rtol, what=""):
 
 
 def assert_grad_bf16(got, ref, what=""):
-    """bf16-mode gradients against the fp32 oracle: north_star's 2e-3 relative to the largest element (plus half a bf16
-    ulp of it, 2^-9, when the gradient itself is STORED in bf16 -- a bf16 parameter's gradient), and element by element
-    wherever the reference is not negligible (|ref| > 1e-3 max|ref|): within 1.5 % of the element."""
+    """bf16-mode gradients against the fp32 oracle, north_star's 2e-3 in two norms: the largest error relative to the
+    largest element (plus half a bf16 ulp of it, 2^-9, when the gradient itself is STORED in bf16 -- a bf16
+    parameter's gradient), and the Euclidean norm of the error relative to that of the reference.  (An element-by-
+    element relative bound is not meaningful here: the one bf16 rounding of the softmax tile gives every element an
+    ABSOLUTE error proportional to the size of its summands, and dU = sum_j P_ij w_j - w_label cancels by design.)"""
     stored_bf16 = got.dtype == torch.bfloat16
     got, ref = got.detach().float().cpu(), torch.as_tensor(ref).float()
     mx = float(ref.abs().max().clamp_min(1e-30))
     tol = BF16_RTOL + (2.0 ** -9 if stored_bf16 else 0.0)
     err = float((got - ref).abs().max()) / mx
     assert err <= tol, f"{what}: max err / max|ref| = {err:.3e} > {tol:.1e}"
-    big = ref.abs() > 1e-3 * mx
-    rel = ((got - ref).abs()[big] / ref.abs()[big])
-    worst = float(rel.max()) if rel.numel() else 0.0
-    assert worst <= 1.5e-2, f"{what}: worst element-wise relative error {worst:.3e} among {int(big.sum())} significant elements"
+    l2 = float((got - ref).double().norm() / ref.double().norm().clamp_min(1e-30))
+    assert l2 <= tol, f"{what}: |err|_2 / |ref|_2 = {l2:.3e} > {tol:.1e}"
 
 
 def bf16_round(x):

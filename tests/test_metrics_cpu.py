@@ -126,3 +126,23 @@ def test_device_eval_split_matches_per_batch_csr(monkeypatch):
         for m, v in orc.evaluate_batch(orc.score_dense(U[lo:hi], W), sc, sl, tc, tl, mons).items():
             meters[m].update(v, hi - lo)
     assert got == {m: meters[m].avg for m in mons}
+
+
+def test_device_eval_split_from_reference_rows():
+    """8f-4, loader-facing half: rows in the format the reference's samplers yield (HSTU/sampler.py:107-125) become the
+    finished batch tensors of the reference's pipes: last ``maxlen`` items, ids + NUM_PADS, left-padded with 0."""
+    from recboard_b200 import evaluate as EV
+    rows = [
+        {"U": 3, "S": (5, 9, 2), "UNSEEN": (7,), "SEEN": (5, 9, 2)},
+        {"U": 0, "S": (1, 1, 4, 8, 6, 3), "UNSEEN": (2,), "SEEN": (1, 4, 8, 6, 3)},
+        {"U": 9, "S": (), "UNSEEN": (0, 4), "SEEN": ()},
+    ]
+    split = EV.DeviceEvalSplit.from_rows(rows, "U", "S", "UNSEEN", "SEEN", torch.device("cpu"), maxlen=4)
+    assert split.users.tolist() == [[3], [0], [9]]
+    assert split.seqs.tolist() == [[0, 6, 10, 3], [5, 9, 7, 4], [0, 0, 0, 0]]
+    sc, sl, tc, tl = split.batch(0, 3)
+    assert sc.tolist() == [0, 3, 8, 8] and sl.tolist() == [2, 5, 9, 1, 3, 4, 6, 8]
+    assert tc.tolist() == [0, 1, 2, 4] and tl.tolist() == [7, 2, 0, 4]
+    model = type("M", (), {"User": "User", "ISeq": "ISeq"})()
+    d = split.data(1, 3, model)
+    assert d["User"].tolist() == [[0], [9]] and d["ISeq"].shape == (2, 4)

@@ -152,3 +152,61 @@ def test_two_rank_sharded_autograd_and_topk():
         assert torch.allclose(dW, rdW[a:b], rtol=1e-4, atol=1e-6)     # the local shard, never communicated
         assert torch.allclose(db, rdb[a:b], rtol=1e-4, atol=1e-6)
         assert torch.equal(i.long(), ri) and torch.allclose(v, rv)
+
+
+# ---- input-side gather over a sharded table (global ids, one all-reduce, local backward) and the checkpoint contract
+def _gather_ckpt_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from recboard_b200 import ops
+
+    def gather_rows_raw(table, idx):   # what rb_gather_rows does: ids outside [0, rows) give zero rows
+        ok = (idx >= 0) & (idx < table.shape[0])
+        return torch.where(ok[..., None], table[idx.clamp(0, table.shape[0] - 1)], torch.zeros((), dtype=table.dtype))
+
+    def scatter_add_rows_(grad_table, grad_out, idx, padding_idx=-1):
+        ok = (idx >= 0) & (idx < grad_table.shape[0]) & (idx != padding_idx)
+        grad_table.index_add_(0, idx[ok], grad_out[ok].to(grad_table.dtype))
+        return grad_table
+
+    ops.gather_rows_raw, ops.scatter_add_rows_ = gather_rows_raw, scatter_add_rows_
+    g = torch.Generator().manual_seed(31)
+    N, P, d, B, S = 101, 1, 8, 5, 7
+    full = torch.randn(N, d, generator=g)                       # item rows (global ids 0..N-1 are items, -1 = padding)
+    idx = torch.randint(-1, N, (B, S), generator=g)
+    gout = torch.randn(B, S, d, generator=g)
+    a, b = sharded.shard_bounds(N, world, rank)
+    shard = full[a:b].clone().requires_grad_(True)
+    out = sharded.sharded_gather_rows(shard, idx, a, padding_idx=-1)
+    out.backward(gout)
+    # checkpoint round trip: shards -> the reference's single key (with its pad row) -> shards
+    sd = sharded.sharded_state_dict({"other": torch.ones(1)}, "Item.embeddings.weight", shard.detach(), N, n_pads=P)
+    back = sharded.load_table_shard(sd, "Item.embeddings.weight", world, rank, n_pads=P)
+    q.put((rank, a, b, out.detach().numpy(), shard.grad.numpy(), sd["Item.embeddings.weight"].numpy(), back.numpy()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_gather_and_checkpoint():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gather_ckpt_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(31)
+    N, P, d, B, S = 101, 1, 8, 5, 7
+    full = torch.randn(N, d, generator=g).requires_grad_(True)
+    idx = torch.randint(-1, N, (B, S), generator=g)
+    gout = torch.randn(B, S, d, generator=g)
+    table = torch.cat([torch.zeros(P, d), full])                 # the reference's layout: pad row first
+    ref = torch.nn.functional.embedding(idx + P, table, padding_idx=0)
+    ref.backward(gout)
+    for rank, a, b, out, grad, ckpt, back in outs:
+        assert torch.allclose(torch.from_numpy(out), ref.detach())
+        assert torch.allclose(torch.from_numpy(grad), full.grad[a:b], atol=1e-6)
+        assert torch.equal(torch.from_numpy(ckpt)[P:], full.detach()) and bool((torch.from_numpy(ckpt)[:P] == 0).all())
+        assert torch.equal(torch.from_numpy(back), full.detach()[a:b])
