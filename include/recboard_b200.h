@@ -91,6 +91,13 @@ int rb_gather_dot_bwd(const void* U, const void* table, const int64_t* idx, cons
 int rb_spmm_csr(const int64_t* crow, const int64_t* col, const float* val, const float* X, float* Y,
                 float* acc, float beta, int64_t n_rows, int64_t n_cols, int d, rb_stream_t stream);
 
+/* Device-side row compaction: row_index[k] = position of the k-th non-zero byte of mask[0..n) for k < *count, -1
+ * beyond; *count = number of non-zero bytes.  Replaces the boolean indexing `userEmbds[indices]` /
+ * `positives[indices]` (SASRec/main.py:199-200), `fc(userEmbds)[masks]` (BERT4Rec/main.py:181), whose nonzero()
+ * waits for the count on the host every step: gather the rows with rb_gather_rows(row_index) (entries -1 give zero
+ * rows) and hand `count` to the rb_ce_* entries as m_dev. */
+int rb_compact_index(const void* mask, int64_t n, int64_t* row_index, int32_t* count, rb_stream_t stream);
+
 /* S = scale * U W^T + bias  (M,N) fp32.          replaces `torch.einsum("BD,ND->BN", ...)`
  * (SASRec/main.py:228; MF-BPR/main.py:104; LightGCN/main.py:120; HSTU/main.py:209) and
  * `self.fc(userEmbds)` (BERT4Rec/main.py:189).  Compatibility path: it materialises (M,N). */
@@ -107,11 +114,17 @@ int rb_score_dense(const void* U, const void* W, const float* bias, float scale,
  * loss = mean(row_max + log(row_sumexp) - label_logit) replaces
  * `einsum("MD,ND->MN")` + `self.criterion(logits, labels)` (SASRec/main.py:217-219,
  * GRU4Rec/main.py:175-178, BERT4Rec/main.py:181-182).  Row-sharded tables: merge
- * (max, sumexp, label_logit) across ranks. */
+ * (max, sumexp, label_logit) across ranks.
+ *
+ * m_dev (nullable, every rb_ce_* entry): a DEVICE int32 holding how many of the M query rows exist.  M is then the
+ * capacity the caller sized U / labels / the outputs for; rows >= *m_dev get neutral statistics (max 0, sumexp 1,
+ * label_logit 0: lse = 0), zero dU, contribute nothing to dW / dbias, and whole tiles beyond the count are skipped.
+ * This is what lets the caller compact the non-padding positions (`userEmbds[indices]`, SASRec/main.py:199-200;
+ * `fc(userEmbds)[masks]`, BERT4Rec/main.py:181) on the device without reading the count back (no nonzero() sync). */
 int rb_ce_fwd(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
               int64_t label_base, int64_t M, int64_t N, int d, int dtype, int mode, float* row_max,
-              float* row_sumexp, float* label_logit, float* dU_unnorm, void* ws, size_t ws_bytes,
-              rb_stream_t stream);
+              float* row_sumexp, float* label_logit, float* dU_unnorm, const int32_t* m_dev, void* ws,
+              size_t ws_bytes, rb_stream_t stream);
 
 /* dU (M,d) = g*scale*( dU_unnorm * exp(row_max - lse) - [label in shard] W_label ): this shard's
  * piece of the CE gradient wrt U from rb_ce_fwd's accumulator and the GLOBAL lse; pieces of
@@ -120,7 +133,7 @@ int rb_ce_fwd(const void* U, const void* W, const float* bias, float scale, cons
 int rb_ce_du_finish(const float* dU_unnorm, const float* row_max, const float* lse, const void* W,
                     const int64_t* labels, int64_t label_base, float scale, float grad_scale,
                     const float* grad_scale_dev, int64_t M, int64_t N, int d, int dtype, float* dU,
-                    rb_stream_t stream);
+                    const int32_t* m_dev, rb_stream_t stream);
 
 /* Gradients of g * sum_i (lse_i - S_i,label_i) given the GLOBAL lse (natural log), where
  * g = grad_scale * (grad_scale_dev ? *grad_scale_dev : 1)  (a device scalar lets autograd's
@@ -138,7 +151,7 @@ int rb_ce_du_finish(const float* dU_unnorm, const float* row_max, const float* l
 int rb_ce_bwd(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
               int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
               int64_t M, int64_t N, int d, int dtype, int mode, float* dU, float* dW, float* dbias,
-              void* ws, size_t ws_bytes, rb_stream_t stream);
+              const int32_t* m_dev, void* ws, size_t ws_bytes, rb_stream_t stream);
 
 /* rb_ce_bwd's dW (+ dbias) with the gradient stored in bf16 (the dtype of a bf16 parameter): the pass
  * writes bf16 rows directly instead of an fp32 (N,d) matrix that the caller would cast (1.5 N d bytes less
@@ -147,8 +160,8 @@ int rb_ce_bwd(const void* U, const void* W, const float* bias, float scale, cons
  * bf16 mode, d <= 128, scale > 0; workspace RB_OP_CE_BWD. */
 int rb_ce_bwd_dw_bf16(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
                       int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
-                      int64_t M, int64_t N, int d, void* dW_bf16, float* dbias, void* ws, size_t ws_bytes,
-                      rb_stream_t stream);
+                      int64_t M, int64_t N, int d, void* dW_bf16, float* dbias, const int32_t* m_dev, void* ws,
+                      size_t ws_bytes, rb_stream_t stream);
 
 /* The same pass ADDING its rows to what dW_bf16 already holds: dW_bf16 is the parameter's existing gradient buffer
  * (e.g. already carrying the embedding gather's rows), so the scoring head's dW and the gather's scatter-add end up
@@ -157,8 +170,8 @@ int rb_ce_bwd_dw_bf16(const void* U, const void* W, const float* bias, float sca
  * (several splits of the query range, or M > 16384): accumulate on the caller's side then. */
 int rb_ce_bwd_dw_bf16_acc(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
                           int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
-                          int64_t M, int64_t N, int d, void* dW_bf16, float* dbias, void* ws, size_t ws_bytes,
-                          rb_stream_t stream);
+                          int64_t M, int64_t N, int d, void* dW_bf16, float* dbias, const int32_t* m_dev, void* ws,
+                          size_t ws_bytes, rb_stream_t stream);
 
 /* Masked full-catalog top-K: for every query row the K best (score desc, id asc) items among this
  * shard's N items, skipping ids in the row's seen list (CSR over GLOBAL ids, sorted ascending per

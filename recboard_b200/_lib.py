@@ -24,6 +24,7 @@ _p, _i64, _i32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_
 #: every symbol include/recboard_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "rb_gather_rows": (_i32, [_p, _p, _p, _i64, _i64, _i32, _i32, _p]),
+    "rb_compact_index": (_i32, [_p, _i64, _p, _p, _p]),
     "rb_normalize_rows": (_i32, [_p, _p, _p, _i64, _i32, _i32, _i32, _f32, _p]),
     "rb_scatter_add_rows": (_i32, [_p, _p, _p, _i64, _i64, _i32, _i32, _i64, _p, _sz, _p]),
     "rb_scatter_add_rows_into": (_i32, [_p, _p, _p, _i64, _i64, _i32, _i32, _i32, _i64, _p, _sz, _p]),
@@ -31,11 +32,11 @@ SIGNATURES = {
     "rb_gather_dot_bwd": (_i32, [_p, _p, _p, _p, _f32, _p, _p, _i64, _i64, _i64, _i32, _i32, _i64, _p, _sz, _p]),
     "rb_spmm_csr": (_i32, [_p, _p, _p, _p, _p, _p, _f32, _i64, _i64, _i32, _p]),
     "rb_score_dense": (_i32, [_p, _p, _p, _f32, _p, _i64, _i64, _i32, _i32, _i32, _p, _sz, _p]),
-    "rb_ce_fwd": (_i32, [_p, _p, _p, _f32, _p, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _sz, _p]),
-    "rb_ce_du_finish": (_i32, [_p, _p, _p, _p, _p, _i64, _f32, _f32, _p, _i64, _i64, _i32, _i32, _p, _p]),
-    "rb_ce_bwd": (_i32, [_p, _p, _p, _f32, _p, _i64, _p, _f32, _p, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _sz, _p]),
-    "rb_ce_bwd_dw_bf16": (_i32, [_p, _p, _p, _f32, _p, _i64, _p, _f32, _p, _i64, _i64, _i32, _p, _p, _p, _sz, _p]),
-    "rb_ce_bwd_dw_bf16_acc": (_i32, [_p, _p, _p, _f32, _p, _i64, _p, _f32, _p, _i64, _i64, _i32, _p, _p, _p, _sz, _p]),
+    "rb_ce_fwd": (_i32, [_p, _p, _p, _f32, _p, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "rb_ce_du_finish": (_i32, [_p, _p, _p, _p, _p, _i64, _f32, _f32, _p, _i64, _i64, _i32, _i32, _p, _p, _p]),
+    "rb_ce_bwd": (_i32, [_p, _p, _p, _f32, _p, _i64, _p, _f32, _p, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _sz, _p]),
+    "rb_ce_bwd_dw_bf16": (_i32, [_p, _p, _p, _f32, _p, _i64, _p, _f32, _p, _i64, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
+    "rb_ce_bwd_dw_bf16_acc": (_i32, [_p, _p, _p, _f32, _p, _i64, _p, _f32, _p, _i64, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
     "rb_topk_eval": (_i32, [_p, _p, _p, _f32, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _p, _p, _p, _sz, _p]),
     "rb_topk_debug_layout": (_i32, [_i64, _i64, _i32, _i32, _i32, _i64, _p]),
     "rb_topk_hits": (_i32, [_p, _p, _p, _i64, _i32, _p, _p]),

@@ -29,6 +29,11 @@ class FusedFullCatalogMixin:
 
     #: "bf16" | "fp32" | None (None: follow the operand dtype; fp32 tensors -> 3xTF32 "fp32 parity")
     fused_precision: Optional[str] = None
+    #: True: the query rows are compacted on the device (``ops.compact_queries``) and their count never travels to the
+    #: host -- no ``nonzero()`` synchronisation in ``fit`` (the reference's ``userEmbds[indices]``,
+    #: SASRec/main.py:199-200, waits for it every step).  The fused passes are then PLANNED for the capacity B x S and
+    #: skip the tiles beyond the count, which under-fills the GPU on small batches; off by default.
+    fused_sync_free: bool = False
 
     # -- hooks -------------------------------------------------------------------------
     def _train_operands(self, data) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, Optional[torch.Tensor], float]:
@@ -53,11 +58,13 @@ class FusedFullCatalogMixin:
 
     # -- RecSysArch contract ------------------------------------------------------------
     def fit(self, data: Dict) -> Dict[str, torch.Tensor]:
-        U, W, labels, bias, scale = self._train_operands(data)
+        U, W, labels, bias, scale, *rest = self._train_operands(data)
+        n_valid = rest[0] if rest else None      # device-side row count of a sync-free compaction
         n_skip = 0
         if bias is None:
             W, n_skip = self._whole_table(W)
-        return {"rec_loss": ops.fused_ce(U, W, labels, bias=bias, scale=scale, precision=self.fused_precision, n_skip=n_skip)}
+        return {"rec_loss": ops.fused_ce(U, W, labels, bias=bias, scale=scale, precision=self.fused_precision, n_skip=n_skip,
+                                         n_valid=n_valid)}
 
     def recommend_from_full(self, data: Dict) -> torch.Tensor:
         U, W, bias, scale, n_skip = self._eval_operands(data)
@@ -93,6 +100,9 @@ class SASRecFused(FusedFullCatalogMixin):
     def _train_operands(self, data):
         userEmbds, itemEmbds = self.encode(data)
         indices = data[self.ISeq] != self.PADDING_VALUE
+        if self.fused_sync_free:
+            U, (labels,), count = ops.compact_queries(userEmbds, indices, data[self.IPos])
+            return U, itemEmbds, labels, None, 1.0, count
         return userEmbds[indices], itemEmbds, data[self.IPos][indices], None, 1.0
 
     def _eval_operands(self, data):
@@ -119,9 +129,14 @@ class BERT4RecFused(FusedFullCatalogMixin):
     (:181); here the masked rows are selected first and only they are scored."""
 
     def _train_operands(self, data):
-        masked_seqs, labels, masks = self.random_mask(seqs=data[self.ISeq], p=self.mask_ratio)
+        seqs = data[self.ISeq]
+        masked_seqs, labels, masks = self.random_mask(seqs=seqs, p=self.mask_ratio)
         data[self.ISeq] = masked_seqs
         userEmbds = self.encode(data)
+        if self.fused_sync_free:   # the labels are the original ids at the masked positions (BERT4Rec/main.py:147-160);
+            # (the model's own random_mask still indexes ``seqs[masks]``: that synchronisation is inside the reference method)
+            U, (lab,), count = ops.compact_queries(userEmbds, masks, seqs)
+            return U, self.fc.weight, lab, self.fc.bias, 1.0, count
         return userEmbds[masks], self.fc.weight, labels, self.fc.bias, 1.0
 
     def _eval_operands(self, data):

@@ -230,6 +230,17 @@ extern "C" int rb_gather_rows(const void* table, const int64_t* idx, void* out, 
   return 0;
 }
 
+// ================================================================== row compaction
+extern "C" int rb_compact_index(const void* mask, int64_t n, int64_t* row_index, int32_t* count, rb_stream_t stream) {
+  RB_RANGE("rb_compact_index");
+  DevInfo dv; if (int r = get_dev(dv)) return r;
+  if (!mask || !row_index || !count) return fail(RB_E_ARG, "null pointer");
+  if (n < 0 || n >= (1ll << 31)) return fail(RB_E_ARG, "bad length %lld", (long long)n);
+  compact_index_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(static_cast<const unsigned char*>(mask), n, row_index, count);
+  RB_LAUNCH_CHECK("compact_index_kernel");
+  return 0;
+}
+
 // ========================================================================= normalise
 extern "C" int rb_normalize_rows(const void* x, void* out, float* inv_norm, int64_t n_rows, int d, int in_dtype,
                                  int out_dtype, float eps, rb_stream_t stream) {
@@ -437,7 +448,8 @@ static size_t pair_fwd_ws(long long M, long long N, int d, int sms) {
 // Fused pass (pair kernel, PASS_FWD) when dU_unnorm is requested; statistics-only sweep otherwise.
 static int ce_fwd_pair(const DevInfo& dv, const void* U, const void* W, const float* bias, float scale,
                        const int64_t* labels, int64_t label_base, int64_t M, int64_t N, int d, float* row_max,
-                       float* row_sumexp, float* label_logit, float* dU_unnorm, Bump& b, cudaStream_t st) {
+                       float* row_sumexp, float* label_logit, float* dU_unnorm, Bump& b, cudaStream_t st,
+                       const int* m_dev = nullptr) {
   Plan p = make_plan(M, N, dv.sms, 1 << 20, 8, 256);
   const long long stat_pad = 1ll * p.n_stat_tiles * 256;
   const long long n_pad = 1ll * p.n_strm_tiles * 128;
@@ -456,20 +468,20 @@ static int ce_fwd_pair(const DevInfo& dv, const void* U, const void* W, const fl
   PairArgs a{};
   a.n_stat = (int)M; a.n_strm = (int)N; a.n_pair_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
   a.n_splits = p.n_splits; a.d = d; a.stat_pad = (int)stat_pad; a.scale = scale; a.aux = bias2;
-  a.part_m2 = pm2; a.part_l = pl; a.acc_out = pacc;
+  a.part_m2 = pm2; a.part_l = pl; a.acc_out = pacc; a.m_dev = m_dev;
   if (int r = launch_pair_fwd(kc_for(d, RB_MODE_BF16), bias != nullptr, ts, ty, a, p.grid, st)) return r;
   const int grid = (int)((M * 32 + 255) / 256);
   ce_fwd_finish_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
       pm2, pl, pacc, p.n_splits, stat_pad, (int)M, d, static_cast<const __nv_bfloat16*>(U),
-      static_cast<const __nv_bfloat16*>(W), bias, labels, label_base, N, scale, row_max, row_sumexp, label_logit, dU_unnorm);
+      static_cast<const __nv_bfloat16*>(W), bias, labels, label_base, N, scale, row_max, row_sumexp, label_logit, dU_unnorm, m_dev);
   RB_LAUNCH_CHECK("ce_fwd_finish_kernel");
   return 0;
 }
 
 extern "C" int rb_ce_fwd(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
                          int64_t label_base, int64_t M, int64_t N, int d, int dtype, int mode, float* row_max,
-                         float* row_sumexp, float* label_logit, float* dU_unnorm, void* ws, size_t ws_bytes,
-                         rb_stream_t stream) {
+                         float* row_sumexp, float* label_logit, float* dU_unnorm, const int32_t* m_dev, void* ws,
+                         size_t ws_bytes, rb_stream_t stream) {
   RB_RANGE("rb_ce_fwd");
   DevInfo dv; if (int r = get_dev(dv)) return r;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -480,7 +492,7 @@ extern "C" int rb_ce_fwd(const void* U, const void* W, const float* bias, float 
   if (dU_unnorm) {
     if (!pair_ok(mode, d, scale))
       return fail(RB_E_UNSUPPORTED, "the fused forward+dU pass needs bf16 mode, d <= 128 and scale > 0 (use rb_ce_bwd's dU instead)");
-    return ce_fwd_pair(dv, U, W, bias, scale, labels, label_base, M, N, d, row_max, row_sumexp, label_logit, dU_unnorm, b, st);
+    return ce_fwd_pair(dv, U, W, bias, scale, labels, label_base, M, N, d, row_max, row_sumexp, label_logit, dU_unnorm, b, st, m_dev);
   }
   Operand ou, ow;
   if (int r = stage_operand(U, M, d, mode, b, ou, st)) return r;
@@ -501,9 +513,9 @@ extern "C" int rb_ce_fwd(const void* U, const void* W, const float* bias, float 
   SweepArgs a{};
   a.n_stat = (int)M; a.n_strm = (int)N; a.n_stat_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
   a.n_splits = p.n_splits; a.d = d; a.scale = scale; a.bias = bias; a.labels = lab32;
-  a.part_m2 = pm2; a.part_l = pl; a.part_ll = pll;
+  a.part_m2 = pm2; a.part_l = pl; a.part_ll = pll; a.m_dev = m_dev;
   if (int r = launch_sweep_lse(mode, kc_for(d, mode), ts, ty, a, p.grid, st, xt)) return r;
-  lse_merge_kernel<<<(int)((M + 255) / 256), 256, 0, st>>>(pm2, pl, pll, p.n_splits, m_pad, (int)M, row_max, row_sumexp, label_logit);
+  lse_merge_kernel<<<(int)((M + 255) / 256), 256, 0, st>>>(pm2, pl, pll, p.n_splits, m_pad, (int)M, row_max, row_sumexp, label_logit, m_dev);
   RB_LAUNCH_CHECK("lse_merge_kernel");
   return 0;
 }
@@ -512,7 +524,7 @@ extern "C" int rb_ce_fwd(const void* U, const void* W, const float* bias, float 
 extern "C" int rb_ce_du_finish(const float* dU_unnorm, const float* row_max, const float* lse, const void* W,
                                const int64_t* labels, int64_t label_base, float scale, float grad_scale,
                                const float* grad_scale_dev, int64_t M, int64_t N, int d, int dtype, float* dU,
-                               rb_stream_t stream) {
+                               const int32_t* m_dev, rb_stream_t stream) {
   RB_RANGE("rb_ce_du_finish");
   DevInfo dv; if (int r = get_dev(dv)) return r;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -521,9 +533,9 @@ extern "C" int rb_ce_du_finish(const float* dU_unnorm, const float* row_max, con
   const int grid = (int)((M * 32 + 255) / 256);
   const float gs = grad_scale * scale;
   if (dtype == RB_DTYPE_BF16)
-    ce_du_finish_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(dU_unnorm, row_max, lse, static_cast<const __nv_bfloat16*>(W), labels, label_base, N, gs, grad_scale_dev, (int)M, d, dU);
+    ce_du_finish_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(dU_unnorm, row_max, lse, static_cast<const __nv_bfloat16*>(W), labels, label_base, N, gs, grad_scale_dev, (int)M, d, dU, m_dev);
   else if (dtype == RB_DTYPE_F32)
-    ce_du_finish_kernel<float><<<grid, 256, 0, st>>>(dU_unnorm, row_max, lse, static_cast<const float*>(W), labels, label_base, N, gs, grad_scale_dev, (int)M, d, dU);
+    ce_du_finish_kernel<float><<<grid, 256, 0, st>>>(dU_unnorm, row_max, lse, static_cast<const float*>(W), labels, label_base, N, gs, grad_scale_dev, (int)M, d, dU, m_dev);
   else
     return fail(RB_E_ARG, "unknown dtype %d", dtype);
   RB_LAUNCH_CHECK("ce_du_finish_kernel");
@@ -536,7 +548,7 @@ extern "C" int rb_ce_du_finish(const float* dU_unnorm, const float* row_max, con
 static int ce_bwd_dw_pair(const DevInfo& dv, const void* U, const void* W, const float* bias, float scale,
                           const int64_t* labels, int64_t label_base, const float* lse2, float grad_scale,
                           const float* grad_scale_dev, int64_t M, int64_t N, int d, float* dW, float* dbias, Bump& b,
-                          cudaStream_t st, __nv_bfloat16* dW_bf16 = nullptr, bool accumulate = false) {
+                          cudaStream_t st, __nv_bfloat16* dW_bf16 = nullptr, bool accumulate = false, const int* m_dev = nullptr) {
   Plan p = make_plan(N, M, dv.sms, 64, 8, 256);
   const long long n_pad = 1ll * p.n_stat_tiles * 256;
   // One-hot correction: up to LABEL_FIX_MAX query rows without a sort (label_owner + label_fix), beyond that
@@ -575,6 +587,7 @@ static int ce_bwd_dw_pair(const DevInfo& dv, const void* U, const void* W, const
   a.n_stat = (int)N; a.n_strm = (int)M; a.n_pair_tiles = p.n_stat_tiles; a.n_strm_tiles = p.n_strm_tiles;
   a.n_splits = p.n_splits; a.d = d; a.stat_pad = (int)n_pad; a.scale = scale; a.bias2_stat = bias2; a.aux = lse2;
   a.gscale = grad_scale * scale; a.rscale = grad_scale; a.gscale_dev = grad_scale_dev; a.acc_out = part; a.rowsum_out = rs_part;
+  a.m_dev = m_dev;
   if (direct_bf16) { a.out_bf16 = dW_bf16; a.slot_of_row = first_of; a.side = side; a.accumulate = accumulate ? 1 : 0; }
   if (int r = launch_pair_dw(kc_for(d, RB_MODE_BF16), bias_cfg, ts, ty, a, p.grid, st)) return r;
   if (p.n_splits > 1) {
@@ -643,7 +656,7 @@ static int launch_f32grad(const F32GradArgs& a, cudaStream_t st) {
 static int ce_bwd_f32(const DevInfo& dv, const float* U, const float* W, const float* bias, float scale,
                       const int64_t* labels, int64_t label_base, const float* lse, float grad_scale,
                       const float* grad_scale_dev, int64_t M, int64_t N, int d, float* dU, float* dW, float* dbias,
-                      Bump& b, cudaStream_t st) {
+                      Bump& b, cudaStream_t st, const int* m_dev = nullptr) {
   if (d > 128) return fail(RB_E_UNSUPPORTED, "fp32 CE backward supports d <= 128");
   const float c2 = scale * 1.4426950408889634f;
   if (dU) {  // rows stationary, items streamed: acc_i = sum_j softmax_ij w_j
@@ -655,6 +668,7 @@ static int ce_bwd_f32(const DevInfo& dv, const float* U, const float* W, const f
     a.X = U; a.Y = W; a.n_stat = (int)M; a.n_strm = (int)N; a.d = d; a.n_splits = ns; a.c2 = c2;
     a.stat_vec = lse; a.stat_mul = -1.f; a.strm_vec = bias; a.strm_mul = 1.f;
     a.out_scale = 1.f; a.rowsum_scale = 0.f; a.scale_dev = nullptr; a.acc_out = part; a.rowsum_out = nullptr;
+    a.m_dev = m_dev; a.m_side = 0;
     if (int r = launch_f32grad(a, st)) return r;
     if (ns > 1) {
       const long long n = M * d;
@@ -663,7 +677,7 @@ static int ce_bwd_f32(const DevInfo& dv, const float* U, const float* W, const f
     }
     // dU = g*scale*(acc - w_label): the finishing kernel of the fused pass with row_max == lse (factor 1)
     ce_du_finish_kernel<float><<<(int)((M * 32 + 255) / 256), 256, 0, st>>>(acc, lse, lse, W, labels, label_base, N,
-                                                                            grad_scale * scale, grad_scale_dev, (int)M, d, dU);
+                                                                            grad_scale * scale, grad_scale_dev, (int)M, d, dU, m_dev);
     RB_LAUNCH_CHECK("ce_du_finish_kernel");
   }
   if (dW) {  // items stationary, rows streamed: dW_j = g*scale*sum_i softmax_ij u_i, dbias_j = g*sum_i softmax_ij
@@ -677,7 +691,7 @@ static int ce_bwd_f32(const DevInfo& dv, const float* U, const float* W, const f
     a.X = W; a.Y = U; a.n_stat = (int)N; a.n_strm = (int)M; a.d = d; a.n_splits = ns; a.c2 = c2;
     a.stat_vec = bias; a.stat_mul = 1.f; a.strm_vec = lse; a.strm_mul = -1.f;
     a.out_scale = grad_scale * scale; a.rowsum_scale = grad_scale; a.scale_dev = grad_scale_dev;
-    a.acc_out = part; a.rowsum_out = rs_part;
+    a.acc_out = part; a.rowsum_out = rs_part; a.m_dev = m_dev; a.m_side = 1;
     if (int r = launch_f32grad(a, st)) return r;
     if (ns > 1) {
       const long long n = N * d;
@@ -710,43 +724,44 @@ static int ce_bwd_f32(const DevInfo& dv, const float* U, const float* W, const f
 static int ce_bwd_impl(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
                        int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
                        int64_t M, int64_t N, int d, int dtype, int mode, float* dU, float* dW, float* dbias,
-                       void* ws, size_t ws_bytes, rb_stream_t stream, void* dW_bf16, bool accumulate = false);
+                       void* ws, size_t ws_bytes, rb_stream_t stream, void* dW_bf16, bool accumulate = false,
+                       const int* m_dev = nullptr);
 
 extern "C" int rb_ce_bwd(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
                          int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
                          int64_t M, int64_t N, int d, int dtype, int mode, float* dU, float* dW, float* dbias,
-                         void* ws, size_t ws_bytes, rb_stream_t stream) {
+                         const int32_t* m_dev, void* ws, size_t ws_bytes, rb_stream_t stream) {
   RB_RANGE("rb_ce_bwd");
   return ce_bwd_impl(U, W, bias, scale, labels, label_base, lse, grad_scale, grad_scale_dev, M, N, d, dtype, mode, dU, dW,
-                     dbias, ws, ws_bytes, stream, nullptr);
+                     dbias, ws, ws_bytes, stream, nullptr, false, m_dev);
 }
 
 extern "C" int rb_ce_bwd_dw_bf16(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
                                  int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
-                                 int64_t M, int64_t N, int d, void* dW_bf16, float* dbias, void* ws, size_t ws_bytes,
-                                 rb_stream_t stream) {
+                                 int64_t M, int64_t N, int d, void* dW_bf16, float* dbias, const int32_t* m_dev, void* ws,
+                                 size_t ws_bytes, rb_stream_t stream) {
   RB_RANGE("rb_ce_bwd_dw_bf16");
   if (!dW_bf16) return fail(RB_E_ARG, "null output");
   if (reinterpret_cast<uintptr_t>(dW_bf16) & 15) return fail(RB_E_ALIGN, "dW must be 16-byte aligned");
   return ce_bwd_impl(U, W, bias, scale, labels, label_base, lse, grad_scale, grad_scale_dev, M, N, d, RB_DTYPE_BF16,
-                     RB_MODE_BF16, nullptr, nullptr, dbias, ws, ws_bytes, stream, dW_bf16);
+                     RB_MODE_BF16, nullptr, nullptr, dbias, ws, ws_bytes, stream, dW_bf16, false, m_dev);
 }
 
 extern "C" int rb_ce_bwd_dw_bf16_acc(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
                                      int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
-                                     int64_t M, int64_t N, int d, void* dW_bf16, float* dbias, void* ws, size_t ws_bytes,
-                                     rb_stream_t stream) {
+                                     int64_t M, int64_t N, int d, void* dW_bf16, float* dbias, const int32_t* m_dev, void* ws,
+                                     size_t ws_bytes, rb_stream_t stream) {
   RB_RANGE("rb_ce_bwd_dw_bf16_acc");
   if (!dW_bf16) return fail(RB_E_ARG, "null output");
   if (reinterpret_cast<uintptr_t>(dW_bf16) & 15) return fail(RB_E_ALIGN, "dW must be 16-byte aligned");
   return ce_bwd_impl(U, W, bias, scale, labels, label_base, lse, grad_scale, grad_scale_dev, M, N, d, RB_DTYPE_BF16,
-                     RB_MODE_BF16, nullptr, nullptr, dbias, ws, ws_bytes, stream, dW_bf16, true);
+                     RB_MODE_BF16, nullptr, nullptr, dbias, ws, ws_bytes, stream, dW_bf16, true, m_dev);
 }
 
 static int ce_bwd_impl(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
                        int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
                        int64_t M, int64_t N, int d, int dtype, int mode, float* dU, float* dW, float* dbias,
-                       void* ws, size_t ws_bytes, rb_stream_t stream, void* dW_bf16, bool accumulate) {
+                       void* ws, size_t ws_bytes, rb_stream_t stream, void* dW_bf16, bool accumulate, const int* m_dev) {
   DevInfo dv; if (int r = get_dev(dv)) return r;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (int r = check_common(U, W, M, N, d, dtype, mode)) return r;
@@ -757,7 +772,7 @@ static int ce_bwd_impl(const void* U, const void* W, const float* bias, float sc
   Bump b(ws, ws_bytes);
   if (mode == RB_MODE_FP32X3)  // fp32 parity: exact fp32 passes (any sign of scale)
     return ce_bwd_f32(dv, static_cast<const float*>(U), static_cast<const float*>(W), bias, scale, labels, label_base, lse,
-                      grad_scale, grad_scale_dev, M, N, d, dU, dW, dbias, b, st);
+                      grad_scale, grad_scale_dev, M, N, d, dU, dW, dbias, b, st, m_dev);
   if (!(scale > 0.f)) return fail(RB_E_UNSUPPORTED, "CE backward needs scale > 0");
 
   if (dU) {  // no forward accumulator at hand: re-run the fused forward pass, then finish against the GLOBAL lse.
@@ -767,20 +782,20 @@ static int ce_bwd_impl(const void* U, const void* W, const float* bias, float sc
     float* rll = b.take<float>(M);
     float* du_un = b.take<float>(static_cast<size_t>(M) * d);
     if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small: need %zu bytes", b.off);
-    if (int r = ce_fwd_pair(dv, U, W, bias, scale, labels, label_base, M, N, d, rm, rl, rll, du_un, b, st)) return r;
+    if (int r = ce_fwd_pair(dv, U, W, bias, scale, labels, label_base, M, N, d, rm, rl, rll, du_un, b, st, m_dev)) return r;
     const int grid = (int)((M * 32 + 255) / 256);
     ce_du_finish_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(du_un, rm, lse, static_cast<const __nv_bfloat16*>(W), labels,
-                                                               label_base, N, grad_scale * scale, grad_scale_dev, (int)M, d, dU);
+                                                               label_base, N, grad_scale * scale, grad_scale_dev, (int)M, d, dU, m_dev);
     RB_LAUNCH_CHECK("ce_du_finish_kernel");
   }
   if (dW || dW_bf16) {
     const long long m_pad = ((M + 127) / 128) * 128;
     float* lse2 = b.take<float>(m_pad);
     if (!b.ok()) return fail(RB_E_WORKSPACE, "workspace too small");
-    lse2_kernel<<<(int)((m_pad + 255) / 256), 256, 0, st>>>(lse, lse2, (int)M, (int)m_pad);
+    lse2_kernel<<<(int)((m_pad + 255) / 256), 256, 0, st>>>(lse, lse2, (int)M, (int)m_pad, m_dev);
     RB_LAUNCH_CHECK("lse2_kernel");
     return ce_bwd_dw_pair(dv, U, W, bias, scale, labels, label_base, lse2, grad_scale, grad_scale_dev, M, N, d, dW, dbias, b, st,
-                          static_cast<__nv_bfloat16*>(dW_bf16), accumulate);
+                          static_cast<__nv_bfloat16*>(dW_bf16), accumulate, m_dev);
   }
   return 0;
 }

@@ -41,6 +41,9 @@ struct F32GradArgs {
   const float* scale_dev;     // optional device scalar
   float* acc_out;             // [n_splits][n_stat][d]
   float* rowsum_out;          // [n_splits][n_stat], nullable
+  // device-side count of QUERY rows (nullable) and which side they are on: 0 = stationary (dU pass), 1 = streamed (dW pass)
+  const int* m_dev;
+  int m_side;
 };
 
 template <int DP>
@@ -52,12 +55,18 @@ __global__ void __launch_bounds__(F32G_THREADS, 2) ce_grad_f32_kernel(const F32G
   float* Ps = Ys + F32G_TILE * C::LDX;
 
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int n_tiles = (a.n_stat + F32G_TILE - 1) / F32G_TILE;
-  const int n_strm_tiles = (a.n_strm + F32G_TILE - 1) / F32G_TILE;
+  const int n_tiles = (a.n_stat + F32G_TILE - 1) / F32G_TILE;   // the grid and the output pitch follow the host's capacity
+  int n_strm_eff = a.n_strm, n_stat_eff = a.n_stat;
+  if (a.m_dev != nullptr) {
+    const int m = max(0, *a.m_dev);
+    if (a.m_side == 0) n_stat_eff = min(n_stat_eff, m); else n_strm_eff = min(n_strm_eff, m);
+  }
+  const int n_strm_tiles = (n_strm_eff + F32G_TILE - 1) / F32G_TILE;
   const int tile = blockIdx.x % n_tiles, split = blockIdx.x / n_tiles;
   const int t0 = static_cast<int>((static_cast<long long>(split) * n_strm_tiles) / a.n_splits);
-  const int t1 = static_cast<int>((static_cast<long long>(split + 1) * n_strm_tiles) / a.n_splits);
   const int row0 = tile * F32G_TILE;
+  // a stationary tile beyond the device-side row count streams nothing and stores zeros
+  const int t1 = (row0 >= n_stat_eff) ? t0 : static_cast<int>((static_cast<long long>(split + 1) * n_strm_tiles) / a.n_splits);
   constexpr int VPR = DP / 4;   // float4 per padded row
   constexpr int NG = DP / 64;   // float4 column groups per thread in the second contraction
 
@@ -90,14 +99,14 @@ __global__ void __launch_bounds__(F32G_THREADS, 2) ce_grad_f32_kernel(const F32G
     for (int v = tid; v < F32G_TILE * VPR; v += F32G_THREADS) {
       const int r = v / VPR, c = (v - r * VPR) * 4;
       float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (col0 + r < a.n_strm && c < a.d) y = __ldg(reinterpret_cast<const float4*>(a.Y + static_cast<long long>(col0 + r) * a.d + c));
+      if (col0 + r < n_strm_eff && c < a.d) y = __ldg(reinterpret_cast<const float4*>(a.Y + static_cast<long long>(col0 + r) * a.d + c));
       *reinterpret_cast<float4*>(Ys + r * C::LDX + c) = y;
     }
     float sb[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = col0 + tx + 16 * j;
-      sb[j] = (c < a.n_strm) ? ((a.strm_vec != nullptr) ? a.strm_mul * 1.4426950408889634f * __ldg(a.strm_vec + c) : 0.f) : -INFINITY;
+      sb[j] = (c < n_strm_eff) ? ((a.strm_vec != nullptr) ? a.strm_mul * 1.4426950408889634f * __ldg(a.strm_vec + c) : 0.f) : -INFINITY;
     }
     __syncthreads();
 

@@ -77,6 +77,9 @@ struct PairArgs {
   void* out_bf16;              // [n_stat][d] bf16, nullable
   const int* slot_of_row;      // [n_stat]
   float* side;                 // [n_slots][d]
+  // Device-side row count (nullable): only the first *m_dev QUERY rows exist (stationary rows in PASS_FWD, streamed rows
+  // in PASS_DW); tiles beyond them are skipped.  The host sizes buffers, tensor maps and the grid for the capacity.
+  const int* m_dev;
   int accumulate;              // bf16 output only: rows are ADDED to what out_bf16 already holds (the parameter's existing gradient)
 };
 
@@ -156,7 +159,14 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_items = a.n_pair_tiles * a.n_splits;
+  // effective extents: the host's, or what the device-side count of query rows leaves of them
+  int n_stat = a.n_stat, n_pair_tiles = a.n_pair_tiles, n_strm_tiles = a.n_strm_tiles;
+  if (a.m_dev != nullptr) {
+    const int m = max(0, *a.m_dev);
+    if (C::PASS == PASS_FWD) { n_stat = min(n_stat, m); n_pair_tiles = min(n_pair_tiles, (n_stat + 255) / 256); }
+    else n_strm_tiles = min(n_strm_tiles, (min(a.n_strm, m) + 127) / 128);
+  }
+  const int total_items = n_pair_tiles * a.n_splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_stat);
@@ -183,13 +193,29 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
   const uint32_t tmem_base = bar->tmem_base;
 
   auto item_range = [&](int item, int& pair_tile, int& split, int& t0, int& t1) {
-    pair_tile = item % a.n_pair_tiles;  // split-major: concurrent CTAs stream the same tiles (L2 reuse)
-    split = item / a.n_pair_tiles;
-    t0 = static_cast<int>((static_cast<long long>(split) * a.n_strm_tiles) / a.n_splits);
-    t1 = static_cast<int>((static_cast<long long>(split + 1) * a.n_strm_tiles) / a.n_splits);
+    pair_tile = item % n_pair_tiles;  // split-major: concurrent CTAs stream the same tiles (L2 reuse)
+    split = item / n_pair_tiles;
+    t0 = static_cast<int>((static_cast<long long>(split) * n_strm_tiles) / a.n_splits);
+    t1 = static_cast<int>((static_cast<long long>(split + 1) * n_strm_tiles) / a.n_splits);
   };
 
-  if (warp == 0) {
+  if (C::PASS == PASS_DW && n_strm_tiles == 0) {
+    // no query rows at all (device-side count 0): the gradient of this pass is zero; nothing to stream
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int pt = item % n_pair_tiles, split = item / n_pair_tiles;
+      for (int i = threadIdx.x; i < 256 * (a.d / 4); i += blockDim.x) {
+        const int row = pt * 256 + i / (a.d / 4), c = (i % (a.d / 4)) * 4;
+        if (row < a.n_stat) {
+          if (a.out_bf16 != nullptr) {
+            if (!a.accumulate) *reinterpret_cast<uint2*>(static_cast<uint16_t*>(a.out_bf16) + static_cast<long long>(row) * a.d + c) = make_uint2(0u, 0u);
+          } else {
+            *reinterpret_cast<float4*>(a.acc_out + (static_cast<long long>(split) * a.n_stat + row) * a.d + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          if (c == 0 && a.rowsum_out != nullptr) a.rowsum_out[static_cast<long long>(split) * a.n_stat + row] = 0.f;
+        }
+      }
+    }
+  } else if (warp == 0) {
     // ======================================================================= TMA producer
     // The whole warp runs the (uniform) control flow; one elected lane issues the copies.
     uint32_t it = 0, k = 0;
@@ -323,7 +349,7 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
       int pt, split, t0, t1;
       item_range(item, pt, split, t0, t1);
       const int srow = (pt * 2 + g) * 128 + r;   // global stationary row
-      const bool srow_ok = srow < a.n_stat;
+      const bool srow_ok = srow < n_stat;
 
       float m2 = 0.f, l = 0.f;      // FWD: row reference (log2 domain) and this thread's share of sum P
       float nb = 0.f;               // DW: bias2 of this item row

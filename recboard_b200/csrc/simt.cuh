@@ -342,6 +342,39 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16*
   }
 }
 
+// ------------------------------------------------------------------- row compaction (a4)
+// row_index[k] = position of the k-th set byte of mask (k < count), -1 beyond; *count = number of set bytes.
+// The device-side replacement of `indices = positives != 0; userEmbds[indices]` (SASRec/main.py:199-200): torch's
+// boolean indexing calls nonzero() and waits for the count on the host; here the count stays on the device and the
+// fused CE entries take it as m_dev.  One CTA of 1024 threads walks the mask in chunks of 1024 with a running offset
+// (n is the B x S positions of a batch: tens of thousands to a few hundred thousand).
+__global__ void __launch_bounds__(1024) compact_index_kernel(const unsigned char* __restrict__ mask, long long n,
+                                                             int64_t* __restrict__ row_index, int* __restrict__ count) {
+  __shared__ int warp_sums[32];
+  __shared__ int running;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) running = 0;
+  __syncthreads();
+  for (long long base = 0; base < n; base += 1024) {
+    const long long i = base + tid;
+    const int flag = (i < n && mask[i] != 0) ? 1 : 0;
+    const unsigned int bal = __ballot_sync(0xffffffffu, flag);
+    const int before = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_sums[wid] = __popc(bal);
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < wid; ++w) woff += warp_sums[w];
+    const int start = running;
+    if (flag) row_index[start + woff + before] = i;
+    __syncthreads();
+    if (tid == 1023) running = start + woff + before + flag;   // the last thread's exclusive offset + its own flag = chunk total
+    __syncthreads();
+  }
+  const int total = running;
+  for (long long i = total + tid; i < n; i += 1024) row_index[i] = -1;
+  if (tid == 0) *count = total;
+}
+
 // ------------------------------------------------------------------- operand preparation
 // labels (int64, global) -> int32 local (label - base) or -1 when outside [0, n_items)
 __global__ void labels_local_kernel(const int64_t* __restrict__ labels, long long base, long long n_items,
@@ -358,8 +391,9 @@ __global__ void labels_local_kernel(const int64_t* __restrict__ labels, long lon
 }
 
 // lse (natural log) -> -lse * log2(e), padded with -inf (=> exp2(x + aux) = 0 for padding rows)
-__global__ void lse2_kernel(const float* __restrict__ lse, float* __restrict__ out, int m, int m_pad) {
+__global__ void lse2_kernel(const float* __restrict__ lse, float* __restrict__ out, int m, int m_pad, const int* __restrict__ m_dev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m_dev != nullptr) m = min(m, max(0, __ldg(m_dev)));   // rows beyond the device-side count do not exist
   if (i < m_pad) out[i] = (i < m) ? -lse[i] * 1.4426950408889634f : -INFINITY;
 }
 
@@ -407,10 +441,17 @@ __global__ void ce_fwd_finish_kernel(const float* __restrict__ pm2, const float*
                                      const T* __restrict__ U, const T* __restrict__ W, const float* __restrict__ bias,
                                      const int64_t* __restrict__ labels, long long label_base, long long n_items,
                                      float scale, float* __restrict__ row_max, float* __restrict__ row_sumexp,
-                                     float* __restrict__ label_logit, float* __restrict__ du_unnorm) {
+                                     float* __restrict__ label_logit, float* __restrict__ du_unnorm,
+                                     const int* __restrict__ m_dev) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= m) return;
+  if (m_dev != nullptr && row >= __ldg(m_dev)) {   // a row beyond the device-side count: neutral statistics (lse = 0, loss 0)
+    if (lane == 0) { row_max[row] = 0.f; row_sumexp[row] = 1.f; label_logit[row] = 0.f; }
+    if (du_unnorm != nullptr)
+      for (int c = lane * 4; c < d; c += 128) *reinterpret_cast<float4*>(du_unnorm + static_cast<long long>(row) * d + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
   float mx = -INFINITY;
   for (int s = 0; s < n_splits; ++s) mx = fmaxf(mx, pm2[s * slot_stride + row]);
   float l = 0.f;
@@ -452,10 +493,15 @@ template <typename T>
 __global__ void ce_du_finish_kernel(const float* __restrict__ du_unnorm, const float* __restrict__ row_max,
                                     const float* __restrict__ lse, const T* __restrict__ W,
                                     const int64_t* __restrict__ labels, long long label_base, long long n_items,
-                                    float gs, const float* __restrict__ gs_dev, int m, int d, float* __restrict__ dU) {
+                                    float gs, const float* __restrict__ gs_dev, int m, int d, float* __restrict__ dU,
+                                    const int* __restrict__ m_dev) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= m) return;
+  if (m_dev != nullptr && row >= __ldg(m_dev)) {   // no such query row: zero gradient
+    for (int c = lane * 4; c < d; c += 128) *reinterpret_cast<float4*>(dU + static_cast<long long>(row) * d + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
   const float g = gs * (gs_dev != nullptr ? __ldg(gs_dev) : 1.f);
   const float f = expf(row_max[row] - lse[row]);
   const long long lab = labels[row] - label_base;
@@ -473,9 +519,11 @@ __global__ void ce_du_finish_kernel(const float* __restrict__ du_unnorm, const f
 // ------------------------------------------------------------------------ partial merges
 __global__ void lse_merge_kernel(const float* __restrict__ pm2, const float* __restrict__ pl, const float* __restrict__ pll,
                                  int n_splits, long long slot_stride, int m, float* __restrict__ row_max,
-                                 float* __restrict__ row_sumexp, float* __restrict__ label_logit) {
+                                 float* __restrict__ row_sumexp, float* __restrict__ label_logit,
+                                 const int* __restrict__ m_dev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
+  if (m_dev != nullptr && i >= __ldg(m_dev)) { row_max[i] = 0.f; row_sumexp[i] = 1.f; label_logit[i] = 0.f; return; }
   float mx = -INFINITY;
   for (int s = 0; s < n_splits; ++s) mx = fmaxf(mx, pm2[s * slot_stride + i]);
   float l = 0.f, ll = 0.f;

@@ -66,6 +66,8 @@ struct SweepArgs {
   int d;             // true feature width (<= KC*64)
   float scale;       // logits = scale * <u,w> + bias
   const float* bias; // per ITEM bias (nullable)
+  // device-side count of stationary (query) rows, nullable: stationary tiles beyond it are skipped (EPI_LSE)
+  const int* m_dev;
   // EPI_DENSE (rows stationary)
   float* out;
   long long ld_out;
@@ -179,7 +181,12 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_items = a.n_stat_tiles * a.n_splits;
+  int n_stat = a.n_stat, n_stat_tiles = a.n_stat_tiles;   // effective extents under a device-side row count
+  if (a.m_dev != nullptr) {
+    n_stat = min(n_stat, max(0, *a.m_dev));
+    n_stat_tiles = min(n_stat_tiles, (n_stat + 128 * C::XT - 1) / (128 * C::XT));
+  }
+  const int total_items = n_stat_tiles * a.n_splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_stat);
@@ -203,8 +210,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
   const uint32_t tmem_base = bar->tmem_base;
 
   auto item_range = [&](int item, int& stat_tile, int& split, int& t0, int& t1) {
-    stat_tile = item % a.n_stat_tiles;  // split-major order: concurrent CTAs share streamed tiles in L2
-    split = item / a.n_stat_tiles;
+    stat_tile = item % n_stat_tiles;  // split-major order: concurrent CTAs share streamed tiles in L2
+    split = item / n_stat_tiles;
     t0 = static_cast<int>((static_cast<long long>(split) * a.n_strm_tiles) / a.n_splits);
     t1 = static_cast<int>((static_cast<long long>(split + 1) * a.n_strm_tiles) / a.n_splits);
   };
@@ -327,7 +334,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
       item_range(item, stat_tile, split, t0, t1);
       const int stile = (C::XT == 1) ? stat_tile : stat_tile * 2 + xsel;   // global 128-row stationary tile
       const int srow = stile * 128 + r;  // global stationary row
-      const bool srow_ok = srow < a.n_stat;
+      const bool srow_ok = srow < n_stat;
       const long long pslot = static_cast<long long>(split) * a.n_stat_tiles * (128 * C::XT) + srow;
 
       // ---- per-item, per-warpgroup state

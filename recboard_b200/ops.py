@@ -115,6 +115,34 @@ def gather_rows(table: torch.Tensor, idx: torch.Tensor, padding_idx: int = -1, a
 
 
 # --------------------------------------------------------------------------------------
+# device-side compaction of query rows (a4): no nonzero(), no count read back to the host
+# --------------------------------------------------------------------------------------
+def compact_index(mask: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(row_index int64 (n,), count int32 (1,)) of a boolean mask with n elements: row_index[k] is the flat position of
+    the k-th True for k < count and -1 beyond; both stay on the device (rb_compact_index)."""
+    dev = L.require_cuda(mask)
+    m8 = mask.reshape(-1).to(torch.uint8).contiguous()
+    n = m8.numel()
+    row_index = torch.empty(n, dtype=torch.int64, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    L.call(dev, "rb_compact_index", L.ptr(m8), n, L.ptr(row_index), L.ptr(count), L.stream_ptr(dev))
+    return row_index, count
+
+
+def compact_queries(X: torch.Tensor, mask: torch.Tensor, *aligned: torch.Tensor):
+    """The sync-free stand-in for ``X[mask]`` / ``t[mask]`` (``userEmbds[indices]``, ``positives[indices]``,
+    SASRec/main.py:199-200): -> (Xc (n, d), [t_c (n,) ...], count) where n = mask.numel() is the CAPACITY, the first
+    ``count`` rows are the selected ones in order, the rest are zero rows / -1 entries.  Hand ``count`` to ``fused_ce`` as
+    ``n_valid``.  Differentiable w.r.t. ``X`` (the backward scatters the rows back; the selected positions are unique)."""
+    d = X.shape[-1]
+    row_index, count = compact_index(mask)
+    Xc = gather_rows(X.reshape(-1, d), row_index, padding_idx=-1)
+    safe = row_index.clamp_min(0)
+    outs = [torch.where(row_index >= 0, t.reshape(-1)[safe], torch.full_like(safe, -1).to(t.dtype)) for t in aligned]
+    return Xc, outs, count
+
+
+# --------------------------------------------------------------------------------------
 # fused gather + row-wise dot (pool ranking, sampled softmax, BPR / BCE logits)
 # --------------------------------------------------------------------------------------
 def _same_storage(U, table):
@@ -259,8 +287,16 @@ def fused_du_supported(U, precision: Optional[str], scale: float) -> bool:
     return _mode_for(U, precision) == "bf16" and U.shape[1] <= 128 and scale > 0
 
 
+def _count_ptr(n_valid, dev):
+    if n_valid is None:
+        return None
+    if n_valid.dtype != torch.int32 or n_valid.numel() != 1 or n_valid.device != dev:
+        raise TypeError("n_valid must be an int32 scalar tensor on the operands' device")
+    return L.ptr(n_valid.reshape(1))
+
+
 def ce_rowstats(U, W, labels, bias=None, scale: float = 1.0, label_base: int = 0,
-                precision: Optional[str] = None, want_dU: bool = False):
+                precision: Optional[str] = None, want_dU: bool = False, n_valid: Optional[torch.Tensor] = None):
     """(row_max, row_sumexp, label_logit) of scale*U W^T + bias over this shard; (M,N) never exists.
     With ``want_dU`` a fourth tensor is returned: dU_unnorm (M,d) = sum_j exp(S_ij - row_max_i) W_j,
     accumulated by the same sweep (see ``ce_du_finish``)."""
@@ -276,14 +312,14 @@ def ce_rowstats(U, W, labels, bias=None, scale: float = 1.0, label_base: int = 0
     ws, n = _ws(dev, L.OP_CE_FWD, M, N, d, mode=mode)
     L.call(dev, "rb_ce_fwd", L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(labels.contiguous()), label_base,
                           M, N, d, L.dtype_code(Uc), mode, L.ptr(out[0]), L.ptr(out[1]), L.ptr(out[2]), L.ptr(du),
-                          L.ptr(ws), n, L.stream_ptr(dev))
+                          _count_ptr(n_valid, dev), L.ptr(ws), n, L.stream_ptr(dev))
     if want_dU:
         return out[0], out[1], out[2], du
     return out[0], out[1], out[2]
 
 
 def ce_du_finish(du_unnorm, row_max, lse, W, labels, grad_scale: float, scale: float = 1.0, label_base: int = 0,
-                 grad_scale_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 grad_scale_dev: Optional[torch.Tensor] = None, n_valid: Optional[torch.Tensor] = None) -> torch.Tensor:
     """This shard's piece of dU: g*scale*(du_unnorm*exp(row_max - lse) - [label in shard] W[label])."""
     dev = L.require_cuda(du_unnorm, row_max, lse, W, labels, grad_scale_dev)
     Wc = W.detach()
@@ -295,7 +331,7 @@ def ce_du_finish(du_unnorm, row_max, lse, W, labels, grad_scale: float, scale: f
     L.call(dev, "rb_ce_du_finish", L.ptr(du_unnorm), L.ptr(row_max), L.ptr(lse.float().contiguous()), L.ptr(Wc),
                                 L.ptr(labels.contiguous()), label_base, float(scale), float(grad_scale),
                                 L.ptr(grad_scale_dev), M, Wc.shape[0], d, L.dtype_code(Wc), L.ptr(dU),
-                                L.stream_ptr(dev))
+                                _count_ptr(n_valid, dev), L.stream_ptr(dev))
     return dU
 
 
@@ -303,7 +339,7 @@ def ce_backward(U, W, labels, lse, grad_scale: float, bias=None, scale: float = 
                 need_dU: bool = True, need_dW: bool = True, need_dbias: bool = False,
                 precision: Optional[str] = None, grad_scale_dev: Optional[torch.Tensor] = None,
                 dw_dtype: Optional[torch.dtype] = None, dw_out: Optional[torch.Tensor] = None,
-                accumulate: bool = False):
+                accumulate: bool = False, n_valid: Optional[torch.Tensor] = None):
     """Gradients of ``g * sum_i (lse_i - S_i,label_i)`` -> (dU, dW, dbias) fp32, with
     ``g = grad_scale * grad_scale_dev`` (the latter an optional fp32 device scalar).
     ``dw_dtype=torch.bfloat16`` (bf16 mode) makes the pass store dW in bf16 itself -- the correctly rounded
@@ -325,13 +361,14 @@ def ce_backward(U, W, labels, lse, grad_scale: float, bias=None, scale: float = 
         if need_dU:   # dU alone through the generic entry, dW (+ dbias) through the bf16-output pass
             L.call(dev, "rb_ce_bwd", L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(labels.contiguous()), label_base,
                                   L.ptr(lse.float().contiguous()), float(grad_scale), L.ptr(grad_scale_dev), M, N, d,
-                                  L.dtype_code(Uc), mode, L.ptr(dU), None, None, L.ptr(ws), n, L.stream_ptr(dev))
+                                  L.dtype_code(Uc), mode, L.ptr(dU), None, None, _count_ptr(n_valid, dev), L.ptr(ws), n,
+                                  L.stream_ptr(dev))
         dWb = dw_out if dw_out is not None else torch.empty(N, d, dtype=torch.bfloat16, device=dev)
         if dWb.dtype != torch.bfloat16 or dWb.shape != (N, d):
             raise TypeError("dw_out must be a bfloat16 (N,d) tensor here")
         args = (L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(labels.contiguous()), label_base,
                 L.ptr(lse.float().contiguous()), float(grad_scale), L.ptr(grad_scale_dev), M, N, d,
-                L.ptr(dWb), L.ptr(db), L.ptr(ws), n, L.stream_ptr(dev))
+                L.ptr(dWb), L.ptr(db), _count_ptr(n_valid, dev), L.ptr(ws), n, L.stream_ptr(dev))
         if accumulate:
             with torch.cuda.device(dev):
                 code = L.lib().rb_ce_bwd_dw_bf16_acc(*args)
@@ -351,13 +388,13 @@ def ce_backward(U, W, labels, lse, grad_scale: float, bias=None, scale: float = 
     L.call(dev, "rb_ce_bwd", L.ptr(Uc), L.ptr(Wc), L.ptr(b), float(scale), L.ptr(labels.contiguous()), label_base,
                           L.ptr(lse.float().contiguous()), float(grad_scale), L.ptr(grad_scale_dev), M, N, d,
                           L.dtype_code(Uc), mode,
-                          L.ptr(dU), L.ptr(dW), L.ptr(db), L.ptr(ws), n, L.stream_ptr(dev))
+                          L.ptr(dU), L.ptr(dW), L.ptr(db), _count_ptr(n_valid, dev), L.ptr(ws), n, L.stream_ptr(dev))
     return dU, (dW if need_dW else None), db
 
 
 class _FusedCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, U, Wfull, labels, bias, scale, precision, reduction, n_skip, accumulate):
+    def forward(ctx, U, Wfull, labels, bias, scale, precision, reduction, n_skip, accumulate, n_valid):
         # ``Wfull`` is the whole parameter (N+P, d); the scored table is the view Wfull[n_skip:] (SASRec/main.py:193).
         # Taking the parameter itself lets the backward hand autograd ONE (N+P,d) gradient, written in place by the
         # dW pass, instead of a (N,d) one that the slice's backward would pad into a fresh zero-filled copy.
@@ -368,9 +405,9 @@ class _FusedCE(torch.autograd.Function):
         ctx.fused_du = bool(ctx.needs_input_grad[0]) and fused_du_supported(U, precision, scale)
         du = m = None
         if ctx.fused_du:
-            m, l, ll, du = ce_rowstats(U, W, labels, bias, scale, 0, precision, want_dU=True)
+            m, l, ll, du = ce_rowstats(U, W, labels, bias, scale, 0, precision, want_dU=True, n_valid=n_valid)
         else:
-            m, l, ll = ce_rowstats(U, W, labels, bias, scale, 0, precision)
+            m, l, ll = ce_rowstats(U, W, labels, bias, scale, 0, precision, n_valid=n_valid)
         lse = m + torch.log(l)
         if CHECK_FINITE and not bool(torch.isfinite(lse).all()):   # debugging aid: costs a device->host sync
             raise FloatingPointError("fused_ce: non-finite log-sum-exp (inf/nan logits, or an empty / all -inf row)")
@@ -380,6 +417,10 @@ class _FusedCE(torch.autograd.Function):
                               du if du is not None else empty, m if du is not None else empty)
         ctx.has_bias = bias is not None
         ctx.scale, ctx.precision, ctx.reduction = scale, precision, reduction
+        ctx.n_valid = n_valid
+        if n_valid is not None:   # rows beyond the device-side count report lse = label_logit = 0: they add nothing
+            total = row_loss.sum()
+            return total / n_valid.to(total.dtype).reshape(()) if reduction == "mean" else total
         if reduction == "mean":
             return row_loss.mean()
         if reduction == "sum":
@@ -393,27 +434,31 @@ class _FusedCE(torch.autograd.Function):
         P = ctx.n_skip
         W = Wfull[P:] if P else Wfull
         M = U.shape[0]
-        g = 1.0 / (M if ctx.reduction == "mean" else 1)
+        nv = ctx.n_valid
+        g = 1.0 / (M if (ctx.reduction == "mean" and nv is None) else 1)
         need = ctx.needs_input_grad
         # the upstream scalar stays on the device: no host synchronisation in backward
         gdev = grad_out.detach().float().reshape(1).contiguous()
+        if nv is not None and ctx.reduction == "mean":
+            gdev = gdev / nv.to(gdev.dtype)   # mean over the device-side row count
         need_db = ctx.has_bias and need[3]
         dU = None
         if ctx.fused_du:
-            dU = ce_du_finish(du_un, row_max, lse, W, labels, g, ctx.scale, 0, gdev)
+            dU = ce_du_finish(du_un, row_max, lse, W, labels, g, ctx.scale, 0, gdev, n_valid=nv)
         dU2, dW, db = table_gradient(U, Wfull, P, labels, lse, g, bias, ctx.scale, 0, ctx.precision, gdev,
-                                     need[0] and not ctx.fused_du, need[1], need_db, ctx.leaf)
+                                     need[0] and not ctx.fused_du, need[1], need_db, ctx.leaf, n_valid=nv)
         dU = dU if dU is not None else dU2
         return (
             dU.to(U.dtype) if dU is not None else None,
             dW,
             None,
             db.to(bias.dtype) if db is not None else None,
-            None, None, None, None, None,
+            None, None, None, None, None, None,
         )
 
 
-def table_gradient(U, Wfull, P, labels, lse, g, bias, scale, label_base, precision, gdev, need_du, need_dw, need_db, leaf):
+def table_gradient(U, Wfull, P, labels, lse, g, bias, scale, label_base, precision, gdev, need_du, need_dw, need_db, leaf,
+                   n_valid=None):
     """The CE backward's dW / dbias (and dU when the forward did not accumulate it) for a scored table
     ``Wfull[P:]`` -> (dU | None, gradient for ``Wfull`` as autograd wants it | None, dbias | None).
 
@@ -426,7 +471,8 @@ def table_gradient(U, Wfull, P, labels, lse, g, bias, scale, label_base, precisi
             and leaf.grad.is_contiguous() and leaf.grad.shape == Wfull.shape and Wfull.dtype == torch.bfloat16 and bf16_mode):
         try:
             _, _, db = ce_backward(U, W, labels, lse, g, bias, scale, label_base, False, True, need_db, precision,
-                                   grad_scale_dev=gdev, dw_dtype=torch.bfloat16, dw_out=leaf.grad[P:], accumulate=True)
+                                   grad_scale_dev=gdev, dw_dtype=torch.bfloat16, dw_out=leaf.grad[P:], accumulate=True,
+                                   n_valid=n_valid)
             return None, None, db
         except NotImplementedError:
             pass   # several splits / very many query rows: a separate dW below, autograd accumulates it
@@ -436,7 +482,7 @@ def table_gradient(U, Wfull, P, labels, lse, g, bias, scale, label_base, precisi
         dfull[:P].zero_()
         dw_out = dfull[P:]
     dU, dW, db = ce_backward(U, W, labels, lse, g, bias, scale, label_base, need_du, need_dw, need_db, precision,
-                             grad_scale_dev=gdev, dw_dtype=W.dtype, dw_out=dw_out)
+                             grad_scale_dev=gdev, dw_dtype=W.dtype, dw_out=dw_out, n_valid=n_valid)
     if dW is not None:
         if dfull is not None:
             dW = dfull
@@ -448,7 +494,7 @@ def table_gradient(U, Wfull, P, labels, lse, g, bias, scale, label_base, precisi
 
 def fused_ce(U: torch.Tensor, W: torch.Tensor, labels: torch.Tensor, bias: Optional[torch.Tensor] = None,
              scale: float = 1.0, precision: Optional[str] = None, reduction: str = "mean", n_skip: int = 0,
-             accumulate: bool = False) -> torch.Tensor:
+             accumulate: bool = False, n_valid: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Drop-in for ``self.criterion(torch.einsum("MD,ND->MN", U, W), labels)`` with
     ``criterion = CrossEntropy4Logits(reduction="mean")`` (SASRec/main.py:126,217-219): same value,
     same gradients, no (M,N) logit matrix in forward or backward.
@@ -459,7 +505,10 @@ def fused_ce(U: torch.Tensor, W: torch.Tensor, labels: torch.Tensor, bias: Optio
 
     ``accumulate=True`` (bf16 parameter whose ``.grad`` buffer is kept allocated): the dW pass adds its rows
     straight into ``W.grad`` -- together with ``gather_rows(..., accumulate=True)`` the table's gradient is built
-    in ONE buffer without any table-sized temporary.  Same caveat as there: not for ``torch.autograd.grad``."""
+    in ONE buffer without any table-sized temporary.  Same caveat as there: not for ``torch.autograd.grad``.
+
+    ``n_valid`` (int32 device scalar, from ``compact_queries``): only the first ``n_valid`` rows of ``U`` / ``labels``
+    exist, the rest is capacity; the mean runs over ``n_valid`` and no count ever travels to the host."""
     if U.shape[0] == 0:
         # no query rows (e.g. a BERT4Rec step whose random mask selected nothing): F.cross_entropy returns
         # NaN for "mean" and 0 for "sum", with zero gradients -- reproduced without a launch
@@ -467,7 +516,7 @@ def fused_ce(U: torch.Tensor, W: torch.Tensor, labels: torch.Tensor, bias: Optio
         return zero / 0 if reduction == "mean" else zero
     if n_skip and bias is not None:
         raise ValueError("n_skip is for bias-free embedding tables (a bias head scores every row of its weight)")
-    return _FusedCE.apply(U, W, labels, bias, float(scale), precision, reduction, int(n_skip), bool(accumulate))
+    return _FusedCE.apply(U, W, labels, bias, float(scale), precision, reduction, int(n_skip), bool(accumulate), n_valid)
 
 
 # --------------------------------------------------------------------------------------

@@ -20,7 +20,7 @@ pytestmark = pytest.mark.skipif(not Path("/root/reference/SASRec/main.py").exist
 def oracle_ops(monkeypatch):
     """Stand-in for recboard_b200.ops on a GPU-less host (test only)."""
     stub = types.SimpleNamespace(
-        fused_ce=lambda U, W, labels, bias=None, scale=1.0, precision=None, n_skip=0: orc.ce_loss(U, W[n_skip:], labels, bias, scale),
+        fused_ce=lambda U, W, labels, bias=None, scale=1.0, precision=None, n_skip=0, n_valid=None: orc.ce_loss(U, W[n_skip:], labels, bias, scale),
         score_dense=lambda U, W, bias=None, scale=1.0, precision=None: orc.score_dense(U, W, bias, scale),
         gather_rows_raw=lambda table, idx: table[idx],
         spmm=lambda A, X, symmetric=False, At=None: orc.spmm(A, X),

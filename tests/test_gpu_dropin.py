@@ -98,6 +98,32 @@ def test_sasrec_fused_fit_full_pool_topk(cuda):
     _check_eval(fused, eager, data_fn, N)
 
 
+def test_sasrec_fused_sync_free_fit(cuda):
+    """fused_sync_free: the non-padding query rows are compacted on the device; ``fit`` runs without any device->host
+    synchronisation and reproduces the eager loss and gradients."""
+    N = 300
+    F_ = fuse(arch.SASRecFused, DM.TinySASRec, fused_sync_free=True)
+    data_fn = _seq_data(cuda, N=N)
+    torch.manual_seed(0)
+    eager = DM.TinySASRec(n_users=9, n_items=N).to(cuda).train()
+    fused = F_(n_users=9, n_items=N).to(cuda).train()
+    fused.load_state_dict(eager.state_dict())
+    le = eager(data_fn(eager))["rec_loss"]
+    le.backward()
+    data = data_fn(fused)
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        lf = fused(data)["rec_loss"]
+        lf.backward()
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    assert abs(float(lf) - float(le)) <= FP32_RTOL * abs(float(le))
+    ge, gf = grads_of(eager), grads_of(fused)
+    for name in ge:
+        assert rel(gf[name], ge[name]) <= 2e-5, name
+
+
 def test_sasrec_fused_bf16_precision(cuda):
     N = 300
     F_ = fuse(arch.SASRecFused, DM.TinySASRec, fused_precision="bf16")

@@ -636,6 +636,53 @@ def test_config3_full_size_gradients_against_fp64_oracle(ops):
         assert err <= BF16_RTOL, (name, err)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_device_side_row_count_matches_compacted_rows(ops, precision):
+    """a4: capacity rows + a device-side count (ops.compact_queries -> fused_ce(n_valid=...)) against the oracle on the
+    rows torch's boolean indexing selects -- loss, dX through the compaction, dW -- with NO host synchronisation
+    between the mask and the loss (torch.cuda.set_sync_debug_mode("error"))."""
+    g = torch.Generator().manual_seed(17)
+    B, S, N, d = 24, 30, 2000, 64
+    X = torch.randn(B, S, d, generator=g) * 0.4
+    W = torch.randn(N, d, generator=g) * 0.4
+    pos = torch.randint(0, N, (B, S), generator=g)
+    mask = torch.rand(B, S, generator=g) < 0.2
+    mask[0, 0] = True
+    if precision == "bf16":
+        X, W = bf16_round(X), bf16_round(W)
+    Xr = X.clone().requires_grad_(True)
+    ref_loss, _, ref_dW, _ = orc.ce_fwd_bwd(X[mask], W, pos[mask])
+    lossr = orc.ce_loss(Xr[mask], W, pos[mask])
+    lossr.backward()
+    cast = (lambda x: dev(x).bfloat16()) if precision == "bf16" else dev
+    Xd, Wd = cast(X).requires_grad_(True), cast(W).requires_grad_(True)
+    maskd, posd = dev(mask), dev(pos)
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        U, (labels,), count = ops.compact_queries(Xd, maskd, posd)
+        loss = ops.fused_ce(U, Wd, labels, n_valid=count, precision=precision)
+        loss.backward()
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    assert int(count) == int(mask.sum()) and U.shape[0] == B * S
+    tol = FP32_RTOL if precision == "fp32" else 1e-5
+    assert abs(float(loss) - float(ref_loss)) <= tol * abs(float(ref_loss))
+    if precision == "fp32":
+        assert_rel(Xd.grad, Xr.grad, 2e-5, "dX through the compaction")
+        assert_rel(Wd.grad, ref_dW, 2e-5, "dW")
+    else:
+        assert_grad_bf16(Xd.grad, Xr.grad, "dX through the compaction")
+        assert_grad_bf16(Wd.grad, ref_dW, "dW")
+    # nothing selected at all: F.cross_entropy(mean) over zero rows is NaN, the gradients are zero
+    Xz, Wz = cast(X).requires_grad_(True), cast(W).requires_grad_(True)
+    U0, (lab0,), c0 = ops.compact_queries(Xz, torch.zeros_like(maskd), posd)
+    l0 = ops.fused_ce(U0, Wz, lab0, n_valid=c0, precision=precision, reduction="sum")
+    l0.backward()
+    assert float(l0) == 0.0 and int(c0) == 0
+    assert float(Wz.grad.float().abs().max()) == 0.0 and float(Xz.grad.float().abs().max()) == 0.0
+
+
 def test_sharded_partials_merge_like_multi_gpu(ops):
     """Single-GPU simulation of R row shards: sharded stats/top-K/dW == unsharded."""
     from recboard_b200 import sharded

@@ -77,7 +77,8 @@ def _install_oracle_ops():
         return m, l, ll
 
     def ce_backward(U, W, labels, lse, grad_scale, bias=None, scale=1.0, label_base=0, need_dU=True, need_dW=True,
-                    need_dbias=False, precision=None, grad_scale_dev=None, dw_dtype=None, dw_out=None, accumulate=False):
+                    need_dbias=False, precision=None, grad_scale_dev=None, dw_dtype=None, dw_out=None, accumulate=False,
+                    n_valid=None):
         S = orc.score_dense(U, W, bias, scale)
         G = torch.exp(S - lse[:, None])
         loc = labels - label_base
