@@ -12,7 +12,7 @@
  *     exits; rb_last_error() returns a thread-local message for the last failure.
  *   - dtype: storage type of U / W / table.  mode: arithmetic of the contraction.
  *   - Matrices are row-major and contiguous: U (M,d), W (N,d) ("TN" GEMM, both K-major).
- *   - d must be a multiple of 8; bf16 mode supports d <= 256 (CE backward: d <= 128),
+ *   - d must be a multiple of 8; bf16 mode supports d <= 256 (fused CE passes included),
  *     fp32x3 mode supports d <= 128.  Base pointers must be 16-byte aligned.
  *   - There is no CPU fallback: without a CUDA device every compute entry returns an error.
  */
@@ -110,7 +110,7 @@ int rb_score_dense(const void* U, const void* W, const float* bias, float scale,
  *   row_max[i] ~ max_j S_ij (any reference within 2^16 of it), row_sumexp[i] = sum_j exp(S_ij - row_max[i]),
  *   label_logit[i] = S_i,(labels[i]-label_base) if that column lies in [0,N) else 0 (exact fp32 dot),
  *   dU_unnorm[i,:] = sum_j exp(S_ij - row_max[i]) W_j   (nullable; the same sweep feeds a second MMA,
- *                    so the gradient wrt U costs no extra pass -- bf16 mode, d <= 128, scale > 0).
+ *                    so the gradient wrt U costs no extra pass -- bf16 mode, d <= 256, scale > 0).
  * loss = mean(row_max + log(row_sumexp) - label_logit) replaces
  * `einsum("MD,ND->MN")` + `self.criterion(logits, labels)` (SASRec/main.py:217-219,
  * GRU4Rec/main.py:175-178, BERT4Rec/main.py:181-182).  Row-sharded tables: merge
@@ -146,7 +146,7 @@ int rb_ce_du_finish(const float* dU_unnorm, const float* row_max, const float* l
  * Recomputes S tile by tile; the softmax tile lives only in TMEM; the one-hot is applied exactly in
  * fp32 by an index-ordered (deterministic) row update.  Replaces the autograd of SASRec/main.py:217-219 run
  * by `loss.backward()` (:249): nll_loss_backward, _log_softmax_backward_data and the two cuBLAS
- * GEMMs.  bf16 mode: d <= 128, scale > 0.  fp32x3 mode (fp32 parity, d <= 128): the same gradients from
+ * GEMMs.  bf16 mode: d <= 256, scale > 0.  fp32x3 mode (fp32 parity, d <= 128): the same gradients from
  * exact fp32 FFMA passes (64 x 64 softmax tiles in shared memory), any sign of scale. */
 int rb_ce_bwd(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
               int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
@@ -157,7 +157,7 @@ int rb_ce_bwd(const void* U, const void* W, const float* bias, float scale, cons
  * writes bf16 rows directly instead of an fp32 (N,d) matrix that the caller would cast (1.5 N d bytes less
  * traffic, one pass less); rows that receive the exact fp32 one-hot correction go through an fp32 side
  * table first, so every element is the correctly rounded fp32 value rb_ce_bwd would have produced.
- * bf16 mode, d <= 128, scale > 0; workspace RB_OP_CE_BWD. */
+ * bf16 mode, d <= 256, scale > 0; workspace RB_OP_CE_BWD. */
 int rb_ce_bwd_dw_bf16(const void* U, const void* W, const float* bias, float scale, const int64_t* labels,
                       int64_t label_base, const float* lse, float grad_scale, const float* grad_scale_dev,
                       int64_t M, int64_t N, int d, void* dW_bf16, float* dbias, const int32_t* m_dev, void* ws,

@@ -188,7 +188,9 @@ static int sweep_xt(int mode, int d, long long n_stat) {
   if (mode != RB_MODE_BF16 && d > 64) return 1;   // fp32x3 at d = 128: one [hi|lo] stationary tile is already 128 KB
   return n_stat > 128 ? 2 : 1;
 }
-static bool pair_ok(int mode, int d, float scale) { return mode == RB_MODE_BF16 && d <= 128 && scale > 0.f; }
+static bool pair_ok(int mode, int d, float scale) { return mode == RB_MODE_BF16 && d <= 256 && scale > 0.f; }
+// stationary rows per work item of the fused CE passes: two 128-row tiles, or one for 128 < d <= 256 (pair.cuh, DS)
+static int pair_rows(int d) { return d > 128 ? 128 : 256; }
 
 // Operand staging: bf16 operands are used in place; fp32x3 operands are split into [hi|lo] in ws.
 struct Operand { const void* ptr; long long cols; bool bf16; };
@@ -438,8 +440,8 @@ extern "C" int rb_score_dense(const void* U, const void* W, const float* bias, f
 }
 
 static size_t pair_fwd_ws(long long M, long long N, int d, int sms) {
-  Plan p = make_plan(M, N, sms, 1 << 20, 8, 256);
-  const size_t stat_pad = static_cast<size_t>(p.n_stat_tiles) * 256;
+  Plan p = make_plan(M, N, sms, 1 << 20, 8, pair_rows(d));
+  const size_t stat_pad = static_cast<size_t>(p.n_stat_tiles) * pair_rows(d);
   return 2 * stat_pad * p.n_splits * 4 + static_cast<size_t>(p.n_splits) * M * d * 4 +
          static_cast<size_t>(p.n_strm_tiles) * 128 * 4 + 2048;
 }
@@ -450,8 +452,8 @@ static int ce_fwd_pair(const DevInfo& dv, const void* U, const void* W, const fl
                        const int64_t* labels, int64_t label_base, int64_t M, int64_t N, int d, float* row_max,
                        float* row_sumexp, float* label_logit, float* dU_unnorm, Bump& b, cudaStream_t st,
                        const int* m_dev = nullptr) {
-  Plan p = make_plan(M, N, dv.sms, 1 << 20, 8, 256);
-  const long long stat_pad = 1ll * p.n_stat_tiles * 256;
+  Plan p = make_plan(M, N, dv.sms, 1 << 20, 8, pair_rows(d));
+  const long long stat_pad = 1ll * p.n_stat_tiles * pair_rows(d);
   const long long n_pad = 1ll * p.n_strm_tiles * 128;
   float* pm2 = b.take<float>(stat_pad * p.n_splits);
   float* pl = b.take<float>(stat_pad * p.n_splits);
@@ -491,7 +493,7 @@ extern "C" int rb_ce_fwd(const void* U, const void* W, const float* bias, float 
   Bump b(ws, ws_bytes);
   if (dU_unnorm) {
     if (!pair_ok(mode, d, scale))
-      return fail(RB_E_UNSUPPORTED, "the fused forward+dU pass needs bf16 mode, d <= 128 and scale > 0 (use rb_ce_bwd's dU instead)");
+      return fail(RB_E_UNSUPPORTED, "the fused forward+dU pass needs bf16 mode, d <= 256 and scale > 0");
     return ce_fwd_pair(dv, U, W, bias, scale, labels, label_base, M, N, d, row_max, row_sumexp, label_logit, dU_unnorm, b, st, m_dev);
   }
   Operand ou, ow;
@@ -549,8 +551,8 @@ static int ce_bwd_dw_pair(const DevInfo& dv, const void* U, const void* W, const
                           const int64_t* labels, int64_t label_base, const float* lse2, float grad_scale,
                           const float* grad_scale_dev, int64_t M, int64_t N, int d, float* dW, float* dbias, Bump& b,
                           cudaStream_t st, __nv_bfloat16* dW_bf16 = nullptr, bool accumulate = false, const int* m_dev = nullptr) {
-  Plan p = make_plan(N, M, dv.sms, 64, 8, 256);
-  const long long n_pad = 1ll * p.n_stat_tiles * 256;
+  Plan p = make_plan(N, M, dv.sms, 64, 8, pair_rows(d));
+  const long long n_pad = 1ll * p.n_stat_tiles * pair_rows(d);
   // One-hot correction: up to LABEL_FIX_MAX query rows without a sort (label_owner + label_fix), beyond that
   // through the sorted scatter.  bf16 gradient requested: with one split and the sort-free correction the
   // kernel stores bf16 rows directly (label rows also in fp32 in a side table, corrected there, then rounded);
@@ -765,7 +767,7 @@ static int ce_bwd_impl(const void* U, const void* W, const float* bias, float sc
   DevInfo dv; if (int r = get_dev(dv)) return r;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (int r = check_common(U, W, M, N, d, dtype, mode)) return r;
-  if (d > 128) return fail(RB_E_UNSUPPORTED, "CE backward supports d <= 128");
+  if (d > 256) return fail(RB_E_UNSUPPORTED, "CE backward supports d <= 256");
   if (!labels || !lse) return fail(RB_E_ARG, "null pointer");
   if (!ws) return fail(RB_E_WORKSPACE, "workspace required");
   if (dbias && !dW && !dW_bf16) return fail(RB_E_ARG, "dbias is produced by the dW pass: pass dW too");
@@ -1014,10 +1016,10 @@ extern "C" size_t rb_workspace_bytes(int op, int64_t M, int64_t N, int d, int K,
     case RB_OP_CE_BWD: {
       if (mode == RB_MODE_FP32X3) return need + f32grad_ws(M, N, d, sms) + scatter_ws_bytes(M, d) + static_cast<size_t>(N) * 4 + 2048;
       size_t n = need + static_cast<size_t>(M) * (d + 3) * 4 + 2048 + pair_fwd_ws(M, N, d, sms);  // dU by recompute
-      Plan pw = make_plan(N, M, sms, 64, 8, 256);
+      Plan pw = make_plan(N, M, sms, 64, 8, pair_rows(d));
       n += ((M + 127) / 128) * 128 * 4 + 512;
       n += (pw.n_splits > 1 ? static_cast<size_t>(pw.n_splits) * N * (d + 1) * 4 : 0) + 1024;
-      n += static_cast<size_t>(pw.n_stat_tiles) * 256 * 4 + 512;  // bias2
+      n += static_cast<size_t>(pw.n_stat_tiles) * pair_rows(d) * 4 + 512;  // bias2
       // rb_ce_bwd_dw_bf16: slot map + side table (one split) or an fp32 staging copy of dW (several splits)
       n += static_cast<size_t>(N) * 4 + static_cast<size_t>(M) * (d * 4 + 12) + 2048;   // label owners + side table
       if (pw.n_splits > 1 || M > 16384) n += static_cast<size_t>(N) * d * 4 + 512;        // fp32 staging copy of dW

@@ -84,7 +84,11 @@ int launch_pair(int kc, bool bias, const CUtensorMap& ts, const CUtensorMap& ty,
     if (bias) return launch_pair_t<PairCfg<PASS, 2, 4, true>>(ts, ty, a, grid, st);
     return launch_pair_t<PairCfg<PASS, 2, 4, false>>(ts, ty, a, grid, st);
   }
-  return host_fail(RB_E_UNSUPPORTED, "the fused CE passes support d <= 128");
+  if (kc <= 4) {  // 128 < d <= 256: the d-split variant (one stationary tile, two output column halves; pair.cuh)
+    if (bias) return launch_pair_t<PairCfg<PASS, 2, 2, true, true>>(ts, ty, a, grid, st);
+    return launch_pair_t<PairCfg<PASS, 2, 2, false, true>>(ts, ty, a, grid, st);
+  }
+  return host_fail(RB_E_UNSUPPORTED, "the fused CE passes support d <= 256");
 }
 
 }  // namespace rb

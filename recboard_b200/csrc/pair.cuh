@@ -51,11 +51,11 @@ __device__ __forceinline__ constexpr bool pair_use_poly(int i) { return PAIR_POL
 struct PairArgs {
   int n_stat;        // valid rows of the stationary operand
   int n_strm;        // valid rows of the streamed operand
-  int n_pair_tiles;  // ceil(n_stat / 256)
+  int n_pair_tiles;  // ceil(n_stat / 256)  (d-split variant: ceil(n_stat / 128))
   int n_strm_tiles;  // ceil(n_strm / 128)
   int n_splits;      // streamed range of every pair tile is cut into n_splits work items
   int d;             // true feature width
-  int stat_pad;      // n_pair_tiles * 256 (row pitch of the per-row partial arrays)
+  int stat_pad;      // n_pair_tiles * 256 (d-split: * 128): row pitch of the per-row partial arrays
   float scale;       // logits = scale * <u,w> + bias
   // per STREAMED row, padded to n_strm_tiles*128: FWD = bias*log2(e) (BIAS only, 0 padding),
   //                                                DW  = -lse*log2(e) (-inf padding => P = 0)
@@ -83,19 +83,30 @@ struct PairArgs {
   int accumulate;              // bf16 output only: rows are ADDED to what out_bf16 already holds (the parameter's existing gradient)
 };
 
-template <int PASS_, int KC_, int NS_, bool BIAS_>
+// DS_ ("d split", 128 < d <= 256): the accumulator of a 128-row stationary tile is 256 columns wide, so the CTA keeps
+// ONE stationary tile X (128 rows x 4 K-chunks, the same 64 KB as two d = 128 tiles) and the two chains g = 0, 1
+// work on the SAME rows: both compute S = X . Y_t^T over all of d (16 K-steps) and chain g accumulates output
+// columns [128 g, 128 g + 128) from the g-th column half of the streamed tile.  S and its exponentials are computed
+// twice (executed flop per pair: 2*(2d) + 2d against 2d + 2d), which keeps every hand-shake, the TMEM map and the
+// epilogue of the d <= 128 kernel; both chains see bit-identical scores, so they take the same rescale decisions.
+template <int PASS_, int KC_, int NS_, bool BIAS_, bool DS_ = false>
 struct PairCfg {
   static constexpr int PASS = PASS_, KC = KC_, NS = NS_;
   static constexpr bool BIAS = BIAS_;
+  static constexpr bool DS = DS_;
   static constexpr bool AUX = (PASS_ == PASS_DW) || BIAS_;   // a per-streamed-row vector rides with the tiles
-  static constexpr int DPAD = KC_ * 64;
-  static constexpr int TILE_BYTES = KC_ * 128 * 128;  // one 128-row operand tile
+  static constexpr int DPAD = KC_ * 64;                // accumulator columns of one chain
+  static constexpr int XK = DS_ ? 4 : KC_;             // 64-element K chunks of an operand tile (MMA1 runs 4 XK K-steps)
+  static constexpr int STAT_ROWS = DS_ ? 128 : 256;    // stationary rows per work item
+  static constexpr int TILE_BYTES = XK * 128 * 128;    // one 128-row operand tile
+  static constexpr int X_BYTES = DS_ ? TILE_BYTES : 2 * TILE_BYTES;
   static constexpr int AUX_BYTES = 512;
   static constexpr int CTRL_BYTES = 1024 + 4096;      // barriers + the row exchange between the column halves
-  static constexpr int SMEM_BYTES = (2 + NS_) * TILE_BYTES + NS_ * AUX_BYTES + CTRL_BYTES + 1024 /*align*/;
+  static constexpr int SMEM_BYTES = X_BYTES + NS_ * TILE_BYTES + NS_ * AUX_BYTES + CTRL_BYTES + 1024 /*align*/;
   static constexpr int TMEM_COLS = 512;
   static constexpr int ACC0 = 0, ACC1 = 128, S0 = 256;   // S_g at S0 + 128 g
-  static_assert(KC_ == 1 || KC_ == 2, "d <= 128");
+  static_assert(KC_ == 1 || KC_ == 2, "128 accumulator columns per chain");
+  static_assert(!DS_ || KC_ == 2, "the d-split variant accumulates two 128-column halves");
   static_assert(SMEM_BYTES <= 227 * 1024, "SMEM budget");
 };
 
@@ -152,8 +163,8 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
             const PairArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* x_smem = smem;                         // X0 | X1
-  uint8_t* y_smem = smem + 2 * C::TILE_BYTES;     // NS stages
+  uint8_t* x_smem = smem;                         // X0 | X1   (d-split: one tile of four K chunks)
+  uint8_t* y_smem = smem + C::X_BYTES;            // NS stages
   float* aux_smem = reinterpret_cast<float*>(y_smem + C::NS * C::TILE_BYTES);   // NS x 128 floats
   PairControl* bar = reinterpret_cast<PairControl*>(y_smem + C::NS * C::TILE_BYTES + C::NS * C::AUX_BYTES);
 
@@ -163,7 +174,7 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
   int n_stat = a.n_stat, n_pair_tiles = a.n_pair_tiles, n_strm_tiles = a.n_strm_tiles;
   if (a.m_dev != nullptr) {
     const int m = max(0, *a.m_dev);
-    if (C::PASS == PASS_FWD) { n_stat = min(n_stat, m); n_pair_tiles = min(n_pair_tiles, (n_stat + 255) / 256); }
+    if (C::PASS == PASS_FWD) { n_stat = min(n_stat, m); n_pair_tiles = min(n_pair_tiles, (n_stat + C::STAT_ROWS - 1) / C::STAT_ROWS); }
     else n_strm_tiles = min(n_strm_tiles, (min(a.n_strm, m) + 127) / 128);
   }
   const int total_items = n_pair_tiles * a.n_splits;
@@ -203,8 +214,8 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
     // no query rows at all (device-side count 0): the gradient of this pass is zero; nothing to stream
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int pt = item % n_pair_tiles, split = item / n_pair_tiles;
-      for (int i = threadIdx.x; i < 256 * (a.d / 4); i += blockDim.x) {
-        const int row = pt * 256 + i / (a.d / 4), c = (i % (a.d / 4)) * 4;
+      for (int i = threadIdx.x; i < C::STAT_ROWS * (a.d / 4); i += blockDim.x) {
+        const int row = pt * C::STAT_ROWS + i / (a.d / 4), c = (i % (a.d / 4)) * 4;
         if (row < a.n_stat) {
           if (a.out_bf16 != nullptr) {
             if (!a.accumulate) *reinterpret_cast<uint2*>(static_cast<uint16_t*>(a.out_bf16) + static_cast<long long>(row) * a.d + c) = make_uint2(0u, 0u);
@@ -224,12 +235,18 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
       item_range(item, pt, split, t0, t1);
       mbar_wait(&bar->x_empty, (k & 1) ^ 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(&bar->x_full, 2 * C::TILE_BYTES);
+        mbar_arrive_expect_tx(&bar->x_full, C::X_BYTES);
+        if (C::DS) {
 #pragma unroll
-        for (int g = 0; g < 2; ++g)
+          for (int c = 0; c < C::XK; ++c)
+            tma_load_2d(x_smem + c * 16384, &tm_stat, &bar->x_full, c * 64, pt * 128);
+        } else {
 #pragma unroll
-          for (int c = 0; c < C::KC; ++c)
-            tma_load_2d(x_smem + g * C::TILE_BYTES + c * 16384, &tm_stat, &bar->x_full, c * 64, (pt * 2 + g) * 128);
+          for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int c = 0; c < C::KC; ++c)
+              tma_load_2d(x_smem + g * C::TILE_BYTES + c * 16384, &tm_stat, &bar->x_full, c * 64, (pt * 2 + g) * 128);
+        }
       }
       __syncwarp();
       for (int t = t0; t < t1; ++t, ++it) {
@@ -238,7 +255,7 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
         if (elect_one()) {
           mbar_arrive_expect_tx(&bar->full[st], C::TILE_BYTES + (C::AUX ? C::AUX_BYTES : 0));
 #pragma unroll
-          for (int c = 0; c < C::KC; ++c)
+          for (int c = 0; c < C::XK; ++c)
             tma_load_2d(y_smem + st * C::TILE_BYTES + c * 16384, &tm_strm, &bar->full[st], c * 64, t * 128);
           if (C::AUX)
             bulk_load_1d(aux_smem + st * 128, a.aux + static_cast<long long>(t) * 128, C::AUX_BYTES, &bar->full[st]);
@@ -261,9 +278,9 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
     // S_g = X_g . Y^T   (the streamed tile in stage st)
     auto m1 = [&](int g, uint32_t st) {
       const uint32_t d_tmem = tmem_base + C::S0 + g * 128;
-      const uint32_t xg = x_lo + ((g * C::TILE_BYTES) >> 4), ys = y_lo1 + ((st * C::TILE_BYTES) >> 4);
+      const uint32_t xg = x_lo + (C::DS ? 0u : ((g * C::TILE_BYTES) >> 4)), ys = y_lo1 + ((st * C::TILE_BYTES) >> 4);
 #pragma unroll
-      for (int c = 0; c < C::KC; ++c) {
+      for (int c = 0; c < C::XK; ++c) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
           mma_f16_ss(d_tmem, smem_desc(dhi, xg + ((c * 16384 + kk * 32) >> 4)),
@@ -276,7 +293,8 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
     auto m2_piece = [&](int g, int pz, uint32_t st, bool first) {
       const uint32_t d_tmem = tmem_base + (g == 0 ? C::ACC0 : C::ACC1);
       const uint32_t a_tmem = tmem_base + C::S0 + g * 128 + (pz >> 1) * 64 + (pz & 1) * 16;
-      const uint32_t ys = y_lo2 + ((st * C::TILE_BYTES + pz * 4096) >> 4);
+      // d-split: chain g multiplies by the g-th column half (K chunks 2g, 2g+1) of the streamed tile
+      const uint32_t ys = y_lo2 + ((st * C::TILE_BYTES + (C::DS ? g * 2 * 16384 : 0) + pz * 4096) >> 4);
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk)
         mma_f16_ts(d_tmem, a_tmem + kk * 8, smem_desc(dhi, ys + ((kk * 2048) >> 4)), idesc2, !(first && kk == 0));
@@ -348,7 +366,8 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++k) {
       int pt, split, t0, t1;
       item_range(item, pt, split, t0, t1);
-      const int srow = (pt * 2 + g) * 128 + r;   // global stationary row
+      const int srow = (C::DS ? pt : pt * 2 + g) * 128 + r;   // global stationary row
+      const bool stats_owner = ch == 0 && (!C::DS || g == 0);   // the thread that reports the row's scalars
       const bool srow_ok = srow < n_stat;
 
       float m2 = 0.f, l = 0.f;      // FWD: row reference (log2 domain) and this thread's share of sum P
@@ -533,7 +552,7 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
         uint32_t v[32];
         tmem_ld32(t_acc + cc * 32, v);
         tmem_ld_wait();
-        const int col0 = ch * HALF + cc * 32;   // first accumulator column of this chunk
+        const int col0 = (C::DS ? g * 128 : 0) + ch * HALF + cc * 32;   // first output column of this chunk
         if (bf16_out) {
           if (srow_ok) {
 #pragma unroll
@@ -578,9 +597,9 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
       }
       tc_fence_before();
       mbar_arrive(&bar->acc_empty[g]);
-      if (ch == 0) {
+      if (stats_owner) {
         if (C::PASS == PASS_FWD) {
-          const long long pslot = static_cast<long long>(split) * a.stat_pad + (pt * 2 + g) * 128 + r;
+          const long long pslot = static_cast<long long>(split) * a.stat_pad + (C::DS ? pt : pt * 2 + g) * 128 + r;
           a.part_m2[pslot] = m2;
           a.part_l[pslot] = l;
         } else if (a.rowsum_out != nullptr && srow_ok) {

@@ -283,8 +283,8 @@ def score_dense(U: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] =
 # fused full-catalog cross-entropy
 # --------------------------------------------------------------------------------------
 def fused_du_supported(U, precision: Optional[str], scale: float) -> bool:
-    """Can rb_ce_fwd also produce the dU accumulator in the same sweep?  (bf16 mode, d <= 128, scale > 0)"""
-    return _mode_for(U, precision) == "bf16" and U.shape[1] <= 128 and scale > 0
+    """Can rb_ce_fwd also produce the dU accumulator in the same sweep?  (bf16 mode, d <= 256, scale > 0)"""
+    return _mode_for(U, precision) == "bf16" and U.shape[1] <= 256 and scale > 0
 
 
 def _count_ptr(n_valid, dev):

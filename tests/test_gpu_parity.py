@@ -191,7 +191,8 @@ def test_scores_and_rowstats(ops, M, N, d, precision):
 
 
 @pytest.mark.parametrize("M,N,d", [(1, 130, 64), (300, 1000, 64), (513, 4099, 128), (3013, 12101, 64),
-                                   (17000, 700, 64)])   # > 16384 rows: one-hot correction through the sorted scatter
+                                   (17000, 700, 64),    # > 16384 rows: one-hot correction through the sorted scatter
+                                   (300, 1000, 256), (513, 4099, 192), (2100, 40_000, 256)])   # 128 < d <= 256: d-split passes
 def test_ce_gradients_bf16(ops, M, N, d):
     g = torch.Generator().manual_seed(M + N + d)
     U = bf16_round(torch.randn(M, d, generator=g) * 1.5 / d ** 0.25)
@@ -205,6 +206,26 @@ def test_ce_gradients_bf16(ops, M, N, d):
     assert abs(float(loss) - float(ref_loss)) <= 1e-5 * abs(float(ref_loss))
     assert_grad_bf16(Ud.grad, rdU, "dU")
     assert_grad_bf16(Wd.grad, rdW, "dW")
+
+
+@pytest.mark.parametrize("M,N,d", [(700, 5000, 256), (257, 1300, 200)])
+def test_ce_bias_head_wide_rows(ops, M, N, d):
+    """128 < d <= 256 (CCFRec / E4SRec-style heads, config-4-shaped training): the d-split fused passes with bias and a
+    scale, through autograd -- loss, dU, dW, dbias against the oracle."""
+    g = torch.Generator().manual_seed(M + N + d)
+    U = bf16_round(torch.randn(M, d, generator=g) * 1.2 / d ** 0.25)
+    W = bf16_round(torch.randn(N, d, generator=g) * 1.2 / d ** 0.25)
+    b = torch.randn(N, generator=g) * 0.3
+    lab = torch.randint(0, N, (M,), generator=g)
+    lab[: M // 6] = N - 1
+    ref_loss, rdU, rdW, rdb = orc.ce_fwd_bwd(U, W, lab, bias=b, scale=0.8)
+    Ud, Wd, bd = dev(U).bfloat16().requires_grad_(True), dev(W).bfloat16().requires_grad_(True), dev(b).requires_grad_(True)
+    loss = ops.fused_ce(Ud, Wd, dev(lab), bias=bd, scale=0.8)
+    loss.backward()
+    assert abs(float(loss) - float(ref_loss)) <= 1e-5 * abs(float(ref_loss))
+    assert_grad_bf16(Ud.grad, rdU, "dU")
+    assert_grad_bf16(Wd.grad, rdW, "dW")
+    assert_grad_bf16(bd.grad, rdb, "dbias")
 
 
 @pytest.mark.parametrize("M,N,d,with_bias", [(1, 130, 64, False), (300, 1000, 64, True), (513, 4099, 32, False),
@@ -249,7 +270,7 @@ def test_golden_ce_fp32_gradients(ops, golden):
 
 
 @pytest.mark.parametrize("M,N,d,with_bias", [(300, 1000, 64, True), (513, 40_000, 128, False), (2000, 70_000, 128, True),
-                                             (17000, 50_000, 64, True)])
+                                             (17000, 50_000, 64, True), (700, 30_000, 256, True), (513, 4099, 136, False)])
 def test_ce_dw_bf16_output_is_the_rounded_fp32_gradient(ops, M, N, d, with_bias):
     """rb_ce_bwd_dw_bf16 (one split: direct bf16 rows + fp32 side table for label rows; several splits: fp32
     staging) must equal the fp32 gradient of rb_ce_bwd rounded to bf16, bit for bit; dbias to the last ulp."""
@@ -553,11 +574,12 @@ def test_gather_rows_backward_accumulates_into_existing_grad(ops):
             assert Wd.grad.data_ptr() == buf.data_ptr()           # still the same buffer: nothing was re-allocated
 
 
-def test_bf16_table_gradient_built_in_one_buffer(ops):
+@pytest.mark.parametrize("d", [128, 256])
+def test_bf16_table_gradient_built_in_one_buffer(ops, d):
     """bf16 parameter, ``.grad`` kept allocated: the gather's rows and the head's dW are both added inside their own
     kernels into that ONE (N+P,d) buffer (gather_rows(accumulate=True) + fused_ce(n_skip, accumulate=True))."""
     g = torch.Generator().manual_seed(6)
-    N, P, d, B, S, M = 3000, 1, 128, 32, 12, 300
+    N, P, B, S, M = 3000, 1, 32, 12, 300
     W0 = bf16_round(torch.randn(N + P, d, generator=g) * 0.3)
     W0[0] = 0
     idx = torch.randint(0, N + P, (B, S), generator=g)
@@ -636,15 +658,15 @@ def test_config3_full_size_gradients_against_fp64_oracle(ops):
         assert err <= BF16_RTOL, (name, err)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_device_side_row_count_matches_compacted_rows(ops, precision):
+@pytest.mark.parametrize("precision,d", [("fp32", 64), ("bf16", 64), ("bf16", 256)])
+def test_device_side_row_count_matches_compacted_rows(ops, precision, d):
     """a4: capacity rows + a device-side count (ops.compact_queries -> fused_ce(n_valid=...)) against the oracle on the
     rows torch's boolean indexing selects -- loss, dX through the compaction, dW -- with NO host synchronisation
     between the mask and the loss (torch.cuda.set_sync_debug_mode("error"))."""
     g = torch.Generator().manual_seed(17)
-    B, S, N, d = 24, 30, 2000, 64
-    X = torch.randn(B, S, d, generator=g) * 0.4
-    W = torch.randn(N, d, generator=g) * 0.4
+    B, S, N = 24, 30, 2000
+    X = torch.randn(B, S, d, generator=g) * 0.4 * (64 / d) ** 0.25
+    W = torch.randn(N, d, generator=g) * 0.4 * (64 / d) ** 0.25
     pos = torch.randint(0, N, (B, S), generator=g)
     mask = torch.rand(B, S, generator=g) < 0.2
     mask[0, 0] = True
