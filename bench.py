@@ -219,7 +219,7 @@ def run_ours(args):
     def hot_path(U_tr, lab, sq, U_ev, s_crow, s_col):
         """One pass of the path through the public API (recboard_b200.ops / .sharded), gradients through autograd:
         the table's gradient -- the gather's scatter-add rows plus the scoring head's dW -- ends up in table.grad."""
-        table.grad.zero_()                                                        # zero_grad(set_to_none=False)
+        table.grad = None                                                         # optimizer.zero_grad() (set_to_none=True, torch's default)
         if world > 1:   # a2 over the row-sharded table: owners gather, one all-reduce assembles the replicated rows
             emb = sharded.sharded_gather_rows(table, sq - 1, row_start - 1, padding_idx=-1, accumulate=True)
         else:

@@ -115,7 +115,7 @@ struct PairControl {
   uint64_t x_full, x_empty;
   uint64_t s_full[2];                    // per stationary tile
   uint64_t p_full[2][4];                 // per stationary tile and 32-column piece (column half * 2 + piece of the half)
-  uint64_t m2_done[2];                   // one completion per MMA2 of tile g (rescale safety)
+  uint64_t unused_[2];
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_base;
   uint32_t pad_[31];
@@ -188,7 +188,6 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
     for (int g = 0; g < 2; ++g) {
       mbar_init(&bar->s_full[g], 1);
       for (int pz = 0; pz < 4; ++pz) mbar_init(&bar->p_full[g][pz], 128);
-      mbar_init(&bar->m2_done[g], 1);
       mbar_init(&bar->acc_full[g], 1);
       mbar_init(&bar->acc_empty[g], 256);
     }
@@ -337,7 +336,6 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
             __syncwarp();
           }
           if (elect_one()) {
-            if (C::PASS == PASS_FWD) tc_commit(&bar->m2_done[g]);
             if (g == 1) tc_commit(&bar->empty[st]);   // every MMA on Y_j retires before this fires
             if (!more) tc_commit(&bar->acc_full[g]);
             if (more) {
@@ -429,10 +427,9 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant__
           } else {
             const bool grow = cm2 > m2 + PAIR_RESCALE_TH;
             if (__any_sync(0xffffffffu, grow)) {
-              // A_g must be quiescent.  MMA2 of the previous tile is the it-th completion of m2_done[g]
-              // (parity (it-1)&1); MMA2 of this tile cannot start before our p_full arrivals.
-              mbar_wait(&bar->m2_done[g], (it & 1) ^ 1);
-              tc_fence_after();
+              // A_g is quiescent here: MMA1 of this tile was issued behind MMA2 of the previous one and tcgen05.commit
+              // completes in issue order, so s_full[g] (waited above) implies that MMA2 has retired; MMA2 of this tile
+              // cannot start before our p_full arrivals.
               const float f = grow ? ex2_approx(m2 - cm2) : 1.f;
               pair_rescale_acc(t_acc, HALF, f);   // this thread's half of the row's accumulator
               l *= f;

@@ -463,7 +463,8 @@ def table_gradient(U, Wfull, P, labels, lse, g, bias, scale, label_base, precisi
     ``Wfull[P:]`` -> (dU | None, gradient for ``Wfull`` as autograd wants it | None, dbias | None).
 
     * ``leaf`` (the parameter itself, accumulate mode) with an allocated bf16 ``.grad``: the dW pass ADDS its rows
-      into ``leaf.grad[P:]`` and autograd gets ``None`` for the table;
+      into ``leaf.grad[P:]`` and autograd gets ``None`` for the table; with ``leaf.grad is None`` (bf16) the pass
+      writes the new gradient buffer and assigns it;
     * otherwise one (N+P,d) tensor in the parameter's dtype, rows [P:] written in place by the pass, pad rows zero."""
     W = Wfull[P:] if P else Wfull
     bf16_mode = _mode_for(U, precision) == "bf16"
@@ -476,6 +477,18 @@ def table_gradient(U, Wfull, P, labels, lse, g, bias, scale, label_base, precisi
             return None, None, db
         except NotImplementedError:
             pass   # several splits / very many query rows: a separate dW below, autograd accumulates it
+    if (need_dw and not need_du and leaf is not None and leaf.grad is None and Wfull.dtype == torch.bfloat16 and bf16_mode
+            and Wfull.is_contiguous()):
+        # ``zero_grad()`` left no gradient (set_to_none=True, torch's default): the pass WRITES the parameter's new
+        # gradient buffer -- what autograd does with the first gradient of a leaf -- and whoever comes next in this
+        # backward (the gather's scatter-add) adds into it.  No zero-fill of the (N+P,d) buffer, no read of old rows.
+        buf = torch.empty_like(Wfull)
+        if P:
+            buf[:P].zero_()
+        _, _, db = ce_backward(U, W, labels, lse, g, bias, scale, label_base, False, True, need_db, precision,
+                               grad_scale_dev=gdev, dw_dtype=torch.bfloat16, dw_out=buf[P:], n_valid=n_valid)
+        leaf.grad = buf
+        return None, None, db
     dfull = dw_out = None
     if need_dw and P and (Wfull.dtype == torch.float32 or (Wfull.dtype == torch.bfloat16 and bf16_mode)):
         dfull = torch.empty_like(Wfull)     # the pass writes rows [P:] in place, the P pad rows are zero
@@ -503,9 +516,9 @@ def fused_ce(U: torch.Tensor, W: torch.Tensor, labels: torch.Tensor, bias: Optio
     (``self.Item.embeddings.weight[self.NUM_PADS:]``, SASRec/main.py:193; labels index that view).  The gradient
     then comes back as one (N+P,d) tensor written in place -- no zero-padded copy from the slice's backward.
 
-    ``accumulate=True`` (bf16 parameter whose ``.grad`` buffer is kept allocated): the dW pass adds its rows
-    straight into ``W.grad`` -- together with ``gather_rows(..., accumulate=True)`` the table's gradient is built
-    in ONE buffer without any table-sized temporary.  Same caveat as there: not for ``torch.autograd.grad``.
+    ``accumulate=True`` (bf16 parameter): the dW pass adds its rows straight into ``W.grad`` -- or, after a
+    ``zero_grad()`` that set it to None, writes the new ``W.grad`` -- and together with
+    ``gather_rows(..., accumulate=True)`` the table's gradient is built in ONE buffer without any table-sized temporary.  Same caveat as there: not for ``torch.autograd.grad``.
 
     ``n_valid`` (int32 device scalar, from ``compact_queries``): only the first ``n_valid`` rows of ``U`` / ``labels``
     exist, the rest is capacity; the mean runs over ``n_valid`` and no count ever travels to the host."""

@@ -602,6 +602,16 @@ def test_bf16_table_gradient_built_in_one_buffer(ops, d):
     assert abs(float(lossd) - float(loss)) <= 1e-5 * abs(float(loss))
     assert_rel(Wd.grad.float() - dev(old), Wr.grad, 3 * BF16_RTOL, "bf16 table gradient (two roundings: gather rows, dW)")
     assert bool((Wd.grad[0].float().cpu() == old[0]).all())     # the padding row received nothing
+    # after zero_grad() (set_to_none=True): the dW pass writes the new gradient buffer, the gather adds into it
+    Wd.grad = None
+    Ud2 = dev(U).bfloat16().requires_grad_(True)
+    embd = ops.gather_rows(Wd, dev(idx), padding_idx=0, accumulate=True)
+    lossd = ops.fused_ce(Ud2, Wd, dev(labels), n_skip=P, accumulate=True)
+    torch.autograd.backward([lossd, embd], [None, dev(gemb).bfloat16()])
+    assert Wd.grad is not None and Wd.grad.dtype == torch.bfloat16 and Wd.grad.shape == Wd.shape
+    assert_rel(Wd.grad.float(), Wr.grad, 3 * BF16_RTOL, "bf16 table gradient from a fresh buffer")
+    assert float(Wd.grad[0].float().abs().max()) == 0.0
+    assert_grad_bf16(Ud2.grad, Ud.grad.float().cpu(), "dU unchanged")
 
 
 def test_config2_full_size_topk_against_fp64_oracle(ops):
