@@ -204,6 +204,9 @@ def run_ours(args):
                        synth.embeddings(n_shard, D, gw, dev, torch.bfloat16, gain=1.5)]).requires_grad_(True)
     table.grad = torch.zeros_like(table)
     W = table.detach()[1:]                                            # the scored view weight[NUM_PADS:] (:193)
+    peers = None
+    if world > 1 and os.environ.get("RB_BENCH_GATHER", "peer") == "peer":
+        peers = sharded.PeerTable(table, row_start, n_skip=1)
     # ---- one batch of inputs (identical on every rank: queries are replicated)
     g = torch.Generator(device=dev).manual_seed(2026 + 3)
     U_train = synth.embeddings(ROWS, D, g, dev, torch.bfloat16, gain=1.5)
@@ -220,8 +223,14 @@ def run_ours(args):
         """One pass of the path through the public API (recboard_b200.ops / .sharded), gradients through autograd:
         the table's gradient -- the gather's scatter-add rows plus the scoring head's dW -- ends up in table.grad."""
         table.grad = None                                                         # optimizer.zero_grad() (set_to_none=True, torch's default)
-        if world > 1:   # a2 over the row-sharded table: owners gather, one all-reduce assembles the replicated rows
-            emb = sharded.sharded_gather_rows(table, sq - 1, row_start - 1, padding_idx=-1, accumulate=True)
+        if world > 1:   # a2 over the row-sharded table, GLOBAL ids: rows are read where they live (own shard, or a peer's
+            #              over NVLink through the IPC mapping); fence() is what follows an optimizer step in a real loop.
+            #              RB_BENCH_GATHER=allreduce: owners gather + one all-reduce of the replicated rows instead.
+            if peers is not None:
+                peers.fence()
+                emb = peers.gather(sq - 1, padding_idx=-1, accumulate=True)
+            else:
+                emb = sharded.sharded_gather_rows(table, sq - 1, row_start - 1, padding_idx=-1, accumulate=True)
         else:
             emb = ops.gather_rows(table, sq, padding_idx=0, accumulate=True)      # a2
         Uq = U_tr.detach().requires_grad_(True)
@@ -463,6 +472,8 @@ def run_ours(args):
             "dtype": "bf16", "data": "synthetic", "step_ms": step_ms,
             "config": {"workload": WORKLOAD,
                        "rows": ROWS, "n_items_total": n_total, "d": D, "topk": TOPK, "parallelism": f"row-sharded table x{world}",
+                       "input_gather": ("local" if world == 1 else ("global ids, rows read from the owning GPU over NVLink (CUDA IPC peer memory)"
+                                                                    if peers is not None else "global ids, owners gather + all-reduce")),
                        "l2": "inputs larger than L2 (256 MB table shard streamed per sweep); no flush",
                        "pre_warm": f"{n_pre} untimed steps (~2.3 s) before the {max(args.warmup, 3)} warm-up steps"},
             "clocks": clocks,

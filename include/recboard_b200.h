@@ -91,6 +91,22 @@ int rb_gather_dot_bwd(const void* U, const void* table, const int64_t* idx, cons
 int rb_spmm_csr(const int64_t* crow, const int64_t* col, const float* val, const float* X, float* Y,
                 float* acc, float beta, int64_t n_rows, int64_t n_cols, int d, rb_stream_t stream);
 
+/* ---- a2 over a ROW-SHARDED table on the GPUs of one box (the input side of `self.Item.embeddings(seqs)`,
+ * SASRec/main.py:183, when the table is split by rows across ranks): every rank reads the rows where they live --
+ * its own shard or a peer's, mapped through CUDA IPC, loaded over NVLink -- instead of gathering zeros for foreign ids
+ * and all-reducing the replicated activations.
+ *   rb_ipc_export        owner: handle (64 bytes) of the allocation holding `ptr` + the offset of `ptr` inside it
+ *   rb_ipc_open          peer (its own device current): maps the allocation, enables peer access; *ptr_out = the
+ *                        owner's `ptr` in this process, *base_out = what rb_ipc_close takes
+ *   rb_gather_rows_peers out[i,:] = shard r's row (idx[i] - starts[r]) for starts[r] <= idx[i] < starts[r+1];
+ *                        ids outside [starts[0], starts[n_shards]) give zero rows.  shard_ptrs / starts are HOST
+ *                        arrays (n_shards <= 16 pointers, n_shards + 1 bounds). */
+int rb_ipc_export(const void* ptr, void* handle64, int64_t* offset);
+int rb_ipc_open(const void* handle64, int64_t offset, void** ptr_out, void** base_out);
+int rb_ipc_close(void* base);
+int rb_gather_rows_peers(const void* const* shard_ptrs, const int64_t* starts, int n_shards, const int64_t* idx, void* out,
+                         int64_t n_idx, int d, int dtype, rb_stream_t stream);
+
 /* Device-side row compaction: row_index[k] = position of the k-th non-zero byte of mask[0..n) for k < *count, -1
  * beyond; *count = number of non-zero bytes.  Replaces the boolean indexing `userEmbds[indices]` /
  * `positives[indices]` (SASRec/main.py:199-200), `fc(userEmbds)[masks]` (BERT4Rec/main.py:181), whose nonzero()

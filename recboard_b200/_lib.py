@@ -24,6 +24,10 @@ _p, _i64, _i32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_
 #: every symbol include/recboard_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "rb_gather_rows": (_i32, [_p, _p, _p, _i64, _i64, _i32, _i32, _p]),
+    "rb_ipc_export": (_i32, [_p, _p, _p]),
+    "rb_ipc_open": (_i32, [_p, _i64, _p, _p]),
+    "rb_ipc_close": (_i32, [_p]),
+    "rb_gather_rows_peers": (_i32, [_p, _p, _i32, _p, _p, _i64, _i32, _i32, _p]),
     "rb_compact_index": (_i32, [_p, _i64, _p, _p, _p]),
     "rb_normalize_rows": (_i32, [_p, _p, _p, _i64, _i32, _i32, _i32, _f32, _p]),
     "rb_scatter_add_rows": (_i32, [_p, _p, _p, _i64, _i64, _i32, _i32, _i64, _p, _sz, _p]),

@@ -232,6 +232,74 @@ extern "C" int rb_gather_rows(const void* table, const int64_t* idx, void* out, 
   return 0;
 }
 
+// ------------------------------------------------------- gather over peer-mapped shards (one box, NVLink)
+// rb_ipc_export / rb_ipc_open: the CUDA IPC plumbing a process needs to map another rank's shard (the owner exports the
+// handle of the allocation that holds `ptr` and the offset of `ptr` inside it; a peer opens it with ITS device
+// current, which also enables peer access between the two devices).
+extern "C" int rb_ipc_export(const void* ptr, void* handle64, int64_t* offset) {
+  RB_RANGE("rb_ipc_export");
+  DevInfo dv; if (int r = get_dev(dv)) return r;
+  if (!ptr || !handle64 || !offset) return fail(RB_E_ARG, "null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CUdeviceptr base = 0; size_t size = 0;
+  typedef CUresult (*range_fn_t)(CUdeviceptr*, size_t*, CUdeviceptr);
+  void* fp = nullptr; cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fp, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fp)
+    return fail(RB_E_NODEVICE, "cuMemGetAddressRange not available from the driver");
+  CUresult cr = reinterpret_cast<range_fn_t>(fp)(&base, &size, reinterpret_cast<CUdeviceptr>(ptr));
+  if (cr != CUDA_SUCCESS) return fail(RB_E_ARG, "cuMemGetAddressRange failed with CUresult %d", (int)cr);
+  cudaIpcMemHandle_t h;
+  RB_CUDA(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base)));
+  std::memcpy(handle64, &h, 64);
+  *offset = static_cast<int64_t>(reinterpret_cast<CUdeviceptr>(ptr) - base);
+  return 0;
+}
+extern "C" int rb_ipc_open(const void* handle64, int64_t offset, void** ptr_out, void** base_out) {
+  RB_RANGE("rb_ipc_open");
+  DevInfo dv; if (int r = get_dev(dv)) return r;
+  if (!handle64 || !ptr_out || !base_out) return fail(RB_E_ARG, "null pointer");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  void* base = nullptr;
+  RB_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+  *base_out = base;
+  *ptr_out = static_cast<char*>(base) + offset;
+  return 0;
+}
+extern "C" int rb_ipc_close(void* base) {
+  if (!base) return 0;
+  RB_CUDA(cudaIpcCloseMemHandle(base));
+  return 0;
+}
+extern "C" int rb_gather_rows_peers(const void* const* shard_ptrs, const int64_t* starts, int n_shards, const int64_t* idx,
+                                    void* out, int64_t n_idx, int d, int dtype, rb_stream_t stream) {
+  RB_RANGE("rb_gather_rows_peers");
+  DevInfo dv; if (int r = get_dev(dv)) return r;
+  if (!shard_ptrs || !starts || !idx || !out) return fail(RB_E_ARG, "null pointer");
+  if (n_shards < 1 || n_shards > PEER_MAX_SHARDS) return fail(RB_E_ARG, "1 <= n_shards <= %d (got %d)", PEER_MAX_SHARDS, n_shards);
+  if (n_idx < 0 || d <= 0) return fail(RB_E_ARG, "bad shape");
+  const int es = dtype == RB_DTYPE_BF16 ? 2 : 4;
+  const long long row_bytes = 1ll * d * es;
+  if (row_bytes % 16) return fail(RB_E_ALIGN, "row of %lld bytes is not a multiple of 16", row_bytes);
+  PeerShards sh{};
+  sh.n = n_shards;
+  for (int r = 0; r < n_shards; ++r) {
+    if (!shard_ptrs[r] || (reinterpret_cast<uintptr_t>(shard_ptrs[r]) & 15)) return fail(RB_E_ALIGN, "shard %d: null or not 16-byte aligned", r);
+    if (starts[r + 1] < starts[r]) return fail(RB_E_ARG, "shard starts must be non-decreasing");
+    sh.base[r] = static_cast<const uint4*>(shard_ptrs[r]);
+    sh.start[r] = starts[r];
+  }
+  sh.start[n_shards] = starts[n_shards];
+  if (reinterpret_cast<uintptr_t>(out) & 15) return fail(RB_E_ALIGN, "out must be 16-byte aligned");
+  if (n_idx == 0) return 0;
+  const int vpr = static_cast<int>(row_bytes / 16);
+  const long long total = n_idx * vpr;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 1ll * dv.sms * 8));
+  gather_rows_peers_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(sh, idx, static_cast<uint4*>(out), n_idx, vpr);
+  RB_LAUNCH_CHECK("gather_rows_peers_kernel");
+  return 0;
+}
+
 // ================================================================== row compaction
 extern "C" int rb_compact_index(const void* mask, int64_t n, int64_t* row_index, int32_t* count, rb_stream_t stream) {
   RB_RANGE("rb_compact_index");

@@ -39,6 +39,42 @@ __global__ void gather_rows_kernel(const uint4* __restrict__ table, const int64_
   }
 }
 
+// The same gather over a ROW-SHARDED table whose shards live on the GPUs of one box (input side):
+// shard r holds the rows of global ids [starts[r], starts[r+1]) at shards[r] (the local shard, or a peer's mapped
+// through CUDA IPC -- the loads then travel over NVLink).  Every rank reads the rows where they live: no collective,
+// no replicated copy of the table.  Ids outside [starts[0], starts[n_shards]) (the padding id) give zero rows.
+constexpr int PEER_MAX_SHARDS = 16;
+struct PeerShards {
+  const uint4* base[PEER_MAX_SHARDS];
+  long long start[PEER_MAX_SHARDS + 1];
+  int n;
+};
+__global__ void gather_rows_peers_kernel(const PeerShards sh, const int64_t* __restrict__ idx, uint4* __restrict__ out,
+                                         long long n_idx, int vpr) {
+  const long long total = n_idx * vpr;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  auto fetch = [&](long long tt) -> uint4 {
+    const long long row = tt / vpr;
+    const int c = static_cast<int>(tt - row * vpr);
+    const long long id = __ldg(idx + row);
+    if (id < sh.start[0] || id >= sh.start[sh.n]) return make_uint4(0, 0, 0, 0);
+    int r = 0;
+#pragma unroll
+    for (int k = 1; k < PEER_MAX_SHARDS; ++k) r += (k < sh.n && id >= sh.start[k]) ? 1 : 0;
+    // plain (coherent) loads: a peer's rows are not read-only for the lifetime of the kernel's module
+    return *(sh.base[r] + (id - sh.start[r]) * vpr + c);
+  };
+  long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; t + 7 * stride < total; t += 8 * stride) {   // 8 loads in flight per thread: NVLink latency is ~2x HBM's
+    uint4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = fetch(t + u * stride);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) out[t + u * stride] = v[u];
+  }
+  for (; t < total; t += stride) out[t] = fetch(t);
+}
+
 // --------------------------------------------------------------------------- normalise
 // out[i,:] = x[i,:] / max(||x[i,:]||_2, eps)  (reference: F.normalize(weight[1:], dim=-1) and the user
 // side, HSTU/main.py:180-184; run once per evaluation sweep instead of once per batch).  One warp per

@@ -92,6 +92,28 @@ check("sharded gather backward shard", Wg.grad, ref_gW[lo:hi].to(dev), 2.0 ** -8
 if rank == 0:
     print(f"[rank 0] sharded gather forward bit-exact: {bool(torch.equal(emb.float().cpu(), ref_emb))}", flush=True)
 
+# the same through peer memory (CUDA IPC over NVLink): every rank reads the rows where they live, no collective; the
+# shard is the rank's whole parameter (one pad row in front), the gradient is added into its existing buffer
+Wq = torch.cat([torch.zeros(1, d, dtype=torch.bfloat16, device=dev), W[lo:hi]]).requires_grad_(True)
+Wq.grad = torch.zeros_like(Wq)
+peers = sharded.PeerTable(Wq, lo, n_skip=1)
+emb_p = peers.gather(seqs - 1, padding_idx=-1, accumulate=True)
+emb_p.backward(gout)
+ok_fwd = bool(torch.equal(emb_p.float().cpu(), ref_emb))
+ok &= ok_fwd
+check("peer-memory gather backward shard", Wq.grad[1:], ref_gW[lo:hi].to(dev), 2.0 ** -8)
+ok &= bool((Wq.grad[0] == 0).all())
+with torch.no_grad():      # an owner's update becomes visible to its peers after fence()
+    Wq[1:] += 1.0
+peers.fence()
+emb_p2 = peers.gather(seqs - 1)
+ref2 = orc.gather_rows(torch.cat([torch.zeros(1, d), (W.float() + 1.0).bfloat16().float().cpu()]), seqs.cpu())
+ok_upd = bool(torch.equal(emb_p2.float().cpu(), ref2))
+ok &= ok_upd
+peers.close()
+if rank == 0:
+    print(f"[rank 0] peer-memory gather forward bit-exact: {ok_fwd}; after an owner-side update + fence: {ok_upd}", flush=True)
+
 # ---- BERT4Rec-style bias head (config 5 shape scaled down): bias shard + dbias shard
 ref_lb, ref_dUb, ref_dWb, ref_db = from_rank0(lambda: oracle_ce(True), [((1,), torch.float32), ((M, d), torch.float32),
                                                                          ((N, d), torch.float32), ((N,), torch.float32)])
