@@ -160,12 +160,11 @@ def strong_scaling(dev: torch.device, world: int, rank: int, n_total: int = 10_0
     out = {"n_items_total": n_total, "rows": rows, "n_gpus": world}
     # (i) CE train
     table = synth.embeddings(n_shard, 128, g, dev, torch.bfloat16, gain=1.5).requires_grad_(True)
-    table.grad = torch.zeros_like(table)
     U = synth.embeddings(rows, 128, gq, dev, torch.bfloat16, gain=1.5)
     labels = synth.zipf_ids(rows, n_total, gq, dev)
 
     def train():
-        table.grad.zero_()
+        table.grad = None                      # optimizer.zero_grad(): the dW pass writes the new gradient buffer
         Uq = U.detach().requires_grad_(True)
         if world > 1:
             loss = sharded.sharded_fused_ce(Uq, table, labels, a, accumulate=True)
