@@ -30,9 +30,19 @@ def _mode_for(U: torch.Tensor, precision: Optional[str]) -> str:
     return precision
 
 
+def _pad_cols(x: torch.Tensor, mult: int = 8) -> torch.Tensor:
+    """Zero columns up to a multiple of ``mult``: the kernels move rows as 16-byte vectors (TMA rows, 128-bit loads), and
+    zero columns change no dot product or norm.  For embedding widths like HSTU's 50
+    (HSTU/configs/MovieLens1M_500_LOU.yaml) this costs a padded copy of the operand per call; differentiable
+    (autograd slices the gradient back)."""
+    r = x.shape[-1] % mult
+    return x if r == 0 else torch.nn.functional.pad(x, (0, mult - r))
+
+
 def _prep(U, W, precision):
-    """Cast operands to the storage type the chosen arithmetic mode needs."""
+    """Cast operands to the storage type the chosen arithmetic mode needs (rows padded to whole 16-byte vectors)."""
     precision = _mode_for(U, precision)
+    U, W = _pad_cols(U), _pad_cols(W)
     if precision == "bf16":
         return U.to(torch.bfloat16).contiguous(), W.to(torch.bfloat16).contiguous(), L.MODE_BF16
     return U.float().contiguous(), W.float().contiguous(), L.MODE_FP32X3
@@ -187,6 +197,8 @@ def gather_dot(U: torch.Tensor, table: torch.Tensor, idx: torch.Tensor, scale: f
     """``torch.einsum("MD,MKD->MK", U, table[idx]) * scale`` -> fp32 (M,K) without the (M,K,D) gather
     (recommend_from_pool SASRec/main.py:230-236; sampled softmax HSTU/main.py:192-197; BPR/BCE logits
     SASRec/main.py:203-206).  Differentiable w.r.t. ``U`` and ``table`` (dense, deterministic)."""
+    if U.shape[-1] % 8:
+        U, table = _pad_cols(U), _pad_cols(table)
     return _GatherDot.apply(U, table, idx, scale, padding_idx)
 
 
@@ -249,7 +261,8 @@ def normalize_rows(x: torch.Tensor, out_dtype: Optional[torch.dtype] = None, eps
     xc = x.detach()
     if xc.dtype not in (torch.float32, torch.bfloat16):
         xc = xc.float()
-    xc = xc.contiguous()
+    d_true = xc.shape[1]
+    xc = _pad_cols(xc).contiguous()
     out_dtype = out_dtype or xc.dtype
     if out_dtype not in (torch.float32, torch.bfloat16):
         raise TypeError("out_dtype must be float32 or bfloat16")
@@ -258,6 +271,8 @@ def normalize_rows(x: torch.Tensor, out_dtype: Optional[torch.dtype] = None, eps
     inv = torch.empty(n, dtype=torch.float32, device=dev) if return_inv_norm else None
     L.call(dev, "rb_normalize_rows", L.ptr(xc), L.ptr(out), L.ptr(inv), n, d, L.dtype_code(xc), L.dtype_code(out),
                                   float(eps), L.stream_ptr(dev))
+    if d != d_true:
+        out = out[:, :d_true].contiguous()
     return (out, inv) if return_inv_norm else out
 
 
@@ -350,6 +365,13 @@ def ce_backward(U, W, labels, lse, grad_scale: float, bias=None, scale: float = 
     dev = L.require_cuda(U, W, labels, lse, bias, grad_scale_dev)
     if grad_scale_dev is not None and (grad_scale_dev.dtype != torch.float32 or grad_scale_dev.numel() != 1):
         raise TypeError("grad_scale_dev must be a float32 scalar tensor")
+    if U.shape[1] % 8:   # rows are not whole 16-byte vectors: run on zero-padded copies, hand back the true columns
+        if dw_out is not None:
+            raise TypeError("dw_out needs an embedding width that is a multiple of 8")
+        d0 = U.shape[1]
+        dU, dW, db = ce_backward(_pad_cols(U.detach()), _pad_cols(W.detach()), labels, lse, grad_scale, bias, scale, label_base,
+                                 need_dU, need_dW, need_dbias, precision, grad_scale_dev, dw_dtype, None, False, n_valid)
+        return (dU[:, :d0].contiguous() if dU is not None else None, dW[:, :d0].contiguous() if dW is not None else None, db)
     Uc, Wc, mode = _prep(U.detach(), W.detach(), precision)
     M, d = Uc.shape
     N = Wc.shape[0]
@@ -529,6 +551,8 @@ def fused_ce(U: torch.Tensor, W: torch.Tensor, labels: torch.Tensor, bias: Optio
         return zero / 0 if reduction == "mean" else zero
     if n_skip and bias is not None:
         raise ValueError("n_skip is for bias-free embedding tables (a bias head scores every row of its weight)")
+    if U.shape[1] % 8:   # e.g. d = 50: zero columns (a padded copy per call; the in-place gradient routes do not apply)
+        U, W = _pad_cols(U), _pad_cols(W)
     return _FusedCE.apply(U, W, labels, bias, float(scale), precision, reduction, int(n_skip), bool(accumulate), n_valid)
 
 

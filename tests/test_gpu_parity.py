@@ -208,6 +208,41 @@ def test_ce_gradients_bf16(ops, M, N, d):
     assert_grad_bf16(Wd.grad, rdW, "dW")
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_embedding_width_not_a_multiple_of_8(ops, precision):
+    """d = 50 (HSTU/configs/MovieLens1M_500_LOU.yaml): the host layer zero-pads the columns; scores, CE loss and
+    gradients (true width), masked top-K, cosine normalisation and pool scores against the oracle."""
+    g = torch.Generator().manual_seed(50)
+    M, N, d, K = 130, 3706, 50, 20
+    U, W = torch.randn(M, d, generator=g) * 0.4, torch.randn(N, d, generator=g) * 0.4
+    if precision == "bf16":
+        U, W = bf16_round(U), bf16_round(W)
+    lab = torch.randint(0, N, (M,), generator=g)
+    cast = (lambda x: dev(x).bfloat16()) if precision == "bf16" else dev
+    rtol = FP32_RTOL if precision == "fp32" else 1e-5
+    assert_rel(ops.score_dense(cast(U), cast(W), precision=precision), orc.score_dense(U, W), rtol, "scores")
+    ref_loss, rdU, rdW, _ = orc.ce_fwd_bwd(U, W, lab)
+    Ud, Wd = cast(U).requires_grad_(True), cast(W).requires_grad_(True)
+    loss = ops.fused_ce(Ud, Wd, dev(lab), precision=precision)
+    loss.backward()
+    assert Ud.grad.shape == (M, d) and Wd.grad.shape == (N, d)
+    assert abs(float(loss) - float(ref_loss)) <= rtol * abs(float(ref_loss))
+    if precision == "fp32":
+        assert_rel(Ud.grad, rdU, 2e-5, "dU"); assert_rel(Wd.grad, rdW, 2e-5, "dW")
+    else:
+        assert_grad_bf16(Ud.grad, rdU, "dU"); assert_grad_bf16(Wd.grad, rdW, "dW")
+    seen = _seen_lists(g, M, N, 30)
+    crow, col = MX.lists_to_csr(seen)
+    vals, ids = ops.topk_eval(cast(U), cast(W), K, dev(crow), dev(col), precision=precision)
+    _check_topk(vals, ids, orc.mask_seen(orc.score_dense(U, W), crow, col), K, 1e-5 if precision == "fp32" else 2e-5)
+    Wn = ops.normalize_rows(dev(W))
+    assert Wn.shape == (N, d)
+    assert_rel(Wn, torch.nn.functional.normalize(W, dim=-1), 1e-6, "normalised rows")
+    idx = torch.randint(0, N, (M, 7), generator=g)
+    S = ops.gather_dot(cast(U), cast(W), dev(idx))
+    assert_rel(S, torch.einsum("md,mkd->mk", U, W[idx]), rtol, "pool scores")
+
+
 @pytest.mark.parametrize("M,N,d", [(700, 5000, 256), (257, 1300, 200)])
 def test_ce_bias_head_wide_rows(ops, M, N, d):
     """128 < d <= 256 (CCFRec / E4SRec-style heads, config-4-shaped training): the d-split fused passes with bias and a
