@@ -206,7 +206,11 @@ def run_ours(args):
     W = table.detach()[1:]                                            # the scored view weight[NUM_PADS:] (:193)
     peers = None
     if world > 1 and os.environ.get("RB_BENCH_GATHER", "peer") == "peer":
-        peers = sharded.PeerTable(table, row_start, n_skip=1)
+        try:
+            peers = sharded.PeerTable(table, row_start, n_skip=1)
+        except RuntimeError as e:   # raised on ALL ranks together; the collective-only gather (also CUDA + NCCL) takes over
+            if rank == 0:
+                print(f"bench: peer-memory gather unavailable, using the all-reduce variant: {e}", file=sys.stderr)
     # ---- one batch of inputs (identical on every rank: queries are replicated)
     g = torch.Generator(device=dev).manual_seed(2026 + 3)
     U_train = synth.embeddings(ROWS, D, g, dev, torch.bfloat16, gain=1.5)

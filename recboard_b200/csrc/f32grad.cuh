@@ -84,13 +84,16 @@ __global__ void __launch_bounds__(F32G_THREADS, 2) ce_grad_f32_kernel(const F32G
     sa[i] = (a.stat_vec != nullptr && r < a.n_stat) ? a.stat_mul * 1.4426950408889634f * __ldg(a.stat_vec + r) : 0.f;
   }
 
-  float acc[4][NG][4];
+  // Packed fp32 arithmetic (fma.rn.f32x2): a three-register FFMA issues every second cycle per scheduler on this
+  // architecture, the packed form does two FMAs in the same slot.  Accumulators are register PAIRS: output columns
+  // (c, c+1) here, the even-k / odd-k partial sums of a score below.
+  uint64_t acc2[4][NG][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int g = 0; g < NG; ++g)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) acc[i][g][e] = 0.f;
+      for (int e = 0; e < 2; ++e) acc2[i][g][e] = 0ull;
   float rs[4] = {0.f, 0.f, 0.f, 0.f};
 
   for (int t = t0; t < t1; ++t) {
@@ -111,28 +114,35 @@ __global__ void __launch_bounds__(F32G_THREADS, 2) ce_grad_f32_kernel(const F32G
     __syncthreads();
 
     // ---- S = X Y^T : rows ty*4+i, columns tx+16j
-    float s[4][4];
+    uint64_t s2[4][4];   // (sum over even k, sum over odd k)
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+      for (int j = 0; j < 4; ++j) s2[i][j] = 0ull;
 #pragma unroll 4
     for (int k = 0; k < DP; k += 4) {
-      float4 xv[4], yv[4];
+      ulonglong2 xv[4], yv[4];   // four consecutive k as two packed pairs: operands come paired straight from the loads
 #pragma unroll
-      for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(Xs + (ty * 4 + i) * C::LDX + k);
+      for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const ulonglong2*>(Xs + (ty * 4 + i) * C::LDX + k);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) yv[j] = *reinterpret_cast<const float4*>(Ys + (tx + 16 * j) * C::LDX + k);
+      for (int j = 0; j < 4; ++j) yv[j] = *reinterpret_cast<const ulonglong2*>(Ys + (tx + 16 * j) * C::LDX + k);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          s[i][j] = fmaf(xv[i].x, yv[j].x, s[i][j]);
-          s[i][j] = fmaf(xv[i].y, yv[j].y, s[i][j]);
-          s[i][j] = fmaf(xv[i].z, yv[j].z, s[i][j]);
-          s[i][j] = fmaf(xv[i].w, yv[j].w, s[i][j]);
+          s2[i][j] = ffma2(xv[i].x, yv[j].x, s2[i][j]);
+          s2[i][j] = ffma2(xv[i].y, yv[j].y, s2[i][j]);
         }
     }
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float e, o;
+        unpack2(s2[i][j], e, o);
+        s[i][j] = e + o;
+      }
     // ---- P tile
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -152,16 +162,19 @@ __global__ void __launch_bounds__(F32G_THREADS, 2) ce_grad_f32_kernel(const F32G
       for (int i = 0; i < 4; ++i) pv[i] = *reinterpret_cast<const float4*>(Ps + (ty * 4 + i) * C::LDP + jj);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
+        uint64_t pp[4];   // (p, p) per row
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float p = (u == 0) ? pv[i].x : (u == 1) ? pv[i].y : (u == 2) ? pv[i].z : pv[i].w;
+          pp[i] = pack2(p, p);
+        }
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
-          const float4 yv = *reinterpret_cast<const float4*>(Ys + (jj + u) * C::LDX + tx * 4 + 64 * g);
+          const ulonglong2 yv = *reinterpret_cast<const ulonglong2*>(Ys + (jj + u) * C::LDX + tx * 4 + 64 * g);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float p = (u == 0) ? pv[i].x : (u == 1) ? pv[i].y : (u == 2) ? pv[i].z : pv[i].w;
-            acc[i][g][0] = fmaf(p, yv.x, acc[i][g][0]);
-            acc[i][g][1] = fmaf(p, yv.y, acc[i][g][1]);
-            acc[i][g][2] = fmaf(p, yv.z, acc[i][g][2]);
-            acc[i][g][3] = fmaf(p, yv.w, acc[i][g][3]);
+            acc2[i][g][0] = ffma2(pp[i], yv.x, acc2[i][g][0]);
+            acc2[i][g][1] = ffma2(pp[i], yv.y, acc2[i][g][1]);
           }
         }
       }
@@ -178,9 +191,10 @@ __global__ void __launch_bounds__(F32G_THREADS, 2) ce_grad_f32_kernel(const F32G
 #pragma unroll
       for (int g = 0; g < NG; ++g) {
         const int c = tx * 4 + 64 * g;
-        if (c < a.d)
-          *reinterpret_cast<float4*>(o + c) =
-              make_float4(acc[i][g][0] * osc, acc[i][g][1] * osc, acc[i][g][2] * osc, acc[i][g][3] * osc);
+        float v0, v1, v2, v3;
+        unpack2(acc2[i][g][0], v0, v1);
+        unpack2(acc2[i][g][1], v2, v3);
+        if (c < a.d) *reinterpret_cast<float4*>(o + c) = make_float4(v0 * osc, v1 * osc, v2 * osc, v3 * osc);
       }
     }
   }

@@ -7,6 +7,9 @@
 #include "sweep.cuh"
 #include "pair.cuh"
 
+#ifndef RB_LSE_NWG
+#define RB_LSE_NWG 4   // epilogue warpgroups of the statistics sweep with two stationary tiles (2 or 4; sweep.cuh)
+#endif
 namespace rb {
 
 constexpr int BN = 128;  // streamed tile rows
@@ -41,7 +44,7 @@ int launch_sweep(int mode, int kc, const CUtensorMap& ts, const CUtensorMap& ty,
   if (xt == 2) {
     if constexpr (EPI != EPI_DENSE) {
       // the top-K sweeps are bound by their epilogue's own instruction stream: four epilogue warpgroups (one per S buffer)
-      constexpr int NWG = (EPI == EPI_CAND || EPI == EPI_TOPK) ? 4 : 2;
+      constexpr int NWG = (EPI == EPI_CAND || EPI == EPI_TOPK || (EPI == EPI_LSE && RB_LSE_NWG == 4)) ? 4 : 2;
       if (mode == RB_MODE_BF16) {
         if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 1, BN, 10, ROWS, 2, NWG>>(ts, ty, a, grid, st);
         if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 2, BN, 4, ROWS, 2, NWG>>(ts, ty, a, grid, st);

@@ -140,7 +140,7 @@ struct Control {
   uint64_t s_full[4], s_empty[4];
   uint32_t tmem_base;
   uint32_t pad_;
-  float xchg[3][128];  // warpgroup 1 -> warpgroup 0 hand-over of per-row partials
+  float xchg[2][3][128];  // [stationary tile][m2, l, ll][row]: hand-over of per-row partials between the two parities' warpgroups
 };
 static_assert(sizeof(Control) <= 4096, "control block");
 
@@ -165,8 +165,8 @@ __device__ __forceinline__ void group_max8(const uint32_t (&r)[32], float (&m)[4
   }
 }
 
-// named barrier over the 256 epilogue threads (id 1; id 0 is __syncthreads)
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// named barrier over the 256 epilogue threads that share a stationary tile (ids 1, 2; id 0 is __syncthreads)
+__device__ __forceinline__ void epi_bar_sync(int xsel = 0) { asm volatile("bar.sync %0, 256;" ::"r"(xsel + 1) : "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 template <class C>
@@ -621,17 +621,18 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
         if (n1 != 0u) atomicAdd(ld->cnt + lvl + 1, n1);   // leftovers still help the row's other splits
         if (n2 != 0u && lvl + 2 <= 7) atomicAdd(ld->cnt + lvl + 2, n2);
       }
-      if (C::EPI == EPI_LSE && C::XT == 2) {  // each warpgroup owns its rows: no hand-over
+      if (C::EPI == EPI_LSE && C::XT == 2 && C::NWG == 2) {  // each warpgroup owns its rows: no hand-over
         a.part_m2[pslot] = m2;
         a.part_l[pslot] = l;
         a.part_ll[pslot] = ll;
       }
-      if (C::EPI == EPI_LSE && C::XT == 1) {
-        // warpgroup 1 hands its partial to warpgroup 0, which merges and writes one slot per row
-        if (par == 1) { bar->xchg[0][r] = m2; bar->xchg[1][r] = l; bar->xchg[2][r] = ll; }
-        epi_bar_sync();
+      if (C::EPI == EPI_LSE && (C::XT == 1 || C::NWG == 4)) {
+        // the odd-parity warpgroup hands its partial to the even-parity one of the same stationary tile, which merges
+        // and writes one slot per row
+        if (par == 1) { bar->xchg[xsel][0][r] = m2; bar->xchg[xsel][1][r] = l; bar->xchg[xsel][2][r] = ll; }
+        epi_bar_sync(xsel);
         if (par == 0) {
-          const float om = bar->xchg[0][r], ol = bar->xchg[1][r], oll = bar->xchg[2][r];
+          const float om = bar->xchg[xsel][0][r], ol = bar->xchg[xsel][1][r], oll = bar->xchg[xsel][2][r];
           const float mm = fmaxf(m2, om);
           float lm = 0.f;
           if (mm > -INFINITY) lm = l * ex2_approx(m2 - mm) + ol * ex2_approx(om - mm);
@@ -639,7 +640,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
           a.part_l[pslot] = lm;
           a.part_ll[pslot] = ll + oll;
         }
-        epi_bar_sync();  // xchg is free again before the next item
+        epi_bar_sync(xsel);  // xchg is free again before the next item
       }
     }  // items
   }

@@ -206,29 +206,49 @@ class PeerTable:
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         body = table_shard.detach()[n_skip:]
         self.n_rows, self.d, self.dtype = body.shape[0], body.shape[1], body.dtype
-        handle = C.create_string_buffer(64)
-        off = C.c_int64(0)
-        L.call(dev, "rb_ipc_export", L.ptr(body), C.cast(handle, C.c_void_p), C.cast(C.pointer(off), C.c_void_p))
-        mine = (bytes(handle.raw), int(off.value), self.row_start, self.n_rows, self.d, str(self.dtype))
+        # Every rank takes part in both collectives whatever happens locally, and all ranks fail together: a mapping
+        # that works on some ranks only would leave the others hanging in the next collective.
+        mine, err = None, None
+        try:
+            handle = C.create_string_buffer(64)
+            off = C.c_int64(0)
+            L.call(dev, "rb_ipc_export", L.ptr(body), C.cast(handle, C.c_void_p), C.cast(C.pointer(off), C.c_void_p))
+            mine = (bytes(handle.raw), int(off.value), self.row_start, self.n_rows, self.d, str(self.dtype))
+        except RuntimeError as e:   # e.g. memory that CUDA IPC cannot export
+            err = f"rank {self.rank}: {e}"
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine, group=group)
         self._bases, ptrs, starts = [], [], []
-        for r, (h, o, rs, nr, d, dt) in enumerate(everyone):
-            if d != self.d or dt != str(self.dtype):
-                raise ValueError(f"rank {r} holds a ({nr},{d}) {dt} shard, this rank ({self.n_rows},{self.d}) {self.dtype}")
-            if starts and rs != starts[-1] + everyone[r - 1][3]:
-                raise ValueError("the ranks' row ranges must tile one interval in rank order")
-            starts.append(rs)
-            if r == self.rank:
-                ptrs.append(body.data_ptr())
-                continue
-            p_out, b_out = C.c_void_p(0), C.c_void_p(0)
-            hb = C.create_string_buffer(h, 64)
-            L.call(dev, "rb_ipc_open", C.cast(hb, C.c_void_p), o, C.cast(C.pointer(p_out), C.c_void_p),
-                   C.cast(C.pointer(b_out), C.c_void_p))
-            self._bases.append(b_out.value)
-            ptrs.append(p_out.value)
-        starts.append(starts[-1] + everyone[-1][3])
+        if err is None and any(e is None for e in everyone):
+            err = "a peer could not export its shard"
+        if err is None:
+            try:
+                for r, (h, o, rs, nr, d, dt) in enumerate(everyone):
+                    if d != self.d or dt != str(self.dtype):
+                        raise ValueError(f"rank {r} holds a ({nr},{d}) {dt} shard, this rank ({self.n_rows},{self.d}) {self.dtype}")
+                    if starts and rs != starts[-1] + everyone[r - 1][3]:
+                        raise ValueError("the ranks' row ranges must tile one interval in rank order")
+                    starts.append(rs)
+                    if r == self.rank:
+                        ptrs.append(body.data_ptr())
+                        continue
+                    p_out, b_out = C.c_void_p(0), C.c_void_p(0)
+                    hb = C.create_string_buffer(h, 64)
+                    L.call(dev, "rb_ipc_open", C.cast(hb, C.c_void_p), o, C.cast(C.pointer(p_out), C.c_void_p),
+                           C.cast(C.pointer(b_out), C.c_void_p))
+                    self._bases.append(b_out.value)
+                    ptrs.append(p_out.value)
+                starts.append(starts[-1] + everyone[-1][3])
+            except (RuntimeError, ValueError) as e:
+                err = f"rank {self.rank}: {e}"
+        ok = torch.tensor([0.0 if err else 1.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if float(ok) == 0.0:
+            for b_ in self._bases:
+                L.call(dev, "rb_ipc_close", b_)
+            self._bases = []
+            raise RuntimeError("PeerTable: the shards could not be mapped on every rank"
+                               + (f" ({err})" if err else " (another rank failed)"))
         self._ptrs = (C.c_void_p * self.world)(*ptrs)
         self._starts = (C.c_int64 * (self.world + 1))(*starts)
         self.first_id, self.end_id = starts[0], starts[-1]

@@ -15,4 +15,12 @@ for _ in range(3):
     U.grad = None; W.grad = None
     ops.fused_ce(U, W, labels, precision="fp32").backward()
 torch.cuda.synchronize()
+if "--time" in sys.argv:
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(50):
+        U.grad = None; W.grad = None
+        ops.fused_ce(U, W, labels, precision="fp32").backward()
+    b.record(); torch.cuda.synchronize()
+    print(f"config-1 fused fp32 train step: {a.elapsed_time(b) / 50:.4f} ms")
 print("done")
