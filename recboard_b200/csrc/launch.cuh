@@ -46,6 +46,11 @@ int launch_sweep(int mode, int kc, const CUtensorMap& ts, const CUtensorMap& ty,
       // the top-K sweeps are bound by their epilogue's own instruction stream: four epilogue warpgroups (one per S buffer)
       constexpr int NWG = (EPI == EPI_CAND || EPI == EPI_TOPK || (EPI == EPI_LSE && RB_LSE_NWG == 4)) ? 4 : 2;
       if (mode == RB_MODE_BF16) {
+        if (a.bias == nullptr) {   // the bias branches compiled out (SweepCfg::MAYBE_BIAS)
+          if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 1, BN, 10, ROWS, 2, NWG, false>>(ts, ty, a, grid, st);
+          if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 2, BN, 4, ROWS, 2, NWG, false>>(ts, ty, a, grid, st);
+          if (kc <= 4) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 4, BN, 5, ROWS, 2, NWG, false>>(ts, ty, a, grid, st);
+        }
         if (kc == 1) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 1, BN, 10, ROWS, 2, NWG>>(ts, ty, a, grid, st);
         if (kc == 2) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 2, BN, 4, ROWS, 2, NWG>>(ts, ty, a, grid, st);
         if (kc <= 4) return launch_sweep_t<SweepCfg<EPI, DT_BF16, 4, BN, 5, ROWS, 2, NWG>>(ts, ty, a, grid, st);

@@ -99,9 +99,12 @@ __device__ __forceinline__ float logit_of(uint32_t raw, float scale, const float
   return __fmul_rn(__uint_as_float(raw), scale);  // explicit roundings: no contraction differences between call sites
 }
 
-template <int EPI_, int DT_, int KC_, int BN_, int NS_, bool STAT_ROWS_, int XT_ = 1, int NWG_ = 2>
+template <int EPI_, int DT_, int KC_, int BN_, int NS_, bool STAT_ROWS_, int XT_ = 1, int NWG_ = 2, bool MAYBE_BIAS_ = true>
 struct SweepCfg {
   static constexpr int EPI = EPI_, DT = DT_, KC = KC_, BN = BN_, NS = NS_, XT = XT_;
+  // false: the launch has no bias vector -- the bias branches of the epilogues are compiled out, so that the hot
+  // bias-free kernels (96 registers per thread with four warpgroups) do not pay registers or spills for them
+  static constexpr bool MAYBE_BIAS = MAYBE_BIAS_;
   // Epilogue warpgroups.  2: XT = 1 -> one per tile parity, XT = 2 -> one per stationary tile (both of its S buffers).
   // 4 (XT = 2 only): two per stationary tile, one per tile parity, i.e. one warpgroup per S buffer -- twice the issue
   // slots and latency tolerance for epilogues that are bound by their own instruction stream (the top-K sweeps).
@@ -325,7 +328,11 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
     const int r = q * 32 + lane;       // stationary row within the tile == TMEM lane
     const uint32_t t_lane0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float c2 = a.scale * LOG2E;
-    const bool plain = (a.bias == nullptr) && (c2 > 0.f);  // fast paths: no bias, positive scale
+    const float* const bias = C::MAYBE_BIAS ? a.bias : nullptr;
+    const bool plain = (bias == nullptr) && (c2 > 0.f);  // fast paths: no bias, positive scale
+    // bias head (BERT4Rec/main.py:83): the 32 biases of a full chunk come as eight 16-byte loads (the address is the same
+    // for every row of the warp) when the vector is 16-byte aligned; element by element otherwise
+    const bool bias_vec = (bias != nullptr) && ((reinterpret_cast<uintptr_t>(bias) & 15) == 0);
     constexpr int NCH = C::BN / 32;
     uint32_t it = 0, k = 0;
 
@@ -450,7 +457,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
           if (C::EPI == EPI_DENSE) {
             if (srow_ok && nv > 0) {
               float* o = a.out + static_cast<long long>(srow) * a.ld_out + col_base + c0;
-              if (a.bias == nullptr && nv >= 32) {
+              if (bias == nullptr && nv >= 32) {
 #pragma unroll
                 for (int c = 0; c < 32; ++c) o[c] = __uint_as_float(v[c]) * a.scale;
               } else {
@@ -458,7 +465,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
                 for (int c = 0; c < 32; ++c) {
                   if (c < nv) {
                     float s = __uint_as_float(v[c]) * a.scale;
-                    if (a.bias != nullptr) s += __ldg(a.bias + col_base + c0 + c);
+                    if (bias != nullptr) s += __ldg(bias + col_base + c0 + c);
                     o[c] = s;
                   }
                 }
@@ -510,13 +517,26 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
             } else if (nv > 0) {
               float x[32];
               float cmax = -INFINITY;
+              if (bias_vec && nv >= 32) {
+                const float4* bp = reinterpret_cast<const float4*>(bias + col_base + c0);
 #pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                float b2 = 0.f;
-                if (a.bias != nullptr) b2 = (c < nv) ? __ldg(a.bias + col_base + c0 + c) * LOG2E : 0.f;
-                x[c] = fmaf(__uint_as_float(v[c]), c2, b2);
-                if (c >= nv) x[c] = -INFINITY;
-                cmax = fmaxf(cmax, x[c]);
+                for (int g = 0; g < 8; ++g) {
+                  const float4 b = __ldg(bp + g);
+                  x[4 * g + 0] = fmaf(__uint_as_float(v[4 * g + 0]), c2, b.x * LOG2E);
+                  x[4 * g + 1] = fmaf(__uint_as_float(v[4 * g + 1]), c2, b.y * LOG2E);
+                  x[4 * g + 2] = fmaf(__uint_as_float(v[4 * g + 2]), c2, b.z * LOG2E);
+                  x[4 * g + 3] = fmaf(__uint_as_float(v[4 * g + 3]), c2, b.w * LOG2E);
+                  cmax = fmaxf(cmax, fmaxf(fmaxf(x[4 * g], x[4 * g + 1]), fmaxf(x[4 * g + 2], x[4 * g + 3])));
+                }
+              } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                  float b2 = 0.f;
+                  if (bias != nullptr) b2 = (c < nv) ? __ldg(bias + col_base + c0 + c) * LOG2E : 0.f;
+                  x[c] = fmaf(__uint_as_float(v[c]), c2, b2);
+                  if (c >= nv) x[c] = -INFINITY;
+                  cmax = fmaxf(cmax, x[c]);
+                }
               }
               const float m_new = fmaxf(m2, cmax);
               float acc = 0.f;
@@ -533,11 +553,21 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
           } else if (C::EPI == EPI_TOPK) {
             if (tile_quick) {
               tmax = fmaxf(tmax, max32(v));  // raw scores; scaled once per tile (scale > 0)
+            } else if (bias_vec && nv >= 32) {  // bias head, full chunk: the same logits as logit_of, biases in vectors
+              const float4* bp = reinterpret_cast<const float4*>(bias + col_base + c0);
+              float cm = -INFINITY;
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 b = __ldg(bp + g);
+                cm = fmaxf(cm, fmaxf(fmaxf(__fmaf_rn(__uint_as_float(v[4 * g]), a.scale, b.x), __fmaf_rn(__uint_as_float(v[4 * g + 1]), a.scale, b.y)),
+                                     fmaxf(__fmaf_rn(__uint_as_float(v[4 * g + 2]), a.scale, b.z), __fmaf_rn(__uint_as_float(v[4 * g + 3]), a.scale, b.w))));
+              }
+              tmax = fmaxf(tmax, cm);
             } else if (nv > 0) {  // bias and/or the last, partial tile
               float cm = -INFINITY;
 #pragma unroll
               for (int c = 0; c < 32; ++c)
-                if (c < nv) cm = fmaxf(cm, logit_of(v[c], a.scale, a.bias, col_base + c0 + c));
+                if (c < nv) cm = fmaxf(cm, logit_of(v[c], a.scale, bias, col_base + c0 + c));
               tmax = fmaxf(tmax, cm);
             }
           } else if (C::EPI == EPI_CAND) {
@@ -550,13 +580,21 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
               for (int g = 0; g < 8; ++g)
                 m8[g] = fmaxf(fmax3(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2])),
                               __uint_as_float(v[4 * g + 3]));
+            } else if (bias_vec && nv >= 32) {  // bias head, full chunk: the same logits as logit_of, biases in vectors
+              const float4* bp = reinterpret_cast<const float4*>(bias + col_base + c0);
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 b = __ldg(bp + g);
+                m8[g] = fmaxf(fmaxf(__fmaf_rn(__uint_as_float(v[4 * g]), a.scale, b.x), __fmaf_rn(__uint_as_float(v[4 * g + 1]), a.scale, b.y)),
+                              fmaxf(__fmaf_rn(__uint_as_float(v[4 * g + 2]), a.scale, b.z), __fmaf_rn(__uint_as_float(v[4 * g + 3]), a.scale, b.w)));
+              }
             } else {  // bias and/or the last, partial tile: finished logits
 #pragma unroll
               for (int g = 0; g < 8; ++g) {
                 m8[g] = -INFINITY;
 #pragma unroll
                 for (int c = 4 * g; c < 4 * g + 4; ++c)
-                  if (c < nv) m8[g] = fmaxf(m8[g], logit_of(v[c], a.scale, a.bias, col_base + c0 + c));
+                  if (c < nv) m8[g] = fmaxf(m8[g], logit_of(v[c], a.scale, bias, col_base + c0 + c));
               }
             }
             const float mm = fmax3(fmax3(m8[0], m8[1], m8[2]), fmax3(m8[3], m8[4], m8[5]), fmaxf(m8[6], m8[7]));

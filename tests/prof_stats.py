@@ -21,4 +21,11 @@ for name, M, N, d, dt in (("bf16_4096x1M_d128", 4096, 1_000_000, 128, torch.bflo
     lab = torch.randint(0, N, (M,), device="cuda", generator=g)
     bias = torch.randn(N, device="cuda", generator=g) * 0.1 if "bias" in name else None
     out[name] = t(lambda: ops.ce_rowstats(U, W, lab, bias=bias))
+g = torch.Generator(device="cuda").manual_seed(5)
+M, N, d = 4096, 1_000_000, 128
+U = (torch.randn(M, d, device="cuda", generator=g) / d ** 0.25).bfloat16()
+W = (torch.randn(N, d, device="cuda", generator=g) / d ** 0.25).bfloat16()
+bias = torch.randn(N, device="cuda", generator=g) * 0.1
+out["topk50_bf16_4096x1M_d128"] = t(lambda: ops.topk_eval(U, W, 50))
+out["topk50_bias_bf16_4096x1M_d128"] = t(lambda: ops.topk_eval(U, W, 50, bias=bias))
 print(json.dumps(out))

@@ -387,6 +387,28 @@ def test_masked_topk_and_metrics(ops, B, N, d, K, max_seen, precision):
         assert all(abs(got[k] - ref[k]) <= 2.0 / B for k in ref)
 
 
+@pytest.mark.parametrize("B,N,d,K,offset", [(300, 5000, 64, 20, 0), (513, 40_000, 128, 50, 1), (200, 3000, 256, 10, 0)])
+def test_masked_topk_with_bias_head(ops, B, N, d, K, offset):
+    """BERT4Rec-style head (scale * U W^T + bias, BERT4Rec/main.py:83,189): masked top-K and row statistics with a bias
+    vector that is 16-byte aligned (vector loads in the epilogue) or not (``offset`` = 1: a slice of a larger buffer)."""
+    g = torch.Generator().manual_seed(B + N + d)
+    U = bf16_round(torch.randn(B, d, generator=g) / d ** 0.25)
+    W = bf16_round(torch.randn(N, d, generator=g) / d ** 0.25)
+    bias = torch.randn(N, generator=g) * 0.5
+    lab = torch.randint(0, N, (B,), generator=g)
+    seen = _seen_lists(g, B, N, 40)
+    crow, col = orc.lists_to_csr(seen)
+    bd = dev(torch.cat([torch.zeros(offset), bias]))[offset:]
+    vals, ids = ops.topk_eval(dev(U).bfloat16(), dev(W).bfloat16(), K, dev(crow), dev(col), bias=bd, scale=0.7)
+    masked = orc.mask_seen(orc.score_dense(U, W, bias, 0.7), crow, col)
+    assert _check_topk(vals, ids, masked, K, 2e-6) > 0.99
+    m, l, ll = ops.ce_rowstats(dev(U).bfloat16(), dev(W).bfloat16(), dev(lab), bias=bd, scale=0.7)
+    rm, rl, rll = orc.ce_rowstats(U, W, lab, bias, 0.7)
+    lse, rlse = (m + torch.log(l)).cpu(), rm + torch.log(rl)
+    assert float((lse - rlse).abs().max()) <= 1e-5 * float(rlse.abs().max()) + 1e-6
+    assert_rel(ll, rll, 1e-5, "label logit")
+
+
 def test_golden_unisrec_evaluate_masked_topk_and_hits(ops, golden):
     """a8-a10 against the reference's own evaluate (tests/golden/unisrec_evaluate.npz: the masked scores and dense
     targets ``CoachForUniSRec.evaluate`` handed to its metric functions): the fused masked top-K must be the top-K of
