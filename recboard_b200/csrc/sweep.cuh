@@ -6,14 +6,15 @@
 //   EPI_DENSE  store S (compat path for recommend_from_full, reference SASRec/main.py:228)
 //   EPI_LSE    online (max, sum-exp) + label-logit pick   (F.cross_entropy fwd, SASRec/main.py:217-219)
 //   EPI_TOPK   maximum of every (row, 128-item tile) of a short PREFIX of the catalog (a few percent): the
-//              seed of the exact top-K (UniSRec/main.py:408-435 without dense (B,N)).  A tile holding one of
-//              the row's seen ids is reported as NaN ("dirty": it never supports a threshold), so no per-item
-//              masking happens here.  simt.cuh turns the clean tile maxima of the prefix into the row's
+//              seed of the exact top-K (UniSRec/main.py:408-435 without dense (B,N)).  The maximum runs over the
+//              row's UNSEEN items (the seen ids of a chunk, read off the sorted list as the sweep passes them,
+//              are set to -inf; with scale <= 0 a tile holding a seen id is reported as NaN, "dirty", instead),
+//              so a user with thousands of seen ids still gets a threshold.  simt.cuh turns the tile maxima of the prefix into the row's
 //              starting threshold tau0 = K-th largest (>= K unseen items reach it) and a ladder of
 //              checkpoints c_k = (K >> k)-th largest.
 //   EPI_CAND   the one sweep over the whole catalog: every (row, aligned group of 4 items) whose maximum
 //              reaches the row's RUNNING threshold goes to the (row, split[, warpgroup]) sub-list as
-//              (group maximum, group id).  The threshold climbs the ladder while the sweep runs: a thread
+//              (group maximum, group id; groups that hold a seen id are marked dirty and support no count).  The threshold climbs the ladder while the sweep runs: a thread
 //              counts its clean candidates that reach the next two checkpoints in registers, publishes the
 //              counts every fourth tile (two REDs into the row's shared counters -- all splits of a row share
 //              them) and re-reads the counters (the loads in flight behind the tile's arithmetic); once >= K
@@ -389,17 +390,33 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
 
       // ---- EPI_CAND: the parked hit chunk of this thread (see the chunk loop) and its service routine
       float pk_m[8], pk_mul = 1.f;
-      unsigned int pk_item0 = 0u;
+      unsigned int pk_item0 = 0u;    // first item of the parked chunk
       bool pk_pend = false;
       auto serve_parked = [&]() {
+        // which of the chunk's 32 columns are seen ids of this row: read off the sorted list from the cursor, which
+        // still stands at the first seen id of the TILE (it moves on after the tile) -- on the rare hit path only,
+        // the per-tile loop pays nothing for it
+        unsigned int pk_seen = 0u;
+        if (next_seen < static_cast<int>(pk_item0) + 32) {
+          int j = seen_cur, id = next_seen;
+          while (id < static_cast<int>(pk_item0) + 32) {
+            if (id >= static_cast<int>(pk_item0)) pk_seen |= 1u << (id - static_cast<int>(pk_item0));
+            ++j;
+            id = (j < seen_end) ? __ldg(a.seen_col + j) : 0x7fffffff;
+          }
+        }
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const float sg = __fmul_rn(pk_m[g], pk_mul);
           if (sg >= tau) {
+            // a group of 4 that holds a seen id is "dirty": its maximum may belong to the seen item, so it is listed (the
+            // finish kernel re-scores it item by item) but supports no checkpoint.  Dirtiness is per GROUP: a user with
+            // thousands of seen ids still has clean groups, counts, and a threshold that climbs.
+            const bool dirty = ((pk_seen >> (4 * g)) & 0xFu) != 0u;
             if (n_cand < a.cand_cap)
-              cand_list[n_cand] = make_uint2(__float_as_uint(sg), ((pk_item0 & ~CAND_DIRTY) >> 2) + g | (pk_item0 & CAND_DIRTY));
+              cand_list[n_cand] = make_uint2(__float_as_uint(sg), ((pk_item0 >> 2) + g) | (dirty ? CAND_DIRTY : 0u));
             ++n_cand;
-            if (!(pk_item0 & CAND_DIRTY)) {  // a clean group's maximum is an unseen item: it supports the checkpoints it reaches
+            if (!dirty) {  // a clean group's maximum is an unseen item: it supports the checkpoints it reaches
               n1 += (sg >= ck1) ? 1u : 0u;
               n2 += (sg >= ck2) ? 1u : 0u;
             }
@@ -420,16 +437,19 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
         // the two loads are in flight behind this tile's arithmetic and are consumed after it
         bool refresh = false;
         uint4 h_lo = make_uint4(0u, 0u, 0u, 0u), h_hi = make_uint4(0u, 0u, 0u, 0u);
-        unsigned int dirty_bit = 0u;
         if (C::EPI == EPI_CAND) {
           refresh = (ld != nullptr) && ((my_tiles++ & 3u) == 3u);
           if (refresh) {
             h_lo = __ldcg(reinterpret_cast<const uint4*>(ld->cnt));
             h_hi = __ldcg(reinterpret_cast<const uint4*>(ld->cnt) + 1);
           }
-          while (next_seen < col_base) seen_advance();   // seen ids that fell into the other warpgroup's tiles
-          dirty_bit = (next_seen < col_base + C::BN) ? CAND_DIRTY : 0u;
         }
+        if (C::EPI == EPI_CAND || C::EPI == EPI_TOPK)
+          while (next_seen < col_base) seen_advance();   // seen ids that fell into the other warpgroup's tiles
+        // TOPK: the tile maximum is taken over the row's UNSEEN items (seen columns are set to -inf chunk by chunk),
+        // which needs scale > 0; otherwise a tile that holds a seen id is reported NaN ("dirty") as a whole
+        const bool mask_exact = a.scale > 0.f;
+        bool tile_dirty = false;
         mbar_wait(&bar->s_full[bidx], sph);
         tc_fence_after();
         float tmax = -INFINITY;   // TOPK: max of this tile for this row
@@ -450,9 +470,24 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
             tmem_ld32(t_lane + ch * 32, raw[0]);
             tmem_ld_wait();
           }
-          const uint32_t (&v)[32] = raw[DB ? (ch & 1) : 0];
+          uint32_t (&v)[32] = raw[DB ? (ch & 1) : 0];
           const int c0 = ch * 32;                  // first column of the chunk within the tile
           const int nv = n_valid - c0;             // valid columns in this chunk (may be <= 0 or >= 32)
+          unsigned int seen32 = 0u;                // TOPK: the row's seen ids among the chunk's 32 columns
+          if (C::EPI == EPI_TOPK) {
+            while (next_seen < col_base + c0 + 32) {   // sorted list, chunks in order: usually no iteration
+              seen32 |= 1u << (next_seen - (col_base + c0));
+              seen_advance();
+            }
+            if (seen32 != 0u) {
+              tile_dirty = true;
+              if (mask_exact) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                  if ((seen32 >> c) & 1u) v[c] = 0xff800000u;   // -inf: a seen item never carries a tile maximum
+              }
+            }
+          }
 
           if (C::EPI == EPI_DENSE) {
             if (srow_ok && nv > 0) {
@@ -608,7 +643,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
             if (hit) {
 #pragma unroll
               for (int g = 0; g < 8; ++g) pk_m[g] = m8[g];
-              pk_item0 = static_cast<unsigned int>(col_base + c0) | dirty_bit;
+              pk_item0 = static_cast<unsigned int>(col_base + c0);
               pk_mul = mul;
               pk_pend = true;
             }
@@ -644,11 +679,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tm_stat, const __grid_constant_
           }
         }
         if (C::EPI == EPI_TOPK) {
-          while (next_seen < col_base) seen_advance();  // seen ids that fell into the other warpgroup's tiles
-          const bool dirty = next_seen < col_base + C::BN;
-          while (next_seen < col_base + C::BN) seen_advance();
           float out = tile_quick ? __fmul_rn(tmax, a.scale) : tmax;
-          if (dirty) out = __int_as_float(0x7fc00000);  // NaN
+          if (tile_dirty && !mask_exact) out = __int_as_float(0x7fc00000);  // NaN
           if (srow_ok) a.tile_max[static_cast<long long>(srow) * a.n_strm_tiles + t] = out;
         }
       }  // tiles

@@ -455,6 +455,30 @@ def test_topk_without_seen_and_ties(ops):
     assert_rel(vals, rv, 2e-6, "tie vals")
 
 
+def test_topk_heavy_users_keep_a_threshold(ops):
+    """Users whose seen list covers a large part of a small catalog (every 128-item tile holds seen ids): the prefix
+    maxima run over the unseen items and candidate groups are dirty one by one, so those rows still get a threshold and
+    do not fall back to the exact scan (checked through rb_topk_debug_layout: no overflowed sub-list)."""
+    import ctypes
+    from recboard_b200 import _lib as L
+    g = torch.Generator().manual_seed(33)
+    B, N, d, K = 300, 38_048, 64, 20
+    U = bf16_round(torch.randn(B, d, generator=g) / d ** 0.25)
+    W = bf16_round(torch.randn(N, d, generator=g) / d ** 0.25)
+    seen = _seen_lists(g, B, N, 40)
+    for r in range(0, B, 7):                       # heavy users: 3000-9000 seen ids, ~10-30 per tile
+        seen[r] = torch.randperm(N, generator=g)[: 3000 + 20 * r].tolist()
+    crow, col = orc.lists_to_csr(seen)
+    vals, ids = ops.topk_eval(dev(U).bfloat16(), dev(W).bfloat16(), K, dev(crow), dev(col))
+    masked = orc.mask_seen(orc.score_dense(U, W), crow, col)
+    assert _check_topk(vals, ids, masked, K, 2e-6) > 0.99
+    out = (ctypes.c_int64 * 8)()
+    L.check(L.lib().rb_topk_debug_layout(B, N, d, K, L.MODE_BF16, col.numel(), out), "rb_topk_debug_layout")
+    ws = next(iter(L.Workspace._bufs.values()))
+    overflow = ws[out[5]:out[5] + 4 * B].view(torch.int32)
+    assert int(overflow.sum()) == 0, f"{int(overflow.sum())} rows fell back to the exact scan"
+
+
 def test_topk_candidate_overflow_falls_back(ops):
     # massive ties: every item of a 5000-item catalog scores the same for half of the rows, so the candidate
     # list of the threshold sweep overflows and the exact fallback must take over (lowest ids win)
