@@ -780,6 +780,7 @@ __device__ __forceinline__ float exact_logit(const float* __restrict__ u, const 
 //   2. the groups that reach T (about K, plus the dirty ones) are re-scored exactly in fp32, eight groups = 32 items
 //      per step as they come, seen items dropped (UniSRec/main.py:413), the K best by (score desc, id asc) kept.
 // Only a sub-list that ran over its own capacity flags the row for the fallback below.  One warp per row.
+constexpr int TFC_MAXSUB = 1024;   // sub-lists per row the flattened walk handles (prefix array in shared memory)
 template <typename TW, int E>
 __global__ void __launch_bounds__(128)
 topk_from_cands_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const float* __restrict__ bias, float scale,
@@ -791,6 +792,7 @@ topk_from_cands_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const
   __shared__ unsigned long long stage_s[4][256];
   __shared__ float fstage_s[4][32 * E];
   __shared__ unsigned int queue_s[4][64];
+  __shared__ int pref_s[4][TFC_MAXSUB + 1];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 4 + wib;
   if (row >= n_rows) return;
@@ -803,6 +805,57 @@ topk_from_cands_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const
   ovf = __any_sync(0xffffffffu, ovf);
   if (lane == 0) overflow[row] = ovf ? 1 : 0;
   if (ovf) return;
+  // ---- the row's candidates as ONE sequence.  A small batch is swept by many splits (256 rows: 148 splits x 2 tile
+  // parities = 296 sub-lists of two or three entries each), and walking them one by one costs two dependent L2 round
+  // trips per sub-list (386 us for 256 rows).  So: exclusive prefix of the counts in shared memory, and lane l of
+  // step s takes entry 32 s + l of the concatenation (binary search for its sub-list).
+  int* pref = pref_s[wib];
+  const bool flat = n_sub <= TFC_MAXSUB;
+  int total = 0;
+  if (flat) {
+    for (int b0 = 0; b0 < n_sub; b0 += 32) {
+      const int c = (b0 + lane < n_sub) ? cnts[b0 + lane] : 0;
+      int inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += up;
+      }
+      if (b0 + lane < n_sub) pref[b0 + lane] = total + inc - c;
+      total += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) pref[n_sub] = total;
+    __syncwarp();
+  }
+  // body(ok, entry) is called warp-uniformly once per 32 candidates, in list order
+  auto walk = [&](auto&& body) {
+    if (flat) {
+      for (int e0 = 0; e0 < total; e0 += 32) {
+        const int f = e0 + lane;
+        uint2 x = make_uint2(0u, 0u);
+        if (f < total) {
+          int lo = 0, hi = n_sub;   // the last sub-list whose first entry is at or before f
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (pref[mid] <= f) lo = mid; else hi = mid;
+          }
+          x = __ldg(lists + static_cast<long long>(lo) * cap + (f - pref[lo]));
+        }
+        body(f < total, x);
+      }
+    } else {
+      for (int j = 0; j < n_sub; ++j) {
+        const int c = cnts[j];
+        const uint2* gl = lists + static_cast<long long>(j) * cap;
+        for (int e0 = 0; e0 < c; e0 += 32) {
+          const int e = e0 + lane;
+          uint2 x = make_uint2(0u, 0u);
+          if (e < c) x = __ldg(gl + e);
+          body(e < c, x);
+        }
+      }
+    }
+  };
   // ---- trip 1: the cut = K-th largest maximum among the clean groups (-inf when there are fewer than K)
   float cut = -INFINITY;
   {
@@ -826,25 +879,17 @@ topk_from_cands_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const
       ns = 0;
       __syncwarp();
     };
-    for (int j = 0; j < n_sub; ++j) {
-      const int c = cnts[j];
-      const uint2* gl = lists + static_cast<long long>(j) * cap;
-      for (int e0 = 0; e0 < c; e0 += 32) {
-        const int e = e0 + lane;
-        float v = -INFINITY;
-        if (e < c) {
-          const uint2 x = __ldg(gl + e);
-          if (!(x.y & CAND_DIRTY)) v = __uint_as_float(x.x);
-        }
-        const bool pass = v > kthf;
-        const uint32_t m = __ballot_sync(0xffffffffu, pass);
-        if (m != 0u) {
-          if (pass) fstage[ns + __popc(m & lt)] = v;
-          ns += __popc(m);
-          if (ns > 32 * E - 32) flushf();
-        }
+    walk([&](bool ok, uint2 x) {
+      float v = -INFINITY;
+      if (ok && !(x.y & CAND_DIRTY)) v = __uint_as_float(x.x);
+      const bool pass = v > kthf;
+      const uint32_t m = __ballot_sync(0xffffffffu, pass);
+      if (m != 0u) {
+        if (pass) fstage[ns + __popc(m & lt)] = v;
+        ns += __popc(m);
+        if (ns > 32 * E - 32) flushf();
       }
-    }
+    });
     if (ns > 0) flushf();
     cut = kthf;
     if (cut > -INFINITY) cut -= fabsf(cut) * 3.8146973e-06f;   // tensor-core vs exact fp32 scores differ in the last bits
@@ -899,33 +944,23 @@ topk_from_cands_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const
     if (ns > 256 - 32) flush();
   };
   int nq = 0;   // groups waiting in the queue (< 8 between steps, up to 8 + 31 inside one)
-  for (int j = 0; j < n_sub; ++j) {
-    const int c = cnts[j];
-    const uint2* gl = lists + static_cast<long long>(j) * cap;
-    for (int e0 = 0; e0 < c; e0 += 32) {
-      const int e = e0 + lane;
-      bool keep = false;
-      unsigned int gid = 0u;
-      if (e < c) {
-        const uint2 x = __ldg(gl + e);
-        keep = __uint_as_float(x.x) >= cut;
-        gid = x.y & ~CAND_DIRTY;
-      }
-      const uint32_t m = __ballot_sync(0xffffffffu, keep);
-      if (keep) queue[nq + __popc(m & lt)] = gid;
-      nq += __popc(m);
+  walk([&](bool ok, uint2 x) {
+    const bool keep = ok && __uint_as_float(x.x) >= cut;
+    const unsigned int gid = x.y & ~CAND_DIRTY;
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    if (keep) queue[nq + __popc(m & lt)] = gid;
+    nq += __popc(m);
+    __syncwarp();
+    while (nq >= 8) {
+      score_step(8);
       __syncwarp();
-      while (nq >= 8) {
-        score_step(8);
-        __syncwarp();
-        const unsigned int moved = (lane + 8 < nq) ? queue[lane + 8] : 0u;   // nq <= 39: one lane-wide shift suffices
-        __syncwarp();
-        if (lane + 8 < nq) queue[lane] = moved;
-        nq -= 8;
-        __syncwarp();
-      }
+      const unsigned int moved = (lane + 8 < nq) ? queue[lane + 8] : 0u;   // nq <= 39: one lane-wide shift suffices
+      __syncwarp();
+      if (lane + 8 < nq) queue[lane] = moved;
+      nq -= 8;
+      __syncwarp();
     }
-  }
+  });
   if (nq > 0) score_step(nq);
   flush();
 #pragma unroll
