@@ -41,8 +41,8 @@ SEQ = 50
 TOPK = 50
 METRIC = "full-catalog scored user-item pairs/sec (CE train + top-K eval)"
 # dram__bytes_read.sum + dram__bytes_write.sum of one pair_kernel<PASS_DW> launch at this workload (ncu --set full)
-PROFILED_TRAFFIC_BYTES = 261_200_000 + 207_600_000
-PROFILED_TRAFFIC_SOURCE = "profiles/r2_ncu_summary.md (ncu --set full, one launch of pair_kernel<PASS_DW>, N=1M shard: dram read + write)"
+PROFILED_TRAFFIC_BYTES = 261_439_488 + 208_969_472
+PROFILED_TRAFFIC_SOURCE = "profiles/r2_ncu_summary.md, final capture (ncu --set full, one launch of pair_kernel<PASS_DW>, N=1M shard: dram read + write)"
 UNIT = "pairs/s"
 WORKLOAD = ("configs[2]: SASRec bf16 full-softmax CE train + masked top-50 eval, "
             "1M-item catalog per GPU (row-sharded), d=128, 4096 query rows, gather 4096x50")
