@@ -79,11 +79,10 @@ def _eager_eval(U, W, seen_crow, seen_col, tgt_crow, tgt_col, ks, autocast: bool
     return out
 
 
-def _fused_eval(U, W, K, seen_crow, seen_col, tgt_crow, tgt_col, precision):
+def _fused_eval(U, W, K, seen_crow, seen_col, tgt_crow, tgt_col, precision, monitors):
     from recboard_b200 import metrics as MX
     _, ids = ops.topk_eval(U, W, K, seen_crow, seen_col, precision=precision)
-    hits = MX.hits_from_topk(ids, tgt_crow, tgt_col, W.shape[0])
-    return MX.metrics_from_hits(hits.cpu(), (tgt_crow[1:] - tgt_crow[:-1]).float().cpu(), [f"HITRATE@{K}", f"NDCG@{K}"])
+    return MX.batch_metrics(ids, tgt_crow, tgt_col, W.shape[0], monitors, exact=False)   # one pass, one small read
 
 
 def eager_baseline(dev: torch.device, reps: int = 3) -> Dict[str, Dict]:
@@ -132,11 +131,12 @@ def eager_baseline(dev: torch.device, reps: int = 3) -> Dict[str, Dict]:
         eager = {"fp32": time_ms(lambda: _eager_eval(Ue, W, seen_crow, seen_col, tgt_crow, tgt, c["ks"], False, c["eval_batch"]), 2),
                  "bf16": time_ms(lambda: _eager_eval(Ue, W, seen_crow, seen_col, tgt_crow, tgt, c["ks"], True, c["eval_batch"]), 2)}
         ev = {"eager_fp32_ms": eager["fp32"], "eager_bf16_autocast_ms": eager["bf16"],
-              "note": "both sides include the metric reduction and its device->host reads"}
+              "note": "both sides evaluate the same metric@k list and include its device->host reads"}
         for fp in modes:
             cast = (lambda x: x.bfloat16()) if fp == "bf16" else (lambda x: x)
             Uef, Wef = cast(Ue), cast(W)
-            ef = time_ms(lambda: _fused_eval(Uef, Wef, c["K"], seen_crow, seen_col, tgt_crow, tgt, fp), max(reps, 5), 2)
+            mons = [f"{n}@{k}" for n, k in c["ks"]]   # the same metric@k list the eager side evaluates
+            ef = time_ms(lambda: _fused_eval(Uef, Wef, c["K"], seen_crow, seen_col, tgt_crow, tgt, fp, mons), max(reps, 5), 2)
             ev[f"fused_{fp}_ms"] = ef
             ev[f"speedup_{fp}"] = eager[fp] / ef
             ev[f"fused_{fp}_pairs_per_s"] = B * N / (ef * 1e-3)

@@ -218,6 +218,17 @@ int rb_topk_merge(const float* vals, const int32_t* ids, int R, int64_t B, int K
 int rb_topk_hits(const int32_t* top_ids, const int64_t* target_crow, const int64_t* target_col, int64_t B,
                  int K, float* hits, rb_stream_t stream);
 
+/* a10 in one pass: batch means of n_metrics METRIC@k values straight from the ranked ids -- what
+ * `self.monitor(scores, targets, n=bsz, reduction="mean", pool=[...])` (UniSRec/main.py:428-435) returns per batch,
+ * without a hit matrix, per-metric top-k calls or per-metric scalar reads.  kinds (HOST array): 0 HITRATE, 1 RECALL,
+ * 2 PRECISION, 3 NDCG, 4 MRR; ks (HOST array): the k of each.  w[K] = 1/log2(rank+2) and w_cum[K] = its running sum
+ * (device, float32); partial = device scratch of rb_topk_metrics_blocks(B) * 32 doubles; out[n_metrics] float32
+ * (device).  Per-row values in float32, batch sums in double in a fixed order (deterministic). */
+int rb_topk_metrics_blocks(int64_t B);
+int rb_topk_metrics(const int32_t* top_ids, const int64_t* target_crow, const int64_t* target_col, int64_t B, int K,
+                    const float* w, const float* w_cum, const int32_t* kinds, const int32_t* ks, int n_metrics,
+                    double* partial, float* out, rb_stream_t stream);
+
 /* Upper bound of the workspace an op needs (bytes). nnz = seen-list entries for RB_OP_TOPK_EVAL,
  * number of indices for RB_OP_SCATTER_ADD, else ignored. */
 size_t rb_workspace_bytes(int op, int64_t M, int64_t N, int d, int K, int mode, int64_t nnz);

@@ -1066,6 +1066,36 @@ extern "C" int rb_topk_hits(const int32_t* top_ids, const int64_t* target_crow, 
   return 0;
 }
 
+// Batch means of n_metrics METRIC@k values straight from the ranked ids (kinds: 0 HITRATE, 1 RECALL, 2 PRECISION, 3 NDCG,
+// 4 MRR; kinds / ks are HOST arrays).  w[K] = 1/log2(rank+2), w_cum[K] = its running sum (device, float32);
+// partial: device scratch of rb_topk_metrics_blocks(B) * 32 doubles; out[n_metrics] float32 on the device.
+extern "C" int rb_topk_metrics_blocks(int64_t B) {
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((B + 7) / 8, 148 * 4)));
+}
+extern "C" int rb_topk_metrics(const int32_t* top_ids, const int64_t* target_crow, const int64_t* target_col, int64_t B, int K,
+                               const float* w, const float* w_cum, const int32_t* kinds, const int32_t* ks, int n_metrics,
+                               double* partial, float* out, rb_stream_t stream) {
+  RB_RANGE("rb_topk_metrics");
+  DevInfo dv; if (int r = get_dev(dv)) return r;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!top_ids || !target_crow || !w || !w_cum || !kinds || !ks || !partial || !out) return fail(RB_E_ARG, "null pointer");
+  if (B <= 0 || K < 1) return fail(RB_E_ARG, "bad shape B=%lld K=%d", (long long)B, K);
+  if (n_metrics < 1 || n_metrics > TM_MAX_METRICS) return fail(RB_E_ARG, "1 <= n_metrics <= %d (got %d)", TM_MAX_METRICS, n_metrics);
+  MetricSpec spec{};
+  spec.n = n_metrics;
+  for (int m = 0; m < n_metrics; ++m) {
+    if (kinds[m] < 0 || kinds[m] > 4) return fail(RB_E_ARG, "unknown metric kind %d", kinds[m]);
+    if (ks[m] < 1 || ks[m] > K) return fail(RB_E_ARG, "metric %d: k=%d outside [1, %d]", m, ks[m], K);
+    spec.kind[m] = kinds[m]; spec.k[m] = ks[m];
+  }
+  const int blocks = rb_topk_metrics_blocks(B);
+  topk_metrics_kernel<<<blocks, 256, 0, st>>>(top_ids, target_crow, target_col, B, K, w, w_cum, spec, partial);
+  RB_LAUNCH_CHECK("topk_metrics_kernel");
+  topk_metrics_finish_kernel<<<1, 32, 0, st>>>(partial, blocks, n_metrics, B, out);
+  RB_LAUNCH_CHECK("topk_metrics_finish_kernel");
+  return 0;
+}
+
 // ========================================================================== workspace
 extern "C" size_t rb_workspace_bytes(int op, int64_t M, int64_t N, int d, int K, int mode, int64_t nnz) {
   int sms = 148;  // B200; refined from the current device when there is one

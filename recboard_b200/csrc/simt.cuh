@@ -1166,6 +1166,84 @@ __global__ void topk_hits_kernel(const int* __restrict__ top_ids, const int64_t*
   hits[i] = h;
 }
 
+// ---- every METRIC@k of a batch in one pass over the ranked ids (rb_topk_metrics): no (B,K) hit matrix travels, no
+// per-metric launches.  One warp per row (lane <-> rank, 32 ranks at a time); lane m < n_metrics ends up with metric
+// m's row value, summed over the warp's rows in double; blocks write partial sums, a second one-block launch adds
+// them in block order and divides by the batch size => deterministic.  Metric definitions as metrics.metric_rows
+// (HR = any hit, RECALL = hits / max(|targets|, 1), PRECISION = hits / k, NDCG = DCG / IDCG(min(k, |targets|)),
+// MRR = 1 / (rank of the first hit + 1)); w = 1 / log2(rank + 2) and its running sum come from the host in float32.
+constexpr int TM_MAX_METRICS = 32;
+struct MetricSpec { int kind[TM_MAX_METRICS]; int k[TM_MAX_METRICS]; int n; };
+__global__ void __launch_bounds__(256)
+topk_metrics_kernel(const int* __restrict__ top_ids, const int64_t* __restrict__ tcrow, const int64_t* __restrict__ tcol,
+                    long long n_rows, int K, const float* __restrict__ w, const float* __restrict__ w_cum,
+                    const MetricSpec spec, double* __restrict__ partial) {
+  __shared__ double blk[8][TM_MAX_METRICS];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long warp0 = static_cast<long long>(blockIdx.x) * 8 + wib, n_warps = static_cast<long long>(gridDim.x) * 8;
+  const int my_kind = lane < spec.n ? spec.kind[lane] : -1, my_k = lane < spec.n ? spec.k[lane] : 0;
+  double acc = 0.0;
+  for (long long row = warp0; row < n_rows; row += n_warps) {
+    const long long t_lo = tcrow[row], t_hi = tcrow[row + 1];
+    const int n_t = static_cast<int>(t_hi - t_lo);
+    float cnt = 0.f, dcg = 0.f;      // lane m: hits within the first k_m ranks, and their discounted sum
+    int first = 0x7fffffff;          // rank of the first hit (same in every lane)
+    for (int r0 = 0; r0 < K; r0 += 32) {
+      const int r = r0 + lane;
+      bool hit = false;
+      float wr = 0.f;
+      if (r < K) {
+        const long long id = top_ids[row * K + r];
+        wr = __ldg(w + r);
+        if (id >= 0) {
+          long long lo = t_lo, hi = t_hi;
+          while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if (__ldg(tcol + mid) < id) lo = mid + 1; else hi = mid;
+          }
+          hit = lo < t_hi && __ldg(tcol + lo) == id;
+        }
+      }
+      const uint32_t hm = __ballot_sync(0xffffffffu, hit);
+      if (hm != 0u && first == 0x7fffffff) first = r0 + __ffs(hm) - 1;
+      // lane m needs the hits of ranks < k_m: ranks r0 .. min(r0+32, k_m)
+      const int upto = my_k - r0;   // how many ranks of this chunk count for lane m's metric
+      const uint32_t mine = upto >= 32 ? hm : (upto > 0 ? (hm & ((1u << upto) - 1u)) : 0u);
+      cnt += static_cast<float>(__popc(mine));
+      uint32_t rest = hm;
+      while (rest != 0u) {          // warp-uniform loop over the chunk's hits (LOU: at most one)
+        const int j = __ffs(rest) - 1;
+        rest &= rest - 1u;
+        const float wj = __shfl_sync(0xffffffffu, wr, j);
+        if ((mine >> j) & 1u) dcg += wj;
+      }
+    }
+    float v = 0.f;
+    if (my_kind == 0) v = cnt > 0.f ? 1.f : 0.f;
+    else if (my_kind == 1) v = cnt / fmaxf(static_cast<float>(n_t), 1.f);
+    else if (my_kind == 2) v = cnt / static_cast<float>(my_k);
+    else if (my_kind == 3) { const int n_rel = min(n_t, my_k); v = n_rel > 0 ? dcg / __ldg(w_cum + n_rel - 1) : 0.f; }
+    else if (my_kind == 4) v = first < my_k ? 1.f / (static_cast<float>(first) + 1.f) : 0.f;
+    acc += static_cast<double>(v);
+  }
+  blk[wib][lane] = acc;
+  __syncthreads();
+  if (wib == 0 && lane < spec.n) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += blk[q][lane];
+    partial[static_cast<long long>(blockIdx.x) * TM_MAX_METRICS + lane] = s;
+  }
+}
+__global__ void topk_metrics_finish_kernel(const double* __restrict__ partial, int n_blocks, int n_metrics, long long n_rows,
+                                           float* __restrict__ out) {
+  const int m = threadIdx.x;
+  if (m >= n_metrics) return;
+  double s = 0.0;
+  for (int b = 0; b < n_blocks; ++b) s += partial[static_cast<long long>(b) * TM_MAX_METRICS + m];
+  out[m] = static_cast<float>(s / static_cast<double>(n_rows));
+}
+
 // ---- merge of R sorted per-shard lists (rb_topk_merge): list l of row i at (l*n_rows + i)*K + e
 template <int E>
 __global__ void topk_merge_kernel(const float* __restrict__ vals, const int* __restrict__ ids, int n_lists,

@@ -132,12 +132,19 @@ def evaluate_split(score_topk, split: DeviceEvalSplit, monitors: Sequence[str], 
     returns the sorted (vals, ids) of rows [lo, hi) (e.g. a closure over ``model.recommend_topk``)."""
     kmax = MX.kmax_of(monitors)
     meters = {m.upper(): MX.AverageMeter() for m in monitors}
+    acc = None   # exact=False: bsz-weighted sums stay on the device, ONE read-back at the end of the sweep
     for lo in range(0, split.n_rows, batch_size):
         hi = min(lo + batch_size, split.n_rows)
         s_crow, s_col, t_crow, t_col = split.batch(lo, hi)
         _, ids = score_topk(lo, hi, kmax, s_crow if remove_seen else None, s_col if remove_seen else None)
-        for name, v in MX.batch_metrics(ids, t_crow, t_col, n_items, monitors, exact=exact).items():
-            meters[name].update(v, hi - lo)                                         # UniSRec/main.py:428-435, n=bsz
+        if exact:
+            for name, v in MX.batch_metrics(ids, t_crow, t_col, n_items, monitors, exact=True).items():
+                meters[name].update(v, hi - lo)                                     # UniSRec/main.py:428-435, n=bsz
+        else:
+            v = MX.batch_metrics_device(ids, t_crow, t_col, monitors).double() * (hi - lo)
+            acc = v if acc is None else acc + v
+    if not exact and acc is not None:
+        return {m.upper(): float(x) for m, x in zip(monitors, (acc / split.n_rows).cpu())}
     return {k: m.avg for k, m in meters.items()}
 
 

@@ -260,6 +260,9 @@ def test_evaluate_sweep_and_split_match_oracle(cuda):
         return model.recommend_topk({model.ISeq: seqs_d[lo:hi]}, k, crow, col)
 
     assert EV.evaluate_split(score_topk, split, MONS, model.Item.count, batch_size=32) == ref
+    # metrics reduced on the device in one pass per batch, one read-back per sweep: same values to 1e-6
+    fast = EV.evaluate_split(score_topk, split, MONS, model.Item.count, batch_size=32, exact=False)
+    assert set(fast) == set(ref) and all(abs(fast[k] - ref[k]) <= 1e-6 * max(1.0, abs(ref[k])) for k in ref)
 
 
 def test_evaluate_split_model_from_reference_rows(cuda):

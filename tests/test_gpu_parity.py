@@ -427,6 +427,30 @@ def test_golden_unisrec_evaluate_masked_topk_and_hits(ops, golden):
         assert torch.equal(hits.cpu(), targets.gather(1, ri))
 
 
+@pytest.mark.parametrize("B,N,K,multi", [(300, 5000, 50, False), (257, 900, 100, True), (1, 40, 7, True)])
+def test_metrics_in_one_pass_match_the_exact_reduction(ops, B, N, K, multi):
+    """rb_topk_metrics (all METRIC@k of a batch from the ranked ids, on the device) against the oracle's float32
+    reductions: single-target rows (LOU) and ragged multi-target rows incl. rows without targets and -1 ids."""
+    g = torch.Generator().manual_seed(B + K)
+    ids = torch.stack([torch.randperm(N, generator=g)[:K] for _ in range(B)]).int()
+    ids[0, K // 2:] = -1                         # a row whose ranked list ran out of unmasked items
+    tgts = []
+    for r in range(B):
+        n_t = int(torch.randint(0, 6, (1,), generator=g)) if multi else 1
+        pick = ids[r, torch.randperm(K, generator=g)[: n_t // 2 + 1]].tolist() if r % 3 else []
+        extra = torch.randint(0, N, (max(n_t - len(pick), 0),), generator=g).tolist()
+        t = sorted(set(int(x) for x in pick + extra if x >= 0))
+        tgts.append(t if (multi or t) else [int(torch.randint(0, N, (1,), generator=g))])
+    crow, col = orc.lists_to_csr(tgts)
+    mons = [f"{m}@{k}" for m in ("HITRATE", "RECALL", "PRECISION", "NDCG", "MRR") for k in (1, 5, K) if k <= K]
+    n_t = (crow[1:] - crow[:-1]).float()
+    ref = MX.metrics_from_hits(orc.hits_from_topk(ids, crow, col, N), n_t, mons)
+    got = MX.batch_metrics(dev(ids), dev(crow), dev(col), N, mons, exact=False)
+    assert set(got) == set(ref)
+    for k in ref:
+        assert abs(got[k] - ref[k]) <= 1e-6 * max(1.0, abs(ref[k])), (k, got[k], ref[k])
+
+
 def test_topk_hits_kernel_matches_host_logic(ops):
     """rb_topk_hits vs the oracle's dense-target gather (multi-target rows, missing entries, empty rows)."""
     g = torch.Generator().manual_seed(3)
