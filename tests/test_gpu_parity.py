@@ -951,6 +951,17 @@ def test_full_size_config4_hstu_retrieval_shard(ops):
         S[torch.arange(4, device="cuda").repeat_interleave(3), col[:12]] = -1e23
         rv, ri = torch.sort(S, dim=1, descending=True, stable=True)
         assert torch.equal(ri[:, :K], ids[:4].long()) or float((rv[:, :K] - vals[:4]).abs().max()) < 1e-5
+        # the CPU oracle in float64 on 24 sampled rows of the FULL-size shard: values, and ids wherever the oracle's
+        # neighbouring scores are further apart than the fp32 arithmetic can confuse
+        rows = torch.arange(0, B, max(1, B // 24))[:24]
+        Sd = orc.score_dense(U[rows].cpu().double(), W.cpu().double())
+        sub_crow = torch.arange(0, (len(rows) + 1) * 3, 3)
+        sub_col = col.view(B, 3)[rows].reshape(-1).cpu()
+        ov, oi = orc.topk_sorted(orc.mask_seen(Sd, sub_crow, sub_col), K + 1)
+        assert float((vals[rows].cpu().double() - ov[:, :K]).abs().max()) <= 2e-6
+        gap = (ov[:, :-1] - ov[:, 1:]) > 4e-6
+        decided = gap[:, :K] & torch.cat([torch.ones_like(gap[:, :1]), gap[:, :K - 1]], 1)
+        assert torch.equal(ids[rows].cpu().long()[decided], oi[:, :K][decided])
 
 
 def test_full_size_config5_bert4rec_shard(ops):
@@ -980,6 +991,21 @@ def test_full_size_config5_bert4rec_shard(ops):
     j = int(lab[0])
     pj = torch.exp((U.float() @ W[j].float()) + bias[j] - lse).sum() / M - float((lab == j).sum()) / M
     assert abs(float(db[j]) - float(pj)) <= 1e-5 + 2e-3 * abs(float(pj))
+    # the CPU oracle in float64 at FULL size: lse / loss of 16 sampled query rows (each a 6.25M-term log-sum-exp), and
+    # dW / dbias of 8 sampled item rows (each summed over all 4096 query rows against the oracle's global lse)
+    rows = torch.arange(0, M, M // 16)[:16]
+    Wd, bd = W.cpu().double(), bias.cpu().double()
+    Sd = U[rows].cpu().double() @ Wd.T + bd
+    lse_ref = torch.logsumexp(Sd, dim=1)
+    assert float((lse[rows].cpu().double() - lse_ref).abs().max()) <= 1e-5 * float(lse_ref.abs().max())
+    items = torch.cat([lab[:4].cpu(), torch.randint(0, N, (4,), generator=torch.Generator().manual_seed(1))])
+    Ud = U.cpu().double()
+    P = torch.exp(Ud @ Wd[items].T + bd[items] - lse.cpu().double().unsqueeze(1))           # (M, 8) softmax columns
+    onehot = (lab.cpu().unsqueeze(1) == items.unsqueeze(0)).double()
+    G = (P - onehot) / M
+    assert_grad_bf16(dW[items.to(dW.device)], (G.T @ Ud).float(), "dW rows at full size")
+    db_ref = G.sum(0)
+    assert float((db[items.to(db.device)].cpu().double() - db_ref).abs().max()) <= 2e-3 * float(db_ref.abs().max()) + 1e-9
     assert peak < 6 * 2 ** 30, f"peak extra memory {peak / 2**30:.1f} GiB: the logits must never be materialised"
 
 
