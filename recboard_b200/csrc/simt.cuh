@@ -780,9 +780,12 @@ __device__ __forceinline__ float exact_logit(const float* __restrict__ u, const 
 //   2. the groups that reach T (about K, plus the dirty ones) are re-scored exactly in fp32, eight groups = 32 items
 //      per step as they come, seen items dropped (UniSRec/main.py:413), the K best by (score desc, id asc) kept.
 // Only a sub-list that ran over its own capacity flags the row for the fallback below.  One warp per row.
+#ifndef TFC_MIN_BLOCKS
+#define TFC_MIN_BLOCKS 4
+#endif
 constexpr int TFC_MAXSUB = 1024;   // sub-lists per row the flattened walk handles (prefix array in shared memory)
 template <typename TW, int E>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (E <= 4 ? TFC_MIN_BLOCKS : 1))
 topk_from_cands_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const float* __restrict__ bias, float scale,
                        int d, long long n_rows, int n_items, const uint2* __restrict__ cand,
                        const int* __restrict__ cand_cnt, int n_sub, int cap, const int* __restrict__ seen_crow,
