@@ -783,7 +783,9 @@ __device__ __forceinline__ float exact_logit(const float* __restrict__ u, const 
 #ifndef TFC_MIN_BLOCKS
 #define TFC_MIN_BLOCKS 4
 #endif
-constexpr int TFC_MAXSUB = 1024;   // sub-lists per row the flattened walk handles (prefix array in shared memory)
+constexpr int TFC_MAXSUB = 512;    // sub-lists per row the flattened walk handles (prefix array in shared memory)
+constexpr int TFC_KEEP = 512;      // candidates per row kept in shared memory between the two trips
+constexpr int TFC_SEEN = 64;       // seen ids per row kept in shared memory for the filter
 template <typename TW, int E>
 __global__ void __launch_bounds__(128, (E <= 4 ? TFC_MIN_BLOCKS : 1))
 topk_from_cands_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const float* __restrict__ bias, float scale,
@@ -796,6 +798,8 @@ topk_from_cands_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const
   __shared__ float fstage_s[4][32 * E];
   __shared__ unsigned int queue_s[4][64];
   __shared__ int pref_s[4][TFC_MAXSUB + 1];
+  __shared__ uint2 keep_s[4][TFC_KEEP];   // trip 1 parks the row's candidates here for trip 2 (when they fit)
+  __shared__ int seen_s[4][TFC_SEEN];     // the row's seen ids (when they fit): the filter's binary search stays on chip
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 4 + wib;
   if (row >= n_rows) return;
@@ -830,9 +834,17 @@ topk_from_cands_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const
     if (lane == 0) pref[n_sub] = total;
     __syncwarp();
   }
+  uint2* keep = keep_s[wib];
+  const bool parked = flat && total <= TFC_KEEP;   // trip 2 reads the candidates back from shared memory
+  bool from_keep = false;
   // body(ok, entry) is called warp-uniformly once per 32 candidates, in list order
   auto walk = [&](auto&& body) {
-    if (flat) {
+    if (from_keep) {
+      for (int e0 = 0; e0 < total; e0 += 32) {
+        const int f = e0 + lane;
+        body(f < total, (f < total) ? keep[f] : make_uint2(0u, 0u));
+      }
+    } else if (flat) {
       for (int e0 = 0; e0 < total; e0 += 32) {
         const int f = e0 + lane;
         uint2 x = make_uint2(0u, 0u);
@@ -843,6 +855,7 @@ topk_from_cands_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const
             if (pref[mid] <= f) lo = mid; else hi = mid;
           }
           x = __ldg(lists + static_cast<long long>(lo) * cap + (f - pref[lo]));
+          if (parked) keep[f] = x;
         }
         body(f < total, x);
       }
@@ -905,6 +918,12 @@ topk_from_cands_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const
   __syncwarp();
   int s_lo = 0, s_hi = 0;
   if (seen_crow != nullptr) { s_lo = seen_crow[row]; s_hi = seen_crow[row + 1]; }
+  int* seen_l = seen_s[wib];
+  const bool seen_local = (s_hi - s_lo) <= TFC_SEEN;
+  if (seen_local)
+    for (int k = lane; k < s_hi - s_lo; k += 32) seen_l[k] = __ldg(seen_col + s_lo + k);
+  from_keep = parked;
+  __syncwarp();
   unsigned long long best[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) best[e] = 0ull;
@@ -934,12 +953,21 @@ topk_from_cands_kernel(const TW* __restrict__ U, const TW* __restrict__ W, const
     if (item < n_items) key = topk_key(exact_logit<TW>(u, W + static_cast<long long>(item) * d, d, scale, bias, item), item);
     bool pass = key > kth;
     if (pass && s_hi > s_lo) {  // seen items never rank
-      int lo = s_lo, hi = s_hi;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(seen_col + mid) < item) lo = mid + 1; else hi = mid;
+      if (seen_local) {
+        int lo = 0, hi = s_hi - s_lo;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (seen_l[mid] < item) lo = mid + 1; else hi = mid;
+        }
+        if (lo < s_hi - s_lo && seen_l[lo] == item) pass = false;
+      } else {
+        int lo = s_lo, hi = s_hi;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (__ldg(seen_col + mid) < item) lo = mid + 1; else hi = mid;
+        }
+        if (lo < s_hi && __ldg(seen_col + lo) == item) pass = false;
       }
-      if (lo < s_hi && __ldg(seen_col + lo) == item) pass = false;
     }
     const uint32_t m = __ballot_sync(0xffffffffu, pass);
     if (pass) stage[ns + __popc(m & lt)] = key;
