@@ -210,6 +210,9 @@ int rb_topk_debug_layout(int64_t B, int64_t N, int d, int K, int mode, int64_t n
 /* Merge R sorted per-shard lists (vals,ids)[R][B][K] into the global top-K (rb_topk_eval order). */
 int rb_topk_merge(const float* vals, const int32_t* ids, int R, int64_t B, int K, float* out_vals,
                   int32_t* out_ids, rb_stream_t stream);
+/* the same merge over packed[R][2][B][K] (plane 0 = float32 values, plane 1 = int32 ids): the layout ONE all-gather of
+ * the per-rank (values, ids) leaves behind */
+int rb_topk_merge_packed(const int32_t* packed, int R, int64_t B, int K, float* out_vals, int32_t* out_ids, rb_stream_t stream);
 
 /* hits[b,k] = 1.0 if top_ids[b,k] (global item id, -1 = missing) is one of row b's targets, else 0.0.
  * Targets: CSR (target_crow[B+1], target_col[nnz]) of `Item.to_csr(data[IUnseen])`, ids sorted per row
@@ -217,6 +220,11 @@ int rb_topk_merge(const float* vals, const int32_t* ids, int R, int64_t B, int K
  * per metric@k, :428-435).  HR/NDCG/RECALL/PRECISION/MRR@k are prefix reductions of this (B,K) matrix. */
 int rb_topk_hits(const int32_t* top_ids, const int64_t* target_crow, const int64_t* target_col, int64_t B,
                  int K, float* hits, rb_stream_t stream);
+
+/* ---- 8e: merge of the per-rank (row_max, row_sumexp, label_logit) of a row-sharded table -- stats[R][3][M] as one
+ * all-gather delivers them -- into the global lse and label logit of every query row (the reference has no
+ * counterpart: its only multi-GPU mode is DDP).  Ranks are combined in order (deterministic). */
+int rb_rowstats_merge(const float* stats, int n_ranks, int64_t M, float* lse, float* label_logit, rb_stream_t stream);
 
 /* a10 in one pass: batch means of n_metrics METRIC@k values straight from the ranked ids -- what
  * `self.monitor(scores, targets, n=bsz, reduction="mean", pool=[...])` (UniSRec/main.py:428-435) returns per batch,

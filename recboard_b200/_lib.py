@@ -44,6 +44,8 @@ SIGNATURES = {
     "rb_topk_eval": (_i32, [_p, _p, _p, _f32, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _p, _p, _p, _sz, _p]),
     "rb_topk_debug_layout": (_i32, [_i64, _i64, _i32, _i32, _i32, _i64, _p]),
     "rb_topk_hits": (_i32, [_p, _p, _p, _i64, _i32, _p, _p]),
+    "rb_rowstats_merge": (_i32, [_p, _i32, _i64, _p, _p, _p]),
+    "rb_topk_merge_packed": (_i32, [_p, _i32, _i64, _i32, _p, _p, _p]),
     "rb_topk_metrics_blocks": (_i32, [_i64]),
     "rb_topk_metrics": (_i32, [_p, _p, _p, _i64, _i32, _p, _p, _p, _p, _i32, _p, _p, _p]),
     "rb_topk_merge": (_i32, [_p, _p, _i32, _i64, _i32, _p, _p, _p]),

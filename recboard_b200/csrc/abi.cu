@@ -1046,8 +1046,25 @@ extern "C" int rb_topk_merge(const float* vals, const int32_t* ids, int R, int64
   if (!vals || !ids || !out_vals || !out_ids) return fail(RB_E_ARG, "null pointer");
   if (R < 1 || B < 1 || K < 1 || K > 256) return fail(RB_E_ARG, "bad shape R=%d B=%lld K=%d", R, (long long)B, K);
   const int grid = static_cast<int>((B * 32 + 127) / 128);
-  if (K <= 128) topk_merge_kernel<4><<<grid, 128, 0, st>>>(vals, ids, R, B, K, out_vals, out_ids);
-  else topk_merge_kernel<8><<<grid, 128, 0, st>>>(vals, ids, R, B, K, out_vals, out_ids);
+  if (K <= 128) topk_merge_kernel<4><<<grid, 128, 0, st>>>(vals, ids, R, B, K, out_vals, out_ids, B * K);
+  else topk_merge_kernel<8><<<grid, 128, 0, st>>>(vals, ids, R, B, K, out_vals, out_ids, B * K);
+  RB_LAUNCH_CHECK("topk_merge_kernel");
+  return 0;
+}
+// The same merge reading the lists where ONE all-gather of the per-rank [vals bits | ids] pairs left them:
+// packed[R][2][B][K] (32-bit words; plane 0 = float32 values, plane 1 = int32 ids) -- no unpacking copies.
+extern "C" int rb_topk_merge_packed(const int32_t* packed, int R, int64_t B, int K, float* out_vals, int32_t* out_ids,
+                                    rb_stream_t stream) {
+  RB_RANGE("rb_topk_merge_packed");
+  DevInfo dv; if (int r = get_dev(dv)) return r;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!packed || !out_vals || !out_ids) return fail(RB_E_ARG, "null pointer");
+  if (R < 1 || B < 1 || K < 1 || K > 256) return fail(RB_E_ARG, "bad shape R=%d B=%lld K=%d", R, (long long)B, K);
+  const float* vals = reinterpret_cast<const float*>(packed);
+  const int32_t* ids = packed + B * K;
+  const int grid = static_cast<int>((B * 32 + 127) / 128);
+  if (K <= 128) topk_merge_kernel<4><<<grid, 128, 0, st>>>(vals, ids, R, B, K, out_vals, out_ids, 2 * B * K);
+  else topk_merge_kernel<8><<<grid, 128, 0, st>>>(vals, ids, R, B, K, out_vals, out_ids, 2 * B * K);
   RB_LAUNCH_CHECK("topk_merge_kernel");
   return 0;
 }
@@ -1063,6 +1080,19 @@ extern "C" int rb_topk_hits(const int32_t* top_ids, const int64_t* target_crow, 
   const long long n = B * K;
   topk_hits_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(top_ids, target_crow, target_col, B, K, hits);
   RB_LAUNCH_CHECK("topk_hits_kernel");
+  return 0;
+}
+
+// Merge of the per-rank row statistics of a row-sharded table (stats[R][3][M] from one all-gather) into the global
+// lse and label logit of every query row.
+extern "C" int rb_rowstats_merge(const float* stats, int n_ranks, int64_t M, float* lse, float* label_logit, rb_stream_t stream) {
+  RB_RANGE("rb_rowstats_merge");
+  DevInfo dv; if (int r = get_dev(dv)) return r;
+  if (!stats || !lse || !label_logit) return fail(RB_E_ARG, "null pointer");
+  if (n_ranks < 1 || M < 0) return fail(RB_E_ARG, "bad shape");
+  if (M == 0) return 0;
+  rowstats_merge_kernel<<<static_cast<int>((M + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(stats, n_ranks, M, lse, label_logit);
+  RB_LAUNCH_CHECK("rowstats_merge_kernel");
   return 0;
 }
 

@@ -572,6 +572,25 @@ __global__ void lse_merge_kernel(const float* __restrict__ pm2, const float* __r
   label_logit[i] = ll;
 }
 
+// Row-sharded table: the per-rank (row_max, row_sumexp, label_logit) triples, gathered as stats[R][3][M] (natural-log
+// units), merged into the global lse and label logit of every query row in one launch (rb_rowstats_merge):
+//   lse_i = mx + log(sum_r l_r exp(m_r - mx)),  ll_i = sum_r ll_r   (ranks in order => deterministic)
+__global__ void rowstats_merge_kernel(const float* __restrict__ stats, int n_ranks, long long m, float* __restrict__ lse,
+                                      float* __restrict__ label_logit) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  float mx = -INFINITY;
+  for (int r = 0; r < n_ranks; ++r) mx = fmaxf(mx, stats[(static_cast<long long>(r) * 3 + 0) * m + i]);
+  float l = 0.f, ll = 0.f;
+  for (int r = 0; r < n_ranks; ++r) {
+    const float mr = stats[(static_cast<long long>(r) * 3 + 0) * m + i];
+    l += stats[(static_cast<long long>(r) * 3 + 1) * m + i] * expf(mr - mx);
+    ll += stats[(static_cast<long long>(r) * 3 + 2) * m + i];
+  }
+  lse[i] = mx + logf(l);
+  label_logit[i] = ll;
+}
+
 // out[i] = sum_s part[s][i]   (fixed order => deterministic)
 __global__ void partial_sum_kernel(const float* __restrict__ part, int n_splits, long long n, float* __restrict__ out) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
@@ -1278,7 +1297,8 @@ __global__ void topk_metrics_finish_kernel(const double* __restrict__ partial, i
 // ---- merge of R sorted per-shard lists (rb_topk_merge): list l of row i at (l*n_rows + i)*K + e
 template <int E>
 __global__ void topk_merge_kernel(const float* __restrict__ vals, const int* __restrict__ ids, int n_lists,
-                                  long long n_rows, int K, float* __restrict__ out_vals, int* __restrict__ out_ids) {
+                                  long long n_rows, int K, float* __restrict__ out_vals, int* __restrict__ out_ids,
+                                  long long list_stride) {
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n_rows) return;
@@ -1286,7 +1306,7 @@ __global__ void topk_merge_kernel(const float* __restrict__ vals, const int* __r
 #pragma unroll
   for (int e = 0; e < E; ++e) best[e] = 0ull;
   for (int l = 0; l < n_lists; ++l) {
-    const long long ebase = (static_cast<long long>(l) * n_rows + row) * K;
+    const long long ebase = static_cast<long long>(l) * list_stride + row * K;   // list_stride = n_rows*K, or the pitch of a packed gather
     for (int base = 0; base < K; base += 32 * E) {
       unsigned long long cur[E];
 #pragma unroll

@@ -310,6 +310,17 @@ def _count_ptr(n_valid, dev):
     return L.ptr(n_valid.reshape(1))
 
 
+def rowstats_merge(stats: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """stats (R,3,M) = per-rank (max, sumexp, label_logit) of a row-sharded table -> (global lse (M,), label_logit (M,))
+    in one launch (rb_rowstats_merge)."""
+    dev = L.require_cuda(stats)
+    R, three, M = stats.shape
+    st = stats.float().contiguous()
+    out = torch.empty(2, M, dtype=torch.float32, device=dev)
+    L.call(dev, "rb_rowstats_merge", L.ptr(st), R, M, L.ptr(out[0]), L.ptr(out[1]), L.stream_ptr(dev))
+    return out[0], out[1]
+
+
 def ce_rowstats(U, W, labels, bias=None, scale: float = 1.0, label_base: int = 0,
                 precision: Optional[str] = None, want_dU: bool = False, n_valid: Optional[torch.Tensor] = None):
     """(row_max, row_sumexp, label_logit) of scale*U W^T + bias over this shard; (M,N) never exists.
@@ -589,6 +600,19 @@ def topk_eval(U: torch.Tensor, W: torch.Tensor, K: int, seen_crow: Optional[torc
                              id_base, B, N, d, L.dtype_code(Uc), mode, K, L.ptr(vals), L.ptr(ids), L.ptr(ws), n,
                              L.stream_ptr(dev))
     return vals, ids
+
+
+def topk_merge_packed(packed: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge of per-shard sorted lists in the layout one all-gather leaves them: packed (R,2,B,K) int32, plane 0 the
+    float32 values' bits, plane 1 the ids -> the global (B,K) list."""
+    dev = L.require_cuda(packed)
+    R, two, B, K = packed.shape
+    if packed.dtype != torch.int32 or two != 2 or not packed.is_contiguous():
+        raise TypeError("packed must be a contiguous int32 (R,2,B,K) tensor")
+    ov = torch.empty(B, K, dtype=torch.float32, device=dev)
+    oi = torch.empty(B, K, dtype=torch.int32, device=dev)
+    L.call(dev, "rb_topk_merge_packed", L.ptr(packed), R, B, K, L.ptr(ov), L.ptr(oi), L.stream_ptr(dev))
+    return ov, oi
 
 
 def topk_merge(vals: torch.Tensor, ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -38,7 +38,12 @@ def merge_rowstats(stats: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 def allgather_rowstats(m: torch.Tensor, l: torch.Tensor, ll: torch.Tensor, group=None) -> torch.Tensor:
-    local = torch.stack([m, l, ll]).contiguous()
+    base = getattr(m, "_base", None)
+    if (base is not None and base.dim() == 2 and base.shape[0] == 3 and base.is_contiguous() and m.data_ptr() == base.data_ptr()
+            and l.data_ptr() == base[1].data_ptr() and ll.data_ptr() == base[2].data_ptr()):
+        local = base       # ops.ce_rowstats hands out the three rows of one (3,M) buffer: no stack copy
+    else:
+        local = torch.stack([m, l, ll]).contiguous()
     world = dist.get_world_size(group)
     out = torch.empty(world * local.shape[0], *local.shape[1:], dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, local, group=group)  # concatenates along dim 0 (gloo and nccl)
@@ -67,7 +72,8 @@ class _ShardedCE(torch.autograd.Function):
                                            precision=precision, want_dU=True)
         else:
             m, l, ll = ops.ce_rowstats(U, W_shard, labels, bias_shard, scale, label_base=row_start, precision=precision)
-        lse, llg = merge_rowstats(allgather_rowstats(m, l, ll, group))
+        gathered = allgather_rowstats(m, l, ll, group)
+        lse, llg = ops.rowstats_merge(gathered) if gathered.is_cuda else merge_rowstats(gathered)   # one launch on the GPU
         empty = torch.empty(0, device=U.device)
         ctx.save_for_backward(U, W_full, labels, bias_shard if bias_shard is not None else empty, lse,
                               du if du is not None else empty, m if du is not None else empty)
@@ -128,6 +134,12 @@ def sharded_topk(U: torch.Tensor, W_shard: torch.Tensor, K: int, row_start: int,
     from . import ops
     vals, ids = ops.topk_eval(U, W_shard, K, seen_crow, seen_col, bias=bias_shard, scale=scale,
                               id_base=row_start, precision=precision)
+    if merge_fn is None and vals.is_cuda:   # one collective, merged where it lands: no packing / unpacking copies beyond the stack
+        packed = torch.stack([vals.contiguous().view(torch.int32), ids.contiguous()])
+        world = dist.get_world_size(group)
+        out = torch.empty(world, *packed.shape, dtype=torch.int32, device=packed.device)
+        dist.all_gather_into_tensor(out.view(world * 2, *vals.shape), packed, group=group)
+        return ops.topk_merge_packed(out)
     av, ai = allgather_topk(vals, ids, group)
     return (merge_fn or ops.topk_merge)(av, ai)
 

@@ -842,6 +842,13 @@ def test_sharded_partials_merge_like_multi_gpu(ops):
     gv, gi = ops.topk_eval(Ud, Wd, K)
     # every finishing path re-scores its winners with the same fp32 FMA chain: bit-identical values
     assert torch.equal(mi, gi) and torch.equal(mv, gv)
+    # the one-launch merges of the multi-GPU path: row statistics, and the top-K lists in the packed layout one
+    # all-gather leaves behind (R,2,B,K)
+    lse_k, ll_k = ops.rowstats_merge(torch.stack(stats))
+    assert torch.allclose(lse_k, lse, rtol=0, atol=2e-6) and torch.allclose(ll_k, ll, rtol=1e-6, atol=1e-6)
+    packed = torch.stack([torch.stack([t[0].view(torch.int32), t[1]]) for t in tops]).contiguous()
+    pv, pi = ops.topk_merge_packed(packed)
+    assert torch.equal(pi, mi) and torch.equal(pv, mv)
     # gradient shards: dW of shard == rows of the unsharded dW; partial dU sum == dU
     _, rdU, rdW, _ = orc.ce_fwd_bwd(U, W, lab)
     dU_sum = torch.zeros(M, d, device="cuda")
