@@ -222,6 +222,19 @@ def run_ours(args):
     tgt = synth.targets(ROWS, n_total, g, dev, (seen_crow, seen_col))
     tgt_crow = torch.arange(ROWS + 1, device=dev, dtype=torch.int64)
     monitors = ["HITRATE@1", "HITRATE@5", "HITRATE@10", "HITRATE@20", "HITRATE@50", "NDCG@5", "NDCG@10", "NDCG@20", "NDCG@50"]
+    # Random embeddings never rank a random held-out item among the top 50 of a million, so the reported metrics would
+    # all be 0: every fourth row's target becomes the item this very model ranks 1st / 8th / 30th (cycling) -- the metric
+    # values in the line then have a known answer (HITRATE@1 = 1/12, @10 = 2/12, @50 = 3/12 of the rows).
+    with torch.no_grad():
+        if world > 1:
+            _, ids0 = sharded.sharded_topk(U_eval, W, TOPK, row_start, seen_crow, seen_col)
+        else:
+            _, ids0 = ops.topk_eval(U_eval, W, TOPK, seen_crow, seen_col)
+    pick = torch.arange(0, ROWS, 4, device=dev)
+    rank_of = torch.tensor([0, 7, 29], device=dev)[(pick // 4) % 3]
+    tgt[pick] = ids0[pick, rank_of].long()
+    n_r = [int((rank_of == v).sum()) for v in (0, 7, 29)]
+    metrics_expected = {"HITRATE@1": n_r[0] / ROWS, "HITRATE@10": (n_r[0] + n_r[1]) / ROWS, "HITRATE@50": sum(n_r) / ROWS}
 
     def hot_path(U_tr, lab, sq, U_ev, s_crow, s_col):
         """One pass of the path through the public API (recboard_b200.ops / .sharded), gradients through autograd:
@@ -480,7 +493,7 @@ def run_ours(args):
                        "pre_warm": f"{n_pre} untimed steps (~2.3 s) before the {max(args.warmup, 3)} warm-up steps"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "loss": loss_host, "metrics": res, "cuda_mallocs_in_region": e2e_mallocs,
+                    "loss": loss_host, "metrics": res, "metrics_expected": metrics_expected, "cuda_mallocs_in_region": e2e_mallocs,
                     "how": "pinned host inputs copied in, loss + the 9 metric@k batch means (computed on the device from the ranked "
                            "ids) copied out and consumed every step; the copy of step i+1 overlaps step i"},
             "gpu_launches": launches,
