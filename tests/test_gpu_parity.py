@@ -192,7 +192,8 @@ def test_scores_and_rowstats(ops, M, N, d, precision):
 
 @pytest.mark.parametrize("M,N,d", [(1, 130, 64), (300, 1000, 64), (513, 4099, 128), (3013, 12101, 64),
                                    (17000, 700, 64),    # > 16384 rows: one-hot correction through the sorted scatter
-                                   (300, 1000, 256), (513, 4099, 192), (2100, 40_000, 256)])   # 128 < d <= 256: d-split passes
+                                   (300, 1000, 256), (513, 4099, 192), (2100, 40_000, 256),   # 128 < d <= 256: d-split passes
+                                   (5000, 1000, 256)])    # ... with the query range of the dW pass cut into several splits
 def test_ce_gradients_bf16(ops, M, N, d):
     g = torch.Generator().manual_seed(M + N + d)
     U = bf16_round(torch.randn(M, d, generator=g) * 1.5 / d ** 0.25)
