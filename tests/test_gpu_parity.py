@@ -821,6 +821,33 @@ def test_device_side_row_count_matches_compacted_rows(ops, precision, d):
     assert float(Wz.grad.float().abs().max()) == 0.0 and float(Xz.grad.float().abs().max()) == 0.0
 
 
+def test_gather_over_several_shards_one_device(ops):
+    """rb_gather_rows_peers with the shards of a table as separate allocations (here all on this GPU; across ranks they
+    are IPC-mapped peers, tests/multi_gpu_check.py): every id is served by the shard that owns it, ids outside the
+    table give zero rows; rb_ipc_export returns the allocation handle and the offset of an interior pointer."""
+    import ctypes as C
+    from recboard_b200 import _lib as L
+    g = torch.Generator().manual_seed(12)
+    N, d = 10_007, 64
+    W = bf16_round(torch.randn(N, d, generator=g))
+    bounds = [0, 3000, 3001, 7777, N]                       # ragged shards, one of a single row
+    shards = [dev(W[a:b]).bfloat16().contiguous() for a, b in zip(bounds[:-1], bounds[1:])]
+    idx = torch.randint(-3, N + 5, (500, 7), generator=g)   # incl. ids below and above the table
+    idx[0, :4] = torch.tensor([0, 2999, 3000, N - 1])
+    out = torch.empty(idx.numel(), d, dtype=torch.bfloat16, device="cuda")
+    ptrs = (C.c_void_p * len(shards))(*[s_.data_ptr() for s_ in shards])
+    starts = (C.c_int64 * len(bounds))(*bounds)
+    L.call(out.device, "rb_gather_rows_peers", ptrs, starts, len(shards), L.ptr(dev(idx).view(-1)), L.ptr(out), idx.numel(), d,
+           L.DTYPE_BF16, L.stream_ptr(out.device))
+    ok = (idx >= 0) & (idx < N)
+    ref = torch.where(ok.unsqueeze(-1), W[idx.clamp(0, N - 1)], torch.zeros(1, d)).view(-1, d)
+    assert torch.equal(out.float().cpu(), ref)
+    handle, off = C.create_string_buffer(64), C.c_int64(-1)
+    inner = shards[3][5:]                                   # a pointer inside an allocation
+    L.call(out.device, "rb_ipc_export", L.ptr(inner), C.cast(handle, C.c_void_p), C.cast(C.pointer(off), C.c_void_p))
+    assert off.value >= 5 * d * 2 and any(handle.raw)
+
+
 def test_sharded_partials_merge_like_multi_gpu(ops):
     """Single-GPU simulation of R row shards: sharded stats/top-K/dW == unsharded."""
     from recboard_b200 import sharded
